@@ -1,0 +1,174 @@
+/* tvae_b200.h - C ABI of libtvae_b200.so: the B200 (sm_100a) kernels behind the TARGET-VAE training hot path.
+ *
+ * The reference (SMLC-NYSBC/TARGET-VAE) has no FFI / plugin layer: its only stable boundary is the Python
+ * surface of src/models.py and the trainers' eval_minibatch.  These entry points are what the
+ * drop-in Python classes in target-vae_b200/src/models.py bind through ctypes; each comment names the reference
+ * code the call replaces (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 data unless noted; `stream` is a cudaStream_t
+ *   - calls never allocate, never synchronise, and are re-entrant; all scratch is passed in by the caller
+ *   - return 0 on success, < 0 on error; tvae_last_error() returns the thread-local message
+ *   - "tf32" tensors hold fp32 values already rounded to TF32 (10-bit mantissa)
+ *
+ * Internal activation layout (rows are (b, r, pos) with pos = i*W' + j, P = H'*W'):
+ *   x1, h  : [(b*G + r)*P + pos][O]
+ *   heads  : (B, NH, G, P) planar, NH = 3 + 2*z, channels = [attn, theta_mu, theta_logstd, z_mu.., z_logstd..]
+ *            == attn (B,G,H',W'), theta (B,2,G,H',W'), z (B,2z,G,H',W') of models.py:403 stacked on dim 1
+ */
+#ifndef TVAE_B200_H
+#define TVAE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* tvae_last_error(void);
+int tvae_version(void);
+
+/* ------------------------------------------------------------------ encoder (models.py:132-225, 326-403) */
+typedef struct {
+    int B, C, n, k, p, G, O, z;
+    int kpad;            /* row pitch of the filter bank: multiple of 32 and > C*k*k (tvae_bank_pitch) */
+} tvae_enc_shape;
+
+int tvae_bank_pitch(int C, int k);
+
+/* GroupConv.trans_filter (models.py:174-197): weight (O,C,1,k,k) -> bank [G*O][kpad] (row r*O + o), tf32. */
+int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* bank, void* stream);
+/* adjoint of the above plus conv1 bias gradient from the ones column: dbank [G*O][kpad] ->
+ * dweight (O,C,1,k,k), dbias (O).  Both outputs are overwritten. */
+int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dweight, float* dbias, void* stream);
+
+typedef struct {
+    const float* y;          /* (B,C,n,n) */
+    const float* bank;       /* [G*O][kpad] from tvae_filter_bank_fwd */
+    const float* conv1_bias; /* (O) */
+    const float* w2;         /* conv2.weight (O,O) */
+    const float* b2;         /* (O) */
+    const float* wh;         /* [NH][O]: conv_a, conv_r, conv_z weights stacked */
+    const float* bh;         /* [NH] */
+    const float* head_add;   /* [NH][G]: p_r on channel 0, rotation offsets on channel 1, else 0 */
+    float* x1;               /* out [B*G*P][O]  LeakyReLU(conv1)   (tf32) */
+    float* h;                /* out [B*G*P][O]  LeakyReLU(conv2) */
+    float* heads;            /* out (B,NH,G,P) */
+    float* w2_tf32;          /* scratch (O,O) */
+} tvae_enc_fwd_args;
+/* GroupConv.forward + InferenceNetwork_AttentionTranslation_AttentionRotation.forward up to the head maps
+ * (models.py:202-225, 355-358, 382, 390-399). */
+int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream);
+
+typedef struct {
+    const float* y;
+    const float* w2;
+    const float* wh;
+    float* x1;               /* in: saved activation; overwritten with d(conv1 pre-activation) */
+    const float* h;
+    const float* d_heads;    /* (B,NH,G,P) */
+    float* dhpre;            /* scratch [B*G*P][O] */
+    float* w2t_tf32;         /* scratch (O,O) */
+    float* dbank;            /* out [G*O][kpad] (feed to tvae_filter_bank_bwd) */
+    float* dw2;              /* out (O,O) */
+    float* db2;              /* out (O) */
+    float* dwh;              /* out [NH][O] */
+    float* dbh;              /* out [NH] */
+} tvae_enc_bwd_args;
+/* autograd of the above (convolution_backward x5, train_mnist.py:321). */
+int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------ attention inference + KL
+ * models.py:383-387 (log_softmax, gumbel_softmax) and train_mnist.py:187-282. */
+typedef struct {
+    int B, G, d, z;          /* d = H' = W' */
+    float s;                 /* pixel spacing x[1,0] - x[0,0] */
+    float theta_prior_std;   /* pi / G */
+    float offsets[16];       /* rotation offsets (0 when no refinement) */
+} tvae_attn_shape;
+
+/* log_prior[G*d*d] = log_softmax over (r,t) of [sum_xy N(0,0.1).log_prob(grid_t) + p_r[r]] (train_mnist.py:258-262) */
+int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float* log_prior, void* stream);
+
+typedef struct {
+    const float* heads; const float* gumbel; const float* r_z; const float* r_theta; const float* log_prior;
+    float* stats;            /* (B,4) max/lse of the two softmaxes */
+    float* zb;               /* (B,z) sampled z */
+    float* theta_b;          /* (B) sampled rotation */
+    float* dx;               /* (B,2) expected translation */
+    float* kl;               /* (B) per-image KL (val1 + val2) */
+} tvae_attn_fwd_args;
+int tvae_attn_fwd(const tvae_attn_shape* s, const tvae_attn_fwd_args* a, void* stream);
+
+typedef struct {
+    tvae_attn_fwd_args f;    /* the forward's inputs and outputs */
+    const float* g_zb; const float* g_theta; const float* g_dx;   /* dLoss/d(zb, theta_b, dx) */
+    const float* g_kl;       /* device scalar: dLoss/d(kl_b) (already divided by B) */
+    float* d_heads;          /* out (B,NH,G,P) */
+} tvae_attn_bwd_args;
+int tvae_attn_bwd(const tvae_attn_shape* s, const tvae_attn_bwd_args* a, void* stream);
+
+/* module-interface tail: q_t_r = log_softmax(attn), a_sampled = softmax(attn + gumbel) (models.py:383-388) */
+int tvae_attn_softmax_pair(const float* heads, const float* gumbel, float* q_t_r, float* a_sampled, int B, int NH, int L, void* stream);
+/* clustering_mnist.py:122-161: argmax (r,t), z/theta at the argmax, softmax-expected translation */
+int tvae_get_latent(const tvae_attn_shape* s, const float* heads, float* z_content, float* theta_mu, float* dx, int* argmax, void* stream);
+
+/* ------------------------------------------------------------------ generator (models.py:53-58, 95-123) */
+typedef struct {
+    int B, N;                /* images, pixels per image (M = B*N rows) */
+    int E;                   /* Fourier features (1024) or 0 when no expansion (coord_linear in_dim = 2) */
+    int H;                   /* hidden width */
+    int L;                   /* number of hidden Linear(H,H) layers = num_layers - 1 */
+    int n_out, zdim;
+} tvae_gen_shape;
+
+typedef struct {
+    const float* x;          /* (N,2) base coords, or (B*N,2) explicit coords when theta == NULL */
+    const float* theta;      /* (B) or NULL */
+    const float* dx;         /* (B,2) or NULL */
+    const float* z;          /* (B,zdim) */
+    const float* wf_scaled;  /* (E,2) embed_latent.weight / sigma */
+    const float* bf;         /* (E) */
+    const float* w1;         /* coord_linear.weight (H, E or 2) */
+    const float* b1;         /* (H) */
+    const float* wz;         /* latent_linear.weight (H,zdim) */
+    const float* wh;         /* [L][H][H] hidden weights */
+    const float* bh;         /* [L][H] */
+    const float* wout;       /* (n_out,H) */
+    const float* bout;       /* (n_out) */
+    float* zb;               /* out (B,H) latent_linear(z) */
+    float* acts;             /* out [L+1][B*N][H] post-activation of every hidden layer (tf32) */
+    float* y_hat;            /* out (B*N, n_out) */
+    float* w_tf32;           /* scratch: H*max(E,2) + L*H*H floats */
+} tvae_gen_fwd_args;
+int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void* stream);
+
+typedef struct {
+    tvae_gen_fwd_args f;
+    const float* d_yhat;     /* (B*N, n_out) */
+    float* dpre0; float* dpre1;   /* scratch [B*N][H] each */
+    float* wt_tf32;          /* scratch: max(E*H, H*H) floats (transposed weights) */
+    float* dxp;              /* scratch/out (B*N,2): gradient w.r.t. the transformed coordinates */
+    float* dzb;              /* scratch (B,H) */
+    float* dw1; float* db1; float* dwz; float* dwh; float* dbh; float* dwout; float* dbout;  /* out, same shapes as weights */
+    float* d_theta;          /* out (B)   (NULL when explicit coords: dxp is the coordinate gradient) */
+    float* d_dx;             /* out (B,2) */
+    float* d_z;              /* out (B,zdim) */
+} tvae_gen_bwd_args;
+int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------ likelihoods
+ * Bernoulli (train_mnist.py:288-291, train_galaxy.py:288-292): ll[b] = -sum_e BCEWithLogits; d_yhat = g*(sigmoid - y).
+ * g is a device scalar = dLoss/d(ll_b) * (-1) (i.e. 1/B for loss = -elbo). d_yhat may be NULL. */
+int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat, const float* g, int B, int E, void* stream);
+/* Gaussian with optional CTF and mask (train_particles.py:298-338): mu = ctf (*) y_hat (scratch (B,n,n)),
+ * ll[b] = -0.5 sum mask (mu - y)^2, d_yhat = adjoint-ctf(g * mask * (mu - y)).  ctf may be NULL, radius 0 = no mask. */
+int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
+                  float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream);
+
+/* ------------------------------------------------------------------ test hooks for the GEMM core */
+int tvae_test_linear_nt(const float* A, const float* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);
+int tvae_test_linear_tn(const float* P, const float* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,270 @@
+// Generator layer-1 GEMM policies (a-4 coordinate transform + a-5 random Fourier features + a-6 first
+// Linear; models.py:53-58,95-117 and train_mnist.py:222,234-239).
+//
+// The (B*n^2) x 1024 Fourier feature matrix is never written to HBM: generator warps evaluate
+//   x' = (x - dx_b) R(theta_b),  feat[m][f] = cos(x'_0 wx_f + x'_1 wy_f + b_f)      (wx, wy = W / sigma)
+// per tile directly into the swizzled A operand, forward and again in the weight-gradient GEMM; the
+// coordinate gradient GEMM applies -sin(.) and the projection onto (wx, wy) in its epilogue.
+//
+//   GenL1Fwd   : h1 = LeakyReLU(feat W1^T + b1 + zb[b])                 A generated (K-major), B = W1 (TMA)
+//   GenL1Wgrad : dW1[j][f] = sum_m dpre[m][j] feat[m][f]                A = feat^T generated (MN-major), B = dpre (TMA)
+//   GenL1Dgrad : dx'[m] = sum_f (-sin(phase) * (dpre W1)[m][f]) (wx_f, wy_f)   A = dpre (TMA), B = W1^T (TMA)
+#pragma once
+#include "linear_policies.cuh"
+
+namespace tvae {
+
+struct CoordXform {
+    const float* x;         // base coords (N,2), or explicit per-row coords (M,2) when theta == nullptr
+    const float* theta;     // (B) or nullptr
+    const float* dx;        // (B,2)
+    int N;                  // pixels per image
+    long long M;            // B*N rows
+};
+
+__device__ __forceinline__ void transformed_coord(const CoordXform& c, long long m, float& x0, float& x1) {
+    if (m >= c.M) { x0 = 0.f; x1 = 0.f; return; }
+    if (c.theta == nullptr) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(c.x) + m);
+        x0 = v.x; x1 = v.y;
+        return;
+    }
+    const int b = static_cast<int>(m / c.N);
+    const int px = static_cast<int>(m - (long long)b * c.N);
+    const float2 v = __ldg(reinterpret_cast<const float2*>(c.x) + px);
+    const float2 d = __ldg(reinterpret_cast<const float2*>(c.dx) + b);
+    float sn, cs;
+    sincosf(__ldg(c.theta + b), &sn, &cs);
+    const float t0 = v.x - d.x, t1 = v.y - d.y;
+    // x' = (x - dx) [[cos, sin], [-sin, cos]]   (train_mnist.py:234-239)
+    x0 = t0 * cs - t1 * sn;
+    x1 = t0 * sn + t1 * cs;
+}
+
+// feature table in shared memory: float4 {wx, wy, b, 0} per feature
+__device__ __forceinline__ void load_fourier_table(float4* tab, const float* wf_scaled, const float* bf, int E, int tid, int nthreads) {
+    for (int f = tid; f < E; f += nthreads)
+        tab[f] = make_float4(__ldg(wf_scaled + 2 * f), __ldg(wf_scaled + 2 * f + 1), __ldg(bf + f), 0.f);
+}
+
+__device__ __forceinline__ float fourier_phase(const float4& w, float x0, float x1) {
+    return fmaf(x1, w.y, fmaf(x0, w.x, w.z));
+}
+
+// ------------------------------------------------------------------------------------------------
+struct GenL1FwdParams {
+    CUtensorMap tmB;          // W1 [H][E]
+    int num_stages, num_tiles, tiles_n, k_chunks;
+    CoordXform cx;
+    const float* wf_scaled;   // (E,2) = embed_latent.weight / sigma
+    const float* bf;          // (E)
+    int E, H;
+    const float* bias;        // (H)
+    const float* zb;          // (B,H) latent_linear(z)
+    float* h1;                // [M][H]
+};
+
+template <int BN>
+struct GenL1Fwd : PolicyBase {
+    using Params = GenL1FwdParams;
+    static constexpr int kBN = BN;
+    static constexpr bool kAGen = true;
+    static constexpr int kProdWarps = 8;
+    struct GenState { float x0, x1; };
+    __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmB); }
+    __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
+        load_fourier_table(reinterpret_cast<float4*>(extra), p.wf_scaled, p.bf, p.E, tid, nthreads);
+    }
+    __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        ti.m0 = mt * kBM;
+        ti.n0 = nt * BN;
+        ti.kc_begin = 0;
+        ti.kc_end = p.k_chunks;
+    }
+    __device__ static constexpr uint32_t tx_bytes() { return BN * 128; }
+    __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t, uint32_t sb, uint32_t bar) {
+        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+    }
+    __device__ static void gen_tile_begin(const Params& p, const TileInfo& ti, GenState& s, uint8_t*, int ptid) {
+        transformed_coord(p.cx, (long long)ti.m0 + (ptid & (kBM - 1)), s.x0, s.x1);
+    }
+    __device__ static void gen_chunk(const Params& p, const TileInfo&, GenState& s, int kc, uint8_t* a_stage, uint8_t* extra, int ptid) {
+        const float4* tab = reinterpret_cast<const float4*>(extra);
+        const int row = ptid & (kBM - 1), half = ptid >> 7;
+        const int f0 = kc * kBK + half * 16;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float e[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = f0 + ch * 4 + q;
+                e[q] = f < p.E ? to_tf32(__cosf(fourier_phase(tab[f], s.x0, s.x1))) : 0.f;
+            }
+            *reinterpret_cast<float4*>(a_stage + sw128_offset(row, half * 4 + ch)) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
+        const long long m = (long long)ti.m0 + row;
+        const bool ok = m < p.cx.M;
+        const float* zb = (ok && p.zb) ? p.zb + (m / p.cx.N) * p.H : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr + c * 32, rr);
+            tmem_ld_wait();
+            const int n0 = ti.n0 + c * 32;
+            if (!ok || n0 >= p.H) continue;
+            float* dst = p.h1 + m * p.H + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                float4 t;
+                t.x = to_tf32(lrelu(__uint_as_float(rr[j]) + bb.x + bz.x));
+                t.y = to_tf32(lrelu(__uint_as_float(rr[j + 1]) + bb.y + bz.y));
+                t.z = to_tf32(lrelu(__uint_as_float(rr[j + 2]) + bb.z + bz.z));
+                t.w = to_tf32(lrelu(__uint_as_float(rr[j + 3]) + bb.w + bz.w));
+                *reinterpret_cast<float4*>(dst + j) = t;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct GenL1WgradParams {
+    CUtensorMap tmQ;          // dpre [M][H], MN-major boxes
+    int num_stages, num_tiles, tiles_m, tiles_n, splits, chunks_total, chunks_per_split;
+    CoordXform cx;
+    const float* wf_scaled; const float* bf;
+    int E, H;
+    float* dW1;               // [H][E], zero-filled by the caller
+};
+
+template <int BN>
+struct GenL1Wgrad : PolicyBase {
+    using Params = GenL1WgradParams;
+    static constexpr int kBN = BN;
+    static constexpr bool kAMajorMN = true;
+    static constexpr bool kBMajorMN = true;
+    static constexpr bool kAGen = true;
+    static constexpr int kProdWarps = 8;
+    __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmQ); }
+    __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
+        load_fourier_table(reinterpret_cast<float4*>(extra), p.wf_scaled, p.bf, p.E, tid, nthreads);
+    }
+    __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
+        const int per_split = p.tiles_m * p.tiles_n;
+        const int sp = tile / per_split;
+        const int rem = tile - sp * per_split;
+        const int mt = rem / p.tiles_n, nt = rem - mt * p.tiles_n;
+        ti.m0 = mt * kBM;   // feature f
+        ti.n0 = nt * BN;    // hidden j
+        ti.kc_begin = sp * p.chunks_per_split;
+        ti.kc_end = min(ti.kc_begin + p.chunks_per_split, p.chunks_total);
+    }
+    __device__ static constexpr uint32_t tx_bytes() { return BN * 128; }
+    __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t, uint32_t sb, uint32_t bar) {
+        tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
+    }
+    __device__ static void gen_chunk(const Params& p, const TileInfo& ti, GenState&, int kc, uint8_t* a_stage, uint8_t* extra, int ptid) {
+        const float4* tab = reinterpret_cast<const float4*>(extra);
+        const int rrow = ptid & 31, cb = (ptid >> 5) & 3, half = ptid >> 7;
+        float x0, x1;
+        const long long m = (long long)kc * kBK + rrow;
+        transformed_coord(p.cx, m, x0, x1);
+        const bool ok = m < p.cx.M;
+        const int f0 = ti.m0 + cb * 32 + half * 16;
+        uint8_t* blk = a_stage + cb * (kBK * 128);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float e[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = f0 + ch * 4 + q;
+                e[q] = (ok && f < p.E) ? to_tf32(__cosf(fourier_phase(tab[f], x0, x1))) : 0.f;
+            }
+            *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, half * 4 + ch)) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
+        const int f = ti.m0 + row;
+        const bool empty = ti.kc_begin >= ti.kc_end;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr + c * 32, rr);
+            tmem_ld_wait();
+            if (f >= p.E || empty) continue;
+            const int j0 = ti.n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j0 + j < p.H) atomicAdd(p.dW1 + (long long)(j0 + j) * p.E + f, __uint_as_float(rr[j]));
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct GenL1DgradParams {
+    CUtensorMap tmA, tmB;     // dpre [M][H]; W1^T [E][H]
+    int num_stages, num_tiles, tiles_n, k_chunks;
+    CoordXform cx;
+    const float* wf_scaled; const float* bf;
+    int E, H;
+    float* dxp;               // [M][2] gradient w.r.t. transformed coords, zero-filled by the caller
+};
+
+template <int BN>
+struct GenL1Dgrad : PolicyBase {
+    using Params = GenL1DgradParams;
+    static constexpr int kBN = BN;
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
+        load_fourier_table(reinterpret_cast<float4*>(extra), p.wf_scaled, p.bf, p.E, tid, nthreads);
+    }
+    __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        ti.m0 = mt * kBM;
+        ti.n0 = nt * BN;
+        ti.kc_begin = 0;
+        ti.kc_end = p.k_chunks;
+    }
+    __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
+    __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
+        tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
+        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+    }
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
+        const float4* tab = reinterpret_cast<const float4*>(extra);
+        const long long m = (long long)ti.m0 + row;
+        float x0, x1;
+        transformed_coord(p.cx, m, x0, x1);
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr + c * 32, rr);
+            tmem_ld_wait();
+            const int f0 = ti.n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int f = f0 + j;
+                if (f < p.E) {
+                    const float4 w = tab[f];
+                    const float dph = -__sinf(fourier_phase(w, x0, x1)) * __uint_as_float(rr[j]);
+                    g0 = fmaf(dph, w.x, g0);
+                    g1 = fmaf(dph, w.y, g1);
+                }
+            }
+        }
+        if (m < p.cx.M) {
+            atomicAdd(p.dxp + 2 * m, g0);
+            atomicAdd(p.dxp + 2 * m + 1, g1);
+        }
+    }
+};
+
+}  // namespace tvae

@@ -1,0 +1,81 @@
+// Host-side helpers: error reporting, TMA tensor-map encoding (driver entry point fetched at run time,
+// so the library does not link against libcuda), SM count.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace tvae {
+
+inline thread_local std::string g_last_error;
+
+inline int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define TVAE_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return ::tvae::fail(-2, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+#define TVAE_REQUIRE(cond, msg)                                                                        \
+    do {                                                                                               \
+        if (!(cond)) return ::tvae::fail(-1, std::string("invalid argument: ") + (msg));               \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [rows][cols] (leading dimension ld elements), box = {32 cols, box_rows},
+// 128-byte swizzle (16 B chunks for K-major operands; 32 B chunks when `mn_major`, the layout the tensor
+// core requires for MN-major tf32), out-of-bounds elements read as zero.
+inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                        bool mn_major = false) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15)) return fail(-1, "TMA operand must be 16-byte aligned with 16-byte row pitch");
+    if (box_rows == 0 || box_rows > 256) return fail(-1, "TMA box rows out of range");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace tvae

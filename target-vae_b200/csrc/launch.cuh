@@ -1,0 +1,97 @@
+// Host-side launch helpers for tc_gemm_kernel policies.
+#pragma once
+#include "host_utils.cuh"
+#include "linear_policies.cuh"
+
+namespace tvae {
+
+constexpr int kMaxSmemBytes = 227 * 1024;
+
+template <class P>
+inline int pick_stages(int extra_bytes) {
+    const int per_stage = kAStageBytes + P::kBN * 128;
+    const SmemLayout L0 = make_smem_layout<P>(0, extra_bytes);
+    int s = (kMaxSmemBytes - static_cast<int>(L0.total) - 1024) / per_stage;
+    if (s > kMaxStages) s = kMaxStages;
+    return s;
+}
+
+template <class P>
+inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t stream) {
+    prm.num_stages = pick_stages<P>(extra_bytes);
+    if (prm.num_stages < 2) return fail(-1, "tile does not fit shared memory with >= 2 stages");
+    if (prm.num_tiles <= 0) return 0;
+    const SmemLayout L = make_smem_layout<P>(prm.num_stages, extra_bytes);
+    static int configured = 0;  // per policy instantiation
+    if (configured < static_cast<int>(L.total)) {
+        TVAE_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+        configured = kMaxSmemBytes;
+    }
+    const int threads = (kCtrlWarps + kEpiWarps + P::kProdWarps) * 32;
+    const int grid = prm.num_tiles < sm_count() ? prm.num_tiles : sm_count();
+    tc_gemm_kernel<P><<<grid, threads, L.total, stream>>>(prm);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// C[M,N] = epi(A[M,K] B[N,K]^T); A, B row-major with leading dims lda, ldb (elements).
+struct LinearNTArgs {
+    const float* A; long long lda;
+    const float* B; long long ldb;
+    int M, N, K;
+    float* C = nullptr; long long ldc = 0;
+    const float* bias = nullptr;
+    const float* row_bias = nullptr; int rows_per_group = 1; long long ld_rb = 0;
+    const float* aux = nullptr; long long ld_aux = 0;
+    int act = 0, round_tf32 = 0;
+    const float* proj_w = nullptr; const float* proj_bias = nullptr; float* proj_out = nullptr; int n_proj = 0;
+};
+
+inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
+    TVAE_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_nt: empty problem");
+    TVAE_REQUIRE(a.N % 4 == 0, "linear_nt: N must be a multiple of 4");
+    TVAE_REQUIRE(a.n_proj <= 4, "linear_nt: at most 4 fused projection outputs");
+    LinearNTParams p{};
+    const bool wide = a.N > 128;
+    const int BN = wide ? 256 : 128;
+    int rc;
+    if ((rc = make_tmap_2d(&p.tmA, a.A, a.M, a.K, a.lda, kBM))) return rc;
+    if ((rc = make_tmap_2d(&p.tmB, a.B, a.N, a.K, a.ldb, BN))) return rc;
+    p.M = a.M; p.N = a.N;
+    p.k_chunks = cdiv(a.K, kBK);
+    p.tiles_n = cdiv(a.N, BN);
+    p.num_tiles = cdiv(a.M, kBM) * p.tiles_n;
+    p.C = a.C; p.ldc = a.ldc; p.bias = a.bias;
+    p.row_bias = a.row_bias; p.rows_per_group = a.rows_per_group; p.ld_rb = a.ld_rb;
+    p.aux = a.aux; p.ld_aux = a.ld_aux; p.act = a.act; p.round_tf32 = a.round_tf32;
+    p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
+    return wide ? launch_gemm<LinearNT<256>>(p, 0, stream) : launch_gemm<LinearNT<128>>(p, 0, stream);
+}
+
+// C[Ma,Nb] (+)= sum_r P[r,Ma] Q[r,Nb]; caller zero-fills C (accumulated with atomics across row splits).
+inline int linear_tn(const float* P, long long ldp, const float* Q, long long ldq, int R, int Ma, int Nb,
+                     float* C, long long ldc, int transpose_out, cudaStream_t stream) {
+    TVAE_REQUIRE(R > 0 && Ma > 0 && Nb > 0, "linear_tn: empty problem");
+    LinearTNParams p{};
+    const bool wide = Nb > 128;
+    const int BN = wide ? 256 : 128;
+    int rc;
+    if ((rc = make_tmap_2d(&p.tmP, P, R, Ma, ldp, kBK, true))) return rc;
+    if ((rc = make_tmap_2d(&p.tmQ, Q, R, Nb, ldq, kBK, true))) return rc;
+    p.Ma = Ma; p.Nb = Nb;
+    p.tiles_m = cdiv(Ma, kBM);
+    p.tiles_n = cdiv(Nb, BN);
+    p.chunks_total = cdiv(R, kBK);
+    const int out_tiles = p.tiles_m * p.tiles_n;
+    int splits = cdiv(2 * sm_count(), out_tiles);        // ~2 waves of work items
+    const int min_chunks = 16;                            // keep >= 512 reduction rows per split
+    if (splits > cdiv(p.chunks_total, min_chunks)) splits = cdiv(p.chunks_total, min_chunks);
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = cdiv(p.chunks_total, splits);
+    p.splits = cdiv(p.chunks_total, p.chunks_per_split);
+    p.num_tiles = out_tiles * p.splits;
+    p.C = C; p.ldc = ldc; p.transpose_out = transpose_out;
+    return wide ? launch_gemm<LinearTN<256>>(p, 0, stream) : launch_gemm<LinearTN<128>>(p, 0, stream);
+}
+
+}  // namespace tvae

@@ -1,0 +1,189 @@
+// GEMM policies whose operands are both loaded by TMA.
+//   LinearNT<BN>: C[M,N] = epi(A[M,K] * B[N,K]^T)      (forward linear layers, dgrads with pre-transposed weights)
+//   LinearTN<BN>: C[Ma,Nb] += sum_r P[r,Ma] * Q[r,Nb]  (weight gradients; split over r, fp32 atomics)
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace tvae {
+
+constexpr float kLreluSlope = 0.01f;
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kLreluSlope * x; }
+__device__ __forceinline__ float lrelu_grad_from_out(float a) { return a > 0.f ? 1.f : kLreluSlope; }
+
+struct LinearNTParams {
+    CUtensorMap tmA, tmB;
+    int num_stages, num_tiles, tiles_n, k_chunks;
+    int M, N;
+    float* C;                 // [M][ldc] or null
+    long long ldc;
+    const float* bias;        // [N] or null
+    const float* row_bias;    // [M / rows_per_group][ld_rb] or null   (z-conditioned bias)
+    int rows_per_group;
+    long long ld_rb;
+    const float* aux;         // [M][ld_aux] or null: multiply by lrelu'(aux)
+    long long ld_aux;
+    int act;                  // 1 = LeakyReLU(0.01)
+    int round_tf32;           // round stored values to tf32 (consumer is another tf32 MMA)
+    const float* proj_w;      // [n_proj][N] or null: fused  proj_out[m][o] += sum_n v[m][n] * proj_w[o][n]
+    const float* proj_bias;   // [n_proj]
+    float* proj_out;          // [M][n_proj], pre-zeroed
+    int n_proj;
+};
+
+template <int BN>
+struct LinearNT : PolicyBase {
+    using Params = LinearNTParams;
+    static constexpr int kBN = BN;
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        ti.m0 = mt * kBM;
+        ti.n0 = nt * BN;
+        ti.kc_begin = 0;
+        ti.kc_end = p.k_chunks;
+    }
+    __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
+    __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
+        tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
+        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+    }
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
+        const int m = ti.m0 + row;
+        const bool m_ok = m < p.M;
+        float proj[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* rb = (p.row_bias && m_ok) ? p.row_bias + (long long)(m / p.rows_per_group) * p.ld_rb : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            const int n_base = ti.n0 + c * 32;
+            if (!m_ok || n_base >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n_base + j < p.N) v[j] += __ldg(p.bias + n_base + j);
+            }
+            if (rb) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n_base + j < p.N) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(rb + n_base + j));
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    }
+                }
+            }
+            if (p.act) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j]);
+            }
+            if (p.aux) {
+                const float* ax = p.aux + (long long)m * p.ld_aux + n_base;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n_base + j < p.N) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(ax + j));
+                        v[j] *= lrelu_grad_from_out(t.x);
+                        v[j + 1] *= lrelu_grad_from_out(t.y);
+                        v[j + 2] *= lrelu_grad_from_out(t.z);
+                        v[j + 3] *= lrelu_grad_from_out(t.w);
+                    }
+                }
+            }
+            if (p.proj_w) {
+                for (int o = 0; o < p.n_proj; ++o) {
+                    const float* w = p.proj_w + (long long)o * p.N + n_base;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n_base + j < p.N) acc = fmaf(v[j], __ldg(w + j), acc);
+                    proj[o] += acc;
+                }
+            }
+            if (p.C) {
+                float* dst = p.C + (long long)m * p.ldc + n_base;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n_base + j < p.N) {
+                        float4 t;
+                        if (p.round_tf32) t = make_float4(to_tf32(v[j]), to_tf32(v[j + 1]), to_tf32(v[j + 2]), to_tf32(v[j + 3]));
+                        else              t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        *reinterpret_cast<float4*>(dst + j) = t;
+                    }
+                }
+            }
+        }
+        if (p.proj_w && m_ok) {
+            for (int o = 0; o < p.n_proj; ++o) {
+                float add = proj[o];
+                if (ti.n0 == 0 && p.proj_bias) add += __ldg(p.proj_bias + o);
+                atomicAdd(p.proj_out + (long long)m * p.n_proj + o, add);
+            }
+        }
+    }
+};
+
+struct LinearTNParams {
+    CUtensorMap tmP, tmQ;     // P [R][Ma], Q [R][Nb]  (row-major, reduction over R)
+    int num_stages, num_tiles, tiles_m, tiles_n, splits, chunks_total, chunks_per_split;
+    int Ma, Nb;
+    float* C;                 // accumulated with atomics; caller zero-fills
+    long long ldc;
+    int transpose_out;        // 0: C[ma][nb], 1: C[nb][ma]
+};
+
+template <int BN>
+struct LinearTN : PolicyBase {
+    using Params = LinearTNParams;
+    static constexpr int kBN = BN;
+    static constexpr bool kAMajorMN = true;
+    static constexpr bool kBMajorMN = true;
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmP);
+        tma_prefetch_desc(&p.tmQ);
+    }
+    __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
+        const int per_split = p.tiles_m * p.tiles_n;
+        const int sp = tile / per_split;
+        const int rem = tile - sp * per_split;
+        const int mt = rem / p.tiles_n, nt = rem - mt * p.tiles_n;
+        ti.m0 = mt * kBM;
+        ti.n0 = nt * BN;
+        ti.kc_begin = sp * p.chunks_per_split;
+        ti.kc_end = min(ti.kc_begin + p.chunks_per_split, p.chunks_total);
+    }
+    __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
+    __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
+        tma_mnmajor(sa, &p.tmP, bar, ti.m0, kc * kBK, kBM / 32);
+        tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
+    }
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
+        const int ma = ti.m0 + row;
+        const bool empty = ti.kc_begin >= ti.kc_end;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if (ma >= p.Ma || empty) continue;
+            const int nb0 = ti.n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int nb = nb0 + j;
+                if (nb < p.Nb) {
+                    float* dst = p.transpose_out ? p.C + (long long)nb * p.ldc + ma : p.C + (long long)ma * p.ldc + nb;
+                    atomicAdd(dst, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+};
+
+}  // namespace tvae

@@ -1,0 +1,632 @@
+// CUDA-core (HBM-bound) kernels of the hot path: rotated filter bank fwd/bwd, attention inference
+// (softmax / Gumbel-softmax / expectations / KL) fwd/bwd, likelihoods, thin-layer backward, small helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace tvae {
+
+constexpr int kMaxG = 16;
+constexpr int kMaxHeads = 3 + 2 * 16;  // attn, theta_mu, theta_logstd, 2*z  (z <= 16)
+constexpr float kEpsStd = 1e-6f;       // train_mnist.py:197
+constexpr float kSlope = 0.01f;
+
+struct RotTable {
+    float cs[kMaxG];
+    float sn[kMaxG];
+};
+
+// ------------------------------------------------------------------------------------------
+// a-1  rotated filter bank (models.py:174-197), closed form of affine_grid + grid_sample
+//      (bilinear, zeros padding, align_corners=False).
+//   weight (O,C,k,k)  ->  bank [G*O][kpad], row n' = r*O + o, column kk = (c*k + v)*k + u,
+//   values rounded to tf32; columns kk >= C*k*k are zero.
+// ------------------------------------------------------------------------------------------
+struct BilinearTap {
+    int x0, y0;
+    float wx0, wx1, wy0, wy1;
+};
+__device__ __forceinline__ BilinearTap rot_tap(int u, int v, int k, float cs, float sn) {
+    const float c0 = 0.5f * (k - 1);
+    const float cx = u - c0, cy = v - c0;
+    const float ix = cs * cx + sn * cy + c0;
+    const float iy = -sn * cx + cs * cy + c0;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    BilinearTap t;
+    t.x0 = static_cast<int>(fx0);
+    t.y0 = static_cast<int>(fy0);
+    t.wx1 = ix - fx0; t.wx0 = 1.f - t.wx1;
+    t.wy1 = iy - fy0; t.wy0 = 1.f - t.wy1;
+    return t;
+}
+
+__global__ void filter_bank_fwd_kernel(const float* __restrict__ w, float* __restrict__ bank, int O, int C, int k, int G,
+                                       int kpad, RotTable rot) {
+    const int K = C * k * k;
+    const long long total = (long long)G * O * kpad;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int kk = static_cast<int>(idx % kpad);
+        const int np = static_cast<int>(idx / kpad);
+        float val = 0.f;
+        if (kk < K) {
+            const int r = np / O, o = np - r * O;
+            const int u = kk % k, v = (kk / k) % k, c = kk / (k * k);
+            const BilinearTap t = rot_tap(u, v, k, rot.cs[r], rot.sn[r]);
+            const float* wp = w + ((long long)o * C + c) * k * k;
+            const bool x0ok = t.x0 >= 0 && t.x0 < k, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < k;
+            const bool y0ok = t.y0 >= 0 && t.y0 < k, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < k;
+            if (y0ok && x0ok) val += wp[t.y0 * k + t.x0] * (t.wy0 * t.wx0);
+            if (y0ok && x1ok) val += wp[t.y0 * k + t.x0 + 1] * (t.wy0 * t.wx1);
+            if (y1ok && x0ok) val += wp[(t.y0 + 1) * k + t.x0] * (t.wy1 * t.wx0);
+            if (y1ok && x1ok) val += wp[(t.y0 + 1) * k + t.x0 + 1] * (t.wy1 * t.wx1);
+            val = to_tf32(val);
+        }
+        bank[idx] = val;
+    }
+}
+
+// adjoint: dweight (O,C,k,k) += bilinear-scatter of dbank [G*O][ld] (first C*k*k columns).
+__global__ void filter_bank_bwd_kernel(const float* __restrict__ dbank, long long ld, float* __restrict__ dw, int O, int C,
+                                       int k, int G, RotTable rot) {
+    const int K = C * k * k;
+    const long long total = (long long)G * O * K;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int kk = static_cast<int>(idx % K);
+        const int np = static_cast<int>(idx / K);
+        const int r = np / O, o = np - r * O;
+        const int u = kk % k, v = (kk / k) % k, c = kk / (k * k);
+        const float g = dbank[(long long)np * ld + kk];
+        const BilinearTap t = rot_tap(u, v, k, rot.cs[r], rot.sn[r]);
+        float* wp = dw + ((long long)o * C + c) * k * k;
+        const bool x0ok = t.x0 >= 0 && t.x0 < k, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < k;
+        const bool y0ok = t.y0 >= 0 && t.y0 < k, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < k;
+        if (y0ok && x0ok) atomicAdd(wp + t.y0 * k + t.x0, g * (t.wy0 * t.wx0));
+        if (y0ok && x1ok) atomicAdd(wp + t.y0 * k + t.x0 + 1, g * (t.wy0 * t.wx1));
+        if (y1ok && x0ok) atomicAdd(wp + (t.y0 + 1) * k + t.x0, g * (t.wy1 * t.wx0));
+        if (y1ok && x1ok) atomicAdd(wp + (t.y0 + 1) * k + t.x0 + 1, g * (t.wy1 * t.wx1));
+    }
+}
+
+// out[c][r] = round_tf32(in[r][c]) : small weight transposes for dgrad GEMMs
+__global__ void transpose_round_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int do_round) {
+    const long long total = (long long)rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = static_cast<int>(idx % cols);
+        const int r = static_cast<int>(idx / cols);
+        const float v = in[idx];
+        out[(long long)c * rows + r] = do_round ? to_tf32(v) : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide reductions (blockDim.x multiple of 32, <= 1024)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// reduces NV values per thread; result valid in all threads. scratch: NV * 32 floats.
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_reduce(float (&v)[NV], float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = IS_MAX ? warp_max(v[i]) : warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float x = lane < nw ? scratch[i * 32 + lane] : (IS_MAX ? -CUDART_INF_F : 0.f);
+        v[i] = IS_MAX ? warp_max(x) : warp_sum(x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a-3 tail + a-4: attention inference over the head maps of one image.
+//   heads (B, NH, G, P) planar, channel order [attn(+p_r), theta_mu(+offset), theta_logstd,
+//   z_mu[0..z), z_logstd[0..z)], P = H'*W'.  One CTA per image, two passes (second hits L2).
+//   Outputs per image (fp32): stats[b] = {max_q, lse_q, max_a, lse_a}, zb (z), theta_b, dx (2), kl_b.
+// ------------------------------------------------------------------------------------------
+struct AttnParams {
+    const float* heads;     // (B, NH, G, P)
+    const float* gumbel;    // (B, G*P)
+    const float* r_z;       // (B, z)
+    const float* r_theta;   // (B)
+    const float* log_prior; // (G*P) : log_softmax over (r,t) of p_t + p_r  (train_mnist.py:258-262)
+    float* stats;           // (B, 4)
+    float* zb;              // (B, z)
+    float* theta_b;         // (B)
+    float* dx;              // (B, 2)
+    float* kl;              // (B)
+    int B, G, d, z;         // d = H' = W'
+    float s;                // pixel spacing x[1,0]-x[0,0]
+    float theta_prior_std;  // pi / G (train_mnist.py:269-272)
+    float offsets[kMaxG];
+};
+
+__device__ __forceinline__ void grid_xy(int t, int d, float s, float& gx, float& gy) {
+    // train_mnist.py:209-217: cell (i,j) -> ((j - d/2) s, (d-1-i - d/2) s)
+    const int i = t / d, j = t - i * d;
+    gx = (j - d / 2) * s;
+    gy = (d - 1 - i - d / 2) * s;
+}
+
+template <int Z>
+__global__ void __launch_bounds__(1024) attn_fwd_kernel(AttnParams p) {
+    __shared__ float scratch[32 * (6 + 4 * Z)];
+    const int b = blockIdx.x;
+    const int P = p.d * p.d, L = p.G * P, NH = 3 + 2 * Z;
+    const float* hb = p.heads + (long long)b * NH * L;
+    const float* gb = p.gumbel + (long long)b * L;
+
+    // pass 1: maxima
+    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const float a = hb[l];
+        mx[0] = fmaxf(mx[0], a);
+        mx[1] = fmaxf(mx[1], a + gb[l]);
+    }
+    block_reduce<2, true>(mx, scratch);
+    float se[2] = {0.f, 0.f};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const float a = hb[l];
+        se[0] += __expf(a - mx[0]);
+        se[1] += __expf(a + gb[l] - mx[1]);
+    }
+    block_reduce<2, false>(se, scratch);
+    const float lse_q = mx[0] + logf(se[0]);
+    const float lse_a = mx[1] + logf(se[1]);
+
+    // pass 2: expectations under a (Gumbel-softmax sample) and KL sums under pi = exp(q)
+    float acc[6 + 4 * Z];
+#pragma unroll
+    for (int i = 0; i < 6 + 4 * Z; ++i) acc[i] = 0.f;
+    const float inv2s2 = 1.f / (2.f * p.theta_prior_std * p.theta_prior_std);
+    const float log_sp = logf(p.theta_prior_std);
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const int r = l / P, t = l - r * P;
+        const float logit = hb[l];
+        const float q = logit - lse_q;
+        const float pi = expf(q);
+        const float a = expf(logit + gb[l] - lse_a);
+        float gx, gy;
+        grid_xy(t, p.d, p.s, gx, gy);
+        acc[0] += a * gx;
+        acc[1] += a * gy;
+        const bool dead = (pi == 0.f);  // train_mnist.py:246-254 guards
+        const float th_mu = hb[L + l], th_std = expf(hb[2 * L + l]) + kEpsStd;
+        acc[2] += a * th_mu;
+        acc[3] += a * th_std;
+        float f = q - p.log_prior[l];
+        if (!dead) {
+            const float dm = th_mu - p.offsets[r];
+            f += log_sp - logf(th_std) + (th_std * th_std + dm * dm) * inv2s2 - 0.5f;
+        }
+#pragma unroll
+        for (int k = 0; k < Z; ++k) {
+            const float zm = hb[(3 + k) * L + l], zs = expf(hb[(3 + Z + k) * L + l]) + kEpsStd;
+            acc[6 + k] += a * zm;
+            acc[6 + Z + k] += a * zs;
+            if (!dead) f += -logf(zs) + 0.5f * (zs * zs + zm * zm) - 0.5f;
+        }
+        acc[4] += pi * f;
+    }
+    block_reduce<6 + 4 * Z, false>(acc, scratch);
+    if (threadIdx.x == 0) {
+        p.stats[b * 4 + 0] = mx[0];
+        p.stats[b * 4 + 1] = lse_q;
+        p.stats[b * 4 + 2] = mx[1];
+        p.stats[b * 4 + 3] = lse_a;
+        p.dx[b * 2 + 0] = acc[0];
+        p.dx[b * 2 + 1] = acc[1];
+        p.theta_b[b] = acc[3] * p.r_theta[b] + acc[2];
+        p.kl[b] = acc[4];
+        for (int k = 0; k < Z; ++k) p.zb[b * Z + k] = acc[6 + Z + k] * p.r_z[b * Z + k] + acc[6 + k];
+    }
+}
+
+struct AttnBwdParams {
+    const float* heads; const float* gumbel; const float* r_z; const float* r_theta; const float* log_prior;
+    const float* stats; const float* zb; const float* theta_b; const float* dx; const float* kl;
+    const float* g_zb;     // (B, z)   dLoss/dz_b
+    const float* g_theta;  // (B)
+    const float* g_dx;     // (B, 2)
+    const float* g_kl;     // device scalar dLoss/dkl_b (same for every image)
+    float* d_heads;        // (B, NH, G, P)
+    int B, G, d, z;
+    float s, theta_prior_std;
+    float offsets[kMaxG];
+};
+
+// elementwise over (b, l): one read of the maps, one write of their gradients.
+template <int Z>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdParams p) {
+    const int P = p.d * p.d, L = p.G * P, NH = 3 + 2 * Z;
+    const int b = blockIdx.y;
+    const float* hb = p.heads + (long long)b * NH * L;
+    const float* gb = p.gumbel + (long long)b * L;
+    float* db = p.d_heads + (long long)b * NH * L;
+    const float lse_q = p.stats[b * 4 + 1], lse_a = p.stats[b * 4 + 3];
+    const float K = p.kl[b];
+    const float g_kl = __ldg(p.g_kl);
+    const float g_th = p.g_theta[b], r_th = p.r_theta[b];
+    const float gdx = p.g_dx[b * 2], gdy = p.g_dx[b * 2 + 1];
+    float gz[Z], rz[Z];
+    float s_ac = g_th * p.theta_b[b] + gdx * p.dx[b * 2] + gdy * p.dx[b * 2 + 1];
+#pragma unroll
+    for (int k = 0; k < Z; ++k) {
+        gz[k] = p.g_zb[b * Z + k];
+        rz[k] = p.r_z[b * Z + k];
+        s_ac += gz[k] * p.zb[b * Z + k];
+    }
+    const float inv_s2 = 1.f / (p.theta_prior_std * p.theta_prior_std);
+    const float log_sp = logf(p.theta_prior_std);
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+        const int r = l / P, t = l - r * P;
+        const float logit = hb[l];
+        const float q = logit - lse_q;
+        const float pi = expf(q);
+        const float a = expf(logit + gb[l] - lse_a);
+        const bool dead = (pi == 0.f);
+        float gx, gy;
+        grid_xy(t, p.d, p.s, gx, gy);
+        const float th_mu = hb[L + l], e_th = expf(hb[2 * L + l]), th_std = e_th + kEpsStd;
+        float c = g_th * (th_std * r_th + th_mu) + gdx * gx + gdy * gy;
+        float f = q - p.log_prior[l];
+        float d_thmu = g_th * a, d_thls = g_th * r_th * a * e_th;
+        if (!dead) {
+            const float dm = th_mu - p.offsets[r];
+            f += log_sp - logf(th_std) + 0.5f * (th_std * th_std + dm * dm) * inv_s2 - 0.5f;
+            d_thmu += g_kl * pi * dm * inv_s2;
+            d_thls += g_kl * pi * (-1.f / th_std + th_std * inv_s2) * e_th;
+        }
+#pragma unroll
+        for (int k = 0; k < Z; ++k) {
+            const float zm = hb[(3 + k) * L + l], e_z = expf(hb[(3 + Z + k) * L + l]), zs = e_z + kEpsStd;
+            c += gz[k] * (zs * rz[k] + zm);
+            float d_zm = gz[k] * a, d_zl = gz[k] * rz[k] * a * e_z;
+            if (!dead) {
+                f += -logf(zs) + 0.5f * (zs * zs + zm * zm) - 0.5f;
+                d_zm += g_kl * pi * zm;
+                d_zl += g_kl * pi * (-1.f / zs + zs) * e_z;
+            }
+            db[(3 + k) * L + l] = d_zm;
+            db[(3 + Z + k) * L + l] = d_zl;
+        }
+        db[L + l] = d_thmu;
+        db[2 * L + l] = d_thls;
+        db[l] = a * (c - s_ac) + g_kl * pi * (f - K);
+    }
+}
+
+// log_prior[l] = log_softmax_{(r,t)}( sum_xy N(grid; 0, 0.1).log_prob + p_r[r] )   (one small CTA)
+__global__ void log_prior_kernel(float* __restrict__ out, int G, int d, float s, RotTable p_r_in_cs) {
+    __shared__ float scratch[32];
+    const int P = d * d, L = G * P;
+    const float sig = 0.1f;
+    const float c0 = -logf(sig) - 0.5f * logf(2.f * CUDART_PI_F);
+    float mx[1] = {-CUDART_INF_F};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const int r = l / P, t = l - r * P;
+        float gx, gy;
+        grid_xy(t, d, s, gx, gy);
+        const float v = (-(gx * gx) / (2.f * sig * sig) + c0) + (-(gy * gy) / (2.f * sig * sig) + c0) + p_r_in_cs.cs[r];
+        out[l] = v;
+        mx[0] = fmaxf(mx[0], v);
+    }
+    block_reduce<1, true>(mx, scratch);
+    float se[1] = {0.f};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) se[0] += expf(out[l] - mx[0]);
+    block_reduce<1, false>(se, scratch);
+    const float lse = mx[0] + logf(se[0]);
+    for (int l = threadIdx.x; l < L; l += blockDim.x) out[l] -= lse;
+}
+
+// ------------------------------------------------------------------------------------------
+// module-interface tail (models.py:382-388): q_t_r = log_softmax(attn), a_sampled = softmax(attn + g)
+// from the stats of attn_fwd-style reductions.  One CTA per image.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) softmax_pair_kernel(const float* __restrict__ heads, const float* __restrict__ gumbel,
+                                                            float* __restrict__ q_out, float* __restrict__ a_out, int NH, int L) {
+    __shared__ float scratch[64];
+    const int b = blockIdx.x;
+    const float* hb = heads + (long long)b * NH * L;
+    const float* gb = gumbel + (long long)b * L;
+    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        mx[0] = fmaxf(mx[0], hb[l]);
+        mx[1] = fmaxf(mx[1], hb[l] + gb[l]);
+    }
+    block_reduce<2, true>(mx, scratch);
+    float se[2] = {0.f, 0.f};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        se[0] += __expf(hb[l] - mx[0]);
+        se[1] += __expf(hb[l] + gb[l] - mx[1]);
+    }
+    block_reduce<2, false>(se, scratch);
+    const float lse_q = mx[0] + logf(se[0]), lse_a = mx[1] + logf(se[1]);
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        q_out[(long long)b * L + l] = hb[l] - lse_q;
+        a_out[(long long)b * L + l] = expf(hb[l] + gb[l] - lse_a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a-10 get_latent (clustering_mnist.py:122-161): argmax over (r,t) of attn, z / theta at the argmax,
+// softmax-expected translation.  One CTA per image.
+// ------------------------------------------------------------------------------------------
+template <int Z>
+__global__ void __launch_bounds__(1024) get_latent_kernel(const float* __restrict__ heads, int G, int d, float s,
+                                                          float* __restrict__ z_content, float* __restrict__ theta_mu,
+                                                          float* __restrict__ dx, int* __restrict__ argmax_out) {
+    __shared__ float scratch[64];
+    __shared__ int sidx[32];
+    const int b = blockIdx.x;
+    const int P = d * d, L = G * P, NH = 3 + 2 * Z;
+    const float* hb = heads + (long long)b * NH * L;
+    float best = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const float v = hb[l];
+        if (v > best) { best = v; bi = l; }  // ascending l per thread: first maximum wins
+    }
+    // first-index argmax across the block (torch.max returns the first maximal index)
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { scratch[warp] = best; sidx[warp] = bi; }
+    __syncthreads();
+    best = lane < nw ? scratch[lane] : -CUDART_INF_F;
+    bi = lane < nw ? sidx[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    float se[1] = {0.f};
+    for (int l = threadIdx.x; l < L; l += blockDim.x) se[0] += __expf(hb[l] - best);
+    block_reduce<1, false>(se, scratch);
+    float acc[2] = {0.f, 0.f};
+    const float inv = 1.f / se[0];
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const int t = l % P;
+        float gx, gy;
+        grid_xy(t, d, s, gx, gy);
+        const float pi = __expf(hb[l] - best) * inv;
+        acc[0] += pi * gx;
+        acc[1] += pi * gy;
+    }
+    block_reduce<2, false>(acc, scratch);
+    if (threadIdx.x == 0) {
+        argmax_out[b] = bi;
+        dx[b * 2] = acc[0];
+        dx[b * 2 + 1] = acc[1];
+        theta_mu[b] = hb[L + bi];
+        for (int k = 0; k < Z; ++k) {
+            z_content[b * 2 * Z + k] = hb[(3 + k) * L + bi];
+            z_content[b * 2 * Z + Z + k] = expf(hb[(3 + Z + k) * L + bi]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a-7 Bernoulli likelihood (train_mnist.py:288-291) fwd + dLoss/dy_hat in one pass.
+//   ll[b] = -sum_e (softplus(yh) - y*yh);  d_yhat = g * (y - sigmoid(yh)), g = dLoss/d(ll_b) (device scalar)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bernoulli_kernel(const float* __restrict__ yhat, const float* __restrict__ y,
+                                                        float* __restrict__ ll, float* __restrict__ d_yhat, int E, const float* __restrict__ g_ptr) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.y;
+    const float g = d_yhat ? __ldg(g_ptr) : 0.f;
+    const float* yh = yhat + (long long)b * E;
+    const float* yy = y + (long long)b * E;
+    float acc[1] = {0.f};
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const float x = yh[e], t = yy[e];
+        // BCE-with-logits: max(x,0) - x*t + log1p(exp(-|x|))
+        acc[0] += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+        if (d_yhat) d_yhat[(long long)b * E + e] = g * (t - 1.f / (1.f + expf(-x)));
+    }
+    block_reduce<1, false>(acc, scratch);
+    if (threadIdx.x == 0) atomicAdd(ll + b, -acc[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// a-8 CTF point-spread correlation (train_particles.py:298-302): per-image (n-1)x(n-1) kernel,
+// zero padding (n-1)/2, cross-correlation.  out[b,i,j] = sum_{v,u} in[b, i+v-pad, j+u-pad] * ctf[b,v,u].
+// TRANSPOSED = adjoint (gradient w.r.t. in).  One CTA per (image, 16x16 output tile); the
+// needed input window and the filter stream through shared memory in row slabs.
+// ------------------------------------------------------------------------------------------
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) ctf_apply_kernel(const float* __restrict__ in, const float* __restrict__ ctf,
+                                                        float* __restrict__ out, int n) {
+    extern __shared__ float sm[];
+    const int m = n - 1, pad = m / 2;
+    const int b = blockIdx.z;
+    const int ti = blockIdx.y * 16, tj = blockIdx.x * 16;
+    const int ly = threadIdx.x / 16, lx = threadIdx.x % 16;
+    const int W = 16 + m - 1;              // window width/height
+    float* win = sm;                       // W*W input window (zero padded)
+    float* flt = sm + W * W;               // m*m filter
+    const float* inb = in + (long long)b * n * n;
+    const float* fb = ctf + (long long)b * m * m;
+    // forward:  out[i,j] = sum in[i+v-pad, j+u-pad] f[v,u]       window origin (ti-pad, tj-pad)
+    // adjoint:  out[i,j] = sum in[i-v+pad, j-u+pad] f[v,u]       window origin (ti+pad-(m-1), tj+pad-(m-1)), f flipped
+    const int oy = TRANSPOSED ? ti + pad - (m - 1) : ti - pad;
+    const int ox = TRANSPOSED ? tj + pad - (m - 1) : tj - pad;
+    for (int idx = threadIdx.x; idx < W * W; idx += blockDim.x) {
+        const int yy = oy + idx / W, xx = ox + idx % W;
+        win[idx] = (yy >= 0 && yy < n && xx >= 0 && xx < n) ? inb[yy * n + xx] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+        const int v = idx / m, u = idx % m;
+        flt[idx] = TRANSPOSED ? fb[(m - 1 - v) * m + (m - 1 - u)] : fb[idx];
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int v = 0; v < m; ++v) {
+        const float* wr = win + (ly + v) * W + lx;
+        const float* fr = flt + v * m;
+#pragma unroll 4
+        for (int u = 0; u < m; ++u) acc = fmaf(wr[u], fr[u], acc);
+    }
+    const int i = ti + ly, j = tj + lx;
+    if (i < n && j < n) out[(long long)b * n * n + i * n + j] = acc;
+}
+
+// Gaussian likelihood with optional mask (train_particles.py:326-338, no learned variance):
+//   ll[b] = -0.5 sum_px mask*(mu - y)^2 ; d_mu = g * mask * (y - mu), g = dLoss/d(ll_b) (device scalar)
+// mask: pixels within `radius` of dx/s on the integer grid x in [-n/2, n/2), y in (-n/2, n/2]  (:309-324)
+__global__ void __launch_bounds__(256) gaussian_kernel(const float* __restrict__ mu, const float* __restrict__ y,
+                                                       const float* __restrict__ dx, float s, int n, int radius,
+                                                       float* __restrict__ ll, float* __restrict__ d_mu, const float* __restrict__ g_ptr) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.y, E = n * n;
+    const float g = d_mu ? __ldg(g_ptr) : 0.f;
+    float cx = 0.f, cy = 0.f;
+    if (radius > 0) { cx = dx[b * 2] / s; cy = dx[b * 2 + 1] / s; }
+    float acc[1] = {0.f};
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        bool keep = true;
+        if (radius > 0) {
+            const int i = e / n, j = e - i * n;
+            // np.arange(-n//2, n//2) / np.arange(n//2, -n//2, -1) with python floor division
+            const int half_lo = -((n + 1) / 2);      // -n//2 for positive n  (floor)
+            const float gx = static_cast<float>(half_lo + j);
+            const float gy = static_cast<float>(n / 2 - i);
+            const double ddx = (double)cx - gx, ddy = (double)cy - gy;
+            keep = sqrt(ddx * ddx + ddy * ddy) < (double)radius;
+        }
+        const float diff = keep ? mu[(long long)b * E + e] - y[(long long)b * E + e] : 0.f;
+        acc[0] += diff * diff;
+        if (d_mu) d_mu[(long long)b * E + e] = -g * diff;
+    }
+    block_reduce<1, false>(acc, scratch);
+    if (threadIdx.x == 0) atomicAdd(ll + b, -0.5f * acc[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Thin-layer backward.  A "thin" layer maps a wide activation a[m][W] to T outputs t[m][j] =
+// sum_c a[m][c] Wt[j][c] + bt[j]  (attention/theta/z heads: T = 3+2z; generator output layer: T = n_out).
+// Given dt it produces, in one pass over a:
+//   dpre[m][c] = (sum_j dt[m][j] Wt[j][c]) * lrelu'(a[m][c])      (gradient w.r.t. the pre-activation of a)
+//   dWt[j][c] += sum_m dt[m][j] a[m][c],  dbt[j] += sum_m dt[m][j],  dcol[c] += sum_m dpre[m][c]
+// Thread = column c (coalesced rows), CTA = a chunk of rows.  dt is addressed as
+//   dt[(m / P) * dt_outer + j * dt_chan + (m % P)]   (planar head maps), or row-major with P = 1.
+// ------------------------------------------------------------------------------------------
+struct ThinBwdParams {
+    const float* a;      // [M][W] post-activation
+    const float* dt;
+    const float* Wt;     // [T][W]
+    float* dpre;         // [M][W]
+    float* dWt;          // [T][W]
+    float* dbt;          // [T]
+    float* dcol;         // [W]
+    long long M;
+    int W, T, P;
+    long long dt_outer, dt_chan;
+    int rows_per_cta;
+};
+
+template <int TMAX, bool PLANAR>
+__device__ __forceinline__ void thin_bwd_body(const ThinBwdParams& p, int G, float* s_dt) {
+    const int c = threadIdx.x;       // blockDim.x == W
+    const long long m_begin = (long long)blockIdx.x * p.rows_per_cta;
+    const long long m_end = min(m_begin + p.rows_per_cta, p.M);
+    float wt[TMAX], dw[TMAX];
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+        wt[j] = j < p.T ? p.Wt[(long long)j * p.W + c] : 0.f;
+        dw[j] = 0.f;
+    }
+    float dcol = 0.f, dbt = 0.f;
+    for (long long m0 = m_begin; m0 < m_end; m0 += 64) {
+        const int rows = static_cast<int>(min((long long)64, m_end - m0));
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < rows * p.T; idx += blockDim.x) {
+            long long addr;
+            int j, rr;
+            if (PLANAR) {
+                j = idx / rows; rr = idx - j * rows;   // consecutive threads -> consecutive rows (coalesced planar read)
+                const long long m = m0 + rr;
+                const long long br = m / p.P;
+                const int pos = static_cast<int>(m - br * p.P);
+                const long long b = br / G;
+                const int r = static_cast<int>(br - b * G);
+                addr = b * p.dt_outer + (long long)j * p.dt_chan + (long long)r * p.P + pos;
+            } else {
+                rr = idx / p.T; j = idx - rr * p.T;
+                addr = (m0 + rr) * p.T + j;
+            }
+            s_dt[rr * p.T + j] = p.dt[addr];
+        }
+        __syncthreads();
+        for (int rr = 0; rr < rows; ++rr) {
+            const long long m = m0 + rr;
+            const float av = p.a[m * p.W + c];
+            float g = 0.f;
+#pragma unroll
+            for (int j = 0; j < TMAX; ++j) {
+                if (j < p.T) {
+                    const float d = s_dt[rr * p.T + j];
+                    g = fmaf(d, wt[j], g);
+                    dw[j] = fmaf(d, av, dw[j]);
+                }
+            }
+            g *= (av > 0.f ? 1.f : kSlope);
+            p.dpre[m * p.W + c] = g;
+            dcol += g;
+        }
+        if (p.dbt && c < p.T) {
+            for (int rr = 0; rr < rows; ++rr) dbt += s_dt[rr * p.T + c];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j)
+        if (j < p.T) atomicAdd(p.dWt + (long long)j * p.W + c, dw[j]);
+    if (p.dcol) atomicAdd(p.dcol + c, dcol);
+    if (p.dbt && c < p.T) atomicAdd(p.dbt + c, dbt);
+}
+
+// row-major dt[m][T] (generator output layer)
+template <int TMAX>
+__global__ void __launch_bounds__(1024) thin_bwd_kernel(ThinBwdParams p) {
+    extern __shared__ float s_dt[];  // [64][T]
+    thin_bwd_body<TMAX, false>(p, 1, s_dt);
+}
+// planar dt (B, T, G, P) with rows m = (b*G + r)*P + pos (encoder heads); dt_outer = T*G*P, dt_chan = G*P
+__global__ void __launch_bounds__(256) thin_bwd_heads_kernel(ThinBwdParams p, int G) {
+    extern __shared__ float s_dt[];
+    thin_bwd_body<kMaxHeads + 1, true>(p, G, s_dt);
+}
+
+// column sums per group of rows: out[g][c] = sum_{m in group g} x[m][c]   (z-conditioned bias gradient),
+// and total[c] += sum over all rows.  grid = (chunks, groups), blockDim.x = W.
+__global__ void __launch_bounds__(1024) group_colsum_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                           float* __restrict__ total, int rows_per_group, int W, int rows_per_cta) {
+    const int c = threadIdx.x, g = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows_per_group);
+    const float* xg = x + ((long long)g * rows_per_group) * W;
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += xg[(long long)r * W + c];
+    if (out) atomicAdd(out + (long long)g * W + c, acc);
+    if (total) atomicAdd(total + c, acc);
+}
+
+}  // namespace tvae

@@ -1,0 +1,250 @@
+// Warp-specialised persistent TF32 GEMM core for sm_100a (tcgen05 + TMEM + TMA).
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x K] * B[BN x K]^T
+//
+// One CTA per SM.  Warp roles:
+//   warp 0      TMA producer (one lane): bulk-tensor loads into a ring of smem stages
+//   warp 1      MMA issuer   (one lane): tcgen05.mma.kind::tf32 on swizzled smem descriptors
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld accumulator rows -> registers -> policy epilogue
+//   warps 8..   optional operand generators (im2col window / Fourier features / ...) that
+//               synthesise the A tile straight into swizzled smem instead of loading it
+// Three pipelines: smem full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
+// and a static contiguous tile schedule per CTA.
+//
+// Operand layouts in smem (128-byte swizzle, tf32 = 4 bytes, 32 elements per swizzle row):
+//   K-major  operand: [rows][32 k]           8-row atoms of 1024 B, SBO = 1024, K step = +32 B
+//   MN-major operand: [col-block][k rows][32 mn] per 32-wide block of the M/N extent, in the
+//                     32-byte-atom flavour of the 128 B swizzle (4-row atoms of 512 B):
+//                     LBO = block stride (k_rows*128 B), SBO = 512, K step (8 rows) = +1024 B
+// A policy `P` supplies tile geometry, TMA issue, optional generator and the epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace tvae {
+
+constexpr int kBM = 128;        // accumulator rows (TMEM lanes)
+constexpr int kBK = 32;         // tf32 elements per smem stage along the reduction (one 128 B swizzle row)
+constexpr int kUmmaK = 8;       // tf32 elements per tcgen05.mma
+constexpr int kAStageBytes = kBM * 128;
+constexpr int kCtrlWarps = 4;
+constexpr int kEpiWarps = 4;
+constexpr int kFirstEpiWarp = kCtrlWarps;
+constexpr int kFirstProdWarp = kCtrlWarps + kEpiWarps;
+constexpr int kMaxStages = 8;
+
+struct TileInfo {
+    int m0;        // first accumulator row in the policy's row space
+    int n0;        // first accumulator column
+    int kc_begin;  // reduction chunks [kc_begin, kc_end) of kBK elements each
+    int kc_end;
+    int a0, a1, a2;  // policy scratch (image index, split index, ...)
+};
+
+struct SmemLayout {
+    uint32_t a_off, b_off, bar_off, tmem_ptr_off, extra_off, total;
+};
+
+template <class P>
+__host__ __device__ inline SmemLayout make_smem_layout(int stages, int extra_bytes) {
+    SmemLayout L;
+    L.a_off = 0;
+    L.b_off = L.a_off + stages * kAStageBytes;
+    L.bar_off = L.b_off + stages * (P::kBN * 128);
+    L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 8) * 8;
+    L.extra_off = (L.tmem_ptr_off + 16 + 127) & ~127u;
+    L.total = L.extra_off + extra_bytes;
+    return L;
+}
+
+template <class P>
+__global__ void __launch_bounds__((kCtrlWarps + kEpiWarps + P::kProdWarps) * 32, 1)
+tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kBN = P::kBN;
+    constexpr int kAccStages = (512 / kBN) > 4 ? 4 : (512 / kBN);
+    constexpr int kTmemCols = 512;
+    constexpr int kBStageBytes = kBN * 128;
+    constexpr uint32_t kIdesc = make_idesc_tf32(kBM, kBN, P::kAMajorMN, P::kBMajorMN);
+    static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "invalid UMMA N");
+
+    const int stages = prm.num_stages;
+    const SmemLayout L = make_smem_layout<P>(stages, 0);
+    uint8_t* smem_a = smem + L.a_off;
+    uint8_t* smem_b = smem + L.b_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+    uint8_t* extra = smem + L.extra_off;
+
+    const uint32_t full_bar = smem_u32(bars);                       // [stages]
+    const uint32_t empty_bar = smem_u32(bars + kMaxStages);          // [stages]
+    const uint32_t tfull_bar = smem_u32(bars + 2 * kMaxStages);      // [kAccStages]
+    const uint32_t tempty_bar = smem_u32(bars + 2 * kMaxStages + 4); // [kAccStages]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        P::prefetch_descs(prm);
+    }
+    if (warp == 1 && lane == 0) {
+        const uint32_t full_count = 1 + (P::kAGen ? P::kProdWarps * 32 : 0);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar + 8 * s, full_count);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(tfull_bar + 8 * s, 1);
+            mbar_init(tempty_bar + 8 * s, kEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+        tmem_relinquish();
+    }
+    P::setup(prm, extra, threadIdx.x, blockDim.x);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const long long nt = prm.num_tiles;
+    const int tile_begin = static_cast<int>(nt * blockIdx.x / gridDim.x);
+    const int tile_end = static_cast<int>(nt * (blockIdx.x + 1) / gridDim.x);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                TileInfo ti;
+                P::tile_info(prm, tile, ti);
+                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_arrive_expect_tx(fb, P::tx_bytes());
+                    P::issue_tma(prm, ti, kc, smem_u32(smem_a + stage * kAStageBytes),
+                                 smem_u32(smem_b + stage * kBStageBytes), fb);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                TileInfo ti;
+                P::tile_info(prm, tile, ti);
+                mbar_wait(tempty_bar + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kBN;
+                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * kAStageBytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * kBStageBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+                        uint64_t adesc, bdesc;
+                        if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                        else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                        if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                        else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
+                        umma_tf32(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar + 8 * as);  // accumulator complete -> epilogue
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
+        // ------------------------------------------------------------ epilogue
+        const int ewarp = warp - kFirstEpiWarp;  // == warp % 4 -> TMEM lane quarter
+        const int row = ewarp * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        typename P::EpiState est;
+        P::epi_init(prm, est, extra, row);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            TileInfo ti;
+            P::tile_info(prm, tile, ti);
+            mbar_wait(tfull_bar + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + as * kBN;
+            P::epilogue(prm, ti, est, taddr, row, extra);
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * as);
+            if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+        P::epi_finish(prm, est, extra, row);
+    } else if (P::kAGen && warp >= kFirstProdWarp) {
+        // ------------------------------------------------------------ operand generators
+        const int ptid = threadIdx.x - kFirstProdWarp * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        typename P::GenState gst;
+        P::gen_init(prm, gst, extra, ptid);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            TileInfo ti;
+            P::tile_info(prm, tile, ti);
+            P::gen_tile_begin(prm, ti, gst, extra, ptid);
+            for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                P::gen_chunk(prm, ti, gst, kc, smem_a + stage * kAStageBytes, extra, ptid);
+                fence_proxy_async_smem();
+                mbar_arrive(full_bar + 8 * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Defaults a policy can inherit.
+struct PolicyBase {
+    static constexpr bool kAMajorMN = false;
+    static constexpr bool kBMajorMN = false;
+    static constexpr bool kAGen = false;
+    static constexpr int kProdWarps = 0;
+    struct EpiState {};
+    struct GenState {};
+    template <class Prm> __device__ static void setup(const Prm&, uint8_t*, int, int) {}
+    template <class Prm, class St> __device__ static void epi_init(const Prm&, St&, uint8_t*, int) {}
+    template <class Prm, class St> __device__ static void epi_finish(const Prm&, St&, uint8_t*, int) {}
+    template <class Prm, class St> __device__ static void gen_init(const Prm&, St&, uint8_t*, int) {}
+    template <class Prm, class St> __device__ static void gen_tile_begin(const Prm&, const TileInfo&, St&, uint8_t*, int) {}
+    template <class Prm, class St> __device__ static void gen_chunk(const Prm&, const TileInfo&, St&, int, uint8_t*, uint8_t*, int) {}
+};
+
+// named barrier among a subset of warps (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Issue helpers shared by the policies -----------------------------------------------------------
+// K-major operand tile: `rows` rows x 32 k-elements at (k = kc*32, row = r0): one box.
+__device__ __forceinline__ void tma_kmajor(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int kc, int r0) {
+    tma_load_2d(dst, tm, bar, kc * kBK, r0);
+}
+// MN-major operand tile: kBK reduction rows x (32*nblk) features starting at feature f0, rows r0..:
+// one {32 feat x kBK rows} box per 32-wide feature block.
+__device__ __forceinline__ void tma_mnmajor(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int f0, int r0, int nblk) {
+    for (int b = 0; b < nblk; ++b) tma_load_2d(dst + b * (kBK * 128), tm, bar, f0 + 32 * b, r0);
+}
+
+}  // namespace tvae

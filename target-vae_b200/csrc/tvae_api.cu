@@ -1,0 +1,492 @@
+// C-ABI entry points of libtvae_b200.so (declared in include/tvae_b200.h).
+#include "../../include/tvae_b200.h"
+
+#include "conv_policies.cuh"
+#include "gen_policies.cuh"
+#include "launch.cuh"
+#include "simt_gen.cuh"
+#include "simt_kernels.cuh"
+
+using namespace tvae;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline int blocks_for(long long n, int threads, int cap = 148 * 8) {
+    long long b = (n + threads - 1) / threads;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+RotTable make_rot_table(int G) {
+    // theta accumulated in double exactly like models.py:181-195, cos/sin rounded to fp32 (models.py:186-190)
+    RotTable t{};
+    const double d_theta = 2.0 * 3.14159265358979323846 / G;
+    double theta = 0.0;
+    for (int i = 0; i < G && i < kMaxG; ++i) {
+        t.cs[i] = static_cast<float>(cos(theta));
+        t.sn[i] = static_cast<float>(sin(theta));
+        theta += d_theta;
+    }
+    return t;
+}
+
+ConvGeom make_geom(const tvae_enc_shape* s) {
+    ConvGeom g{};
+    g.B = s->B; g.C = s->C; g.n = s->n; g.k = s->k; g.p = s->p; g.G = s->G; g.O = s->O;
+    g.d = s->n + 2 * s->p - s->k + 1;
+    g.P = g.d * g.d;
+    g.K = s->C * s->k * s->k;
+    g.kpad = s->kpad;
+    return g;
+}
+
+int check_enc_shape(const tvae_enc_shape* s) {
+    TVAE_REQUIRE(s->B > 0 && s->C > 0 && s->n > 0 && s->k > 0 && s->p >= 0, "encoder: non-positive dimension");
+    TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG, "encoder: groupconv must be in 1..16");
+    TVAE_REQUIRE(s->O % 32 == 0 && s->O >= 32 && s->O <= 256, "encoder: kernel count must be a multiple of 32 in [32,256]");
+    TVAE_REQUIRE(s->z >= 1 && 3 + 2 * s->z <= kMaxNH, "encoder: latent dim out of range");
+    TVAE_REQUIRE(s->n + 2 * s->p - s->k + 1 >= 1, "encoder: kernel larger than padded image");
+    TVAE_REQUIRE(s->kpad == tvae_bank_pitch(s->C, s->k), "encoder: kpad must come from tvae_bank_pitch");
+    return 0;
+}
+
+template <class P>
+int launch_split_tn(typename P::Params& p, int out_tiles, int chunks_total, int align, int extra, cudaStream_t st) {
+    int splits = cdiv(2 * sm_count(), out_tiles);
+    const int min_chunks = 16;
+    if (splits > cdiv(chunks_total, min_chunks)) splits = cdiv(chunks_total, min_chunks);
+    if (splits < 1) splits = 1;
+    int cps = cdiv(chunks_total, splits);
+    if (align > 1) cps = cdiv(cps, align) * align;   // whole images per split where possible
+    p.chunks_total = chunks_total;
+    p.chunks_per_split = cps;
+    p.splits = cdiv(chunks_total, cps);
+    p.num_tiles = out_tiles * p.splits;
+    return launch_gemm<P>(p, extra, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tvae_last_error(void) { return g_last_error.c_str(); }
+int tvae_version(void) { return 100; }
+
+int tvae_bank_pitch(int C, int k) {
+    const int K = C * k * k;
+    return (K / 32 + 1) * 32;   // always leaves >= 1 spare column for the bias-gradient ones column
+}
+
+// ================================================================================ filter bank
+int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* bank, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    const long long total = (long long)s->G * s->O * s->kpad;
+    filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, bank, s->O, s->C, s->k, s->G, s->kpad, make_rot_table(s->G));
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dweight, float* dbias, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    const int K = s->C * s->k * s->k;
+    TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
+    const long long total = (long long)s->G * s->O * K;
+    filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    if (dbias) bank_bias_grad_kernel<<<cdiv(s->O, 128), 128, 0, S(stream)>>>(dbank, dbias, s->O, s->G, s->kpad, K);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ================================================================================ encoder
+int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    const ConvGeom g = make_geom(s);
+    const int NH = 3 + 2 * s->z;
+    const long long R = (long long)g.B * g.G * g.P;
+    cudaStream_t st = S(stream);
+
+    // ---- conv1: implicit GEMM with generated im2col operand
+    {
+        Conv1FwdParams p{};
+        const int N = g.G * g.O;
+        const bool wide = N > 128;
+        const int BN = wide ? 256 : 128;
+        if ((rc = make_tmap_2d(&p.tmB, a->bank, N, g.kpad, g.kpad, BN))) return rc;
+        p.g = g;
+        p.y = a->y; p.bias = a->conv1_bias; p.x1 = a->x1;
+        p.tiles_n = cdiv(N, BN);
+        p.tiles_per_image = cdiv(g.P, kBM);
+        p.k_chunks = cdiv(g.K, kBK);
+        p.num_tiles = g.B * p.tiles_per_image * p.tiles_n;
+        const int span_rows = (kBM - 1) / g.d + 2;
+        int slab_rows = span_rows + g.k - 1;
+        if (slab_rows > g.n) slab_rows = g.n;
+        p.slab_rows_max = slab_rows;
+        const int extra = g.C * slab_rows * g.n * static_cast<int>(sizeof(float));
+        rc = wide ? launch_gemm<Conv1Fwd<256>>(p, extra, st) : launch_gemm<Conv1Fwd<128>>(p, extra, st);
+        if (rc) return rc;
+    }
+    // ---- conv2 (1x1x1) + heads
+    {
+        round_tf32_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2_tf32, (long long)g.O * g.O);
+        Conv2HeadsParams p{};
+        const bool wide = g.O > 128;
+        const int BN = wide ? 256 : 128;
+        if ((rc = make_tmap_2d(&p.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
+        if ((rc = make_tmap_2d(&p.tmB, a->w2_tf32, g.O, g.O, g.O, BN))) return rc;
+        p.R = R; p.O = g.O; p.NH = NH; p.G = g.G; p.P = g.P;
+        p.k_chunks = cdiv(g.O, kBK);
+        p.num_tiles = cdiv(R, kBM);
+        p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh; p.head_add = a->head_add; p.h = a->h; p.heads = a->heads;
+        const int extra = (NH * g.O + g.O) * static_cast<int>(sizeof(float));
+        if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH>>(p, extra, st);
+        else if (NH <= 8) rc = launch_gemm<Conv2Heads<128, 8>>(p, extra, st);
+        else if (NH <= 20) rc = launch_gemm<Conv2Heads<128, 20>>(p, extra, st);
+        else rc = launch_gemm<Conv2Heads<128, kMaxNH>>(p, extra, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    const ConvGeom g = make_geom(s);
+    const int NH = 3 + 2 * s->z;
+    const long long R = (long long)g.B * g.G * g.P;
+    cudaStream_t st = S(stream);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwh, 0, sizeof(float) * NH * g.O, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbh, 0, sizeof(float) * NH, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->db2, 0, sizeof(float) * g.O, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dw2, 0, sizeof(float) * g.O * g.O, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbank, 0, sizeof(float) * g.G * g.O * g.kpad, st));
+    // ---- heads backward: dhpre = (d_heads . Wh) * lrelu'(h); dWh, dbh, db2
+    {
+        ThinBwdParams p{};
+        p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
+        p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
+        // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]: group = (b*G + r) is not affine in j,
+        // so address through b and r: outer index = m / P = b*G + r.
+        p.dt_outer = 0; p.dt_chan = 0;  // unused by the planar accessor below
+        p.rows_per_cta = 1024;
+        // planar accessor: encode G and NH for the kernel via dt_outer / dt_chan
+        p.dt_outer = (long long)NH * g.G * g.P;   // stride of b
+        p.dt_chan = (long long)g.G * g.P;         // stride of channel j
+        const int grid = cdiv(R, p.rows_per_cta);
+        const size_t sm = 64 * NH * sizeof(float);
+        thin_bwd_heads_kernel<<<grid, g.O, sm, st>>>(p, g.G);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    // ---- dW2 = dhpre^T x1
+    if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st))) return rc;
+    // ---- dx1pre = (dhpre W2) * lrelu'(x1), in place over x1
+    transpose_round_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2t_tf32, g.O, g.O, 1);
+    {
+        LinearNTArgs l{};
+        l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_tf32; l.ldb = g.O;
+        l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
+        l.C = a->x1; l.ldc = g.O; l.aux = a->x1; l.ld_aux = g.O;
+        if ((rc = linear_nt(l, st))) return rc;
+    }
+    // ---- conv1 weight gradient (w.r.t. the rotated bank)
+    {
+        Conv1WgradParams p{};
+        const int N = g.G * g.O;
+        const bool wide = N > 128;
+        const int BN = wide ? 256 : 128;
+        if ((rc = make_tmap_2d(&p.tmQ, a->x1, R, g.O, g.O, kBK, true))) return rc;
+        p.g = g; p.y = a->y; p.dbank = a->dbank;
+        p.tiles_m = cdiv(g.K + 1, kBM);     // + ones column
+        p.tiles_n = cdiv(N, BN);
+        p.chunks_per_image = cdiv(g.P, kBK);
+        const int extra = g.C * g.n * g.n * static_cast<int>(sizeof(float));
+        const int out_tiles = p.tiles_m * p.tiles_n;
+        rc = wide ? launch_split_tn<Conv1Wgrad<256>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st)
+                  : launch_split_tn<Conv1Wgrad<128>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ================================================================================ attention
+static AttnParams to_attn_params(const tvae_attn_shape* s, const tvae_attn_fwd_args* a) {
+    AttnParams p{};
+    p.heads = a->heads; p.gumbel = a->gumbel; p.r_z = a->r_z; p.r_theta = a->r_theta; p.log_prior = a->log_prior;
+    p.stats = a->stats; p.zb = a->zb; p.theta_b = a->theta_b; p.dx = a->dx; p.kl = a->kl;
+    p.B = s->B; p.G = s->G; p.d = s->d; p.z = s->z; p.s = s->s; p.theta_prior_std = s->theta_prior_std;
+    for (int i = 0; i < kMaxG; ++i) p.offsets[i] = s->offsets[i];
+    return p;
+}
+
+int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float* log_prior, void* stream) {
+    RotTable t{};
+    for (int i = 0; i < s->G && i < kMaxG; ++i) t.cs[i] = p_r_host16[i];
+    log_prior_kernel<<<1, 1024, 0, S(stream)>>>(log_prior, s->G, s->d, s->s, t);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define TVAE_DISPATCH_Z(zval, CALL)                                                        \
+    switch (zval) {                                                                        \
+        case 1: { constexpr int ZZ = 1; CALL; } break;                                     \
+        case 2: { constexpr int ZZ = 2; CALL; } break;                                     \
+        case 3: { constexpr int ZZ = 3; CALL; } break;                                     \
+        case 4: { constexpr int ZZ = 4; CALL; } break;                                     \
+        case 5: { constexpr int ZZ = 5; CALL; } break;                                     \
+        case 6: { constexpr int ZZ = 6; CALL; } break;                                     \
+        case 8: { constexpr int ZZ = 8; CALL; } break;                                     \
+        case 10: { constexpr int ZZ = 10; CALL; } break;                                   \
+        case 16: { constexpr int ZZ = 16; CALL; } break;                                   \
+        default: return fail(-1, "latent dim not instantiated (supported: 1-6, 8, 10, 16)"); \
+    }
+
+int tvae_attn_fwd(const tvae_attn_shape* s, const tvae_attn_fwd_args* a, void* stream) {
+    TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG && s->d >= 1 && s->B >= 1, "attention: bad shape");
+    const AttnParams p = to_attn_params(s, a);
+    TVAE_DISPATCH_Z(s->z, (attn_fwd_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(p)));
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_attn_bwd(const tvae_attn_shape* s, const tvae_attn_bwd_args* a, void* stream) {
+    TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG && s->d >= 1 && s->B >= 1, "attention: bad shape");
+    AttnBwdParams p{};
+    p.heads = a->f.heads; p.gumbel = a->f.gumbel; p.r_z = a->f.r_z; p.r_theta = a->f.r_theta; p.log_prior = a->f.log_prior;
+    p.stats = a->f.stats; p.zb = a->f.zb; p.theta_b = a->f.theta_b; p.dx = a->f.dx; p.kl = a->f.kl;
+    p.g_zb = a->g_zb; p.g_theta = a->g_theta; p.g_dx = a->g_dx; p.g_kl = a->g_kl; p.d_heads = a->d_heads;
+    p.B = s->B; p.G = s->G; p.d = s->d; p.z = s->z; p.s = s->s; p.theta_prior_std = s->theta_prior_std;
+    for (int i = 0; i < kMaxG; ++i) p.offsets[i] = s->offsets[i];
+    const int L = s->G * s->d * s->d;
+    dim3 grid(blocks_for(L, 256, 64), s->B);
+    TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ><<<grid, 256, 0, S(stream)>>>(p)));
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_attn_softmax_pair(const float* heads, const float* gumbel, float* q_t_r, float* a_sampled, int B, int NH, int L, void* stream) {
+    softmax_pair_kernel<<<B, 1024, 0, S(stream)>>>(heads, gumbel, q_t_r, a_sampled, NH, L);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_get_latent(const tvae_attn_shape* s, const float* heads, float* z_content, float* theta_mu, float* dx, int* argmax, void* stream) {
+    TVAE_DISPATCH_Z(s->z, (get_latent_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(heads, s->G, s->d, s->s, z_content, theta_mu, dx, argmax)));
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ================================================================================ generator
+static int check_gen_shape(const tvae_gen_shape* s) {
+    TVAE_REQUIRE(s->B > 0 && s->N > 0, "generator: empty batch");
+    TVAE_REQUIRE(s->H % 32 == 0 && s->H >= 32 && s->H <= 1024, "generator: hidden dim must be a multiple of 32 in [32,1024]");
+    TVAE_REQUIRE(s->E == 0 || (s->E % 32 == 0 && s->E <= 4096), "generator: Fourier dim must be a multiple of 32");
+    TVAE_REQUIRE(s->L >= 0 && s->L <= 8, "generator: 0..8 hidden layers");
+    TVAE_REQUIRE(s->n_out >= 1 && s->n_out <= 4 && s->zdim >= 1, "generator: n_out in 1..4");
+    return 0;
+}
+
+static CoordXform make_xform(const tvae_gen_shape* s, const tvae_gen_fwd_args* a) {
+    CoordXform c{};
+    c.x = a->x; c.theta = a->theta; c.dx = a->dx; c.N = s->N; c.M = (long long)s->B * s->N;
+    return c;
+}
+
+int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void* stream) {
+    int rc = check_gen_shape(s);
+    if (rc) return rc;
+    cudaStream_t st = S(stream);
+    const long long M = (long long)s->B * s->N;
+    const int H = s->H, E = s->E;
+    const CoordXform cx = make_xform(s, a);
+    latent_bias_kernel<<<cdiv(s->B * H, 256), 256, 0, st>>>(a->z, a->wz, a->zb, s->B, H, s->zdim);
+    float* w1r = a->w_tf32;                              // [H][E]
+    float* whr = a->w_tf32 + (long long)H * (E > 0 ? E : 2);   // [L][H][H]
+    if (s->L > 0) round_tf32_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whr, (long long)s->L * H * H);
+    float* a0 = a->acts;
+    if (E > 0) {
+        round_tf32_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1r, (long long)H * E);
+        GenL1FwdParams p{};
+        const bool wide = H > 128;
+        const int BN = wide ? 256 : 128;
+        if ((rc = make_tmap_2d(&p.tmB, w1r, H, E, E, BN))) return rc;
+        p.cx = cx; p.wf_scaled = a->wf_scaled; p.bf = a->bf; p.E = E; p.H = H;
+        p.bias = a->b1; p.zb = a->zb; p.h1 = a0;
+        p.tiles_n = cdiv(H, BN);
+        p.k_chunks = cdiv(E, kBK);
+        p.num_tiles = cdiv(M, kBM) * p.tiles_n;
+        const int extra = E * 16;
+        rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
+        if (rc) return rc;
+    } else {
+        const int rows_per_cta = 64;
+        coord_layer_fwd_kernel<<<cdiv(M, rows_per_cta), H, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, rows_per_cta);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    if (s->L == 0) {
+        thin_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(a0, a->wout, a->bout, a->y_hat, M, H, s->n_out);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->y_hat, 0, sizeof(float) * M * s->n_out, st));
+    for (int i = 1; i <= s->L; ++i) {
+        LinearNTArgs l{};
+        l.A = a->acts + (long long)(i - 1) * M * H; l.lda = H;
+        l.B = whr + (long long)(i - 1) * H * H; l.ldb = H;
+        l.M = static_cast<int>(M); l.N = H; l.K = H;
+        l.C = a->acts + (long long)i * M * H; l.ldc = H;
+        l.bias = a->bh + (long long)(i - 1) * H;
+        l.act = 1; l.round_tf32 = 1;
+        if (i == s->L) { l.proj_w = a->wout; l.proj_bias = a->bout; l.proj_out = a->y_hat; l.n_proj = s->n_out; }
+        if ((rc = linear_nt(l, st))) return rc;
+    }
+    return 0;
+}
+
+int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void* stream) {
+    int rc = check_gen_shape(s);
+    if (rc) return rc;
+    cudaStream_t st = S(stream);
+    const long long M = (long long)s->B * s->N;
+    const int H = s->H, E = s->E, L = s->L;
+    const CoordXform cx = make_xform(s, &a->f);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwout, 0, sizeof(float) * s->n_out * H, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbout, 0, sizeof(float) * s->n_out, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->db1, 0, sizeof(float) * H, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dzb, 0, sizeof(float) * s->B * H, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->dw1, 0, sizeof(float) * H * (E > 0 ? E : 2), st));
+    if (L > 0) {
+        TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwh, 0, sizeof(float) * L * H * H, st));
+        TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbh, 0, sizeof(float) * L * H, st));
+    }
+    float* dcur = a->dpre0;
+    float* dnext = a->dpre1;
+    // ---- output layer backward -> dpre of the last hidden activation
+    {
+        ThinBwdParams p{};
+        p.a = a->f.acts + (long long)L * M * H; p.dt = a->d_yhat; p.Wt = a->f.wout; p.dpre = dcur;
+        p.dWt = a->dwout; p.dbt = a->dbout; p.dcol = (L > 0) ? a->dbh + (long long)(L - 1) * H : nullptr;
+        p.M = M; p.W = H; p.T = s->n_out; p.P = 1; p.dt_outer = s->n_out; p.dt_chan = 1;
+        p.rows_per_cta = 1024;
+        thin_bwd_kernel<4><<<cdiv(M, p.rows_per_cta), H, 64 * s->n_out * sizeof(float), st>>>(p);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    // ---- hidden layers, last to first
+    for (int i = L; i >= 1; --i) {
+        const float* a_prev = a->f.acts + (long long)(i - 1) * M * H;
+        const float* w = a->f.wh + (long long)(i - 1) * H * H;
+        if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st))) return rc;
+        transpose_round_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, a->wt_tf32, H, H, 1);
+        LinearNTArgs l{};
+        l.A = dcur; l.lda = H; l.B = a->wt_tf32; l.ldb = H;
+        l.M = static_cast<int>(M); l.N = H; l.K = H;
+        l.C = dnext; l.ldc = H; l.aux = a_prev; l.ld_aux = H;
+        if ((rc = linear_nt(l, st))) return rc;
+        float* t = dcur; dcur = dnext; dnext = t;
+        if (i - 1 >= 1) {
+            group_colsum_kernel<<<dim3(cdiv(M, 2048), 1), H, 0, st>>>(dcur, nullptr, a->dbh + (long long)(i - 2) * H, static_cast<int>(M), H, 2048);
+            TVAE_CHECK_CUDA(cudaGetLastError());
+        }
+    }
+    // ---- dcur == dpre of layer 1: bias / latent-bias gradients
+    group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->dzb, a->db1, s->N, H, 512);
+    latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    // ---- layer 1 weight and coordinate gradients
+    if (E > 0) {
+        {
+            GenL1WgradParams p{};
+            const bool wide = H > 128;
+            const int BN = wide ? 256 : 128;
+            if ((rc = make_tmap_2d(&p.tmQ, dcur, M, H, H, kBK, true))) return rc;
+            p.cx = cx; p.wf_scaled = a->f.wf_scaled; p.bf = a->f.bf; p.E = E; p.H = H; p.dW1 = a->dw1;
+            p.tiles_m = cdiv(E, kBM);
+            p.tiles_n = cdiv(H, BN);
+            const int extra = E * 16;
+            const int out_tiles = p.tiles_m * p.tiles_n;
+            rc = wide ? launch_split_tn<GenL1Wgrad<256>>(p, out_tiles, cdiv(M, kBK), 1, extra, st)
+                      : launch_split_tn<GenL1Wgrad<128>>(p, out_tiles, cdiv(M, kBK), 1, extra, st);
+            if (rc) return rc;
+        }
+        {
+            TVAE_CHECK_CUDA(cudaMemsetAsync(a->dxp, 0, sizeof(float) * M * 2, st));
+            transpose_round_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->f.w1, a->wt_tf32, H, E, 1);   // -> [E][H]
+            GenL1DgradParams p{};
+            const bool wide = E > 128;
+            const int BN = wide ? 256 : 128;
+            if ((rc = make_tmap_2d(&p.tmA, dcur, M, H, H, kBM))) return rc;
+            if ((rc = make_tmap_2d(&p.tmB, a->wt_tf32, E, H, H, BN))) return rc;
+            p.cx = cx; p.wf_scaled = a->f.wf_scaled; p.bf = a->f.bf; p.E = E; p.H = H; p.dxp = a->dxp;
+            p.tiles_n = cdiv(E, BN);
+            p.k_chunks = cdiv(H, kBK);
+            p.num_tiles = cdiv(M, kBM) * p.tiles_n;
+            const int extra = E * 16;
+            rc = wide ? launch_gemm<GenL1Dgrad<256>>(p, extra, st) : launch_gemm<GenL1Dgrad<128>>(p, extra, st);
+            if (rc) return rc;
+        }
+    } else {
+        coord_layer_bwd_w_kernel<<<cdiv(M, 2048), H, 0, st>>>(cx, dcur, a->dw1, H, 2048);
+        coord_layer_bwd_x_kernel<<<cdiv(M, 8), 256, 0, st>>>(a->f.w1, dcur, a->dxp, M, H);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    if (a->f.theta && a->d_theta) {
+        coord_xform_bwd_kernel<<<s->B, 256, 0, st>>>(cx, a->dxp, a->d_theta, a->d_dx);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ================================================================================ likelihoods
+int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat, const float* g, int B, int E, void* stream) {
+    cudaStream_t st = S(stream);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
+    dim3 grid(blocks_for(E, 256, 32), B);
+    bernoulli_kernel<<<grid, 256, 0, st>>>(y_hat, y, ll, d_yhat, E, g);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius, float* mu,
+                  float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream) {
+    cudaStream_t st = S(stream);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
+    const int m = n - 1, W = 16 + m - 1;
+    const size_t sm = sizeof(float) * (W * W + m * m);
+    dim3 cgrid(cdiv(n, 16), cdiv(n, 16), B);
+    const float* mu_in = y_hat;
+    if (ctf) {
+        TVAE_REQUIRE(sm <= 227 * 1024, "gaussian: CTF window does not fit shared memory");
+        static bool cfg = false;
+        if (!cfg) {
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            cfg = true;
+        }
+        ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n);
+        mu_in = mu;
+    }
+    dim3 grid(blocks_for(n * n, 256, 32), B);
+    float* dmu_out = d_yhat ? (ctf ? dmu : d_yhat) : nullptr;
+    gaussian_kernel<<<grid, 256, 0, st>>>(mu_in, y, dx, s, n, radius, ll, dmu_out, g);
+    if (ctf && d_yhat) ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ================================================================================ test hooks
+int tvae_test_linear_nt(const float* A, const float* B, float* C, int M, int N, int K, const float* bias, int act,
+                        void* stream) {
+    LinearNTArgs a{};
+    a.A = A; a.lda = K; a.B = B; a.ldb = K; a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = N; a.bias = bias; a.act = act;
+    return linear_nt(a, S(stream));
+}
+
+int tvae_test_linear_tn(const float* P, const float* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
+    return linear_tn(P, Ma, Q, Nb, R, Ma, Nb, C, transpose_out ? Ma : Nb, transpose_out, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+"""Thin torch-tensor wrappers over the C ABI (include/tvae_b200.h).  torch is plumbing only: it owns device
+memory and the stream; every computation is a call into libtvae_b200.so."""
+from __future__ import annotations
+
+import ctypes
+import math
+from ctypes import POINTER, Structure, byref, c_float, c_int, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class EncShape(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "C", "n", "k", "p", "G", "O", "z", "kpad")]
+
+
+class EncFwdArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("y", "bank", "conv1_bias", "w2", "b2", "wh", "bh", "head_add",
+                                         "x1", "h", "heads", "w2_tf32")]
+
+
+class EncBwdArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "w2t_tf32", "dbank",
+                                         "dw2", "db2", "dwh", "dbh")]
+
+
+class AttnShape(Structure):
+    _fields_ = [("B", c_int), ("G", c_int), ("d", c_int), ("z", c_int), ("s", c_float),
+                ("theta_prior_std", c_float), ("offsets", c_float * 16)]
+
+
+class AttnFwdArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("heads", "gumbel", "r_z", "r_theta", "log_prior", "stats", "zb",
+                                         "theta_b", "dx", "kl")]
+
+
+class AttnBwdArgs(Structure):
+    _fields_ = [("f", AttnFwdArgs)] + [(n, c_void_p) for n in ("g_zb", "g_theta", "g_dx", "g_kl", "d_heads")]
+
+
+class GenShape(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "N", "E", "H", "L", "n_out", "zdim")]
+
+
+class GenFwdArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ("x", "theta", "dx", "z", "wf_scaled", "bf", "w1", "b1", "wz", "wh", "bh",
+                                         "wout", "bout", "zb", "acts", "y_hat", "w_tf32")]
+
+
+class GenBwdArgs(Structure):
+    _fields_ = [("f", GenFwdArgs)] + [(n, c_void_p) for n in (
+        "d_yhat", "dpre0", "dpre1", "wt_tf32", "dxp", "dzb", "dw1", "db1", "dwz", "dwh", "dbh", "dwout", "dbout",
+        "d_theta", "d_dx", "d_z")]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _set(struct, **kw):
+    """Fill pointer fields from tensors; the tensors are kept alive on the struct until it is dropped."""
+    keep = struct.__dict__.setdefault("_keep", [])
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+        setattr(struct, k, _p(v) if (v is None or isinstance(v, torch.Tensor)) else v)
+    return struct
+
+
+_configured = False
+
+
+def L():
+    global _configured
+    lib = _lib.lib()
+    if not _configured:
+        lib.tvae_bank_pitch.restype = c_int
+        for name in ("tvae_filter_bank_fwd", "tvae_filter_bank_bwd", "tvae_encoder_fwd", "tvae_encoder_bwd",
+                     "tvae_attn_log_prior", "tvae_attn_fwd", "tvae_attn_bwd", "tvae_attn_softmax_pair",
+                     "tvae_get_latent", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
+                     "tvae_gaussian"):
+            getattr(lib, name).restype = c_int
+        lib.tvae_gaussian.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        lib.tvae_bernoulli.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        _configured = True
+    return lib
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def empty(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------- encoder
+def enc_shape(B, C, n, k, p, G, O, z) -> EncShape:
+    return EncShape(B, C, n, k, p, G, O, z, L().tvae_bank_pitch(C, k))
+
+
+def filter_bank_fwd(s: EncShape, weight: torch.Tensor) -> torch.Tensor:
+    bank = empty(s.G * s.O, s.kpad, device=weight.device)
+    check(L().tvae_filter_bank_fwd(byref(s), ptr(f32(weight)), ptr(bank), stream_ptr()), "tvae_filter_bank_fwd")
+    return bank
+
+
+def filter_bank_bwd(s: EncShape, dbank: torch.Tensor):
+    dw = empty(s.O, s.C, 1, s.k, s.k, device=dbank.device)
+    db = empty(s.O, device=dbank.device)
+    check(L().tvae_filter_bank_bwd(byref(s), ptr(dbank), ptr(dw), ptr(db), stream_ptr()), "tvae_filter_bank_bwd")
+    return dw, db
+
+
+def rotation_offsets(G: int, rot_refinement: bool):
+    """models.py:361-366 / :401."""
+    if not rot_refinement:
+        return [0.0] * G
+    out = []
+    for i in range(G):
+        a = i * 2 * math.pi / G
+        if i > G // 2:
+            a -= 2 * math.pi
+        out.append(float(torch.tensor(a, dtype=torch.float32)))
+    return out
+
+
+def rotation_log_prior(G: int, rot_refinement: bool, normal_prior_over_r: bool, theta_prior: float):
+    """p_r[r] of models.py:360-379 as python floats (fp32 arithmetic like the reference)."""
+    if rot_refinement:
+        offs = torch.tensor(rotation_offsets(G, True), dtype=torch.float32)
+        if normal_prior_over_r:
+            sigma = torch.tensor(theta_prior, dtype=torch.float32)
+            p = -(offs ** 2) / (2 * sigma ** 2) - torch.log(sigma) - 0.5 * math.log(2 * math.pi)
+        else:
+            p = torch.zeros(G) - torch.log(torch.tensor(4 * math.pi, dtype=torch.float32))
+    else:
+        p = torch.zeros(G) - math.log(G)
+    return [float(v) for v in p]
+
+
+def head_tables(wa, ba, wr, br, wz, bz, G, p_r, offsets, device):
+    """Stack the three 1x1x1 head convolutions and build the per-(channel, rotation) additive table."""
+    O = wa.shape[1]
+    wh = torch.cat([f32(wa).reshape(1, O), f32(wr).reshape(2, O), f32(wz).reshape(-1, O)], 0).contiguous()
+    bh = torch.cat([f32(ba).reshape(1), f32(br).reshape(2), f32(bz).reshape(-1)], 0).contiguous()
+    NH = wh.shape[0]
+    add = torch.zeros(NH, G, dtype=torch.float32)
+    add[0] = torch.tensor(p_r, dtype=torch.float32)
+    add[1] = torch.tensor(offsets, dtype=torch.float32)
+    return wh, bh, add.to(device)
+
+
+def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add):
+    dev = y.device
+    d = s.n + 2 * s.p - s.k + 1
+    P = d * d
+    R = s.B * s.G * P
+    NH = 3 + 2 * s.z
+    x1 = empty(R, s.O, device=dev)
+    h = empty(R, s.O, device=dev)
+    heads = empty(s.B, NH, s.G, P, device=dev)
+    w2r = empty(s.O, s.O, device=dev)
+    a = _set(EncFwdArgs(), y=f32(y), bank=bank, conv1_bias=f32(b1), w2=f32(w2), b2=f32(b2), wh=wh, bh=bh,
+             head_add=head_add, x1=x1, h=h, heads=heads, w2_tf32=w2r)
+    check(L().tvae_encoder_fwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_fwd")
+    return x1, h, heads
+
+
+def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
+    dev = y.device
+    NH = 3 + 2 * s.z
+    R = x1.shape[0]
+    dhpre = empty(R, s.O, device=dev)
+    w2t = empty(s.O, s.O, device=dev)
+    dbank = empty(s.G * s.O, s.kpad, device=dev)
+    dw2 = empty(s.O, s.O, device=dev)
+    db2 = empty(s.O, device=dev)
+    dwh = empty(NH, s.O, device=dev)
+    dbh = empty(NH, device=dev)
+    a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, w2t_tf32=w2t,
+             dbank=dbank, dw2=dw2, db2=db2, dwh=dwh, dbh=dbh)
+    check(L().tvae_encoder_bwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_bwd")
+    return dbank, dw2, db2, dwh, dbh
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attn_shape(B, G, d, z, s, offsets) -> AttnShape:
+    a = AttnShape(B, G, d, z, float(s), float(torch.tensor(math.pi / G, dtype=torch.float32)))
+    for i, o in enumerate(offsets):
+        a.offsets[i] = o
+    return a
+
+
+def attn_log_prior(s: AttnShape, p_r, device):
+    out = empty(s.G * s.d * s.d, device=device)
+    arr = (c_float * 16)(*([float(v) for v in p_r] + [0.0] * (16 - len(p_r))))
+    check(L().tvae_attn_log_prior(byref(s), arr, ptr(out), stream_ptr()), "tvae_attn_log_prior")
+    return out
+
+
+def attn_fwd(s: AttnShape, heads, gumbel, r_z, r_theta, log_prior):
+    dev = heads.device
+    out = dict(stats=empty(s.B, 4, device=dev), zb=empty(s.B, s.z, device=dev), theta_b=empty(s.B, device=dev),
+               dx=empty(s.B, 2, device=dev), kl=empty(s.B, device=dev))
+    a = _set(AttnFwdArgs(), heads=heads, gumbel=f32(gumbel), r_z=f32(r_z), r_theta=f32(r_theta), log_prior=log_prior, **out)
+    check(L().tvae_attn_fwd(byref(s), byref(a), stream_ptr()), "tvae_attn_fwd")
+    return out
+
+
+def attn_bwd(s: AttnShape, heads, gumbel, r_z, r_theta, log_prior, fwd_out, g_zb, g_theta, g_dx, g_kl):
+    d_heads = torch.empty_like(heads)
+    a = AttnBwdArgs()
+    _set(a.f, heads=heads, gumbel=f32(gumbel), r_z=f32(r_z), r_theta=f32(r_theta), log_prior=log_prior, **fwd_out)
+    _set(a, g_zb=f32(g_zb), g_theta=f32(g_theta), g_dx=f32(g_dx), g_kl=f32(g_kl), d_heads=d_heads)
+    check(L().tvae_attn_bwd(byref(s), byref(a), stream_ptr()), "tvae_attn_bwd")
+    return d_heads
+
+
+def attn_softmax_pair(heads, gumbel):
+    B, NH = heads.shape[0], heads.shape[1]
+    Lr = heads.shape[2] * heads.shape[3]
+    q = empty(B, Lr, device=heads.device)
+    a = empty(B, Lr, device=heads.device)
+    check(L().tvae_attn_softmax_pair(ptr(heads), ptr(f32(gumbel)), ptr(q), ptr(a), B, NH, Lr, stream_ptr()),
+          "tvae_attn_softmax_pair")
+    return q, a
+
+
+def get_latent(s: AttnShape, heads):
+    dev = heads.device
+    zc = empty(s.B, 2 * s.z, device=dev)
+    th = empty(s.B, 1, device=dev)
+    dx = empty(s.B, 2, device=dev)
+    am = torch.empty(s.B, device=dev, dtype=torch.int32)
+    check(L().tvae_get_latent(byref(s), ptr(heads), ptr(zc), ptr(th), ptr(dx), ptr(am), stream_ptr()), "tvae_get_latent")
+    return zc, th, dx, am
+
+
+# ----------------------------------------------------------------------------------------------- generator
+class GenWeights:
+    """Flat views of SpatialGenerator parameters in the order the C ABI expects."""
+
+    def __init__(self, wf_scaled, bf, w1, b1, wz, hidden_w, hidden_b, wout, bout):
+        self.wf_scaled, self.bf, self.w1, self.b1, self.wz = wf_scaled, bf, f32(w1), f32(b1), f32(wz)
+        self.L = len(hidden_w)
+        H = self.w1.shape[0]
+        dev = self.w1.device
+        self.wh = torch.stack([f32(w) for w in hidden_w]).contiguous() if self.L else torch.zeros(1, device=dev)
+        self.bh = torch.stack([f32(b) for b in hidden_b]).contiguous() if self.L else torch.zeros(1, device=dev)
+        self.wout, self.bout = f32(wout), f32(bout)
+        self.H = H
+        self.E = 0 if wf_scaled is None else wf_scaled.shape[0]
+
+
+def gen_shape(B, N, gw: GenWeights, zdim) -> GenShape:
+    return GenShape(B, N, gw.E, gw.H, gw.L, gw.wout.shape[0], zdim)
+
+
+def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_tf32):
+    return _set(GenFwdArgs(), x=f32(x), theta=None if theta is None else f32(theta), dx=None if dx is None else f32(dx),
+                z=f32(z), wf_scaled=gw.wf_scaled, bf=gw.bf, w1=gw.w1, b1=gw.b1, wz=gw.wz, wh=gw.wh, bh=gw.bh,
+                wout=gw.wout, bout=gw.bout, zb=zb, acts=acts, y_hat=y_hat, w_tf32=w_tf32)
+
+
+def generator_fwd(s: GenShape, gw: GenWeights, x, theta, dx, z):
+    dev = z.device
+    M = s.B * s.N
+    zb = empty(s.B, s.H, device=dev)
+    acts = empty(s.L + 1, M, s.H, device=dev)
+    y_hat = empty(M, s.n_out, device=dev)
+    w_tf32 = empty(s.H * max(s.E, 2) + s.L * s.H * s.H, device=dev)
+    a = _gen_fwd_args(s, gw, x, theta, dx, z, zb, acts, y_hat, w_tf32)
+    check(L().tvae_generator_fwd(byref(s), byref(a), stream_ptr()), "tvae_generator_fwd")
+    return y_hat, dict(zb=zb, acts=acts, w_tf32=w_tf32)
+
+
+def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_yhat):
+    dev = z.device
+    M = s.B * s.N
+    H, E, Lh = s.H, s.E, s.L
+    out = dict(dw1=empty(H, max(E, 2), device=dev), db1=empty(H, device=dev), dwz=empty(H, s.zdim, device=dev),
+               dwh=empty(max(Lh, 1), H, H, device=dev), dbh=empty(max(Lh, 1), H, device=dev),
+               dwout=empty(s.n_out, H, device=dev), dbout=empty(s.n_out, device=dev),
+               d_theta=empty(s.B, device=dev), d_dx=empty(s.B, 2, device=dev), d_z=empty(s.B, s.zdim, device=dev))
+    scratch = dict(dpre0=empty(M, H, device=dev), dpre1=empty(M, H, device=dev),
+                   wt_tf32=empty(max(E * H, H * H), device=dev), dxp=empty(M, 2, device=dev), dzb=empty(s.B, H, device=dev))
+    a = GenBwdArgs()
+    a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_tf32"])
+    _set(a, d_yhat=f32(d_yhat), **scratch, **out)
+    if theta is None:
+        a.d_theta = None
+        a.d_dx = None
+    check(L().tvae_generator_bwd(byref(s), byref(a), stream_ptr()), "tvae_generator_bwd")
+    out["dxp"] = scratch["dxp"]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- likelihoods
+def bernoulli(y_hat, y, g=None):
+    B = y.shape[0]
+    E = y.numel() // B
+    ll = empty(B, device=y.device)
+    d = torch.empty_like(y_hat) if g is not None else None
+    check(L().tvae_bernoulli(_p(f32(y_hat)), _p(f32(y)), _p(ll), _p(d), _p(g), B, E, stream_ptr().value), "tvae_bernoulli")
+    return ll, d
+
+
+def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None):
+    B = y.shape[0]
+    dev = y.device
+    ll = empty(B, device=dev)
+    mu = empty(B, n * n, device=dev) if ctf is not None else None
+    dmu = empty(B, n * n, device=dev) if (ctf is not None and g is not None) else None
+    d = torch.empty_like(y_hat) if g is not None else None
+    check(L().tvae_gaussian(_p(f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)),
+                            _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
+                            _p(g), B, n, stream_ptr().value), "tvae_gaussian")
+    return ll, d

@@ -1,0 +1,285 @@
+"""Per-stage GPU parity: each C-ABI call against the CPU oracle (fp64) on the same seeded inputs.
+
+Tolerances (stated per stage):
+  * TF32 stages (group conv, 1x1x1 convs, generator linears): operands rounded to TF32 (2^-11 relative),
+    fp32 accumulate -> relative Frobenius error <= 3e-3 on activations and <= 5e-3 on gradients when the
+    oracle is evaluated on the same LeakyReLU activation pattern (helpers.ForcedActivations explains why the
+    un-forced comparison is kink-limited to ~3e-2; that end-to-end bound is asserted in test_gpu_step.py).
+  * fp32 CUDA-core stages (filter bank, attention/KL, likelihoods, coordinate transforms): <= 1e-4 relative
+    (fast-math exp/log differences only), filter bank additionally carries the tf32 rounding of its output.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import ForcedActivations, oracle_inputs, rel_err
+from oracle import target_vae_oracle as orc
+from tvae_b200.config import HotPathConfig
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def small_cfgs():
+    return [
+        HotPathConfig("t_mnist", C=1, n=24, k=9, p=3, G=8, z=2, O=32, hidden=128),
+        HotPathConfig("t_galaxy", C=3, n=16, k=16, p=8, G=4, z=3, O=64, hidden=64, gen_layers=4, n_out=3,
+                      likelihood="bernoulli_rgb"),
+        HotPathConfig("t_part", C=1, n=20, k=11, p=2, G=16, z=8, O=128, hidden=256, likelihood="gaussian", ctf=True),
+        HotPathConfig("t_dsp", C=1, n=16, k=16, p=8, G=8, z=2, O=32, hidden=64, fourier=False, normal_prior_over_r=True),
+    ]
+
+
+def _ops():
+    from tvae_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("cfg", small_cfgs(), ids=lambda c: c.name)
+def test_filter_bank_fwd_bwd(cfg):
+    ops = _ops()
+    enc, gen, x, y, ctf, nz = oracle_inputs(cfg, 2, dtype=torch.float64, requires_grad=False)
+    s = ops.enc_shape(2, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
+    w = enc.conv1_w.float().to(DEV)
+    bank = ops.filter_bank_fwd(s, w).cpu()
+    K = cfg.C * cfg.k ** 2
+    ref = orc.rotated_filter_bank(enc.conv1_w, cfg.G)            # (O,G,C,1,k,k)
+    ref = ref.permute(1, 0, 2, 3, 4, 5).reshape(cfg.G * cfg.O, K)  # row r*O + o
+    assert rel_err(bank[:, :K], ref) < 6e-4                        # tf32 rounding of the stored bank
+    assert float(bank[:, K:].abs().max()) == 0.0
+    # adjoint: <bank(w), D> == <w, bank^T(D)>
+    g = torch.Generator().manual_seed(1)
+    D = torch.randn(cfg.G * cfg.O, s.kpad, generator=g)
+    dw, db = ops.filter_bank_bwd(s, D.to(DEV))
+    wv = enc.conv1_w.clone().requires_grad_(True)
+    refb = orc.rotated_filter_bank(wv, cfg.G).permute(1, 0, 2, 3, 4, 5).reshape(cfg.G * cfg.O, K)
+    (refb * D[:, :K].double()).sum().backward()
+    assert rel_err(dw.cpu(), wv.grad) < 1e-5
+    ref_db = D[:, K].view(cfg.G, cfg.O).sum(0)
+    assert rel_err(db.cpu(), ref_db) < 1e-5
+
+
+def _encoder_inputs(cfg, B):
+    ops = _ops()
+    enc, gen, x, y, ctf, nz = oracle_inputs(cfg, B, dtype=torch.float64, requires_grad=True)
+    s = ops.enc_shape(B, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
+    p_r = ops.rotation_log_prior(cfg.G, cfg.rot_refinement, cfg.normal_prior_over_r, cfg.theta_prior)
+    offs = ops.rotation_offsets(cfg.G, cfg.rot_refinement)
+    t = lambda v: v.detach().float().to(DEV)
+    wh, bh, add = ops.head_tables(t(enc.conv_a_w), t(enc.conv_a_b), t(enc.conv_r_w), t(enc.conv_r_b), t(enc.conv_z_w),
+                                  t(enc.conv_z_b), cfg.G, p_r, offs, DEV)
+    return ops, enc, y, nz, s, wh, bh, add, t
+
+
+def _oracle_heads(cfg, enc, y):
+    attn, theta, z = orc.encoder_head_maps(y, enc, cfg.G, cfg.p)
+    dt = y.dtype
+    attn = attn + orc.rotation_log_prior(cfg.G, cfg.rot_refinement, cfg.normal_prior_over_r, cfg.theta_prior, dt)
+    offs = orc.rotation_offsets(cfg.G, cfg.rot_refinement, dt)
+    theta = torch.stack((theta[:, 0] + offs.view(1, cfg.G, 1, 1), theta[:, 1]), 1)
+    B = y.shape[0]
+    return torch.cat([attn.unsqueeze(1), theta, z], 1).reshape(B, 3 + 2 * cfg.z, cfg.G, -1)
+
+
+@pytest.mark.parametrize("cfg", small_cfgs(), ids=lambda c: c.name)
+def test_encoder_fwd_bwd(cfg):
+    B = 3
+    ops, enc, y, nz, s, wh, bh, add, t = _encoder_inputs(cfg, B)
+    bank = ops.filter_bank_fwd(s, t(enc.conv1_w))
+    x1, h, heads = ops.encoder_fwd(s, t(y), bank, t(enc.conv1_b), t(enc.conv2_w).view(cfg.O, cfg.O), t(enc.conv2_b), wh, bh, add)
+    torch.cuda.synchronize()
+    ref_heads = _oracle_heads(cfg, enc, y)
+    # conv1 activation, internal layout [(b*G + r)*P + pos][O]
+    ref_x1 = F.leaky_relu(orc.groupconv_forward(y, enc.conv1_w, enc.conv1_b, cfg.G, cfg.p), 0.01)  # (B,O,G,H,W)
+    ref_x1 = ref_x1.permute(0, 2, 3, 4, 1).reshape(-1, cfg.O)
+    e1 = rel_err(x1.cpu(), ref_x1.detach())
+    eh = rel_err(heads.cpu(), ref_heads.detach())
+    print(f"{cfg.name}: conv1 rel err {e1:.2e}, heads rel err {eh:.2e}")
+    assert e1 < 3e-3
+    assert eh < 3e-3
+    # backward against autograd of the oracle (same activation pattern) for a random cotangent on the head maps
+    g = torch.Generator().manual_seed(2)
+    D = torch.randn(ref_heads.shape, generator=g, dtype=torch.float64)
+    d = cfg.Hout
+    to_ref = lambda a: a.cpu().double().view(B, cfg.G, d, d, cfg.O).permute(0, 4, 1, 2, 3)
+    with ForcedActivations([to_ref(x1), to_ref(h)]):
+        forced_heads = _oracle_heads(cfg, enc, y)
+    (forced_heads * D).sum().backward()
+    dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, t(y), t(enc.conv2_w).view(cfg.O, cfg.O), wh, x1, h, D.float().to(DEV))
+    dw1, db1 = ops.filter_bank_bwd(s, dbank)
+    torch.cuda.synchronize()
+    NH = 3 + 2 * cfg.z
+    ref_dwh = torch.cat([enc.conv_a_w.grad.view(1, -1), enc.conv_r_w.grad.view(2, -1), enc.conv_z_w.grad.view(NH - 3, -1)], 0)
+    ref_dbh = torch.cat([enc.conv_a_b.grad.view(1), enc.conv_r_b.grad.view(2), enc.conv_z_b.grad.view(-1)], 0)
+    errs = {
+        "dwh": rel_err(dwh.cpu(), ref_dwh), "dbh": rel_err(dbh.cpu(), ref_dbh),
+        "dw2": rel_err(dw2.cpu(), enc.conv2_w.grad.view(cfg.O, cfg.O)), "db2": rel_err(db2.cpu(), enc.conv2_b.grad),
+        "dw1": rel_err(dw1.cpu(), enc.conv1_w.grad), "db1": rel_err(db1.cpu(), enc.conv1_b.grad),
+    }
+    print(f"{cfg.name}: encoder grad rel errs {errs}")
+    for k, v in errs.items():
+        assert v < 5e-3, (k, v)
+
+
+def _enc_out_from_heads(heads, cfg, gumbel, dt):
+    B = heads.shape[0]
+    d = cfg.Hout
+    attn = heads[:, 0].reshape(B, cfg.G, d, d)
+    theta = heads[:, 1:3].reshape(B, 2, cfg.G, d, d)
+    z = heads[:, 3:].reshape(B, 2 * cfg.z, cfg.G, d, d)
+    q = F.log_softmax(attn.reshape(B, -1), 1).view_as(attn)
+    a = F.softmax(attn.reshape(B, -1) + gumbel, 1).view_as(attn)
+    p_r = orc.rotation_log_prior(cfg.G, cfg.rot_refinement, cfg.normal_prior_over_r, cfg.theta_prior, dt)
+    offs = orc.rotation_offsets(cfg.G, cfg.rot_refinement, dt)
+    return attn, q, p_r, a, offs, theta, z
+
+
+@pytest.mark.parametrize("cfg", small_cfgs(), ids=lambda c: c.name)
+def test_attention_fwd_bwd(cfg):
+    ops = _ops()
+    B, d = 4, cfg.Hout
+    NH = 3 + 2 * cfg.z
+    g = torch.Generator().manual_seed(3)
+    heads = (torch.randn(B, NH, cfg.G, d * d, generator=g, dtype=torch.float64) * 0.7).requires_grad_(True)
+    from tvae_b200 import synth
+    nz = {k: torch.from_numpy(v).double() for k, v in synth.noise(cfg, B, 5).items()}
+    x = orc.image_coords(cfg.n, torch.float64)
+    enc_out = _enc_out_from_heads(heads, cfg, nz["gumbel"], torch.float64)
+    z_b, theta_b, dx, x_t, kl = orc.attention_posterior(enc_out, x, nz["r_z"], nz["r_theta"], cfg.G, cfg.G, cfg.theta_prior)
+    spacing = float(x[1, 0] - x[0, 0])
+    offs = ops.rotation_offsets(cfg.G, cfg.rot_refinement)
+    p_r = ops.rotation_log_prior(cfg.G, cfg.rot_refinement, cfg.normal_prior_over_r, cfg.theta_prior)
+    s = ops.attn_shape(B, cfg.G, d, cfg.z, spacing, offs)
+    lp = ops.attn_log_prior(s, p_r, DEV)
+    hg = heads.detach().float().to(DEV)
+    gum, rz, rth = nz["gumbel"].float().to(DEV), nz["r_z"][:, :, 0].float().contiguous().to(DEV), nz["r_theta"].view(B).float().to(DEV)
+    out = ops.attn_fwd(s, hg, gum, rz, rth, lp)
+    torch.cuda.synchronize()
+    assert rel_err(out["zb"].cpu(), z_b.detach()) < 1e-4
+    assert rel_err(out["theta_b"].cpu(), theta_b.detach()) < 1e-4
+    assert rel_err(out["dx"].cpu(), dx.detach().view(B, 2)) < 1e-4
+    assert abs(float(out["kl"].double().mean().cpu()) - float(kl.detach())) < 1e-4 * abs(float(kl.detach()))
+    # module-interface tail
+    q, a = ops.attn_softmax_pair(hg, gum)
+    assert rel_err(q.cpu(), enc_out[1].detach().reshape(B, -1)) < 1e-5
+    assert rel_err(a.cpu(), enc_out[3].detach().reshape(B, -1)) < 1e-4
+    # backward: random cotangents on (z_b, theta_b, dx) and weight g_kl on the per-image KL
+    gz = torch.randn(B, cfg.z, generator=g, dtype=torch.float64)
+    gt = torch.randn(B, generator=g, dtype=torch.float64)
+    gd = torch.randn(B, 2, generator=g, dtype=torch.float64)
+    loss = (z_b * gz).sum() + (theta_b * gt).sum() + (dx.view(B, 2) * gd).sum() + kl
+    loss.backward()
+    gkl = torch.full((1,), 1.0 / B, device=DEV)
+    dh = ops.attn_bwd(s, hg, gum, rz, rth, lp, out, gz.float().to(DEV), gt.float().to(DEV), gd.float().to(DEV), gkl)
+    torch.cuda.synchronize()
+    e = rel_err(dh.cpu(), heads.grad)
+    print(f"{cfg.name}: attention d_heads rel err {e:.2e}")
+    assert e < 2e-4
+    # get_latent
+    zc, th, dxl, am = ops.get_latent(s, hg)
+    attn = heads.detach()[:, 0].reshape(B, -1)
+    ind = attn.argmax(1)
+    assert torch.equal(am.cpu().long(), ind)
+    ar = torch.arange(B)
+    hv = heads.detach().reshape(B, NH, -1)
+    ref_zc = torch.cat([hv[ar, 3:3 + cfg.z, ind], torch.exp(hv[ar, 3 + cfg.z:, ind])], 1)
+    assert rel_err(zc.cpu(), ref_zc) < 1e-5
+    assert rel_err(th.cpu().view(B), hv[ar, 1, ind]) < 1e-6
+    ref_dx = F.softmax(attn, 1).view(B, cfg.G, d * d).sum(1) @ orc.translation_grid(d, x[1, 0] - x[0, 0], torch.float64)
+    assert rel_err(dxl.cpu(), ref_dx) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", small_cfgs(), ids=lambda c: c.name)
+@pytest.mark.parametrize("explicit_coords", [False, True])
+def test_generator_fwd_bwd(cfg, explicit_coords):
+    ops = _ops()
+    B = 3
+    enc, gen, x, y, ctf, nz = oracle_inputs(cfg, B, dtype=torch.float64, requires_grad=True)
+    g = torch.Generator().manual_seed(4)
+    theta = (torch.randn(B, generator=g, dtype=torch.float64)).requires_grad_(True)
+    dx = (torch.randn(B, 2, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    zb = torch.randn(B, cfg.z, generator=g, dtype=torch.float64).requires_grad_(True)
+    c, sn = torch.cos(theta), torch.sin(theta)
+    rot = torch.stack([torch.stack([c, sn], 1), torch.stack([-sn, c], 1)], 1)
+    xt = torch.bmm(x.expand(B, -1, 2) - dx.unsqueeze(1), rot)
+    if explicit_coords:
+        xt = xt.detach().requires_grad_(True)
+    y_ref = orc.generator_forward(xt, zb, gen)
+    t = lambda v: v.detach().float().to(DEV)
+    wf = None if gen.fourier_w is None else t(gen.fourier_w / torch.tensor(gen.sigma, dtype=torch.float32).double())
+    if wf is not None:
+        # the product divides in fp32 like the reference (models.py:57)
+        wf = (gen.fourier_w.float() / torch.tensor(gen.sigma, dtype=torch.float32)).to(DEV)
+    gw = ops.GenWeights(wf, None if gen.fourier_b is None else t(gen.fourier_b), t(gen.coord_w), t(gen.coord_b), t(gen.latent_w),
+                        [t(w) for w in gen.hidden_w], [t(b) for b in gen.hidden_b], t(gen.out_w), t(gen.out_b))
+    N = cfg.n ** 2
+    s = ops.gen_shape(B, N, gw, cfg.z)
+    if explicit_coords:
+        xin, th_in, dx_in = t(xt).reshape(B * N, 2), None, None
+    else:
+        xin, th_in, dx_in = t(x), t(theta), t(dx)
+    y_hat, saved = ops.generator_fwd(s, gw, xin, th_in, dx_in, t(zb))
+    torch.cuda.synchronize()
+    e = rel_err(y_hat.cpu().view(B, N, -1), y_ref.detach())
+    print(f"{cfg.name} explicit={explicit_coords}: generator y_hat rel err {e:.2e}")
+    assert e < 5e-3
+    D = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    with ForcedActivations([a.cpu().double() for a in saved["acts"]]):
+        y_forced = orc.generator_forward(xt, zb, gen)
+    (y_forced * D).sum().backward()
+    out = ops.generator_bwd(s, gw, xin, th_in, dx_in, t(zb), saved, y_hat, D.float().to(DEV).reshape(B * N, -1))
+    torch.cuda.synchronize()
+    errs = {
+        "dw1": rel_err(out["dw1"].cpu(), gen.coord_w.grad), "db1": rel_err(out["db1"].cpu(), gen.coord_b.grad),
+        "dwz": rel_err(out["dwz"].cpu(), gen.latent_w.grad), "dwout": rel_err(out["dwout"].cpu(), gen.out_w.grad),
+        "dbout": rel_err(out["dbout"].cpu(), gen.out_b.grad), "d_z": rel_err(out["d_z"].cpu(), zb.grad),
+    }
+    for i, (w, b) in enumerate(zip(gen.hidden_w, gen.hidden_b)):
+        errs[f"dwh{i}"] = rel_err(out["dwh"][i].cpu(), w.grad)
+        errs[f"dbh{i}"] = rel_err(out["dbh"][i].cpu(), b.grad)
+    if explicit_coords:
+        errs["dxp"] = rel_err(out["dxp"].cpu().view(B, N, 2), xt.grad)
+    else:
+        errs["d_theta"] = rel_err(out["d_theta"].cpu(), theta.grad)
+        errs["d_dx"] = rel_err(out["d_dx"].cpu(), dx.grad)
+    print(f"{cfg.name} explicit={explicit_coords}: generator grad rel errs " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < 5e-3, (k, v)
+
+
+def test_bernoulli_and_gaussian():
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    B, n = 3, 20
+    yh = torch.randn(B, n * n, generator=g, dtype=torch.float64).requires_grad_(True)
+    y = torch.rand(B, n * n, generator=g, dtype=torch.float64)
+    ll_ref = -(F.binary_cross_entropy_with_logits(yh, y, reduction="none")).sum(1)
+    gsc = torch.tensor([-1.0 / B], device=DEV)
+    ll, d = ops.bernoulli(yh.detach().float().to(DEV), y.float().to(DEV), gsc)
+    (ll_ref.sum() * (-1.0 / B)).backward()
+    assert rel_err(ll.cpu(), ll_ref.detach()) < 1e-5
+    assert rel_err(d.cpu(), yh.grad) < 1e-5
+    # gaussian + CTF (+ mask)
+    from tvae_b200 import synth
+    import numpy as np
+    ctf = torch.from_numpy(synth.ctf_kernels(np.random.default_rng(0), B, n)).double()
+    for radius in (0, 6):
+        yh = torch.randn(B, n * n, generator=g, dtype=torch.float64).requires_grad_(True)
+        yy = torch.randn(B, n * n, generator=g, dtype=torch.float64)
+        dx = torch.randn(B, 1, 2, generator=g, dtype=torch.float64) * 0.1
+        s = torch.tensor(2.0 / (n - 1), dtype=torch.float32)
+        mask = orc.particle_mask(dx, s, n, radius) if radius else None
+        mu = F.conv2d(yh.view(1, B, n, n), ctf, padding=(n - 1) // 2, groups=B).view(B, -1)
+        diff = mu - yy
+        if mask is not None:
+            diff = torch.where(mask, diff, torch.zeros_like(diff))
+        ll_ref = -0.5 * (diff ** 2).sum(1)
+        (ll_ref.sum() * (-1.0 / B)).backward()
+        ll, d = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
+                             dx.view(B, 2).float().to(DEV), float(s), radius, gsc)
+        torch.cuda.synchronize()
+        assert rel_err(ll.cpu(), ll_ref.detach()) < 1e-4, radius
+        assert rel_err(d.cpu(), yh.grad) < 1e-4, radius
