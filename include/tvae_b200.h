@@ -25,6 +25,7 @@ extern "C" {
 
 const char* tvae_last_error(void);
 int tvae_version(void);
+long long tvae_launch_count(void);   /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------ encoder (models.py:132-225, 326-403) */
 typedef struct {
@@ -39,6 +40,11 @@ int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* ba
 /* adjoint of the above plus conv1 bias gradient from the ones column: dbank [G*O][kpad] ->
  * dweight (O,C,1,k,k), dbias (O).  Both outputs are overwritten. */
 int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dweight, float* dbias, void* stream);
+
+/* GroupConv.forward alone (models.py:202-225): out [(b*G + r)*P + pos][O] = conv + bias, no activation.
+ * bias may be NULL.  tvae_groupconv_wgrad: dout in the same layout -> dbank [G*O][kpad] (overwritten). */
+int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream);
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, float* dbank, void* stream);
 
 typedef struct {
     const float* y;          /* (B,C,n,n) */

@@ -39,9 +39,12 @@ def _import_reference():
     for m in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.axes_grid1", "seaborn",
               "astropy", "astropy.stats", "astropy.units"):
         sys.modules.setdefault(m, mock.MagicMock())
-    # the product package also ships a `src` mirror: make sure the reference's wins here
+    # the product package also ships a `src` mirror (a regular package, which would shadow the reference's
+    # namespace package `src`): take it off sys.path while the reference is imported
     for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
         del sys.modules[k]
+    pkg = os.path.join(ROOT, "target-vae_b200")
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != pkg]
     sys.path.insert(0, REF)
     import src.models as ref_models
     import train_mnist, train_dsprites, train_galaxy, train_particles, clustering_mnist
@@ -53,15 +56,15 @@ def _import_reference():
 CASES = {
     # name: (trainer, cfg, B)
     "g1_mnist": ("mnist", HotPathConfig("cfg1_g", C=1, n=20, k=9, p=3, G=8, z=2, O=32, hidden=64), 3),
-    "g2_dsprites": ("dsprites", HotPathConfig("cfg2_g", C=1, n=16, k=16, p=8, G=4, z=2, O=16, hidden=64,
+    "g2_dsprites": ("dsprites", HotPathConfig("cfg2_g", C=1, n=16, k=16, p=8, G=4, z=2, O=32, hidden=64,
                                               fourier=False, normal_prior_over_r=True), 2),
-    "g3_galaxy": ("galaxy", HotPathConfig("cfg3_g", C=3, n=12, k=12, p=6, G=8, z=3, O=16, hidden=32,
+    "g3_galaxy": ("galaxy", HotPathConfig("cfg3_g", C=3, n=12, k=12, p=6, G=8, z=3, O=32, hidden=32,
                                           gen_layers=4, n_out=3, likelihood="bernoulli_rgb"), 2),
-    "g4_particles_ctf": ("particles", HotPathConfig("cfg4_g", C=1, n=16, k=9, p=2, G=16, z=8, O=16, hidden=32,
+    "g4_particles_ctf": ("particles", HotPathConfig("cfg4_g", C=1, n=16, k=9, p=2, G=16, z=8, O=32, hidden=32,
                                                     likelihood="gaussian", ctf=True), 3),
-    "g5_particles_mask": ("particles", HotPathConfig("cfg4_gm", C=1, n=16, k=9, p=2, G=8, z=2, O=16, hidden=32,
+    "g5_particles_mask": ("particles", HotPathConfig("cfg4_gm", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                      likelihood="gaussian", ctf=True, mask_radius=5), 2),
-    "g6_mnist_noref": ("mnist", HotPathConfig("cfg1_gn", C=1, n=14, k=7, p=2, G=4, z=2, O=16, hidden=32,
+    "g6_mnist_noref": ("mnist", HotPathConfig("cfg1_gn", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=32,
                                               rot_refinement=False), 2),
 }
 

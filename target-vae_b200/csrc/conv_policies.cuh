@@ -60,6 +60,7 @@ struct Conv1FwdParams {
     const float* bias;        // (O)
     float* x1;                // [(b*G + r)*P + pos][O]
     int slab_rows_max;
+    int act;                  // 1: LeakyReLU + tf32 rounding (encoder path), 0: raw conv + bias (GroupConv.forward)
 };
 
 template <int BN>
@@ -146,10 +147,13 @@ struct Conv1Fwd : PolicyBase {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 t;
-                t.x = to_tf32(lrelu(__uint_as_float(rr[j]) + __ldg(bs + j)));
-                t.y = to_tf32(lrelu(__uint_as_float(rr[j + 1]) + __ldg(bs + j + 1)));
-                t.z = to_tf32(lrelu(__uint_as_float(rr[j + 2]) + __ldg(bs + j + 2)));
-                t.w = to_tf32(lrelu(__uint_as_float(rr[j + 3]) + __ldg(bs + j + 3)));
+                t.x = __uint_as_float(rr[j]) + (p.bias ? __ldg(bs + j) : 0.f);
+                t.y = __uint_as_float(rr[j + 1]) + (p.bias ? __ldg(bs + j + 1) : 0.f);
+                t.z = __uint_as_float(rr[j + 2]) + (p.bias ? __ldg(bs + j + 2) : 0.f);
+                t.w = __uint_as_float(rr[j + 3]) + (p.bias ? __ldg(bs + j + 3) : 0.f);
+                if (p.act) {
+                    t.x = to_tf32(lrelu(t.x)); t.y = to_tf32(lrelu(t.y)); t.z = to_tf32(lrelu(t.z)); t.w = to_tf32(lrelu(t.w));
+                }
                 *reinterpret_cast<float4*>(dst + j) = t;
             }
         }

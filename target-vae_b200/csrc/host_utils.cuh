@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace tvae {
 
 inline thread_local std::string g_last_error;
+inline std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py reports it)
 
 inline int fail(int code, const std::string& msg) {
     g_last_error = msg;

@@ -29,6 +29,7 @@ inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t st
     }
     const int threads = (kCtrlWarps + kEpiWarps + P::kProdWarps) * 32;
     const int grid = prm.num_tiles < sm_count() ? prm.num_tiles : sm_count();
+    ++g_launch_count;
     tc_gemm_kernel<P><<<grid, threads, L.total, stream>>>(prm);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;

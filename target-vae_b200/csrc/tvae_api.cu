@@ -73,6 +73,7 @@ extern "C" {
 
 const char* tvae_last_error(void) { return g_last_error.c_str(); }
 int tvae_version(void) { return 100; }
+long long tvae_launch_count(void) { return g_launch_count.load(); }
 
 int tvae_bank_pitch(int C, int k) {
     const int K = C * k * k;
@@ -84,7 +85,7 @@ int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* ba
     int rc = check_enc_shape(s);
     if (rc) return rc;
     const long long total = (long long)s->G * s->O * s->kpad;
-    filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, bank, s->O, s->C, s->k, s->G, s->kpad, make_rot_table(s->G));
+    ++g_launch_count; filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, bank, s->O, s->C, s->k, s->G, s->kpad, make_rot_table(s->G));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -95,13 +96,73 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
     const int K = s->C * s->k * s->k;
     TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
     const long long total = (long long)s->G * s->O * K;
-    filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
-    if (dbias) bank_bias_grad_kernel<<<cdiv(s->O, 128), 128, 0, S(stream)>>>(dbank, dbias, s->O, s->G, s->kpad, K);
+    ++g_launch_count; filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    if (dbias) { ++g_launch_count; bank_bias_grad_kernel<<<cdiv(s->O, 128), 128, 0, S(stream)>>>(dbank, dbias, s->O, s->G, s->kpad, K); }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 // ================================================================================ encoder
+}  // extern "C"
+
+namespace {
+// conv1: implicit GEMM with generated im2col operand
+int conv1_forward(const ConvGeom& g, const float* y, const float* bank, const float* bias, float* x1, int act, cudaStream_t st) {
+    Conv1FwdParams p{};
+    const int N = g.G * g.O;
+    const bool wide = N > 128;
+    const int BN = wide ? 256 : 128;
+    int rc;
+    if ((rc = make_tmap_2d(&p.tmB, bank, N, g.kpad, g.kpad, BN))) return rc;
+    p.g = g;
+    p.y = y; p.bias = bias; p.x1 = x1; p.act = act;
+    p.tiles_n = cdiv(N, BN);
+    p.tiles_per_image = cdiv(g.P, kBM);
+    p.k_chunks = cdiv(g.K, kBK);
+    p.num_tiles = g.B * p.tiles_per_image * p.tiles_n;
+    const int span_rows = (kBM - 1) / g.d + 2;
+    int slab_rows = span_rows + g.k - 1;
+    if (slab_rows > g.n) slab_rows = g.n;
+    p.slab_rows_max = slab_rows;
+    const int extra = g.C * slab_rows * g.n * static_cast<int>(sizeof(float));
+    return wide ? launch_gemm<Conv1Fwd<256>>(p, extra, st) : launch_gemm<Conv1Fwd<128>>(p, extra, st);
+}
+// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed)
+int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dbank, cudaStream_t st) {
+    Conv1WgradParams p{};
+    const int N = g.G * g.O;
+    const long long R = (long long)g.B * g.G * g.P;
+    const bool wide = N > 128;
+    const int BN = wide ? 256 : 128;
+    int rc;
+    if ((rc = make_tmap_2d(&p.tmQ, dx1, R, g.O, g.O, kBK, true))) return rc;
+    p.g = g; p.y = y; p.dbank = dbank;
+    p.tiles_m = cdiv(g.K + 1, kBM);     // + ones column
+    p.tiles_n = cdiv(N, BN);
+    p.chunks_per_image = cdiv(g.P, kBK);
+    const int extra = g.C * g.n * g.n * static_cast<int>(sizeof(float));
+    const int out_tiles = p.tiles_m * p.tiles_n;
+    return wide ? launch_split_tn<Conv1Wgrad<256>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st)
+                : launch_split_tn<Conv1Wgrad<128>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st);
+}
+}  // namespace
+
+extern "C" {
+
+int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    return conv1_forward(make_geom(s), y, bank, bias, out, 0, S(stream));
+}
+
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, float* dbank, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    const ConvGeom g = make_geom(s);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(dbank, 0, sizeof(float) * g.G * g.O * g.kpad, S(stream)));
+    return conv1_wgrad(g, y, dout, dbank, S(stream));
+}
+
 int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
@@ -109,31 +170,10 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
     const int NH = 3 + 2 * s->z;
     const long long R = (long long)g.B * g.G * g.P;
     cudaStream_t st = S(stream);
-
-    // ---- conv1: implicit GEMM with generated im2col operand
-    {
-        Conv1FwdParams p{};
-        const int N = g.G * g.O;
-        const bool wide = N > 128;
-        const int BN = wide ? 256 : 128;
-        if ((rc = make_tmap_2d(&p.tmB, a->bank, N, g.kpad, g.kpad, BN))) return rc;
-        p.g = g;
-        p.y = a->y; p.bias = a->conv1_bias; p.x1 = a->x1;
-        p.tiles_n = cdiv(N, BN);
-        p.tiles_per_image = cdiv(g.P, kBM);
-        p.k_chunks = cdiv(g.K, kBK);
-        p.num_tiles = g.B * p.tiles_per_image * p.tiles_n;
-        const int span_rows = (kBM - 1) / g.d + 2;
-        int slab_rows = span_rows + g.k - 1;
-        if (slab_rows > g.n) slab_rows = g.n;
-        p.slab_rows_max = slab_rows;
-        const int extra = g.C * slab_rows * g.n * static_cast<int>(sizeof(float));
-        rc = wide ? launch_gemm<Conv1Fwd<256>>(p, extra, st) : launch_gemm<Conv1Fwd<128>>(p, extra, st);
-        if (rc) return rc;
-    }
+    if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, a->x1, 1, st))) return rc;
     // ---- conv2 (1x1x1) + heads
     {
-        round_tf32_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2_tf32, (long long)g.O * g.O);
+        ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2_tf32, (long long)g.O * g.O);
         Conv2HeadsParams p{};
         const bool wide = g.O > 128;
         const int BN = wide ? 256 : 128;
@@ -179,13 +219,13 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         p.dt_chan = (long long)g.G * g.P;         // stride of channel j
         const int grid = cdiv(R, p.rows_per_cta);
         const size_t sm = 64 * NH * sizeof(float);
-        thin_bwd_heads_kernel<<<grid, g.O, sm, st>>>(p, g.G);
+        ++g_launch_count; thin_bwd_heads_kernel<<<grid, g.O, sm, st>>>(p, g.G);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     // ---- dW2 = dhpre^T x1
     if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st))) return rc;
     // ---- dx1pre = (dhpre W2) * lrelu'(x1), in place over x1
-    transpose_round_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2t_tf32, g.O, g.O, 1);
+    ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2t_tf32, g.O, g.O, 1);
     {
         LinearNTArgs l{};
         l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_tf32; l.ldb = g.O;
@@ -194,23 +234,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         if ((rc = linear_nt(l, st))) return rc;
     }
     // ---- conv1 weight gradient (w.r.t. the rotated bank)
-    {
-        Conv1WgradParams p{};
-        const int N = g.G * g.O;
-        const bool wide = N > 128;
-        const int BN = wide ? 256 : 128;
-        if ((rc = make_tmap_2d(&p.tmQ, a->x1, R, g.O, g.O, kBK, true))) return rc;
-        p.g = g; p.y = a->y; p.dbank = a->dbank;
-        p.tiles_m = cdiv(g.K + 1, kBM);     // + ones column
-        p.tiles_n = cdiv(N, BN);
-        p.chunks_per_image = cdiv(g.P, kBK);
-        const int extra = g.C * g.n * g.n * static_cast<int>(sizeof(float));
-        const int out_tiles = p.tiles_m * p.tiles_n;
-        rc = wide ? launch_split_tn<Conv1Wgrad<256>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st)
-                  : launch_split_tn<Conv1Wgrad<128>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st);
-        if (rc) return rc;
-    }
-    return 0;
+    return conv1_wgrad(g, a->y, a->x1, a->dbank, st);
 }
 
 // ================================================================================ attention
@@ -226,7 +250,7 @@ static AttnParams to_attn_params(const tvae_attn_shape* s, const tvae_attn_fwd_a
 int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float* log_prior, void* stream) {
     RotTable t{};
     for (int i = 0; i < s->G && i < kMaxG; ++i) t.cs[i] = p_r_host16[i];
-    log_prior_kernel<<<1, 1024, 0, S(stream)>>>(log_prior, s->G, s->d, s->s, t);
+    ++g_launch_count; log_prior_kernel<<<1, 1024, 0, S(stream)>>>(log_prior, s->G, s->d, s->s, t);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -248,6 +272,7 @@ int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float
 int tvae_attn_fwd(const tvae_attn_shape* s, const tvae_attn_fwd_args* a, void* stream) {
     TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG && s->d >= 1 && s->B >= 1, "attention: bad shape");
     const AttnParams p = to_attn_params(s, a);
+    ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (attn_fwd_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(p)));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -263,18 +288,20 @@ int tvae_attn_bwd(const tvae_attn_shape* s, const tvae_attn_bwd_args* a, void* s
     for (int i = 0; i < kMaxG; ++i) p.offsets[i] = s->offsets[i];
     const int L = s->G * s->d * s->d;
     dim3 grid(blocks_for(L, 256, 64), s->B);
+    ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ><<<grid, 256, 0, S(stream)>>>(p)));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int tvae_attn_softmax_pair(const float* heads, const float* gumbel, float* q_t_r, float* a_sampled, int B, int NH, int L, void* stream) {
-    softmax_pair_kernel<<<B, 1024, 0, S(stream)>>>(heads, gumbel, q_t_r, a_sampled, NH, L);
+    ++g_launch_count; softmax_pair_kernel<<<B, 1024, 0, S(stream)>>>(heads, gumbel, q_t_r, a_sampled, NH, L);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int tvae_get_latent(const tvae_attn_shape* s, const float* heads, float* z_content, float* theta_mu, float* dx, int* argmax, void* stream) {
+    ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (get_latent_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(heads, s->G, s->d, s->s, z_content, theta_mu, dx, argmax)));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -303,13 +330,13 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     const long long M = (long long)s->B * s->N;
     const int H = s->H, E = s->E;
     const CoordXform cx = make_xform(s, a);
-    latent_bias_kernel<<<cdiv(s->B * H, 256), 256, 0, st>>>(a->z, a->wz, a->zb, s->B, H, s->zdim);
+    ++g_launch_count; latent_bias_kernel<<<cdiv(s->B * H, 256), 256, 0, st>>>(a->z, a->wz, a->zb, s->B, H, s->zdim);
     float* w1r = a->w_tf32;                              // [H][E]
     float* whr = a->w_tf32 + (long long)H * (E > 0 ? E : 2);   // [L][H][H]
-    if (s->L > 0) round_tf32_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whr, (long long)s->L * H * H);
+    if (s->L > 0) { ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whr, (long long)s->L * H * H); }
     float* a0 = a->acts;
     if (E > 0) {
-        round_tf32_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1r, (long long)H * E);
+        ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1r, (long long)H * E);
         GenL1FwdParams p{};
         const bool wide = H > 128;
         const int BN = wide ? 256 : 128;
@@ -324,11 +351,11 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         if (rc) return rc;
     } else {
         const int rows_per_cta = 64;
-        coord_layer_fwd_kernel<<<cdiv(M, rows_per_cta), H, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, rows_per_cta);
+        ++g_launch_count; coord_layer_fwd_kernel<<<cdiv(M, rows_per_cta), H, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, rows_per_cta);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (s->L == 0) {
-        thin_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(a0, a->wout, a->bout, a->y_hat, M, H, s->n_out);
+        ++g_launch_count; thin_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(a0, a->wout, a->bout, a->y_hat, M, H, s->n_out);
         TVAE_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
@@ -372,7 +399,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         p.dWt = a->dwout; p.dbt = a->dbout; p.dcol = (L > 0) ? a->dbh + (long long)(L - 1) * H : nullptr;
         p.M = M; p.W = H; p.T = s->n_out; p.P = 1; p.dt_outer = s->n_out; p.dt_chan = 1;
         p.rows_per_cta = 1024;
-        thin_bwd_kernel<4><<<cdiv(M, p.rows_per_cta), H, 64 * s->n_out * sizeof(float), st>>>(p);
+        ++g_launch_count; thin_bwd_kernel<4><<<cdiv(M, p.rows_per_cta), H, 64 * s->n_out * sizeof(float), st>>>(p);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     // ---- hidden layers, last to first
@@ -380,7 +407,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         const float* a_prev = a->f.acts + (long long)(i - 1) * M * H;
         const float* w = a->f.wh + (long long)(i - 1) * H * H;
         if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st))) return rc;
-        transpose_round_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, a->wt_tf32, H, H, 1);
+        ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, a->wt_tf32, H, H, 1);
         LinearNTArgs l{};
         l.A = dcur; l.lda = H; l.B = a->wt_tf32; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
@@ -388,13 +415,13 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         if ((rc = linear_nt(l, st))) return rc;
         float* t = dcur; dcur = dnext; dnext = t;
         if (i - 1 >= 1) {
-            group_colsum_kernel<<<dim3(cdiv(M, 2048), 1), H, 0, st>>>(dcur, nullptr, a->dbh + (long long)(i - 2) * H, static_cast<int>(M), H, 2048);
+            ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(M, 2048), 1), H, 0, st>>>(dcur, nullptr, a->dbh + (long long)(i - 2) * H, static_cast<int>(M), H, 2048);
             TVAE_CHECK_CUDA(cudaGetLastError());
         }
     }
     // ---- dcur == dpre of layer 1: bias / latent-bias gradients
-    group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->dzb, a->db1, s->N, H, 512);
-    latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
+    ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->dzb, a->db1, s->N, H, 512);
+    ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
     TVAE_CHECK_CUDA(cudaGetLastError());
     // ---- layer 1 weight and coordinate gradients
     if (E > 0) {
@@ -414,7 +441,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         }
         {
             TVAE_CHECK_CUDA(cudaMemsetAsync(a->dxp, 0, sizeof(float) * M * 2, st));
-            transpose_round_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->f.w1, a->wt_tf32, H, E, 1);   // -> [E][H]
+            ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->f.w1, a->wt_tf32, H, E, 1);   // -> [E][H]
             GenL1DgradParams p{};
             const bool wide = E > 128;
             const int BN = wide ? 256 : 128;
@@ -429,12 +456,12 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
             if (rc) return rc;
         }
     } else {
-        coord_layer_bwd_w_kernel<<<cdiv(M, 2048), H, 0, st>>>(cx, dcur, a->dw1, H, 2048);
-        coord_layer_bwd_x_kernel<<<cdiv(M, 8), 256, 0, st>>>(a->f.w1, dcur, a->dxp, M, H);
+        ++g_launch_count; coord_layer_bwd_w_kernel<<<cdiv(M, 2048), H, 0, st>>>(cx, dcur, a->dw1, H, 2048);
+        ++g_launch_count; coord_layer_bwd_x_kernel<<<cdiv(M, 8), 256, 0, st>>>(a->f.w1, dcur, a->dxp, M, H);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (a->f.theta && a->d_theta) {
-        coord_xform_bwd_kernel<<<s->B, 256, 0, st>>>(cx, a->dxp, a->d_theta, a->d_dx);
+        ++g_launch_count; coord_xform_bwd_kernel<<<s->B, 256, 0, st>>>(cx, a->dxp, a->d_theta, a->d_dx);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -445,7 +472,7 @@ int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat,
     cudaStream_t st = S(stream);
     TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
     dim3 grid(blocks_for(E, 256, 32), B);
-    bernoulli_kernel<<<grid, 256, 0, st>>>(y_hat, y, ll, d_yhat, E, g);
+    ++g_launch_count; bernoulli_kernel<<<grid, 256, 0, st>>>(y_hat, y, ll, d_yhat, E, g);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -466,13 +493,13 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
             TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             cfg = true;
         }
-        ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n);
+        ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n);
         mu_in = mu;
     }
     dim3 grid(blocks_for(n * n, 256, 32), B);
     float* dmu_out = d_yhat ? (ctf ? dmu : d_yhat) : nullptr;
-    gaussian_kernel<<<grid, 256, 0, st>>>(mu_in, y, dx, s, n, radius, ll, dmu_out, g);
-    if (ctf && d_yhat) ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n);
+    ++g_launch_count; gaussian_kernel<<<grid, 256, 0, st>>>(mu_in, y, dx, s, n, radius, ll, dmu_out, g);
+    if (ctf && d_yhat) { ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n); }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

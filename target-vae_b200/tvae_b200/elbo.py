@@ -1,0 +1,86 @@
+"""Fused `eval_minibatch` for the attention/attention(+offsets) branch - the reference's ELBO call site
+(train_mnist.py:26-294, train_dsprites.py:27-295, train_galaxy.py:27-295, train_particles.py:28-343) as one
+autograd node over the sm_100a kernels.
+
+    elbo, log_p_x_g_z, kl_div = eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
+                                               theta_prior, groupconv, image_dim)
+    (-elbo).backward()
+
+Same positional signature, same return triple (0-d tensors on `device` with an autograd graph that populates
+`.grad` of every generator / encoder parameter).  `eval_minibatch_particles` takes the particle trainer's
+signature (ctf, padding, mask_radius).  Noise: by default drawn on the device from torch's generator with the
+distributions the reference uses (Gumbel via -log(Exp(1)), N(0,1)); pass `noise=dict(gumbel, r_z, r_theta)` for
+identical-input parity runs.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as TF
+
+
+def draw_noise(B, L, z, device, generator=None):
+    """Same draws as models.py:387 (gumbel_softmax) and train_mnist.py:206,230."""
+    e = torch.empty(B, L, device=device, dtype=torch.float32).exponential_(generator=generator)
+    gumbel = -e.log()
+    r_z = torch.randn(B, z, device=device, generator=generator)
+    r_theta = torch.randn(B, device=device, generator=generator)
+    return dict(gumbel=gumbel, r_z=r_z, r_theta=r_theta)
+
+
+def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, hooks=None):
+    if not (t_inf == 'attention' and r_inf in ('attention', 'attention+offsets')):
+        raise NotImplementedError("only --t-inf attention with --r-inf attention / attention+offsets is on the "
+                                  "accelerated hot path (SURVEY.md §8)")
+    y = y.to(device)
+    x = x.to(device)
+    if not y.is_cuda:
+        raise RuntimeError("eval_minibatch: the hot path runs on sm_100a only (no CPU fallback)")
+    es = encoder_model.encoder_spec()
+    if (r_inf == 'attention+offsets') != es.rot_refinement:
+        raise ValueError("r_inf does not match the encoder's rot_refinement")
+    B = y.shape[0]
+    n = y.shape[-1]
+    d = n + 2 * es.padding - encoder_model.kernels_size + 1
+    if noise is None:
+        noise = draw_noise(B, es.G * d * d, es.z, y.device)
+    fw, fb = generator_model.fourier_buffers()
+    gen_params = generator_model.hot_path_params()
+    spec = TF.StepSpec(enc=es, sigma=generator_model._sigma, likelihood=likelihood, mask_radius=int(mask_radius),
+                       n_gen_hidden=(len(gen_params) - 5) // 2)
+    if hooks:
+        spec.on_generator_grads, spec.on_encoder_grads = hooks
+    return TF.FusedStepFn.apply(spec, x, y, ctf, noise["gumbel"], noise["r_z"], noise["r_theta"], fw, fb,
+                                *encoder_model.hot_path_params(), *gen_params)
+
+
+def eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
+                   theta_prior, groupconv, image_dim, noise=None, hooks=None):
+    """train_mnist / train_dsprites / train_galaxy signature; Bernoulli likelihood (RGB handled by flat order)."""
+    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, hooks)
+
+
+def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, epoch, device,
+                             theta_prior, groupconv, padding, mask_radius, noise=None, hooks=None):
+    """train_particles signature; Gaussian likelihood, optional CTF and circular mask (no --fit-noise)."""
+    if generator_model.layers[-1].out_features != 1:
+        raise NotImplementedError("--fit-noise is not on the accelerated path (broken with CTF upstream, SURVEY §8 a-8)")
+    if ctf is not None:
+        ctf = ctf.to(device)
+    return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, hooks)
+
+
+def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
+    """clustering_*.get_latent, attention branch (clustering_mnist.py:122-161): one encoder pass + one reduction
+    kernel; returns (z_content (B,2z), theta_mu (B,1), dx (B,2))."""
+    from . import ops
+    if not (t_inf == 'attention' and r_inf in ('attention', 'attention+offsets')):
+        raise NotImplementedError("only the attention/attention branch is on the accelerated path")
+    with torch.no_grad():
+        y = y.to(device)
+        heads = encoder_model.head_maps(y)
+        B, NH, G, d, _ = heads.shape
+        es = encoder_model.encoder_spec()
+        s = ops.attn_shape(B, G, d, es.z, TF.pixel_spacing(x.to(device)), es.tables()[1])
+        zc, th, dx, _ = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
+    return zc, th, dx

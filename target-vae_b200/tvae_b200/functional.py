@@ -1,0 +1,268 @@
+"""torch.autograd.Functions over the C ABI.
+
+  GroupConvFn        GroupConv.forward                         (models.py:202-225)
+  EncoderHeadsFn     encoder up to the attention / theta / z maps (models.py:354-358, 382, 390-399)
+  GeneratorFn        SpatialGenerator.forward                   (models.py:95-123)
+  FusedStepFn        the whole attention/attention(+offsets) branch of eval_minibatch
+                     (train_mnist.py:187-294, train_particles.py:186-343) in one node
+
+Backward runs on the autograd engine thread on the current stream, like the reference's backward.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------ GroupConv
+class GroupConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, weight, bias, G, padding):
+        B, n = y.shape[0], y.shape[-1]
+        O, C, _, k, _ = weight.shape
+        s = ops.enc_shape(B, C, n, k, padding, G, O, 1)
+        yc = ops.f32(y).reshape(B, C, n, n)
+        bank = ops.filter_bank_fwd(s, weight)
+        d = n + 2 * padding - k + 1
+        out = ops.empty(B * G * d * d, O, device=y.device)
+        ops.check(ops.L().tvae_groupconv_fwd(ops.byref(s), ops.ptr(yc), ops.ptr(bank),
+                                             ops.ptr(None if bias is None else ops.f32(bias)), ops.ptr(out),
+                                             ops.stream_ptr()), "tvae_groupconv_fwd")
+        ctx.s, ctx.has_bias = s, bias is not None
+        ctx.save_for_backward(yc)
+        # internal [(b,r,pos)][o] -> reference (B,O,G,H',W')
+        return out.view(B, G, d, d, O).permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, g):
+        (yc,) = ctx.saved_tensors
+        s = ctx.s
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("GroupConv: gradient w.r.t. the input image is not part of the hot path")
+        gi = g.permute(0, 2, 3, 4, 1).contiguous().view(-1, s.O).float()
+        dbank = ops.empty(s.G * s.O, s.kpad, device=g.device)
+        ops.check(ops.L().tvae_groupconv_wgrad(ops.byref(s), ops.ptr(yc), ops.ptr(gi), ops.ptr(dbank), ops.stream_ptr()),
+                  "tvae_groupconv_wgrad")
+        dw, db = ops.filter_bank_bwd(s, dbank)
+        return None, dw, (db if ctx.has_bias else None), None, None
+
+
+# ------------------------------------------------------------------------------------------------ encoder heads
+@dataclass
+class EncoderSpec:
+    G: int
+    padding: int
+    z: int
+    rot_refinement: bool
+    normal_prior_over_r: bool
+    theta_prior: float
+
+    def tables(self):
+        p_r = ops.rotation_log_prior(self.G, self.rot_refinement, self.normal_prior_over_r, self.theta_prior)
+        offs = ops.rotation_offsets(self.G, self.rot_refinement)
+        return p_r, offs
+
+
+ENC_PARAM_NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv_a.weight", "conv_a.bias",
+                   "conv_r.weight", "conv_r.bias", "conv_z.weight", "conv_z.bias"]
+
+
+def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz):
+    B, n = y.shape[0], y.shape[-1]
+    O, C, _, k, _ = w1.shape
+    s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z)
+    p_r, offs = spec.tables()
+    yc = ops.f32(y).reshape(B, C, n, n)
+    wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.G, p_r, offs, y.device)
+    bank = ops.filter_bank_fwd(s, w1)
+    w2m = ops.f32(w2).reshape(O, O)
+    x1, h, heads = ops.encoder_fwd(s, yc, bank, b1, w2m, b2, wh, bh, add)
+    return s, yc, w2m, wh, x1, h, heads
+
+
+def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads):
+    """-> grads in ENC_PARAM_NAMES order.  x1 is consumed (overwritten)."""
+    dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
+    dw1, db1 = ops.filter_bank_bwd(s, dbank)
+    O, z = s.O, spec.z
+    sh = (O, 1, 1, 1)
+    return [dw1, db1, dw2.view(O, O, 1, 1, 1), db2,
+            dwh[0:1].reshape(1, *sh), dbh[0:1], dwh[1:3].reshape(2, *sh), dbh[1:3],
+            dwh[3:].reshape(2 * z, *sh), dbh[3:]]
+
+
+class EncoderHeadsFn(torch.autograd.Function):
+    """heads (B, 3+2z, G, H', W'): attn(+p_r), theta(+offsets), z stacked on dim 1."""
+
+    @staticmethod
+    def forward(ctx, spec, y, *params):
+        s, yc, w2m, wh, x1, h, heads = _encoder_forward(spec, y, *params)
+        ctx.spec, ctx.s = spec, s
+        ctx.save_for_backward(yc, w2m, wh, x1, h)
+        d = s.n + 2 * s.p - s.k + 1
+        return heads.view(s.B, 3 + 2 * spec.z, s.G, d, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        yc, w2m, wh, x1, h = ctx.saved_tensors
+        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1.clone(), h, g.contiguous())
+        return (None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------ generator
+GEN_FIXED = ["coord_linear.weight", "coord_linear.bias", "latent_linear.weight"]
+
+
+def _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout):
+    wf = None
+    if fourier_w is not None:
+        # F.linear(x, weight / sigma, bias) with sigma an fp32 tensor (models.py:40,57)
+        wf = (ops.f32(fourier_w) / torch.tensor(sigma, dtype=torch.float32, device=fourier_w.device)).contiguous()
+    hw = [hidden[i] for i in range(0, len(hidden), 2)]
+    hb = [hidden[i] for i in range(1, len(hidden), 2)]
+    return ops.GenWeights(wf, None if fourier_b is None else ops.f32(fourier_b), w1, b1, wz, hw, hb, wout, bout)
+
+
+def _gen_param_grads(out, L):
+    grads = [out["dw1"], out["db1"], out["dwz"]]
+    for i in range(L):
+        grads += [out["dwh"][i], out["dbh"][i]]
+    grads += [out["dwout"], out["dbout"]]
+    return grads
+
+
+class GeneratorFn(torch.autograd.Function):
+    """y_hat (B,N,n_out) from explicit coordinates x (B,N,2) and z (B,zdim).
+    params = coord_linear.weight, coord_linear.bias, latent_linear.weight, (hidden w, b)*, out w, out b."""
+
+    @staticmethod
+    def forward(ctx, fourier_w, fourier_b, sigma, x, z, *params):
+        w1, b1, wz = params[:3]
+        hidden, (wout, bout) = params[3:-2], params[-2:]
+        gw = _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout)
+        B, N = x.shape[0], x.shape[1]
+        s = ops.gen_shape(B, N, gw, z.shape[1])
+        xc, zc = ops.f32(x).reshape(B * N, 2), ops.f32(z)
+        y_hat, saved = ops.generator_fwd(s, gw, xc, None, None, zc)
+        ctx.s, ctx.gw, ctx.saved = s, gw, saved
+        ctx.save_for_backward(xc, zc, y_hat)
+        return y_hat.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, zc, y_hat = ctx.saved_tensors
+        s = ctx.s
+        out = ops.generator_bwd(s, ctx.gw, xc, None, None, zc, ctx.saved, y_hat, g.reshape(s.B * s.N, -1).contiguous())
+        ctx.saved = None
+        return (None, None, None, out["dxp"].view(s.B, s.N, 2), out["d_z"], *_gen_param_grads(out, s.L))
+
+
+# ------------------------------------------------------------------------------------------------ fused step
+_spacing_cache: dict = {}
+
+
+def pixel_spacing(x_coord: torch.Tensor) -> float:
+    """btw_pixels_space = x[1,0] - x[0,0] (train_mnist.py:30).  The reference syncs for it every step; the
+    coordinate grid is constant, so it is read once per grid and cached."""
+    key = (x_coord.data_ptr(), tuple(x_coord.shape), str(x_coord.device))
+    v = _spacing_cache.get(key)
+    if v is None:
+        v = float((x_coord[1, 0] - x_coord[0, 0]).float().cpu())
+        if len(_spacing_cache) > 64:
+            _spacing_cache.clear()
+        _spacing_cache[key] = v
+    return v
+
+
+@dataclass
+class StepSpec:
+    enc: EncoderSpec
+    sigma: float
+    likelihood: str = "bernoulli"      # bernoulli | gaussian
+    mask_radius: int = 0
+    n_gen_hidden: int = 1
+    # optional hook called in backward once the generator gradients exist (before the encoder backward runs):
+    # used by the data-parallel wrapper to start the first all-reduce bucket early.
+    on_generator_grads: Optional[Callable] = None
+    on_encoder_grads: Optional[Callable] = None
+
+
+class FusedStepFn(torch.autograd.Function):
+    """(elbo, log_p_x_g_z, kl_div) of eval_minibatch's attention/attention(+offsets) branch.
+
+    inputs: spec, x_coord (N,2), y (B,C,n,n), ctf or None, gumbel (B,L), r_z (B,z), r_theta (B),
+            fourier_w, fourier_b, then 10 encoder params (ENC_PARAM_NAMES) and the generator params.
+    """
+
+    @staticmethod
+    def forward(ctx, spec: StepSpec, x_coord, y, ctf, gumbel, r_z, r_theta, fourier_w, fourier_b, *params):
+        enc_params, gen_params = params[:10], params[10:]
+        es = spec.enc
+        s, yc, w2m, wh, x1, h, heads = _encoder_forward(es, y, *enc_params)
+        B, n = s.B, s.n
+        d = s.n + 2 * s.p - s.k + 1
+        xc = ops.f32(x_coord)
+        spacing = pixel_spacing(xc)
+        p_r, offs = es.tables()
+        ashape = ops.attn_shape(B, s.G, d, es.z, spacing, offs)
+        log_prior = ops.attn_log_prior(ashape, p_r, y.device)
+        gum, rz, rth = ops.f32(gumbel), ops.f32(r_z).reshape(B, es.z), ops.f32(r_theta).reshape(B)
+        att = ops.attn_fwd(ashape, heads, gum, rz, rth, log_prior)
+
+        w1, b1, wz = gen_params[:3]
+        hidden, (wout, bout) = gen_params[3:-2], gen_params[-2:]
+        gw = _gen_weights(fourier_w, fourier_b, spec.sigma, w1, b1, wz, hidden, wout, bout)
+        N = xc.shape[0]
+        gs = ops.gen_shape(B, N, gw, es.z)
+        y_hat, gsaved = ops.generator_fwd(gs, gw, xc, att["theta_b"], att["dx"], att["zb"])
+
+        yflat = yc.reshape(B, -1)
+        ctfc = None if ctf is None else ops.f32(ctf)
+        if spec.likelihood == "bernoulli":
+            ll, _ = ops.bernoulli(y_hat, yflat)
+        else:
+            ll, _ = ops.gaussian(y_hat, yflat, n, ctfc, att["dx"], spacing, spec.mask_radius)
+        log_p = ll.mean()
+        kl = att["kl"].mean()
+        elbo = log_p - kl
+
+        ctx.spec, ctx.s, ctx.ashape, ctx.gs, ctx.gw, ctx.gsaved, ctx.att = spec, s, ashape, gs, gw, gsaved, att
+        ctx.spacing = spacing
+        ctx.save_for_backward(yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc if ctfc is not None else yc)
+        ctx.has_ctf = ctfc is not None
+        return elbo, log_p, kl
+
+    @staticmethod
+    def backward(ctx, g_elbo, g_logp, g_kl):
+        yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc = ctx.saved_tensors
+        spec, s, gs, att = ctx.spec, ctx.s, ctx.gs, ctx.att
+        B = s.B
+        zero = torch.zeros((), device=yc.device)
+        g_elbo = zero if g_elbo is None else g_elbo
+        g_logp = zero if g_logp is None else g_logp
+        g_kl = zero if g_kl is None else g_kl
+        # device scalars: dLoss/d(ll_b) and dLoss/d(kl_b) (no host sync)
+        w_ll = ((g_elbo + g_logp) / B).reshape(1).float().contiguous()
+        w_kl = ((g_kl - g_elbo) / B).reshape(1).float().contiguous()
+        yflat = yc.reshape(B, -1)
+        if spec.likelihood == "bernoulli":
+            _, d_yhat = ops.bernoulli(y_hat, yflat, w_ll)
+        else:
+            _, d_yhat = ops.gaussian(y_hat, yflat, s.n, ctfc if ctx.has_ctf else None, att["dx"], ctx.spacing,
+                                     spec.mask_radius, w_ll)
+        gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
+        gen_grads = _gen_param_grads(gout, gs.L)
+        if spec.on_generator_grads is not None:
+            gen_grads = spec.on_generator_grads(gen_grads)
+        d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
+        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads)
+        if spec.on_encoder_grads is not None:
+            enc_grads = spec.on_encoder_grads(enc_grads)
+        ctx.gsaved = None
+        ctx.att = None
+        return (None,) * 9 + tuple(enc_grads) + tuple(gen_grads)

@@ -3,6 +3,7 @@ memory and the stream; every computation is a call into libtvae_b200.so."""
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 from ctypes import POINTER, Structure, byref, c_float, c_int, c_void_p
 
@@ -118,6 +119,7 @@ def filter_bank_bwd(s: EncShape, dbank: torch.Tensor):
     return dw, db
 
 
+@functools.lru_cache(maxsize=None)
 def rotation_offsets(G: int, rot_refinement: bool):
     """models.py:361-366 / :401."""
     if not rot_refinement:
@@ -131,6 +133,7 @@ def rotation_offsets(G: int, rot_refinement: bool):
     return out
 
 
+@functools.lru_cache(maxsize=None)
 def rotation_log_prior(G: int, rot_refinement: bool, normal_prior_over_r: bool, theta_prior: float):
     """p_r[r] of models.py:360-379 as python floats (fp32 arithmetic like the reference)."""
     if rot_refinement:
@@ -150,11 +153,15 @@ def head_tables(wa, ba, wr, br, wz, bz, G, p_r, offsets, device):
     O = wa.shape[1]
     wh = torch.cat([f32(wa).reshape(1, O), f32(wr).reshape(2, O), f32(wz).reshape(-1, O)], 0).contiguous()
     bh = torch.cat([f32(ba).reshape(1), f32(br).reshape(2), f32(bz).reshape(-1)], 0).contiguous()
-    NH = wh.shape[0]
+    return wh, bh, _head_add_table(wh.shape[0], G, tuple(p_r), tuple(offsets), str(device))
+
+
+@functools.lru_cache(maxsize=64)
+def _head_add_table(NH, G, p_r, offsets, device):
     add = torch.zeros(NH, G, dtype=torch.float32)
     add[0] = torch.tensor(p_r, dtype=torch.float32)
     add[1] = torch.tensor(offsets, dtype=torch.float32)
-    return wh, bh, add.to(device)
+    return add.to(device)
 
 
 def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add):
