@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py - train images/s (fwd+bwd) of the TARGET-VAE hot path on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                        # our arm, one JSON line
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                   # the reference algorithm on host cores
+
+A "step" is one pass of the hot path (eval_minibatch forward + (-elbo).backward(), no optimiser step, exactly
+the metric of BASELINE.json) over one synthetic minibatch of the workload's shape.  Workload at N = 1 is
+BASELINE.json configs[1] (dSprites-shaped 64x64, z=2, P8 group conv, attention t/r inference); other configs via
+--config.  Weak scaling: the per-GPU minibatch is fixed (100, the reference's --minibatch-size default).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "target-vae_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tvae_b200 import synth  # noqa: E402
+from tvae_b200.config import PRESETS  # noqa: E402
+
+METRIC = "train images/sec (fwd+bwd)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(PRESETS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU minibatch (default: the trainer's 100; cfg5: 256)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_images_per_s(cfg, B, steps, warmup):
+    """The reference algorithm (oracle port of eval_minibatch + backward) on the host cores, all threads."""
+    from helpers import oracle_step
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(warmup):
+        oracle_step(cfg, B, dtype=torch.float32)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(cfg, B, dtype=torch.float32)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps
+
+
+def default_cpu_batch(cfg):
+    return {"cfg1": 48, "cfg2": 16, "cfg3": 4, "cfg4b": 8, "cfg4": 2, "cfg5": 2}.get(cfg.name.split("_")[0], 4)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch or default_cpu_batch(cfg)
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ips, s_per_step = cpu_reference_images_per_s(cfg, B, steps, warm)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(cfg, args.batch or cfg.batch, args.gpus),
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} step(s) of {B} images, oracle port of eval_minibatch + backward, torch CPU fp32, "
+                                   f"{torch.get_num_threads()} threads"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, B, n_gpus):
+    return {"workload": f"{cfg.name}: y ({B},{cfg.C},{cfg.n},{cfg.n}) per GPU, P{cfg.G} group conv k={cfg.k} p={cfg.p} "
+                        f"O={cfg.O}, z={cfg.z}, attention t/r inference{' + offsets' if cfg.rot_refinement else ''}, "
+                        f"generator {cfg.gen_layers}x{cfg.hidden}{' Fourier-1024' if cfg.fourier else ''}, {cfg.likelihood}"
+                        f"{' + CTF' if cfg.ctf else ''}",
+            "per_gpu_batch": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus}",
+            "l2": "activations streamed per step (GBs) far exceed the 126 MB L2; a different input batch every step"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_models(cfg, dev):
+    import torch.nn as nn
+    import src.models as models
+    with contextlib.redirect_stdout(io.StringIO()):
+        gen = models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=nn.LeakyReLU,
+                                      resid=False, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
+        enc = models.InferenceNetwork_AttentionTranslation_AttentionRotation(
+            cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+            groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
+            normal_prior_over_r=cfg.normal_prior_over_r)
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg).items()})
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg).items()})
+    return gen.to(dev), enc.to(dev)
+
+
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 GEMM 8192^3, best of 10 (same method MEASURED_PEAKS.json uses for bf16)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev); c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        best = 1e9
+        for _ in range(10):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def run_ours(args, cfg):
+    import torch.distributed as dist
+    from tvae_b200 import dp, elbo as E, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or cfg.batch
+    gen, enc = build_models(cfg, dev)
+    params = list(gen.parameters()) + list(enc.parameters())
+    sync = dp.GradSync() if world > 1 else None
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(dev)
+    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+
+    # distinct synthetic minibatches: pinned host copies (e2e leg) and device-resident copies (value leg)
+    NB = 4
+    host = [synth.minibatch(cfg, B, seed=100 * rank + i) for i in range(NB)]
+    y_pin = [torch.from_numpy(h["y"]).pin_memory() for h in host]
+    ctf_pin = [torch.from_numpy(h["ctf"]).pin_memory() if h["ctf"] is not None else None for h in host]
+    y_dev = [t.to(dev) for t in y_pin]
+    ctf_dev = [None if t is None else t.to(dev) for t in ctf_pin]
+    y_stage = torch.empty_like(y_dev[0])
+    ctf_stage = None if ctf_dev[0] is None else torch.empty_like(ctf_dev[0])
+
+    def step(y, ctf):
+        for p in params:
+            p.grad = None
+        if cfg.likelihood == "gaussian":
+            elbo, logp, kl = E.eval_minibatch_particles(x, y, ctf, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G,
+                                                        cfg.p, cfg.mask_radius, sync=sync)
+        else:
+            elbo, logp, kl = E.eval_minibatch(x, y, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G, cfg.n, sync=sync)
+        (-elbo).backward()
+        return elbo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        step(y_dev[i % NB], ctf_dev[i % NB])
+    barrier()
+
+    # ---- value: inputs resident in HBM, device-timed, max over ranks
+    launches0 = ops.launch_count()
+    ops.profile_enable(True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step(y_dev[i % NB], ctf_dev[i % NB])
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = ops.profile_collect()
+    ops.profile_enable(False)
+    launches = ops.launch_count() - launches0
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- e2e: same call, host buffers: H2D of the step's inputs from pinned memory + D2H read of the result
+    h2d = y_pin[0].numel() * 4 + (0 if ctf_pin[0] is None else ctf_pin[0].numel() * 4)
+    for i in range(2):
+        y_stage.copy_(y_pin[i % NB], non_blocking=True)
+        float(step(y_stage, ctf_stage if ctf_stage is None else ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)))
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        y_stage.copy_(y_pin[i % NB], non_blocking=True)
+        if ctf_stage is not None:
+            ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)
+        _ = float(step(y_stage, ctf_stage))        # D2H read of the ELBO every step
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = world * B * K / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (event-timed inside the timed region above)
+    flops = cfg.flops_fwd()
+    algo = {"conv1_fwd": flops["conv1"] * B, "conv1_wgrad": flops["conv1"] * B}
+    if cfg.fourier:
+        first = 2 * cfg.fourier_dim * cfg.hidden * cfg.n ** 2 * B
+        algo.update({"gen_l1_fwd": first, "gen_l1_wgrad": first, "gen_l1_dgrad": first})
+    dom = max((k for k in prof if k in algo), key=lambda k: prof[k][0], default=None)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tf32_peak = measure_tf32_peak(dev)
+    roofline = None
+    if dom is not None and prof[dom][1] > 0:
+        ms_launch = prof[dom][0] / prof[dom][1]
+        achieved = algo[dom] / (ms_launch * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(cfg.name.split("_")[0], {}).get(dom)
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf32_peak, "traffic": traffic,
+                    "peak_source": "cuBLAS TF32 8192^3 best-of-10 measured in this run (kernel computes in TF32, nominally half "
+                                   "the BF16 rate); MEASURED_PEAKS.json bf16_tflops_sustained = %.1f -> frac_of_bf16 below" % bf16_peak,
+                    "frac_of_bf16": achieved / bf16_peak, "ms_per_launch": ms_launch,
+                    "share_of_step": prof[dom][0] / ms_total,
+                    "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Bc = args.cpu_batch or default_cpu_batch(cfg)
+        ips, _ = cpu_reference_images_per_s(cfg, Bc, 2, 1)
+        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"2 steps of {Bc} images (after 1 warm-up), oracle port of eval_minibatch + backward, torch CPU fp32, "
+                         f"{torch.get_num_threads()} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic", "config": workload_config(cfg, B, world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
+        "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = PRESETS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

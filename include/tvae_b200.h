@@ -26,6 +26,10 @@ extern "C" {
 const char* tvae_last_error(void);
 int tvae_version(void);
 long long tvae_launch_count(void);   /* kernels launched by this library so far (process-wide) */
+/* Optional timing of every tensor-core GEMM launch with CUDA events on its own stream (used by bench.py for the
+ * roofline of the dominant kernel).  collect() synchronises the device and returns the number of kernel names. */
+void tvae_profile_enable(int on);
+int tvae_profile_collect(const char** names, float* total_ms, int* launches, int cap);
 
 /* ------------------------------------------------------------------ encoder (models.py:132-225, 326-403) */
 typedef struct {

@@ -1,0 +1,42 @@
+"""Builds libtvae_b200.so in-tree with nvcc for sm_100a (no torch headers, no libcuda link).
+
+    python target-vae_b200/csrc/build.py [--force]
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tvae_b200", "libtvae_b200.so")
+SOURCES = ["tvae_api.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+         "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (HERE, os.path.join(os.path.dirname(os.path.dirname(HERE)), "include")):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                h.update(f.encode())
+                h.update(open(os.path.join(root, f), "rb").read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    stamp = OUT + ".sha256"
+    dig = _digest()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(HERE, s) for s in SOURCES] + ["-o", OUT]
+    subprocess.check_call(cmd, cwd=HERE)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

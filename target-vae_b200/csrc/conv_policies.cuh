@@ -65,6 +65,7 @@ struct Conv1FwdParams {
 
 template <int BN>
 struct Conv1Fwd : PolicyBase {
+    static constexpr const char* kName = "conv1_fwd";
     using Params = Conv1FwdParams;
     static constexpr int kBN = BN;
     static constexpr bool kAGen = true;
@@ -171,6 +172,7 @@ struct Conv1WgradParams {
 
 template <int BN>
 struct Conv1Wgrad : PolicyBase {
+    static constexpr const char* kName = "conv1_wgrad";
     using Params = Conv1WgradParams;
     static constexpr int kBN = BN;
     static constexpr bool kAMajorMN = true;
@@ -279,6 +281,7 @@ struct Conv2HeadsParams {
 
 template <int BN, int NHMAX>
 struct Conv2Heads : PolicyBase {
+    static constexpr const char* kName = "conv2_heads";
     using Params = Conv2HeadsParams;
     static constexpr int kBN = BN;
     __device__ static void prefetch_descs(const Params& p) {

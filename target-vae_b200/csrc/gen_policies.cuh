@@ -66,6 +66,7 @@ struct GenL1FwdParams {
 
 template <int BN>
 struct GenL1Fwd : PolicyBase {
+    static constexpr const char* kName = "gen_l1_fwd";
     using Params = GenL1FwdParams;
     static constexpr int kBN = BN;
     static constexpr bool kAGen = true;
@@ -143,6 +144,7 @@ struct GenL1WgradParams {
 
 template <int BN>
 struct GenL1Wgrad : PolicyBase {
+    static constexpr const char* kName = "gen_l1_wgrad";
     using Params = GenL1WgradParams;
     static constexpr int kBN = BN;
     static constexpr bool kAMajorMN = true;
@@ -216,6 +218,7 @@ struct GenL1DgradParams {
 
 template <int BN>
 struct GenL1Dgrad : PolicyBase {
+    static constexpr const char* kName = "gen_l1_dgrad";
     using Params = GenL1DgradParams;
     static constexpr int kBN = BN;
     __device__ static void prefetch_descs(const Params& p) {

@@ -67,6 +67,45 @@ inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64
     return 0;
 }
 
+// ---- optional per-kernel timing (bench.py): CUDA events recorded around every tc_gemm launch on its own stream
+struct KernelTimer {
+    static constexpr int kMaxNames = 32;
+    static constexpr int kMaxEvents = 8192;
+    bool enabled = false;
+    int n_names = 0;
+    const char* names[kMaxNames];
+    int n_events = 0;
+    cudaEvent_t start[kMaxEvents], stop[kMaxEvents];
+    int name_of[kMaxEvents];
+    int n_created = 0;
+    int name_id(const char* nm) {
+        for (int i = 0; i < n_names; ++i)
+            if (names[i] == nm) return i;
+        if (n_names >= kMaxNames) return -1;
+        names[n_names] = nm;
+        return n_names++;
+    }
+    // returns slot or -1
+    int begin(const char* nm, cudaStream_t st) {
+        if (!enabled || n_events >= kMaxEvents) return -1;
+        const int id = name_id(nm);
+        if (id < 0) return -1;
+        const int e = n_events++;
+        if (e >= n_created) {
+            cudaEventCreate(&start[e]);
+            cudaEventCreate(&stop[e]);
+            n_created = e + 1;
+        }
+        name_of[e] = id;
+        cudaEventRecord(start[e], st);
+        return e;
+    }
+    void end(int e, cudaStream_t st) {
+        if (e >= 0) cudaEventRecord(stop[e], st);
+    }
+};
+inline KernelTimer g_timer;
+
 inline int sm_count() {
     static int n = 0;
     if (!n) {

@@ -30,7 +30,9 @@ inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t st
     const int threads = (kCtrlWarps + kEpiWarps + P::kProdWarps) * 32;
     const int grid = prm.num_tiles < sm_count() ? prm.num_tiles : sm_count();
     ++g_launch_count;
+    const int tslot = g_timer.begin(P::kName, stream);
     tc_gemm_kernel<P><<<grid, threads, L.total, stream>>>(prm);
+    g_timer.end(tslot, stream);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -33,6 +33,7 @@ struct LinearNTParams {
 
 template <int BN>
 struct LinearNT : PolicyBase {
+    static constexpr const char* kName = "linear_nt";
     using Params = LinearNTParams;
     static constexpr int kBN = BN;
     __device__ static void prefetch_descs(const Params& p) {
@@ -141,6 +142,7 @@ struct LinearTNParams {
 
 template <int BN>
 struct LinearTN : PolicyBase {
+    static constexpr const char* kName = "linear_tn";
     using Params = LinearTNParams;
     static constexpr int kBN = BN;
     static constexpr bool kAMajorMN = true;

@@ -75,6 +75,27 @@ const char* tvae_last_error(void) { return g_last_error.c_str(); }
 int tvae_version(void) { return 100; }
 long long tvae_launch_count(void) { return g_launch_count.load(); }
 
+// per-kernel timing of the tensor-core GEMM launches (CUDA events on the launching stream)
+void tvae_profile_enable(int on) {
+    g_timer.enabled = on != 0;
+    if (on) g_timer.n_events = 0;
+}
+// Synchronises, then fills up to `cap` entries: names[i] (static strings), total_ms[i], launches[i]. Returns count.
+int tvae_profile_collect(const char** names, float* total_ms, int* launches, int cap) {
+    cudaDeviceSynchronize();
+    int n = g_timer.n_names < cap ? g_timer.n_names : cap;
+    for (int i = 0; i < n; ++i) { names[i] = g_timer.names[i]; total_ms[i] = 0.f; launches[i] = 0; }
+    for (int e = 0; e < g_timer.n_events; ++e) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_timer.start[e], g_timer.stop[e]) == cudaSuccess && g_timer.name_of[e] < n) {
+            total_ms[g_timer.name_of[e]] += ms;
+            launches[g_timer.name_of[e]] += 1;
+        }
+    }
+    g_timer.n_events = 0;
+    return n;
+}
+
 int tvae_bank_pitch(int C, int k) {
     const int K = C * k * k;
     return (K / 32 + 1) * 32;   // always leaves >= 1 spare column for the bias-gradient ones column

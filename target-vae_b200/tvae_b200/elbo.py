@@ -28,7 +28,7 @@ def draw_noise(B, L, z, device, generator=None):
     return dict(gumbel=gumbel, r_z=r_z, r_theta=r_theta)
 
 
-def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, hooks=None):
+def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, sync=None):
     if not (t_inf == 'attention' and r_inf in ('attention', 'attention+offsets')):
         raise NotImplementedError("only --t-inf attention with --r-inf attention / attention+offsets is on the "
                                   "accelerated hot path (SURVEY.md §8)")
@@ -48,26 +48,25 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
     gen_params = generator_model.hot_path_params()
     spec = TF.StepSpec(enc=es, sigma=generator_model._sigma, likelihood=likelihood, mask_radius=int(mask_radius),
                        n_gen_hidden=(len(gen_params) - 5) // 2)
-    if hooks:
-        spec.on_generator_grads, spec.on_encoder_grads = hooks
+    spec.sync = sync
     return TF.FusedStepFn.apply(spec, x, y, ctf, noise["gumbel"], noise["r_z"], noise["r_theta"], fw, fb,
                                 *encoder_model.hot_path_params(), *gen_params)
 
 
 def eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
-                   theta_prior, groupconv, image_dim, noise=None, hooks=None):
+                   theta_prior, groupconv, image_dim, noise=None, sync=None):
     """train_mnist / train_dsprites / train_galaxy signature; Bernoulli likelihood (RGB handled by flat order)."""
-    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, hooks)
+    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, sync)
 
 
 def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, epoch, device,
-                             theta_prior, groupconv, padding, mask_radius, noise=None, hooks=None):
+                             theta_prior, groupconv, padding, mask_radius, noise=None, sync=None):
     """train_particles signature; Gaussian likelihood, optional CTF and circular mask (no --fit-noise)."""
     if generator_model.layers[-1].out_features != 1:
         raise NotImplementedError("--fit-noise is not on the accelerated path (broken with CTF upstream, SURVEY §8 a-8)")
     if ctf is not None:
         ctf = ctf.to(device)
-    return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, hooks)
+    return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync)
 
 
 def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):

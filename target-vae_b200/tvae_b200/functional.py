@@ -186,10 +186,9 @@ class StepSpec:
     likelihood: str = "bernoulli"      # bernoulli | gaussian
     mask_radius: int = 0
     n_gen_hidden: int = 1
-    # optional hook called in backward once the generator gradients exist (before the encoder backward runs):
-    # used by the data-parallel wrapper to start the first all-reduce bucket early.
-    on_generator_grads: Optional[Callable] = None
-    on_encoder_grads: Optional[Callable] = None
+    # optional data-parallel gradient synchroniser (tvae_b200.dp.GradSync): bucket 0 (generator) is started as
+    # soon as the generator backward has been issued, so its all-reduce overlaps the encoder backward.
+    sync: Optional[object] = None
 
 
 class FusedStepFn(torch.autograd.Function):
@@ -257,12 +256,13 @@ class FusedStepFn(torch.autograd.Function):
                                      spec.mask_radius, w_ll)
         gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
         gen_grads = _gen_param_grads(gout, gs.L)
-        if spec.on_generator_grads is not None:
-            gen_grads = spec.on_generator_grads(gen_grads)
+        if spec.sync is not None:
+            spec.sync.start(0, gen_grads)
         d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
         enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads)
-        if spec.on_encoder_grads is not None:
-            enc_grads = spec.on_encoder_grads(enc_grads)
+        if spec.sync is not None:
+            spec.sync.start(1, enc_grads)
+            gen_grads, enc_grads = spec.sync.finish()
         ctx.gsaved = None
         ctx.att = None
         return (None,) * 9 + tuple(enc_grads) + tuple(gen_grads)

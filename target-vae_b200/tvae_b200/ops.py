@@ -78,6 +78,9 @@ def L():
     lib = _lib.lib()
     if not _configured:
         lib.tvae_bank_pitch.restype = c_int
+        lib.tvae_launch_count.restype = ctypes.c_longlong
+        lib.tvae_profile_enable.restype = None
+        lib.tvae_profile_collect.restype = c_int
         for name in ("tvae_filter_bank_fwd", "tvae_filter_bank_bwd", "tvae_encoder_fwd", "tvae_encoder_bwd",
                      "tvae_attn_log_prior", "tvae_attn_fwd", "tvae_attn_bwd", "tvae_attn_softmax_pair",
                      "tvae_get_latent", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
@@ -330,3 +333,22 @@ def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None):
                             _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
                             _p(g), B, n, stream_ptr().value), "tvae_gaussian")
     return ll, d
+
+
+# ----------------------------------------------------------------------------------------------- instrumentation
+def launch_count() -> int:
+    return int(L().tvae_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    L().tvae_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kernel name: (total ms, launches)} of the tensor-core GEMM launches since profile_enable(True)."""
+    cap = 32
+    names = (ctypes.c_char_p * cap)()
+    ms = (c_float * cap)()
+    cnt = (c_int * cap)()
+    n = L().tvae_profile_collect(names, ms, cnt, cap)
+    return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
