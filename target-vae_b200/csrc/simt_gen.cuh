@@ -33,50 +33,114 @@ __global__ void latent_bias_bwd_kernel(const float* __restrict__ dzb, const floa
     }
 }
 
-// No Fourier expansion (cfg2): a0[m][j] = LeakyReLU(x'0 W1[j][0] + x'1 W1[j][1] + b1[j] + zb[b][j]).  blockDim.x = H.
-__global__ void __launch_bounds__(1024) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                               const float* __restrict__ zb, float* __restrict__ a0, int H, int rows_per_cta) {
-    const int j = threadIdx.x;
-    const float wx = w1[2 * j], wy = w1[2 * j + 1], bb = b1[j];
-    const long long m0 = (long long)blockIdx.x * rows_per_cta;
-    for (long long m = m0; m < min(m0 + rows_per_cta, cx.M); ++m) {
+// No Fourier expansion (cfg2): a0[m][j] = LeakyReLU(x'0 W1[j][0] + x'1 W1[j][1] + b1[j] + zb[b][j]), tf32-rounded.
+// CTA = kCoordRB rows; the transformed coordinates of the block are computed once into shared memory, then
+// thread = 4 adjacent columns x one row slot streams float4 stores (HBM-bound: one write of a0).
+constexpr int kCoordRB = 64;
+__global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                              const float* __restrict__ zb, float* __restrict__ a0, int H) {
+    __shared__ float2 s_x[kCoordRB];
+    const int cgs = H / 4, rpp = blockDim.x / cgs;
+    const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
+    const long long m0 = (long long)blockIdx.x * kCoordRB;
+    if (threadIdx.x < kCoordRB) {
         float x0, x1;
-        transformed_coord(cx, m, x0, x1);
-        const float zz = zb ? zb[(m / cx.N) * H + j] : 0.f;
-        a0[m * H + j] = to_tf32(lrelu(fmaf(x1, wy, fmaf(x0, wx, bb)) + zz));
+        transformed_coord(cx, m0 + threadIdx.x, x0, x1);
+        s_x[threadIdx.x] = make_float2(x0, x1);
+    }
+    const int c0 = cg * 4;
+    float wx[4], wy[4], bb[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; bb[v] = b1[c0 + v]; }
+    __syncthreads();
+    const int rows = static_cast<int>(min((long long)kCoordRB, cx.M - m0));
+    for (int rr = rs; rr < rows; rr += rpp) {
+        const long long m = m0 + rr;
+        const float2 x = s_x[rr];
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0));
+        float4 o;
+        o.x = to_tf32(lrelu(fmaf(x.y, wy[0], fmaf(x.x, wx[0], bb[0])) + z4.x));
+        o.y = to_tf32(lrelu(fmaf(x.y, wy[1], fmaf(x.x, wx[1], bb[1])) + z4.y));
+        o.z = to_tf32(lrelu(fmaf(x.y, wy[2], fmaf(x.x, wx[2], bb[2])) + z4.z));
+        o.w = to_tf32(lrelu(fmaf(x.y, wy[3], fmaf(x.x, wx[3], bb[3])) + z4.w));
+        *reinterpret_cast<float4*>(a0 + m * H + c0) = o;
     }
 }
-// backward of the above, weight part: dW1[j][0..1] += sum_m dpre[m][j] x'[m]   (thread = column j)
-__global__ void __launch_bounds__(1024) coord_layer_bwd_w_kernel(CoordXform cx, const float* __restrict__ dpre, float* __restrict__ dw1,
-                                                                 int H, int rows_per_cta) {
-    const int j = threadIdx.x;
-    float dwx = 0.f, dwy = 0.f;
-    const long long m0 = (long long)blockIdx.x * rows_per_cta;
-    for (long long m = m0; m < min(m0 + rows_per_cta, cx.M); ++m) {
-        float x0, x1;
-        transformed_coord(cx, m, x0, x1);
-        const float g = dpre[m * H + j];
-        dwx = fmaf(g, x0, dwx);
-        dwy = fmaf(g, x1, dwy);
+// backward of the above in one pass over dpre:  dW1[j][0..1] += sum_m dpre[m][j] x'[m]  and
+// dxp[m] = sum_j dpre[m][j] W1[j][:]   (CTA = rows_per_cta rows in blocks of kCoordRB).
+__global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ dpre,
+                                                              float* __restrict__ dw1, float* __restrict__ dxp, int H, int rows_per_cta) {
+    extern __shared__ float s_cl[];
+    float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [kCoordRB]
+    float* s_dx = s_cl + 2 * kCoordRB;                              // [kCoordRB][2]
+    float* s_dw = s_dx + 2 * kCoordRB;                              // [H][2]
+    const int cgs = H / 4, rpp = blockDim.x / cgs;
+    const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
+    const int c0 = cg * 4, lane = threadIdx.x & 31;
+    const bool warp_rows = (cgs % 32) == 0;                         // every warp lies inside one row
+    float wx[4], wy[4], dwx[4], dwy[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; dwx[v] = 0.f; dwy[v] = 0.f; }
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) s_dw[i] = 0.f;
+    const long long m_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long m_end = min(m_begin + rows_per_cta, cx.M);
+    for (long long m0 = m_begin; m0 < m_end; m0 += kCoordRB) {
+        const int rows = static_cast<int>(min((long long)kCoordRB, m_end - m0));
+        __syncthreads();
+        if (threadIdx.x < kCoordRB) {
+            float x0, x1;
+            transformed_coord(cx, m0 + threadIdx.x, x0, x1);
+            s_x[threadIdx.x] = make_float2(x0, x1);
+            s_dx[2 * threadIdx.x] = 0.f;
+            s_dx[2 * threadIdx.x + 1] = 0.f;
+        }
+        __syncthreads();
+        for (int rr0 = rs; rr0 < rows; rr0 += 4 * rpp) {
+            float4 g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rr = rr0 + q * rpp;
+                if (rr < rows) g[q] = *reinterpret_cast<const float4*>(dpre + (m0 + rr) * H + c0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int rr = rr0 + q * rpp;
+                if (rr < rows) {
+                    const float2 x = s_x[rr];
+                    const float gv[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+                    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        dwx[v] = fmaf(gv[v], x.x, dwx[v]);
+                        dwy[v] = fmaf(gv[v], x.y, dwy[v]);
+                        p0 = fmaf(gv[v], wx[v], p0);
+                        p1 = fmaf(gv[v], wy[v], p1);
+                    }
+                    if (warp_rows) {
+                        p0 = warp_sum(p0);
+                        p1 = warp_sum(p1);
+                        if (lane == 0) { atomicAdd(s_dx + 2 * rr, p0); atomicAdd(s_dx + 2 * rr + 1, p1); }
+                    } else {
+                        atomicAdd(s_dx + 2 * rr, p0);
+                        atomicAdd(s_dx + 2 * rr + 1, p1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < rows) {
+            dxp[2 * (m0 + threadIdx.x)] = s_dx[2 * threadIdx.x];
+            dxp[2 * (m0 + threadIdx.x) + 1] = s_dx[2 * threadIdx.x + 1];
+        }
     }
-    atomicAdd(dw1 + 2 * j, dwx);
-    atomicAdd(dw1 + 2 * j + 1, dwy);
-}
-// coordinate part: dxp[m] = sum_j dpre[m][j] W1[j][:]   (warp per row)
-__global__ void __launch_bounds__(256) coord_layer_bwd_x_kernel(const float* __restrict__ w1, const float* __restrict__ dpre,
-                                                                float* __restrict__ dxp, long long M, int H) {
-    const int lane = threadIdx.x & 31;
-    const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m >= M) return;
-    float g0 = 0.f, g1 = 0.f;
-    for (int j = lane; j < H; j += 32) {
-        const float g = dpre[m * H + j];
-        g0 = fmaf(g, __ldg(w1 + 2 * j), g0);
-        g1 = fmaf(g, __ldg(w1 + 2 * j + 1), g1);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        atomicAdd(s_dw + 2 * (c0 + v), dwx[v]);
+        atomicAdd(s_dw + 2 * (c0 + v) + 1, dwy[v]);
     }
-    g0 = warp_sum(g0);
-    g1 = warp_sum(g1);
-    if (lane == 0) { dxp[2 * m] = g0; dxp[2 * m + 1] = g1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) atomicAdd(dw1 + i, s_dw[i]);
 }
 
 // dxp (B*N,2) -> d_theta (B), d_dx (B,2) through x' = (x - dx) R(theta)   (train_mnist.py:222,234-239).

@@ -524,11 +524,13 @@ __global__ void __launch_bounds__(256) gaussian_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // Thin-layer backward.  A "thin" layer maps a wide activation a[m][W] to T outputs t[m][j] =
 // sum_c a[m][c] Wt[j][c] + bt[j]  (attention/theta/z heads: T = 3+2z; generator output layer: T = n_out).
-// Given dt it produces, in one pass over a:
+// Given dt it produces, in one streaming pass over a (HBM-bound: one read of a, one write of dpre):
 //   dpre[m][c] = (sum_j dt[m][j] Wt[j][c]) * lrelu'(a[m][c])      (gradient w.r.t. the pre-activation of a)
 //   dWt[j][c] += sum_m dt[m][j] a[m][c],  dbt[j] += sum_m dt[m][j],  dcol[c] += sum_m dpre[m][c]
-// Thread = column c (coalesced rows), CTA = a chunk of rows.  dt is addressed as
-//   dt[(m / P) * dt_outer + j * dt_chan + (m % P)]   (planar head maps), or row-major with P = 1.
+// Thread = VEC adjacent columns x one row slot; a CTA streams a contiguous chunk of rows in blocks of
+// kThinRB rows whose dt values are staged in shared memory.  dt is addressed as
+//   dt[b * dt_outer + j * dt_chan + r * P + pos],  m = (b*G + r)*P + pos   (planar head maps), or row-major dt[m][T].
+// Per-CTA partial sums are combined in shared memory, then one global atomicAdd per output element.
 // ------------------------------------------------------------------------------------------
 struct ThinBwdParams {
     const float* a;      // [M][W] post-activation
@@ -543,21 +545,58 @@ struct ThinBwdParams {
     long long dt_outer, dt_chan;
     int rows_per_cta;
 };
+constexpr int kThinRB = 64;
 
-template <int TMAX, bool PLANAR>
-__device__ __forceinline__ void thin_bwd_body(const ThinBwdParams& p, int G, float* s_dt) {
-    const int c = threadIdx.x;       // blockDim.x == W
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+template <int VEC>
+__device__ __forceinline__ void vec_load(const float* p, float (&v)[VEC]) {
+    using V = typename VecT<VEC>::type;
+    const V t = *reinterpret_cast<const V*>(p);
+    if constexpr (VEC == 4) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { v[0] = t.x; v[1] = t.y; }
+    else v[0] = t;
+}
+template <int VEC>
+__device__ __forceinline__ void vec_store(float* p, const float (&v)[VEC]) {
+    using V = typename VecT<VEC>::type;
+    V t;
+    if constexpr (VEC == 4) { t.x = v[0]; t.y = v[1]; t.z = v[2]; t.w = v[3]; }
+    else if constexpr (VEC == 2) { t.x = v[0]; t.y = v[1]; }
+    else t = v[0];
+    *reinterpret_cast<V*>(p) = t;
+}
+
+// dynamic smem: [kThinRB * T] staged dt, then [(T + 1) * W + T] CTA partial sums (dWt, dcol, dbt)
+template <int TMAX, int VEC, bool PLANAR>
+__global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
+    extern __shared__ float s_thin[];
+    float* s_dt = s_thin;
+    float* s_red = s_thin + kThinRB * p.T;
+    const int cgs = p.W / VEC;                 // column groups
+    const int rpp = blockDim.x / cgs;          // rows per pass
+    const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
+    const int c0 = cg * VEC;
+    const int n_red = (p.T + 1) * p.W + p.T;
+    for (int i = threadIdx.x; i < n_red; i += blockDim.x) s_red[i] = 0.f;
     const long long m_begin = (long long)blockIdx.x * p.rows_per_cta;
     const long long m_end = min(m_begin + p.rows_per_cta, p.M);
-    float wt[TMAX], dw[TMAX];
+    float wt[TMAX][VEC], dw[TMAX][VEC], dcol[VEC];
 #pragma unroll
     for (int j = 0; j < TMAX; ++j) {
-        wt[j] = j < p.T ? p.Wt[(long long)j * p.W + c] : 0.f;
-        dw[j] = 0.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            wt[j][v] = j < p.T ? p.Wt[(long long)j * p.W + c0 + v] : 0.f;
+            dw[j][v] = 0.f;
+        }
     }
-    float dcol = 0.f, dbt = 0.f;
-    for (long long m0 = m_begin; m0 < m_end; m0 += 64) {
-        const int rows = static_cast<int>(min((long long)64, m_end - m0));
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dcol[v] = 0.f;
+    float dbt = 0.f;   // threads with tid < T accumulate column tid of the staged dt block
+    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB) {
+        const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
         __syncthreads();
         for (int idx = threadIdx.x; idx < rows * p.T; idx += blockDim.x) {
             long long addr;
@@ -577,43 +616,63 @@ __device__ __forceinline__ void thin_bwd_body(const ThinBwdParams& p, int G, flo
             s_dt[rr * p.T + j] = p.dt[addr];
         }
         __syncthreads();
-        for (int rr = 0; rr < rows; ++rr) {
-            const long long m = m0 + rr;
-            const float av = p.a[m * p.W + c];
-            float g = 0.f;
+        if (rs < rpp) {
+            for (int rr0 = rs; rr0 < rows; rr0 += 4 * rpp) {
+                float av[4][VEC];
 #pragma unroll
-            for (int j = 0; j < TMAX; ++j) {
-                if (j < p.T) {
-                    const float d = s_dt[rr * p.T + j];
-                    g = fmaf(d, wt[j], g);
-                    dw[j] = fmaf(d, av, dw[j]);
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = rr0 + q * rpp;
+                    if (rr < rows) vec_load<VEC>(p.a + (m0 + rr) * p.W + c0, av[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rr = rr0 + q * rpp;
+                    if (rr < rows) {
+                        float g[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) g[v] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < TMAX; ++j) {
+                            if (j < p.T) {
+                                const float d = s_dt[rr * p.T + j];
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    g[v] = fmaf(d, wt[j][v], g[v]);
+                                    dw[j][v] = fmaf(d, av[q][v], dw[j][v]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            g[v] *= (av[q][v] > 0.f ? 1.f : kSlope);
+                            dcol[v] += g[v];
+                        }
+                        vec_store<VEC>(p.dpre + (m0 + rr) * p.W + c0, g);
+                    }
                 }
             }
-            g *= (av > 0.f ? 1.f : kSlope);
-            p.dpre[m * p.W + c] = g;
-            dcol += g;
         }
-        if (p.dbt && c < p.T) {
-            for (int rr = 0; rr < rows; ++rr) dbt += s_dt[rr * p.T + c];
+        if (p.dbt && threadIdx.x < p.T) {
+            for (int rr = 0; rr < rows; ++rr) dbt += s_dt[rr * p.T + threadIdx.x];
         }
     }
+    if (rs < rpp) {
 #pragma unroll
-    for (int j = 0; j < TMAX; ++j)
-        if (j < p.T) atomicAdd(p.dWt + (long long)j * p.W + c, dw[j]);
-    if (p.dcol) atomicAdd(p.dcol + c, dcol);
-    if (p.dbt && c < p.T) atomicAdd(p.dbt + c, dbt);
-}
-
-// row-major dt[m][T] (generator output layer)
-template <int TMAX>
-__global__ void __launch_bounds__(1024) thin_bwd_kernel(ThinBwdParams p) {
-    extern __shared__ float s_dt[];  // [64][T]
-    thin_bwd_body<TMAX, false>(p, 1, s_dt);
-}
-// planar dt (B, T, G, P) with rows m = (b*G + r)*P + pos (encoder heads); dt_outer = T*G*P, dt_chan = G*P
-__global__ void __launch_bounds__(256) thin_bwd_heads_kernel(ThinBwdParams p, int G) {
-    extern __shared__ float s_dt[];
-    thin_bwd_body<kMaxHeads + 1, true>(p, G, s_dt);
+        for (int j = 0; j < TMAX; ++j) {
+            if (j < p.T) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) atomicAdd(s_red + j * p.W + c0 + v, dw[j][v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) atomicAdd(s_red + p.T * p.W + c0 + v, dcol[v]);
+    }
+    if (p.dbt && threadIdx.x < p.T) s_red[(p.T + 1) * p.W + threadIdx.x] = dbt;
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.T * p.W; i += blockDim.x) atomicAdd(p.dWt + i, s_red[i]);
+    if (p.dcol)
+        for (int i = threadIdx.x; i < p.W; i += blockDim.x) atomicAdd(p.dcol + i, s_red[p.T * p.W + i]);
+    if (p.dbt && threadIdx.x < p.T) atomicAdd(p.dbt + threadIdx.x, s_red[(p.T + 1) * p.W + threadIdx.x]);
 }
 
 // column sums per group of rows: out[g][c] = sum_{m in group g} x[m][c]   (z-conditioned bias gradient),

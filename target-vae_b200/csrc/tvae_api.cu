@@ -52,6 +52,22 @@ int check_enc_shape(const tvae_enc_shape* s) {
     return 0;
 }
 
+template <int TMAX, int VEC, bool PLANAR>
+int launch_thin_bwd(ThinBwdParams& p, int G, cudaStream_t st) {
+    TVAE_REQUIRE(p.W % VEC == 0 && p.W / VEC <= 256 && p.T <= TMAX, "thin backward: unsupported width");
+    const int cgs = p.W / VEC;
+    const int rpp = 256 / cgs > 0 ? 256 / cgs : 1;
+    long long rows = (p.M + 148LL * 8 - 1) / (148LL * 8);
+    rows = (rows + kThinRB - 1) / kThinRB * kThinRB;
+    p.rows_per_cta = static_cast<int>(rows);
+    const size_t sm = sizeof(float) * (kThinRB * p.T + (p.T + 1) * p.W + p.T);
+    TVAE_REQUIRE(sm <= 48 * 1024, "thin backward: shared memory");
+    ++g_launch_count;
+    thin_bwd_kernel<TMAX, VEC, PLANAR><<<cdiv(p.M, rows), cgs * rpp, sm, st>>>(p, G);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <class P>
 int launch_split_tn(typename P::Params& p, int out_tiles, int chunks_total, int align, int extra, cudaStream_t st) {
     int splits = cdiv(2 * sm_count(), out_tiles);
@@ -231,17 +247,13 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         ThinBwdParams p{};
         p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
         p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
-        // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]: group = (b*G + r) is not affine in j,
-        // so address through b and r: outer index = m / P = b*G + r.
-        p.dt_outer = 0; p.dt_chan = 0;  // unused by the planar accessor below
-        p.rows_per_cta = 1024;
-        // planar accessor: encode G and NH for the kernel via dt_outer / dt_chan
+        // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]
         p.dt_outer = (long long)NH * g.G * g.P;   // stride of b
         p.dt_chan = (long long)g.G * g.P;         // stride of channel j
-        const int grid = cdiv(R, p.rows_per_cta);
-        const size_t sm = 64 * NH * sizeof(float);
-        ++g_launch_count; thin_bwd_heads_kernel<<<grid, g.O, sm, st>>>(p, g.G);
-        TVAE_CHECK_CUDA(cudaGetLastError());
+        if (NH <= 8) rc = launch_thin_bwd<8, 4, true>(p, g.G, st);
+        else if (NH <= 20) rc = launch_thin_bwd<20, 2, true>(p, g.G, st);
+        else rc = launch_thin_bwd<kMaxHeads + 1, 1, true>(p, g.G, st);
+        if (rc) return rc;
     }
     // ---- dW2 = dhpre^T x1
     if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st))) return rc;
@@ -371,8 +383,8 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
         if (rc) return rc;
     } else {
-        const int rows_per_cta = 64;
-        ++g_launch_count; coord_layer_fwd_kernel<<<cdiv(M, rows_per_cta), H, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, rows_per_cta);
+        const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
+        ++g_launch_count; coord_layer_fwd_kernel<<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (s->L == 0) {
@@ -419,9 +431,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         p.a = a->f.acts + (long long)L * M * H; p.dt = a->d_yhat; p.Wt = a->f.wout; p.dpre = dcur;
         p.dWt = a->dwout; p.dbt = a->dbout; p.dcol = (L > 0) ? a->dbh + (long long)(L - 1) * H : nullptr;
         p.M = M; p.W = H; p.T = s->n_out; p.P = 1; p.dt_outer = s->n_out; p.dt_chan = 1;
-        p.rows_per_cta = 1024;
-        ++g_launch_count; thin_bwd_kernel<4><<<cdiv(M, p.rows_per_cta), H, 64 * s->n_out * sizeof(float), st>>>(p);
-        TVAE_CHECK_CUDA(cudaGetLastError());
+        if ((rc = launch_thin_bwd<4, 4, false>(p, 1, st))) return rc;
     }
     // ---- hidden layers, last to first
     for (int i = L; i >= 1; --i) {
@@ -477,8 +487,11 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
             if (rc) return rc;
         }
     } else {
-        ++g_launch_count; coord_layer_bwd_w_kernel<<<cdiv(M, 2048), H, 0, st>>>(cx, dcur, a->dw1, H, 2048);
-        ++g_launch_count; coord_layer_bwd_x_kernel<<<cdiv(M, 8), 256, 0, st>>>(a->f.w1, dcur, a->dxp, M, H);
+        const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
+        long long rows = (M + 148LL * 8 - 1) / (148LL * 8);
+        rows = (rows + kCoordRB - 1) / kCoordRB * kCoordRB;
+        const size_t sm = sizeof(float) * (4 * kCoordRB + 2 * H);
+        ++g_launch_count; coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->dw1, a->dxp, H, static_cast<int>(rows));
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (a->f.theta && a->d_theta) {
@@ -492,7 +505,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
 int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat, const float* g, int B, int E, void* stream) {
     cudaStream_t st = S(stream);
     TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
-    dim3 grid(blocks_for(E, 256, 32), B);
+    dim3 grid(1, B);   // one CTA per image: ll[b] is a fixed-order sum (bit-deterministic forward)
     ++g_launch_count; bernoulli_kernel<<<grid, 256, 0, st>>>(y_hat, y, ll, d_yhat, E, g);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -517,7 +530,7 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
         ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n);
         mu_in = mu;
     }
-    dim3 grid(blocks_for(n * n, 256, 32), B);
+    dim3 grid(1, B);   // one CTA per image: deterministic ll[b]
     float* dmu_out = d_yhat ? (ctf ? dmu : d_yhat) : nullptr;
     ++g_launch_count; gaussian_kernel<<<grid, 256, 0, st>>>(mu_in, y, dx, s, n, radius, ll, dmu_out, g);
     if (ctf && d_yhat) { ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n); }
