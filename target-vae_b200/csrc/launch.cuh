@@ -2,6 +2,7 @@
 #pragma once
 #include "host_utils.cuh"
 #include "linear_policies.cuh"
+#include "tc_gemm2.cuh"
 
 namespace tvae {
 
@@ -32,6 +33,34 @@ inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t st
     ++g_launch_count;
     const int tslot = g_timer.begin(P::kName, stream);
     tc_gemm_kernel<P><<<grid, threads, L.total, stream>>>(prm);
+    g_timer.end(tslot, stream);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// CTA-pair kernel: grid = 2 x min(#pairs on the device, tiles), cluster dims (2,1,1) are part of the kernel.
+inline int pick_stages2(int extra_bytes) {
+    const Smem2Layout L0 = make_smem2_layout(0, extra_bytes);
+    int s = (kMaxSmemBytes - static_cast<int>(L0.total) - 1024) / kStage2Bytes;
+    if (s > kMaxStages) s = kMaxStages;
+    return s;
+}
+template <class P>
+inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t stream) {
+    prm.num_stages = pick_stages2(extra_bytes);
+    if (prm.num_stages < 2) return fail(-1, "pair tile does not fit shared memory with >= 2 stages");
+    if (prm.num_tiles <= 0) return 0;
+    const Smem2Layout L = make_smem2_layout(prm.num_stages, extra_bytes);
+    static bool configured = false;  // per policy instantiation
+    if (!configured) {
+        TVAE_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+        configured = true;
+    }
+    const int pairs_dev = sm_count() / 2;
+    const int pairs = prm.num_tiles < pairs_dev ? prm.num_tiles : pairs_dev;
+    ++g_launch_count;
+    const int tslot = g_timer.begin(P::kName, stream);
+    tc_gemm2_kernel<P><<<2 * pairs, kPairThreads, L.total, stream>>>(prm);
     g_timer.end(tslot, stream);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;

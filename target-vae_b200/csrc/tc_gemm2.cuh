@@ -1,0 +1,262 @@
+// CTA-pair (cta_group::2) persistent TF32 GEMM core for the group convolution and its weight gradient.
+//
+//   D[256 x 512] (fp32, TMEM of both CTAs) += A[256 x K] * B[512 x K]^T        per pair-tile
+//
+// Two CTAs of one cluster (the two SMs of a TPC) share every tcgen05.mma: the pair computes 256 accumulator
+// rows (128 per CTA) and each CTA stages only HALF of the B tile, which halves both the L2->SM operand
+// stream and the shared-memory bandwidth the tensor core needs per FLOP.  The accumulator fills TMEM:
+// two N = 256 accumulators per CTA, both fed from the same generated A stage, so the synthesised im2col
+// operand is produced once per 512 output columns.
+//
+// Warp roles in BOTH CTAs (512 threads):
+//   warp 0      TMA producer: this CTA's half of the B tile, complete_tx on the LEADER's full barrier
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, M = 256, N = 256
+//   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, same warp in both CTAs)
+//   warps 4-7   epilogue: tcgen05.ld of this CTA's 128 accumulator rows -> policy epilogue
+//   warps 8-15  operand generators: synthesise this CTA's 128 A rows straight into swizzled smem
+// Barriers: full[s] lives in the leader (1 expect_tx arrive + one arrive per generator warp of both CTAs);
+// empty[s] and tfull live in each CTA and are signalled by a multicast tcgen05.commit; tempty lives in the
+// leader and collects one arrive per epilogue warp of both CTAs.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace tvae {
+
+constexpr int kPairThreads = 512;
+constexpr int kGenWarps = 8;
+constexpr int kAcc = 2;                 // accumulators per CTA (N = 256 each)
+constexpr int kAccN = 256;
+constexpr int kBHalfBytes = 128 * 128;  // this CTA's half of one accumulator's B stage
+constexpr int kStage2Bytes = kAStageBytes + kAcc * kBHalfBytes;   // 48 KB
+
+// ---------------------------------------------------------------- cluster / pair PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D TMA load issued by either CTA of the pair; bytes are credited to the mbarrier at `bar_cluster`
+// (a shared::cluster address, normally the leader's full barrier).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once all previously issued MMAs of this thread retire) on the barrier at the same smem offset in
+// every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
+struct PairTile {
+    int n0;              // first accumulator column of the pair-tile
+    int n_acc;           // accumulators in use (1 or 2)
+    int kc_begin, kc_end;
+    int m_tile;          // this CTA's own 128-row tile index (policy space), -1 = none (padding half)
+    int a0, a1, a2;      // policy scratch
+};
+
+struct Smem2Layout {
+    uint32_t stage_off, bar_off, tmem_ptr_off, extra_off, total;
+};
+__host__ __device__ inline Smem2Layout make_smem2_layout(int stages, int extra_bytes) {
+    Smem2Layout L;
+    L.stage_off = 0;
+    L.bar_off = stages * kStage2Bytes;
+    L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 2) * 8;
+    L.extra_off = (L.tmem_ptr_off + 16 + 127) & ~127u;
+    L.total = L.extra_off + extra_bytes;
+    return L;
+}
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t kIdesc = make_idesc_tf32(256, kAccN, P::kAMajorMN, P::kBMajorMN);
+
+    const int stages = prm.num_stages;
+    const Smem2Layout L = make_smem2_layout(stages, 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+    uint8_t* extra = smem + L.extra_off;
+
+    const uint32_t full_bar = smem_u32(bars);                       // [stages]   (used in the leader)
+    const uint32_t empty_bar = smem_u32(bars + kMaxStages);          // [stages]   (each CTA)
+    const uint32_t tfull_bar = smem_u32(bars + 2 * kMaxStages);      // each CTA
+    const uint32_t tempty_bar = smem_u32(bars + 2 * kMaxStages + 1); // leader
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) P::prefetch_descs(prm);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar + 8 * s, 1 + 2 * kGenWarps);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 2 * kEpiWarps);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(tmem_ptr_smem), 512);
+        tmem_relinquish_pair();
+    }
+    P::setup(prm, extra, threadIdx.x, blockDim.x);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // barrier inits of both CTAs are visible before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_pairs = gridDim.x >> 1;
+    const int pair = blockIdx.x >> 1;
+    const long long nt = prm.num_tiles;
+    const int tile_begin = static_cast<int>(nt * pair / n_pairs);
+    const int tile_end = static_cast<int>(nt * (pair + 1) / n_pairs);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t full_leader = mapa_rank(full_bar, 0);
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                PairTile ti;
+                P::tile_info(prm, tile, rank, ti);
+                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full_leader + 8 * stage;
+                    if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2u * ti.n_acc * kBHalfBytes);
+                    const uint32_t sb = smem_u32(smem + L.stage_off + stage * kStage2Bytes + kAStageBytes);
+                    for (int a = 0; a < ti.n_acc; ++a)
+                        P::issue_tma(prm, ti, kc, ti.n0 + a * kAccN + static_cast<int>(rank) * 128, sb + a * kBHalfBytes, fb);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader only)
+        if (leader && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                PairTile ti;
+                P::tile_info(prm, tile, rank, ti);
+                mbar_wait(tempty_bar, tphase ^ 1);
+                tc_fence_after();
+                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + L.stage_off + stage * kStage2Bytes);
+                    const uint32_t b_addr = a_addr + kAStageBytes;
+                    for (int a = 0; a < ti.n_acc; ++a) {
+#pragma unroll
+                        for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+                            uint64_t adesc, bdesc;
+                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            const uint32_t bb = b_addr + a * kBHalfBytes;
+                            if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                            else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
+                            umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit_pair(empty_bar + 8 * stage, 3);   // frees the slot in both CTAs
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(tfull_bar, 3);                   // accumulators complete -> both epilogues
+                tphase ^= 1;
+            }
+        }
+    } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
+        // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int ewarp = warp - kFirstEpiWarp;
+        const int row = ewarp * 32 + lane;
+        uint32_t tphase = 0;
+        const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            PairTile ti;
+            P::tile_info(prm, tile, rank, ti);
+            mbar_wait(tfull_bar, tphase);
+            tc_fence_after();
+            const bool has_work = ti.kc_end > ti.kc_begin;
+            for (int a = 0; a < ti.n_acc; ++a) {
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + a * kAccN;
+                P::epilogue(prm, ti, ti.n0 + a * kAccN, taddr, row, has_work, extra);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);
+            tphase ^= 1;
+        }
+    } else if (warp >= kFirstProdWarp) {
+        // ------------------------------------------------------------ operand generators (both CTAs)
+        const int ptid = threadIdx.x - kFirstProdWarp * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t full_leader = mapa_rank(full_bar, 0);
+        typename P::GenState gst;
+        P::gen_init(prm, gst, extra, ptid);
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            PairTile ti;
+            P::tile_info(prm, tile, rank, ti);
+            P::gen_tile_begin(prm, ti, gst, extra, ptid);
+            for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                P::gen_chunk(prm, ti, gst, kc, smem + L.stage_off + stage * kStage2Bytes, extra, ptid);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_leader + 8 * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // no CTA exits (or frees TMEM) while its peer can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+}  // namespace tvae

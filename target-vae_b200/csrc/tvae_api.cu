@@ -2,6 +2,7 @@
 #include "../../include/tvae_b200.h"
 
 #include "conv_policies.cuh"
+#include "conv2_policies.cuh"
 #include "gen_policies.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
@@ -143,44 +144,67 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
 }  // extern "C"
 
 namespace {
-// conv1: implicit GEMM with generated im2col operand
+// conv1: implicit GEMM with the im2col operand generated on chip (CTA-pair kernel, tc_gemm2.cuh)
+SlabGeom make_slab(const ConvGeom& g, int rows_max) {
+    SlabGeom sg{};
+    sg.Wp = g.n + 2 * g.p;
+    sg.pitch = (sg.Wp + 3) / 4 * 4;
+    sg.rows_max = rows_max < sg.Wp ? rows_max : sg.Wp;
+    return sg;
+}
 int conv1_forward(const ConvGeom& g, const float* y, const float* bank, const float* bias, float* x1, int act, cudaStream_t st) {
-    Conv1FwdParams p{};
+    Conv1Fwd2Params p{};
     const int N = g.G * g.O;
-    const bool wide = N > 128;
-    const int BN = wide ? 256 : 128;
     int rc;
-    if ((rc = make_tmap_2d(&p.tmB, bank, N, g.kpad, g.kpad, BN))) return rc;
+    if ((rc = make_tmap_2d(&p.tmB, bank, N, g.kpad, g.kpad, 128))) return rc;
     p.g = g;
     p.y = y; p.bias = bias; p.x1 = x1; p.act = act;
-    p.tiles_n = cdiv(N, BN);
+    p.n_passes = cdiv(N, kAcc * kAccN);
     p.tiles_per_image = cdiv(g.P, kBM);
+    p.m_tiles = g.B * p.tiles_per_image;
     p.k_chunks = cdiv(g.K, kBK);
-    p.num_tiles = g.B * p.tiles_per_image * p.tiles_n;
-    const int span_rows = (kBM - 1) / g.d + 2;
-    int slab_rows = span_rows + g.k - 1;
-    if (slab_rows > g.n) slab_rows = g.n;
-    p.slab_rows_max = slab_rows;
-    const int extra = g.C * slab_rows * g.n * static_cast<int>(sizeof(float));
-    return wide ? launch_gemm<Conv1Fwd<256>>(p, extra, st) : launch_gemm<Conv1Fwd<128>>(p, extra, st);
+    p.num_tiles = cdiv(p.m_tiles, 2) * p.n_passes;
+    p.sg = make_slab(g, (kBM - 1) / g.d + 2 + g.k - 1);
+    p.gran = (g.k % 4 == 0) ? 1 : 0;
+    p.tab_entries = p.k_chunks * (p.gran ? kBK / 4 : kBK);
+    const int extra = p.tab_entries * 4 + g.C * p.sg.rows_max * p.sg.pitch * static_cast<int>(sizeof(float));
+    return launch_gemm2<Conv1Fwd2>(p, extra, st);
 }
-// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed)
+// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); column kk == K accumulates the bias gradient
 int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dbank, cudaStream_t st) {
-    Conv1WgradParams p{};
+    Conv1Wgrad2Params p{};
     const int N = g.G * g.O;
     const long long R = (long long)g.B * g.G * g.P;
-    const bool wide = N > 128;
-    const int BN = wide ? 256 : 128;
     int rc;
     if ((rc = make_tmap_2d(&p.tmQ, dx1, R, g.O, g.O, kBK, true))) return rc;
-    p.g = g; p.y = y; p.dbank = dbank;
-    p.tiles_m = cdiv(g.K + 1, kBM);     // + ones column
-    p.tiles_n = cdiv(N, BN);
+    p.g = g; p.y = y; p.dbank = dbank; p.ones_col = 1;
+    p.m_tiles = cdiv(g.K + 1, kBM);     // + ones column
+    p.m_pairs = cdiv(p.m_tiles, 2);
+    p.n_passes = cdiv(N, kAcc * kAccN);
     p.chunks_per_image = cdiv(g.P, kBK);
-    const int extra = g.C * g.n * g.n * static_cast<int>(sizeof(float));
-    const int out_tiles = p.tiles_m * p.tiles_n;
-    return wide ? launch_split_tn<Conv1Wgrad<256>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st)
-                : launch_split_tn<Conv1Wgrad<128>>(p, out_tiles, g.B * p.chunks_per_image, p.chunks_per_image, extra, st);
+    p.chunks_total = g.B * p.chunks_per_image;
+    // slab: one channel and the few padded rows a 128-wide kk tile touches, or whole padded channels when a tile can
+    // straddle channels
+    const bool straddles = g.C > 1 && (g.k * g.k) % kBM != 0;
+    const int nc_max = straddles ? (g.C < kBM / (g.k * g.k) + 2 ? g.C : kBM / (g.k * g.k) + 2) : 1;
+    p.sg = make_slab(g, straddles ? g.n + 2 * g.p : g.d + (kBM - 1) / g.k + 1);
+    const int extra = kBM * 4 + nc_max * p.sg.rows_max * p.sg.pitch * static_cast<int>(sizeof(float));
+    // reduction splits: minimise waves x (chunks per split + epilogue) over the CTA pairs of the device
+    const int out_tiles = p.m_pairs * p.n_passes;
+    const int pairs_dev = sm_count() / 2;
+    double best = 1e30;
+    int best_cps = p.chunks_total;
+    for (int s = 1; s <= 64 && s <= p.chunks_total; ++s) {
+        const int cps = cdiv(p.chunks_total, s);
+        const int s_eff = cdiv(p.chunks_total, cps);
+        const int waves = cdiv((long long)out_tiles * s_eff, pairs_dev);
+        const double cost = waves * (cps * 1024.0 + 60000.0);
+        if (cost < best) { best = cost; best_cps = cps; }
+    }
+    p.chunks_per_split = best_cps;
+    p.splits = cdiv(p.chunks_total, best_cps);
+    p.num_tiles = out_tiles * p.splits;
+    return launch_gemm2<Conv1Wgrad2>(p, extra, st);
 }
 }  // namespace
 
