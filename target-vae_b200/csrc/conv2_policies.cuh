@@ -18,7 +18,7 @@ namespace tvae {
 
 struct SlabGeom {
     int Wp;        // padded image width  n + 2p
-    int pitch;     // slab row pitch in floats (multiple of 4)
+    int pitch;     // slab row pitch in floats, = d (mod 32) so that lane-consecutive cells never bank-conflict
     int rows_max;  // slab rows allocated per channel
 };
 
@@ -48,6 +48,8 @@ struct Conv1Fwd2Params {
     int act;
     int gran;                 // 1: offset table per 4-float granule (k % 4 == 0), 0: per element
     int tab_entries;
+    int skip;                 // 1: skip K chunks that only meet zero padding (needs k*k % 32 == 0)
+    int chunks_per_channel;   // k*k / 32 when skip, else k_chunks
 };
 
 struct Conv1Fwd2 : PolicyBase {
@@ -73,17 +75,46 @@ struct Conv1Fwd2 : PolicyBase {
             tab[e] = off;
         }
     }
+    // Zero-padding skip: filter row v only meets image rows for output rows i with 0 <= i + v - p < n.  For the
+    // output rows of BOTH CTAs' tiles the live v range is [v_lo, v_hi); K chunks outside it multiply zeros and
+    // are never generated, loaded or issued (cfg2/cfg3: ~25 % of the dense count).  Needs chunk-aligned channels.
     __device__ static void tile_info(const Params& p, int tile, uint32_t rank, PairTile& ti) {
+        const ConvGeom& g = p.g;
         const int mp = tile / p.n_passes, np = tile - mp * p.n_passes;
-        const int N = p.g.G * p.g.O;
+        const int N = g.G * g.O;
         ti.n0 = np * (kAcc * kAccN);
         ti.n_acc = (N - ti.n0 > kAccN) ? 2 : 1;
-        ti.kc_begin = 0;
-        ti.kc_end = p.k_chunks;
         const int mt = 2 * mp + static_cast<int>(rank);
         ti.m_tile = mt < p.m_tiles ? mt : -1;
         ti.a0 = mt / p.tiles_per_image;                               // image
         ti.a1 = (mt - ti.a0 * p.tiles_per_image) * kBM;               // first position
+        if (p.skip) {
+            int v_lo = g.k, v_hi = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * mp + h;
+                if (t < p.m_tiles) {
+                    const int pos0 = (t % p.tiles_per_image) * kBM;
+                    const int i_first = pos0 / g.d, i_last = min(pos0 + kBM - 1, g.P - 1) / g.d;
+                    v_lo = min(v_lo, max(0, g.p - i_last));
+                    v_hi = max(v_hi, min(g.k, g.p - i_first + g.n));
+                }
+            }
+            const int lo = (v_lo * g.k) / kBK, hi = (v_hi * g.k + kBK - 1) / kBK;   // chunks within one channel
+            ti.a2 = lo;
+            ti.a3 = hi > lo ? hi - lo : 0;
+            ti.kc_begin = 0;
+            ti.kc_end = g.C * ti.a3;
+        } else {
+            ti.a2 = 0;
+            ti.a3 = p.k_chunks;
+            ti.kc_begin = 0;
+            ti.kc_end = p.k_chunks;
+        }
+    }
+    __device__ static int chunk(const Params& p, const PairTile& ti, int q) {
+        const int c = q / ti.a3;
+        return c * p.chunks_per_channel + ti.a2 + (q - c * ti.a3);
     }
     __device__ static void issue_tma(const Params& p, const PairTile&, int kc, int n_row0, uint32_t sb, uint32_t bar) {
         tma_load_2d_pair(sb, &p.tmB, bar, kc * kBK, n_row0);
@@ -177,6 +208,7 @@ struct Conv1Wgrad2Params {
     const float* y;
     float* dbank;             // [G*O][kpad], zero-filled by the caller
     int ones_col;             // 1: accumulator row kk == K is fed with ones (conv1 bias gradient)
+    int skip;                 // 1: skip position chunks that only meet zero padding
 };
 
 struct Conv1Wgrad2 : PolicyBase {
@@ -189,19 +221,45 @@ struct Conv1Wgrad2 : PolicyBase {
         int c_lo, r_lo;
     };
     __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmQ); }
+    // Zero-padding skip: accumulator rows kk of the pair cover filter rows [va, vb]; only output rows i with
+    // 0 <= i + v - p < n for some such v contribute, i.e. a contiguous range of position chunks per image.
+    // The reduction runs over the compact index q = b * cnt + (pc - lo) and is split evenly in q.
     __device__ static void tile_info(const Params& p, int tile, uint32_t rank, PairTile& ti) {
+        const ConvGeom& g = p.g;
         const int per_split = p.m_pairs * p.n_passes;
         const int sp = tile / per_split;
         const int rem = tile - sp * per_split;
         const int mp = rem / p.n_passes, np = rem - mp * p.n_passes;
-        const int N = p.g.G * p.g.O;
+        const int N = g.G * g.O;
         ti.n0 = np * (kAcc * kAccN);
         ti.n_acc = (N - ti.n0 > kAccN) ? 2 : 1;
-        ti.kc_begin = sp * p.chunks_per_split;
-        ti.kc_end = min(ti.kc_begin + p.chunks_per_split, p.chunks_total);
         const int mt = 2 * mp + static_cast<int>(rank);
         ti.m_tile = mt < p.m_tiles ? mt : -1;
         ti.a0 = mt * kBM;                                             // first kk of this CTA's accumulator rows
+        int lo = 0, cnt = p.chunks_per_image;
+        const int kk0 = 2 * mp * kBM, kk1 = kk0 + 2 * kBM - 1;        // kk range of the pair
+        if (p.skip && !(p.ones_col && kk1 >= g.K)) {
+            const Im2colCursor c0 = im2col_cursor(kk0, g.k), c1 = im2col_cursor(min(kk1, g.K - 1), g.k);
+            if (c0.c == c1.c) {
+                const int i_lo = max(0, g.p - c1.v), i_hi = min(g.d - 1, g.p - c0.v + g.n - 1);
+                if (i_hi >= i_lo) {
+                    lo = (i_lo * g.d) / kBK;
+                    cnt = ((i_hi + 1) * g.d + kBK - 1) / kBK - lo;
+                } else {
+                    cnt = 0;
+                }
+            }
+        }
+        ti.a1 = lo;
+        ti.a2 = cnt;
+        const int total = g.B * cnt;
+        const int cps = (total + p.splits - 1) / p.splits;
+        ti.kc_begin = min(sp * cps, total);
+        ti.kc_end = min(ti.kc_begin + cps, total);
+    }
+    __device__ static int chunk(const Params& p, const PairTile& ti, int q) {
+        const int b = q / ti.a2;
+        return b * p.chunks_per_image + ti.a1 + (q - b * ti.a2);
     }
     // B-half of one accumulator: 128 (r,o) columns starting at n_col0, reduction rows = 32 positions of chunk kc
     __device__ static void issue_tma(const Params& p, const PairTile&, int kc, int n_col0, uint32_t sb, uint32_t bar) {
@@ -249,12 +307,18 @@ struct Conv1Wgrad2 : PolicyBase {
         const ConvGeom& g = p.g;
         const int* tab = reinterpret_cast<const int*>(extra);
         float* slab = reinterpret_cast<float*>(extra + kBM * 4);
-        const int rrow = ptid & 31, cb = (ptid >> 5) & 3, half = ptid >> 7;
+        // lane -> (position row, chunk parity): every aligned group of 8 lanes covers 4 rows x 2 adjacent 16-byte
+        // chunks = 8 distinct slots of the 32-byte-atom swizzle (conflict-free STS.128), while the LDS stay within
+        // 20 consecutive words.  warp -> (32-wide kk block, half of the 32 position rows).
+        const int lane = ptid & 31, w = ptid >> 5;
+        const int cb = w & 3;
+        const int rrow = (lane & 3) | (((lane >> 3) & 3) << 2) | ((w >> 2) << 4);
+        const int par = (lane >> 2) & 1;
         uint8_t* blk = a_stage + cb * (kBK * 128);
         if (ti.m_tile < 0) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
-                *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, half * 4 + ch)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, 2 * ch + par)) = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
         }
         const int b = kc / p.chunks_per_image, pc = kc - b * p.chunks_per_image;
@@ -274,13 +338,14 @@ struct Conv1Wgrad2 : PolicyBase {
         const float* src = slab + i * p.sg.pitch + j;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            const int4 o = *reinterpret_cast<const int4*>(tab + cb * 32 + half * 16 + ch * 4);
+            const int chunk = 2 * ch + par;
+            const int4 o = *reinterpret_cast<const int4*>(tab + cb * 32 + chunk * 4);
             float4 v;
             v.x = !valid ? 0.f : (o.x >= 0 ? src[o.x] : (o.x == -2 ? 1.f : 0.f));
             v.y = !valid ? 0.f : (o.y >= 0 ? src[o.y] : (o.y == -2 ? 1.f : 0.f));
             v.z = !valid ? 0.f : (o.z >= 0 ? src[o.z] : (o.z == -2 ? 1.f : 0.f));
             v.w = !valid ? 0.f : (o.w >= 0 ? src[o.w] : (o.w == -2 ? 1.f : 0.f));
-            *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, half * 4 + ch)) = v;
+            *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, chunk)) = v;
         }
     }
     __device__ static void epilogue(const Params& p, const PairTile& ti, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {

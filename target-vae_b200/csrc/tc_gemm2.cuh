@@ -44,8 +44,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Default (.release.cta) semantics on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR per
+// call, which throttled the generator warps to ~45 % tensor-pipe activity (profiles/r01_conv_pair_ncu.md).  The
+// operand bytes are published to the async proxy by fence.proxy.async before the arrive, and each CTA's tile is
+// read by its own SM's tensor core.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D TMA load issued by either CTA of the pair; bytes are credited to the mbarrier at `bar_cluster`
 // (a shared::cluster address, normally the leader's full barrier).
@@ -85,9 +89,9 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
 struct PairTile {
     int n0;              // first accumulator column of the pair-tile
     int n_acc;           // accumulators in use (1 or 2)
-    int kc_begin, kc_end;
+    int kc_begin, kc_end;  // compact reduction steps [kc_begin, kc_end); P::chunk maps a step to its K chunk
     int m_tile;          // this CTA's own 128-row tile index (policy space), -1 = none (padding half)
-    int a0, a1, a2;      // policy scratch
+    int a0, a1, a2, a3;  // policy scratch
 };
 
 struct Smem2Layout {
@@ -148,9 +152,9 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
 
     const int n_pairs = gridDim.x >> 1;
     const int pair = blockIdx.x >> 1;
-    const long long nt = prm.num_tiles;
-    const int tile_begin = static_cast<int>(nt * pair / n_pairs);
-    const int tile_end = static_cast<int>(nt * (pair + 1) / n_pairs);
+    // strided schedule: tile costs vary smoothly with the tile index (zero-padding chunks are skipped), so
+    // interleaving gives every pair the same mix
+    const int tile_begin = pair, tile_end = prm.num_tiles, tile_step = n_pairs;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -158,10 +162,11 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_leader = mapa_rank(full_bar, 0);
-            for (int tile = tile_begin; tile < tile_end; ++tile) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 PairTile ti;
                 P::tile_info(prm, tile, rank, ti);
-                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
+                    const int kc = P::chunk(prm, ti, q);
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t fb = full_leader + 8 * stage;
                     if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2u * ti.n_acc * kBHalfBytes);
@@ -177,12 +182,12 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         if (leader && lane == 0) {
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
-            for (int tile = tile_begin; tile < tile_end; ++tile) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 PairTile ti;
                 P::tile_info(prm, tile, rank, ti);
                 mbar_wait(tempty_bar, tphase ^ 1);
                 tc_fence_after();
-                for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+                for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
                     mbar_wait(full_bar + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + L.stage_off + stage * kStage2Bytes);
@@ -196,7 +201,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                             const uint32_t bb = b_addr + a * kBHalfBytes;
                             if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
                             else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
-                            umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                            umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit_pair(empty_bar + 8 * stage, 3);   // frees the slot in both CTAs
@@ -212,7 +217,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         const int row = ewarp * 32 + lane;
         uint32_t tphase = 0;
         const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
             PairTile ti;
             P::tile_info(prm, tile, rank, ti);
             mbar_wait(tfull_bar, tphase);
@@ -235,11 +240,12 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         const uint32_t full_leader = mapa_rank(full_bar, 0);
         typename P::GenState gst;
         P::gen_init(prm, gst, extra, ptid);
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
             PairTile ti;
             P::tile_info(prm, tile, rank, ti);
             P::gen_tile_begin(prm, ti, gst, extra, ptid);
-            for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
+            for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
+                const int kc = P::chunk(prm, ti, q);
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                 P::gen_chunk(prm, ti, gst, kc, smem + L.stage_off + stage * kStage2Bytes, extra, ptid);
                 fence_proxy_async_smem();

@@ -148,7 +148,8 @@ namespace {
 SlabGeom make_slab(const ConvGeom& g, int rows_max) {
     SlabGeom sg{};
     sg.Wp = g.n + 2 * g.p;
-    sg.pitch = (sg.Wp + 3) / 4 * 4;
+    // pitch = d (mod 32): a warp's 32 consecutive output cells keep consecutive banks across image-row wraps
+    sg.pitch = sg.Wp + (((1 - g.k) % 32) + 32) % 32;
     sg.rows_max = rows_max < sg.Wp ? rows_max : sg.Wp;
     return sg;
 }
@@ -167,6 +168,8 @@ int conv1_forward(const ConvGeom& g, const float* y, const float* bank, const fl
     p.sg = make_slab(g, (kBM - 1) / g.d + 2 + g.k - 1);
     p.gran = (g.k % 4 == 0) ? 1 : 0;
     p.tab_entries = p.k_chunks * (p.gran ? kBK / 4 : kBK);
+    p.skip = ((g.k * g.k) % kBK == 0) ? 1 : 0;
+    p.chunks_per_channel = p.skip ? (g.k * g.k) / kBK : p.k_chunks;
     const int extra = p.tab_entries * 4 + g.C * p.sg.rows_max * p.sg.pitch * static_cast<int>(sizeof(float));
     return launch_gemm2<Conv1Fwd2>(p, extra, st);
 }
@@ -204,6 +207,7 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dban
     p.chunks_per_split = best_cps;
     p.splits = cdiv(p.chunks_total, best_cps);
     p.num_tiles = out_tiles * p.splits;
+    p.skip = 1;
     return launch_gemm2<Conv1Wgrad2>(p, extra, st);
 }
 }  // namespace
