@@ -67,6 +67,24 @@ inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64
     return 0;
 }
 
+// MN-major operand view of a row-major fp32 matrix [rows][cols] (cols % 32 == 0): 3-D map {32 cols, rows, cols/32
+// column blocks} with boxes {32, box_rows, nb}: one TMA fills nb consecutive [box_rows][32] column blocks, each in the
+// 32-byte-atom 128 B swizzle the tensor core needs for MN-major tf32.
+inline int make_tmap_3d_mn(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t nb) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15) || (cols & 31)) return fail(-1, "TMA operand must be 16-byte aligned with whole 32-column blocks");
+    cuuint64_t dims[3] = {32, rows, cols / 32};
+    cuuint64_t strides[2] = {ld * sizeof(float), 32 * sizeof(float)};
+    cuuint32_t box[3] = {32, box_rows, nb};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // ---- optional per-kernel timing (bench.py): CUDA events recorded around every tc_gemm launch on its own stream
 struct KernelTimer {
     static constexpr int kMaxNames = 32;

@@ -46,7 +46,7 @@ inline int pick_stages2(int extra_bytes) {
     return s;
 }
 template <class P>
-inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t stream) {
+inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t stream, int force_pairs = 0) {
     prm.num_stages = pick_stages2(extra_bytes);
     if (prm.num_stages < 2) return fail(-1, "pair tile does not fit shared memory with >= 2 stages");
     if (prm.num_tiles <= 0) return 0;
@@ -57,7 +57,7 @@ inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t s
         configured = true;
     }
     const int pairs_dev = sm_count() / 2;
-    const int pairs = prm.num_tiles < pairs_dev ? prm.num_tiles : pairs_dev;
+    const int pairs = force_pairs > 0 ? force_pairs : (prm.num_tiles < pairs_dev ? prm.num_tiles : pairs_dev);
     ++g_launch_count;
     const int tslot = g_timer.begin(P::kName, stream);
     tc_gemm2_kernel<P><<<2 * pairs, kPairThreads, L.total, stream>>>(prm);

@@ -13,8 +13,9 @@
 //   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, M = 256, N = 256
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, same warp in both CTAs)
 //   warps 4-7   epilogue: tcgen05.ld of this CTA's 128 accumulator rows -> policy epilogue
-//   warps 8-15  operand generators: synthesise this CTA's 128 A rows straight into swizzled smem
-// Barriers: full[s] lives in the leader (1 expect_tx arrive + one arrive per generator warp of both CTAs);
+//   warps 8-15  operand generators: synthesise this CTA's 128 A rows straight into swizzled smem (two groups
+//               of 4 warps, alternate stages)
+// Barriers: full[s] lives in the leader (1 expect_tx arrive + one arrive per generator warp of the owning group in both CTAs);
 // empty[s] and tfull live in each CTA and are signalled by a multicast tcgen05.commit; tempty lives in the
 // leader and collects one arrive per epilogue warp of both CTAs.
 #pragma once
@@ -89,7 +90,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
 struct PairTile {
     int n0;              // first accumulator column of the pair-tile
     int n_acc;           // accumulators in use (1 or 2)
-    int kc_begin, kc_end;  // compact reduction steps [kc_begin, kc_end); P::chunk maps a step to its K chunk
+    int kc_begin, kc_end;  // compact reduction steps [kc_begin, kc_end); the policy's Tma/Gen states map steps to K chunks
     int m_tile;          // this CTA's own 128-row tile index (policy space), -1 = none (padding half)
     int a0, a1, a2, a3;  // policy scratch
 };
@@ -132,7 +133,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
     if (warp == 0 && lane == 0) P::prefetch_descs(prm);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full_bar + 8 * s, 1 + 2 * kGenWarps);
+            mbar_init(full_bar + 8 * s, 1 + kGenWarps);   // expect_tx + 4 generator warps per CTA (one group per stage)
             mbar_init(empty_bar + 8 * s, 1);
         }
         mbar_init(tfull_bar, 1);
@@ -158,21 +159,23 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
+        // One elected lane: everything it does per chunk is on the critical path of the operand stream, so the
+        // policy keeps its coordinates incrementally (TmaState) - no integer division per chunk.
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_leader = mapa_rank(full_bar, 0);
+            typename P::TmaState tst;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 PairTile ti;
                 P::tile_info(prm, tile, rank, ti);
+                P::tma_tile_begin(prm, ti, rank, tst);
                 for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
-                    const int kc = P::chunk(prm, ti, q);
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t fb = full_leader + 8 * stage;
                     if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2u * ti.n_acc * kBHalfBytes);
                     const uint32_t sb = smem_u32(smem + L.stage_off + stage * kStage2Bytes + kAStageBytes);
-                    for (int a = 0; a < ti.n_acc; ++a)
-                        P::issue_tma(prm, ti, kc, ti.n0 + a * kAccN + static_cast<int>(rank) * 128, sb + a * kBHalfBytes, fb);
+                    P::tma_chunk(prm, ti, tst, sb, fb);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -234,7 +237,11 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         }
     } else if (warp >= kFirstProdWarp) {
         // ------------------------------------------------------------ operand generators (both CTAs)
+        // Two groups of 4 warps fill alternate stages: the fixed per-stage latencies (barrier wait, smem round trips,
+        // proxy fence, arrive) of one group hide behind the other group's gathers.  Both groups walk every chunk
+        // (gen_advance) so that slab refills (gen_prepare, all 8 warps) happen at the same logical point.
         const int ptid = threadIdx.x - kFirstProdWarp * 32;
+        const int grp = ptid >> 7, gtid = ptid & 127;
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t full_leader = mapa_rank(full_bar, 0);
@@ -245,12 +252,15 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
             P::tile_info(prm, tile, rank, ti);
             P::gen_tile_begin(prm, ti, gst, extra, ptid);
             for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
-                const int kc = P::chunk(prm, ti, q);
-                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                P::gen_chunk(prm, ti, gst, kc, smem + L.stage_off + stage * kStage2Bytes, extra, ptid);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(full_leader + 8 * stage);
+                P::gen_prepare(prm, ti, gst, extra, ptid);
+                if (((q - ti.kc_begin) & 1) == grp) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    P::gen_chunk(prm, ti, gst, smem + L.stage_off + stage * kStage2Bytes, extra, gtid);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(full_leader + 8 * stage);
+                }
+                P::gen_advance(prm, ti, gst);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
