@@ -99,21 +99,99 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # unmodified reference files, installed by __graft_entry__.build()
+TRAINER_OF = {"cfg1": "train_mnist", "cfg2": "train_dsprites", "cfg3": "train_galaxy", "cfg4": "train_particles",
+              "cfg4b": "train_particles", "cfg5": "train_particles"}
+
+
+def host_threads():
+    """Threads the process can really use: affinity mask clipped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def _reference_step_fn(cfg, B):
+    """eval_minibatch + backward of the UNMODIFIED reference (baseline/_ref), or None when it is not installed."""
+    name = TRAINER_OF.get(cfg.name.split("_")[0])
+    if name is None or not os.path.exists(os.path.join(REF_DIR, name + ".py")):
+        return None
+    import importlib
+    import torch.nn as nn
+    # the product's drop-in `src` package must not shadow the reference's `src`
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    saved = list(sys.path)
+    sys.path[:] = [REF_DIR] + [p for p in sys.path if os.path.abspath(p or ".") != PKG]
+    try:
+        ref_models = importlib.import_module("src.models")
+        trainer = importlib.import_module(name)
+    finally:
+        sys.path[:] = saved
+    assert os.path.abspath(ref_models.__file__).startswith(REF_DIR), ref_models.__file__
+    with contextlib.redirect_stdout(io.StringIO()):
+        gen = ref_models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=nn.LeakyReLU,
+                                          resid=False, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
+        enc = ref_models.InferenceNetwork_AttentionTranslation_AttentionRotation(
+            cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+            groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
+            normal_prior_over_r=cfg.normal_prior_over_r)
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg).items()})
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg).items()})
+    params = list(gen.parameters()) + list(enc.parameters())
+    data = synth.minibatch(cfg, B, seed=0)
+    x = torch.from_numpy(synth.image_coords(cfg.n))
+    y = torch.from_numpy(data["y"])
+    ctf = torch.from_numpy(data["ctf"]) if data["ctf"] is not None else None
+    dev = torch.device("cpu")
+    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+
+    def step():
+        for p in params:
+            p.grad = None
+        if name == "train_particles":
+            elbo, _, _ = trainer.eval_minibatch(x, y, ctf, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G, cfg.p,
+                                                cfg.mask_radius)
+        else:
+            elbo, _, _ = trainer.eval_minibatch(x, y, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G, cfg.n)
+        (-elbo).backward()
+    return step
+
+
 def cpu_reference_images_per_s(cfg, B, steps, warmup):
-    """The reference algorithm (oracle port of eval_minibatch + backward) on the host cores, all threads."""
-    from helpers import oracle_step
-    torch.set_num_threads(os.cpu_count() or 1)
+    """The reference's CPU path on the host cores: the unmodified reference from baseline/_ref when installed
+    (kind "reference"), else the oracle port of eval_minibatch + backward (kind "port").  All usable threads."""
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    step = _reference_step_fn(cfg, B)
+    kind = "reference"
+    if step is None:
+        from helpers import oracle_step
+        kind = "port"
+
+        def step():
+            oracle_step(cfg, B, dtype=torch.float32)
     for _ in range(warmup):
-        oracle_step(cfg, B, dtype=torch.float32)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle_step(cfg, B, dtype=torch.float32)
+        step()
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps
+    return B * steps / dt, dt / steps, kind, threads
 
 
 def default_cpu_batch(cfg):
     return {"cfg1": 48, "cfg2": 16, "cfg3": 4, "cfg4b": 8, "cfg4": 2, "cfg5": 2}.get(cfg.name.split("_")[0], 4)
+
+
+def _cpu_what(kind):
+    return ("unmodified reference train_*.eval_minibatch + (-elbo).backward() from baseline/_ref" if kind == "reference"
+            else "oracle port of eval_minibatch + backward")
 
 
 def run_reference(args, cfg):
@@ -123,15 +201,14 @@ def run_reference(args, cfg):
     B = args.cpu_batch or default_cpu_batch(cfg)
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    ips, s_per_step = cpu_reference_images_per_s(cfg, B, steps, warm)
-    cores = os.cpu_count() or 1
+    ips, s_per_step, kind, threads = cpu_reference_images_per_s(cfg, B, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(cfg, args.batch or cfg.batch, args.gpus),
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} step(s) of {B} images, oracle port of eval_minibatch + backward, torch CPU fp32, "
-                                   f"{torch.get_num_threads()} threads"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{steps} step(s) of {B} images, {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
+                                   f"(os.cpu_count() = {os.cpu_count()})"},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,13 +240,14 @@ def build_models(cfg, dev):
     return gen.to(dev), enc.to(dev)
 
 
-def measure_tf32_peak(dev):
-    """cuBLAS TF32 GEMM 8192^3, best of 10 (same method MEASURED_PEAKS.json uses for bf16)."""
+def measure_tf32_peak(dev, dtype=torch.float32):
+    """cuBLAS TF32 (or fp16) GEMM 8192^3, best of 10 (same method MEASURED_PEAKS.json uses for bf16)."""
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         n = 8192
-        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev); c = torch.empty(n, n, device=dev)
+        a = torch.randn(n, n, device=dev, dtype=dtype); b = torch.randn(n, n, device=dev, dtype=dtype)
+        c = torch.empty(n, n, device=dev, dtype=dtype)
         for _ in range(3):
             torch.matmul(a, b, out=c)
         best = 1e9
@@ -293,6 +371,7 @@ def run_ours(args, cfg):
         pass
     bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     tf32_peak = measure_tf32_peak(dev)
+    f16_peak = measure_tf32_peak(dev, torch.float16)
     roofline = None
     if dom is not None and prof[dom][1] > 0:
         ms_launch = prof[dom][0] / prof[dom][1]
@@ -302,10 +381,21 @@ def run_ours(args, cfg):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(cfg.name.split("_")[0], {}).get(dom)
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": traffic,
-                    "peak_source": "cuBLAS TF32 8192^3 best-of-10 measured in this run (kernel computes in TF32, nominally half "
-                                   "the BF16 rate); MEASURED_PEAKS.json bf16_tflops_sustained = %.1f -> frac_of_bf16 below" % bf16_peak,
+        # the conv1 kernels skip K chunks that only meet zero padding: report the executed-MAC rate next to the
+        # dense-count (contract) figure - the dense-count figure can exceed the tensor peak, the executed one cannot
+        executed = 1.0
+        if dom.startswith("conv1"):
+            es = ops.enc_shape(B, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
+            executed = ops.conv1_executed_fraction(es, dom == "conv1_wgrad")
+        op_peak, op_dtype = (f16_peak, "f16 operands") if dom in ops.F16_KERNELS else (tf32_peak, "tf32 operands")
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": op_peak, "unit": "TFLOP/s",
+                    "frac": achieved / op_peak, "traffic": traffic,
+                    "achieved_counts": "dense MAC count x2 per launch (SURVEY 8d: zero-padding taps included, what cuDNN executes)",
+                    "executed_fraction": executed, "achieved_executed": achieved * executed,
+                    "frac_executed": achieved * executed / op_peak,
+                    "peak_source": f"cuBLAS {op_dtype} 8192^3 best-of-10 measured in this run, same method as "
+                                   "MEASURED_PEAKS.json; bf16_tflops_sustained there = %.1f -> frac_of_bf16" % bf16_peak,
+                    "tf32_peak": tf32_peak, "f16_peak": f16_peak,
                     "frac_of_bf16": achieved / bf16_peak, "ms_per_launch": ms_launch,
                     "share_of_step": prof[dom][0] / ms_total,
                     "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
@@ -313,10 +403,10 @@ def run_ours(args, cfg):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_batch or default_cpu_batch(cfg)
-        ips, _ = cpu_reference_images_per_s(cfg, Bc, 2, 1)
-        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"2 steps of {Bc} images (after 1 warm-up), oracle port of eval_minibatch + backward, torch CPU fp32, "
-                         f"{torch.get_num_threads()} threads"}
+        ips, _, kind, threads = cpu_reference_images_per_s(cfg, Bc, 2, 1)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"2 steps of {Bc} images (after 1 warm-up), {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
+                         f"(os.cpu_count() = {os.cpu_count()})"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

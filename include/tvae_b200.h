@@ -50,6 +50,11 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
 int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream);
 int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, float* dbank, void* stream);
 
+/* Executed / dense-count ratio of the K chunks of tvae_groupconv_fwd (wgrad = 0) or tvae_groupconv_wgrad (wgrad = 1):
+ * chunks that only meet zero padding are skipped.  > 1 is possible for the wgrad (tile-grid padding of the kk rows).
+ * Host-only arithmetic, used by bench.py to report the executed-MAC roofline next to the dense-count one. */
+double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad);
+
 typedef struct {
     const float* y;          /* (B,C,n,n) */
     const float* bank;       /* [G*O][kpad] from tvae_filter_bank_fwd */

@@ -227,6 +227,55 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dban
 
 extern "C" {
 
+// Fraction of the dense K-chunk count the conv1 kernels actually execute (same arithmetic as Conv1Fwd2::tile_info /
+// Conv1Wgrad2::tile_info: chunks that only meet zero padding are skipped).
+double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
+    if (check_enc_shape(s)) return -1.0;
+    const ConvGeom g = make_geom(s);
+    auto imin = [](int a, int b) { return a < b ? a : b; };
+    auto imax = [](int a, int b) { return a > b ? a : b; };
+    double live = 0.0, dense = 0.0;
+    if (!wgrad) {
+        const int tiles_per_image = cdiv(g.P, kBM), m_tiles = g.B * tiles_per_image, m_pairs = cdiv(m_tiles, 2);
+        const int k_chunks = cdiv(g.K, kBK);
+        const bool skip = (g.k * g.k) % kBK == 0;
+        for (int mp = 0; mp < m_pairs; ++mp) {
+            dense += k_chunks;
+            if (!skip) { live += k_chunks; continue; }
+            int v_lo = g.k, v_hi = 0;
+            for (int h = 0; h < 2; ++h) {
+                const int t = 2 * mp + h;
+                if (t >= m_tiles) continue;
+                const int pos0 = (t % tiles_per_image) * kBM;
+                const int i_first = pos0 / g.d, i_last = imin(pos0 + kBM - 1, g.P - 1) / g.d;
+                v_lo = imin(v_lo, imax(0, g.p - i_last));
+                v_hi = imax(v_hi, imin(g.k, g.p - i_first + g.n));
+            }
+            const int lo = (v_lo * g.k) / kBK, hi = (v_hi * g.k + kBK - 1) / kBK;
+            live += hi > lo ? g.C * (hi - lo) : 0;
+        }
+    } else {
+        const int m_tiles = cdiv(g.K + 1, kBM), m_pairs = cdiv(m_tiles, 2), cpi = cdiv(g.P, kBK);
+        for (int mp = 0; mp < m_pairs; ++mp) {
+            dense += cpi;
+            const int kk0 = 2 * mp * kBM, kk1 = kk0 + 2 * kBM - 1;
+            int cnt = cpi;
+            if (kk1 < g.K) {
+                const int c0 = kk0 / (g.k * g.k), c1 = kk1 / (g.k * g.k);
+                const int v0 = (kk0 - c0 * g.k * g.k) / g.k, v1 = (kk1 - c1 * g.k * g.k) / g.k;
+                if (c0 == c1) {
+                    const int i_lo = imax(0, g.p - v1), i_hi = imin(g.d - 1, g.p - v0 + g.n - 1);
+                    cnt = i_hi >= i_lo ? ((i_hi + 1) * g.d + kBK - 1) / kBK - (i_lo * g.d) / kBK : 0;
+                }
+            }
+            live += cnt;
+        }
+        // dense count of the contract has K rows, the kernel's tile grid has 2 * m_pairs * 128
+        dense *= static_cast<double>(g.K) / (2.0 * m_pairs * kBM);
+    }
+    return dense > 0 ? live / dense : 1.0;
+}
+
 int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;

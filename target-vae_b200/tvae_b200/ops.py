@@ -81,6 +81,8 @@ def L():
         lib.tvae_launch_count.restype = ctypes.c_longlong
         lib.tvae_profile_enable.restype = None
         lib.tvae_profile_collect.restype = c_int
+        lib.tvae_conv1_executed_fraction.restype = ctypes.c_double
+        lib.tvae_conv1_executed_fraction.argtypes = [c_void_p, c_int]
         for name in ("tvae_filter_bank_fwd", "tvae_filter_bank_bwd", "tvae_encoder_fwd", "tvae_encoder_bwd",
                      "tvae_attn_log_prior", "tvae_attn_fwd", "tvae_attn_bwd", "tvae_attn_softmax_pair",
                      "tvae_get_latent", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
@@ -338,6 +340,15 @@ def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None):
 # ----------------------------------------------------------------------------------------------- instrumentation
 def launch_count() -> int:
     return int(L().tvae_launch_count())
+
+
+# kernels (names of tvae_profile_collect) whose MMAs run with 16-bit operands (kind::f16); the rest are kind::tf32
+F16_KERNELS: set = set()
+
+
+def conv1_executed_fraction(s: EncShape, wgrad: bool) -> float:
+    """Executed / dense-count K chunks of the conv1 kernels (zero-padding chunks are skipped); host arithmetic."""
+    return float(L().tvae_conv1_executed_fraction(ctypes.cast(ctypes.pointer(s), c_void_p), 1 if wgrad else 0))
 
 
 def profile_enable(on: bool) -> None:
