@@ -163,26 +163,34 @@ def _reference_step_fn(cfg, B):
     return step
 
 
-def cpu_reference_images_per_s(cfg, B, steps, warmup):
+def cpu_reference_images_per_s(cfg, B, steps, warmup, budget_s=12.0):
     """The reference's CPU path on the host cores: the unmodified reference from baseline/_ref when installed
-    (kind "reference"), else the oracle port of eval_minibatch + backward (kind "port").  All usable threads."""
+    (kind "reference"), else the oracle port of eval_minibatch + backward (kind "port").  All usable threads.
+    The sample is bounded: a 2-image probe step estimates the per-image cost and the batch is cut so that one step
+    takes about `budget_s` seconds (never above the requested B)."""
     threads = host_threads()
     torch.set_num_threads(threads)
-    step = _reference_step_fn(cfg, B)
-    kind = "reference"
-    if step is None:
-        from helpers import oracle_step
-        kind = "port"
 
-        def step():
-            oracle_step(cfg, B, dtype=torch.float32)
+    def make(Bx):
+        step = _reference_step_fn(cfg, Bx)
+        if step is not None:
+            return step, "reference"
+        from helpers import oracle_step
+        return (lambda: oracle_step(cfg, Bx, dtype=torch.float32)), "port"
+
+    probe, kind = make(min(2, B))
+    t0 = time.perf_counter()
+    probe()
+    per_image = (time.perf_counter() - t0) / min(2, B)
+    B = max(1, min(B, int(budget_s / max(per_image, 1e-6))))
+    step, kind = make(B)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps, kind, threads
+    return B * steps / dt, dt / steps, kind, threads, B
 
 
 def default_cpu_batch(cfg):
@@ -201,7 +209,7 @@ def run_reference(args, cfg):
     B = args.cpu_batch or default_cpu_batch(cfg)
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    ips, s_per_step, kind, threads = cpu_reference_images_per_s(cfg, B, steps, warm)
+    ips, s_per_step, kind, threads, B = cpu_reference_images_per_s(cfg, B, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -403,7 +411,7 @@ def run_ours(args, cfg):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_batch or default_cpu_batch(cfg)
-        ips, _, kind, threads = cpu_reference_images_per_s(cfg, Bc, 2, 1)
+        ips, _, kind, threads, Bc = cpu_reference_images_per_s(cfg, Bc, 2, 1)
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"2 steps of {Bc} images (after 1 warm-up), {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
                          f"(os.cpu_count() = {os.cpu_count()})"}
