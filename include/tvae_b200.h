@@ -9,7 +9,7 @@
  *   - every pointer is a DEVICE pointer to contiguous fp32 data unless noted; `stream` is a cudaStream_t
  *   - calls never allocate, never synchronise, and are re-entrant; all scratch is passed in by the caller
  *   - return 0 on success, < 0 on error; tvae_last_error() returns the thread-local message
- *   - "tf32" tensors hold fp32 values already rounded to TF32 (10-bit mantissa)
+ *   - "tf32" tensors hold fp32 values already rounded to TF32 (10-bit mantissa); fp16 / bf16 tensors are void*
  *
  * Internal activation layout (rows are (b, r, pos) with pos = i*W' + j, P = H'*W'):
  *   x1, h  : [(b*G + r)*P + pos][O]
@@ -37,18 +37,21 @@ typedef struct {
     int kpad;            /* row pitch of the filter bank: multiple of 32 and > C*k*k (tvae_bank_pitch) */
 } tvae_enc_shape;
 
-int tvae_bank_pitch(int C, int k);
+int tvae_bank_pitch(int C, int k);     /* row pitch (floats) of the fp32 bank GRADIENT dbank */
+int tvae_bank16_pitch(int C, int k);   /* row pitch (halves) of the fp16 bank: C*k*k rounded up to 64 */
 
-/* GroupConv.trans_filter (models.py:174-197): weight (O,C,1,k,k) -> bank [G*O][kpad] (row r*O + o), tf32. */
-int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* bank, void* stream);
-/* adjoint of the above plus conv1 bias gradient from the ones column: dbank [G*O][kpad] ->
- * dweight (O,C,1,k,k), dbias (O).  Both outputs are overwritten. */
+/* GroupConv.trans_filter (models.py:174-197): weight (O,C,1,k,k) -> bank fp16 [G*O][kpad16] (row r*O + o).
+ * The conv GEMMs run kind::f16: an fp16 operand carries the same 11-bit significand as a TF32 one. */
+int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, void* bank, void* stream);
+/* adjoint of the above; the conv1 bias gradient is read from column C*k*k of dbank (rows r*O + o, summed over r),
+ * where the backward kernels deposit it: dbank [G*O][kpad] -> dweight (O,C,1,k,k), dbias (O).  Both overwritten. */
 int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dweight, float* dbias, void* stream);
 
 /* GroupConv.forward alone (models.py:202-225): out [(b*G + r)*P + pos][O] = conv + bias, no activation.
- * bias may be NULL.  tvae_groupconv_wgrad: dout in the same layout -> dbank [G*O][kpad] (overwritten). */
-int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream);
-int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, float* dbank, void* stream);
+ * bias may be NULL.  tvae_groupconv_wgrad: dout in the same layout -> dbank [G*O][kpad] (overwritten);
+ * dout16 is scratch for the bf16 copy of dout the GEMM consumes (B*G*P*O 16-bit values). */
+int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const void* bank, const float* bias, float* out, void* stream);
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* dbank, void* stream);
 
 /* Executed / dense-count ratio of the K chunks of tvae_groupconv_fwd (wgrad = 0) or tvae_groupconv_wgrad (wgrad = 1):
  * chunks that only meet zero padding are skipped.  > 1 is possible for the wgrad (tile-grid padding of the kk rows).
@@ -57,7 +60,7 @@ double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad);
 
 typedef struct {
     const float* y;          /* (B,C,n,n) */
-    const float* bank;       /* [G*O][kpad] from tvae_filter_bank_fwd */
+    const void* bank;        /* fp16 [G*O][kpad16] from tvae_filter_bank_fwd */
     const float* conv1_bias; /* (O) */
     const float* w2;         /* conv2.weight (O,O) */
     const float* b2;         /* (O) */
@@ -77,10 +80,11 @@ typedef struct {
     const float* y;
     const float* w2;
     const float* wh;
-    float* x1;               /* in: saved activation; overwritten with d(conv1 pre-activation) */
+    const float* x1;         /* in: saved activation LeakyReLU(conv1) */
     const float* h;
     const float* d_heads;    /* (B,NH,G,P) */
     float* dhpre;            /* scratch [B*G*P][O] */
+    void* dx1_16;            /* scratch [B*G*P][O] bf16: d(conv1 pre-activation), the wgrad GEMM's operand */
     float* w2t_tf32;         /* scratch (O,O) */
     float* dbank;            /* out [G*O][kpad] (feed to tvae_filter_bank_bwd) */
     float* dw2;              /* out (O,O) */

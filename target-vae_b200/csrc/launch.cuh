@@ -77,6 +77,8 @@ struct LinearNTArgs {
     const float* aux = nullptr; long long ld_aux = 0;
     int act = 0, round_tf32 = 0;
     const float* proj_w = nullptr; const float* proj_bias = nullptr; float* proj_out = nullptr; int n_proj = 0;
+    void* C16 = nullptr; long long ldc16 = 0;
+    float* colsum = nullptr; long long colsum_stride = 1;
 };
 
 inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
@@ -97,7 +99,10 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.row_bias = a.row_bias; p.rows_per_group = a.rows_per_group; p.ld_rb = a.ld_rb;
     p.aux = a.aux; p.ld_aux = a.ld_aux; p.act = a.act; p.round_tf32 = a.round_tf32;
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
-    return wide ? launch_gemm<LinearNT<256>>(p, 0, stream) : launch_gemm<LinearNT<128>>(p, 0, stream);
+    p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
+    TVAE_REQUIRE(!a.colsum || p.tiles_n == 1, "linear_nt: column sums need a single N tile");
+    return wide ? launch_gemm<LinearNT<256>>(p, LinearNT<256>::kExtraBytes, stream)
+                : launch_gemm<LinearNT<128>>(p, LinearNT<128>::kExtraBytes, stream);
 }
 
 // C[Ma,Nb] (+)= sum_r P[r,Ma] Q[r,Nb]; caller zero-fills C (accumulated with atomics across row splits).

@@ -2,6 +2,7 @@
 //   LinearNT<BN>: C[M,N] = epi(A[M,K] * B[N,K]^T)      (forward linear layers, dgrads with pre-transposed weights)
 //   LinearTN<BN>: C[Ma,Nb] += sum_r P[r,Ma] * Q[r,Nb]  (weight gradients; split over r, fp32 atomics)
 #pragma once
+#include <cuda_bf16.h>
 #include "tc_gemm.cuh"
 
 namespace tvae {
@@ -29,13 +30,55 @@ struct LinearNTParams {
     const float* proj_bias;   // [n_proj]
     float* proj_out;          // [M][n_proj], pre-zeroed
     int n_proj;
+    void* C16;                // [M][ldc16] bf16 copy of the stored value (the conv1 wgrad's MN-major operand) or null
+    long long ldc16;
+    float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient; needs tiles_n == 1) or null
+    long long colsum_stride;
 };
+
+// In: v[j] of lane l = value (row l, column j) of a 32 x 32 block.  Out (returned): in lane l, the sum over the 32
+// rows of column l.  Recursive halving: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const bool up = lane & 16;
+        const float keep = up ? v[j + 16] : v[j], send = up ? v[j] : v[j + 16];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+            const bool up = lane & w;
+            const float keep = up ? a[j + w] : a[j], send = up ? a[j] : a[j + w];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return a[0];
+}
 
 template <int BN>
 struct LinearNT : PolicyBase {
     static constexpr const char* kName = "linear_nt";
     using Params = LinearNTParams;
     static constexpr int kBN = BN;
+    // column sums: extra smem [4 epilogue warps][BN] floats, entry (warp, c*32 + lane) is owned by one thread
+    static constexpr int kExtraBytes = kEpiWarps * BN * 4;
+    __device__ static void epi_init(const Params& p, EpiState&, uint8_t* extra, int row) {
+        if (!p.colsum) return;
+        float* cs = reinterpret_cast<float*>(extra) + (row >> 5) * BN + (row & 31);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) cs[c * 32] = 0.f;
+    }
+    __device__ static void epi_finish(const Params& p, EpiState&, uint8_t* extra, int row) {
+        if (!p.colsum) return;
+        const int lane = row & 31;
+        const float* cs = reinterpret_cast<const float*>(extra) + (row >> 5) * BN + lane;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c)
+            if (c * 32 + lane < p.N) atomicAdd(p.colsum + (long long)(c * 32 + lane) * p.colsum_stride, cs[c * 32]);
+    }
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -52,7 +95,7 @@ struct LinearNT : PolicyBase {
         tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
         tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
     }
-    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
         const int m = ti.m0 + row;
         const bool m_ok = m < p.M;
         float proj[4] = {0.f, 0.f, 0.f, 0.f};
@@ -63,7 +106,11 @@ struct LinearNT : PolicyBase {
             tmem_ld_32x32(taddr + c * 32, r);
             tmem_ld_wait();
             const int n_base = ti.n0 + c * 32;
-            if (!m_ok || n_base >= p.N) continue;
+            if (p.colsum) {                       // warp-uniform path: every lane takes part in the shuffles
+                if (n_base >= p.N) continue;
+            } else if (!m_ok || n_base >= p.N) {
+                continue;
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -95,6 +142,29 @@ struct LinearNT : PolicyBase {
                         v[j + 1] *= lrelu_grad_from_out(t.y);
                         v[j + 2] *= lrelu_grad_from_out(t.z);
                         v[j + 3] *= lrelu_grad_from_out(t.w);
+                    }
+                }
+            }
+            if (p.colsum) {
+                if (!m_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                reinterpret_cast<float*>(extra)[(row >> 5) * BN + c * 32 + (row & 31)] += warp_colsum32(v, row & 31);
+                if (!m_ok) continue;
+            }
+            if (p.C16) {
+                __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.C16) + (long long)m * p.ldc16 + n_base;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (n_base + j < p.N) {
+                        uint4 t;
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(v[j], v[j + 1]);     t.x = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(v[j + 2], v[j + 3]); t.y = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(v[j + 4], v[j + 5]); t.z = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(v[j + 6], v[j + 7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+                        *reinterpret_cast<uint4*>(d16 + j) = t;
                     }
                 }
             }

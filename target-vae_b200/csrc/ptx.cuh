@@ -154,6 +154,20 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
            | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: 16-bit operands (format 0 = FP16, 1 = BF16, chosen per operand) -> FP32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4)                        // c_format = F32
+           | (a_fmt << 7)
+           | (b_fmt << 10)
+           | ((a_mn_major ? 1u : 0u) << 15)
+           | ((b_mn_major ? 1u : 0u) << 16)
+           | (static_cast<uint32_t>(N >> 3) << 17)
+           | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Layout types for 16-bit operands: K-major and MN-major 128 B swizzle (64-element rows, 8-row atoms) and the
+// 64 B swizzle (32-element rows) used for MN-major operands whose contiguous extent is only 32 elements.
+constexpr uint32_t kLayoutSw64 = 4;
+
 // fp32 -> tf32 (round to nearest, ties away), result kept in an fp32 container
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;

@@ -1,6 +1,7 @@
 // CUDA-core helpers around the generator GEMMs: latent bias, no-Fourier first layer, coordinate-gradient
 // reductions, thin output layer.
 #pragma once
+#include <cuda_bf16.h>
 #include "gen_policies.cuh"
 #include "simt_kernels.cuh"
 
@@ -194,6 +195,32 @@ __global__ void bank_bias_grad_kernel(const float* __restrict__ dbank, float* __
     float acc = 0.f;
     for (int r = 0; r < G; ++r) acc += dbank[((long long)r * O + o) * kpad + K];
     dbias[o] = acc;
+}
+
+// out16[r][c] = bf16(in[r][c]) and colsum[c * cs_stride] += sum_r in[r][c]   (standalone GroupConv backward: the
+// gradient arrives in fp32; the wgrad GEMM consumes bf16, the conv1 bias gradient is the column sum)
+__global__ void __launch_bounds__(256) rows_to_bf16_colsum_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out16,
+                                                                  float* __restrict__ colsum, long long cs_stride, long long R, int W,
+                                                                  int rows_per_cta) {
+    extern __shared__ float sm_cs[];
+    for (int c = threadIdx.x; c < W; c += blockDim.x) sm_cs[c] = 0.f;
+    __syncthreads();
+    const int cpr = W / 2;                          // column pairs per row
+    const int rpp = blockDim.x / cpr > 0 ? blockDim.x / cpr : 1;
+    const int cp = threadIdx.x % cpr, rr = threadIdx.x / cpr;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    float s0 = 0.f, s1 = 0.f;
+    if (rr < rpp) {
+        for (long long r = r0 + rr; r < r0 + rows_per_cta && r < R; r += rpp) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(in + r * W) + cp);
+            reinterpret_cast<__nv_bfloat162*>(out16 + r * W)[cp] = __floats2bfloat162_rn(v.x, v.y);
+            s0 += v.x; s1 += v.y;
+        }
+        atomicAdd(&sm_cs[2 * cp], s0);
+        atomicAdd(&sm_cs[2 * cp + 1], s1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += blockDim.x) atomicAdd(colsum + c * cs_stride, sm_cs[c]);
 }
 
 }  // namespace tvae

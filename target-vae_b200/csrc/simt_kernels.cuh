@@ -1,6 +1,8 @@
 // CUDA-core (HBM-bound) kernels of the hot path: rotated filter bank fwd/bwd, attention inference
 // (softmax / Gumbel-softmax / expectations / KL) fwd/bwd, likelihoods, thin-layer backward, small helpers.
 #pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -22,8 +24,8 @@ struct RotTable {
 // ------------------------------------------------------------------------------------------
 // a-1  rotated filter bank (models.py:174-197), closed form of affine_grid + grid_sample
 //      (bilinear, zeros padding, align_corners=False).
-//   weight (O,C,k,k)  ->  bank [G*O][kpad], row n' = r*O + o, column kk = (c*k + v)*k + u,
-//   values rounded to tf32; columns kk >= C*k*k are zero.
+//   weight (O,C,k,k)  ->  bank [G*O][kpad16] fp16, row n' = r*O + o, column kk = (c*k + v)*k + u;
+//   columns kk >= C*k*k are zero.  (fp16 keeps the 11-bit significand of a TF32 operand.)
 // ------------------------------------------------------------------------------------------
 struct BilinearTap {
     int x0, y0;
@@ -43,7 +45,7 @@ __device__ __forceinline__ BilinearTap rot_tap(int u, int v, int k, float cs, fl
     return t;
 }
 
-__global__ void filter_bank_fwd_kernel(const float* __restrict__ w, float* __restrict__ bank, int O, int C, int k, int G,
+__global__ void filter_bank_fwd_kernel(const float* __restrict__ w, __half* __restrict__ bank, int O, int C, int k, int G,
                                        int kpad, RotTable rot) {
     const int K = C * k * k;
     const long long total = (long long)G * O * kpad;
@@ -62,9 +64,8 @@ __global__ void filter_bank_fwd_kernel(const float* __restrict__ w, float* __res
             if (y0ok && x1ok) val += wp[t.y0 * k + t.x0 + 1] * (t.wy0 * t.wx1);
             if (y1ok && x0ok) val += wp[(t.y0 + 1) * k + t.x0] * (t.wy1 * t.wx0);
             if (y1ok && x1ok) val += wp[(t.y0 + 1) * k + t.x0 + 1] * (t.wy1 * t.wx1);
-            val = to_tf32(val);
         }
-        bank[idx] = val;
+        bank[idx] = __float2half_rn(val);
     }
 }
 

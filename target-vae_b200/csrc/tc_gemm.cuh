@@ -221,6 +221,9 @@ struct PolicyBase {
     static constexpr bool kBMajorMN = false;
     static constexpr bool kAGen = false;
     static constexpr int kProdWarps = 0;
+    static constexpr bool kF16 = false;       // tc_gemm2: 16-bit operands (kind::f16)
+    static constexpr uint32_t kAFmt = 0;      // 0 = FP16, 1 = BF16
+    static constexpr uint32_t kBFmt = 0;
     struct EpiState {};
     struct GenState {};
     template <class Prm> __device__ static void setup(const Prm&, uint8_t*, int, int) {}

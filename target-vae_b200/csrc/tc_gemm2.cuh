@@ -79,6 +79,16 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrives (once all previously issued MMAs of this thread retire) on the barrier at the same smem offset in
 // every CTA of `mask`
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
@@ -112,7 +122,9 @@ template <class P>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr uint32_t kIdesc = make_idesc_tf32(256, kAccN, P::kAMajorMN, P::kBMajorMN);
+    // 16-bit policies (P::kF16): kind::f16, a stage row of 128 B holds 64 reduction elements, one MMA consumes 16.
+    constexpr uint32_t kIdesc = P::kF16 ? make_idesc_f16(256, kAccN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt)
+                                        : make_idesc_tf32(256, kAccN, P::kAMajorMN, P::kBMajorMN);
 
     const int stages = prm.num_stages;
     const Smem2Layout L = make_smem2_layout(stages, 0);
@@ -199,12 +211,22 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
 #pragma unroll
                         for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
                             uint64_t adesc, bdesc;
-                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
                             const uint32_t bb = b_addr + a * kBHalfBytes;
-                            if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                            else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
-                            umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
+                            if (P::kF16) {
+                                // MN-major 16-bit: A in 64-element blocks [64 k][128 B] (128 B swizzle), B in
+                                // 32-element blocks [64 k][64 B] (64 B swizzle); 16 k rows per MMA
+                                if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 2048, 64 * 128, 1024, kLayoutSw128);
+                                else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                                if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, 64 * 64, 512, kLayoutSw64);
+                                else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
+                                umma_f16_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
+                            } else {
+                                if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                                else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                                if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                                else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
+                                umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit_pair(empty_bar + 8 * stage, 3);   // frees the slot in both CTAs

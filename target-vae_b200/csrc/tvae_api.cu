@@ -3,6 +3,7 @@
 
 #include "conv_policies.cuh"
 #include "conv2_policies.cuh"
+#include "conv_f16_policies.cuh"
 #include "gen_policies.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
@@ -118,12 +119,18 @@ int tvae_bank_pitch(int C, int k) {
     return (K / 32 + 1) * 32;   // always leaves >= 1 spare column for the bias-gradient ones column
 }
 
+int tvae_bank16_pitch(int C, int k) {
+    const int K = C * k * k;
+    return (K + 63) / 64 * 64;   // whole 64-tap stage rows of the fp16 bank
+}
+
 // ================================================================================ filter bank
-int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, float* bank, void* stream) {
+int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, void* bank, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
-    const long long total = (long long)s->G * s->O * s->kpad;
-    ++g_launch_count; filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, bank, s->O, s->C, s->k, s->G, s->kpad, make_rot_table(s->G));
+    const int kpad16 = tvae_bank16_pitch(s->C, s->k);
+    const long long total = (long long)s->G * s->O * kpad16;
+    ++g_launch_count; filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -144,69 +151,79 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
 }  // extern "C"
 
 namespace {
-// conv1: implicit GEMM with the im2col operand generated on chip (CTA-pair kernel, tc_gemm2.cuh)
-SlabGeom make_slab(const ConvGeom& g, int rows_max) {
-    SlabGeom sg{};
+// conv1: implicit GEMM with the im2col operand generated on chip (CTA-pair kernel, tc_gemm2.cuh), fp16 operands
+Slab16Geom make_slab16(const ConvGeom& g, int rows_max, int channels) {
+    Slab16Geom sg{};
     sg.Wp = g.n + 2 * g.p;
-    // pitch = d (mod 32): a warp's 32 consecutive output cells keep consecutive banks across image-row wraps
-    sg.pitch = sg.Wp + (((1 - g.k) % 32) + 32) % 32;
+    // even pitch (a quad of taps keeps its 4-byte alignment class on every slab row) with pitch - d = 0 or +-1 (mod 64):
+    // the 32 consecutive output cells of a warp keep (almost) consecutive words across image-row wraps
+    int pitch = sg.Wp + (sg.Wp & 1);
+    for (;; pitch += 2) {
+        const int m = (((pitch - g.d) % 64) + 64) % 64;
+        if (m == 0 || m == 1 || m == 63) break;
+    }
+    sg.pitch = pitch;
     sg.rows_max = rows_max < sg.Wp ? rows_max : sg.Wp;
+    int words = (channels * sg.rows_max * sg.pitch + 1) / 2 + 4;
+    words += ((16 - words % 32) + 32) % 32;          // copy 1 starts 16 banks after copy 0
+    sg.copy_words = words;
     return sg;
 }
-int conv1_forward(const ConvGeom& g, const float* y, const float* bank, const float* bias, float* x1, int act, cudaStream_t st) {
-    Conv1Fwd2Params p{};
+int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const float* bias, float* x1, int act, cudaStream_t st) {
+    Conv1FwdHParams p{};
     const int N = g.G * g.O;
+    const int kpad16 = tvae_bank16_pitch(g.C, g.k);
     int rc;
-    if ((rc = make_tmap_2d(&p.tmB, bank, N, g.kpad, g.kpad, 128))) return rc;
+    if ((rc = make_tmap_2d_h(&p.tmB, bank16, N, kpad16, kpad16, 128))) return rc;
     p.g = g;
     p.y = y; p.bias = bias; p.x1 = x1; p.act = act;
     p.n_passes = cdiv(N, kAcc * kAccN);
     p.tiles_per_image = cdiv(g.P, kBM);
     p.m_tiles = g.B * p.tiles_per_image;
-    p.k_chunks = cdiv(g.K, kBK);
+    p.k_chunks = cdiv(g.K, kBK16);
     p.m_pairs = cdiv(p.m_tiles, 2);
     const int pairs_dev = sm_count() / 2;
     p.pairs = p.m_pairs < pairs_dev ? p.m_pairs : pairs_dev;
     p.num_tiles = p.pairs * cdiv(p.m_pairs, p.pairs) * p.n_passes;   // (m-pair, pass) grid padded to whole rounds of the pairs
-    p.sg = make_slab(g, (kBM - 1) / g.d + 2 + g.k - 1);
-    p.gran = (g.k % 4 == 0) ? 1 : 0;
-    p.tab_entries = p.k_chunks * (p.gran ? kBK / 4 : kBK);
-    p.skip = ((g.k * g.k) % kBK == 0) ? 1 : 0;
-    p.chunks_per_channel = p.skip ? (g.k * g.k) / kBK : p.k_chunks;
-    const int extra = p.tab_entries * 4 + g.C * p.sg.rows_max * p.sg.pitch * static_cast<int>(sizeof(float));
-    return launch_gemm2<Conv1Fwd2>(p, extra, st, p.pairs);
+    p.sg = make_slab16(g, (kBM - 1) / g.d + 2 + g.k - 1, g.C);
+    p.quad = (g.k % 4 == 0) ? 1 : 0;
+    p.tab_entries = p.k_chunks * (p.quad ? kBK16 / 4 : kBK16);
+    p.skip = ((g.k * g.k) % kBK16 == 0) ? 1 : 0;
+    p.chunks_per_channel = p.skip ? (g.k * g.k) / kBK16 : p.k_chunks;
+    const int extra = p.tab_entries * 4 + 2 * p.sg.copy_words * 4;
+    return launch_gemm2<Conv1FwdH>(p, extra, st, p.pairs);
 }
-// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); column kk == K accumulates the bias gradient
-int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dbank, cudaStream_t st) {
-    Conv1Wgrad2Params p{};
+// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); dx1 is bf16 [(b,r,pos)][O]
+int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, float* dbank, cudaStream_t st) {
+    Conv1WgradHParams p{};
     const int N = g.G * g.O;
     const long long R = (long long)g.B * g.G * g.P;
     int rc;
     const int oblocks = g.O / 32;
     p.nb = (oblocks % 4 == 0) ? 4 : (oblocks % 2 == 0 ? 2 : 1);   // 128 accumulator columns = 4 / nb boxes of nb o-blocks
-    if ((rc = make_tmap_3d_mn(&p.tmQ, dx1, R, g.O, g.O, kBK, p.nb))) return rc;
-    p.g = g; p.y = y; p.dbank = dbank; p.ones_col = 1;
-    p.m_tiles = cdiv(g.K + 1, kBM);     // + ones column
+    if ((rc = make_tmap_3d_mn_h(&p.tmQ, dx1_16, R, g.O, g.O, kBK16, p.nb))) return rc;
+    p.g = g; p.y = y; p.dbank = dbank;
+    p.m_tiles = cdiv(g.K, kBM);
     p.m_pairs = cdiv(p.m_tiles, 2);
     p.n_passes = cdiv(N, kAcc * kAccN);
-    p.chunks_per_image = cdiv(g.P, kBK);
+    p.chunks_per_image = cdiv(g.P, kBK16);
     p.chunks_total = g.B * p.chunks_per_image;
+    p.quad = (g.k % 4 == 0) ? 1 : 0;
     // slab: one channel and the few padded rows a 128-wide kk tile touches, or whole padded channels when a tile can
     // straddle channels
     const bool straddles = g.C > 1 && (g.k * g.k) % kBM != 0;
     const int nc_max = straddles ? (g.C < kBM / (g.k * g.k) + 2 ? g.C : kBM / (g.k * g.k) + 2) : 1;
-    p.sg = make_slab(g, straddles ? g.n + 2 * g.p : g.d + (kBM - 1) / g.k + 1);
-    const int extra = kBM * 4 + nc_max * p.sg.rows_max * p.sg.pitch * static_cast<int>(sizeof(float));
+    p.sg = make_slab16(g, straddles ? g.n + 2 * g.p : g.d + (kBM - 1) / g.k + 1, nc_max);
+    const int extra = kBM * 4 + 2 * p.sg.copy_words * 4;
     // Reduction splits.  Tiles are ordered split-major, so the CTA pairs of the device work on ~pairs/out_tiles
     // consecutive splits at any time, and every m-pair of a split re-reads the same dX1 rows: keep that footprint
-    // inside L2 (ncu: 40 % hit rate / 15 GB of DRAM reads with 13 coarse splits at cfg2), then minimise
-    // waves x (chunks per split + epilogue) over the candidates.
+    // inside L2, then minimise waves x (chunks per split + epilogue) over the candidates.
     const int out_tiles = p.m_pairs * p.n_passes;
     const int pairs_dev = sm_count() / 2;
-    const double bytes_img = 4.0 * g.G * g.P * g.O;
+    const double bytes_img = 2.0 * g.G * g.P * g.O;
     const double inflight = out_tiles < pairs_dev ? static_cast<double>(pairs_dev) / out_tiles : 1.0;
     int s_min = static_cast<int>(g.B * inflight * bytes_img / 48e6) + 1;
-    const int s_cap = p.chunks_total / 64 > 1 ? p.chunks_total / 64 : 1;      // keep >= 64 chunks per split
+    const int s_cap = p.chunks_total / 32 > 1 ? p.chunks_total / 32 : 1;      // keep >= 32 chunks (2048 positions) per split
     if (s_min > s_cap) s_min = s_cap;
     double best = 1e30;
     int best_cps = p.chunks_total;
@@ -221,14 +238,16 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const float* dx1, float* dban
     p.splits = cdiv(p.chunks_total, best_cps);
     p.num_tiles = out_tiles * p.splits;
     p.skip = 1;
-    return launch_gemm2<Conv1Wgrad2>(p, extra, st);
+    return launch_gemm2<Conv1WgradH>(p, extra, st);
 }
+// conv1 bias gradient slot: column K of dbank row (r = 0, o)  (summed over r by tvae_filter_bank_bwd)
+inline float* bias_grad_slot(const ConvGeom& g, float* dbank) { return dbank + g.K; }
 }  // namespace
 
 extern "C" {
 
-// Fraction of the dense K-chunk count the conv1 kernels actually execute (same arithmetic as Conv1Fwd2::tile_info /
-// Conv1Wgrad2::tile_info: chunks that only meet zero padding are skipped).
+// Fraction of the dense K-chunk count the conv1 kernels actually execute (same arithmetic as Conv1FwdH::tile_info /
+// Conv1WgradH::tile_info: chunks that only meet zero padding are skipped).
 double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
     if (check_enc_shape(s)) return -1.0;
     const ConvGeom g = make_geom(s);
@@ -237,8 +256,8 @@ double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
     double live = 0.0, dense = 0.0;
     if (!wgrad) {
         const int tiles_per_image = cdiv(g.P, kBM), m_tiles = g.B * tiles_per_image, m_pairs = cdiv(m_tiles, 2);
-        const int k_chunks = cdiv(g.K, kBK);
-        const bool skip = (g.k * g.k) % kBK == 0;
+        const int k_chunks = cdiv(g.K, kBK16);
+        const bool skip = (g.k * g.k) % kBK16 == 0;
         for (int mp = 0; mp < m_pairs; ++mp) {
             dense += k_chunks;
             if (!skip) { live += k_chunks; continue; }
@@ -251,21 +270,21 @@ double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
                 v_lo = imin(v_lo, imax(0, g.p - i_last));
                 v_hi = imax(v_hi, imin(g.k, g.p - i_first + g.n));
             }
-            const int lo = (v_lo * g.k) / kBK, hi = (v_hi * g.k + kBK - 1) / kBK;
+            const int lo = (v_lo * g.k) / kBK16, hi = (v_hi * g.k + kBK16 - 1) / kBK16;
             live += hi > lo ? g.C * (hi - lo) : 0;
         }
     } else {
-        const int m_tiles = cdiv(g.K + 1, kBM), m_pairs = cdiv(m_tiles, 2), cpi = cdiv(g.P, kBK);
+        const int m_tiles = cdiv(g.K, kBM), m_pairs = cdiv(m_tiles, 2), cpi = cdiv(g.P, kBK16);
         for (int mp = 0; mp < m_pairs; ++mp) {
             dense += cpi;
-            const int kk0 = 2 * mp * kBM, kk1 = kk0 + 2 * kBM - 1;
+            const int kk0 = 2 * mp * kBM, kk1 = imin(kk0 + 2 * kBM, g.K) - 1;
             int cnt = cpi;
-            if (kk1 < g.K) {
+            {
                 const int c0 = kk0 / (g.k * g.k), c1 = kk1 / (g.k * g.k);
                 const int v0 = (kk0 - c0 * g.k * g.k) / g.k, v1 = (kk1 - c1 * g.k * g.k) / g.k;
                 if (c0 == c1) {
                     const int i_lo = imax(0, g.p - v1), i_hi = imin(g.d - 1, g.p - v0 + g.n - 1);
-                    cnt = i_hi >= i_lo ? ((i_hi + 1) * g.d + kBK - 1) / kBK - (i_lo * g.d) / kBK : 0;
+                    cnt = i_hi >= i_lo ? ((i_hi + 1) * g.d + kBK16 - 1) / kBK16 - (i_lo * g.d) / kBK16 : 0;
                 }
             }
             live += cnt;
@@ -276,18 +295,25 @@ double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
     return dense > 0 ? live / dense : 1.0;
 }
 
-int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const float* bank, const float* bias, float* out, void* stream) {
+int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const void* bank, const float* bias, float* out, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
     return conv1_forward(make_geom(s), y, bank, bias, out, 0, S(stream));
 }
 
-int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, float* dbank, void* stream) {
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* dbank, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
     const ConvGeom g = make_geom(s);
-    TVAE_CHECK_CUDA(cudaMemsetAsync(dbank, 0, sizeof(float) * g.G * g.O * g.kpad, S(stream)));
-    return conv1_wgrad(g, y, dout, dbank, S(stream));
+    cudaStream_t st = S(stream);
+    TVAE_CHECK_CUDA(cudaMemsetAsync(dbank, 0, sizeof(float) * g.G * g.O * g.kpad, st));
+    const long long R = (long long)g.B * g.G * g.P;
+    const int rows_per_cta = static_cast<int>((R + 148LL * 8 - 1) / (148LL * 8));
+    ++g_launch_count;
+    rows_to_bf16_colsum_kernel<<<cdiv(R, rows_per_cta), 256, g.O * sizeof(float), st>>>(
+        dout, static_cast<__nv_bfloat16*>(dout16), bias_grad_slot(g, dbank), g.kpad, R, g.O, rows_per_cta);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return conv1_wgrad(g, y, dout16, dbank, st);
 }
 
 int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream) {
@@ -353,11 +379,12 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         LinearNTArgs l{};
         l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_tf32; l.ldb = g.O;
         l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
-        l.C = a->x1; l.ldc = g.O; l.aux = a->x1; l.ld_aux = g.O;
+        l.C = nullptr; l.C16 = a->dx1_16; l.ldc16 = g.O; l.aux = a->x1; l.ld_aux = g.O;
+        l.colsum = bias_grad_slot(g, a->dbank); l.colsum_stride = g.kpad;     // conv1 bias gradient
         if ((rc = linear_nt(l, st))) return rc;
     }
     // ---- conv1 weight gradient (w.r.t. the rotated bank)
-    return conv1_wgrad(g, a->y, a->x1, a->dbank, st);
+    return conv1_wgrad(g, a->y, a->dx1_16, a->dbank, st);
 }
 
 // ================================================================================ attention

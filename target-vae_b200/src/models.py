@@ -160,7 +160,7 @@ class GroupConv(nn.Module):
         _require_cuda(self.weight, "GroupConv.trans_filter")
         O, C, _, k, _ = self.weight.shape
         s = _ops.enc_shape(1, C, k, k, 0, self.output_rot_dim, O, 1)
-        bank = _ops.filter_bank_fwd(s, self.weight)[:, :C * k * k]
+        bank = _ops.filter_bank_fwd(s, self.weight)[:, :C * k * k].float()   # stored fp16 (GEMM operand)
         return bank.view(self.output_rot_dim, O, C, 1, k, k).permute(1, 0, 2, 3, 4, 5)
 
     def forward(self, input, device):

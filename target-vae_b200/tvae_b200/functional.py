@@ -46,7 +46,8 @@ class GroupConvFn(torch.autograd.Function):
             raise NotImplementedError("GroupConv: gradient w.r.t. the input image is not part of the hot path")
         gi = g.permute(0, 2, 3, 4, 1).contiguous().view(-1, s.O).float()
         dbank = ops.empty(s.G * s.O, s.kpad, device=g.device)
-        ops.check(ops.L().tvae_groupconv_wgrad(ops.byref(s), ops.ptr(yc), ops.ptr(gi), ops.ptr(dbank), ops.stream_ptr()),
+        gi16 = torch.empty(gi.shape, device=g.device, dtype=torch.bfloat16)
+        ops.check(ops.L().tvae_groupconv_wgrad(ops.byref(s), ops.ptr(yc), ops.ptr(gi), ops.ptr(gi16), ops.ptr(dbank), ops.stream_ptr()),
                   "tvae_groupconv_wgrad")
         dw, db = ops.filter_bank_bwd(s, dbank)
         return None, dw, (db if ctx.has_bias else None), None, None
@@ -86,7 +87,7 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
 
 
 def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads):
-    """-> grads in ENC_PARAM_NAMES order.  x1 is consumed (overwritten)."""
+    """-> grads in ENC_PARAM_NAMES order."""
     dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
     dw1, db1 = ops.filter_bank_bwd(s, dbank)
     O, z = s.O, spec.z
@@ -110,7 +111,7 @@ class EncoderHeadsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         yc, w2m, wh, x1, h = ctx.saved_tensors
-        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1.clone(), h, g.contiguous())
+        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous())
         return (None, None, *grads)
 
 

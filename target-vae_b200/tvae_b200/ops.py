@@ -23,7 +23,7 @@ class EncFwdArgs(Structure):
 
 
 class EncBwdArgs(Structure):
-    _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "w2t_tf32", "dbank",
+    _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "dx1_16", "w2t_tf32", "dbank",
                                          "dw2", "db2", "dwh", "dbh")]
 
 
@@ -78,6 +78,7 @@ def L():
     lib = _lib.lib()
     if not _configured:
         lib.tvae_bank_pitch.restype = c_int
+        lib.tvae_bank16_pitch.restype = c_int
         lib.tvae_launch_count.restype = ctypes.c_longlong
         lib.tvae_profile_enable.restype = None
         lib.tvae_profile_collect.restype = c_int
@@ -112,7 +113,8 @@ def enc_shape(B, C, n, k, p, G, O, z) -> EncShape:
 
 
 def filter_bank_fwd(s: EncShape, weight: torch.Tensor) -> torch.Tensor:
-    bank = empty(s.G * s.O, s.kpad, device=weight.device)
+    # fp16 [G*O][kpad16]: operand of the kind::f16 conv GEMM (same 11-bit significand as TF32)
+    bank = torch.empty(s.G * s.O, L().tvae_bank16_pitch(s.C, s.k), device=weight.device, dtype=torch.float16)
     check(L().tvae_filter_bank_fwd(byref(s), ptr(f32(weight)), ptr(bank), stream_ptr()), "tvae_filter_bank_fwd")
     return bank
 
@@ -196,7 +198,8 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
     db2 = empty(s.O, device=dev)
     dwh = empty(NH, s.O, device=dev)
     dbh = empty(NH, device=dev)
-    a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, w2t_tf32=w2t,
+    dx1_16 = torch.empty(R, s.O, device=dev, dtype=torch.bfloat16)
+    a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, dx1_16=dx1_16, w2t_tf32=w2t,
              dbank=dbank, dw2=dw2, db2=db2, dwh=dwh, dbh=dbh)
     check(L().tvae_encoder_bwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_bwd")
     return dbank, dw2, db2, dwh, dbh
@@ -343,7 +346,7 @@ def launch_count() -> int:
 
 
 # kernels (names of tvae_profile_collect) whose MMAs run with 16-bit operands (kind::f16); the rest are kind::tf32
-F16_KERNELS: set = set()
+F16_KERNELS: set = {"conv1_fwd", "conv1_wgrad"}
 
 
 def conv1_executed_fraction(s: EncShape, wgrad: bool) -> float:

@@ -48,8 +48,8 @@ def test_filter_bank_fwd_bwd(cfg):
     K = cfg.C * cfg.k ** 2
     ref = orc.rotated_filter_bank(enc.conv1_w, cfg.G)            # (O,G,C,1,k,k)
     ref = ref.permute(1, 0, 2, 3, 4, 5).reshape(cfg.G * cfg.O, K)  # row r*O + o
-    assert rel_err(bank[:, :K], ref) < 6e-4                        # tf32 rounding of the stored bank
-    assert float(bank[:, K:].abs().max()) == 0.0
+    assert rel_err(bank[:, :K], ref) < 6e-4                        # fp16 rounding of the stored bank (11-bit significand, like tf32)
+    assert bank.shape[1] % 64 == 0 and float(bank[:, K:].abs().sum()) == 0.0
     # adjoint: <bank(w), D> == <w, bank^T(D)>
     g = torch.Generator().manual_seed(1)
     D = torch.randn(cfg.G * cfg.O, s.kpad, generator=g)
