@@ -11,8 +11,13 @@
  *   - return 0 on success, < 0 on error; tvae_last_error() returns the thread-local message
  *   - "tf32" tensors hold fp32 values already rounded to TF32 (10-bit mantissa); fp16 / bf16 tensors are void*
  *
+ * Precision: every dense contraction runs on the tensor cores with FP16 operands and FP32 accumulation
+ * (tcgen05.mma.kind::f16).  An fp16 operand has the 11-bit significand of a TF32 one (the precision the reference's
+ * cuDNN path uses); gradients are kept inside fp16's exponent range by power-of-two scales chosen on the device
+ * from max|.| bounds and divided out (exactly) in the consuming kernel's epilogue.
+ *
  * Internal activation layout (rows are (b, r, pos) with pos = i*W' + j, P = H'*W'):
- *   x1, h  : [(b*G + r)*P + pos][O]
+ *   x1, h  : fp16 [(b*G + r)*P + pos][O]
  *   heads  : (B, NH, G, P) planar, NH = 3 + 2*z, channels = [attn, theta_mu, theta_logstd, z_mu.., z_logstd..]
  *            == attn (B,G,H',W'), theta (B,2,G,H',W'), z (B,2z,G,H',W') of models.py:403 stacked on dim 1
  */
@@ -49,9 +54,9 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
 
 /* GroupConv.forward alone (models.py:202-225): out [(b*G + r)*P + pos][O] = conv + bias, no activation.
  * bias may be NULL.  tvae_groupconv_wgrad: dout in the same layout -> dbank [G*O][kpad] (overwritten);
- * dout16 is scratch for the bf16 copy of dout the GEMM consumes (B*G*P*O 16-bit values). */
+ * dout16 is scratch for the scaled fp16 copy of dout the GEMM consumes (B*G*P*O halves), scales8 scratch of 8 floats. */
 int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const void* bank, const float* bias, float* out, void* stream);
-int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* dbank, void* stream);
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* scales8, float* dbank, void* stream);
 
 /* Executed / dense-count ratio of the K chunks of tvae_groupconv_fwd (wgrad = 0) or tvae_groupconv_wgrad (wgrad = 1):
  * chunks that only meet zero padding are skipped.  > 1 is possible for the wgrad (tile-grid padding of the kk rows).
@@ -67,10 +72,10 @@ typedef struct {
     const float* wh;         /* [NH][O]: conv_a, conv_r, conv_z weights stacked */
     const float* bh;         /* [NH] */
     const float* head_add;   /* [NH][G]: p_r on channel 0, rotation offsets on channel 1, else 0 */
-    float* x1;               /* out [B*G*P][O]  LeakyReLU(conv1)   (tf32) */
-    float* h;                /* out [B*G*P][O]  LeakyReLU(conv2) */
+    void* x1;                /* out fp16 [B*G*P][O]  LeakyReLU(conv1) */
+    void* h;                 /* out fp16 [B*G*P][O]  LeakyReLU(conv2) */
     float* heads;            /* out (B,NH,G,P) */
-    float* w2_tf32;          /* scratch (O,O) */
+    void* w2_h;              /* scratch fp16 (O,O) */
 } tvae_enc_fwd_args;
 /* GroupConv.forward + InferenceNetwork_AttentionTranslation_AttentionRotation.forward up to the head maps
  * (models.py:202-225, 355-358, 382, 390-399). */
@@ -80,12 +85,13 @@ typedef struct {
     const float* y;
     const float* w2;
     const float* wh;
-    const float* x1;         /* in: saved activation LeakyReLU(conv1) */
-    const float* h;
+    const void* x1;          /* in: saved fp16 activation LeakyReLU(conv1) */
+    const void* h;           /* in: saved fp16 activation LeakyReLU(conv2) */
     const float* d_heads;    /* (B,NH,G,P) */
-    float* dhpre;            /* scratch [B*G*P][O] */
-    void* dx1_16;            /* scratch [B*G*P][O] bf16: d(conv1 pre-activation), the wgrad GEMM's operand */
-    float* w2t_tf32;         /* scratch (O,O) */
+    void* dhpre;             /* scratch fp16 [B*G*P][O]: d(conv2 pre-activation) * s1 */
+    void* dx1_16;            /* scratch fp16 [B*G*P][O]: d(conv1 pre-activation) * s2, the wgrad GEMM's operand */
+    void* w2t_h;             /* scratch fp16 (O,O) */
+    float* scales;           /* scratch, 8 floats: the power-of-two scales s1, 1/s1, s2, 1/s2 (computed on the device) */
     float* dbank;            /* out [G*O][kpad] (feed to tvae_filter_bank_bwd) */
     float* dw2;              /* out (O,O) */
     float* db2;              /* out (O) */

@@ -3,7 +3,8 @@
 //
 //   Conv1FwdH   : X1[(b,pos), (r,o)] = lrelu(im2col . bank^T + bias)     A = im2col tile (K-major, generated), B = bank (TMA)
 //   Conv1WgradH : dbank[(r,o), kk]  += sum_(b,pos) dX1[(b,r,pos), o] im2col[(b,pos), kk]
-//                 A = im2col^T (bf16, MN-major, generated), B = dX1 (bf16, MN-major, TMA), fp32 atomics into dbank
+//                 A = im2col^T (MN-major, generated), B = dX1 (fp16 with a power-of-two scale, MN-major, TMA),
+//                 fp32 atomics into dbank
 //
 // Why FP16: an fp16 value carries the same 11-bit significand a TF32 operand does, so for values inside fp16's
 // normal range (6.1e-5 .. 65504; images and filter taps are) the products are the ones kind::tf32 would form, while
@@ -63,7 +64,8 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
     return slabw + (par ? sg.copy_words : 0) + ((a - par) >> 1);
 }
 
-// conv1 forward epilogue shared by the policies: bias + LeakyReLU (+ tf32 rounding: conv2 consumes x1 as a TF32 operand)
+// conv1 forward epilogue: bias (+ LeakyReLU); fp16 store (x1h: the encoder's activation, conv2's MMA operand) or fp32
+// store (x1: GroupConv.forward alone)
 template <class Prm>
 __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, int n0, uint32_t taddr, int row, bool has_work) {
     const ConvGeom& g = p.g;
@@ -78,19 +80,30 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
         const int np = n0 + c * 32;
         if (!ok || np >= N) continue;
         const int r = np / g.O, o0 = np - r * g.O;
-        float* dst = p.x1 + (((long long)ti.a0 * g.G + r) * g.P + pos) * g.O + o0;
         const float* bs = p.bias + o0;
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 t;
-            t.x = __uint_as_float(rr[j]) + (p.bias ? __ldg(bs + j) : 0.f);
-            t.y = __uint_as_float(rr[j + 1]) + (p.bias ? __ldg(bs + j + 1) : 0.f);
-            t.z = __uint_as_float(rr[j + 2]) + (p.bias ? __ldg(bs + j + 2) : 0.f);
-            t.w = __uint_as_float(rr[j + 3]) + (p.bias ? __ldg(bs + j + 3) : 0.f);
-            if (p.act) {
-                t.x = to_tf32(lrelu(t.x)); t.y = to_tf32(lrelu(t.y)); t.z = to_tf32(lrelu(t.z)); t.w = to_tf32(lrelu(t.w));
+        for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(rr[j]) + (p.bias ? __ldg(bs + j) : 0.f);
+            if (p.act) v[j] = lrelu(v[j]);
+        }
+        const long long off = (((long long)ti.a0 * g.G + r) * g.P + pos) * g.O + o0;
+        if (p.x1h) {
+            __half* dst = p.x1h + off;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 q;
+                __half2 hv;
+                hv = __floats2half2_rn(v[j], v[j + 1]);     q.x = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 2], v[j + 3]); q.y = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 4], v[j + 5]); q.z = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 6], v[j + 7]); q.w = *reinterpret_cast<uint32_t*>(&hv);
+                *reinterpret_cast<uint4*>(dst + j) = q;
             }
-            *reinterpret_cast<float4*>(dst + j) = t;
+        } else {
+            float* dst = p.x1 + off;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
 }
@@ -104,7 +117,8 @@ struct Conv1FwdHParams {
     Slab16Geom sg;
     const float* y;           // (B,C,n,n)
     const float* bias;        // (O) or null
-    float* x1;                // [(b*G + r)*P + pos][O]
+    float* x1;                // fp32 [(b*G + r)*P + pos][O] or null
+    __half* x1h;              // fp16 output in the same layout or null
     int act;
     int quad;                 // 1: offset table per 4-tap quad (k % 4 == 0), 0: per tap
     int tab_entries;
@@ -266,13 +280,14 @@ struct Conv1FwdH : PolicyBase {
 
 // ------------------------------------------------------------------------------------------------
 struct Conv1WgradHParams {
-    CUtensorMap tmQ;          // dX1 bf16 [(B*G*P)][O] as a 3-D map {32 o, rows, O/32 o-blocks}, MN-major boxes {32, 64, nb}
+    CUtensorMap tmQ;          // dX1 fp16 (scaled) [(B*G*P)][O] as a 3-D map {32 o, rows, O/32 o-blocks}, MN-major boxes {32, 64, nb}
     int num_stages, num_tiles, m_pairs, n_passes, m_tiles, splits, chunks_total, chunks_per_split, chunks_per_image;
     int nb;                   // o-blocks (of 32 columns) per TMA box: 4, 2 or 1
     ConvGeom g;
     Slab16Geom sg;
     const float* y;
     float* dbank;             // [G*O][kpad] fp32, zero-filled by the caller
+    const float* acc_scale;   // device scalar: 1 / (scale dX1 was stored with)
     int quad;                 // 1: offset table per 4-tap quad, 0: per tap
     int skip;                 // 1: skip position chunks that only meet zero padding
 };
@@ -281,10 +296,8 @@ struct Conv1WgradH : PolicyBase {
     static constexpr const char* kName = "conv1_wgrad";
     using Params = Conv1WgradHParams;
     static constexpr bool kF16 = true;
-    // dX1 is bf16 (a gradient needs the exponent range); the tensor core rejects mixed fp16 x bf16 operands
-    // (illegal instruction), so the im2col operand of this GEMM is bf16 as well
-    static constexpr uint32_t kAFmt = 1;
-    static constexpr uint32_t kBFmt = 1;
+    // both operands fp16 (the tensor core rejects mixed fp16 x bf16 operands: illegal instruction).  dX1 is stored
+    // multiplied by a power-of-two scale that keeps it inside fp16's range; the epilogue divides it out (acc_scale).
     static constexpr bool kAMajorMN = true;
     static constexpr bool kBMajorMN = true;
     struct ChunkWalk {
@@ -431,7 +444,7 @@ struct Conv1WgradH : PolicyBase {
         const Im2colCursor lo = im2col_cursor(min(ti.a0, g.K - 1), g.k), hi = im2col_cursor(kk_hi, g.k);
         const int nc = hi.c - lo.c + 1;
         const int rows = (nc == 1 ? hi.v - lo.v : g.k - 1) + g.d;      // padded rows [r_lo, r_lo + rows)
-        fill_slab16<true>(slabw, p.sg, g, p.y + (long long)s.w.b * g.C * g.n * g.n, lo.c, nc, s.r_lo, rows, ptid, kGenWarps * 32);
+        fill_slab16(slabw, p.sg, g, p.y + (long long)s.w.b * g.C * g.n * g.n, lo.c, nc, s.r_lo, rows, ptid, kGenWarps * 32);
         named_bar_sync(1, kGenWarps * 32);
         s.b = s.w.b;
     }
@@ -490,6 +503,7 @@ struct Conv1WgradH : PolicyBase {
         const int kk = ti.a0 + row;
         const int N = g.G * g.O;
         const bool ok = has_work && ti.m_tile >= 0 && kk < g.K;
+        const float acc_scale = __ldg(p.acc_scale);
 #pragma unroll 1
         for (int c = 0; c < kAccN / 32; ++c) {
             uint32_t rr[32];
@@ -500,7 +514,7 @@ struct Conv1WgradH : PolicyBase {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int np = np0 + j;
-                if (np < N) atomicAdd(p.dbank + (long long)np * g.kpad + kk, __uint_as_float(rr[j]));
+                if (np < N) atomicAdd(p.dbank + (long long)np * g.kpad + kk, __uint_as_float(rr[j]) * acc_scale);
             }
         }
     }

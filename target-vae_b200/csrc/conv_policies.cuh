@@ -31,7 +31,7 @@ __device__ __forceinline__ Im2colCursor im2col_cursor(int kk, int k) {
 // O <= BN so one accumulator tile holds a full channel vector per row.
 constexpr int kMaxNH = 36;
 struct Conv2HeadsParams {
-    CUtensorMap tmA, tmB;     // x1 [R][O]; W2 [O][O]
+    CUtensorMap tmA, tmB;     // x1 fp16 [R][O]; W2 fp16 [O][O]
     int num_stages, num_tiles, k_chunks;
     long long R;              // B*G*P rows
     int O, NH, G, P;
@@ -39,7 +39,7 @@ struct Conv2HeadsParams {
     const float* wh;          // [NH][O]
     const float* bh;          // [NH]
     const float* head_add;    // [NH][G]
-    float* h;                 // [R][O]
+    __half* h;                // fp16 [R][O]
     float* heads;             // (B,NH,G,P)
 };
 
@@ -48,6 +48,7 @@ struct Conv2Heads : PolicyBase {
     static constexpr const char* kName = "conv2_heads";
     using Params = Conv2HeadsParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = true;        // x1 and W2 are fp16 operands (64 k-elements per stage)
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -65,8 +66,8 @@ struct Conv2Heads : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
-        tma_kmajor(sb, &p.tmB, bar, kc, 0);
+        tma_kmajor_h(sa, &p.tmA, bar, kc, ti.m0);
+        tma_kmajor_h(sb, &p.tmB, bar, kc, 0);
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
         const float* s_wh = reinterpret_cast<const float*>(extra);
@@ -86,9 +87,17 @@ struct Conv2Heads : PolicyBase {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = lrelu(__uint_as_float(rr[j]) + s_b2[o0 + j]);
-            float* dst = p.h + m * p.O + o0;
+            __half* dst = p.h + m * p.O + o0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 8) {
+                uint4 q;
+                __half2 hv;
+                hv = __floats2half2_rn(v[j], v[j + 1]);     q.x = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 2], v[j + 3]); q.y = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 4], v[j + 5]); q.z = *reinterpret_cast<uint32_t*>(&hv);
+                hv = __floats2half2_rn(v[j + 6], v[j + 7]); q.w = *reinterpret_cast<uint32_t*>(&hv);
+                *reinterpret_cast<uint4*>(dst + j) = q;
+            }
 #pragma unroll
             for (int hh = 0; hh < NHMAX; ++hh) {
                 if (hh < p.NH) {

@@ -102,6 +102,22 @@ inline int make_tmap_2d_h(CUtensorMap* tm, const void* ptr, uint64_t rows, uint6
     return 0;
 }
 
+// 2-D 16-bit row-major tensor [rows][cols] read as an MN-major operand: boxes {32 cols (64 B), box_rows}, 64 B swizzle.
+inline int make_tmap_2d_mn_h(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return fail(-1, "TMA operand must be 16-byte aligned with 16-byte row pitch");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (16-bit, MN-major) failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // MN-major operand view of a row-major 16-bit matrix [rows][cols] (cols % 32 == 0): 3-D map {32 cols, rows, cols/32 column
 // blocks}, boxes {32, box_rows, nb}: one TMA fills nb consecutive [box_rows][64 B] column blocks in the 64 B swizzle.
 inline int make_tmap_3d_mn_h(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t nb) {

@@ -3,6 +3,7 @@
 //   LinearTN<BN>: C[Ma,Nb] += sum_r P[r,Ma] * Q[r,Nb]  (weight gradients; split over r, fp32 atomics)
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "tc_gemm.cuh"
 
 namespace tvae {
@@ -30,8 +31,11 @@ struct LinearNTParams {
     const float* proj_bias;   // [n_proj]
     float* proj_out;          // [M][n_proj], pre-zeroed
     int n_proj;
-    void* C16;                // [M][ldc16] bf16 copy of the stored value (the conv1 wgrad's MN-major operand) or null
+    void* C16;                // [M][ldc16] fp16 output (value * *store_scale) or null
     long long ldc16;
+    const void* aux16;        // [M][ld_aux] fp16 variant of aux or null
+    const float* acc_scale;   // device scalar multiplied into the accumulator first (undoes the operand's scale) or null
+    const float* store_scale; // device scalar applied to the fp16 store only (power of two) or null
     float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient; needs tiles_n == 1) or null
     long long colsum_stride;
 };
@@ -58,11 +62,12 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     return a[0];
 }
 
-template <int BN>
+template <int BN, bool F16 = false>
 struct LinearNT : PolicyBase {
     static constexpr const char* kName = "linear_nt";
     using Params = LinearNTParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = F16;          // fp16 A and B (TMA boxes of 64 k-elements)
     // column sums: extra smem [4 epilogue warps][BN] floats, entry (warp, c*32 + lane) is owned by one thread
     static constexpr int kExtraBytes = kEpiWarps * BN * 4;
     __device__ static void epi_init(const Params& p, EpiState&, uint8_t* extra, int row) {
@@ -92,13 +97,20 @@ struct LinearNT : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
-        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+        if (F16) {
+            tma_kmajor_h(sa, &p.tmA, bar, kc, ti.m0);
+            tma_kmajor_h(sb, &p.tmB, bar, kc, ti.n0);
+        } else {
+            tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
+            tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+        }
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
         const int m = ti.m0 + row;
         const bool m_ok = m < p.M;
         float proj[4] = {0.f, 0.f, 0.f, 0.f};
+        const float acc_scale = p.acc_scale ? __ldg(p.acc_scale) : 1.f;
+        const float store_scale = p.store_scale ? __ldg(p.store_scale) : 1.f;
         const float* rb = (p.row_bias && m_ok) ? p.row_bias + (long long)(m / p.rows_per_group) * p.ld_rb : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -113,7 +125,7 @@ struct LinearNT : PolicyBase {
             }
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;
             if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -145,6 +157,23 @@ struct LinearNT : PolicyBase {
                     }
                 }
             }
+            if (p.aux16 && m_ok) {
+                const __half* ax = reinterpret_cast<const __half*>(p.aux16) + (long long)m * p.ld_aux + n_base;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (n_base + j < p.N) {
+                        const uint4 t = __ldg(reinterpret_cast<const uint4*>(ax + j));
+                        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            // lrelu'(a) from the sign bits of the packed halves (a > 0 <=> positive and non-zero)
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                            v[j + 2 * e] *= lrelu_grad_from_out(f.x);
+                            v[j + 2 * e + 1] *= lrelu_grad_from_out(f.y);
+                        }
+                    }
+                }
+            }
             if (p.colsum) {
                 if (!m_ok) {
 #pragma unroll
@@ -154,16 +183,16 @@ struct LinearNT : PolicyBase {
                 if (!m_ok) continue;
             }
             if (p.C16) {
-                __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.C16) + (long long)m * p.ldc16 + n_base;
+                __half* d16 = reinterpret_cast<__half*>(p.C16) + (long long)m * p.ldc16 + n_base;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     if (n_base + j < p.N) {
                         uint4 t;
-                        __nv_bfloat162 h;
-                        h = __floats2bfloat162_rn(v[j], v[j + 1]);     t.x = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(v[j + 2], v[j + 3]); t.y = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(v[j + 4], v[j + 5]); t.z = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2bfloat162_rn(v[j + 6], v[j + 7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+                        __half2 h;
+                        h = __floats2half2_rn(v[j] * store_scale, v[j + 1] * store_scale);     t.x = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(v[j + 2] * store_scale, v[j + 3] * store_scale); t.y = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(v[j + 4] * store_scale, v[j + 5] * store_scale); t.z = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(v[j + 6] * store_scale, v[j + 7] * store_scale); t.w = *reinterpret_cast<uint32_t*>(&h);
                         *reinterpret_cast<uint4*>(d16 + j) = t;
                     }
                 }
@@ -208,13 +237,15 @@ struct LinearTNParams {
     float* C;                 // accumulated with atomics; caller zero-fills
     long long ldc;
     int transpose_out;        // 0: C[ma][nb], 1: C[nb][ma]
+    const float* acc_scale;   // device scalar multiplied into the accumulator (undoes the operands' scale) or null
 };
 
-template <int BN>
+template <int BN, bool F16 = false>
 struct LinearTN : PolicyBase {
     static constexpr const char* kName = "linear_tn";
     using Params = LinearTNParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = F16;          // fp16 P and Q, reduction chunks of 64 rows
     static constexpr bool kAMajorMN = true;
     static constexpr bool kBMajorMN = true;
     __device__ static void prefetch_descs(const Params& p) {
@@ -233,12 +264,18 @@ struct LinearTN : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        tma_mnmajor(sa, &p.tmP, bar, ti.m0, kc * kBK, kBM / 32);
-        tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
+        if (F16) {
+            tma_mnmajor_h(sa, &p.tmP, bar, ti.m0, kc * kBKh, kBM / 32);
+            tma_mnmajor_h(sb, &p.tmQ, bar, ti.n0, kc * kBKh, BN / 32);
+        } else {
+            tma_mnmajor(sa, &p.tmP, bar, ti.m0, kc * kBK, kBM / 32);
+            tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
+        }
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
         const int ma = ti.m0 + row;
         const bool empty = ti.kc_begin >= ti.kc_end;
+        const float acc_scale = p.acc_scale ? __ldg(p.acc_scale) : 1.f;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
@@ -251,7 +288,7 @@ struct LinearTN : PolicyBase {
                 const int nb = nb0 + j;
                 if (nb < p.Nb) {
                     float* dst = p.transpose_out ? p.C + (long long)nb * p.ldc + ma : p.C + (long long)ma * p.ldc + nb;
-                    atomicAdd(dst, __uint_as_float(r[j]));
+                    atomicAdd(dst, __uint_as_float(r[j]) * acc_scale);
                 }
             }
         }

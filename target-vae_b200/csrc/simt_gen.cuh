@@ -197,14 +197,15 @@ __global__ void bank_bias_grad_kernel(const float* __restrict__ dbank, float* __
     dbias[o] = acc;
 }
 
-// out16[r][c] = bf16(in[r][c]) and colsum[c * cs_stride] += sum_r in[r][c]   (standalone GroupConv backward: the
-// gradient arrives in fp32; the wgrad GEMM consumes bf16, the conv1 bias gradient is the column sum)
-__global__ void __launch_bounds__(256) rows_to_bf16_colsum_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out16,
-                                                                  float* __restrict__ colsum, long long cs_stride, long long R, int W,
-                                                                  int rows_per_cta) {
+// out16[r][c] = fp16(in[r][c] * scales[2]) and colsum[c * cs_stride] += sum_r in[r][c]   (standalone GroupConv
+// backward: the gradient arrives in fp32; the wgrad GEMM consumes scaled fp16, the conv1 bias gradient is the column sum)
+__global__ void __launch_bounds__(256) rows_to_half_colsum_kernel(const float* __restrict__ in, __half* __restrict__ out16,
+                                                                  const float* __restrict__ scales, float* __restrict__ colsum,
+                                                                  long long cs_stride, long long R, int W, int rows_per_cta) {
     extern __shared__ float sm_cs[];
     for (int c = threadIdx.x; c < W; c += blockDim.x) sm_cs[c] = 0.f;
     __syncthreads();
+    const float sc = __ldg(scales + 2);
     const int cpr = W / 2;                          // column pairs per row
     const int rpp = blockDim.x / cpr > 0 ? blockDim.x / cpr : 1;
     const int cp = threadIdx.x % cpr, rr = threadIdx.x / cpr;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) rows_to_bf16_colsum_kernel(const float* _
     if (rr < rpp) {
         for (long long r = r0 + rr; r < r0 + rows_per_cta && r < R; r += rpp) {
             const float2 v = __ldg(reinterpret_cast<const float2*>(in + r * W) + cp);
-            reinterpret_cast<__nv_bfloat162*>(out16 + r * W)[cp] = __floats2bfloat162_rn(v.x, v.y);
+            reinterpret_cast<__half2*>(out16 + r * W)[cp] = __floats2half2_rn(v.x * sc, v.y * sc);
             s0 += v.x; s1 += v.y;
         }
         atomicAdd(&sm_cs[2 * cp], s0);

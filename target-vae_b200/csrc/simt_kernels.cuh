@@ -534,10 +534,11 @@ __global__ void __launch_bounds__(256) gaussian_kernel(const float* __restrict__
 // Per-CTA partial sums are combined in shared memory, then one global atomicAdd per output element.
 // ------------------------------------------------------------------------------------------
 struct ThinBwdParams {
-    const float* a;      // [M][W] post-activation
+    const void* a;       // [M][W] post-activation (fp32, or fp16 when H16)
     const float* dt;
     const float* Wt;     // [T][W]
-    float* dpre;         // [M][W]
+    void* dpre;          // [M][W] (fp32, or fp16 = value * *store_scale when H16)
+    const float* store_scale;
     float* dWt;          // [T][W]
     float* dbt;          // [T]
     float* dcol;         // [W]
@@ -570,8 +571,36 @@ __device__ __forceinline__ void vec_store(float* p, const float (&v)[VEC]) {
     *reinterpret_cast<V*>(p) = t;
 }
 
+// 16-bit variants: VEC fp16 values <-> floats
+template <int VEC>
+__device__ __forceinline__ void vec_load_h(const __half* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else if constexpr (VEC == 2) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p));
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = __half2float(*p);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void vec_store_h(__half* p, const float (&v)[VEC], float scale) {
+    if constexpr (VEC == 4) {
+        const __half2 a = __floats2half2_rn(v[0] * scale, v[1] * scale), b = __floats2half2_rn(v[2] * scale, v[3] * scale);
+        uint2 t;
+        t.x = *reinterpret_cast<const uint32_t*>(&a); t.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = t;
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0] * scale, v[1] * scale);
+    } else {
+        *p = __float2half_rn(v[0] * scale);
+    }
+}
+
 // dynamic smem: [kThinRB * T] staged dt, then [(T + 1) * W + T] CTA partial sums (dWt, dcol, dbt)
-template <int TMAX, int VEC, bool PLANAR>
+template <int TMAX, int VEC, bool PLANAR, bool H16>
 __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
     extern __shared__ float s_thin[];
     float* s_dt = s_thin;
@@ -596,6 +625,7 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) dcol[v] = 0.f;
     float dbt = 0.f;   // threads with tid < T accumulate column tid of the staged dt block
+    const float store_scale = (H16 && p.store_scale) ? __ldg(p.store_scale) : 1.f;
     for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB) {
         const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
         __syncthreads();
@@ -623,7 +653,10 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int rr = rr0 + q * rpp;
-                    if (rr < rows) vec_load<VEC>(p.a + (m0 + rr) * p.W + c0, av[q]);
+                    if (rr < rows) {
+                        if constexpr (H16) vec_load_h<VEC>(static_cast<const __half*>(p.a) + (m0 + rr) * p.W + c0, av[q]);
+                        else vec_load<VEC>(static_cast<const float*>(p.a) + (m0 + rr) * p.W + c0, av[q]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -648,7 +681,8 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
                             g[v] *= (av[q][v] > 0.f ? 1.f : kSlope);
                             dcol[v] += g[v];
                         }
-                        vec_store<VEC>(p.dpre + (m0 + rr) * p.W + c0, g);
+                        if constexpr (H16) vec_store_h<VEC>(static_cast<__half*>(p.dpre) + (m0 + rr) * p.W + c0, g, store_scale);
+                        else vec_store<VEC>(static_cast<float*>(p.dpre) + (m0 + rr) * p.W + c0, g);
                     }
                 }
             }
@@ -687,6 +721,77 @@ __global__ void __launch_bounds__(1024) group_colsum_kernel(const float* __restr
     for (int r = r0; r < r1; ++r) acc += xg[(long long)r * W + c];
     if (out) atomicAdd(out + (long long)g * W + c, acc);
     if (total) atomicAdd(total + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Power-of-two scales that keep the encoder's backward intermediates inside fp16's range.
+//   amax[0] = max |x| over a tensor (float bits compared as ints: all values are >= 0)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ amax) {
+    float m = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
+// largest power of two s with s * bound <= 2^14 (fp16 overflows at 65504; the headroom covers fp32 summation slack)
+__device__ __forceinline__ float pow2_scale_for(float bound) {
+    if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
+    int e;
+    frexpf(bound, &e);                   // bound = f * 2^e, f in [0.5, 1)
+    int k = 14 - e;
+    k = k > 100 ? 100 : (k < -100 ? -100 : k);
+    return ldexpf(1.f, k);
+}
+
+// scales[0] = s1, [1] = 1/s1 : dhpre = (d_heads . Wh) * lrelu'   is stored as fp16(dhpre * s1),  |dhpre| <= amax * max_c sum_t |Wh[t][c]|
+// scales[2] = s2, [3] = 1/s2 : dx1   = (dhpre . W2) * lrelu'     is stored as fp16(dx1 * s2),    |dx1| <= bound1 * max_o sum_j |W2[j][o]|
+// scales[4] = s2/s1 is not needed: the dx1 GEMM rescales with acc_scale = 1/s1 then store_scale = s2.
+// one CTA of 256 threads; O <= 256.
+__global__ void __launch_bounds__(256) enc_bwd_scales_kernel(const float* __restrict__ amax, const float* __restrict__ wh, int NH,
+                                                             const float* __restrict__ w2, int O, float* __restrict__ scales) {
+    __shared__ float red[2][8];
+    const int c = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    if (c < O) {
+        for (int t = 0; t < NH; ++t) a += fabsf(wh[t * O + c]);
+        for (int j = 0; j < O; ++j) b += fabsf(w2[j * O + c]);    // column c of W2 (O,O): dx1[., c] = sum_j dhpre[., j] W2[j][c]
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((c & 31) == 0) { red[0][c >> 5] = a; red[1][c >> 5] = b; }
+    __syncthreads();
+    if (c == 0) {
+        float ma = 0.f, mb = 0.f;
+        for (int w = 0; w < 8; ++w) { ma = fmaxf(ma, red[0][w]); mb = fmaxf(mb, red[1][w]); }
+        const float bound1 = amax[0] * ma, bound2 = bound1 * mb;
+        const float s1 = pow2_scale_for(bound1), s2 = pow2_scale_for(bound2);
+        scales[0] = s1; scales[1] = 1.f / s1; scales[2] = s2; scales[3] = 1.f / s2;
+    }
+}
+
+// scales[2] = s, [3] = 1/s from amax alone (standalone GroupConv backward)
+__global__ void single_scale_kernel(const float* __restrict__ amax, float* __restrict__ scales) {
+    const float s = pow2_scale_for(amax[0]);
+    scales[2] = s; scales[3] = 1.f / s;
+}
+
+__global__ void to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = __float2half_rn(in[i]);
+}
+
+// out[c][r] = fp16(in[r][c]) : small weight transposes for the fp16 dgrad GEMMs
+__global__ void transpose_half_kernel(const float* __restrict__ in, __half* __restrict__ out, int rows, int cols) {
+    const long long total = (long long)rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = static_cast<int>(idx % cols);
+        const int r = static_cast<int>(idx / cols);
+        out[(long long)c * rows + r] = __float2half_rn(in[idx]);
+    }
 }
 
 }  // namespace tvae

@@ -65,7 +65,10 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
     constexpr int kAccStages = (512 / kBN) > 4 ? 4 : (512 / kBN);
     constexpr int kTmemCols = 512;
     constexpr int kBStageBytes = kBN * 128;
-    constexpr uint32_t kIdesc = make_idesc_tf32(kBM, kBN, P::kAMajorMN, P::kBMajorMN);
+    // 16-bit policies (P::kF16): kind::f16, a 128-byte stage row holds 64 reduction elements, one MMA consumes 16;
+    // MN-major 16-bit operands are stored as 32-element blocks [64 k rows][64 B] in the 64 B swizzle.
+    constexpr uint32_t kIdesc = P::kF16 ? make_idesc_f16(kBM, kBN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt)
+                                        : make_idesc_tf32(kBM, kBN, P::kAMajorMN, P::kBMajorMN);
     static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "invalid UMMA N");
 
     const int stages = prm.num_stages;
@@ -152,11 +155,19 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
 #pragma unroll
                     for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
                         uint64_t adesc, bdesc;
-                        if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                        else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                        if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                        else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
-                        umma_tf32(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                        if (P::kF16) {
+                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, 64 * 64, 512, kLayoutSw64);
+                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, 64 * 64, 512, kLayoutSw64);
+                            else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            umma_f16(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                        } else {
+                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
+                            else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            umma_tf32(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -243,6 +254,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // K-major operand tile: `rows` rows x 32 k-elements at (k = kc*32, row = r0): one box.
 __device__ __forceinline__ void tma_kmajor(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int kc, int r0) {
     tma_load_2d(dst, tm, bar, kc * kBK, r0);
+}
+// 16-bit K-major operand tile: `rows` rows x 64 k-elements at (k = kc*64, row = r0): one box.
+constexpr int kBKh = 64;
+__device__ __forceinline__ void tma_kmajor_h(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int kc, int r0) {
+    tma_load_2d(dst, tm, bar, kc * kBKh, r0);
+}
+// 16-bit MN-major operand tile: 64 reduction rows x (32*nblk) features starting at feature f0, rows r0..: one
+// {32 feat x 64 rows} box (64 B swizzle) per 32-wide feature block.
+__device__ __forceinline__ void tma_mnmajor_h(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int f0, int r0, int nblk) {
+    for (int b = 0; b < nblk; ++b) tma_load_2d(dst + b * (kBKh * 64), tm, bar, f0 + 32 * b, r0);
 }
 // MN-major operand tile: kBK reduction rows x (32*nblk) features starting at feature f0, rows r0..:
 // one {32 feat x kBK rows} box per 32-wide feature block.

@@ -54,7 +54,7 @@ int check_enc_shape(const tvae_enc_shape* s) {
     return 0;
 }
 
-template <int TMAX, int VEC, bool PLANAR>
+template <int TMAX, int VEC, bool PLANAR, bool H16 = false>
 int launch_thin_bwd(ThinBwdParams& p, int G, cudaStream_t st) {
     TVAE_REQUIRE(p.W % VEC == 0 && p.W / VEC <= 256 && p.T <= TMAX, "thin backward: unsupported width");
     const int cgs = p.W / VEC;
@@ -65,7 +65,7 @@ int launch_thin_bwd(ThinBwdParams& p, int G, cudaStream_t st) {
     const size_t sm = sizeof(float) * (kThinRB * p.T + (p.T + 1) * p.W + p.T);
     TVAE_REQUIRE(sm <= 48 * 1024, "thin backward: shared memory");
     ++g_launch_count;
-    thin_bwd_kernel<TMAX, VEC, PLANAR><<<cdiv(p.M, rows), cgs * rpp, sm, st>>>(p, G);
+    thin_bwd_kernel<TMAX, VEC, PLANAR, H16><<<cdiv(p.M, rows), cgs * rpp, sm, st>>>(p, G);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -169,14 +169,14 @@ Slab16Geom make_slab16(const ConvGeom& g, int rows_max, int channels) {
     sg.copy_words = words;
     return sg;
 }
-int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const float* bias, float* x1, int act, cudaStream_t st) {
+int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const float* bias, float* x1, __half* x1h, int act, cudaStream_t st) {
     Conv1FwdHParams p{};
     const int N = g.G * g.O;
     const int kpad16 = tvae_bank16_pitch(g.C, g.k);
     int rc;
     if ((rc = make_tmap_2d_h(&p.tmB, bank16, N, kpad16, kpad16, 128))) return rc;
     p.g = g;
-    p.y = y; p.bias = bias; p.x1 = x1; p.act = act;
+    p.y = y; p.bias = bias; p.x1 = x1; p.x1h = x1h; p.act = act;
     p.n_passes = cdiv(N, kAcc * kAccN);
     p.tiles_per_image = cdiv(g.P, kBM);
     p.m_tiles = g.B * p.tiles_per_image;
@@ -193,8 +193,8 @@ int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const f
     const int extra = p.tab_entries * 4 + 2 * p.sg.copy_words * 4;
     return launch_gemm2<Conv1FwdH>(p, extra, st, p.pairs);
 }
-// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); dx1 is bf16 [(b,r,pos)][O]
-int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, float* dbank, cudaStream_t st) {
+// conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); dx1 is fp16 [(b,r,pos)][O] times 1 / *acc_scale
+int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const float* acc_scale, float* dbank, cudaStream_t st) {
     Conv1WgradHParams p{};
     const int N = g.G * g.O;
     const long long R = (long long)g.B * g.G * g.P;
@@ -202,7 +202,7 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, float* db
     const int oblocks = g.O / 32;
     p.nb = (oblocks % 4 == 0) ? 4 : (oblocks % 2 == 0 ? 2 : 1);   // 128 accumulator columns = 4 / nb boxes of nb o-blocks
     if ((rc = make_tmap_3d_mn_h(&p.tmQ, dx1_16, R, g.O, g.O, kBK16, p.nb))) return rc;
-    p.g = g; p.y = y; p.dbank = dbank;
+    p.g = g; p.y = y; p.dbank = dbank; p.acc_scale = acc_scale;
     p.m_tiles = cdiv(g.K, kBM);
     p.m_pairs = cdiv(p.m_tiles, 2);
     p.n_passes = cdiv(N, kAcc * kAccN);
@@ -298,22 +298,25 @@ double tvae_conv1_executed_fraction(const tvae_enc_shape* s, int wgrad) {
 int tvae_groupconv_fwd(const tvae_enc_shape* s, const float* y, const void* bank, const float* bias, float* out, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
-    return conv1_forward(make_geom(s), y, bank, bias, out, 0, S(stream));
+    return conv1_forward(make_geom(s), y, bank, bias, out, nullptr, 0, S(stream));
 }
 
-int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* dbank, void* stream) {
+int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* dout, void* dout16, float* scales, float* dbank, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
     const ConvGeom g = make_geom(s);
     cudaStream_t st = S(stream);
     TVAE_CHECK_CUDA(cudaMemsetAsync(dbank, 0, sizeof(float) * g.G * g.O * g.kpad, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(scales, 0, sizeof(float) * 8, st));
     const long long R = (long long)g.B * g.G * g.P;
+    ++g_launch_count; absmax_kernel<<<blocks_for(R * g.O, 256), 256, 0, st>>>(dout, R * g.O, scales + 7);
+    ++g_launch_count; single_scale_kernel<<<1, 1, 0, st>>>(scales + 7, scales);
     const int rows_per_cta = static_cast<int>((R + 148LL * 8 - 1) / (148LL * 8));
     ++g_launch_count;
-    rows_to_bf16_colsum_kernel<<<cdiv(R, rows_per_cta), 256, g.O * sizeof(float), st>>>(
-        dout, static_cast<__nv_bfloat16*>(dout16), bias_grad_slot(g, dbank), g.kpad, R, g.O, rows_per_cta);
+    rows_to_half_colsum_kernel<<<cdiv(R, rows_per_cta), 256, g.O * sizeof(float), st>>>(
+        dout, static_cast<__half*>(dout16), scales, bias_grad_slot(g, dbank), g.kpad, R, g.O, rows_per_cta);
     TVAE_CHECK_CUDA(cudaGetLastError());
-    return conv1_wgrad(g, y, dout16, dbank, st);
+    return conv1_wgrad(g, y, dout16, scales + 3, dbank, st);
 }
 
 int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream) {
@@ -323,19 +326,19 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
     const int NH = 3 + 2 * s->z;
     const long long R = (long long)g.B * g.G * g.P;
     cudaStream_t st = S(stream);
-    if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, a->x1, 1, st))) return rc;
+    if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, nullptr, static_cast<__half*>(a->x1), 1, st))) return rc;
     // ---- conv2 (1x1x1) + heads
     {
-        ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2_tf32, (long long)g.O * g.O);
+        ++g_launch_count; to_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2_h), (long long)g.O * g.O);
         Conv2HeadsParams p{};
         const bool wide = g.O > 128;
         const int BN = wide ? 256 : 128;
-        if ((rc = make_tmap_2d(&p.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
-        if ((rc = make_tmap_2d(&p.tmB, a->w2_tf32, g.O, g.O, g.O, BN))) return rc;
+        if ((rc = make_tmap_2d_h(&p.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
+        if ((rc = make_tmap_2d_h(&p.tmB, a->w2_h, g.O, g.O, g.O, BN))) return rc;
         p.R = R; p.O = g.O; p.NH = NH; p.G = g.G; p.P = g.P;
-        p.k_chunks = cdiv(g.O, kBK);
+        p.k_chunks = cdiv(g.O, kBKh);
         p.num_tiles = cdiv(R, kBM);
-        p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh; p.head_add = a->head_add; p.h = a->h; p.heads = a->heads;
+        p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh; p.head_add = a->head_add; p.h = static_cast<__half*>(a->h); p.heads = a->heads;
         const int extra = (NH * g.O + g.O) * static_cast<int>(sizeof(float));
         if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH>>(p, extra, st);
         else if (NH <= 8) rc = launch_gemm<Conv2Heads<128, 8>>(p, extra, st);
@@ -358,33 +361,43 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->db2, 0, sizeof(float) * g.O, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dw2, 0, sizeof(float) * g.O * g.O, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbank, 0, sizeof(float) * g.G * g.O * g.kpad, st));
-    // ---- heads backward: dhpre = (d_heads . Wh) * lrelu'(h); dWh, dbh, db2
+    // ---- power-of-two scales that keep the fp16 gradient operands in range (computed on the device, no sync)
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->scales, 0, sizeof(float) * 8, st));
+    {
+        const long long n = (long long)g.B * NH * g.G * g.P;
+        ++g_launch_count; absmax_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->d_heads, n, a->scales + 7);
+        ++g_launch_count; enc_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 7, a->wh, NH, a->w2, g.O, a->scales);
+    }
+    // ---- heads backward: dhpre = (d_heads . Wh) * lrelu'(h), stored fp16 * s1; dWh, dbh, db2
     {
         ThinBwdParams p{};
         p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
+        p.store_scale = a->scales + 0;
         p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
         // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]
         p.dt_outer = (long long)NH * g.G * g.P;   // stride of b
         p.dt_chan = (long long)g.G * g.P;         // stride of channel j
-        if (NH <= 8) rc = launch_thin_bwd<8, 4, true>(p, g.G, st);
-        else if (NH <= 20) rc = launch_thin_bwd<20, 2, true>(p, g.G, st);
-        else rc = launch_thin_bwd<kMaxHeads + 1, 1, true>(p, g.G, st);
+        if (NH <= 8) rc = launch_thin_bwd<8, 4, true, true>(p, g.G, st);
+        else if (NH <= 20) rc = launch_thin_bwd<20, 2, true, true>(p, g.G, st);
+        else rc = launch_thin_bwd<kMaxHeads + 1, 1, true, true>(p, g.G, st);
         if (rc) return rc;
     }
-    // ---- dW2 = dhpre^T x1
-    if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st))) return rc;
-    // ---- dx1pre = (dhpre W2) * lrelu'(x1), in place over x1
-    ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, a->w2t_tf32, g.O, g.O, 1);
+    // ---- dW2 = dhpre^T x1   (fp16 x fp16, accumulators carry s1)
+    if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st, 1, a->scales + 1))) return rc;
+    // ---- dx1pre = (dhpre W2) * lrelu'(x1), stored fp16 * s2; its column sums are the conv1 bias gradient
+    ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
     {
         LinearNTArgs l{};
-        l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_tf32; l.ldb = g.O;
+        l.f16 = 1;
+        l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_h; l.ldb = g.O;
         l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
-        l.C = nullptr; l.C16 = a->dx1_16; l.ldc16 = g.O; l.aux = a->x1; l.ld_aux = g.O;
-        l.colsum = bias_grad_slot(g, a->dbank); l.colsum_stride = g.kpad;     // conv1 bias gradient
+        l.C = nullptr; l.C16 = a->dx1_16; l.ldc16 = g.O; l.aux16 = a->x1; l.ld_aux = g.O;
+        l.acc_scale = a->scales + 1; l.store_scale = a->scales + 2;
+        l.colsum = bias_grad_slot(g, a->dbank); l.colsum_stride = g.kpad;
         if ((rc = linear_nt(l, st))) return rc;
     }
     // ---- conv1 weight gradient (w.r.t. the rotated bank)
-    return conv1_wgrad(g, a->y, a->dx1_16, a->dbank, st);
+    return conv1_wgrad(g, a->y, a->dx1_16, a->scales + 3, a->dbank, st);
 }
 
 // ================================================================================ attention

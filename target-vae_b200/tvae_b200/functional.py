@@ -46,8 +46,10 @@ class GroupConvFn(torch.autograd.Function):
             raise NotImplementedError("GroupConv: gradient w.r.t. the input image is not part of the hot path")
         gi = g.permute(0, 2, 3, 4, 1).contiguous().view(-1, s.O).float()
         dbank = ops.empty(s.G * s.O, s.kpad, device=g.device)
-        gi16 = torch.empty(gi.shape, device=g.device, dtype=torch.bfloat16)
-        ops.check(ops.L().tvae_groupconv_wgrad(ops.byref(s), ops.ptr(yc), ops.ptr(gi), ops.ptr(gi16), ops.ptr(dbank), ops.stream_ptr()),
+        gi16 = ops.half(*gi.shape, device=g.device)
+        scales = ops.empty(8, device=g.device)
+        ops.check(ops.L().tvae_groupconv_wgrad(ops.byref(s), ops.ptr(yc), ops.ptr(gi), ops.ptr(gi16), ops.ptr(scales), ops.ptr(dbank),
+                                               ops.stream_ptr()),
                   "tvae_groupconv_wgrad")
         dw, db = ops.filter_bank_bwd(s, dbank)
         return None, dw, (db if ctx.has_bias else None), None, None

@@ -19,11 +19,11 @@ class EncShape(Structure):
 
 class EncFwdArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ("y", "bank", "conv1_bias", "w2", "b2", "wh", "bh", "head_add",
-                                         "x1", "h", "heads", "w2_tf32")]
+                                         "x1", "h", "heads", "w2_h")]
 
 
 class EncBwdArgs(Structure):
-    _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "dx1_16", "w2t_tf32", "dbank",
+    _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "dx1_16", "w2t_h", "scales", "dbank",
                                          "dw2", "db2", "dwh", "dbh")]
 
 
@@ -107,6 +107,10 @@ def empty(*shape, device):
     return torch.empty(*shape, device=device, dtype=torch.float32)
 
 
+def half(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.float16)
+
+
 # ----------------------------------------------------------------------------------------------- encoder
 def enc_shape(B, C, n, k, p, G, O, z) -> EncShape:
     return EncShape(B, C, n, k, p, G, O, z, L().tvae_bank_pitch(C, k))
@@ -177,12 +181,13 @@ def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add):
     P = d * d
     R = s.B * s.G * P
     NH = 3 + 2 * s.z
-    x1 = empty(R, s.O, device=dev)
-    h = empty(R, s.O, device=dev)
+    # activations are stored fp16 (the MMA operand format: 11-bit significand like TF32, half the HBM traffic)
+    x1 = half(R, s.O, device=dev)
+    h = half(R, s.O, device=dev)
     heads = empty(s.B, NH, s.G, P, device=dev)
-    w2r = empty(s.O, s.O, device=dev)
+    w2r = half(s.O, s.O, device=dev)
     a = _set(EncFwdArgs(), y=f32(y), bank=bank, conv1_bias=f32(b1), w2=f32(w2), b2=f32(b2), wh=wh, bh=bh,
-             head_add=head_add, x1=x1, h=h, heads=heads, w2_tf32=w2r)
+             head_add=head_add, x1=x1, h=h, heads=heads, w2_h=w2r)
     check(L().tvae_encoder_fwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_fwd")
     return x1, h, heads
 
@@ -191,15 +196,17 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
     dev = y.device
     NH = 3 + 2 * s.z
     R = x1.shape[0]
-    dhpre = empty(R, s.O, device=dev)
-    w2t = empty(s.O, s.O, device=dev)
+    dhpre = half(R, s.O, device=dev)
+    w2t = half(s.O, s.O, device=dev)
+    scales = empty(8, device=dev)
     dbank = empty(s.G * s.O, s.kpad, device=dev)
     dw2 = empty(s.O, s.O, device=dev)
     db2 = empty(s.O, device=dev)
     dwh = empty(NH, s.O, device=dev)
     dbh = empty(NH, device=dev)
-    dx1_16 = torch.empty(R, s.O, device=dev, dtype=torch.bfloat16)
-    a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, dx1_16=dx1_16, w2t_tf32=w2t,
+    dx1_16 = half(R, s.O, device=dev)
+    a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, dx1_16=dx1_16, w2t_h=w2t,
+             scales=scales,
              dbank=dbank, dw2=dw2, db2=db2, dwh=dwh, dbh=dbh)
     check(L().tvae_encoder_bwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_bwd")
     return dbank, dw2, db2, dwh, dbh

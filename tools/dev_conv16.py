@@ -28,9 +28,10 @@ def run(B, C, n, k, p, G, O, timing=False):
     e_f = float((out - ref).norm() / ref.norm())
     # wgrad
     g = torch.randn(B * G * d * d, O, device=dev) * 1e-3
-    g16 = torch.empty_like(g, dtype=torch.bfloat16)
+    g16 = torch.empty_like(g, dtype=torch.float16)
+    scales = ops.empty(8, device=dev)
     dbank = ops.empty(G * O, s.kpad, device=dev)
-    ops.check(L.tvae_groupconv_wgrad(ops.byref(s), ops.ptr(y), ops.ptr(g), ops.ptr(g16), ops.ptr(dbank), ops.stream_ptr()), "wgrad")
+    ops.check(L.tvae_groupconv_wgrad(ops.byref(s), ops.ptr(y), ops.ptr(g), ops.ptr(g16), ops.ptr(scales), ops.ptr(dbank), ops.stream_ptr()), "wgrad")
     torch.cuda.synchronize()
     twr = tw.clone().requires_grad_(True)
     o2 = F.conv2d(y, twr, None, 1, p)                   # (B, G*O, d, d)
@@ -41,11 +42,11 @@ def run(B, C, n, k, p, G, O, timing=False):
     refb = g.view(B * G, d * d, O).sum((0, 1))
     gotb = dbank[:O, K]
     e_b = float((gotb - refb).norm() / refb.norm())
-    e_16 = float((g16.float() - g).norm() / g.norm())
-    msg = f"B{B} C{C} n{n} k{k} p{p} G{G} O{O}: fwd {e_f:.2e} wgrad {e_w:.2e} bias {e_b:.2e} (bf16 copy {e_16:.2e})"
+    e_16 = float((g16.float() * float(scales[3]) - g).norm() / g.norm())
+    msg = f"B{B} C{C} n{n} k{k} p{p} G{G} O{O}: fwd {e_f:.2e} wgrad {e_w:.2e} bias {e_b:.2e} (fp16 copy {e_16:.2e}, scale {float(scales[2]):.3g})"
     if timing:
         for fn, nm in ((lambda: L.tvae_groupconv_fwd(ops.byref(s), ops.ptr(y), ops.ptr(bank), ops.ptr(bias), ops.ptr(out), ops.stream_ptr()), "fwd"),
-                       (lambda: L.tvae_groupconv_wgrad(ops.byref(s), ops.ptr(y), ops.ptr(g), ops.ptr(g16), ops.ptr(dbank), ops.stream_ptr()), "wgrad(+cvt)")):
+                       (lambda: L.tvae_groupconv_wgrad(ops.byref(s), ops.ptr(y), ops.ptr(g), ops.ptr(g16), ops.ptr(scales), ops.ptr(dbank), ops.stream_ptr()), "wgrad(+cvt)")):
             for _ in range(3): fn()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
