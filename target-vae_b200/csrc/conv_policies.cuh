@@ -49,6 +49,7 @@ struct Conv2Heads : PolicyBase {
     using Params = Conv2HeadsParams;
     static constexpr int kBN = BN;
     static constexpr bool kF16 = true;        // x1 and W2 are fp16 operands (64 k-elements per stage)
+    static constexpr int kEpiGroups = 2;      // K = O is 2 stages: the epilogue is the critical path
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);

@@ -28,7 +28,7 @@ inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t st
         TVAE_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
         configured = kMaxSmemBytes;
     }
-    const int threads = (kCtrlWarps + kEpiWarps + P::kProdWarps) * 32;
+    const int threads = (kCtrlWarps + kEpiWarps * P::kEpiGroups + P::kProdWarps) * 32;
     const int grid = prm.num_tiles < sm_count() ? prm.num_tiles : sm_count();
     ++g_launch_count;
     const int tslot = g_timer.begin(P::kName, stream);
@@ -86,7 +86,7 @@ struct LinearNTArgs {
 
 inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     TVAE_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_nt: empty problem");
-    TVAE_REQUIRE(a.N % 4 == 0, "linear_nt: N must be a multiple of 4");
+    TVAE_REQUIRE(a.N % 4 == 0 && a.N <= 1024, "linear_nt: N must be a multiple of 4, at most 1024");
     TVAE_REQUIRE(a.n_proj <= 4, "linear_nt: at most 4 fused projection outputs");
     LinearNTParams p{};
     const bool wide = a.N > 128;

@@ -68,18 +68,29 @@ struct LinearNT : PolicyBase {
     using Params = LinearNTParams;
     static constexpr int kBN = BN;
     static constexpr bool kF16 = F16;          // fp16 A and B (TMA boxes of 64 k-elements)
-    // column sums: extra smem [4 epilogue warps][BN] floats, entry (warp, c*32 + lane) is owned by one thread
-    static constexpr int kExtraBytes = kEpiWarps * BN * 4;
-    __device__ static void epi_init(const Params& p, EpiState&, uint8_t* extra, int row) {
+    static constexpr int kEpiGroups = 2;       // short K loops: the epilogue is the critical path, two warpgroups alternate tiles
+    // extra smem: [N] bias, [4][N] fused-projection weights, then column sums [8 epilogue warps][BN] floats (entry
+    // (warp, c*32 + lane) is owned by one thread)
+    static constexpr int kMaxN = 1024;
+    static constexpr int kCsOff = 5 * kMaxN;
+    static constexpr int kExtraBytes = (kCsOff + kEpiGroups * kEpiWarps * BN) * 4;
+    struct EpiState { int cs; };
+    __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
+        float* s = reinterpret_cast<float*>(extra);
+        for (int i = tid; i < p.N; i += nthreads) s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        for (int i = tid; i < p.n_proj * p.N; i += nthreads) s[kMaxN + (i / p.N) * kMaxN + (i % p.N)] = __ldg(p.proj_w + i);
+    }
+    __device__ static void epi_init(const Params& p, EpiState& st, uint8_t* extra, int slot) {
+        st.cs = kCsOff + (slot >> 5) * BN + (slot & 31);
         if (!p.colsum) return;
-        float* cs = reinterpret_cast<float*>(extra) + (row >> 5) * BN + (row & 31);
+        float* cs = reinterpret_cast<float*>(extra) + st.cs;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) cs[c * 32] = 0.f;
     }
-    __device__ static void epi_finish(const Params& p, EpiState&, uint8_t* extra, int row) {
+    __device__ static void epi_finish(const Params& p, EpiState& st, uint8_t* extra, int slot) {
         if (!p.colsum) return;
-        const int lane = row & 31;
-        const float* cs = reinterpret_cast<const float*>(extra) + (row >> 5) * BN + lane;
+        const int lane = slot & 31;
+        const float* cs = reinterpret_cast<const float*>(extra) + st.cs;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c)
             if (c * 32 + lane < p.N) atomicAdd(p.colsum + (long long)(c * 32 + lane) * p.colsum_stride, cs[c * 32]);
@@ -105,7 +116,8 @@ struct LinearNT : PolicyBase {
             tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
         }
     }
-    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
+    __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState& st, uint32_t taddr, int row, uint8_t* extra) {
+        const float* s_bias = reinterpret_cast<const float*>(extra);
         const int m = ti.m0 + row;
         const bool m_ok = m < p.M;
         float proj[4] = {0.f, 0.f, 0.f, 0.f};
@@ -128,8 +140,12 @@ struct LinearNT : PolicyBase {
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;
             if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n_base + j < p.N) v[j] += __ldg(p.bias + n_base + j);
+                for (int j = 0; j < 32; j += 4) {
+                    if (n_base + j < p.N) {
+                        const float4 t = *reinterpret_cast<const float4*>(s_bias + n_base + j);
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    }
+                }
             }
             if (rb) {
 #pragma unroll
@@ -179,7 +195,7 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
-                reinterpret_cast<float*>(extra)[(row >> 5) * BN + c * 32 + (row & 31)] += warp_colsum32(v, row & 31);
+                reinterpret_cast<float*>(extra)[st.cs + c * 32] += warp_colsum32(v, row & 31);
                 if (!m_ok) continue;
             }
             if (p.C16) {
@@ -199,11 +215,16 @@ struct LinearNT : PolicyBase {
             }
             if (p.proj_w) {
                 for (int o = 0; o < p.n_proj; ++o) {
-                    const float* w = p.proj_w + (long long)o * p.N + n_base;
+                    const float* w = s_bias + kMaxN + o * kMaxN + n_base;
                     float acc = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n_base + j < p.N) acc = fmaf(v[j], __ldg(w + j), acc);
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n_base + j < p.N) {
+                            const float4 t = *reinterpret_cast<const float4*>(w + j);
+                            acc = fmaf(v[j], t.x, acc); acc = fmaf(v[j + 1], t.y, acc);
+                            acc = fmaf(v[j + 2], t.z, acc); acc = fmaf(v[j + 3], t.w, acc);
+                        }
+                    }
                     proj[o] += acc;
                 }
             }

@@ -6,8 +6,10 @@
 //   warp 0      TMA producer (one lane): bulk-tensor loads into a ring of smem stages
 //   warp 1      MMA issuer   (one lane): tcgen05.mma.kind::tf32 on swizzled smem descriptors
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue: tcgen05.ld accumulator rows -> registers -> policy epilogue
-//   warps 8..   optional operand generators (im2col window / Fourier features / ...) that
+//   warps 4-7   epilogue: tcgen05.ld accumulator rows -> registers -> policy epilogue; policies whose epilogue
+//               is the bottleneck (streaming GEMMs with a short K loop) run P::kEpiGroups = 2 such warpgroups that
+//               take alternate tiles (each tile has its own TMEM accumulator stage)
+//   then        optional operand generators (im2col window / Fourier features / ...) that
 //               synthesise the A tile straight into swizzled smem instead of loading it
 // Three pipelines: smem full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
 // and a static contiguous tile schedule per CTA.
@@ -58,7 +60,7 @@ __host__ __device__ inline SmemLayout make_smem_layout(int stages, int extra_byt
 }
 
 template <class P>
-__global__ void __launch_bounds__((kCtrlWarps + kEpiWarps + P::kProdWarps) * 32, 1)
+__global__ void __launch_bounds__((kCtrlWarps + kEpiWarps * P::kEpiGroups + P::kProdWarps) * 32, 1)
 tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kBN = P::kBN;
@@ -70,6 +72,9 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
     constexpr uint32_t kIdesc = P::kF16 ? make_idesc_f16(kBM, kBN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt)
                                         : make_idesc_tf32(kBM, kBN, P::kAMajorMN, P::kBMajorMN);
     static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "invalid UMMA N");
+    constexpr int kEpiGroups = P::kEpiGroups;
+    constexpr int kFirstGenWarp = kFirstEpiWarp + kEpiWarps * kEpiGroups;
+    static_assert(kEpiGroups == 1 || (kEpiGroups == 2 && kAccStages % 2 == 0), "two epilogue groups need an even number of accumulator stages");
 
     const int stages = prm.num_stages;
     const SmemLayout L = make_smem_layout<P>(stages, 0);
@@ -176,29 +181,29 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
         }
-    } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
+    } else if (warp >= kFirstEpiWarp && warp < kFirstGenWarp) {
         // ------------------------------------------------------------ epilogue
-        const int ewarp = warp - kFirstEpiWarp;  // == warp % 4 -> TMEM lane quarter
+        const int ewarp = (warp - kFirstEpiWarp) & 3;  // == warp % 4 -> TMEM lane quarter
+        const int egrp = (warp - kFirstEpiWarp) >> 2;  // epilogue group: takes tiles t = egrp, egrp + kEpiGroups, ...
         const int row = ewarp * 32 + lane;
-        int as = 0;
-        uint32_t aphase = 0;
         typename P::EpiState est;
-        P::epi_init(prm, est, extra, row);
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        P::epi_init(prm, est, extra, egrp * kBM + row);     // slot: unique per epilogue thread
+        for (int tile = tile_begin + egrp, t = egrp; tile < tile_end; tile += kEpiGroups, t += kEpiGroups) {
             TileInfo ti;
             P::tile_info(prm, tile, ti);
+            const int as = t % kAccStages;
+            const uint32_t aphase = (t / kAccStages) & 1;
             mbar_wait(tfull_bar + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + as * kBN;
             P::epilogue(prm, ti, est, taddr, row, extra);
             tc_fence_before();
             mbar_arrive(tempty_bar + 8 * as);
-            if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
-        P::epi_finish(prm, est, extra, row);
-    } else if (P::kAGen && warp >= kFirstProdWarp) {
+        P::epi_finish(prm, est, extra, egrp * kBM + row);
+    } else if (P::kAGen && warp >= kFirstGenWarp) {
         // ------------------------------------------------------------ operand generators
-        const int ptid = threadIdx.x - kFirstProdWarp * 32;
+        const int ptid = threadIdx.x - kFirstGenWarp * 32;
         int stage = 0;
         uint32_t phase = 0;
         typename P::GenState gst;
@@ -232,7 +237,8 @@ struct PolicyBase {
     static constexpr bool kBMajorMN = false;
     static constexpr bool kAGen = false;
     static constexpr int kProdWarps = 0;
-    static constexpr bool kF16 = false;       // tc_gemm2: 16-bit operands (kind::f16)
+    static constexpr int kEpiGroups = 1;      // tc_gemm: epilogue warpgroups taking alternate tiles
+    static constexpr bool kF16 = false;       // 16-bit operands (kind::f16)
     static constexpr uint32_t kAFmt = 0;      // 0 = FP16, 1 = BF16
     static constexpr uint32_t kBFmt = 0;
     struct EpiState {};
