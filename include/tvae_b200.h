@@ -160,17 +160,18 @@ typedef struct {
     const float* wout;       /* (n_out,H) */
     const float* bout;       /* (n_out) */
     float* zb;               /* out (B,H) latent_linear(z) */
-    float* acts;             /* out [L+1][B*N][H] post-activation of every hidden layer (tf32) */
+    void* acts;              /* out fp16 [L+1][B*N][H] post-activation of every hidden layer */
     float* y_hat;            /* out (B*N, n_out) */
-    float* w_tf32;           /* scratch: H*max(E,2) + L*H*H floats */
+    void* w_h;               /* scratch fp16: H*max(E,2) + L*H*H halves (fp16 copies of the weights) */
 } tvae_gen_fwd_args;
 int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void* stream);
 
 typedef struct {
     tvae_gen_fwd_args f;
     const float* d_yhat;     /* (B*N, n_out) */
-    float* dpre0; float* dpre1;   /* scratch [B*N][H] each */
-    float* wt_tf32;          /* scratch: max(E*H, H*H) floats (transposed weights) */
+    void* dpre0; void* dpre1;     /* scratch fp16 [B*N][H] each: layer gradients times a power-of-two scale */
+    void* wt_h;              /* scratch fp16: max(E*H, H*H) halves (transposed weights) */
+    float* scales;           /* scratch, 32 floats: the per-layer scales (computed on the device) */
     float* dxp;              /* scratch/out (B*N,2): gradient w.r.t. the transformed coordinates */
     float* dzb;              /* scratch (B,H) */
     float* dw1; float* db1; float* dwz; float* dwh; float* dbh; float* dwout; float* dbout;  /* out, same shapes as weights */

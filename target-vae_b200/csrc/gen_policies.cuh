@@ -6,10 +6,14 @@
 // per tile directly into the swizzled A operand, forward and again in the weight-gradient GEMM; the
 // coordinate gradient GEMM applies -sin(.) and the projection onto (wx, wy) in its epilogue.
 //
+// All three run kind::f16: features, weights and the stored activations / gradients are fp16 (11-bit significand,
+// the precision class of TF32); gradients carry a power-of-two scale that the epilogues divide out (acc_scale).
+//
 //   GenL1Fwd   : h1 = LeakyReLU(feat W1^T + b1 + zb[b])                 A generated (K-major), B = W1 (TMA)
 //   GenL1Wgrad : dW1[j][f] = sum_m dpre[m][j] feat[m][f]                A = feat^T generated (MN-major), B = dpre (TMA)
 //   GenL1Dgrad : dx'[m] = sum_f (-sin(phase) * (dpre W1)[m][f]) (wx_f, wy_f)   A = dpre (TMA), B = W1^T (TMA)
 #pragma once
+#include <cuda_fp16.h>
 #include "linear_policies.cuh"
 
 namespace tvae {
@@ -53,7 +57,7 @@ __device__ __forceinline__ float fourier_phase(const float4& w, float x0, float 
 
 // ------------------------------------------------------------------------------------------------
 struct GenL1FwdParams {
-    CUtensorMap tmB;          // W1 [H][E]
+    CUtensorMap tmB;          // W1 fp16 [H][E]
     int num_stages, num_tiles, tiles_n, k_chunks;
     CoordXform cx;
     const float* wf_scaled;   // (E,2) = embed_latent.weight / sigma
@@ -61,14 +65,20 @@ struct GenL1FwdParams {
     int E, H;
     const float* bias;        // (H)
     const float* zb;          // (B,H) latent_linear(z)
-    float* h1;                // [M][H]
+    __half* h1;               // fp16 [M][H]
 };
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 template <int BN>
 struct GenL1Fwd : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
     using Params = GenL1FwdParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = true;
     static constexpr bool kAGen = true;
     static constexpr int kProdWarps = 8;
     struct GenState { float x0, x1; };
@@ -85,24 +95,26 @@ struct GenL1Fwd : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t, uint32_t sb, uint32_t bar) {
-        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+        tma_kmajor_h(sb, &p.tmB, bar, kc, ti.n0);
     }
     __device__ static void gen_tile_begin(const Params& p, const TileInfo& ti, GenState& s, uint8_t*, int ptid) {
         transformed_coord(p.cx, (long long)ti.m0 + (ptid & (kBM - 1)), s.x0, s.x1);
     }
+    // 256 generator threads: thread = one row, 32 of the chunk's 64 features (4 swizzled 16-byte stores of 8 halves)
     __device__ static void gen_chunk(const Params& p, const TileInfo&, GenState& s, int kc, uint8_t* a_stage, uint8_t* extra, int ptid) {
         const float4* tab = reinterpret_cast<const float4*>(extra);
         const int row = ptid & (kBM - 1), half = ptid >> 7;
-        const int f0 = kc * kBK + half * 16;
+        const int f0 = kc * kBKh + half * 32;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            float e[4];
+            float e[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = f0 + ch * 4 + q;
-                e[q] = f < p.E ? to_tf32(__cosf(fourier_phase(tab[f], s.x0, s.x1))) : 0.f;
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + ch * 8 + q;
+                e[q] = f < p.E ? __cosf(fourier_phase(tab[f], s.x0, s.x1)) : 0.f;
             }
-            *reinterpret_cast<float4*>(a_stage + sw128_offset(row, half * 4 + ch)) = make_float4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, half * 4 + ch)) =
+                make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
         }
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
@@ -116,17 +128,21 @@ struct GenL1Fwd : PolicyBase {
             tmem_ld_wait();
             const int n0 = ti.n0 + c * 32;
             if (!ok || n0 >= p.H) continue;
-            float* dst = p.h1 + m * p.H + n0;
+            __half* dst = p.h1 + m * p.H + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                float4 t;
-                t.x = to_tf32(lrelu(__uint_as_float(rr[j]) + bb.x + bz.x));
-                t.y = to_tf32(lrelu(__uint_as_float(rr[j + 1]) + bb.y + bz.y));
-                t.z = to_tf32(lrelu(__uint_as_float(rr[j + 2]) + bb.z + bz.z));
-                t.w = to_tf32(lrelu(__uint_as_float(rr[j + 3]) + bb.w + bz.w));
-                *reinterpret_cast<float4*>(dst + j) = t;
+            for (int j = 0; j < 32; j += 8) {
+                float t[8];
+#pragma unroll
+                for (int q = 0; q < 8; q += 4) {
+                    const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + n0 + j + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + q));
+                    t[q] = lrelu(__uint_as_float(rr[j + q]) + bb.x + bz.x);
+                    t[q + 1] = lrelu(__uint_as_float(rr[j + q + 1]) + bb.y + bz.y);
+                    t[q + 2] = lrelu(__uint_as_float(rr[j + q + 2]) + bb.z + bz.z);
+                    t[q + 3] = lrelu(__uint_as_float(rr[j + q + 3]) + bb.w + bz.w);
+                }
+                *reinterpret_cast<uint4*>(dst + j) =
+                    make_uint4(pack_half2(t[0], t[1]), pack_half2(t[2], t[3]), pack_half2(t[4], t[5]), pack_half2(t[6], t[7]));
             }
         }
     }
@@ -134,12 +150,13 @@ struct GenL1Fwd : PolicyBase {
 
 // ------------------------------------------------------------------------------------------------
 struct GenL1WgradParams {
-    CUtensorMap tmQ;          // dpre [M][H], MN-major boxes
+    CUtensorMap tmQ;          // dpre fp16 (scaled) [M][H], MN-major boxes
     int num_stages, num_tiles, tiles_m, tiles_n, splits, chunks_total, chunks_per_split;
     CoordXform cx;
     const float* wf_scaled; const float* bf;
     int E, H;
     float* dW1;               // [H][E], zero-filled by the caller
+    const float* acc_scale;   // device scalar: 1 / (scale dpre was stored with)
 };
 
 template <int BN>
@@ -147,6 +164,7 @@ struct GenL1Wgrad : PolicyBase {
     static constexpr const char* kName = "gen_l1_wgrad";
     using Params = GenL1WgradParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = true;
     static constexpr bool kAMajorMN = true;
     static constexpr bool kBMajorMN = true;
     static constexpr bool kAGen = true;
@@ -167,31 +185,36 @@ struct GenL1Wgrad : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t, uint32_t sb, uint32_t bar) {
-        tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
+        tma_mnmajor_h(sb, &p.tmQ, bar, ti.n0, kc * kBKh, BN / 32);
     }
+    // A = feat^T, MN-major: four 32-feature blocks [64 pixel rows][64 B] in the 64 B swizzle.  256 generator threads:
+    // thread = (pixel row of the chunk, feature block), 32 features = 4 x 16-byte stores; the 8 lanes of a store phase
+    // write 8 consecutive rows of one granule column = 8 distinct 16-byte slots (conflict-free).
     __device__ static void gen_chunk(const Params& p, const TileInfo& ti, GenState&, int kc, uint8_t* a_stage, uint8_t* extra, int ptid) {
         const float4* tab = reinterpret_cast<const float4*>(extra);
-        const int rrow = ptid & 31, cb = (ptid >> 5) & 3, half = ptid >> 7;
+        const int rrow = ptid & 63, fb = ptid >> 6;
         float x0, x1;
-        const long long m = (long long)kc * kBK + rrow;
+        const long long m = (long long)kc * kBKh + rrow;
         transformed_coord(p.cx, m, x0, x1);
         const bool ok = m < p.cx.M;
-        const int f0 = ti.m0 + cb * 32 + half * 16;
-        uint8_t* blk = a_stage + cb * (kBK * 128);
+        const int f0 = ti.m0 + fb * 32;
+        uint8_t* blk = a_stage + fb * (kBKh * 64);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            float e[4];
+            float e[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = f0 + ch * 4 + q;
-                e[q] = (ok && f < p.E) ? to_tf32(__cosf(fourier_phase(tab[f], x0, x1))) : 0.f;
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + ch * 8 + q;
+                e[q] = (ok && f < p.E) ? __cosf(fourier_phase(tab[f], x0, x1)) : 0.f;
             }
-            *reinterpret_cast<float4*>(blk + sw128b32_offset(rrow, half * 4 + ch)) = make_float4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<uint4*>(blk + rrow * 64 + ((ch ^ ((rrow >> 1) & 3)) << 4)) =
+                make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
         }
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
         const int f = ti.m0 + row;
         const bool empty = ti.kc_begin >= ti.kc_end;
+        const float acc_scale = __ldg(p.acc_scale);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t rr[32];
@@ -201,19 +224,20 @@ struct GenL1Wgrad : PolicyBase {
             const int j0 = ti.n0 + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (j0 + j < p.H) atomicAdd(p.dW1 + (long long)(j0 + j) * p.E + f, __uint_as_float(rr[j]));
+                if (j0 + j < p.H) atomicAdd(p.dW1 + (long long)(j0 + j) * p.E + f, __uint_as_float(rr[j]) * acc_scale);
         }
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 struct GenL1DgradParams {
-    CUtensorMap tmA, tmB;     // dpre [M][H]; W1^T [E][H]
+    CUtensorMap tmA, tmB;     // dpre fp16 (scaled) [M][H]; W1^T fp16 [E][H]
     int num_stages, num_tiles, tiles_n, k_chunks;
     CoordXform cx;
     const float* wf_scaled; const float* bf;
     int E, H;
     float* dxp;               // [M][2] gradient w.r.t. transformed coords, zero-filled by the caller
+    const float* acc_scale;   // device scalar: 1 / (scale dpre was stored with)
 };
 
 template <int BN>
@@ -221,6 +245,7 @@ struct GenL1Dgrad : PolicyBase {
     static constexpr const char* kName = "gen_l1_dgrad";
     using Params = GenL1DgradParams;
     static constexpr int kBN = BN;
+    static constexpr bool kF16 = true;
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -237,11 +262,12 @@ struct GenL1Dgrad : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
-        tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
+        tma_kmajor_h(sa, &p.tmA, bar, kc, ti.m0);
+        tma_kmajor_h(sb, &p.tmB, bar, kc, ti.n0);
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t* extra) {
         const float4* tab = reinterpret_cast<const float4*>(extra);
+        const float acc_scale = __ldg(p.acc_scale);
         const long long m = (long long)ti.m0 + row;
         float x0, x1;
         transformed_coord(p.cx, m, x0, x1);
@@ -264,8 +290,8 @@ struct GenL1Dgrad : PolicyBase {
             }
         }
         if (m < p.cx.M) {
-            atomicAdd(p.dxp + 2 * m, g0);
-            atomicAdd(p.dxp + 2 * m + 1, g1);
+            atomicAdd(p.dxp + 2 * m, g0 * acc_scale);
+            atomicAdd(p.dxp + 2 * m + 1, g1 * acc_scale);
         }
     }
 };

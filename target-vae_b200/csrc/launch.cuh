@@ -109,7 +109,6 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
     p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
-    TVAE_REQUIRE(!a.colsum || p.tiles_n == 1, "linear_nt: column sums need a single N tile");
     if (a.f16)
         return wide ? launch_gemm<LinearNT<256, true>>(p, LinearNT<256, true>::kExtraBytes, stream)
                     : launch_gemm<LinearNT<128, true>>(p, LinearNT<128, true>::kExtraBytes, stream);

@@ -69,11 +69,11 @@ struct LinearNT : PolicyBase {
     static constexpr int kBN = BN;
     static constexpr bool kF16 = F16;          // fp16 A and B (TMA boxes of 64 k-elements)
     static constexpr int kEpiGroups = 2;       // short K loops: the epilogue is the critical path, two warpgroups alternate tiles
-    // extra smem: [N] bias, [4][N] fused-projection weights, then column sums [8 epilogue warps][BN] floats (entry
-    // (warp, c*32 + lane) is owned by one thread)
+    // extra smem: [N] bias, [4][N] fused-projection weights, then column sums [8 epilogue warps][kMaxN] floats (entry
+    // (warp, column) with column % 32 == lane is owned by one thread)
     static constexpr int kMaxN = 1024;
     static constexpr int kCsOff = 5 * kMaxN;
-    static constexpr int kExtraBytes = (kCsOff + kEpiGroups * kEpiWarps * BN) * 4;
+    static constexpr int kExtraBytes = (kCsOff + kEpiGroups * kEpiWarps * kMaxN) * 4;
     struct EpiState { int cs; };
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         float* s = reinterpret_cast<float*>(extra);
@@ -81,18 +81,16 @@ struct LinearNT : PolicyBase {
         for (int i = tid; i < p.n_proj * p.N; i += nthreads) s[kMaxN + (i / p.N) * kMaxN + (i % p.N)] = __ldg(p.proj_w + i);
     }
     __device__ static void epi_init(const Params& p, EpiState& st, uint8_t* extra, int slot) {
-        st.cs = kCsOff + (slot >> 5) * BN + (slot & 31);
+        st.cs = kCsOff + (slot >> 5) * kMaxN + (slot & 31);
         if (!p.colsum) return;
         float* cs = reinterpret_cast<float*>(extra) + st.cs;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) cs[c * 32] = 0.f;
+        for (int c = 0; c * 32 < p.N; ++c) cs[c * 32] = 0.f;
     }
     __device__ static void epi_finish(const Params& p, EpiState& st, uint8_t* extra, int slot) {
         if (!p.colsum) return;
         const int lane = slot & 31;
         const float* cs = reinterpret_cast<const float*>(extra) + st.cs;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c)
+        for (int c = 0; c * 32 < p.N; ++c)
             if (c * 32 + lane < p.N) atomicAdd(p.colsum + (long long)(c * 32 + lane) * p.colsum_stride, cs[c * 32]);
     }
     __device__ static void prefetch_descs(const Params& p) {
@@ -195,7 +193,7 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
-                reinterpret_cast<float*>(extra)[st.cs + c * 32] += warp_colsum32(v, row & 31);
+                reinterpret_cast<float*>(extra)[st.cs + n_base] += warp_colsum32(v, row & 31);
                 if (!m_ok) continue;
             }
             if (p.C16) {

@@ -34,12 +34,12 @@ __global__ void latent_bias_bwd_kernel(const float* __restrict__ dzb, const floa
     }
 }
 
-// No Fourier expansion (cfg2): a0[m][j] = LeakyReLU(x'0 W1[j][0] + x'1 W1[j][1] + b1[j] + zb[b][j]), tf32-rounded.
+// No Fourier expansion (cfg2): a0[m][j] = LeakyReLU(x'0 W1[j][0] + x'1 W1[j][1] + b1[j] + zb[b][j]), stored fp16.
 // CTA = kCoordRB rows; the transformed coordinates of the block are computed once into shared memory, then
 // thread = 4 adjacent columns x one row slot streams float4 stores (HBM-bound: one write of a0).
 constexpr int kCoordRB = 64;
 __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                              const float* __restrict__ zb, float* __restrict__ a0, int H) {
+                                                              const float* __restrict__ zb, __half* __restrict__ a0, int H) {
     __shared__ float2 s_x[kCoordRB];
     const int cgs = H / 4, rpp = blockDim.x / cgs;
     const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
@@ -60,18 +60,18 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
         const float2 x = s_x[rr];
         float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0));
-        float4 o;
-        o.x = to_tf32(lrelu(fmaf(x.y, wy[0], fmaf(x.x, wx[0], bb[0])) + z4.x));
-        o.y = to_tf32(lrelu(fmaf(x.y, wy[1], fmaf(x.x, wx[1], bb[1])) + z4.y));
-        o.z = to_tf32(lrelu(fmaf(x.y, wy[2], fmaf(x.x, wx[2], bb[2])) + z4.z));
-        o.w = to_tf32(lrelu(fmaf(x.y, wy[3], fmaf(x.x, wx[3], bb[3])) + z4.w));
-        *reinterpret_cast<float4*>(a0 + m * H + c0) = o;
+        const float o0 = lrelu(fmaf(x.y, wy[0], fmaf(x.x, wx[0], bb[0])) + z4.x);
+        const float o1 = lrelu(fmaf(x.y, wy[1], fmaf(x.x, wx[1], bb[1])) + z4.y);
+        const float o2 = lrelu(fmaf(x.y, wy[2], fmaf(x.x, wx[2], bb[2])) + z4.z);
+        const float o3 = lrelu(fmaf(x.y, wy[3], fmaf(x.x, wx[3], bb[3])) + z4.w);
+        *reinterpret_cast<uint2*>(a0 + m * H + c0) = make_uint2(pack_half2(o0, o1), pack_half2(o2, o3));
     }
 }
 // backward of the above in one pass over dpre:  dW1[j][0..1] += sum_m dpre[m][j] x'[m]  and
 // dxp[m] = sum_j dpre[m][j] W1[j][:]   (CTA = rows_per_cta rows in blocks of kCoordRB).
-__global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ dpre,
-                                                              float* __restrict__ dw1, float* __restrict__ dxp, int H, int rows_per_cta) {
+__global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, const float* __restrict__ w1, const __half* __restrict__ dpre,
+                                                              const float* __restrict__ inv_scale, float* __restrict__ dw1,
+                                                              float* __restrict__ dxp, int H, int rows_per_cta) {
     extern __shared__ float s_cl[];
     float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [kCoordRB]
     float* s_dx = s_cl + 2 * kCoordRB;                              // [kCoordRB][2]
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
     const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
     const int c0 = cg * 4, lane = threadIdx.x & 31;
     const bool warp_rows = (cgs % 32) == 0;                         // every warp lies inside one row
+    const float inv = __ldg(inv_scale);
     float wx[4], wy[4], dwx[4], dwy[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; dwx[v] = 0.f; dwy[v] = 0.f; }
@@ -102,7 +103,11 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int rr = rr0 + q * rpp;
-                if (rr < rows) g[q] = *reinterpret_cast<const float4*>(dpre + (m0 + rr) * H + c0);
+                if (rr < rows) {
+                    const uint2 t = *reinterpret_cast<const uint2*>(dpre + (m0 + rr) * H + c0);
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+                    g[q] = make_float4(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -171,14 +176,14 @@ __global__ void __launch_bounds__(256) coord_xform_bwd_kernel(CoordXform cx, con
 }
 
 // thin forward (output layer straight after layer 1 when num_layers == 1): y[m][o] = sum_c a[m][c] W[o][c] + b[o]; warp per row.
-__global__ void __launch_bounds__(256) thin_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256) thin_fwd_kernel(const __half* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ y, long long M, int W, int T) {
     const int lane = threadIdx.x & 31;
     const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= M) return;
     for (int o = 0; o < T; ++o) {
         float acc = 0.f;
-        for (int c = lane; c < W; c += 32) acc = fmaf(a[m * W + c], w[(long long)o * W + c], acc);
+        for (int c = lane; c < W; c += 32) acc = fmaf(__half2float(a[m * W + c]), w[(long long)o * W + c], acc);
         acc = warp_sum(acc);
         if (lane == 0) y[m * T + o] = acc + bias[o];
     }

@@ -712,13 +712,16 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
 
 // column sums per group of rows: out[g][c] = sum_{m in group g} x[m][c]   (z-conditioned bias gradient),
 // and total[c] += sum over all rows.  grid = (chunks, groups), blockDim.x = W.
-__global__ void __launch_bounds__(1024) group_colsum_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                           float* __restrict__ total, int rows_per_group, int W, int rows_per_cta) {
+// x is fp16 holding value * (1 / *inv_scale).
+__global__ void __launch_bounds__(1024) group_colsum_kernel(const __half* __restrict__ x, const float* __restrict__ inv_scale,
+                                                           float* __restrict__ out, float* __restrict__ total, int rows_per_group,
+                                                           int W, int rows_per_cta) {
     const int c = threadIdx.x, g = blockIdx.y;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows_per_group);
-    const float* xg = x + ((long long)g * rows_per_group) * W;
+    const __half* xg = x + ((long long)g * rows_per_group) * W;
     float acc = 0.f;
-    for (int r = r0; r < r1; ++r) acc += xg[(long long)r * W + c];
+    for (int r = r0; r < r1; ++r) acc += __half2float(xg[(long long)r * W + c]);
+    acc *= __ldg(inv_scale);
     if (out) atomicAdd(out + (long long)g * W + c, acc);
     if (total) atomicAdd(total + c, acc);
 }
@@ -771,6 +774,41 @@ __global__ void __launch_bounds__(256) enc_bwd_scales_kernel(const float* __rest
         const float bound1 = amax[0] * ma, bound2 = bound1 * mb;
         const float s1 = pow2_scale_for(bound1), s2 = pow2_scale_for(bound2);
         scales[0] = s1; scales[1] = 1.f / s1; scales[2] = s2; scales[3] = 1.f / s2;
+    }
+}
+
+// Generator backward: dpre_L = (d_yhat . Wout) lrelu', dpre_{i-1} = (dpre_i . W_i) lrelu'; dpre_i is stored as
+// fp16(dpre_i * s_i) with s_i = scales[2i], 1/s_i = scales[2i + 1], i = 0..L.  Bounds: |dpre_L| <= amax max_c sum_o |Wout[o][c]|,
+// |dpre_{i-1}| <= bound_i max_c sum_j |W_i[j][c]|.  One CTA of 256 threads.
+__global__ void __launch_bounds__(256) gen_bwd_scales_kernel(const float* __restrict__ amax, const float* __restrict__ wout, int n_out,
+                                                             const float* __restrict__ wh, int L, int H, float* __restrict__ scales) {
+    __shared__ float red[8];
+    __shared__ float s_bound;
+    const int tid = threadIdx.x;
+    for (int layer = L; layer >= 0; --layer) {
+        // layer == L: column abs-sums of Wout (n_out x H); else of W_{layer+1} = wh[layer] (H x H)
+        const float* w = layer == L ? wout : wh + (long long)layer * H * H;
+        const int rows = layer == L ? n_out : H;
+        float m = 0.f;
+        for (int c = tid; c < H; c += blockDim.x) {
+            float a = 0.f;
+            for (int j = 0; j < rows; ++j) a += fabsf(w[(long long)j * H + c]);
+            m = fmaxf(m, a);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            float mm = 0.f;
+            for (int w8 = 0; w8 < 8; ++w8) mm = fmaxf(mm, red[w8]);
+            const float bound = (layer == L ? amax[0] : s_bound) * mm;
+            s_bound = bound;
+            const float sc = pow2_scale_for(bound);
+            scales[2 * layer] = sc;
+            scales[2 * layer + 1] = 1.f / sc;
+        }
+        __syncthreads();
     }
 }
 

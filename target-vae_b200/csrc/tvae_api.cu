@@ -494,20 +494,21 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     const int H = s->H, E = s->E;
     const CoordXform cx = make_xform(s, a);
     ++g_launch_count; latent_bias_kernel<<<cdiv(s->B * H, 256), 256, 0, st>>>(a->z, a->wz, a->zb, s->B, H, s->zdim);
-    float* w1r = a->w_tf32;                              // [H][E]
-    float* whr = a->w_tf32 + (long long)H * (E > 0 ? E : 2);   // [L][H][H]
-    if (s->L > 0) { ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whr, (long long)s->L * H * H); }
-    float* a0 = a->acts;
+    __half* w1h = static_cast<__half*>(a->w_h);                                    // [H][E]
+    __half* whh = static_cast<__half*>(a->w_h) + (long long)H * (E > 0 ? E : 2);   // [L][H][H]
+    __half* acts = static_cast<__half*>(a->acts);
+    if (s->L > 0) { ++g_launch_count; to_half_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whh, (long long)s->L * H * H); }
+    __half* a0 = acts;
     if (E > 0) {
-        ++g_launch_count; round_tf32_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1r, (long long)H * E);
+        ++g_launch_count; to_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1h, (long long)H * E);
         GenL1FwdParams p{};
         const bool wide = H > 128;
         const int BN = wide ? 256 : 128;
-        if ((rc = make_tmap_2d(&p.tmB, w1r, H, E, E, BN))) return rc;
+        if ((rc = make_tmap_2d_h(&p.tmB, w1h, H, E, E, BN))) return rc;
         p.cx = cx; p.wf_scaled = a->wf_scaled; p.bf = a->bf; p.E = E; p.H = H;
         p.bias = a->b1; p.zb = a->zb; p.h1 = a0;
         p.tiles_n = cdiv(H, BN);
-        p.k_chunks = cdiv(E, kBK);
+        p.k_chunks = cdiv(E, kBKh);
         p.num_tiles = cdiv(M, kBM) * p.tiles_n;
         const int extra = E * 16;
         rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
@@ -525,12 +526,13 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->y_hat, 0, sizeof(float) * M * s->n_out, st));
     for (int i = 1; i <= s->L; ++i) {
         LinearNTArgs l{};
-        l.A = a->acts + (long long)(i - 1) * M * H; l.lda = H;
-        l.B = whr + (long long)(i - 1) * H * H; l.ldb = H;
+        l.f16 = 1;
+        l.A = acts + (long long)(i - 1) * M * H; l.lda = H;
+        l.B = whh + (long long)(i - 1) * H * H; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
-        l.C = a->acts + (long long)i * M * H; l.ldc = H;
+        l.C16 = acts + (long long)i * M * H; l.ldc16 = H;
         l.bias = a->bh + (long long)(i - 1) * H;
-        l.act = 1; l.round_tf32 = 1;
+        l.act = 1;
         if (i == s->L) { l.proj_w = a->wout; l.proj_bias = a->bout; l.proj_out = a->y_hat; l.n_proj = s->n_out; }
         if ((rc = linear_nt(l, st))) return rc;
     }
@@ -544,6 +546,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     const long long M = (long long)s->B * s->N;
     const int H = s->H, E = s->E, L = s->L;
     const CoordXform cx = make_xform(s, &a->f);
+    const __half* acts = static_cast<const __half*>(a->f.acts);
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwout, 0, sizeof(float) * s->n_out * H, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbout, 0, sizeof(float) * s->n_out, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->db1, 0, sizeof(float) * H, st));
@@ -553,35 +556,41 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwh, 0, sizeof(float) * L * H * H, st));
         TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbh, 0, sizeof(float) * L * H, st));
     }
-    float* dcur = a->dpre0;
-    float* dnext = a->dpre1;
+    // ---- power-of-two scales s_i of the fp16 gradient tensors dpre_i (i = L .. 0): scales[2i] = s_i, scales[2i+1] = 1/s_i
+    TVAE_CHECK_CUDA(cudaMemsetAsync(a->scales, 0, sizeof(float) * 32, st));
+    ++g_launch_count; absmax_kernel<<<blocks_for(M * s->n_out, 256), 256, 0, st>>>(a->d_yhat, M * s->n_out, a->scales + 31);
+    ++g_launch_count; gen_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 31, a->f.wout, s->n_out, a->f.wh, L, H, a->scales);
+    __half* dcur = static_cast<__half*>(a->dpre0);
+    __half* dnext = static_cast<__half*>(a->dpre1);
+    __half* wt_h = static_cast<__half*>(a->wt_h);
     // ---- output layer backward -> dpre of the last hidden activation
     {
         ThinBwdParams p{};
-        p.a = a->f.acts + (long long)L * M * H; p.dt = a->d_yhat; p.Wt = a->f.wout; p.dpre = dcur;
+        p.a = acts + (long long)L * M * H; p.dt = a->d_yhat; p.Wt = a->f.wout; p.dpre = dcur;
+        p.store_scale = a->scales + 2 * L;
         p.dWt = a->dwout; p.dbt = a->dbout; p.dcol = (L > 0) ? a->dbh + (long long)(L - 1) * H : nullptr;
         p.M = M; p.W = H; p.T = s->n_out; p.P = 1; p.dt_outer = s->n_out; p.dt_chan = 1;
-        if ((rc = launch_thin_bwd<4, 4, false>(p, 1, st))) return rc;
+        if ((rc = launch_thin_bwd<4, 4, false, true>(p, 1, st))) return rc;
     }
     // ---- hidden layers, last to first
     for (int i = L; i >= 1; --i) {
-        const float* a_prev = a->f.acts + (long long)(i - 1) * M * H;
+        const __half* a_prev = acts + (long long)(i - 1) * M * H;
         const float* w = a->f.wh + (long long)(i - 1) * H * H;
-        if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st))) return rc;
-        ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, a->wt_tf32, H, H, 1);
+        if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st, 1,
+                            a->scales + 2 * i + 1))) return rc;
+        ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, wt_h, H, H);
         LinearNTArgs l{};
-        l.A = dcur; l.lda = H; l.B = a->wt_tf32; l.ldb = H;
+        l.f16 = 1;
+        l.A = dcur; l.lda = H; l.B = wt_h; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
-        l.C = dnext; l.ldc = H; l.aux = a_prev; l.ld_aux = H;
+        l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H;
+        l.acc_scale = a->scales + 2 * i + 1; l.store_scale = a->scales + 2 * (i - 1);
+        if (i - 1 >= 1) { l.colsum = a->dbh + (long long)(i - 2) * H; l.colsum_stride = 1; }   // bias gradient of hidden layer i-1
         if ((rc = linear_nt(l, st))) return rc;
-        float* t = dcur; dcur = dnext; dnext = t;
-        if (i - 1 >= 1) {
-            ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(M, 2048), 1), H, 0, st>>>(dcur, nullptr, a->dbh + (long long)(i - 2) * H, static_cast<int>(M), H, 2048);
-            TVAE_CHECK_CUDA(cudaGetLastError());
-        }
+        __half* t = dcur; dcur = dnext; dnext = t;
     }
-    // ---- dcur == dpre of layer 1: bias / latent-bias gradients
-    ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->dzb, a->db1, s->N, H, 512);
+    // ---- dcur == dpre of layer 1 (scaled by s_0): bias / latent-bias gradients
+    ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512);
     ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
     TVAE_CHECK_CUDA(cudaGetLastError());
     // ---- layer 1 weight and coordinate gradients
@@ -590,27 +599,29 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
             GenL1WgradParams p{};
             const bool wide = H > 128;
             const int BN = wide ? 256 : 128;
-            if ((rc = make_tmap_2d(&p.tmQ, dcur, M, H, H, kBK, true))) return rc;
+            if ((rc = make_tmap_2d_mn_h(&p.tmQ, dcur, M, H, H, kBKh))) return rc;
             p.cx = cx; p.wf_scaled = a->f.wf_scaled; p.bf = a->f.bf; p.E = E; p.H = H; p.dW1 = a->dw1;
+            p.acc_scale = a->scales + 1;
             p.tiles_m = cdiv(E, kBM);
             p.tiles_n = cdiv(H, BN);
             const int extra = E * 16;
             const int out_tiles = p.tiles_m * p.tiles_n;
-            rc = wide ? launch_split_tn<GenL1Wgrad<256>>(p, out_tiles, cdiv(M, kBK), 1, extra, st)
-                      : launch_split_tn<GenL1Wgrad<128>>(p, out_tiles, cdiv(M, kBK), 1, extra, st);
+            rc = wide ? launch_split_tn<GenL1Wgrad<256>>(p, out_tiles, cdiv(M, kBKh), 1, extra, st)
+                      : launch_split_tn<GenL1Wgrad<128>>(p, out_tiles, cdiv(M, kBKh), 1, extra, st);
             if (rc) return rc;
         }
         {
             TVAE_CHECK_CUDA(cudaMemsetAsync(a->dxp, 0, sizeof(float) * M * 2, st));
-            ++g_launch_count; transpose_round_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->f.w1, a->wt_tf32, H, E, 1);   // -> [E][H]
+            ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->f.w1, wt_h, H, E);   // -> [E][H]
             GenL1DgradParams p{};
             const bool wide = E > 128;
             const int BN = wide ? 256 : 128;
-            if ((rc = make_tmap_2d(&p.tmA, dcur, M, H, H, kBM))) return rc;
-            if ((rc = make_tmap_2d(&p.tmB, a->wt_tf32, E, H, H, BN))) return rc;
+            if ((rc = make_tmap_2d_h(&p.tmA, dcur, M, H, H, kBM))) return rc;
+            if ((rc = make_tmap_2d_h(&p.tmB, wt_h, E, H, H, BN))) return rc;
             p.cx = cx; p.wf_scaled = a->f.wf_scaled; p.bf = a->f.bf; p.E = E; p.H = H; p.dxp = a->dxp;
+            p.acc_scale = a->scales + 1;
             p.tiles_n = cdiv(E, BN);
-            p.k_chunks = cdiv(H, kBK);
+            p.k_chunks = cdiv(H, kBKh);
             p.num_tiles = cdiv(M, kBM) * p.tiles_n;
             const int extra = E * 16;
             rc = wide ? launch_gemm<GenL1Dgrad<256>>(p, extra, st) : launch_gemm<GenL1Dgrad<128>>(p, extra, st);
@@ -621,7 +632,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         long long rows = (M + 148LL * 8 - 1) / (148LL * 8);
         rows = (rows + kCoordRB - 1) / kCoordRB * kCoordRB;
         const size_t sm = sizeof(float) * (4 * kCoordRB + 2 * H);
-        ++g_launch_count; coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->dw1, a->dxp, H, static_cast<int>(rows));
+        ++g_launch_count; coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp, H, static_cast<int>(rows));
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (a->f.theta && a->d_theta) {

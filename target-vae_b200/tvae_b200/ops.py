@@ -47,12 +47,12 @@ class GenShape(Structure):
 
 class GenFwdArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ("x", "theta", "dx", "z", "wf_scaled", "bf", "w1", "b1", "wz", "wh", "bh",
-                                         "wout", "bout", "zb", "acts", "y_hat", "w_tf32")]
+                                         "wout", "bout", "zb", "acts", "y_hat", "w_h")]
 
 
 class GenBwdArgs(Structure):
     _fields_ = [("f", GenFwdArgs)] + [(n, c_void_p) for n in (
-        "d_yhat", "dpre0", "dpre1", "wt_tf32", "dxp", "dzb", "dw1", "db1", "dwz", "dwh", "dbh", "dwout", "dbout",
+        "d_yhat", "dpre0", "dpre1", "wt_h", "scales", "dxp", "dzb", "dw1", "db1", "dwz", "dwh", "dbh", "dwout", "dbout",
         "d_theta", "d_dx", "d_z")]
 
 
@@ -285,22 +285,22 @@ def gen_shape(B, N, gw: GenWeights, zdim) -> GenShape:
     return GenShape(B, N, gw.E, gw.H, gw.L, gw.wout.shape[0], zdim)
 
 
-def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_tf32):
+def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_h):
     return _set(GenFwdArgs(), x=f32(x), theta=None if theta is None else f32(theta), dx=None if dx is None else f32(dx),
                 z=f32(z), wf_scaled=gw.wf_scaled, bf=gw.bf, w1=gw.w1, b1=gw.b1, wz=gw.wz, wh=gw.wh, bh=gw.bh,
-                wout=gw.wout, bout=gw.bout, zb=zb, acts=acts, y_hat=y_hat, w_tf32=w_tf32)
+                wout=gw.wout, bout=gw.bout, zb=zb, acts=acts, y_hat=y_hat, w_h=w_h)
 
 
 def generator_fwd(s: GenShape, gw: GenWeights, x, theta, dx, z):
     dev = z.device
     M = s.B * s.N
     zb = empty(s.B, s.H, device=dev)
-    acts = empty(s.L + 1, M, s.H, device=dev)
+    acts = half(s.L + 1, M, s.H, device=dev)        # fp16 activations: the MMA operand format, half the HBM traffic
     y_hat = empty(M, s.n_out, device=dev)
-    w_tf32 = empty(s.H * max(s.E, 2) + s.L * s.H * s.H, device=dev)
-    a = _gen_fwd_args(s, gw, x, theta, dx, z, zb, acts, y_hat, w_tf32)
+    w_h = half(s.H * max(s.E, 2) + s.L * s.H * s.H, device=dev)
+    a = _gen_fwd_args(s, gw, x, theta, dx, z, zb, acts, y_hat, w_h)
     check(L().tvae_generator_fwd(byref(s), byref(a), stream_ptr()), "tvae_generator_fwd")
-    return y_hat, dict(zb=zb, acts=acts, w_tf32=w_tf32)
+    return y_hat, dict(zb=zb, acts=acts, w_h=w_h)
 
 
 def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_yhat):
@@ -311,10 +311,10 @@ def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_
                dwh=empty(max(Lh, 1), H, H, device=dev), dbh=empty(max(Lh, 1), H, device=dev),
                dwout=empty(s.n_out, H, device=dev), dbout=empty(s.n_out, device=dev),
                d_theta=empty(s.B, device=dev), d_dx=empty(s.B, 2, device=dev), d_z=empty(s.B, s.zdim, device=dev))
-    scratch = dict(dpre0=empty(M, H, device=dev), dpre1=empty(M, H, device=dev),
-                   wt_tf32=empty(max(E * H, H * H), device=dev), dxp=empty(M, 2, device=dev), dzb=empty(s.B, H, device=dev))
+    scratch = dict(dpre0=half(M, H, device=dev), dpre1=half(M, H, device=dev), wt_h=half(max(E * H, H * H), device=dev),
+                   scales=empty(32, device=dev), dxp=empty(M, 2, device=dev), dzb=empty(s.B, H, device=dev))
     a = GenBwdArgs()
-    a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_tf32"])
+    a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_h"])
     _set(a, d_yhat=f32(d_yhat), **scratch, **out)
     if theta is None:
         a.d_theta = None
@@ -353,7 +353,7 @@ def launch_count() -> int:
 
 
 # kernels (names of tvae_profile_collect) whose MMAs run with 16-bit operands (kind::f16); the rest are kind::tf32
-F16_KERNELS: set = {"conv1_fwd", "conv1_wgrad"}
+F16_KERNELS: set = {"conv1_fwd", "conv1_wgrad", "conv2_heads", "gen_l1_fwd", "gen_l1_wgrad", "gen_l1_dgrad", "linear_nt", "linear_tn"}
 
 
 def conv1_executed_fraction(s: EncShape, wgrad: bool) -> float:
