@@ -9,7 +9,7 @@
  *   - every pointer is a DEVICE pointer to contiguous fp32 data unless noted; `stream` is a cudaStream_t
  *   - calls never allocate, never synchronise, and are re-entrant; all scratch is passed in by the caller
  *   - return 0 on success, < 0 on error; tvae_last_error() returns the thread-local message
- *   - "tf32" tensors hold fp32 values already rounded to TF32 (10-bit mantissa); fp16 / bf16 tensors are void*
+ *   - fp16 tensors (MMA operands, stored activations, scaled gradients) are passed as void*
  *
  * Precision: every dense contraction runs on the tensor cores with FP16 operands and FP32 accumulation
  * (tcgen05.mma.kind::f16).  An fp16 operand has the 11-bit significand of a TF32 one (the precision the reference's
@@ -190,9 +190,10 @@ int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat,
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
                   float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream);
 
-/* ------------------------------------------------------------------ test hooks for the GEMM core */
-int tvae_test_linear_nt(const float* A, const float* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);
-int tvae_test_linear_tn(const float* P, const float* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream);
+/* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
+ * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
+int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);
+int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream);
 
 #ifdef __cplusplus
 }

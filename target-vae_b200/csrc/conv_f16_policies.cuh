@@ -1,5 +1,5 @@
 // FP16-operand CTA-pair group-convolution policies for tc_gemm2_kernel (a-2, models.py:202-225, and its weight
-// gradient).  Same implicit GEMMs as the TF32 formulation they replace, with 16-bit operands:
+// gradient) as implicit GEMMs with fp16 operands:
 //
 //   Conv1FwdH   : X1[(b,pos), (r,o)] = lrelu(im2col . bank^T + bias)     A = im2col tile (K-major, generated), B = bank (TMA)
 //   Conv1WgradH : dbank[(r,o), kk]  += sum_(b,pos) dX1[(b,r,pos), o] im2col[(b,pos), kk]

@@ -46,45 +46,6 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major tensor [rows][cols] (leading dimension ld elements), box = {32 cols, box_rows},
-// 128-byte swizzle (16 B chunks for K-major operands; 32 B chunks when `mn_major`, the layout the tensor
-// core requires for MN-major tf32), out-of-bounds elements read as zero.
-inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                        bool mn_major = false) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15)) return fail(-1, "TMA operand must be 16-byte aligned with 16-byte row pitch");
-    if (box_rows == 0 || box_rows > 256) return fail(-1, "TMA box rows out of range");
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {32, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
-    return 0;
-}
-
-// MN-major operand view of a row-major fp32 matrix [rows][cols] (cols % 32 == 0): 3-D map {32 cols, rows, cols/32
-// column blocks} with boxes {32, box_rows, nb}: one TMA fills nb consecutive [box_rows][32] column blocks, each in the
-// 32-byte-atom 128 B swizzle the tensor core needs for MN-major tf32.
-inline int make_tmap_3d_mn(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t nb) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15) || (cols & 31)) return fail(-1, "TMA operand must be 16-byte aligned with whole 32-column blocks");
-    cuuint64_t dims[3] = {32, rows, cols / 32};
-    cuuint64_t strides[2] = {ld * sizeof(float), 32 * sizeof(float)};
-    cuuint32_t box[3] = {32, box_rows, nb};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string(static_cast<int>(r)));
-    return 0;
-}
-
 // 2-D 16-bit (fp16 / bf16 bit patterns) row-major tensor [rows][cols], K-major operand boxes {64 cols, box_rows}, 128 B swizzle.
 inline int make_tmap_2d_h(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = get_encode_fn();

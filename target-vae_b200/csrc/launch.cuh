@@ -66,17 +66,16 @@ inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t s
     return 0;
 }
 
-// C[M,N] = epi(A[M,K] B[N,K]^T); A, B row-major with leading dims lda, ldb (elements).
+// C[M,N] = epi(A[M,K] B[N,K]^T); A, B fp16 row-major with leading dims lda, ldb (elements).
 struct LinearNTArgs {
-    const void* A; long long lda;      // fp32 (tf32 MMA) or, with f16 = 1, fp16
-    const void* B; long long ldb;
-    int f16 = 0;
+    const void* A; long long lda;      // fp16
+    const void* B; long long ldb;      // fp16
     int M, N, K;
     float* C = nullptr; long long ldc = 0;
     const float* bias = nullptr;
     const float* row_bias = nullptr; int rows_per_group = 1; long long ld_rb = 0;
-    const float* aux = nullptr; long long ld_aux = 0;
-    int act = 0, round_tf32 = 0;
+    long long ld_aux = 0;
+    int act = 0;
     const float* proj_w = nullptr; const float* proj_bias = nullptr; float* proj_out = nullptr; int n_proj = 0;
     void* C16 = nullptr; long long ldc16 = 0;
     const void* aux16 = nullptr;
@@ -92,51 +91,37 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     const bool wide = a.N > 128;
     const int BN = wide ? 256 : 128;
     int rc;
-    if (a.f16) {
-        if ((rc = make_tmap_2d_h(&p.tmA, a.A, a.M, a.K, a.lda, kBM))) return rc;
-        if ((rc = make_tmap_2d_h(&p.tmB, a.B, a.N, a.K, a.ldb, BN))) return rc;
-    } else {
-        if ((rc = make_tmap_2d(&p.tmA, static_cast<const float*>(a.A), a.M, a.K, a.lda, kBM))) return rc;
-        if ((rc = make_tmap_2d(&p.tmB, static_cast<const float*>(a.B), a.N, a.K, a.ldb, BN))) return rc;
-    }
+    if ((rc = make_tmap_2d_h(&p.tmA, a.A, a.M, a.K, a.lda, kBM))) return rc;
+    if ((rc = make_tmap_2d_h(&p.tmB, a.B, a.N, a.K, a.ldb, BN))) return rc;
     p.M = a.M; p.N = a.N;
-    p.k_chunks = cdiv(a.K, a.f16 ? kBKh : kBK);
+    p.k_chunks = cdiv(a.K, kBKh);
     p.tiles_n = cdiv(a.N, BN);
     p.num_tiles = cdiv(a.M, kBM) * p.tiles_n;
     p.C = a.C; p.ldc = a.ldc; p.bias = a.bias;
     p.row_bias = a.row_bias; p.rows_per_group = a.rows_per_group; p.ld_rb = a.ld_rb;
-    p.aux = a.aux; p.ld_aux = a.ld_aux; p.act = a.act; p.round_tf32 = a.round_tf32;
+    p.ld_aux = a.ld_aux; p.act = a.act;
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
     p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
-    if (a.f16)
-        return wide ? launch_gemm<LinearNT<256, true>>(p, LinearNT<256, true>::kExtraBytes, stream)
-                    : launch_gemm<LinearNT<128, true>>(p, LinearNT<128, true>::kExtraBytes, stream);
     return wide ? launch_gemm<LinearNT<256>>(p, LinearNT<256>::kExtraBytes, stream)
                 : launch_gemm<LinearNT<128>>(p, LinearNT<128>::kExtraBytes, stream);
 }
 
-// C[Ma,Nb] (+)= sum_r P[r,Ma] Q[r,Nb]; caller zero-fills C (accumulated with atomics across row splits).
+// C[Ma,Nb] (+)= sum_r P[r,Ma] Q[r,Nb], P and Q fp16; caller zero-fills C (accumulated with atomics across row splits).
 inline int linear_tn(const void* P, long long ldp, const void* Q, long long ldq, int R, int Ma, int Nb,
-                     float* C, long long ldc, int transpose_out, cudaStream_t stream, int f16 = 0,
-                     const float* acc_scale = nullptr) {
+                     float* C, long long ldc, int transpose_out, cudaStream_t stream, const float* acc_scale = nullptr) {
     TVAE_REQUIRE(R > 0 && Ma > 0 && Nb > 0, "linear_tn: empty problem");
     LinearTNParams p{};
     const bool wide = Nb > 128;
     const int BN = wide ? 256 : 128;
     int rc;
-    if (f16) {
-        if ((rc = make_tmap_2d_mn_h(&p.tmP, P, R, Ma, ldp, kBKh))) return rc;
-        if ((rc = make_tmap_2d_mn_h(&p.tmQ, Q, R, Nb, ldq, kBKh))) return rc;
-    } else {
-        if ((rc = make_tmap_2d(&p.tmP, static_cast<const float*>(P), R, Ma, ldp, kBK, true))) return rc;
-        if ((rc = make_tmap_2d(&p.tmQ, static_cast<const float*>(Q), R, Nb, ldq, kBK, true))) return rc;
-    }
+    if ((rc = make_tmap_2d_mn_h(&p.tmP, P, R, Ma, ldp, kBKh))) return rc;
+    if ((rc = make_tmap_2d_mn_h(&p.tmQ, Q, R, Nb, ldq, kBKh))) return rc;
     p.Ma = Ma; p.Nb = Nb;
     p.acc_scale = acc_scale;
     p.tiles_m = cdiv(Ma, kBM);
     p.tiles_n = cdiv(Nb, BN);
-    p.chunks_total = cdiv(R, f16 ? kBKh : kBK);
+    p.chunks_total = cdiv(R, kBKh);
     const int out_tiles = p.tiles_m * p.tiles_n;
     int splits = cdiv(2 * sm_count(), out_tiles);        // ~2 waves of work items
     const int min_chunks = 16;                            // keep >= 512 reduction rows per split
@@ -146,7 +131,6 @@ inline int linear_tn(const void* P, long long ldp, const void* Q, long long ldq,
     p.splits = cdiv(p.chunks_total, p.chunks_per_split);
     p.num_tiles = out_tiles * p.splits;
     p.C = C; p.ldc = ldc; p.transpose_out = transpose_out;
-    if (f16) return wide ? launch_gemm<LinearTN<256, true>>(p, 0, stream) : launch_gemm<LinearTN<128, true>>(p, 0, stream);
     return wide ? launch_gemm<LinearTN<256>>(p, 0, stream) : launch_gemm<LinearTN<128>>(p, 0, stream);
 }
 

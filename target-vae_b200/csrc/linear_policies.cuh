@@ -1,4 +1,4 @@
-// GEMM policies whose operands are both loaded by TMA.
+// GEMM policies whose operands are both loaded by TMA (fp16 operands, kind::f16, fp32 accumulation).
 //   LinearNT<BN>: C[M,N] = epi(A[M,K] * B[N,K]^T)      (forward linear layers, dgrads with pre-transposed weights)
 //   LinearTN<BN>: C[Ma,Nb] += sum_r P[r,Ma] * Q[r,Nb]  (weight gradients; split over r, fp32 atomics)
 #pragma once
@@ -23,17 +23,15 @@ struct LinearNTParams {
     const float* row_bias;    // [M / rows_per_group][ld_rb] or null   (z-conditioned bias)
     int rows_per_group;
     long long ld_rb;
-    const float* aux;         // [M][ld_aux] or null: multiply by lrelu'(aux)
     long long ld_aux;
     int act;                  // 1 = LeakyReLU(0.01)
-    int round_tf32;           // round stored values to tf32 (consumer is another tf32 MMA)
     const float* proj_w;      // [n_proj][N] or null: fused  proj_out[m][o] += sum_n v[m][n] * proj_w[o][n]
     const float* proj_bias;   // [n_proj]
     float* proj_out;          // [M][n_proj], pre-zeroed
     int n_proj;
     void* C16;                // [M][ldc16] fp16 output (value * *store_scale) or null
     long long ldc16;
-    const void* aux16;        // [M][ld_aux] fp16 variant of aux or null
+    const void* aux16;        // [M][ld_aux] fp16 or null: multiply by lrelu'(aux16)
     const float* acc_scale;   // device scalar multiplied into the accumulator first (undoes the operand's scale) or null
     const float* store_scale; // device scalar applied to the fp16 store only (power of two) or null
     float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient; needs tiles_n == 1) or null
@@ -62,12 +60,12 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     return a[0];
 }
 
-template <int BN, bool F16 = false>
+template <int BN>
 struct LinearNT : PolicyBase {
     static constexpr const char* kName = "linear_nt";
     using Params = LinearNTParams;
     static constexpr int kBN = BN;
-    static constexpr bool kF16 = F16;          // fp16 A and B (TMA boxes of 64 k-elements)
+    static constexpr bool kF16 = true;         // fp16 A and B (TMA boxes of 64 k-elements)
     static constexpr int kEpiGroups = 2;       // short K loops: the epilogue is the critical path, two warpgroups alternate tiles
     // extra smem: [N] bias, [4][N] fused-projection weights, then column sums [8 epilogue warps][kMaxN] floats (entry
     // (warp, column) with column % 32 == lane is owned by one thread)
@@ -106,13 +104,8 @@ struct LinearNT : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        if (F16) {
-            tma_kmajor_h(sa, &p.tmA, bar, kc, ti.m0);
-            tma_kmajor_h(sb, &p.tmB, bar, kc, ti.n0);
-        } else {
-            tma_kmajor(sa, &p.tmA, bar, kc, ti.m0);
-            tma_kmajor(sb, &p.tmB, bar, kc, ti.n0);
-        }
+        tma_kmajor_h(sa, &p.tmA, bar, kc, ti.m0);
+        tma_kmajor_h(sb, &p.tmB, bar, kc, ti.n0);
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState& st, uint32_t taddr, int row, uint8_t* extra) {
         const float* s_bias = reinterpret_cast<const float*>(extra);
@@ -157,19 +150,6 @@ struct LinearNT : PolicyBase {
             if (p.act) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j]);
-            }
-            if (p.aux) {
-                const float* ax = p.aux + (long long)m * p.ld_aux + n_base;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (n_base + j < p.N) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(ax + j));
-                        v[j] *= lrelu_grad_from_out(t.x);
-                        v[j + 1] *= lrelu_grad_from_out(t.y);
-                        v[j + 2] *= lrelu_grad_from_out(t.z);
-                        v[j + 3] *= lrelu_grad_from_out(t.w);
-                    }
-                }
             }
             if (p.aux16 && m_ok) {
                 const __half* ax = reinterpret_cast<const __half*>(p.aux16) + (long long)m * p.ld_aux + n_base;
@@ -231,10 +211,7 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (n_base + j < p.N) {
-                        float4 t;
-                        if (p.round_tf32) t = make_float4(to_tf32(v[j]), to_tf32(v[j + 1]), to_tf32(v[j + 2]), to_tf32(v[j + 3]));
-                        else              t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        *reinterpret_cast<float4*>(dst + j) = t;
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 }
             }
@@ -259,12 +236,12 @@ struct LinearTNParams {
     const float* acc_scale;   // device scalar multiplied into the accumulator (undoes the operands' scale) or null
 };
 
-template <int BN, bool F16 = false>
+template <int BN>
 struct LinearTN : PolicyBase {
     static constexpr const char* kName = "linear_tn";
     using Params = LinearTNParams;
     static constexpr int kBN = BN;
-    static constexpr bool kF16 = F16;          // fp16 P and Q, reduction chunks of 64 rows
+    static constexpr bool kF16 = true;         // fp16 P and Q, reduction chunks of 64 rows
     static constexpr bool kAMajorMN = true;
     static constexpr bool kBMajorMN = true;
     __device__ static void prefetch_descs(const Params& p) {
@@ -283,13 +260,8 @@ struct LinearTN : PolicyBase {
     }
     __device__ static constexpr uint32_t tx_bytes() { return kAStageBytes + BN * 128; }
     __device__ static void issue_tma(const Params& p, const TileInfo& ti, int kc, uint32_t sa, uint32_t sb, uint32_t bar) {
-        if (F16) {
-            tma_mnmajor_h(sa, &p.tmP, bar, ti.m0, kc * kBKh, kBM / 32);
-            tma_mnmajor_h(sb, &p.tmQ, bar, ti.n0, kc * kBKh, BN / 32);
-        } else {
-            tma_mnmajor(sa, &p.tmP, bar, ti.m0, kc * kBK, kBM / 32);
-            tma_mnmajor(sb, &p.tmQ, bar, ti.n0, kc * kBK, BN / 32);
-        }
+        tma_mnmajor_h(sa, &p.tmP, bar, ti.m0, kc * kBKh, kBM / 32);
+        tma_mnmajor_h(sb, &p.tmQ, bar, ti.n0, kc * kBKh, BN / 32);
     }
     __device__ static void epilogue(const Params& p, const TileInfo& ti, EpiState&, uint32_t taddr, int row, uint8_t*) {
         const int ma = ti.m0 + row;

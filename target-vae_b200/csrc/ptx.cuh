@@ -94,18 +94,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 operands, FP32 accumulate, single CTA.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same with 16-bit operands (kind::f16; the formats come from the instruction descriptor)
+// D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit operands (formats in the instruction descriptor), FP32 accumulate, single CTA.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -140,11 +129,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (tcgen05).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1
-//   bits [61,64) layout type: 2 = SWIZZLE_128B (16 B chunks, 8-row atoms; K-major tf32 operands)
-//                             1 = SWIZZLE_128B_BASE32B (32 B chunks, 4-row atoms; the only layout the
-//                                 tensor core accepts for MN-major 32-bit operands)
+//   bits [61,64) layout type: 2 = SWIZZLE_128B (16 B chunks XOR row % 8, 8-row atoms of 1024 B)
+//                             4 = SWIZZLE_64B  (16 B chunks XOR (row / 2) % 4, 8-row atoms of 512 B)
 constexpr uint32_t kLayoutSw128 = 2;
-constexpr uint32_t kLayoutSw128Base32 = 1;
+constexpr uint32_t kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
@@ -154,17 +142,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= static_cast<uint64_t>(layout) << 61;
     return d;
 }
-// Instruction descriptor: TF32 x TF32 -> FP32, M = 128, N = n, selectable operand major-ness.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
-    return (1u << 4)                        // c_format = F32
-           | (2u << 7)                      // a_format = TF32
-           | (2u << 10)                     // b_format = TF32
-           | ((a_mn_major ? 1u : 0u) << 15) // a_major
-           | ((b_mn_major ? 1u : 0u) << 16) // b_major
-           | (static_cast<uint32_t>(N >> 3) << 17)
-           | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
 // kind::f16 instruction descriptor: 16-bit operands (format 0 = FP16, 1 = BF16, chosen per operand) -> FP32.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major, uint32_t a_fmt, uint32_t b_fmt) {
     return (1u << 4)                        // c_format = F32
@@ -175,26 +152,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_ma
            | (static_cast<uint32_t>(N >> 3) << 17)
            | (static_cast<uint32_t>(M >> 4) << 24);
 }
-// Layout types for 16-bit operands: K-major and MN-major 128 B swizzle (64-element rows, 8-row atoms) and the
-// 64 B swizzle (32-element rows) used for MN-major operands whose contiguous extent is only 32 elements.
-constexpr uint32_t kLayoutSw64 = 4;
-
-// fp32 -> tf32 (round to nearest, ties away), result kept in an fp32 container
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
 // byte offset of 16-byte chunk `chunk` (0..7) of 128-byte row `row` inside a 128B-swizzled tile
 // whose base is 1024-byte aligned (Swizzle<3,4,3>: chunk index XOR (row mod 8)).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
     return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }
-// same for the 32-byte-atom flavour (Swizzle<2,5,2>): 32 B chunk index (0..3) XOR (row mod 4); `chunk` is
-// still the 16 B chunk index 0..7.
-__device__ __forceinline__ uint32_t sw128b32_offset(uint32_t row, uint32_t chunk) {
-    return row * 128u + ((((chunk >> 1) ^ (row & 3u)) << 5) | ((chunk & 1u) << 4));
-}
-
 }  // namespace tvae

@@ -189,10 +189,6 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(const __half* __restrict_
     }
 }
 
-__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = to_tf32(in[i]);
-}
-
 // dbias[o] = sum_r dbank[(r*O + o)][K]
 __global__ void bank_bias_grad_kernel(const float* __restrict__ dbank, float* __restrict__ dbias, int O, int G, int kpad, int K) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;

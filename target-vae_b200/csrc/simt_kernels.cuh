@@ -91,17 +91,6 @@ __global__ void filter_bank_bwd_kernel(const float* __restrict__ dbank, long lon
     }
 }
 
-// out[c][r] = round_tf32(in[r][c]) : small weight transposes for dgrad GEMMs
-__global__ void transpose_round_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int do_round) {
-    const long long total = (long long)rows * cols;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = static_cast<int>(idx % cols);
-        const int r = static_cast<int>(idx / cols);
-        const float v = in[idx];
-        out[(long long)c * rows + r] = do_round ? to_tf32(v) : v;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // block-wide reductions (blockDim.x multiple of 32, <= 1024)
 // ------------------------------------------------------------------------------------------

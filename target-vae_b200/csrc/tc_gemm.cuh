@@ -1,10 +1,10 @@
-// Warp-specialised persistent TF32 GEMM core for sm_100a (tcgen05 + TMEM + TMA).
+// Warp-specialised persistent FP16 GEMM core for sm_100a (tcgen05.mma.kind::f16 + TMEM + TMA).
 //
-//   D[128 x BN] (fp32, TMEM) += A[128 x K] * B[BN x K]^T
+//   D[128 x BN] (fp32, TMEM) += A[128 x K] * B[BN x K]^T        (A, B fp16: the 11-bit significand of TF32 at twice its rate)
 //
 // One CTA per SM.  Warp roles:
 //   warp 0      TMA producer (one lane): bulk-tensor loads into a ring of smem stages
-//   warp 1      MMA issuer   (one lane): tcgen05.mma.kind::tf32 on swizzled smem descriptors
+//   warp 1      MMA issuer   (one lane): tcgen05.mma.kind::f16 on swizzled smem descriptors
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld accumulator rows -> registers -> policy epilogue; policies whose epilogue
 //               is the bottleneck (streaming GEMMs with a short K loop) run P::kEpiGroups = 2 such warpgroups that
@@ -14,11 +14,10 @@
 // Three pipelines: smem full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
 // and a static contiguous tile schedule per CTA.
 //
-// Operand layouts in smem (128-byte swizzle, tf32 = 4 bytes, 32 elements per swizzle row):
-//   K-major  operand: [rows][32 k]           8-row atoms of 1024 B, SBO = 1024, K step = +32 B
-//   MN-major operand: [col-block][k rows][32 mn] per 32-wide block of the M/N extent, in the
-//                     32-byte-atom flavour of the 128 B swizzle (4-row atoms of 512 B):
-//                     LBO = block stride (k_rows*128 B), SBO = 512, K step (8 rows) = +1024 B
+// Operand layouts in smem (fp16 = 2 bytes; a stage covers kBKh = 64 reduction elements, one MMA consumes 16):
+//   K-major  operand: [rows][64 k] in the 128 B swizzle, 8-row atoms of 1024 B, SBO = 1024, K step = +32 B
+//   MN-major operand: [col-block][64 k rows][32 mn] per 32-wide block of the M/N extent in the 64 B swizzle
+//                     (8-row atoms of 512 B): LBO = block stride (4096 B), SBO = 512, K step (16 rows) = +1024 B
 // A policy `P` supplies tile geometry, TMA issue, optional generator and the epilogue.
 #pragma once
 #include "ptx.cuh"
@@ -26,8 +25,8 @@
 namespace tvae {
 
 constexpr int kBM = 128;        // accumulator rows (TMEM lanes)
-constexpr int kBK = 32;         // tf32 elements per smem stage along the reduction (one 128 B swizzle row)
-constexpr int kUmmaK = 8;       // tf32 elements per tcgen05.mma
+constexpr int kBKh = 64;        // fp16 elements per smem stage along the reduction (one 128 B swizzle row)
+constexpr int kKSteps = 4;      // tcgen05.mma per stage (16 fp16 reduction elements each)
 constexpr int kAStageBytes = kBM * 128;
 constexpr int kCtrlWarps = 4;
 constexpr int kEpiWarps = 4;
@@ -38,7 +37,7 @@ constexpr int kMaxStages = 8;
 struct TileInfo {
     int m0;        // first accumulator row in the policy's row space
     int n0;        // first accumulator column
-    int kc_begin;  // reduction chunks [kc_begin, kc_end) of kBK elements each
+    int kc_begin;  // reduction chunks [kc_begin, kc_end) of kBKh elements each
     int kc_end;
     int a0, a1, a2;  // policy scratch (image index, split index, ...)
 };
@@ -67,10 +66,7 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
     constexpr int kAccStages = (512 / kBN) > 4 ? 4 : (512 / kBN);
     constexpr int kTmemCols = 512;
     constexpr int kBStageBytes = kBN * 128;
-    // 16-bit policies (P::kF16): kind::f16, a 128-byte stage row holds 64 reduction elements, one MMA consumes 16;
-    // MN-major 16-bit operands are stored as 32-element blocks [64 k rows][64 B] in the 64 B swizzle.
-    constexpr uint32_t kIdesc = P::kF16 ? make_idesc_f16(kBM, kBN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt)
-                                        : make_idesc_tf32(kBM, kBN, P::kAMajorMN, P::kBMajorMN);
+    constexpr uint32_t kIdesc = make_idesc_f16(kBM, kBN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt);
     static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "invalid UMMA N");
     constexpr int kEpiGroups = P::kEpiGroups;
     constexpr int kFirstGenWarp = kFirstEpiWarp + kEpiWarps * kEpiGroups;
@@ -158,21 +154,13 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
                     const uint32_t a_addr = smem_u32(smem_a + stage * kAStageBytes);
                     const uint32_t b_addr = smem_u32(smem_b + stage * kBStageBytes);
 #pragma unroll
-                    for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+                    for (int ks = 0; ks < kKSteps; ++ks) {
                         uint64_t adesc, bdesc;
-                        if (P::kF16) {
-                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, 64 * 64, 512, kLayoutSw64);
-                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                            if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, 64 * 64, 512, kLayoutSw64);
-                            else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
-                            umma_f16(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
-                        } else {
-                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                            if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                            else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
-                            umma_tf32(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
-                        }
+                        if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBKh * 64, 512, kLayoutSw64);
+                        else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                        if (P::kBMajorMN) bdesc = make_smem_desc(b_addr + ks * 1024, kBKh * 64, 512, kLayoutSw64);
+                        else              bdesc = make_smem_desc(b_addr + ks * 32, 16, 1024, kLayoutSw128);
+                        umma_f16(d_tmem, adesc, bdesc, kIdesc, (kc > ti.kc_begin || ks > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -238,8 +226,7 @@ struct PolicyBase {
     static constexpr bool kAGen = false;
     static constexpr int kProdWarps = 0;
     static constexpr int kEpiGroups = 1;      // tc_gemm: epilogue warpgroups taking alternate tiles
-    static constexpr bool kF16 = false;       // 16-bit operands (kind::f16)
-    static constexpr uint32_t kAFmt = 0;      // 0 = FP16, 1 = BF16
+    static constexpr uint32_t kAFmt = 0;      // operand formats of kind::f16: 0 = FP16, 1 = BF16 (both operands must agree)
     static constexpr uint32_t kBFmt = 0;
     struct EpiState {};
     struct GenState {};
@@ -257,24 +244,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // Issue helpers shared by the policies -----------------------------------------------------------
-// K-major operand tile: `rows` rows x 32 k-elements at (k = kc*32, row = r0): one box.
-__device__ __forceinline__ void tma_kmajor(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int kc, int r0) {
-    tma_load_2d(dst, tm, bar, kc * kBK, r0);
-}
-// 16-bit K-major operand tile: `rows` rows x 64 k-elements at (k = kc*64, row = r0): one box.
-constexpr int kBKh = 64;
+// K-major operand tile: `rows` rows x 64 k-elements at (k = kc*64, row = r0): one box.
 __device__ __forceinline__ void tma_kmajor_h(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int kc, int r0) {
     tma_load_2d(dst, tm, bar, kc * kBKh, r0);
 }
-// 16-bit MN-major operand tile: 64 reduction rows x (32*nblk) features starting at feature f0, rows r0..: one
+// MN-major operand tile: 64 reduction rows x (32*nblk) features starting at feature f0, rows r0..: one
 // {32 feat x 64 rows} box (64 B swizzle) per 32-wide feature block.
 __device__ __forceinline__ void tma_mnmajor_h(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int f0, int r0, int nblk) {
     for (int b = 0; b < nblk; ++b) tma_load_2d(dst + b * (kBKh * 64), tm, bar, f0 + 32 * b, r0);
 }
-// MN-major operand tile: kBK reduction rows x (32*nblk) features starting at feature f0, rows r0..:
-// one {32 feat x kBK rows} box per 32-wide feature block.
-__device__ __forceinline__ void tma_mnmajor(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int f0, int r0, int nblk) {
-    for (int b = 0; b < nblk; ++b) tma_load_2d(dst + b * (kBK * 128), tm, bar, f0 + 32 * b, r0);
-}
-
 }  // namespace tvae

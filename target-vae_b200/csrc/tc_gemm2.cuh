@@ -1,4 +1,4 @@
-// CTA-pair (cta_group::2) persistent TF32 GEMM core for the group convolution and its weight gradient.
+// CTA-pair (cta_group::2) persistent FP16 GEMM core for the group convolution and its weight gradient.
 //
 //   D[256 x 512] (fp32, TMEM of both CTAs) += A[256 x K] * B[512 x K]^T        per pair-tile
 //
@@ -10,7 +10,7 @@
 //
 // Warp roles in BOTH CTAs (512 threads):
 //   warp 0      TMA producer: this CTA's half of the B tile, complete_tx on the LEADER's full barrier
-//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, M = 256, N = 256
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M = 256, N = 256
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, same warp in both CTAs)
 //   warps 4-7   epilogue: tcgen05.ld of this CTA's 128 accumulator rows -> policy epilogue
 //   warps 8-15  operand generators: synthesise this CTA's 128 A rows straight into swizzled smem (two groups
@@ -69,16 +69,6 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -122,9 +112,8 @@ template <class P>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // 16-bit policies (P::kF16): kind::f16, a stage row of 128 B holds 64 reduction elements, one MMA consumes 16.
-    constexpr uint32_t kIdesc = P::kF16 ? make_idesc_f16(256, kAccN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt)
-                                        : make_idesc_tf32(256, kAccN, P::kAMajorMN, P::kBMajorMN);
+    // kind::f16: a stage row of 128 B holds 64 reduction elements, one MMA consumes 16.
+    constexpr uint32_t kIdesc = make_idesc_f16(256, kAccN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt);
 
     const int stages = prm.num_stages;
     const Smem2Layout L = make_smem2_layout(stages, 0);
@@ -209,24 +198,16 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                     const uint32_t b_addr = a_addr + kAStageBytes;
                     for (int a = 0; a < ti.n_acc; ++a) {
 #pragma unroll
-                        for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+                        for (int ks = 0; ks < kKSteps; ++ks) {
+                            // MN-major: generated A in 64-element blocks [64 k][128 B] (128 B swizzle), TMA-loaded B in
+                            // 32-element blocks [64 k][64 B] (64 B swizzle); 16 k rows per MMA
                             uint64_t adesc, bdesc;
                             const uint32_t bb = b_addr + a * kBHalfBytes;
-                            if (P::kF16) {
-                                // MN-major 16-bit: A in 64-element blocks [64 k][128 B] (128 B swizzle), B in
-                                // 32-element blocks [64 k][64 B] (64 B swizzle); 16 k rows per MMA
-                                if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 2048, 64 * 128, 1024, kLayoutSw128);
-                                else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                                if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, 64 * 64, 512, kLayoutSw64);
-                                else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
-                                umma_f16_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
-                            } else {
-                                if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                                else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                                if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, kBK * 128, 512, kLayoutSw128Base32);
-                                else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
-                                umma_tf32_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
-                            }
+                            if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 2048, 64 * 128, 1024, kLayoutSw128);
+                            else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
+                            if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, 64 * 64, 512, kLayoutSw64);
+                            else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
+                            umma_f16_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit_pair(empty_bar + 8 * stage, 3);   // frees the slot in both CTAs

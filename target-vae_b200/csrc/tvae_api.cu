@@ -383,12 +383,11 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         if (rc) return rc;
     }
     // ---- dW2 = dhpre^T x1   (fp16 x fp16, accumulators carry s1)
-    if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st, 1, a->scales + 1))) return rc;
+    if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st, a->scales + 1))) return rc;
     // ---- dx1pre = (dhpre W2) * lrelu'(x1), stored fp16 * s2; its column sums are the conv1 bias gradient
     ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
     {
         LinearNTArgs l{};
-        l.f16 = 1;
         l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_h; l.ldb = g.O;
         l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
         l.C = nullptr; l.C16 = a->dx1_16; l.ldc16 = g.O; l.aux16 = a->x1; l.ld_aux = g.O;
@@ -526,7 +525,6 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->y_hat, 0, sizeof(float) * M * s->n_out, st));
     for (int i = 1; i <= s->L; ++i) {
         LinearNTArgs l{};
-        l.f16 = 1;
         l.A = acts + (long long)(i - 1) * M * H; l.lda = H;
         l.B = whh + (long long)(i - 1) * H * H; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
@@ -576,11 +574,10 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     for (int i = L; i >= 1; --i) {
         const __half* a_prev = acts + (long long)(i - 1) * M * H;
         const float* w = a->f.wh + (long long)(i - 1) * H * H;
-        if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st, 1,
+        if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st,
                             a->scales + 2 * i + 1))) return rc;
         ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, wt_h, H, H);
         LinearNTArgs l{};
-        l.f16 = 1;
         l.A = dcur; l.lda = H; l.B = wt_h; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
         l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H;
@@ -680,14 +677,14 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
 }
 
 // ================================================================================ test hooks
-int tvae_test_linear_nt(const float* A, const float* B, float* C, int M, int N, int K, const float* bias, int act,
+int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act,
                         void* stream) {
     LinearNTArgs a{};
     a.A = A; a.lda = K; a.B = B; a.ldb = K; a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = N; a.bias = bias; a.act = act;
     return linear_nt(a, S(stream));
 }
 
-int tvae_test_linear_tn(const float* P, const float* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
+int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
     return linear_tn(P, Ma, Q, Nb, R, Ma, Nb, C, transpose_out ? Ma : Nb, transpose_out, S(stream));
 }
 

@@ -4,7 +4,7 @@ Same class names, constructor signatures, parameter names/shapes (state_dict com
 SURVEY.md §8b) and `forward` signatures/returns as the reference's src/models.py, so that
 `train_*.py` / `clustering_*.py` can import this file unchanged and reference checkpoints (whole-module
 pickles resolved as `src.models.<Name>`) load.  The arithmetic is not PyTorch: forward/backward of
-GroupConv, the attention encoder and the spatial generator run hand-written CUDA (tcgen05 TF32 GEMMs with
+GroupConv, the attention encoder and the spatial generator run hand-written CUDA (tcgen05 FP16-operand GEMMs with
 operand generators, fused heads) through the C ABI in include/tvae_b200.h.  There is no CPU fallback: calling
 `forward` on CPU tensors or without the built library raises.
 

@@ -352,7 +352,7 @@ def launch_count() -> int:
     return int(L().tvae_launch_count())
 
 
-# kernels (names of tvae_profile_collect) whose MMAs run with 16-bit operands (kind::f16); the rest are kind::tf32
+# kernels (names of tvae_profile_collect) whose MMAs run with fp16 operands (kind::f16): all of them
 F16_KERNELS: set = {"conv1_fwd", "conv1_wgrad", "conv2_heads", "gen_l1_fwd", "gen_l1_wgrad", "gen_l1_dgrad", "linear_nt", "linear_tn"}
 
 

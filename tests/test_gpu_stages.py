@@ -1,12 +1,13 @@
 """Per-stage GPU parity: each C-ABI call against the CPU oracle (fp64) on the same seeded inputs.
 
 Tolerances (stated per stage):
-  * TF32 stages (group conv, 1x1x1 convs, generator linears): operands rounded to TF32 (2^-11 relative),
+  * tensor-core stages (group conv, 1x1x1 convs, generator linears): FP16 operands (11-bit significand, 2^-11 relative - the
+    precision class of the reference's cuDNN-TF32 path),
     fp32 accumulate -> relative Frobenius error <= 3e-3 on activations and <= 5e-3 on gradients when the
     oracle is evaluated on the same LeakyReLU activation pattern (helpers.ForcedActivations explains why the
     un-forced comparison is kink-limited to ~3e-2; that end-to-end bound is asserted in test_gpu_step.py).
   * fp32 CUDA-core stages (filter bank, attention/KL, likelihoods, coordinate transforms): <= 1e-4 relative
-    (fast-math exp/log differences only), filter bank additionally carries the tf32 rounding of its output.
+    (fast-math exp/log differences only), filter bank additionally carries the fp16 rounding of its output.
 """
 import math
 

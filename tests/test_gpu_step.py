@@ -6,7 +6,8 @@
 2. Against the fp64 oracle at a larger, MNIST(U)-shaped size, plus size-independent properties at the full cfg1 size
    (data-parallel shard additivity, determinism of the forward ELBO).
 
-Tolerances: ELBO terms are compared at 2e-3 relative (TF32 operands, fp32 accumulation; measured ~1e-4).  Gradients
+Tolerances: ELBO terms are compared at 2e-3 relative (FP16 operands = TF32's 11-bit significand, fp32 accumulation;
+measured ~1e-4).  Gradients
 are compared at 6e-2 relative Frobenius norm per parameter: a ReLU network's gradient is discontinuous in its
 pre-activations, so the TF32-level forward perturbation (the same one the reference's own cuDNN-TF32 path has)
 flips ~5e-4 of the activation derivatives and moves gradients by ~sqrt(5e-4) ~ 2e-2; tests/test_gpu_stages.py
