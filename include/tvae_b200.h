@@ -186,7 +186,8 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
  * g is a device scalar = dLoss/d(ll_b) * (-1) (i.e. 1/B for loss = -elbo). d_yhat may be NULL. */
 int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat, const float* g, int B, int E, void* stream);
 /* Gaussian with optional CTF and mask (train_particles.py:298-338): mu = ctf (*) y_hat (scratch (B,n,n)),
- * ll[b] = -0.5 sum mask (mu - y)^2, d_yhat = adjoint-ctf(g * mask * (mu - y)).  ctf may be NULL, radius 0 = no mask. */
+ * ll[b] = -0.5 sum mask (mu - y)^2, d_yhat = adjoint-ctf(g * mask * (mu - y)).  ctf may be NULL, radius 0 = no mask.
+ * With a ctf, y_hat may be NULL when `mu` still holds ctf (*) y_hat from the forward call (backward pass). */
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
                   float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream);
 

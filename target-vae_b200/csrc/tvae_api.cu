@@ -665,7 +665,8 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
             TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             cfg = true;
         }
-        ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n);
+        // y_hat == NULL: mu already holds ctf (*) y_hat from the forward call (the backward pass does not recompute it)
+        if (y_hat) { ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n); }
         mu_in = mu;
     }
     dim3 grid(1, B);   // one CTA per image: deterministic ll[b]

@@ -228,7 +228,8 @@ class FusedStepFn(torch.autograd.Function):
         if spec.likelihood == "bernoulli":
             ll, _ = ops.bernoulli(y_hat, yflat)
         else:
-            ll, _ = ops.gaussian(y_hat, yflat, n, ctfc, att["dx"], spacing, spec.mask_radius)
+            ll, _, mu = ops.gaussian(y_hat, yflat, n, ctfc, att["dx"], spacing, spec.mask_radius)
+            ctx.mu = mu
         log_p = ll.mean()
         kl = att["kl"].mean()
         elbo = log_p - kl
@@ -255,8 +256,9 @@ class FusedStepFn(torch.autograd.Function):
         if spec.likelihood == "bernoulli":
             _, d_yhat = ops.bernoulli(y_hat, yflat, w_ll)
         else:
-            _, d_yhat = ops.gaussian(y_hat, yflat, s.n, ctfc if ctx.has_ctf else None, att["dx"], ctx.spacing,
-                                     spec.mask_radius, w_ll)
+            _, d_yhat, _ = ops.gaussian(y_hat, yflat, s.n, ctfc if ctx.has_ctf else None, att["dx"], ctx.spacing,
+                                        spec.mask_radius, w_ll, mu=ctx.mu)
+            ctx.mu = None
         gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
         gen_grads = _gen_param_grads(gout, gs.L)
         if spec.sync is not None:

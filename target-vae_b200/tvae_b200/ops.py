@@ -334,17 +334,20 @@ def bernoulli(y_hat, y, g=None):
     return ll, d
 
 
-def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None):
+def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None):
+    """-> (ll, d_yhat, mu).  `mu` = ctf (*) y_hat of an earlier call lets the backward pass skip the forward CTF."""
     B = y.shape[0]
     dev = y.device
     ll = empty(B, device=dev)
-    mu = empty(B, n * n, device=dev) if ctf is not None else None
+    have_mu = mu is not None and ctf is not None
+    if ctf is not None and mu is None:
+        mu = empty(B, n * n, device=dev)
     dmu = empty(B, n * n, device=dev) if (ctf is not None and g is not None) else None
     d = torch.empty_like(y_hat) if g is not None else None
-    check(L().tvae_gaussian(_p(f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)),
+    check(L().tvae_gaussian(_p(None if have_mu else f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)),
                             _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
                             _p(g), B, n, stream_ptr().value), "tvae_gaussian")
-    return ll, d
+    return ll, d, mu
 
 
 # ----------------------------------------------------------------------------------------------- instrumentation

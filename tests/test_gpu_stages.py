@@ -279,7 +279,7 @@ def test_bernoulli_and_gaussian():
             diff = torch.where(mask, diff, torch.zeros_like(diff))
         ll_ref = -0.5 * (diff ** 2).sum(1)
         (ll_ref.sum() * (-1.0 / B)).backward()
-        ll, d = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
+        ll, d, _ = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
                              dx.view(B, 2).float().to(DEV), float(s), radius, gsc)
         torch.cuda.synchronize()
         assert rel_err(ll.cpu(), ll_ref.detach()) < 1e-4, radius
