@@ -395,7 +395,7 @@ def run_ours(args, cfg):
         if dom.startswith("conv1"):
             es = ops.enc_shape(B, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
             executed = ops.conv1_executed_fraction(es, dom == "conv1_wgrad")
-        op_peak, op_dtype = (f16_peak, "f16 operands") if dom in ops.F16_KERNELS else (tf32_peak, "tf32 operands")
+        op_peak, op_dtype = f16_peak, "fp16 operands / fp32 accumulate"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": op_peak, "unit": "TFLOP/s",
                     "frac": achieved / op_peak, "traffic": traffic,
                     "achieved_counts": "dense MAC count x2 per launch (SURVEY 8d: zero-padding taps included, what cuDNN executes)",
@@ -403,7 +403,9 @@ def run_ours(args, cfg):
                     "frac_executed": achieved * executed / op_peak,
                     "peak_source": f"cuBLAS {op_dtype} 8192^3 best-of-10 measured in this run, same method as "
                                    "MEASURED_PEAKS.json; bf16_tflops_sustained there = %.1f -> frac_of_bf16" % bf16_peak,
-                    "tf32_peak": tf32_peak, "f16_peak": f16_peak,
+                    "f16_peak": f16_peak, "tf32_peak": tf32_peak,
+                    "precision": "every contraction is tcgen05.mma.kind::f16: FP16 operands (11-bit significand = TF32's, the "
+                                 "reference's cuDNN default) with FP32 accumulation; gradients carry exact power-of-two scales",
                     "frac_of_bf16": achieved / bf16_peak, "ms_per_launch": ms_launch,
                     "share_of_step": prof[dom][0] / ms_total,
                     "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
@@ -418,7 +420,7 @@ def run_ours(args, cfg):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": workload_config(cfg, B, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
