@@ -64,14 +64,77 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
     return slabw + (par ? sg.copy_words : 0) + ((a - par) >> 1);
 }
 
-// conv1 forward epilogue: bias (+ LeakyReLU); fp16 store (x1h: the encoder's activation, conv2's MMA operand) or fp32
-// store (x1: GroupConv.forward alone)
+// conv1 forward epilogue: bias (+ LeakyReLU), then
+//   * fp16 x1 (the encoder's activation) with O % 64 == 0: every 64-column block [128 positions][64 o] of the tile is a
+//     contiguous 16 KB piece of x1; the 128 epilogue threads write their rows into a swizzled staging buffer (two
+//     buffers, alternating) and one thread hands it to the TMA store unit - fully coalesced, asynchronous, and rows past
+//     the end of the image are clipped by the tensor map;
+//   * otherwise (fp32 output of GroupConv.forward alone, or O % 64 != 0) direct per-row stores.
+constexpr int kStoreBlockBytes = kBM * 128;     // one staging buffer: 128 rows x 64 halves
+struct Conv1EpiState { int blocks; };           // 64-column blocks stored so far by this CTA (selects the staging buffer)
+
 template <class Prm>
-__device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, int n0, uint32_t taddr, int row, bool has_work) {
+__device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, Conv1EpiState& st, int n0, uint32_t taddr, int row,
+                                                   bool has_work, uint8_t* extra) {
     const ConvGeom& g = p.g;
     const int pos = ti.a1 + row;
-    const bool ok = has_work && ti.m_tile >= 0 && pos < g.P;
     const int N = g.G * g.O;
+    const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
+    if (p.tma_store) {
+        const bool tile_ok = has_work && ti.m_tile >= 0;           // uniform over the CTA
+        uint8_t* stage0 = extra + p.stage_off;
+#pragma unroll 1
+        for (int blk = 0; blk < kAccN / 64; ++blk) {
+            const int np = n0 + blk * 64;
+            const bool blk_ok = tile_ok && np < N;                  // uniform
+            uint32_t rr[2][32];
+            tmem_ld_32x32(taddr + blk * 64, rr[0]);
+            tmem_ld_32x32(taddr + blk * 64 + 32, rr[1]);
+            tmem_ld_wait();
+            if (!blk_ok) continue;
+            uint8_t* buf = stage0 + (st.blocks & 1) * kStoreBlockBytes;
+            if (st.blocks >= 2) {                                   // the store that last used this buffer has read it
+                if (row == 0) tma_store_wait_read<1>();
+                named_bar_sync(2, kEpiWarps * 32);
+            }
+            const int r = np / g.O, o0 = np - r * g.O;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + o0 + hf * 32 + j + q);
+                        v[q] = __uint_as_float(rr[hf][j + q]) + bb.x;
+                        v[q + 1] = __uint_as_float(rr[hf][j + q + 1]) + bb.y;
+                        v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z;
+                        v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w;
+                    }
+                    if (p.act) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = lrelu(v[q]);
+                    }
+                    uint4 q4;
+                    __half2 hv;
+                    hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
+                    hv = __floats2half2_rn(v[2], v[3]); q4.y = *reinterpret_cast<uint32_t*>(&hv);
+                    hv = __floats2half2_rn(v[4], v[5]); q4.z = *reinterpret_cast<uint32_t*>(&hv);
+                    hv = __floats2half2_rn(v[6], v[7]); q4.w = *reinterpret_cast<uint32_t*>(&hv);
+                    *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) = q4;
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, kEpiWarps * 32);
+            if (row == 0) {
+                tma_store_3d(&p.tmX, smem_u32(buf), o0, ti.a1, ti.a0 * g.G + r);
+                tma_store_commit();
+            }
+            ++st.blocks;
+        }
+        return;
+    }
+    const bool ok = has_work && ti.m_tile >= 0 && pos < g.P;
 #pragma unroll 1
     for (int c = 0; c < kAccN / 32; ++c) {
         uint32_t rr[32];
@@ -80,11 +143,10 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
         const int np = n0 + c * 32;
         if (!ok || np >= N) continue;
         const int r = np / g.O, o0 = np - r * g.O;
-        const float* bs = p.bias + o0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(rr[j]) + (p.bias ? __ldg(bs + j) : 0.f);
+            v[j] = __uint_as_float(rr[j]) + s_bias[o0 + j];
             if (p.act) v[j] = lrelu(v[j]);
         }
         const long long off = (((long long)ti.a0 * g.G + r) * g.P + pos) * g.O + o0;
@@ -111,8 +173,11 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
 // ------------------------------------------------------------------------------------------------
 struct Conv1FwdHParams {
     CUtensorMap tmB;          // bank fp16 [G*O][kpad16], boxes {64 k, 128 rows}
+    CUtensorMap tmX;          // x1 fp16 as [B*G][P][O] for the epilogue's TMA stores (tma_store == 1)
     int num_stages, num_tiles, n_passes, tiles_per_image, m_tiles, m_pairs, k_chunks;
     int pairs;                // CTA pairs launched (both passes of an m-pair stay on one pair)
+    int tma_store;            // 1: fp16 output through staged TMA stores
+    int bias_off, stage_off;  // byte offsets inside the policy's extra smem: [O] bias floats, 2 staging buffers
     ConvGeom g;
     Slab16Geom sg;
     const float* y;           // (B,C,n,n)
@@ -144,7 +209,15 @@ struct Conv1FwdH : PolicyBase {
         int base;            // slab half-index of this thread's output cell
         ChunkWalk w;
     };
-    __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmB); }
+    using EpiState = Conv1EpiState;
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; }
+    __device__ static void epi_finish(const Params& p, EpiState&, uint8_t*, int row) {
+        if (p.tma_store && row == 0) tma_store_wait<0>();      // staged stores have left shared memory before the CTA exits
+    }
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmB);
+        if (p.tma_store) tma_prefetch_desc(&p.tmX);
+    }
     // extra smem: [tab_entries] int offsets (quad mode: 32-bit word offsets; tap mode: half offsets), then the two slab copies
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         int* tab = reinterpret_cast<int*>(extra);
@@ -160,6 +233,8 @@ struct Conv1FwdH : PolicyBase {
             }
             tab[e] = off;
         }
+        float* s_bias = reinterpret_cast<float*>(extra + p.bias_off);
+        for (int o = tid; o < g.O; o += nthreads) s_bias[o] = p.bias ? __ldg(p.bias + o) : 0.f;
     }
     // Tile order: the kernel hands pair `q` the tiles q, q + pairs, q + 2 pairs, ...; iteration `it` of a pair is
     // pass (it % n_passes) of m-pair q + (it / n_passes) * pairs, so both N passes of an m-pair run back to back on
@@ -273,8 +348,9 @@ struct Conv1FwdH : PolicyBase {
             }
         }
     }
-    __device__ static void epilogue(const Params& p, const PairTile& ti, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
-        conv1_fwd_epilogue(p, ti, n0, taddr, row, has_work);
+    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
+                                    uint8_t* extra) {
+        conv1_fwd_epilogue(p, ti, st, n0, taddr, row, has_work, extra);
     }
 };
 
@@ -498,7 +574,7 @@ struct Conv1WgradH : PolicyBase {
             }
         }
     }
-    __device__ static void epilogue(const Params& p, const PairTile& ti, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
+    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState&, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
         const ConvGeom& g = p.g;
         const int kk = ti.a0 + row;
         const int N = g.G * g.O;

@@ -96,6 +96,22 @@ inline int make_tmap_3d_mn_h(CUtensorMap* tm, const void* ptr, uint64_t rows, ui
     return 0;
 }
 
+// Store view of a 16-bit activation tensor [outer][rows][cols] (cols contiguous): boxes {64 cols (128 B), box_rows, 1},
+// 128 B swizzle; rows >= `rows` of a box are clipped by the TMA unit (ragged last tile of an image).
+inline int make_tmap_3d_store_h(CUtensorMap* tm, void* ptr, uint64_t outer, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols & 63)) return fail(-1, "TMA store target must be 16-byte aligned with whole 64-column blocks");
+    cuuint64_t dims[3] = {cols, rows, outer};
+    cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D store) failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // ---- optional per-kernel timing (bench.py): CUDA events recorded around every tc_gemm launch on its own stream
 struct KernelTimer {
     static constexpr int kMaxNames = 32;

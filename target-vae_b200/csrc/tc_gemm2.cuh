@@ -103,7 +103,7 @@ __host__ __device__ inline Smem2Layout make_smem2_layout(int stages, int extra_b
     L.stage_off = 0;
     L.bar_off = stages * kStage2Bytes;
     L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 2) * 8;
-    L.extra_off = (L.tmem_ptr_off + 16 + 127) & ~127u;
+    L.extra_off = (L.tmem_ptr_off + 16 + 1023) & ~1023u;   // policies may keep 128 B-swizzled tiles in their extra region
     L.total = L.extra_off + extra_bytes;
     return L;
 }
@@ -223,6 +223,8 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         const int row = ewarp * 32 + lane;
         uint32_t tphase = 0;
         const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
+        typename P::EpiState est;
+        P::epi_init(prm, est, extra, row);
         for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
             PairTile ti;
             P::tile_info(prm, tile, rank, ti);
@@ -231,13 +233,14 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
             const bool has_work = ti.kc_end > ti.kc_begin;
             for (int a = 0; a < ti.n_acc; ++a) {
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + a * kAccN;
-                P::epilogue(prm, ti, ti.n0 + a * kAccN, taddr, row, has_work, extra);
+                P::epilogue(prm, ti, est, ti.n0 + a * kAccN, taddr, row, has_work, extra);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader);
             tphase ^= 1;
         }
+        P::epi_finish(prm, est, extra, row);
     } else if (warp >= kFirstProdWarp) {
         // ------------------------------------------------------------ operand generators (both CTAs)
         // Two groups of 4 warps fill alternate stages: the fixed per-stage latencies (barrier wait, smem round trips,

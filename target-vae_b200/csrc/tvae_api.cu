@@ -190,7 +190,16 @@ int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const f
     p.tab_entries = p.k_chunks * (p.quad ? kBK16 / 4 : kBK16);
     p.skip = ((g.k * g.k) % kBK16 == 0) ? 1 : 0;
     p.chunks_per_channel = p.skip ? (g.k * g.k) / kBK16 : p.k_chunks;
-    const int extra = p.tab_entries * 4 + 2 * p.sg.copy_words * 4;
+    int extra = p.tab_entries * 4 + 2 * p.sg.copy_words * 4;
+    p.bias_off = extra;
+    extra += ((g.O * 4 + 1023) / 1024) * 1024;
+    extra = (extra + 1023) / 1024 * 1024;            // staging buffers need the 128 B swizzle's 1024-byte alignment
+    p.stage_off = extra;
+    p.tma_store = (x1h != nullptr && g.O % 64 == 0) ? 1 : 0;
+    if (p.tma_store) {
+        if ((rc = make_tmap_3d_store_h(&p.tmX, x1h, (uint64_t)g.B * g.G, g.P, g.O, kBM))) return rc;
+        extra += 2 * kStoreBlockBytes;
+    }
     return launch_gemm2<Conv1FwdH>(p, extra, st, p.pairs);
 }
 // conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); dx1 is fp16 [(b,r,pos)][O] times 1 / *acc_scale
