@@ -188,8 +188,11 @@ int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat,
 /* Gaussian with optional CTF and mask (train_particles.py:298-338): mu = ctf (*) y_hat (scratch (B,n,n)),
  * ll[b] = -0.5 sum mask (mu - y)^2, d_yhat = adjoint-ctf(g * mask * (mu - y)).  ctf may be NULL, radius 0 = no mask.
  * With a ctf, y_hat may be NULL when `mu` still holds ctf (*) y_hat from the forward call (backward pass). */
+/* ws: scratch of tvae_gaussian_workspace_bytes(B, n) bytes for the tensor-core CTF path (banded-Toeplitz GEMM with
+ * fp16 operands; even n <= 128).  ws == NULL, or a size query of 0, selects the CUDA-core correlation kernel. */
+long long tvae_gaussian_workspace_bytes(int B, int n);
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
-                  float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream);
+                  float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream);
 
 /* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */

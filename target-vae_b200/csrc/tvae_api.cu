@@ -4,6 +4,7 @@
 #include "conv_policies.cuh"
 #include "conv2_policies.cuh"
 #include "conv_f16_policies.cuh"
+#include "ctf_policies.cuh"
 #include "gen_policies.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
@@ -658,15 +659,78 @@ int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat,
     return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// tensor-core CTF path: even n <= 128 (one 128 x 128 accumulator per image, the padded filter fits shared memory)
+bool ctf_gemm_ok(int n) { return n >= 4 && n <= 128 && n % 2 == 0; }
+CtfGeom make_ctf_geom(int B, int n) {
+    CtfGeom g{};
+    g.B = B; g.n = n; g.m = n - 1;
+    g.Hp = n + g.m - 1;
+    g.Wp = (g.Hp + 63) / 64 * 64;
+    g.CP = (g.m + 1 + 7) / 8 * 8;
+    const int fp = g.Wp > g.Hp ? g.Wp : g.Hp;
+    g.FP = (fp + 7) / 8 * 8;
+    g.WQ = g.Wp / 64;
+    return g;
+}
+struct CtfWorkspace { __half* ypad; __half* ctf16; __half* flip16; float* scales; long long bytes; };
+CtfWorkspace ctf_workspace(const CtfGeom& g, void* base) {
+    auto up = [](long long x) { return (x + 255) / 256 * 256; };
+    CtfWorkspace w{};
+    char* p = static_cast<char*>(base);
+    long long off = 0;
+    w.ypad = reinterpret_cast<__half*>(p + off);   off += up(2LL * g.B * g.Hp * g.Wp);
+    w.ctf16 = reinterpret_cast<__half*>(p + off);  off += up(2LL * g.B * g.m * g.CP);
+    w.flip16 = reinterpret_cast<__half*>(p + off); off += up(2LL * g.B * g.m * g.CP);
+    w.scales = reinterpret_cast<float*>(p + off);  off += 256;
+    w.bytes = off;
+    return w;
+}
+// out (B,n,n) = correlation of in (B,n,n) with the fp16 filters `flt` (already flipped for the adjoint)
+int ctf_apply_gemm(const CtfGeom& g, const CtfWorkspace& w, const float* in, const __half* flt, const float* in_scale,
+                   const float* out_scale, float* out, cudaStream_t st) {
+    ++g_launch_count;
+    ctf_pad_input_kernel<<<blocks_for((long long)g.B * g.Hp * g.Wp, 256), 256, 0, st>>>(in, w.ypad, g, in_scale);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    CtfApplyParams p{};
+    int rc;
+    if ((rc = make_tmap_2d_h(&p.tmB, w.ypad, (uint64_t)g.B * g.Hp, g.Wp, g.Wp, 128))) return rc;
+    p.g = g; p.ctf16 = flt; p.out = out; p.acc_scale = out_scale;
+    p.num_tiles = g.B;
+    const int extra = (256 + g.m * g.FP + 256) * 2;
+    return launch_gemm<CtfApply>(p, extra, st);
+}
+}  // namespace
+
+extern "C" {
+
+long long tvae_gaussian_workspace_bytes(int B, int n) {
+    if (!ctf_gemm_ok(n)) return 0;
+    return ctf_workspace(make_ctf_geom(B, n), nullptr).bytes;
+}
+
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius, float* mu,
-                  float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* stream) {
+                  float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream) {
     cudaStream_t st = S(stream);
     TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
     const int m = n - 1, W = 16 + m - 1;
     const size_t sm = sizeof(float) * (W * W + m * m);
     dim3 cgrid(cdiv(n, 16), cdiv(n, 16), B);
+    const bool gemm = ctf && ws && ctf_gemm_ok(n);
+    const CtfGeom cg = make_ctf_geom(B, n);
+    const CtfWorkspace cw = ctf_workspace(cg, ws);
+    int rc;
     const float* mu_in = y_hat;
-    if (ctf) {
+    if (gemm) {
+        ++g_launch_count;
+        ctf_to_half_kernel<<<blocks_for((long long)B * cg.m * cg.CP, 256), 256, 0, st>>>(ctf, cw.ctf16, cw.flip16, cg);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+        // y_hat == NULL: mu already holds ctf (*) y_hat from the forward call (the backward pass does not recompute it)
+        if (y_hat && (rc = ctf_apply_gemm(cg, cw, y_hat, cw.ctf16, nullptr, nullptr, mu, st))) return rc;
+        mu_in = mu;
+    } else if (ctf) {
         TVAE_REQUIRE(sm <= 227 * 1024, "gaussian: CTF window does not fit shared memory");
         static bool cfg = false;
         if (!cfg) {
@@ -674,14 +738,24 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
             TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             cfg = true;
         }
-        // y_hat == NULL: mu already holds ctf (*) y_hat from the forward call (the backward pass does not recompute it)
         if (y_hat) { ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n); }
         mu_in = mu;
     }
     dim3 grid(1, B);   // one CTA per image: deterministic ll[b]
     float* dmu_out = d_yhat ? (ctf ? dmu : d_yhat) : nullptr;
     ++g_launch_count; gaussian_kernel<<<grid, 256, 0, st>>>(mu_in, y, dx, s, n, radius, ll, dmu_out, g);
-    if (ctf && d_yhat) { ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n); }
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    if (ctf && d_yhat) {
+        if (gemm) {
+            // adjoint = correlation with the flipped filters; dmu is scaled into fp16's range by a power of two
+            TVAE_CHECK_CUDA(cudaMemsetAsync(cw.scales, 0, sizeof(float) * 8, st));
+            ++g_launch_count; absmax_kernel<<<blocks_for((long long)B * n * n, 256), 256, 0, st>>>(dmu, (long long)B * n * n, cw.scales + 7);
+            ++g_launch_count; single_scale_kernel<<<1, 1, 0, st>>>(cw.scales + 7, cw.scales);
+            if ((rc = ctf_apply_gemm(cg, cw, dmu, cw.flip16, cw.scales + 2, cw.scales + 3, d_yhat, st))) return rc;
+        } else {
+            ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n);
+        }
+    }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

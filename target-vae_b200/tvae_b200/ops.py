@@ -90,7 +90,9 @@ def L():
                      "tvae_gaussian"):
             getattr(lib, name).restype = c_int
         lib.tvae_gaussian.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+        lib.tvae_gaussian_workspace_bytes.restype = ctypes.c_longlong
+        lib.tvae_gaussian_workspace_bytes.argtypes = [c_int, c_int]
         lib.tvae_bernoulli.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
         _configured = True
     return lib
@@ -334,7 +336,7 @@ def bernoulli(y_hat, y, g=None):
     return ll, d
 
 
-def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None):
+def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None, use_ctf_gemm=True):
     """-> (ll, d_yhat, mu).  `mu` = ctf (*) y_hat of an earlier call lets the backward pass skip the forward CTF."""
     B = y.shape[0]
     dev = y.device
@@ -344,9 +346,14 @@ def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None):
         mu = empty(B, n * n, device=dev)
     dmu = empty(B, n * n, device=dev) if (ctf is not None and g is not None) else None
     d = torch.empty_like(y_hat) if g is not None else None
+    ws = None
+    if ctf is not None and use_ctf_gemm:
+        nbytes = int(L().tvae_gaussian_workspace_bytes(B, n))
+        if nbytes > 0:
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     check(L().tvae_gaussian(_p(None if have_mu else f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)),
                             _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
-                            _p(g), B, n, stream_ptr().value), "tvae_gaussian")
+                            _p(g), B, n, _p(ws), stream_ptr().value), "tvae_gaussian")
     return ll, d, mu
 
 

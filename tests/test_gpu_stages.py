@@ -266,21 +266,30 @@ def test_bernoulli_and_gaussian():
     # gaussian + CTF (+ mask)
     from tvae_b200 import synth
     import numpy as np
-    ctf = torch.from_numpy(synth.ctf_kernels(np.random.default_rng(0), B, n)).double()
-    for radius in (0, 6):
-        yh = torch.randn(B, n * n, generator=g, dtype=torch.float64).requires_grad_(True)
-        yy = torch.randn(B, n * n, generator=g, dtype=torch.float64)
-        dx = torch.randn(B, 1, 2, generator=g, dtype=torch.float64) * 0.1
-        s = torch.tensor(2.0 / (n - 1), dtype=torch.float32)
-        mask = orc.particle_mask(dx, s, n, radius) if radius else None
-        mu = F.conv2d(yh.view(1, B, n, n), ctf, padding=(n - 1) // 2, groups=B).view(B, -1)
-        diff = mu - yy
-        if mask is not None:
-            diff = torch.where(mask, diff, torch.zeros_like(diff))
-        ll_ref = -0.5 * (diff ** 2).sum(1)
-        (ll_ref.sum() * (-1.0 / B)).backward()
-        ll, d, _ = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
-                             dx.view(B, 2).float().to(DEV), float(s), radius, gsc)
-        torch.cuda.synchronize()
-        assert rel_err(ll.cpu(), ll_ref.detach()) < 1e-4, radius
-        assert rel_err(d.cpu(), yh.grad) < 1e-4, radius
+    # CUDA-core correlation kernel (fp32, 1e-4) and the tensor-core banded-Toeplitz GEMM (fp16 operands: 2^-11 relative
+    # per element -> 2e-3), at a toy size and at the particle-stack size n = 128
+    for n, radii in ((20, (0, 6)), (128, (0,))):
+        ctf = torch.from_numpy(synth.ctf_kernels(np.random.default_rng(0), B, n)).double()
+        for radius in radii:
+            yh = torch.randn(B, n * n, generator=g, dtype=torch.float64).requires_grad_(True)
+            yy = torch.randn(B, n * n, generator=g, dtype=torch.float64)
+            dx = torch.randn(B, 1, 2, generator=g, dtype=torch.float64) * 0.1
+            s = torch.tensor(2.0 / (n - 1), dtype=torch.float32)
+            mask = orc.particle_mask(dx, s, n, radius) if radius else None
+            mu = F.conv2d(yh.view(1, B, n, n), ctf, padding=(n - 1) // 2, groups=B).view(B, -1)
+            diff = mu - yy
+            if mask is not None:
+                diff = torch.where(mask, diff, torch.zeros_like(diff))
+            ll_ref = -0.5 * (diff ** 2).sum(1)
+            (ll_ref.sum() * (-1.0 / B)).backward()
+            for gemm, tol in ((False, 1e-4), (True, 2e-3)):
+                ll, d, mu_k = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
+                                           dx.view(B, 2).float().to(DEV), float(s), radius, gsc, use_ctf_gemm=gemm)
+                torch.cuda.synchronize()
+                e = (rel_err(mu_k.cpu(), mu.detach()), rel_err(ll.cpu(), ll_ref.detach()), rel_err(d.cpu(), yh.grad))
+                print(f"gaussian+CTF n={n} radius={radius} gemm={gemm}: rel err mu {e[0]:.2e} ll {e[1]:.2e} d_yhat {e[2]:.2e}")
+                assert max(e) < tol, (n, radius, gemm, e)
+                # backward-only call that reuses the forward's mu
+                _, d2, _ = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
+                                        dx.view(B, 2).float().to(DEV), float(s), radius, gsc, mu=mu_k, use_ctf_gemm=gemm)
+                assert rel_err(d2.cpu(), d.cpu()) < 1e-6
