@@ -699,6 +699,151 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
     if (p.dbt && threadIdx.x < p.T) atomicAdd(p.dbt + threadIdx.x, s_red[(p.T + 1) * p.W + threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-MMA variant of thin_bwd_kernel for fp16 activations, T <= 16 thin outputs and W % 128 == 0.
+// The CUDA-core kernel above spends 16 FMA + ~6 other instructions per element and is latency / issue bound
+// (ncu: 46 % issue slots, 18 % DRAM); here both thin contractions are warp-level mma.sync.m16n8k16 (the operands are
+// far too thin for tcgen05 tiles: K = T <= 16 for dpre, M = T <= 16 for dWt), which leaves a streaming kernel.
+//   grid = (row chunks, W / 128); CTA = 8 warps; per 64-row block warp w owns rows (w & 3) * 16 .. +16 and the 64
+//   columns (w >> 2) * 64 .. of the CTA's 128-column slice.
+//   dpre  = S[16 rows x 16 t] . Wt[16 t x 8 c]     A fragment from the staged dt block, B fragments pre-packed in smem
+//   dWt  += S^T[16 t x 16 rows] . a[16 rows x 8 c]  B fragments by ldmatrix.trans from the staged activation tile
+// dynamic smem: [64 * T] dt | [(T + 1) * 128 + T] partial sums | [16 n-tiles][32 lanes] uint2 Wt fragments | a tile [64][136] halves
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+constexpr int kThinPitch = 136;    // halves per staged activation row: 272 B keeps ldmatrix rows and fragment reads conflict-free
+
+template <bool PLANAR>
+__global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int G) {
+    extern __shared__ __align__(16) float s_thin[];
+    const int T = p.T;
+    float* s_dt = s_thin;                                            // [64][T]
+    float* s_red = s_dt + kThinRB * T;                               // [(T + 1) * 128 + T]
+    const int n_red = (T + 1) * 128 + T;
+    uint2* s_wb = reinterpret_cast<uint2*>(s_red + ((n_red + 3) & ~3));   // [16][32]
+    __half* s_a = reinterpret_cast<__half*>(s_wb + 16 * 32);         // [64][kThinPitch]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = warp & 3, cgp = warp >> 2;
+    const int slice0 = blockIdx.y * 128;                             // first column of this CTA
+    const int lr = lane >> 2, lc = (lane & 3) * 2;                   // fragment row / column-pair of this lane
+    const float store_scale = p.store_scale ? __ldg(p.store_scale) : 1.f;
+    const __half* a_g = static_cast<const __half*>(p.a);
+    __half* dpre_g = static_cast<__half*>(p.dpre);
+    for (int i = tid; i < n_red; i += blockDim.x) s_red[i] = 0.f;
+    // B fragments of Wt (k = t, n = c): b0 = {Wt[lc][c], Wt[lc+1][c]}, b1 = {Wt[lc+8][c], Wt[lc+9][c]}, c = slice0 + nt*8 + lr
+    for (int i = tid; i < 16 * 32; i += blockDim.x) {
+        const int nt = i >> 5, l = i & 31;
+        const int c = slice0 + nt * 8 + (l >> 2), t0 = (l & 3) * 2;
+        auto w = [&](int t) { return t < T ? p.Wt[(long long)t * p.W + c] : 0.f; };
+        s_wb[i] = make_uint2(pack_h2(w(t0), w(t0 + 1)), pack_h2(w(t0 + 8), w(t0 + 9)));
+    }
+    const long long m_begin = (long long)blockIdx.x * p.rows_per_cta;
+    const long long m_end = min(m_begin + p.rows_per_cta, p.M);
+    float dw[8][4], dcol[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        dw[nt][0] = dw[nt][1] = dw[nt][2] = dw[nt][3] = 0.f;
+        dcol[nt][0] = dcol[nt][1] = 0.f;
+    }
+    float dbt = 0.f;
+    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB) {
+        const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
+        __syncthreads();
+        // ---- stage dt (zero rows past the end) and the activation tile
+        for (int idx = tid; idx < kThinRB * T; idx += blockDim.x) {
+            int j, rr;
+            long long addr;
+            if (PLANAR) {
+                j = idx / kThinRB; rr = idx - j * kThinRB;
+                const long long m = m0 + rr;
+                const long long br = m / p.P;
+                const int pos = static_cast<int>(m - br * p.P);
+                const long long b = br / G;
+                const int r = static_cast<int>(br - b * G);
+                addr = b * p.dt_outer + (long long)j * p.dt_chan + (long long)r * p.P + pos;
+            } else {
+                rr = idx / T; j = idx - rr * T;
+                addr = (m0 + rr) * T + j;
+            }
+            s_dt[rr * T + j] = rr < rows ? p.dt[addr] : 0.f;
+        }
+        for (int idx = tid; idx < kThinRB * 16; idx += blockDim.x) {     // 16 uint4 per 128-column row
+            const int rr = idx >> 4, q = idx & 15;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (rr < rows) v = __ldg(reinterpret_cast<const uint4*>(a_g + (m0 + rr) * p.W + slice0) + q);
+            *reinterpret_cast<uint4*>(s_a + rr * kThinPitch + q * 8) = v;
+        }
+        __syncthreads();
+        // ---- fragments of the staged dt block for this warp's 16 rows
+        const int r0 = rg * 16 + lr;
+        auto dval = [&](int rr, int t) { return t < T ? s_dt[rr * T + t] : 0.f; };
+        uint32_t fa[4], ft[4];
+        fa[0] = pack_h2(dval(r0, lc), dval(r0, lc + 1));                  // S[row][t]        (dpre:  A = S)
+        fa[1] = pack_h2(dval(r0 + 8, lc), dval(r0 + 8, lc + 1));
+        fa[2] = pack_h2(dval(r0, lc + 8), dval(r0, lc + 9));
+        fa[3] = pack_h2(dval(r0 + 8, lc + 8), dval(r0 + 8, lc + 9));
+        const int rk = rg * 16 + lc;                                       // S^T[t][row]      (dWt:   A = S^T)
+        ft[0] = pack_h2(dval(rk, lr), dval(rk + 1, lr));
+        ft[1] = pack_h2(dval(rk, lr + 8), dval(rk + 1, lr + 8));
+        ft[2] = pack_h2(dval(rk + 8, lr), dval(rk + 9, lr));
+        ft[3] = pack_h2(dval(rk + 8, lr + 8), dval(rk + 9, lr + 8));
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {                                   // pairs of 8-column n-tiles
+            // B fragments of the activation tile for two n-tiles: ldmatrix.x4.trans, matrix q = (rows (q&1)*8.., cols (q>>1)*8..)
+            uint32_t bm[4];
+            {
+                const int q = lane >> 3, rrow = rg * 16 + (q & 1) * 8 + (lane & 7), ccol = cgp * 64 + np * 16 + (q >> 1) * 8;
+                const uint32_t addr = smem_u32(s_a + rrow * kThinPitch + ccol);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bm[0]), "=r"(bm[1]), "=r"(bm[2]), "=r"(bm[3]) : "r"(addr));
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int nt = np * 2 + h2;
+                mma_m16n8k16(dw[nt], ft, bm[2 * h2], bm[2 * h2 + 1]);
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint2 wb = s_wb[(cgp * 8 + nt) * 32 + lane];
+                mma_m16n8k16(c, fa, wb.x, wb.y);
+                const int col = cgp * 64 + nt * 8 + lc;
+                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(s_a + r0 * kThinPitch + col));
+                const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(s_a + (r0 + 8) * kThinPitch + col));
+                c[0] *= (a0.x > 0.f ? 1.f : kSlope); c[1] *= (a0.y > 0.f ? 1.f : kSlope);
+                c[2] *= (a1.x > 0.f ? 1.f : kSlope); c[3] *= (a1.y > 0.f ? 1.f : kSlope);
+                dcol[nt][0] += c[0] + c[2];
+                dcol[nt][1] += c[1] + c[3];
+                if (r0 < rows) *reinterpret_cast<uint32_t*>(dpre_g + (m0 + r0) * p.W + slice0 + col) = pack_h2(c[0] * store_scale, c[1] * store_scale);
+                if (r0 + 8 < rows) *reinterpret_cast<uint32_t*>(dpre_g + (m0 + r0 + 8) * p.W + slice0 + col) = pack_h2(c[2] * store_scale, c[3] * store_scale);
+            }
+        }
+        if (p.dbt && blockIdx.y == 0 && tid < T) {
+            for (int rr = 0; rr < rows; ++rr) dbt += s_dt[rr * T + tid];
+        }
+    }
+    // ---- CTA reduction, then one global atomic per output element
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int col = cgp * 64 + nt * 8 + lc;
+        if (lr < T) { atomicAdd(s_red + lr * 128 + col, dw[nt][0]); atomicAdd(s_red + lr * 128 + col + 1, dw[nt][1]); }
+        if (lr + 8 < T) { atomicAdd(s_red + (lr + 8) * 128 + col, dw[nt][2]); atomicAdd(s_red + (lr + 8) * 128 + col + 1, dw[nt][3]); }
+        atomicAdd(s_red + T * 128 + col, dcol[nt][0]);
+        atomicAdd(s_red + T * 128 + col + 1, dcol[nt][1]);
+    }
+    if (p.dbt && blockIdx.y == 0 && tid < T) s_red[(T + 1) * 128 + tid] = dbt;
+    __syncthreads();
+    for (int i = tid; i < T * 128; i += blockDim.x) atomicAdd(p.dWt + (long long)(i >> 7) * p.W + slice0 + (i & 127), s_red[i]);
+    if (p.dcol)
+        for (int i = tid; i < 128; i += blockDim.x) atomicAdd(p.dcol + slice0 + i, s_red[T * 128 + i]);
+    if (p.dbt && blockIdx.y == 0 && tid < T) atomicAdd(p.dbt + tid, s_red[(T + 1) * 128 + tid]);
+}
+
 // column sums per group of rows: out[g][c] = sum_{m in group g} x[m][c]   (z-conditioned bias gradient),
 // and total[c] += sum over all rows.  grid = (chunks, groups), blockDim.x = W.
 // x is fp16 holding value * (1 / *inv_scale).
