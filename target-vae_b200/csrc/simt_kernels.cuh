@@ -708,7 +708,6 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
 //   columns (w >> 2) * 64 .. of the CTA's 128-column slice.
 //   dpre  = S[16 rows x 16 t] . Wt[16 t x 8 c]     A fragment from the staged dt block, B fragments pre-packed in smem
 //   dWt  += S^T[16 t x 16 rows] . a[16 rows x 8 c]  B fragments by ldmatrix.trans from the staged activation tile
-// dynamic smem: [64 * T] dt | [(T + 1) * 128 + T] partial sums | [16 n-tiles][32 lanes] uint2 Wt fragments | a tile [64][136] halves
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -721,15 +720,32 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 constexpr int kThinPitch = 136;    // halves per staged activation row: 272 B keeps ldmatrix rows and fragment reads conflict-free
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+    const int sz = valid ? 16 : 0;     // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc, bool valid) {
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Double-buffered: the dt block and the activation tile of row block i+1 are fetched with cp.async while block i is
+// computed; dpre is written back into the activation tile in place (same thread, same element) and leaves the CTA as
+// coalesced 16-byte stores.
+// dynamic smem: [(T + 1) * 128 + T] partial sums | [16][32] uint2 Wt fragments | 2 x { [64 * T] dt | a tile [64][136] halves }
 template <bool PLANAR>
 __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int G) {
     extern __shared__ __align__(16) float s_thin[];
     const int T = p.T;
-    float* s_dt = s_thin;                                            // [64][T]
-    float* s_red = s_dt + kThinRB * T;                               // [(T + 1) * 128 + T]
+    float* s_red = s_thin;                                           // [(T + 1) * 128 + T]
     const int n_red = (T + 1) * 128 + T;
     uint2* s_wb = reinterpret_cast<uint2*>(s_red + ((n_red + 3) & ~3));   // [16][32]
-    __half* s_a = reinterpret_cast<__half*>(s_wb + 16 * 32);         // [64][kThinPitch]
+    const int dt_floats = (kThinRB * T + 3) & ~3;
+    const int buf_bytes = dt_floats * 4 + kThinRB * kThinPitch * 2;
+    uint8_t* bufs = reinterpret_cast<uint8_t*>(s_wb + 16 * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rg = warp & 3, cgp = warp >> 2;
     const int slice0 = blockIdx.y * 128;                             // first column of this CTA
@@ -747,23 +763,17 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
     }
     const long long m_begin = (long long)blockIdx.x * p.rows_per_cta;
     const long long m_end = min(m_begin + p.rows_per_cta, p.M);
-    float dw[8][4], dcol[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        dw[nt][0] = dw[nt][1] = dw[nt][2] = dw[nt][3] = 0.f;
-        dcol[nt][0] = dcol[nt][1] = 0.f;
-    }
-    float dbt = 0.f;
-    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB) {
+    // asynchronous fetch of one 64-row block into buffer `bi` (rows past the end are zero-filled)
+    auto prefetch = [&](long long m0, int bi) {
+        float* d_dt = reinterpret_cast<float*>(bufs + bi * buf_bytes);
+        __half* d_a = reinterpret_cast<__half*>(bufs + bi * buf_bytes + dt_floats * 4);
         const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
-        __syncthreads();
-        // ---- stage dt (zero rows past the end) and the activation tile
         for (int idx = tid; idx < kThinRB * T; idx += blockDim.x) {
             int j, rr;
             long long addr;
             if (PLANAR) {
                 j = idx / kThinRB; rr = idx - j * kThinRB;
-                const long long m = m0 + rr;
+                const long long m = min(m0 + rr, p.M - 1);
                 const long long br = m / p.P;
                 const int pos = static_cast<int>(m - br * p.P);
                 const long long b = br / G;
@@ -771,17 +781,33 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
                 addr = b * p.dt_outer + (long long)j * p.dt_chan + (long long)r * p.P + pos;
             } else {
                 rr = idx / T; j = idx - rr * T;
-                addr = (m0 + rr) * T + j;
+                addr = min(m0 + rr, p.M - 1) * T + j;
             }
-            s_dt[rr * T + j] = rr < rows ? p.dt[addr] : 0.f;
+            cp_async_4(d_dt + rr * T + j, p.dt + addr, rr < rows);
         }
-        for (int idx = tid; idx < kThinRB * 16; idx += blockDim.x) {     // 16 uint4 per 128-column row
+        for (int idx = tid; idx < kThinRB * 16; idx += blockDim.x) {     // 16 x 16 bytes per 128-column row
             const int rr = idx >> 4, q = idx & 15;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (rr < rows) v = __ldg(reinterpret_cast<const uint4*>(a_g + (m0 + rr) * p.W + slice0) + q);
-            *reinterpret_cast<uint4*>(s_a + rr * kThinPitch + q * 8) = v;
+            cp_async_16(d_a + rr * kThinPitch + q * 8, a_g + min(m0 + rr, p.M - 1) * p.W + slice0 + q * 8, rr < rows);
         }
+        cp_async_commit();
+    };
+    float dw[8][4], dcol[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        dw[nt][0] = dw[nt][1] = dw[nt][2] = dw[nt][3] = 0.f;
+        dcol[nt][0] = dcol[nt][1] = 0.f;
+    }
+    float dbt = 0.f;
+    if (m_begin < m_end) prefetch(m_begin, 0);
+    int bi = 0;
+    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB, bi ^= 1) {
+        const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
+        const bool more = m0 + kThinRB < m_end;
+        if (more) prefetch(m0 + kThinRB, bi ^ 1);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
+        const float* s_dt = reinterpret_cast<const float*>(bufs + bi * buf_bytes);
+        __half* s_a = reinterpret_cast<__half*>(bufs + bi * buf_bytes + dt_floats * 4);
         // ---- fragments of the staged dt block for this warp's 16 rows
         const int r0 = rg * 16 + lr;
         auto dval = [&](int rr, int t) { return t < T ? s_dt[rr * T + t] : 0.f; };
@@ -803,7 +829,7 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
                 const int q = lane >> 3, rrow = rg * 16 + (q & 1) * 8 + (lane & 7), ccol = cgp * 64 + np * 16 + (q >> 1) * 8;
                 const uint32_t addr = smem_u32(s_a + rrow * kThinPitch + ccol);
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(bm[0]), "=r"(bm[1]), "=r"(bm[2]), "=r"(bm[3]) : "r"(addr));
+                             : "=r"(bm[0]), "=r"(bm[1]), "=r"(bm[2]), "=r"(bm[3]) : "r"(addr) : "memory");
             }
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -813,19 +839,27 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
                 const uint2 wb = s_wb[(cgp * 8 + nt) * 32 + lane];
                 mma_m16n8k16(c, fa, wb.x, wb.y);
                 const int col = cgp * 64 + nt * 8 + lc;
-                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(s_a + r0 * kThinPitch + col));
-                const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(s_a + (r0 + 8) * kThinPitch + col));
+                __half2* pa0 = reinterpret_cast<__half2*>(s_a + r0 * kThinPitch + col);
+                __half2* pa1 = reinterpret_cast<__half2*>(s_a + (r0 + 8) * kThinPitch + col);
+                const float2 a0 = __half22float2(*pa0), a1 = __half22float2(*pa1);
                 c[0] *= (a0.x > 0.f ? 1.f : kSlope); c[1] *= (a0.y > 0.f ? 1.f : kSlope);
                 c[2] *= (a1.x > 0.f ? 1.f : kSlope); c[3] *= (a1.y > 0.f ? 1.f : kSlope);
                 dcol[nt][0] += c[0] + c[2];
                 dcol[nt][1] += c[1] + c[3];
-                if (r0 < rows) *reinterpret_cast<uint32_t*>(dpre_g + (m0 + r0) * p.W + slice0 + col) = pack_h2(c[0] * store_scale, c[1] * store_scale);
-                if (r0 + 8 < rows) *reinterpret_cast<uint32_t*>(dpre_g + (m0 + r0 + 8) * p.W + slice0 + col) = pack_h2(c[2] * store_scale, c[3] * store_scale);
+                // in place: this element of the tile is read by no later ldmatrix of the warp (they move on to other columns)
+                *pa0 = __floats2half2_rn(c[0] * store_scale, c[1] * store_scale);
+                *pa1 = __floats2half2_rn(c[2] * store_scale, c[3] * store_scale);
             }
         }
         if (p.dbt && blockIdx.y == 0 && tid < T) {
             for (int rr = 0; rr < rows; ++rr) dbt += s_dt[rr * T + tid];
         }
+        __syncthreads();
+        for (int idx = tid; idx < rows * 16; idx += blockDim.x) {          // coalesced 16-byte stores of the dpre tile
+            const int rr = idx >> 4, q = idx & 15;
+            *reinterpret_cast<uint4*>(dpre_g + (m0 + rr) * p.W + slice0 + q * 8) = *reinterpret_cast<const uint4*>(s_a + rr * kThinPitch + q * 8);
+        }
+        __syncthreads();                                                   // the tile is free for the prefetch of block i + 2
     }
     // ---- CTA reduction, then one global atomic per output element
 #pragma unroll

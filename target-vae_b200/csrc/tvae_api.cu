@@ -63,8 +63,15 @@ int launch_thin_bwd_mma(ThinBwdParams& p, int G, cudaStream_t st) {
     rows = (rows + kThinRB - 1) / kThinRB * kThinRB;
     p.rows_per_cta = static_cast<int>(rows);
     const int n_red = (p.T + 1) * 128 + p.T;
-    const size_t sm = sizeof(float) * (kThinRB * p.T + ((n_red + 3) & ~3)) + 16 * 32 * 8 + kThinRB * kThinPitch * 2;
-    TVAE_REQUIRE(sm <= 48 * 1024, "thin backward (mma): shared memory");
+    const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + 16 * 32 * 8 + 2 * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
+    if (sm > 48 * 1024) {
+        static bool cfg = false;
+        if (!cfg) {
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(thin_bwd_mma_kernel<PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            cfg = true;
+        }
+    }
+    TVAE_REQUIRE(sm <= 100 * 1024, "thin backward (mma): shared memory");
     ++g_launch_count;
     thin_bwd_mma_kernel<PLANAR><<<dim3(cdiv(p.M, rows), slices), 256, sm, st>>>(p, G);
     TVAE_CHECK_CUDA(cudaGetLastError());
