@@ -68,10 +68,13 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
     }
 }
 // backward of the above in one pass over dpre:  dW1[j][0..1] += sum_m dpre[m][j] x'[m]  and
-// dxp[m] = sum_j dpre[m][j] W1[j][:]   (CTA = rows_per_cta rows in blocks of kCoordRB).
+// dxp[m] = sum_j dpre[m][j] W1[j][:]   (CTA = rows_per_cta rows in blocks of kCoordRB).  When dzb != null every CTA lies
+// inside one image (rows_per_cta divides the pixels per image) and the same pass also yields the bias gradients
+// db1[j] += sum_m dpre[m][j] and dzb[b][j] += sum_{m in image b} dpre[m][j].
 __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, const float* __restrict__ w1, const __half* __restrict__ dpre,
                                                               const float* __restrict__ inv_scale, float* __restrict__ dw1,
-                                                              float* __restrict__ dxp, int H, int rows_per_cta) {
+                                                              float* __restrict__ dxp, float* __restrict__ dzb, float* __restrict__ db1,
+                                                              int H, int rows_per_cta) {
     extern __shared__ float s_cl[];
     float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [kCoordRB]
     float* s_dx = s_cl + 2 * kCoordRB;                              // [kCoordRB][2]
@@ -81,10 +84,12 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
     const int c0 = cg * 4, lane = threadIdx.x & 31;
     const bool warp_rows = (cgs % 32) == 0;                         // every warp lies inside one row
     const float inv = __ldg(inv_scale);
-    float wx[4], wy[4], dwx[4], dwy[4];
+    float* s_sum = s_dw + 2 * H;                                    // [H] column sums (only with dzb)
+    float wx[4], wy[4], dwx[4], dwy[4], dsum[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; dwx[v] = 0.f; dwy[v] = 0.f; }
+    for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; dwx[v] = 0.f; dwy[v] = 0.f; dsum[v] = 0.f; }
     for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) s_dw[i] = 0.f;
+    if (dzb) for (int i = threadIdx.x; i < H; i += blockDim.x) s_sum[i] = 0.f;
     const long long m_begin = (long long)blockIdx.x * rows_per_cta;
     const long long m_end = min(m_begin + rows_per_cta, cx.M);
     for (long long m0 = m_begin; m0 < m_end; m0 += kCoordRB) {
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
                     for (int v = 0; v < 4; ++v) {
                         dwx[v] = fmaf(gv[v], x.x, dwx[v]);
                         dwy[v] = fmaf(gv[v], x.y, dwy[v]);
+                        dsum[v] += gv[v];
                         p0 = fmaf(gv[v], wx[v], p0);
                         p1 = fmaf(gv[v], wy[v], p1);
                     }
@@ -144,9 +150,17 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
     for (int v = 0; v < 4; ++v) {
         atomicAdd(s_dw + 2 * (c0 + v), dwx[v]);
         atomicAdd(s_dw + 2 * (c0 + v) + 1, dwy[v]);
+        if (dzb) atomicAdd(s_sum + c0 + v, dsum[v]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) atomicAdd(dw1 + i, s_dw[i]);
+    if (dzb) {
+        const long long b = m_begin / cx.N;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            atomicAdd(dzb + b * H + i, s_sum[i]);
+            atomicAdd(db1 + i, s_sum[i]);
+        }
+    }
 }
 
 // dxp (B*N,2) -> d_theta (B), d_dx (B,2) through x' = (x - dx) R(theta)   (train_mnist.py:222,234-239).

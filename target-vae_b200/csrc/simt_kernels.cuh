@@ -947,36 +947,40 @@ __global__ void __launch_bounds__(256) enc_bwd_scales_kernel(const float* __rest
 
 // Generator backward: dpre_L = (d_yhat . Wout) lrelu', dpre_{i-1} = (dpre_i . W_i) lrelu'; dpre_i is stored as
 // fp16(dpre_i * s_i) with s_i = scales[2i], 1/s_i = scales[2i + 1], i = 0..L.  Bounds: |dpre_L| <= amax max_c sum_o |Wout[o][c]|,
-// |dpre_{i-1}| <= bound_i max_c sum_j |W_i[j][c]|.  One CTA of 256 threads.
-__global__ void __launch_bounds__(256) gen_bwd_scales_kernel(const float* __restrict__ amax, const float* __restrict__ wout, int n_out,
-                                                             const float* __restrict__ wh, int L, int H, float* __restrict__ scales) {
-    __shared__ float red[8];
-    __shared__ float s_bound;
-    const int tid = threadIdx.x;
-    for (int layer = L; layer >= 0; --layer) {
-        // layer == L: column abs-sums of Wout (n_out x H); else of W_{layer+1} = wh[layer] (H x H)
-        const float* w = layer == L ? wout : wh + (long long)layer * H * H;
-        const int rows = layer == L ? n_out : H;
-        float m = 0.f;
-        for (int c = tid; c < H; c += blockDim.x) {
-            float a = 0.f;
-            for (int j = 0; j < rows; ++j) a += fabsf(w[(long long)j * H + c]);
-            m = fmaxf(m, a);
-        }
+// |dpre_{i-1}| <= bound_i max_c sum_j |W_i[j][c]|.
+// Step 1 (one CTA of 1024 threads per layer): colmax[layer] = max_c sum_j |W[j][c]|, thread = (column, quarter of the rows).
+__global__ void __launch_bounds__(1024) gen_colmax_kernel(const float* __restrict__ wout, int n_out, const float* __restrict__ wh,
+                                                          int L, int H, float* __restrict__ colmax) {
+    extern __shared__ float s_col[];                     // [H] column abs-sums
+    const int layer = blockIdx.x;                        // layer == L: Wout (n_out x H); else W_{layer+1} = wh[layer] (H x H)
+    const float* w = layer == L ? wout : wh + (long long)layer * H * H;
+    const int rows = layer == L ? n_out : H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) s_col[c] = 0.f;
+    __syncthreads();
+    // blockDim.x = parts * H: thread = (column c, row slice `part`)
+    const int parts = blockDim.x / H;
+    const int per = (rows + parts - 1) / parts;
+    {
+        const int c = threadIdx.x % H, part = threadIdx.x / H;
+        float a = 0.f;
+        for (int j = part * per; j < rows && j < (part + 1) * per; ++j) a += fabsf(w[(long long)j * H + c]);
+        atomicAdd(&s_col[c], a);
+    }
+    __syncthreads();
+    float m = 0.f;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) m = fmaxf(m, s_col[c]);
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((tid & 31) == 0) red[tid >> 5] = m;
-        __syncthreads();
-        if (tid == 0) {
-            float mm = 0.f;
-            for (int w8 = 0; w8 < 8; ++w8) mm = fmaxf(mm, red[w8]);
-            const float bound = (layer == L ? amax[0] : s_bound) * mm;
-            s_bound = bound;
-            const float sc = pow2_scale_for(bound);
-            scales[2 * layer] = sc;
-            scales[2 * layer + 1] = 1.f / sc;
-        }
-        __syncthreads();
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(colmax + layer), __float_as_int(m));
+}
+// Step 2 (one thread): chain the bounds.  colmax must be zero-filled before step 1.
+__global__ void gen_bwd_scales_kernel(const float* __restrict__ amax, const float* __restrict__ colmax, int L, float* __restrict__ scales) {
+    float bound = amax[0];
+    for (int layer = L; layer >= 0; --layer) {
+        bound *= colmax[layer];
+        const float sc = pow2_scale_for(bound);
+        scales[2 * layer] = sc;
+        scales[2 * layer + 1] = 1.f / sc;
     }
 }
 

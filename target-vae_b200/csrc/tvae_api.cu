@@ -591,7 +591,11 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     // ---- power-of-two scales s_i of the fp16 gradient tensors dpre_i (i = L .. 0): scales[2i] = s_i, scales[2i+1] = 1/s_i
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->scales, 0, sizeof(float) * 32, st));
     ++g_launch_count; absmax_kernel<<<blocks_for(M * s->n_out, 256), 256, 0, st>>>(a->d_yhat, M * s->n_out, a->scales + 31);
-    ++g_launch_count; gen_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 31, a->f.wout, s->n_out, a->f.wh, L, H, a->scales);
+    {   // scales[20 .. 20 + L]: per-layer max column abs-sum of the weights (L <= 8)
+        const int threads = H >= 1024 ? 1024 : (1024 / H) * H;
+        ++g_launch_count; gen_colmax_kernel<<<L + 1, threads, H * sizeof(float), st>>>(a->f.wout, s->n_out, a->f.wh, L, H, a->scales + 20);
+        ++g_launch_count; gen_bwd_scales_kernel<<<1, 1, 0, st>>>(a->scales + 31, a->scales + 20, L, a->scales);
+    }
     __half* dcur = static_cast<__half*>(a->dpre0);
     __half* dnext = static_cast<__half*>(a->dpre1);
     __half* wt_h = static_cast<__half*>(a->wt_h);
@@ -620,10 +624,14 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         if ((rc = linear_nt(l, st))) return rc;
         __half* t = dcur; dcur = dnext; dnext = t;
     }
-    // ---- dcur == dpre of layer 1 (scaled by s_0): bias / latent-bias gradients
-    ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512);
-    ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
-    TVAE_CHECK_CUDA(cudaGetLastError());
+    // ---- dcur == dpre of layer 1 (scaled by s_0): bias / latent-bias gradients.  Without Fourier features and with
+    // whole 64-row blocks per image they come out of the coordinate-layer backward pass below instead.
+    int coord_rows = 0;
+    if (E == 0 && s->N % kCoordRB == 0) {
+        for (int r = kCoordRB; r <= s->N && r <= 512; r += kCoordRB)
+            if (s->N % r == 0) coord_rows = r;
+    }
+    if (!coord_rows) { ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512); }
     // ---- layer 1 weight and coordinate gradients
     if (E > 0) {
         {
@@ -662,10 +670,15 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
         long long rows = (M + 148LL * 8 - 1) / (148LL * 8);
         rows = (rows + kCoordRB - 1) / kCoordRB * kCoordRB;
-        const size_t sm = sizeof(float) * (4 * kCoordRB + 2 * H);
-        ++g_launch_count; coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp, H, static_cast<int>(rows));
+        if (coord_rows) rows = coord_rows;
+        const size_t sm = sizeof(float) * (4 * kCoordRB + 3 * H);
+        ++g_launch_count;
+        coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp,
+                                                                      coord_rows ? a->dzb : nullptr, a->db1, H, static_cast<int>(rows));
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
+    ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
+    TVAE_CHECK_CUDA(cudaGetLastError());
     if (a->f.theta && a->d_theta) {
         ++g_launch_count; coord_xform_bwd_kernel<<<s->B, 256, 0, st>>>(cx, a->dxp, a->d_theta, a->d_dx);
         TVAE_CHECK_CUDA(cudaGetLastError());
