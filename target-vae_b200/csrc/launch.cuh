@@ -103,8 +103,15 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
     p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
-    return wide ? launch_gemm<LinearNT<256>>(p, LinearNT<256>::kExtraBytes, stream)
-                : launch_gemm<LinearNT<128>>(p, LinearNT<128>::kExtraBytes, stream);
+    // fp16 output with whole 64-column blocks: staged TMA stores (one 16 KB staging buffer per epilogue group)
+    int extra = (LinearNT<128>::kExtraBytes + 1023) / 1024 * 1024;
+    p.tma_store = (a.C16 != nullptr && a.N % 64 == 0) ? 1 : 0;
+    p.stage_off = extra;
+    if (p.tma_store) {
+        if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;
+        extra += LinearNT<128>::kEpiGroups * LinearNT<128>::kStageBytes;
+    }
+    return wide ? launch_gemm<LinearNT<256>>(p, extra, stream) : launch_gemm<LinearNT<128>>(p, extra, stream);
 }
 
 // C[Ma,Nb] (+)= sum_r P[r,Ma] Q[r,Nb], P and Q fp16; caller zero-fills C (accumulated with atomics across row splits).

@@ -34,8 +34,11 @@ struct LinearNTParams {
     const void* aux16;        // [M][ld_aux] fp16 or null: multiply by lrelu'(aux16)
     const float* acc_scale;   // device scalar multiplied into the accumulator first (undoes the operand's scale) or null
     const float* store_scale; // device scalar applied to the fp16 store only (power of two) or null
-    float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient; needs tiles_n == 1) or null
+    float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient) or null
     long long colsum_stride;
+    CUtensorMap tmC;          // C16 as [M][N] fp16, boxes {64, 128 rows}, for the staged TMA stores (tma_store == 1)
+    int tma_store;            // 1: C16 leaves the SM through a swizzled smem staging buffer + TMA store (N % 64 == 0)
+    int stage_off;            // byte offset of the staging buffers (one 16 KB buffer per epilogue group) in the extra smem
 };
 
 // In: v[j] of lane l = value (row l, column j) of a 32 x 32 block.  Out (returned): in lane l, the sum over the 32
@@ -72,7 +75,8 @@ struct LinearNT : PolicyBase {
     static constexpr int kMaxN = 1024;
     static constexpr int kCsOff = 5 * kMaxN;
     static constexpr int kExtraBytes = (kCsOff + kEpiGroups * kEpiWarps * kMaxN) * 4;
-    struct EpiState { int cs; };
+    static constexpr int kStageBytes = kBM * 128;      // [128 rows][64 halves], 128 B swizzle
+    struct EpiState { int cs, grp, blocks; };
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         float* s = reinterpret_cast<float*>(extra);
         for (int i = tid; i < p.N; i += nthreads) s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -80,11 +84,14 @@ struct LinearNT : PolicyBase {
     }
     __device__ static void epi_init(const Params& p, EpiState& st, uint8_t* extra, int slot) {
         st.cs = kCsOff + (slot >> 5) * kMaxN + (slot & 31);
+        st.grp = slot >> 7;
+        st.blocks = 0;
         if (!p.colsum) return;
         float* cs = reinterpret_cast<float*>(extra) + st.cs;
         for (int c = 0; c * 32 < p.N; ++c) cs[c * 32] = 0.f;
     }
     __device__ static void epi_finish(const Params& p, EpiState& st, uint8_t* extra, int slot) {
+        if (p.tma_store && (slot & 127) == 0) tma_store_wait<0>();    // staged stores have left shared memory
         if (!p.colsum) return;
         const int lane = slot & 31;
         const float* cs = reinterpret_cast<const float*>(extra) + st.cs;
@@ -94,6 +101,7 @@ struct LinearNT : PolicyBase {
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (p.tma_store) tma_prefetch_desc(&p.tmC);
     }
     __device__ static void tile_info(const Params& p, int tile, TileInfo& ti) {
         const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
@@ -121,7 +129,7 @@ struct LinearNT : PolicyBase {
             tmem_ld_32x32(taddr + c * 32, r);
             tmem_ld_wait();
             const int n_base = ti.n0 + c * 32;
-            if (p.colsum) {                       // warp-uniform path: every lane takes part in the shuffles
+            if (p.colsum || p.tma_store) {        // uniform path: every thread takes part in the shuffles / barriers
                 if (n_base >= p.N) continue;
             } else if (!m_ok || n_base >= p.N) {
                 continue;
@@ -174,9 +182,38 @@ struct LinearNT : PolicyBase {
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
                 reinterpret_cast<float*>(extra)[st.cs + n_base] += warp_colsum32(v, row & 31);
-                if (!m_ok) continue;
+                if (!m_ok && !p.tma_store) continue;
             }
-            if (p.C16) {
+            if (p.tma_store) {
+                // 64-column blocks: the even 32-column group opens a block (the group's staging buffer must have been
+                // read by the previous store), the odd one closes it and hands it to the TMA store unit; rows >= M
+                // are clipped by the tensor map
+                uint8_t* buf = extra + p.stage_off + st.grp * kStageBytes;
+                if ((c & 1) == 0 && st.blocks > 0) {
+                    if (row == 0) tma_store_wait_read<0>();
+                    named_bar_sync(2 + st.grp, kEpiWarps * 32);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 t;
+                    __half2 h;
+                    h = __floats2half2_rn(v[j] * store_scale, v[j + 1] * store_scale);     t.x = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(v[j + 2] * store_scale, v[j + 3] * store_scale); t.y = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(v[j + 4] * store_scale, v[j + 5] * store_scale); t.z = *reinterpret_cast<uint32_t*>(&h);
+                    h = __floats2half2_rn(v[j + 6] * store_scale, v[j + 7] * store_scale); t.w = *reinterpret_cast<uint32_t*>(&h);
+                    *reinterpret_cast<uint4*>(buf + sw128_offset(row, (c & 1) * 4 + (j >> 3))) = t;
+                }
+                if (c & 1) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(2 + st.grp, kEpiWarps * 32);
+                    if (row == 0) {
+                        tma_store_2d(&p.tmC, smem_u32(buf), n_base - 32, ti.m0);
+                        tma_store_commit();
+                    }
+                    ++st.blocks;
+                }
+                if (!m_ok) continue;
+            } else if (p.C16) {
                 __half* d16 = reinterpret_cast<__half*>(p.C16) + (long long)m * p.ldc16 + n_base;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {

@@ -53,7 +53,7 @@ __host__ __device__ inline SmemLayout make_smem_layout(int stages, int extra_byt
     L.b_off = L.a_off + stages * kAStageBytes;
     L.bar_off = L.b_off + stages * (P::kBN * 128);
     L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 8) * 8;
-    L.extra_off = (L.tmem_ptr_off + 16 + 127) & ~127u;
+    L.extra_off = (L.tmem_ptr_off + 16 + 1023) & ~1023u;    // policies may keep 128 B-swizzled tiles in their extra region
     L.total = L.extra_off + extra_bytes;
     return L;
 }
