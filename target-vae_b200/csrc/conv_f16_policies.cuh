@@ -189,6 +189,8 @@ struct Conv1FwdHParams {
     int tab_entries;
     int skip;                 // 1: skip K chunks that only meet zero padding (needs k*k % 64 == 0)
     int chunks_per_channel;   // k*k / 64 when skip, else k_chunks
+    int per_channel;          // 1 (C > 1 with chunk-aligned channels): the slab holds ONE channel and is refilled when the
+                              // chunk walk reaches the next channel; the offset table is channel-relative
 };
 
 struct Conv1FwdH : PolicyBase {
@@ -196,17 +198,18 @@ struct Conv1FwdH : PolicyBase {
     using Params = Conv1FwdHParams;
     static constexpr bool kF16 = true;
     struct ChunkWalk {
-        int kc, rel;
-        __device__ void begin(const PairTile& ti) { kc = ti.a2; rel = 0; }
+        int kc, rel, c;      // K chunk, chunk index inside the channel's live range, channel
+        __device__ void begin(const PairTile& ti) { kc = ti.a2; rel = 0; c = 0; }
         __device__ void next(const Params& p, const PairTile& ti) {
             ++kc;
-            if (++rel == ti.a3) { rel = 0; kc += p.chunks_per_channel - ti.a3; }
+            if (++rel == ti.a3) { rel = 0; kc += p.chunks_per_channel - ti.a3; ++c; }
         }
     };
     struct TmaState { ChunkWalk w; int n_row0; };
     struct GenState {
-        int b, r_lo, rows;   // slab currently resident
-        int base;            // slab half-index of this thread's output cell
+        int b, r_lo, rows, c;     // slab currently resident (c: channel, per-channel mode only)
+        int t_r_lo, t_rows;       // row window the current tile needs
+        int base;                 // slab half-index of this thread's output cell
         ChunkWalk w;
     };
     using EpiState = Conv1EpiState;
@@ -286,7 +289,9 @@ struct Conv1FwdH : PolicyBase {
         for (int a = 0; a < ti.n_acc; ++a) tma_load_2d_pair(sb + a * kBHalfBytes, &p.tmB, bar, s.w.kc * kBK16, s.n_row0 + a * kAccN);
         s.w.next(p, ti);
     }
-    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.b = -1; s.r_lo = 0; s.rows = 0; s.base = 0; }
+    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) {
+        s.b = -1; s.r_lo = 0; s.rows = 0; s.c = -1; s.t_r_lo = 0; s.t_rows = 0; s.base = 0;
+    }
     __device__ static void gen_tile_begin(const Params& p, const PairTile& ti, GenState& s, uint8_t* extra, int ptid) {
         s.w.begin(ti);
         if (ti.m_tile < 0 || ti.kc_end <= ti.kc_begin) return;
@@ -296,7 +301,10 @@ struct Conv1FwdH : PolicyBase {
         const int last = min(ti.a1 + kBM - 1, g.P - 1);
         const int i1 = last / g.d;
         const int r_lo = i0, rows = i1 - i0 + g.k;                   // padded rows [i0, i1 + k)
-        if (s.b != ti.a0 || s.r_lo != r_lo || s.rows != rows) {       // uniform across the generator warps
+        s.t_r_lo = r_lo; s.t_rows = rows;
+        if (p.per_channel) {
+            // the slab is (re)filled channel by channel in gen_prepare
+        } else if (s.b != ti.a0 || s.r_lo != r_lo || s.rows != rows) {       // uniform across the generator warps
             named_bar_sync(1, kGenWarps * 32);                        // previous tile's gathers are done
             fill_slab16(slabw, p.sg, g, p.y + (long long)ti.a0 * g.C * g.n * g.n, 0, g.C, r_lo, rows, ptid, kGenWarps * 32);
             named_bar_sync(1, kGenWarps * 32);
@@ -306,7 +314,18 @@ struct Conv1FwdH : PolicyBase {
         const int i = pos / g.d, j = pos - i * g.d;
         s.base = (i - r_lo) * p.sg.pitch + j;
     }
-    __device__ static void gen_prepare(const Params&, const PairTile&, GenState&, uint8_t*, int) {}
+    // all 8 generator warps, every chunk (per-channel mode): refill the one-channel slab when the walk reaches a
+    // chunk of another channel / image / row window.  Both groups walk every chunk, so the condition is uniform.
+    __device__ static void gen_prepare(const Params& p, const PairTile& ti, GenState& s, uint8_t* extra, int ptid) {
+        if (!p.per_channel || ti.m_tile < 0) return;
+        if (s.b == ti.a0 && s.r_lo == s.t_r_lo && s.rows == s.t_rows && s.c == s.w.c) return;
+        const ConvGeom& g = p.g;
+        uint32_t* slabw = reinterpret_cast<uint32_t*>(extra + p.tab_entries * 4);
+        named_bar_sync(1, kGenWarps * 32);                            // gathers from the previous channel are done
+        fill_slab16(slabw, p.sg, g, p.y + (long long)ti.a0 * g.C * g.n * g.n, s.w.c, 1, s.t_r_lo, s.t_rows, ptid, kGenWarps * 32);
+        named_bar_sync(1, kGenWarps * 32);
+        s.b = ti.a0; s.r_lo = s.t_r_lo; s.rows = s.t_rows; s.c = s.w.c;
+    }
     __device__ static void gen_advance(const Params& p, const PairTile& ti, GenState& s) { s.w.next(p, ti); }
     // one group (128 threads): thread = one A row, all 64 taps of the chunk (8 swizzled 16-byte stores)
     __device__ static void gen_chunk(const Params& p, const PairTile& ti, GenState& s, uint8_t* a_stage, uint8_t* extra, int gtid) {
@@ -314,7 +333,7 @@ struct Conv1FwdH : PolicyBase {
         const uint32_t* slabw = reinterpret_cast<const uint32_t*>(extra + p.tab_entries * 4);
         const int row = gtid;
         const bool live = ti.m_tile >= 0;
-        const int kc = s.w.kc;
+        const int kc = p.per_channel ? ti.a2 + s.w.rel : s.w.kc;      // table row: channel-relative in per-channel mode
         if (p.quad) {
             const uint32_t* src = slab16_words(slabw, p.sg, s.base);
 #pragma unroll

@@ -210,11 +210,14 @@ int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const f
     const int pairs_dev = sm_count() / 2;
     p.pairs = p.m_pairs < pairs_dev ? p.m_pairs : pairs_dev;
     p.num_tiles = p.pairs * cdiv(p.m_pairs, p.pairs) * p.n_passes;   // (m-pair, pass) grid padded to whole rounds of the pairs
-    p.sg = make_slab16(g, (kBM - 1) / g.d + 2 + g.k - 1, g.C);
     p.quad = (g.k % 4 == 0) ? 1 : 0;
-    p.tab_entries = p.k_chunks * (p.quad ? kBK16 / 4 : kBK16);
     p.skip = ((g.k * g.k) % kBK16 == 0) ? 1 : 0;
     p.chunks_per_channel = p.skip ? (g.k * g.k) / kBK16 : p.k_chunks;
+    // multi-channel images whose channels are chunk-aligned keep one channel in the slab at a time (cfg3: three
+    // 64x64-tap channels would need 101 KB of slab and leave room for a single pipeline stage)
+    p.per_channel = (g.C > 1 && p.skip) ? 1 : 0;
+    p.sg = make_slab16(g, (kBM - 1) / g.d + 2 + g.k - 1, p.per_channel ? 1 : g.C);
+    p.tab_entries = (p.per_channel ? p.chunks_per_channel : p.k_chunks) * (p.quad ? kBK16 / 4 : kBK16);
     int extra = p.tab_entries * 4 + 2 * p.sg.copy_words * 4;
     p.bias_off = extra;
     extra += ((g.O * 4 + 1023) / 1024) * 1024;

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from helpers import load_golden, oracle_step, rel_err
 from tvae_b200 import synth
-from tvae_b200.config import CFG1, HotPathConfig
+from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, HotPathConfig
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -106,6 +106,20 @@ def test_step_matches_oracle_mnist_shaped():
     assert abs(logp - float(o_logp)) < 2e-3 * abs(float(o_logp))
     assert abs(kl - float(o_kl)) < 2e-3 * abs(float(o_kl))
     check_grads(grads, o_grads, 6e-2, "cfg1_b8")
+
+
+@pytest.mark.parametrize("cfg", [CFG2, CFG3, CFG4], ids=lambda c: c.name)
+def test_full_size_step_matches_oracle(cfg):
+    """BASELINE.json configs[1..3] at their full image / filter sizes (dSprites 64x64 k=64, galaxy RGB: the one-channel-
+    at-a-time slab of the conv kernel, particle stack 128x128 + CTF), B = 2, against the fp32 CPU oracle."""
+    B = 2
+    elbo, logp, kl, grads = run_step(cfg, B)
+    o_elbo, o_logp, o_kl, _, o_grads = oracle_step(cfg, B, dtype=torch.float32)
+    print(f"{cfg.name} B=2: elbo {elbo:.4f} / {float(o_elbo):.4f}, log_p {logp:.4f} / {float(o_logp):.4f}, kl {kl:.4f} / {float(o_kl):.4f}")
+    assert abs(elbo - float(o_elbo)) < 2e-3 * abs(float(o_elbo))
+    assert abs(logp - float(o_logp)) < 2e-3 * abs(float(o_logp))
+    assert abs(kl - float(o_kl)) < 2e-3 * abs(float(o_kl))
+    check_grads(grads, o_grads, 6e-2, cfg.name)
 
 
 def test_full_size_properties_cfg1():
