@@ -10,7 +10,7 @@ constexpr int kMaxSmemBytes = 227 * 1024;
 
 template <class P>
 inline int pick_stages(int extra_bytes) {
-    const int per_stage = kAStageBytes + P::kBN * 128;
+    const int per_stage = kAStageBytes + (P::kBResidentChunks > 0 ? 0 : P::kBN * 128);   // a resident B is part of the fixed layout
     const SmemLayout L0 = make_smem_layout<P>(0, extra_bytes);
     int s = (kMaxSmemBytes - static_cast<int>(L0.total) - 1024) / per_stage;
     if (s > kMaxStages) s = kMaxStages;

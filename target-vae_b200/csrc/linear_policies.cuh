@@ -123,10 +123,38 @@ struct LinearNT : PolicyBase {
         const float acc_scale = p.acc_scale ? __ldg(p.acc_scale) : 1.f;
         const float store_scale = p.store_scale ? __ldg(p.store_scale) : 1.f;
         const float* rb = (p.row_bias && m_ok) ? p.row_bias + (long long)(m / p.rows_per_group) * p.ld_rb : nullptr;
+        // LeakyReLU-mask operand (aux16): its global loads are the longest latency of this epilogue.  They run one
+        // 32-column block ahead of their use, and the rows the group's NEXT tile will need are pulled into L2 now.
+        const __half* ax_row = (p.aux16 && m_ok) ? reinterpret_cast<const __half*>(p.aux16) + (long long)m * p.ld_aux + ti.n0 : nullptr;
+        uint4 ax_next[4];
+        if (ax_row) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ti.n0 + 8 * j < p.N) ax_next[j] = __ldg(reinterpret_cast<const uint4*>(ax_row) + j);
+            const int tile_next = (ti.m0 / kBM) * p.tiles_n + ti.n0 / BN + kEpiGroups;
+            const int mt = tile_next / p.tiles_n, nt = tile_next - mt * p.tiles_n;
+            const long long mn = (long long)mt * kBM + row;
+            if (mn < p.M) {
+                const char* pf = reinterpret_cast<const char*>(reinterpret_cast<const __half*>(p.aux16) + mn * p.ld_aux + nt * BN);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    if (nt * BN + 64 * j < p.N) prefetch_l2(pf + 128 * j);
+            }
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(taddr + c * 32, r);
+            uint4 ax_cur[4];
+            if (ax_row) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ax_cur[j] = ax_next[j];
+                if (c + 1 < BN / 32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ti.n0 + (c + 1) * 32 + 8 * j < p.N) ax_next[j] = __ldg(reinterpret_cast<const uint4*>(ax_row + (c + 1) * 32) + j);
+                }
+            }
             tmem_ld_wait();
             const int n_base = ti.n0 + c * 32;
             if (p.colsum || p.tma_store) {        // uniform path: every thread takes part in the shuffles / barriers
@@ -159,12 +187,11 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j]);
             }
-            if (p.aux16 && m_ok) {
-                const __half* ax = reinterpret_cast<const __half*>(p.aux16) + (long long)m * p.ld_aux + n_base;
+            if (ax_row) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     if (n_base + j < p.N) {
-                        const uint4 t = __ldg(reinterpret_cast<const uint4*>(ax + j));
+                        const uint4 t = ax_cur[j >> 3];
                         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

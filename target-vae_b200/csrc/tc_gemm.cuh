@@ -51,7 +51,8 @@ __host__ __device__ inline SmemLayout make_smem_layout(int stages, int extra_byt
     SmemLayout L;
     L.a_off = 0;
     L.b_off = L.a_off + stages * kAStageBytes;
-    L.bar_off = L.b_off + stages * (P::kBN * 128);
+    // B ring, or (kBResidentChunks > 0) the whole B operand kept resident: its K chunks never change from tile to tile
+    L.bar_off = L.b_off + (P::kBResidentChunks > 0 ? P::kBResidentChunks : stages) * (P::kBN * 128);
     L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 8) * 8;
     L.extra_off = (L.tmem_ptr_off + 16 + 1023) & ~1023u;    // policies may keep 128 B-swizzled tiles in their extra region
     L.total = L.extra_off + extra_bytes;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__((kCtrlWarps + kEpiWarps * P::kEpiGroups + P::k
 tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kBN = P::kBN;
-    constexpr int kAccStages = (512 / kBN) > 4 ? 4 : (512 / kBN);
+    constexpr int kAccStagesFit = (512 / kBN) > 4 ? 4 : (512 / kBN);
+    constexpr int kAccStages = kAccStagesFit < P::kMaxAccStages ? kAccStagesFit : P::kMaxAccStages;   // policies may keep TMEM columns for themselves
     constexpr int kTmemCols = 512;
     constexpr int kBStageBytes = kBN * 128;
     constexpr uint32_t kIdesc = make_idesc_f16(kBM, kBN, P::kAMajorMN, P::kBMajorMN, P::kAFmt, P::kBFmt);
@@ -128,9 +130,17 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
                 for (int kc = ti.kc_begin; kc < ti.kc_end; ++kc) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t fb = full_bar + 8 * stage;
-                    mbar_arrive_expect_tx(fb, P::tx_bytes());
-                    P::issue_tma(prm, ti, kc, smem_u32(smem_a + stage * kAStageBytes),
-                                 smem_u32(smem_b + stage * kBStageBytes), fb);
+                    if constexpr (P::kBResidentChunks > 0) {
+                        // resident B: chunk kc is loaded once, with this CTA's first tile; later stages carry A only
+                        const bool first = tile == tile_begin;
+                        mbar_arrive_expect_tx(fb, kAStageBytes + (first ? kBStageBytes : 0));
+                        P::issue_tma_a(prm, ti, kc, smem_u32(smem_a + stage * kAStageBytes), fb);
+                        if (first) P::issue_tma_b(prm, ti, kc, smem_u32(smem_b + (kc - ti.kc_begin) * kBStageBytes), fb);
+                    } else {
+                        mbar_arrive_expect_tx(fb, P::tx_bytes());
+                        P::issue_tma(prm, ti, kc, smem_u32(smem_a + stage * kAStageBytes),
+                                     smem_u32(smem_b + stage * kBStageBytes), fb);
+                    }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -152,7 +162,7 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
                     mbar_wait(full_bar + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * kAStageBytes);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * kBStageBytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (P::kBResidentChunks > 0 ? kc - ti.kc_begin : stage) * kBStageBytes);
 #pragma unroll
                     for (int ks = 0; ks < kKSteps; ++ks) {
                         uint64_t adesc, bdesc;
@@ -184,9 +194,17 @@ tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
             mbar_wait(tfull_bar + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + as * kBN;
-            P::epilogue(prm, ti, est, taddr, row, extra);
-            tc_fence_before();
-            mbar_arrive(tempty_bar + 8 * as);
+            if constexpr (P::kEpiSelfRelease) {
+                // the policy releases the accumulator itself (as soon as it has read it) and may use the TMEM columns
+                // past the accumulator stages
+                est.tempty = tempty_bar + 8 * as;
+                est.tmem_free = tmem_base + kAccStages * kBN;      // lane 0 of the first free column
+                P::epilogue(prm, ti, est, taddr, row, extra);
+            } else {
+                P::epilogue(prm, ti, est, taddr, row, extra);
+                tc_fence_before();
+                mbar_arrive(tempty_bar + 8 * as);
+            }
         }
         P::epi_finish(prm, est, extra, egrp * kBM + row);
     } else if (P::kAGen && warp >= kFirstGenWarp) {
@@ -226,6 +244,9 @@ struct PolicyBase {
     static constexpr bool kAGen = false;
     static constexpr int kProdWarps = 0;
     static constexpr int kEpiGroups = 1;      // tc_gemm: epilogue warpgroups taking alternate tiles
+    static constexpr int kMaxAccStages = 4;   // tc_gemm: upper bound on the TMEM accumulator stages
+    static constexpr int kBResidentChunks = 0;   // tc_gemm: > 0 = B has this many K chunks, identical for every tile, kept in smem
+    static constexpr bool kEpiSelfRelease = false;   // tc_gemm: the policy's epilogue arrives on EpiState::tempty itself
     static constexpr uint32_t kAFmt = 0;      // operand formats of kind::f16: 0 = FP16, 1 = BF16 (both operands must agree)
     static constexpr uint32_t kBFmt = 0;
     struct EpiState {};

@@ -367,6 +367,18 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
     // ---- conv2 (1x1x1) + heads
     {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2_h), (long long)g.O * g.O);
+        if (g.O == 128 && NH <= 32) {
+            // heads on the tensor core, h through staged TMA stores (Conv2HeadsTC)
+            Conv2HeadsTCParams q{};
+            if ((rc = make_tmap_2d_h(&q.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
+            if ((rc = make_tmap_2d_h(&q.tmB, a->w2_h, g.O, g.O, g.O, 128))) return rc;
+            if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, g.O, g.O, kBM))) return rc;
+            q.R = R; q.O = g.O; q.NH = NH; q.NHpad = NH <= 16 ? 16 : 32; q.G = g.G; q.P = g.P;
+            q.k_chunks = 2;
+            q.num_tiles = cdiv(R, kBM);
+            q.b2 = a->b2; q.wh = a->wh; q.bh = a->bh; q.head_add = a->head_add; q.heads = a->heads;
+            return launch_gemm<Conv2HeadsTC>(q, Conv2HeadsTC::kExtraBytes, st);
+        }
         Conv2HeadsParams p{};
         const bool wide = g.O > 128;
         const int BN = wide ? 256 : 128;
