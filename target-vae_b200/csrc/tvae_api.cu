@@ -6,6 +6,7 @@
 #include "conv_f16_policies.cuh"
 #include "ctf_policies.cuh"
 #include "gen_policies.cuh"
+#include "gen_pair_policies.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
 #include "simt_kernels.cuh"
@@ -649,7 +650,24 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     if (!coord_rows) { ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512); }
     // ---- layer 1 weight and coordinate gradients
     if (E > 0) {
-        {
+        if (H % 128 == 0 && H <= 2 * kAccN) {
+            // CTA-pair kernel: all H hidden columns per generated feature chunk (gen_pair_policies.cuh)
+            GenL1WgradPairParams p{};
+            if ((rc = make_tmap_3d_mn_h(&p.tmQ, dcur, M, H, H, kBKh, 4))) return rc;
+            p.cx = cx; p.wf_scaled = a->f.wf_scaled; p.bf = a->f.bf; p.E = E; p.H = H; p.dW1 = a->dw1;
+            p.acc_scale = a->scales + 1;
+            p.m_tiles = cdiv(E, kBM);
+            p.m_pairs = cdiv(p.m_tiles, 2);
+            p.chunks_total = static_cast<int>(cdiv(M, kBKh));
+            const int pairs_dev = sm_count() / 2;
+            int splits = pairs_dev / p.m_pairs;
+            if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
+            if (splits < 1) splits = 1;
+            p.chunks_per_split = cdiv(p.chunks_total, splits);
+            p.splits = cdiv(p.chunks_total, p.chunks_per_split);
+            p.num_tiles = p.m_pairs * p.splits;
+            if ((rc = launch_gemm2<GenL1WgradPair>(p, E * 16, st))) return rc;
+        } else {
             GenL1WgradParams p{};
             const bool wide = H > 128;
             const int BN = wide ? 256 : 128;
