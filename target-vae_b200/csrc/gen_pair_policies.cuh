@@ -15,7 +15,7 @@
 // A = feat^T generated MN-major in the 128 B swizzle (two 64-feature blocks [64 px][128 B] per stage),
 // B = dpre (fp16 with a power-of-two scale) by 3-D TMA, MN-major, 64 B swizzle; fp32 atomics into dW1.
 #pragma once
-#include "conv2_policies.cuh"
+#include "conv_f16_policies.cuh"
 #include "gen_policies.cuh"
 
 namespace tvae {
@@ -129,6 +129,145 @@ struct GenL1WgradPair : PolicyBase {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j0 + j < p.H) atomicAdd(p.dW1 + (long long)(j0 + j) * p.E + f, __uint_as_float(rr[j]) * acc_scale);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Generator layer 1 forward on the CTA-pair kernel:
+//
+//   h1[m][j] = LeakyReLU(sum_f cos(phase(m, f)) W1[j][f] + b1[j] + zb[image(m)][j])      (models.py:53-58, 95-117)
+//
+// accumulator rows = pixels m (256 per pair, 128 per CTA), columns = ALL hidden units j (two N = 256 accumulators), so
+// a generated [128 px x 64 f] feature chunk (8192 MUFU.COS = 512 clocks) feeds 1024 clocks of tensor-core work instead
+// of 512 (GenL1Fwd<256> evaluates every feature twice, once per 256-column half of H = 512, and is generator-bound).
+// A = features generated K-major in the 128 B swizzle, B = W1 fp16 [H][E] by TMA (each CTA stages half of every B tile),
+// epilogue = bias + latent bias + LeakyReLU, fp16 tiles through a swizzled staging buffer and TMA stores.
+struct GenL1FwdPairParams {
+    CUtensorMap tmB;          // W1 fp16 [H][E], boxes {64 f, 128 rows}
+    CUtensorMap tmC;          // h1 fp16 [M][H] store view, boxes {64, 128 rows}
+    int num_stages, num_tiles, m_tiles, k_chunks;
+    int bias_off, stage_off;  // byte offsets in the extra smem: [H] b1 floats, 2 staging buffers of 16 KB
+    CoordXform cx;
+    const float* wf_scaled; const float* bf;
+    int E, H;
+    const float* bias;        // (H)
+    const float* zb;          // (B,H) latent_linear(z) or null
+};
+
+struct GenL1FwdPair : PolicyBase {
+    static constexpr const char* kName = "gen_l1_fwd";
+    using Params = GenL1FwdPairParams;
+    static constexpr bool kF16 = true;
+    struct TmaState { int kc, n_row0; };
+    struct GenState { float x0, x1; int kc; };
+    struct EpiState { int blocks; };
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmC);
+    }
+    __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
+        load_fourier_table(reinterpret_cast<float4*>(extra), p.wf_scaled, p.bf, p.E, tid, nthreads);
+        float* s_bias = reinterpret_cast<float*>(extra + p.bias_off);
+        for (int j = tid; j < p.H; j += nthreads) s_bias[j] = __ldg(p.bias + j);
+    }
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; }
+    __device__ static void epi_finish(const Params&, EpiState&, uint8_t*, int row) {
+        if (row == 0) tma_store_wait<0>();
+    }
+    __device__ static void tile_info(const Params& p, int tile, uint32_t rank, PairTile& ti) {
+        ti.n0 = 0;
+        ti.n_acc = p.H > kAccN ? 2 : 1;
+        const int mt = 2 * tile + static_cast<int>(rank);
+        ti.m_tile = mt < p.m_tiles ? mt : -1;
+        ti.a0 = mt * kBM;                                  // first pixel row of this CTA's tile
+        ti.kc_begin = 0;
+        ti.kc_end = p.k_chunks;
+        ti.a1 = ti.a2 = ti.a3 = 0;
+    }
+    __device__ static void tma_tile_begin(const Params&, const PairTile&, uint32_t rank, TmaState& s) {
+        s.kc = 0;
+        s.n_row0 = static_cast<int>(rank) * 128;
+    }
+    __device__ static void tma_chunk(const Params& p, const PairTile& ti, TmaState& s, uint32_t sb, uint32_t bar) {
+        for (int a = 0; a < ti.n_acc; ++a) tma_load_2d_pair(sb + a * kBHalfBytes, &p.tmB, bar, s.kc * kBKh, s.n_row0 + a * kAccN);
+        ++s.kc;
+    }
+    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.x0 = 0.f; s.x1 = 0.f; s.kc = 0; }
+    __device__ static void gen_tile_begin(const Params& p, const PairTile& ti, GenState& s, uint8_t*, int ptid) {
+        s.kc = 0;
+        if (ti.m_tile < 0) { s.x0 = 0.f; s.x1 = 0.f; return; }
+        transformed_coord(p.cx, (long long)ti.a0 + (ptid & (kBM - 1)), s.x0, s.x1);
+    }
+    __device__ static void gen_prepare(const Params&, const PairTile&, GenState&, uint8_t*, int) {}
+    __device__ static void gen_advance(const Params&, const PairTile&, GenState& s) { ++s.kc; }
+    // one group (128 threads) fills a stage: thread = one pixel row, all 64 features of the chunk (8 swizzled 16-byte stores)
+    __device__ static void gen_chunk(const Params& p, const PairTile& ti, GenState& s, uint8_t* a_stage, uint8_t* extra, int gtid) {
+        const float4* tab = reinterpret_cast<const float4*>(extra);
+        const int row = gtid;
+        const bool live = ti.m_tile >= 0;
+        const int f0 = s.kc * kBKh;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            float e[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + ch * 8 + q;
+                e[q] = (live && f < p.E) ? __cosf(fourier_phase(tab[f], s.x0, s.x1)) : 0.f;
+            }
+            *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, ch)) =
+                make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+        }
+    }
+    // 64-column blocks: bias + latent bias + LeakyReLU -> fp16 -> staging buffer (two, alternating) -> TMA store;
+    // rows past M are clipped by the tensor map.  Control flow is uniform over the 128 epilogue threads.
+    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
+                                    uint8_t* extra) {
+        const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
+        const bool tile_ok = has_work && ti.m_tile >= 0;
+        const long long m = (long long)ti.a0 + row;
+        const float* zb = (p.zb && tile_ok && m < p.cx.M) ? p.zb + (m / p.cx.N) * p.H : nullptr;
+        uint8_t* stage0 = extra + p.stage_off;
+#pragma unroll 1
+        for (int blk = 0; blk < kAccN / 64; ++blk) {
+            const int j0 = n0 + blk * 64;
+            const bool blk_ok = tile_ok && j0 < p.H;                // uniform
+            uint32_t rr[2][32];
+            tmem_ld_32x32(taddr + blk * 64, rr[0]);
+            tmem_ld_32x32(taddr + blk * 64 + 32, rr[1]);
+            tmem_ld_wait();
+            if (!blk_ok) continue;
+            uint8_t* buf = stage0 + (st.blocks & 1) * kStoreBlockBytes;
+            if (st.blocks >= 2) {                                   // the store that last used this buffer has read it
+                if (row == 0) tma_store_wait_read<1>();
+                named_bar_sync(2, kEpiWarps * 32);
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 4) {
+                        const int jj = j0 + hf * 32 + j + q;
+                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + jj);
+                        const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[q] = lrelu(__uint_as_float(rr[hf][j + q]) + bb.x + bz.x);
+                        v[q + 1] = lrelu(__uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y);
+                        v[q + 2] = lrelu(__uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z);
+                        v[q + 3] = lrelu(__uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w);
+                    }
+                    *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) =
+                        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, kEpiWarps * 32);
+            if (row == 0) {
+                tma_store_2d(&p.tmC, smem_u32(buf), j0, ti.a0);
+                tma_store_commit();
+            }
+            ++st.blocks;
         }
     }
 };

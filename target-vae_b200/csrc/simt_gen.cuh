@@ -163,6 +163,97 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
     }
 }
 
+// Row-streaming variant of the above for H % 8 == 0, H <= 512 (cfg2: H = 512): a warp owns a 256-column slice of whole
+// rows (lane l holds columns 256 g + 8 l + [0,8), g = warp % ceil(H / 256)), four rows = four 16-byte loads in flight
+// per lane at 3 CTAs per SM, the transformed coordinates of the CTA's rows computed once into shared memory, one warp
+// reduction per row slice for dxp and per-lane register accumulators for dW1 / db1 / dzb.
+// HBM-bound: one read of dpre (2 H bytes per row).
+constexpr int kCoordMaxRows = 512;
+__global__ void __launch_bounds__(256) coord_layer_bwd_rows_kernel(CoordXform cx, const float* __restrict__ w1, const __half* __restrict__ dpre,
+                                                                   const float* __restrict__ inv_scale, float* __restrict__ dw1,
+                                                                   float* __restrict__ dxp, float* __restrict__ dzb, float* __restrict__ db1,
+                                                                   int H, int rows_per_cta) {
+    extern __shared__ float s_cl[];
+    float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [kCoordMaxRows] transformed coordinates
+    float* s_dx = s_cl + 2 * kCoordMaxRows;                         // [kCoordMaxRows][2] dxp of the CTA's rows
+    float* s_dw = s_dx + 2 * kCoordMaxRows;                         // [H][2]
+    float* s_sum = s_dw + 2 * H;                                    // [H]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncg = (H + 255) / 256;                                // column groups (1 or 2)
+    const int cg = warp % ncg, rw = warp / ncg, nrw = 8 / ncg;      // this warp: column group, row slot, row slots per pass
+    const int c0 = cg * 256 + lane * 8;
+    const bool col_ok = c0 < H;
+    const float inv = __ldg(inv_scale);
+    const long long m_begin = (long long)blockIdx.x * rows_per_cta;
+    const int rows = static_cast<int>(min((long long)rows_per_cta, cx.M - m_begin));
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        float x0, x1;
+        transformed_coord(cx, m_begin + i, x0, x1);
+        s_x[i] = make_float2(x0, x1);
+        s_dx[2 * i] = 0.f;
+        s_dx[2 * i + 1] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) s_dw[i] = 0.f;
+    float wx[8], wy[8], dwx[8], dwy[8], dsum[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        wx[v] = col_ok ? __ldg(w1 + 2 * (c0 + v)) : 0.f;
+        wy[v] = col_ok ? __ldg(w1 + 2 * (c0 + v) + 1) : 0.f;
+        dwx[v] = 0.f; dwy[v] = 0.f; dsum[v] = 0.f;
+    }
+    __syncthreads();
+    const __half* base = dpre + m_begin * H + c0;
+    for (int r0 = rw; r0 < rows; r0 += 4 * nrw) {                   // rows r0 + nrw * {0,1,2,3} of this warp
+        uint4 t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = r0 + nrw * q;
+            t[q] = (r < rows && col_ok) ? __ldg(reinterpret_cast<const uint4*>(base + (long long)r * H)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = r0 + nrw * q;
+            if (r >= rows) break;                                    // uniform per warp
+            const float2 x = s_x[r];
+            float p0 = 0.f, p1 = 0.f;
+            const uint32_t w[4] = {t[q].x, t[q].y, t[q].z, t[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                dwx[2 * e] = fmaf(f.x, x.x, dwx[2 * e]);         dwx[2 * e + 1] = fmaf(f.y, x.x, dwx[2 * e + 1]);
+                dwy[2 * e] = fmaf(f.x, x.y, dwy[2 * e]);         dwy[2 * e + 1] = fmaf(f.y, x.y, dwy[2 * e + 1]);
+                dsum[2 * e] += f.x;                              dsum[2 * e + 1] += f.y;
+                p0 = fmaf(f.x, wx[2 * e], p0);                   p0 = fmaf(f.y, wx[2 * e + 1], p0);
+                p1 = fmaf(f.x, wy[2 * e], p1);                   p1 = fmaf(f.y, wy[2 * e + 1], p1);
+            }
+            p0 = warp_sum(p0);
+            p1 = warp_sum(p1);
+            if (lane == 0) {
+                if (ncg == 1) { s_dx[2 * r] = p0; s_dx[2 * r + 1] = p1; }
+                else { atomicAdd(s_dx + 2 * r, p0); atomicAdd(s_dx + 2 * r + 1, p1); }
+            }
+        }
+    }
+    if (col_ok) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            atomicAdd(s_dw + 2 * (c0 + v), dwx[v] * inv);
+            atomicAdd(s_dw + 2 * (c0 + v) + 1, dwy[v] * inv);
+            atomicAdd(s_sum + c0 + v, dsum[v] * inv);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * rows; i += blockDim.x) dxp[2 * m_begin + i] = s_dx[i] * inv;
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) atomicAdd(dw1 + i, s_dw[i]);
+    if (dzb) {
+        const long long b = m_begin / cx.N;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            atomicAdd(dzb + b * H + i, s_sum[i]);
+            atomicAdd(db1 + i, s_sum[i]);
+        }
+    }
+}
+
 // dxp (B*N,2) -> d_theta (B), d_dx (B,2) through x' = (x - dx) R(theta)   (train_mnist.py:222,234-239).
 // One CTA per image.
 __global__ void __launch_bounds__(256) coord_xform_bwd_kernel(CoordXform cx, const float* __restrict__ dxp, float* __restrict__ d_theta,

@@ -732,10 +732,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Double-buffered: the dt block and the activation tile of row block i+1 are fetched with cp.async while block i is
-// computed; dpre is written back into the activation tile in place (same thread, same element) and leaves the CTA as
+// Three-buffer ring: the dt block and the activation tile of row blocks i+1 and i+2 are in flight (cp.async) while block i
+// is computed (two CTAs per SM x two 18 KB blocks in flight cover the HBM latency-bandwidth product); dpre is written back into the activation tile in place (same thread, same element) and leaves the CTA as
 // coalesced 16-byte stores.
-// dynamic smem: [(T + 1) * 128 + T] partial sums | [16][32] uint2 Wt fragments | 2 x { [64 * T] dt | a tile [64][136] halves }
+// dynamic smem: [(T + 1) * 128 + T] partial sums | [16][32] uint2 Wt fragments | kThinBufs x { [64 * T] dt | a tile [64][136] halves }
+constexpr int kThinBufs = 3;
 template <bool PLANAR>
 __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int G) {
     extern __shared__ __align__(16) float s_thin[];
@@ -799,12 +800,13 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
     }
     float dbt = 0.f;
     if (m_begin < m_end) prefetch(m_begin, 0);
+    if (m_begin + kThinRB < m_end) prefetch(m_begin + kThinRB, 1);
     int bi = 0;
-    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB, bi ^= 1) {
+    for (long long m0 = m_begin; m0 < m_end; m0 += kThinRB, bi = (bi + 1 == kThinBufs ? 0 : bi + 1)) {
         const int rows = static_cast<int>(min((long long)kThinRB, m_end - m0));
-        const bool more = m0 + kThinRB < m_end;
-        if (more) prefetch(m0 + kThinRB, bi ^ 1);
-        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        const bool more1 = m0 + kThinRB < m_end, more2 = m0 + 2 * kThinRB < m_end;
+        if (more2) prefetch(m0 + 2 * kThinRB, bi + 2 >= kThinBufs ? bi + 2 - kThinBufs : bi + 2);
+        if (more2) cp_async_wait<2>(); else if (more1) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
         const float* s_dt = reinterpret_cast<const float*>(bufs + bi * buf_bytes);
         __half* s_a = reinterpret_cast<__half*>(bufs + bi * buf_bytes + dt_floats * 4);

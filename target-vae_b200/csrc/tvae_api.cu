@@ -64,7 +64,7 @@ int launch_thin_bwd_mma(ThinBwdParams& p, int G, cudaStream_t st) {
     rows = (rows + kThinRB - 1) / kThinRB * kThinRB;
     p.rows_per_cta = static_cast<int>(rows);
     const int n_red = (p.T + 1) * 128 + p.T;
-    const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + 16 * 32 * 8 + 2 * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
+    const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + 16 * 32 * 8 + kThinBufs * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
     if (sm > 48 * 1024) {
         static bool cfg = false;
         if (!cfg) {
@@ -550,6 +550,24 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     __half* a0 = acts;
     if (E > 0) {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1h, (long long)H * E);
+        if (H % 64 == 0 && H <= 2 * kAccN && H > 128) {
+            // CTA-pair kernel: every generated feature chunk feeds all H hidden columns (gen_pair_policies.cuh)
+            GenL1FwdPairParams q{};
+            if ((rc = make_tmap_2d_h(&q.tmB, w1h, H, E, E, 128))) return rc;
+            if ((rc = make_tmap_2d_h(&q.tmC, a0, M, H, H, kBM))) return rc;
+            q.cx = cx; q.wf_scaled = a->wf_scaled; q.bf = a->bf; q.E = E; q.H = H;
+            q.bias = a->b1; q.zb = a->zb;
+            q.m_tiles = static_cast<int>(cdiv(M, kBM));
+            q.k_chunks = cdiv(E, kBKh);
+            q.num_tiles = cdiv(q.m_tiles, 2);
+            int extra = E * 16;
+            q.bias_off = extra;
+            extra += H * 4;
+            extra = (extra + 1023) / 1024 * 1024;
+            q.stage_off = extra;
+            extra += 2 * kStoreBlockBytes;
+            if ((rc = launch_gemm2<GenL1FwdPair>(q, extra, st))) return rc;
+        } else {
         GenL1FwdParams p{};
         const bool wide = H > 128;
         const int BN = wide ? 256 : 128;
@@ -562,6 +580,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         const int extra = E * 16;
         rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
         if (rc) return rc;
+        }
     } else {
         const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
         ++g_launch_count; coord_layer_fwd_kernel<<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
@@ -706,6 +725,12 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         if (coord_rows) rows = coord_rows;
         const size_t sm = sizeof(float) * (4 * kCoordRB + 3 * H);
         ++g_launch_count;
+        if (H % 8 == 0 && H <= 512 && rows <= kCoordMaxRows) {
+            // row-streaming kernel: warps own whole rows, 16-byte loads, register accumulators
+            const size_t smr = sizeof(float) * (4 * kCoordMaxRows + 3 * H);
+            coord_layer_bwd_rows_kernel<<<cdiv(M, rows), 256, smr, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp,
+                                                                          coord_rows ? a->dzb : nullptr, a->db1, H, static_cast<int>(rows));
+        } else
         coord_layer_bwd_kernel<<<cdiv(M, rows), cgs * rpp, sm, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp,
                                                                       coord_rows ? a->dzb : nullptr, a->db1, H, static_cast<int>(rows));
         TVAE_CHECK_CUDA(cudaGetLastError());

@@ -222,7 +222,24 @@ def attn_shape(B, G, d, z, s, offsets) -> AttnShape:
     return a
 
 
+_log_prior_cache: dict = {}
+
+
 def attn_log_prior(s: AttnShape, p_r, device):
+    """log p(t, r) depends only on the attention geometry and the rotation prior: computed once per configuration
+    (the reference rebuilds it on the host every step, train_mnist.py:258-262)."""
+    key = (s.G, s.d, float(s.s), tuple(float(v) for v in p_r), str(device))
+    hit = _log_prior_cache.get(key)
+    if hit is not None:
+        return hit
+    if len(_log_prior_cache) > 32:
+        _log_prior_cache.clear()
+    out = _attn_log_prior(s, p_r, device)
+    _log_prior_cache[key] = out
+    return out
+
+
+def _attn_log_prior(s: AttnShape, p_r, device):
     out = empty(s.G * s.d * s.d, device=device)
     arr = (c_float * 16)(*([float(v) for v in p_r] + [0.0] * (16 - len(p_r))))
     check(L().tvae_attn_log_prior(byref(s), arr, ptr(out), stream_ptr()), "tvae_attn_log_prior")
