@@ -737,16 +737,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // coalesced 16-byte stores.
 // dynamic smem: [(T + 1) * 128 + T] partial sums | [16][32] uint2 Wt fragments | kThinBufs x { [64 * T] dt | a tile [64][136] halves }
 constexpr int kThinBufs = 3;
-template <bool PLANAR>
+// TT = 1: T <= 16.  TT = 2: 16 < T <= 24 (z = 8: 19 heads) - a second k-step for dpre and a second m-tile for dWt of
+// which only rows 16..23 are kept (the accumulator rows 24..31 multiply zero rows of S^T).
+template <bool PLANAR, int TT = 1>
 __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int G) {
     extern __shared__ __align__(16) float s_thin[];
     const int T = p.T;
     float* s_red = s_thin;                                           // [(T + 1) * 128 + T]
     const int n_red = (T + 1) * 128 + T;
-    uint2* s_wb = reinterpret_cast<uint2*>(s_red + ((n_red + 3) & ~3));   // [16][32]
+    uint2* s_wb = reinterpret_cast<uint2*>(s_red + ((n_red + 3) & ~3));   // [TT][16][32]
     const int dt_floats = (kThinRB * T + 3) & ~3;
     const int buf_bytes = dt_floats * 4 + kThinRB * kThinPitch * 2;
-    uint8_t* bufs = reinterpret_cast<uint8_t*>(s_wb + 16 * 32);
+    uint8_t* bufs = reinterpret_cast<uint8_t*>(s_wb + TT * 16 * 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rg = warp & 3, cgp = warp >> 2;
     const int slice0 = blockIdx.y * 128;                             // first column of this CTA
@@ -756,9 +758,9 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
     __half* dpre_g = static_cast<__half*>(p.dpre);
     for (int i = tid; i < n_red; i += blockDim.x) s_red[i] = 0.f;
     // B fragments of Wt (k = t, n = c): b0 = {Wt[lc][c], Wt[lc+1][c]}, b1 = {Wt[lc+8][c], Wt[lc+9][c]}, c = slice0 + nt*8 + lr
-    for (int i = tid; i < 16 * 32; i += blockDim.x) {
-        const int nt = i >> 5, l = i & 31;
-        const int c = slice0 + nt * 8 + (l >> 2), t0 = (l & 3) * 2;
+    for (int i = tid; i < TT * 16 * 32; i += blockDim.x) {
+        const int ks = i >> 9, nt = (i >> 5) & 15, l = i & 31;
+        const int c = slice0 + nt * 8 + (l >> 2), t0 = ks * 16 + (l & 3) * 2;
         auto w = [&](int t) { return t < T ? p.Wt[(long long)t * p.W + c] : 0.f; };
         s_wb[i] = make_uint2(pack_h2(w(t0), w(t0 + 1)), pack_h2(w(t0 + 8), w(t0 + 9)));
     }
@@ -792,11 +794,12 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
         }
         cp_async_commit();
     };
-    float dw[8][4], dcol[8][2];
+    float dw[8][4], dw2[TT == 2 ? 8 : 1][2], dcol[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         dw[nt][0] = dw[nt][1] = dw[nt][2] = dw[nt][3] = 0.f;
         dcol[nt][0] = dcol[nt][1] = 0.f;
+        if (TT == 2) dw2[nt][0] = dw2[nt][1] = 0.f;
     }
     float dbt = 0.f;
     if (m_begin < m_end) prefetch(m_begin, 0);
@@ -813,16 +816,20 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
         // ---- fragments of the staged dt block for this warp's 16 rows
         const int r0 = rg * 16 + lr;
         auto dval = [&](int rr, int t) { return t < T ? s_dt[rr * T + t] : 0.f; };
-        uint32_t fa[4], ft[4];
-        fa[0] = pack_h2(dval(r0, lc), dval(r0, lc + 1));                  // S[row][t]        (dpre:  A = S)
-        fa[1] = pack_h2(dval(r0 + 8, lc), dval(r0 + 8, lc + 1));
-        fa[2] = pack_h2(dval(r0, lc + 8), dval(r0, lc + 9));
-        fa[3] = pack_h2(dval(r0 + 8, lc + 8), dval(r0 + 8, lc + 9));
-        const int rk = rg * 16 + lc;                                       // S^T[t][row]      (dWt:   A = S^T)
-        ft[0] = pack_h2(dval(rk, lr), dval(rk + 1, lr));
-        ft[1] = pack_h2(dval(rk, lr + 8), dval(rk + 1, lr + 8));
-        ft[2] = pack_h2(dval(rk + 8, lr), dval(rk + 9, lr));
-        ft[3] = pack_h2(dval(rk + 8, lr + 8), dval(rk + 9, lr + 8));
+        uint32_t fa[TT][4], ft[TT][4];
+        const int rk = rg * 16 + lc;
+#pragma unroll
+        for (int ks = 0; ks < TT; ++ks) {
+            const int tc = ks * 16 + lc, tr = ks * 16 + lr;
+            fa[ks][0] = pack_h2(dval(r0, tc), dval(r0, tc + 1));              // S[row][t]        (dpre:  A = S)
+            fa[ks][1] = pack_h2(dval(r0 + 8, tc), dval(r0 + 8, tc + 1));
+            fa[ks][2] = pack_h2(dval(r0, tc + 8), dval(r0, tc + 9));
+            fa[ks][3] = pack_h2(dval(r0 + 8, tc + 8), dval(r0 + 8, tc + 9));
+            ft[ks][0] = pack_h2(dval(rk, tr), dval(rk + 1, tr));              // S^T[t][row]      (dWt:   A = S^T)
+            ft[ks][1] = pack_h2(dval(rk, tr + 8), dval(rk + 1, tr + 8));
+            ft[ks][2] = pack_h2(dval(rk + 8, tr), dval(rk + 9, tr));
+            ft[ks][3] = pack_h2(dval(rk + 8, tr + 8), dval(rk + 9, tr + 8));
+        }
 #pragma unroll
         for (int np = 0; np < 4; ++np) {                                   // pairs of 8-column n-tiles
             // B fragments of the activation tile for two n-tiles: ldmatrix.x4.trans, matrix q = (rows (q&1)*8.., cols (q>>1)*8..)
@@ -836,10 +843,19 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
                 const int nt = np * 2 + h2;
-                mma_m16n8k16(dw[nt], ft, bm[2 * h2], bm[2 * h2 + 1]);
+                mma_m16n8k16(dw[nt], ft[0], bm[2 * h2], bm[2 * h2 + 1]);
+                if (TT == 2) {
+                    float d2[4] = {dw2[nt][0], dw2[nt][1], 0.f, 0.f};        // rows 24..31 of S^T are zero
+                    mma_m16n8k16(d2, ft[TT - 1], bm[2 * h2], bm[2 * h2 + 1]);
+                    dw2[nt][0] = d2[0]; dw2[nt][1] = d2[1];
+                }
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
                 const uint2 wb = s_wb[(cgp * 8 + nt) * 32 + lane];
-                mma_m16n8k16(c, fa, wb.x, wb.y);
+                mma_m16n8k16(c, fa[0], wb.x, wb.y);
+                if (TT == 2) {
+                    const uint2 wb1 = s_wb[16 * 32 + (cgp * 8 + nt) * 32 + lane];
+                    mma_m16n8k16(c, fa[TT - 1], wb1.x, wb1.y);
+                }
                 const int col = cgp * 64 + nt * 8 + lc;
                 __half2* pa0 = reinterpret_cast<__half2*>(s_a + r0 * kThinPitch + col);
                 __half2* pa1 = reinterpret_cast<__half2*>(s_a + (r0 + 8) * kThinPitch + col);
@@ -869,6 +885,7 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
         const int col = cgp * 64 + nt * 8 + lc;
         if (lr < T) { atomicAdd(s_red + lr * 128 + col, dw[nt][0]); atomicAdd(s_red + lr * 128 + col + 1, dw[nt][1]); }
         if (lr + 8 < T) { atomicAdd(s_red + (lr + 8) * 128 + col, dw[nt][2]); atomicAdd(s_red + (lr + 8) * 128 + col + 1, dw[nt][3]); }
+        if (TT == 2 && lr + 16 < T) { atomicAdd(s_red + (lr + 16) * 128 + col, dw2[nt][0]); atomicAdd(s_red + (lr + 16) * 128 + col + 1, dw2[nt][1]); }
         atomicAdd(s_red + T * 128 + col, dcol[nt][0]);
         atomicAdd(s_red + T * 128 + col + 1, dcol[nt][1]);
     }

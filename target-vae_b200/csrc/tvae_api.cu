@@ -57,31 +57,32 @@ int check_enc_shape(const tvae_enc_shape* s) {
 }
 
 // warp-MMA thin backward (fp16 activations, T <= 16, W % 128 == 0)
-template <bool PLANAR>
+template <bool PLANAR, int TT = 1>
 int launch_thin_bwd_mma(ThinBwdParams& p, int G, cudaStream_t st) {
     const int slices = p.W / 128;
     long long rows = (p.M * slices + 148LL * 8 - 1) / (148LL * 8);
     rows = (rows + kThinRB - 1) / kThinRB * kThinRB;
     p.rows_per_cta = static_cast<int>(rows);
     const int n_red = (p.T + 1) * 128 + p.T;
-    const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + 16 * 32 * 8 + kThinBufs * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
+    const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + TT * 16 * 32 * 8 + kThinBufs * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
     if (sm > 48 * 1024) {
         static bool cfg = false;
         if (!cfg) {
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(thin_bwd_mma_kernel<PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(thin_bwd_mma_kernel<PLANAR, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             cfg = true;
         }
     }
     TVAE_REQUIRE(sm <= 100 * 1024, "thin backward (mma): shared memory");
     ++g_launch_count;
-    thin_bwd_mma_kernel<PLANAR><<<dim3(cdiv(p.M, rows), slices), 256, sm, st>>>(p, G);
+    thin_bwd_mma_kernel<PLANAR, TT><<<dim3(cdiv(p.M, rows), slices), 256, sm, st>>>(p, G);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <int TMAX, int VEC, bool PLANAR, bool H16 = false>
 int launch_thin_bwd(ThinBwdParams& p, int G, cudaStream_t st) {
-    if (H16 && p.T <= 16 && p.W % 128 == 0) return launch_thin_bwd_mma<PLANAR>(p, G, st);
+    if (H16 && p.T <= 16 && p.W % 128 == 0) return launch_thin_bwd_mma<PLANAR, 1>(p, G, st);
+    if (H16 && p.T <= 24 && p.W % 128 == 0) return launch_thin_bwd_mma<PLANAR, 2>(p, G, st);
     TVAE_REQUIRE(p.W % VEC == 0 && p.W / VEC <= 256 && p.T <= TMAX, "thin backward: unsupported width");
     const int cgs = p.W / VEC;
     const int rpp = 256 / cgs > 0 ? 256 / cgs : 1;
