@@ -194,6 +194,25 @@ long long tvae_gaussian_workspace_bytes(int B, int n);
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
                   float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream);
 
+/* ------------------------------------------------------------------ optimiser step and running statistics
+ * torch.optim.Adam(params, lr).step() [+ zero_grad()] of train_mnist.py:323-324,579 for ALL generator and encoder
+ * parameters in ONE launch (the reference's optimiser launches several kernels per parameter tensor).  Arithmetic of
+ * torch/optim/adam.py::_single_tensor_adam (torch 2.11, amsgrad = False, maximize = False):
+ *     g  = grad (+ weight_decay * p);  m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g g
+ *     p -= (lr / (1 - beta1^step)) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * `tensors` is a HOST array of n descriptors holding DEVICE pointers (fp32); `step` is the 1-based step count.
+ * zero_grad != 0 also clears the gradients (optim.zero_grad(set_to_none=False)). */
+typedef struct {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    long long numel;
+} tvae_adam_tensor;
+int tvae_adam_step(const tvae_adam_tensor* tensors, int n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   int step, int zero_grad, void* stream);   /* doubles: 1 - beta, beta^step are formed like torch's Python floats */
+/* Running means of train_mnist.py:326-338 kept on the device (the reference syncs three .item() per step):
+ * state = {c, elbo_accum, gen_loss_accum, kl_loss_accum};  c += b;  x_accum += b (x - x_accum) / c  with
+ * x = elbo, -log_p_x_g_z, kl_div (device scalars).  Zero the state to start an epoch. */
+int tvae_running_means(const float* elbo, const float* log_p, const float* kl, float b, float* state4, void* stream);
+
 /* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);

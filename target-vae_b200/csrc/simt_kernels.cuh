@@ -1023,4 +1023,71 @@ __global__ void transpose_half_kernel(const float* __restrict__ in, __half* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-tensor Adam (torch/optim/adam.py::_single_tensor_adam arithmetic), one launch for every parameter tensor.
+// Each CTA owns one kAdamChunk-element slice of one tensor; the slice table travels in the kernel parameters.
+// HBM-bound: 16 B read + 12 B written per parameter.
+constexpr int kAdamMaxTensors = 48;
+constexpr int kAdamChunk = 4096;
+struct AdamTable {
+    float* param[kAdamMaxTensors];
+    const float* grad[kAdamMaxTensors];
+    float* m[kAdamMaxTensors];
+    float* v[kAdamMaxTensors];
+    long long numel[kAdamMaxTensors];
+    int block_start[kAdamMaxTensors + 1];     // first CTA of each tensor
+    int n;
+};
+struct AdamHyper {
+    float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, step_size, bc2_sqrt;   // 1 - beta formed in double on the host, like torch's Python floats
+    int zero_grad;
+};
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamHyper& h) {
+    if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
+    m = m + (g - m) * h.one_minus_beta1;                             // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(h.one_minus_beta2 * g, g, v * h.beta2);                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;              // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    p = p - h.step_size * (m / denom);                               // param.addcdiv_(exp_avg, denom, value = -step_size)
+}
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, const AdamHyper h) {
+    int t = 0;
+    while (t + 1 < tab.n && static_cast<int>(blockIdx.x) >= tab.block_start[t + 1]) ++t;
+    const long long off = (long long)(blockIdx.x - tab.block_start[t]) * kAdamChunk;
+    const long long cnt = min((long long)kAdamChunk, tab.numel[t] - off);
+    float* p = tab.param[t] + off;
+    const float* g = tab.grad[t] + off;
+    float* m = tab.m[t] + off;
+    float* v = tab.v[t] + off;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const long long n4 = vec ? cnt / 4 : 0;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        adam_update(pp.x, gg.x, mm.x, vv.x, h); adam_update(pp.y, gg.y, mm.y, vv.y, h);
+        adam_update(pp.z, gg.z, mm.z, vv.z, h); adam_update(pp.w, gg.w, mm.w, vv.w, h);
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+        if (h.zero_grad) reinterpret_cast<float4*>(const_cast<float*>(g))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long i = n4 * 4 + threadIdx.x; i < cnt; i += blockDim.x) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_update(pp, g[i], mm, vv, h);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        if (h.zero_grad) const_cast<float*>(g)[i] = 0.f;
+    }
+}
+// running means of train_mnist.py:326-338 on the device: state = {c, elbo, gen_loss, kl}
+__global__ void running_means_kernel(const float* __restrict__ elbo, const float* __restrict__ log_p, const float* __restrict__ kl, float b,
+                                     float* __restrict__ state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float c = state[0] + b;
+    state[0] = c;
+    const float x[3] = {*elbo, -*log_p, *kl};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float delta = b * (x[i] - state[1 + i]);
+        state[1 + i] += delta / c;
+    }
+}
+
 }  // namespace tvae

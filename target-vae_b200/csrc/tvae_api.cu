@@ -856,6 +856,50 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
     return 0;
 }
 
+// ================================================================================ optimiser step
+int tvae_adam_step(const tvae_adam_tensor* tensors, int n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   int step, int zero_grad, void* stream) {
+    TVAE_REQUIRE(tensors != nullptr && n >= 0, "adam: null tensor table");
+    TVAE_REQUIRE(step >= 1, "adam: step is 1-based");
+    TVAE_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && lr >= 0.0 && eps >= 0.0, "adam: invalid hyper-parameter");
+    // bias corrections in double like the Python-float arithmetic of torch/optim/adam.py
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    AdamHyper h{};
+    h.beta1 = static_cast<float>(beta1); h.beta2 = static_cast<float>(beta2); h.eps = static_cast<float>(eps);
+    h.weight_decay = static_cast<float>(weight_decay);
+    h.step_size = static_cast<float>(lr / bc1);
+    h.bc2_sqrt = static_cast<float>(sqrt(bc2));
+    h.one_minus_beta1 = static_cast<float>(1.0 - beta1);
+    h.one_minus_beta2 = static_cast<float>(1.0 - beta2);
+    h.zero_grad = zero_grad;
+    for (int first = 0; first < n; first += kAdamMaxTensors) {
+        AdamTable tab{};
+        int blocks = 0;
+        tab.n = 0;
+        for (int i = first; i < n && tab.n < kAdamMaxTensors; ++i) {
+            const tvae_adam_tensor& t = tensors[i];
+            if (t.numel <= 0) continue;
+            TVAE_REQUIRE(t.param && t.grad && t.exp_avg && t.exp_avg_sq, "adam: null tensor pointer");
+            const int k = tab.n++;
+            tab.param[k] = t.param; tab.grad[k] = t.grad; tab.m[k] = t.exp_avg; tab.v[k] = t.exp_avg_sq; tab.numel[k] = t.numel;
+            tab.block_start[k] = blocks;
+            blocks += static_cast<int>((t.numel + kAdamChunk - 1) / kAdamChunk);
+        }
+        tab.block_start[tab.n] = blocks;
+        if (blocks == 0) continue;
+        ++g_launch_count; adam_kernel<<<blocks, 256, 0, S(stream)>>>(tab, h);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int tvae_running_means(const float* elbo, const float* log_p, const float* kl, float b, float* state4, void* stream) {
+    TVAE_REQUIRE(elbo && log_p && kl && state4, "running means: null pointer");
+    ++g_launch_count; running_means_kernel<<<1, 32, 0, S(stream)>>>(elbo, log_p, kl, b, state4);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ================================================================================ test hooks
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act,
                         void* stream) {

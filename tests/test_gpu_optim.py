@@ -1,0 +1,104 @@
+"""GPU: the one-launch Adam step and the device-side running means against the CPU oracle and against
+torch.optim.Adam on the same device; a short train_epoch / eval_model run with the reference's call convention.
+Tolerance: fp32 arithmetic, the same operations in a different association -> 2e-6 relative on the moments, 1e-6 on
+the parameters (absolute floor 1e-9)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import adam_oracle as ao
+from tvae_b200.config import HotPathConfig
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(a, b):
+    """fp32 agreement up to re-association: 2e-6 relative, with an absolute floor of 2e-6 x the tensor's scale for
+    elements that are themselves the result of a cancellation."""
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-6 * float(np.abs(b).max()) + 1e-30)
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_matches_oracle_and_torch(wd):
+    from tvae_b200.optim import Adam
+    sizes = [1, 7, 4096, 4097, 100003, (128, 1, 1, 28, 28), (512, 1024)]     # ragged tails, chunk boundaries, real shapes
+    rng = np.random.default_rng(1)
+    host = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    ps = [torch.nn.Parameter(torch.from_numpy(h.copy()).to(DEV)) for h in host]
+    qs = [torch.nn.Parameter(torch.from_numpy(h.copy()).to(DEV)) for h in host]
+    ours, ref = Adam(ps, lr=2e-4, weight_decay=wd), torch.optim.Adam(qs, lr=2e-4, weight_decay=wd)
+    state = [(h.copy(), np.zeros_like(h), np.zeros_like(h)) for h in host]
+    for step in range(1, 6):
+        gs = [(rng.standard_normal(h.shape) * 10.0 ** rng.integers(-3, 2)).astype(np.float32) for h in host]
+        for p, q, g in zip(ps, qs, gs):
+            p.grad = torch.from_numpy(g.copy()).to(DEV)
+            q.grad = torch.from_numpy(g.copy()).to(DEV)
+        ours.step()
+        ref.step()
+        state = [ao.adam_step(p, g, m, v, step, lr=2e-4, weight_decay=wd) for (p, m, v), g in zip(state, gs)]
+    torch.cuda.synchronize()
+    for p, q, (op, om, ov) in zip(ps, qs, state):
+        _close(ours.state[p]["exp_avg"].cpu().numpy(), om)
+        _close(ours.state[p]["exp_avg_sq"].cpu().numpy(), ov)
+        _close(p.detach().cpu().numpy(), op)
+        _close(p.detach().cpu().numpy(), q.detach().cpu().numpy())
+    assert int(ours.state[ps[0]]["step"]) == 5
+    # state_dict is interchangeable with torch.optim.Adam's
+    ref2 = torch.optim.Adam(qs, lr=2e-4, weight_decay=wd)
+    ref2.load_state_dict(ours.state_dict())
+
+
+def test_fused_adam_zero_grad_and_skips_missing_grads():
+    from tvae_b200.optim import Adam
+    a = torch.nn.Parameter(torch.ones(1000, device=DEV))
+    b = torch.nn.Parameter(torch.ones(10, device=DEV))
+    opt = Adam([a, b], lr=1e-2)
+    a.grad = torch.full((1000,), 2.0, device=DEV)
+    opt.step(zero_grad=True)
+    assert float(a.grad.abs().max()) == 0.0
+    assert torch.allclose(a, torch.full_like(a, 1.0 - 1e-2), rtol=1e-5)       # first Adam step moves by lr * sign(g)
+    assert torch.equal(b, torch.ones_like(b)) and b not in opt.state
+
+
+def test_running_means_on_device():
+    from tvae_b200.optim import RunningMeans
+    rng = np.random.default_rng(2)
+    rm = RunningMeans(DEV)
+    state = np.zeros(4, np.float32)
+    for _ in range(10):
+        b = int(rng.integers(1, 101))
+        e, l, k = (float(rng.normal(-500, 50)), float(rng.normal(-480, 50)), float(rng.uniform(1, 30)))
+        rm.update(torch.tensor(e, device=DEV), torch.tensor(l, device=DEV), torch.tensor(k, device=DEV), b)
+        state = ao.running_means(state, e, l, k, b)
+    np.testing.assert_allclose(np.array(rm.read()), state[1:], rtol=1e-5)
+
+
+def test_train_epoch_and_eval_model():
+    """Two optimiser steps through tvae_b200.train.train_epoch: the fused Adam and torch.optim.Adam move the same
+    models (same batches, same injected noise stream) to the same parameters; eval_model runs under no_grad."""
+    from test_gpu_step import build_models
+    from tvae_b200 import synth, train
+    from tvae_b200.optim import Adam
+    cfg = HotPathConfig("t_train", C=1, n=24, k=9, p=3, G=8, z=2, O=32, hidden=128)
+    B = 6
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    batches = [(torch.from_numpy(synth.minibatch(cfg, B, seed=i)["y"]).to(DEV),) for i in range(2)]
+    finals = []
+    for fused in (True, False):
+        gen, enc = build_models(cfg)
+        params = list(gen.parameters()) + list(enc.parameters())
+        opt = Adam(params, lr=2e-4) if fused else torch.optim.Adam(params, lr=2e-4)
+        torch.manual_seed(123)
+        out = train.train_epoch(batches, x, gen, enc, opt, "attention", "attention+offsets", 0, 1, 2 * B, DEV, params,
+                                cfg.theta_prior, cfg.G, cfg.n)
+        assert all(np.isfinite(out)) and out[1] > 0 and out[2] > 0
+        finals.append([p.detach().clone() for p in params])
+        ev = train.eval_model(batches, x, gen, enc, "attention", "attention+offsets", 0, DEV, cfg.theta_prior, cfg.G, cfg.n)
+        assert all(np.isfinite(ev))
+    # Adam's first steps move every weight by ~lr * sign(g): a weight whose gradient is at the fp32-atomics noise floor
+    # may step the other way (bounded by 2 lr per step), every other weight must agree closely
+    lr, steps = 2e-4, 2
+    d = torch.cat([(a - b).abs().flatten() for a, b in zip(*finals)])
+    assert float(d.max()) <= 2 * lr * steps * 1.01
+    assert float(d.mean()) <= 0.02 * lr
