@@ -103,13 +103,16 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
     p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
-    // fp16 output with whole 64-column blocks: staged TMA stores (one 16 KB staging buffer per epilogue group)
-    int extra = (LinearNT<128>::kExtraBytes + 1023) / 1024 * 1024;
+    // extra smem: bias / projection / column-sum rows sized by the actual N, then (fp16 output with whole 64-column
+    // blocks) the staging buffers of the TMA stores: two 16 KB buffers per epilogue group
+    p.npad = (a.N + 31) / 32 * 32;
+    p.cs_off = (1 + a.n_proj) * p.npad;
+    int extra = (LinearNT<128>::extra_floats(a.N, a.n_proj, a.colsum != nullptr) * 4 + 1023) / 1024 * 1024;
     p.tma_store = (a.C16 != nullptr && a.N % 64 == 0) ? 1 : 0;
     p.stage_off = extra;
     if (p.tma_store) {
         if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;
-        extra += LinearNT<128>::kEpiGroups * LinearNT<128>::kStageBytes;
+        extra += LinearNT<128>::kEpiGroups * 2 * LinearNT<128>::kStageBytes;
     }
     return wide ? launch_gemm<LinearNT<256>>(p, extra, stream) : launch_gemm<LinearNT<128>>(p, extra, stream);
 }

@@ -38,7 +38,9 @@ struct LinearNTParams {
     long long colsum_stride;
     CUtensorMap tmC;          // C16 as [M][N] fp16, boxes {64, 128 rows}, for the staged TMA stores (tma_store == 1)
     int tma_store;            // 1: C16 leaves the SM through a swizzled smem staging buffer + TMA store (N % 64 == 0)
-    int stage_off;            // byte offset of the staging buffers (one 16 KB buffer per epilogue group) in the extra smem
+    int stage_off;            // byte offset of the staging buffers (two 16 KB buffers per epilogue group) in the extra smem
+    int npad;                 // N rounded up to 32: row pitch (floats) of the bias / projection / column-sum rows in the extra smem
+    int cs_off;               // float offset of the column-sum rows
 };
 
 // In: v[j] of lane l = value (row l, column j) of a 32 x 32 block.  Out (returned): in lane l, the sum over the 32
@@ -70,20 +72,22 @@ struct LinearNT : PolicyBase {
     static constexpr int kBN = BN;
     static constexpr bool kF16 = true;         // fp16 A and B (TMA boxes of 64 k-elements)
     static constexpr int kEpiGroups = 2;       // short K loops: the epilogue is the critical path, two warpgroups alternate tiles
-    // extra smem: [N] bias, [4][N] fused-projection weights, then column sums [8 epilogue warps][kMaxN] floats (entry
-    // (warp, column) with column % 32 == lane is owned by one thread)
-    static constexpr int kMaxN = 1024;
-    static constexpr int kCsOff = 5 * kMaxN;
-    static constexpr int kExtraBytes = (kCsOff + kEpiGroups * kEpiWarps * kMaxN) * 4;
+    // extra smem, rows of npad floats: bias, n_proj fused-projection weight rows, then (with colsum) one column-sum row
+    // per epilogue warp (entry (warp, column) with column % 32 == lane is owned by one thread); sized by the launcher
+    // from the actual N so that short rows leave the shared memory to the operand ring
+    __host__ static int extra_floats(int N, int n_proj, bool colsum) {
+        const int npad = (N + 31) / 32 * 32;
+        return (1 + n_proj + (colsum ? kEpiGroups * kEpiWarps : 0)) * npad;
+    }
     static constexpr int kStageBytes = kBM * 128;      // [128 rows][64 halves], 128 B swizzle
     struct EpiState { int cs, grp, blocks; };
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         float* s = reinterpret_cast<float*>(extra);
         for (int i = tid; i < p.N; i += nthreads) s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
-        for (int i = tid; i < p.n_proj * p.N; i += nthreads) s[kMaxN + (i / p.N) * kMaxN + (i % p.N)] = __ldg(p.proj_w + i);
+        for (int i = tid; i < p.n_proj * p.N; i += nthreads) s[(1 + i / p.N) * p.npad + (i % p.N)] = __ldg(p.proj_w + i);
     }
     __device__ static void epi_init(const Params& p, EpiState& st, uint8_t* extra, int slot) {
-        st.cs = kCsOff + (slot >> 5) * kMaxN + (slot & 31);
+        st.cs = p.cs_off + (slot >> 5) * p.npad + (slot & 31);
         st.grp = slot >> 7;
         st.blocks = 0;
         if (!p.colsum) return;
@@ -215,9 +219,10 @@ struct LinearNT : PolicyBase {
                 // 64-column blocks: the even 32-column group opens a block (the group's staging buffer must have been
                 // read by the previous store), the odd one closes it and hands it to the TMA store unit; rows >= M
                 // are clipped by the tensor map
-                uint8_t* buf = extra + p.stage_off + st.grp * kStageBytes;
-                if ((c & 1) == 0 && st.blocks > 0) {
-                    if (row == 0) tma_store_wait_read<0>();
+                // two staging buffers per group, alternating: a block only waits for the store issued two blocks ago
+                uint8_t* buf = extra + p.stage_off + (st.grp * 2 + (st.blocks & 1)) * kStageBytes;
+                if ((c & 1) == 0 && st.blocks >= 2) {
+                    if (row == 0) tma_store_wait_read<1>();
                     named_bar_sync(2 + st.grp, kEpiWarps * 32);
                 }
 #pragma unroll
@@ -257,7 +262,7 @@ struct LinearNT : PolicyBase {
             }
             if (p.proj_w) {
                 for (int o = 0; o < p.n_proj; ++o) {
-                    const float* w = s_bias + kMaxN + o * kMaxN + n_base;
+                    const float* w = s_bias + (1 + o) * p.npad + n_base;
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {

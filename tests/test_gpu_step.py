@@ -187,3 +187,33 @@ def test_module_interface_matches_oracle():
     # loud failure without CUDA tensors
     with pytest.raises(RuntimeError):
         enc.conv1(y.float(), "cpu")
+
+
+@pytest.mark.parametrize("B,cfg", [
+    (1, HotPathConfig("edge_b1", C=1, n=24, k=9, p=3, G=8, z=2, O=32, hidden=128)),                      # single image
+    (3, HotPathConfig("edge_odd", C=1, n=25, k=8, p=2, G=4, z=3, O=64, hidden=256)),                     # odd n, even H', ragged tiles
+    (5, HotPathConfig("edge_rgb", C=3, n=16, k=8, p=4, G=8, z=2, O=32, hidden=64, gen_layers=3, n_out=3,
+                      likelihood="bernoulli_rgb")),                                                       # RGB, chunk-aligned channels
+    (2, HotPathConfig("edge_nofourier", C=1, n=20, k=7, p=3, G=16, z=8, O=128, hidden=512, fourier=False,
+                      normal_prior_over_r=True)),                                                         # 19 heads, no Fourier, N % 64 != 0
+])
+def test_edge_shapes_match_oracle(B, cfg):
+    """Ragged / minimal batches and awkward geometries (the reference has no tests; these are the shapes its trainers
+    can produce: last minibatch of an epoch, odd crops, RGB input, --groupconv 16 -z 8)."""
+    elbo, logp, kl, grads = run_step(cfg, B)
+    o_elbo, o_logp, o_kl, _, o_grads = oracle_step(cfg, B, dtype=torch.float64)
+    assert abs(elbo - float(o_elbo)) < 2e-3 * abs(float(o_elbo))
+    assert abs(logp - float(o_logp)) < 2e-3 * abs(float(o_logp))
+    assert abs(kl - float(o_kl)) < 2e-3 * abs(float(o_kl))
+    check_grads(grads, o_grads, 6e-2, cfg.name)
+
+
+def test_empty_batch_fails_loudly():
+    from tvae_b200 import elbo as E
+    from tvae_b200._lib import TvaeError
+    cfg = HotPathConfig("edge_b0", C=1, n=24, k=9, p=3, G=8, z=2, O=32, hidden=128)
+    gen, enc = build_models(cfg)
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    y = torch.zeros(0, 1, cfg.n, cfg.n, device=DEV)
+    with pytest.raises((TvaeError, RuntimeError, ValueError)):
+        E.eval_minibatch(x, y, gen, enc, "attention", "attention+offsets", 0, DEV, cfg.theta_prior, cfg.G, cfg.n)
