@@ -427,6 +427,27 @@ def run_ours(args, cfg):
                     "share_of_step": prof[dom][0] / ms_total,
                     "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
 
+    # per-kernel rooflines of the other event-timed kernels (explanatory; the contract's `roofline` is the dominant one)
+    if roofline is not None:
+        hbm_peak = float(peaks.get("hbm_gbs", 6560.0))
+        pos = cfg.Hout ** 2
+        R = B * cfg.G * pos
+        others = {}
+        for k in algo:
+            if k != dom and k in prof and prof[k][1] > 0:
+                ms = prof[k][0] / prof[k][1]
+                tf = algo[k] / (ms * 1e-3) / 1e12
+                others[k] = {"bound": "tensor", "achieved": tf, "peak": f16_peak, "unit": "TFLOP/s", "frac": tf / f16_peak,
+                             "ms_per_launch": ms}
+        if "conv2_heads" in prof and prof["conv2_heads"][1] > 0:
+            # algorithmic bytes: read x1 (fp16), write h (fp16) and the (3+2z) fp32 head maps
+            nbytes = R * cfg.O * 2 * 2 + R * (3 + 2 * cfg.z) * 4
+            ms = prof["conv2_heads"][0] / prof["conv2_heads"][1]
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            others["conv2_heads"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                     "ms_per_launch": ms, "bytes_per_launch": nbytes}
+        roofline["others"] = others
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_batch or default_cpu_batch(cfg)

@@ -387,8 +387,14 @@ struct Conv1WgradHParams {
     int skip;                 // 1: skip position chunks that only meet zero padding
 };
 
-struct Conv1WgradH : PolicyBase {
+// B128 = true (O % 64 == 0): dX1 is staged in 64-column blocks with the 128 B swizzle (tmQ from make_tmap_3d_mn128_h, p.nb
+// counts 64-column blocks per box); false: 32-column blocks / 64 B swizzle.
+template <bool B128>
+struct Conv1WgradHT : PolicyBase {
     static constexpr const char* kName = "conv1_wgrad";
+    static constexpr bool kBSw128MN = B128;
+    static constexpr int kBlkCols = B128 ? 64 : 32;            // columns per staged block
+    static constexpr int kBoxes = 128 / kBlkCols;              // blocks per 128-column accumulator half
     using Params = Conv1WgradHParams;
     static constexpr bool kF16 = true;
     // both operands fp16 (the tensor core rejects mixed fp16 x bf16 operands: illegal instruction).  dX1 is stored
@@ -411,7 +417,7 @@ struct Conv1WgradH : PolicyBase {
         ChunkWalk w;
         int row0;             // first dX1 row of the current chunk for rotation 0: b*G*P + (lo + rel)*64
         int rterm[kAcc][4];   // r*P per box (or a far out-of-bounds row when r >= G: TMA zero-fills)
-        int oblk[kAcc][4];    // first o-block of the box
+        int oblk[kAcc][4];    // first o-block (of kBlkCols columns) of the box
     };
     struct GenState {
         int b, m_tile;        // image / kk-tile whose slab + table are resident
@@ -465,22 +471,22 @@ struct Conv1WgradH : PolicyBase {
         for (int a = 0; a < kAcc; ++a) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                const int np = ti.n0 + a * kAccN + static_cast<int>(rank) * 128 + x * 32 * p.nb;
+                const int np = ti.n0 + a * kAccN + static_cast<int>(rank) * 128 + x * kBlkCols * p.nb;
                 const int r = np / g.O, o0 = np - r * g.O;
                 s.rterm[a][x] = (r < g.G) ? r * g.P : 0x30000000;
-                s.oblk[a][x] = o0 >> 5;
+                s.oblk[a][x] = o0 / kBlkCols;
             }
         }
     }
     __device__ static void tma_chunk(const Params& p, const PairTile& ti, TmaState& s, uint32_t sb, uint32_t bar) {
-        const int nbx = 4 / p.nb;
+        const int nbx = kBoxes / p.nb;
 #pragma unroll
         for (int a = 0; a < kAcc; ++a) {
             if (a < ti.n_acc) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
                     if (x < nbx)
-                        tma_load_3d_pair(sb + a * kBHalfBytes + x * p.nb * (kBK16 * 64), &p.tmQ, bar, 0, s.row0 + s.rterm[a][x], s.oblk[a][x]);
+                        tma_load_3d_pair(sb + a * kBHalfBytes + x * p.nb * (kBK16 * kBlkCols * 2), &p.tmQ, bar, 0, s.row0 + s.rterm[a][x], s.oblk[a][x]);
             }
         }
         s.row0 += kBK16;
@@ -614,5 +620,8 @@ struct Conv1WgradH : PolicyBase {
         }
     }
 };
+
+using Conv1WgradH = Conv1WgradHT<false>;
+using Conv1WgradH128 = Conv1WgradHT<true>;
 
 }  // namespace tvae

@@ -96,6 +96,23 @@ inline int make_tmap_3d_mn_h(CUtensorMap* tm, const void* ptr, uint64_t rows, ui
     return 0;
 }
 
+// Same view in 64-column blocks (cols % 64 == 0): 3-D map {64 cols, rows, cols/64}, boxes {64, box_rows, nb}: nb consecutive
+// [box_rows][128 B] column blocks in the 128 B swizzle (the MN-major layout the tensor core fetches with full 128-byte rows).
+inline int make_tmap_3d_mn128_h(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t nb) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15) || (cols & 63)) return fail(-1, "TMA operand must be 16-byte aligned with whole 64-column blocks");
+    cuuint64_t dims[3] = {64, rows, cols / 64};
+    cuuint64_t strides[2] = {ld * 2, 64 * 2};
+    cuuint32_t box[3] = {64, box_rows, nb};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (3-D, 16-bit, 128 B blocks) failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // Store view of a 16-bit activation tensor [outer][rows][cols] (cols contiguous): boxes {64 cols (128 B), box_rows, 1},
 // 128 B swizzle; rows >= `rows` of a box are clipped by the TMA unit (ragged last tile of an image).
 inline int make_tmap_3d_store_h(CUtensorMap* tm, void* ptr, uint64_t outer, uint64_t rows, uint64_t cols, uint32_t box_rows) {

@@ -245,6 +245,7 @@ struct PolicyBase {
     static constexpr int kProdWarps = 0;
     static constexpr int kEpiGroups = 1;      // tc_gemm: epilogue warpgroups taking alternate tiles
     static constexpr int kMaxAccStages = 4;   // tc_gemm: upper bound on the TMEM accumulator stages
+    static constexpr bool kBSw128MN = false;  // tc_gemm2: MN-major B staged in 64-column blocks / 128 B swizzle instead of 32-column / 64 B
     static constexpr int kBResidentChunks = 0;   // tc_gemm: > 0 = B has this many K chunks, identical for every tile, kept in smem
     static constexpr bool kEpiSelfRelease = false;   // tc_gemm: the policy's epilogue arrives on EpiState::tempty itself
     static constexpr uint32_t kAFmt = 0;      // operand formats of kind::f16: 0 = FP16, 1 = BF16 (both operands must agree)

@@ -205,7 +205,8 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                             const uint32_t bb = b_addr + a * kBHalfBytes;
                             if (P::kAMajorMN) adesc = make_smem_desc(a_addr + ks * 2048, 64 * 128, 1024, kLayoutSw128);
                             else              adesc = make_smem_desc(a_addr + ks * 32, 16, 1024, kLayoutSw128);
-                            if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, 64 * 64, 512, kLayoutSw64);
+                            if (P::kBMajorMN && P::kBSw128MN) bdesc = make_smem_desc(bb + ks * 2048, 64 * 128, 1024, kLayoutSw128);
+                            else if (P::kBMajorMN) bdesc = make_smem_desc(bb + ks * 1024, 64 * 64, 512, kLayoutSw64);
                             else              bdesc = make_smem_desc(bb + ks * 32, 16, 1024, kLayoutSw128);
                             umma_f16_pair(tmem_base + a * kAccN, adesc, bdesc, kIdesc, (q > ti.kc_begin || ks > 0) ? 1u : 0u);
                         }

@@ -7,6 +7,7 @@
 #include "ctf_policies.cuh"
 #include "gen_policies.cuh"
 #include "gen_pair_policies.cuh"
+#include "enc_bwd_fused.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
 #include "simt_kernels.cuh"
@@ -238,9 +239,15 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
     const int N = g.G * g.O;
     const long long R = (long long)g.B * g.G * g.P;
     int rc;
-    const int oblocks = g.O / 32;
-    p.nb = (oblocks % 4 == 0) ? 4 : (oblocks % 2 == 0 ? 2 : 1);   // 128 accumulator columns = 4 / nb boxes of nb o-blocks
-    if ((rc = make_tmap_3d_mn_h(&p.tmQ, dx1_16, R, g.O, g.O, kBK16, p.nb))) return rc;
+    const bool b128 = g.O % 64 == 0;     // dX1 staged in 64-column blocks / 128 B swizzle (full 128-byte operand rows)
+    if (b128) {
+        p.nb = (g.O % 128 == 0) ? 2 : 1;                              // 128 accumulator columns = 2 / nb boxes of nb 64-column blocks
+        if ((rc = make_tmap_3d_mn128_h(&p.tmQ, dx1_16, R, g.O, g.O, kBK16, p.nb))) return rc;
+    } else {
+        const int oblocks = g.O / 32;
+        p.nb = (oblocks % 4 == 0) ? 4 : (oblocks % 2 == 0 ? 2 : 1);   // 128 accumulator columns = 4 / nb boxes of nb o-blocks
+        if ((rc = make_tmap_3d_mn_h(&p.tmQ, dx1_16, R, g.O, g.O, kBK16, p.nb))) return rc;
+    }
     p.g = g; p.y = y; p.dbank = dbank; p.acc_scale = acc_scale;
     p.m_tiles = cdiv(g.K, kBM);
     p.m_pairs = cdiv(p.m_tiles, 2);
@@ -277,7 +284,7 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
     p.splits = cdiv(p.chunks_total, best_cps);
     p.num_tiles = out_tiles * p.splits;
     p.skip = 1;
-    return launch_gemm2<Conv1WgradH>(p, extra, st);
+    return b128 ? launch_gemm2<Conv1WgradH128>(p, extra, st) : launch_gemm2<Conv1WgradH>(p, extra, st);
 }
 // conv1 bias gradient slot: column K of dbank row (r = 0, o)  (summed over r by tvae_filter_bank_bwd)
 inline float* bias_grad_slot(const ConvGeom& g, float* dbank) { return dbank + g.K; }
@@ -433,10 +440,34 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         else rc = launch_thin_bwd<kMaxHeads + 1, 1, true, true>(p, g.G, st);
         if (rc) return rc;
     }
+    ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
+    if (g.O == 128) {
+        // ---- one pass over dhpre and x1: dW2 = dhpre^T x1, dx1pre = (dhpre W2) * lrelu'(x1) (fp16 * s2) and its column
+        // sums (the conv1 bias gradient)   (enc_bwd_fused.cuh)
+        EncDx1Dw2Params q{};
+        if ((rc = make_tmap_2d_h(&q.tmA, a->dhpre, R, 128, 128, kBM))) return rc;
+        if ((rc = make_tmap_2d_h(&q.tmX, a->x1, R, 128, 128, kBM))) return rc;
+        if ((rc = make_tmap_2d_h(&q.tmW, a->w2t_h, 128, 128, 128, 128))) return rc;
+        if ((rc = make_tmap_2d_h(&q.tmC, a->dx1_16, R, 128, 128, kBM))) return rc;
+        q.R = R; q.num_tiles = static_cast<int>(cdiv(R, kBM));
+        q.acc_scale = a->scales + 1; q.store_scale = a->scales + 2;
+        q.colsum = bias_grad_slot(g, a->dbank); q.colsum_stride = g.kpad;
+        q.dw2 = a->dw2;
+        static bool configured = false;
+        if (!configured) {
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_dx1_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
+            configured = true;
+        }
+        const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
+        ++g_launch_count;
+        const int tslot = g_timer.begin("enc_dx1_dw2", st);
+        enc_dx1_dw2_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(q);
+        g_timer.end(tslot, st);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    } else {
     // ---- dW2 = dhpre^T x1   (fp16 x fp16, accumulators carry s1)
     if ((rc = linear_tn(a->dhpre, g.O, a->x1, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st, a->scales + 1))) return rc;
     // ---- dx1pre = (dhpre W2) * lrelu'(x1), stored fp16 * s2; its column sums are the conv1 bias gradient
-    ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
     {
         LinearNTArgs l{};
         l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_h; l.ldb = g.O;
@@ -445,6 +476,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         l.acc_scale = a->scales + 1; l.store_scale = a->scales + 2;
         l.colsum = bias_grad_slot(g, a->dbank); l.colsum_stride = g.kpad;
         if ((rc = linear_nt(l, st))) return rc;
+    }
     }
     // ---- conv1 weight gradient (w.r.t. the rotated bank)
     return conv1_wgrad(g, a->y, a->dx1_16, a->scales + 3, a->dbank, st);
