@@ -12,7 +12,7 @@ template <class P>
 inline int pick_stages(int extra_bytes) {
     const int per_stage = kAStageBytes + (P::kBResidentChunks > 0 ? 0 : P::kBN * 128);   // a resident B is part of the fixed layout
     const SmemLayout L0 = make_smem_layout<P>(0, extra_bytes);
-    int s = (kMaxSmemBytes - static_cast<int>(L0.total) - 1024) / per_stage;
+    int s = (kMaxSmemBytes - static_cast<int>(L0.total)) / per_stage;     // 227 KB is the opt-in maximum itself: no further margin
     if (s > kMaxStages) s = kMaxStages;
     return s;
 }
