@@ -279,6 +279,8 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default: keep stdout for the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or cfg.batch
     gen, enc = build_models(cfg, dev)

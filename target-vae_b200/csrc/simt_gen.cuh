@@ -36,12 +36,14 @@ __global__ void latent_bias_bwd_kernel(const float* __restrict__ dzb, const floa
 
 // No Fourier expansion (cfg2): a0[m][j] = LeakyReLU(x'0 W1[j][0] + x'1 W1[j][1] + b1[j] + zb[b][j]), stored fp16.
 // CTA = kCoordRB rows; the transformed coordinates of the block are computed once into shared memory, then
-// thread = 4 adjacent columns x one row slot streams float4 stores (HBM-bound: one write of a0).
+// thread = VEC adjacent columns x one row slot streams 16-byte (VEC = 8) or 8-byte (VEC = 4) stores (HBM-bound: one
+// write of a0).
 constexpr int kCoordRB = 64;
+template <int VEC>
 __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
                                                               const float* __restrict__ zb, __half* __restrict__ a0, int H) {
     __shared__ float2 s_x[kCoordRB];
-    const int cgs = H / 4, rpp = blockDim.x / cgs;
+    const int cgs = H / VEC, rpp = blockDim.x / cgs;
     const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
     const long long m0 = (long long)blockIdx.x * kCoordRB;
     if (threadIdx.x < kCoordRB) {
@@ -49,22 +51,29 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
         transformed_coord(cx, m0 + threadIdx.x, x0, x1);
         s_x[threadIdx.x] = make_float2(x0, x1);
     }
-    const int c0 = cg * 4;
-    float wx[4], wy[4], bb[4];
+    const int c0 = cg * VEC;
+    float wx[VEC], wy[VEC], bb[VEC];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; bb[v] = b1[c0 + v]; }
+    for (int v = 0; v < VEC; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; bb[v] = b1[c0 + v]; }
     __syncthreads();
     const int rows = static_cast<int>(min((long long)kCoordRB, cx.M - m0));
     for (int rr = rs; rr < rows; rr += rpp) {
         const long long m = m0 + rr;
         const float2 x = s_x[rr];
-        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0));
-        const float o0 = lrelu(fmaf(x.y, wy[0], fmaf(x.x, wx[0], bb[0])) + z4.x);
-        const float o1 = lrelu(fmaf(x.y, wy[1], fmaf(x.x, wx[1], bb[1])) + z4.y);
-        const float o2 = lrelu(fmaf(x.y, wy[2], fmaf(x.x, wx[2], bb[2])) + z4.z);
-        const float o3 = lrelu(fmaf(x.y, wy[3], fmaf(x.x, wx[3], bb[3])) + z4.w);
-        *reinterpret_cast<uint2*>(a0 + m * H + c0) = make_uint2(pack_half2(o0, o1), pack_half2(o2, o3));
+        float o[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0 + q));
+            o[q] = lrelu(fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x);
+            o[q + 1] = lrelu(fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y);
+            o[q + 2] = lrelu(fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z);
+            o[q + 3] = lrelu(fmaf(x.y, wy[q + 3], fmaf(x.x, wx[q + 3], bb[q + 3])) + z4.w);
+        }
+        if constexpr (VEC == 8)
+            *reinterpret_cast<uint4*>(a0 + m * H + c0) = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+        else
+            *reinterpret_cast<uint2*>(a0 + m * H + c0) = make_uint2(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]));
     }
 }
 // backward of the above in one pass over dpre:  dW1[j][0..1] += sum_m dpre[m][j] x'[m]  and

@@ -615,8 +615,14 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         if (rc) return rc;
         }
     } else {
-        const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
-        ++g_launch_count; coord_layer_fwd_kernel<<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+        ++g_launch_count;
+        if (H % 8 == 0 && H / 8 <= 256) {          // 16-byte stores
+            const int cgs = H / 8, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
+            coord_layer_fwd_kernel<8><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+        } else {
+            const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
+            coord_layer_fwd_kernel<4><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+        }
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
     if (s->L == 0) {
