@@ -7,10 +7,10 @@
 #include "ctf_policies.cuh"
 #include "gen_policies.cuh"
 #include "gen_pair_policies.cuh"
-#include "enc_bwd_fused.cuh"
 #include "launch.cuh"
 #include "simt_gen.cuh"
 #include "simt_kernels.cuh"
+#include "enc_bwd_fused.cuh"
 
 using namespace tvae;
 
@@ -427,7 +427,28 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         ++g_launch_count; enc_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 7, a->wh, NH, a->w2, g.O, a->scales);
     }
     // ---- heads backward: dhpre = (d_heads . Wh) * lrelu'(h), stored fp16 * s1; dWh, dbh, db2
-    {
+    if (g.O == 128 && NH <= 32) {
+        // tensor-core streaming kernel (enc_bwd_fused.cuh): one read of h and d_heads, one write of dhpre
+        EncHeadsBwdParams q{};
+        if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, 128, 128, kBM))) return rc;
+        if ((rc = make_tmap_2d_h(&q.tmC, a->dhpre, R, 128, 128, kBM))) return rc;
+        q.R = R; q.num_tiles = static_cast<int>(cdiv(R, kBM)); q.NH = NH; q.G = g.G; q.P = g.P;
+        q.d_heads = a->d_heads; q.wh = a->wh; q.store_scale = a->scales + 0;
+        q.dwh = a->dwh; q.dbh = a->dbh; q.db2 = a->db2;
+        const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
+        static bool configured = false;
+        if (!configured) {
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_heads_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHbSmemBytes));
+            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_heads_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHbSmemBytes));
+            configured = true;
+        }
+        ++g_launch_count;
+        const int tslot = g_timer.begin("enc_heads_bwd", st);
+        if (NH <= 16) enc_heads_bwd_kernel<16><<<grid, kHbThreads, kHbSmemBytes, st>>>(q);
+        else enc_heads_bwd_kernel<32><<<grid, kHbThreads, kHbSmemBytes, st>>>(q);
+        g_timer.end(tslot, st);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+    } else {
         ThinBwdParams p{};
         p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
         p.store_scale = a->scales + 0;
