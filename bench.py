@@ -429,6 +429,15 @@ def run_ours(args, cfg):
                     "share_of_step": prof[dom][0] / ms_total,
                     "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
 
+    # count-based tensor-pipe utilisation of the dominant kernel: executed MMA flop / (SMs x 8192 flop/clk x sampled SM clock)
+    if roofline is not None:
+        cs = clk.summary()
+        if cs and cs.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            hw_peak = sms * 8192 * cs["sm_mhz"] * 1e6 / 1e12
+            roofline["tensor_pipe_util_est"] = roofline["achieved_executed"] / hw_peak
+            roofline["tensor_pipe_util_how"] = (f"executed TFLOP/s / ({sms} SMs x 8192 flop/clk x {cs['sm_mhz']:.0f} MHz sampled under load "
+                                                f"= {hw_peak:.0f} TFLOP/s); ncu cycle-based figure in profiles/r01_ncu_step_cfg2_final.md")
     # per-kernel rooflines of the other event-timed kernels (explanatory; the contract's `roofline` is the dominant one)
     if roofline is not None:
         hbm_peak = float(peaks.get("hbm_gbs", 6560.0))
