@@ -38,19 +38,22 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._pending: List = [None, None]
+        # NCCL averages inside the collective (no separate scaling kernel); gloo (CPU tests) only sums
+        self._avg = dist.is_initialized() and self.world > 1 and dist.get_backend(group) == "nccl"
 
     def start(self, bucket: int, grads: Sequence[torch.Tensor]):
         flat = torch.cat([g.reshape(-1) for g in grads])
         work = None
         if self.world > 1:
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending[bucket] = (flat, work, [g.shape for g in grads])
 
     def _resolve(self, bucket: int):
         flat, work, shapes = self._pending[bucket]
         if work is not None:
             work.wait()
-            flat.mul_(1.0 / self.world)
+            if not self._avg:
+                flat.mul_(1.0 / self.world)
         out, off = [], 0
         for sh in shapes:
             n = 1
