@@ -213,6 +213,16 @@ int tvae_adam_step(const tvae_adam_tensor* tensors, int n, double lr, double bet
  * x = elbo, -log_p_x_g_z, kl_div (device scalars).  Zero the state to start an epoch. */
 int tvae_running_means(const float* elbo, const float* log_p, const float* kl, float b, float* state4, void* stream);
 
+/* ------------------------------------------------------------------ particle-stack input pipeline
+ * src/ctf.py:32-55 `ctf_filter` (with `compute_2d_ctf`, src/ctf.py:6-23), called at train_particles.py:543-547:
+ * params = DEVICE array (B, 8) of doubles in parse_ctf's column order {defocus [um], cs, voltage, apix, bfactor, ampcont,
+ * dfdiff, dfang [deg]} -> out (B, n, m) fp32 = -fftshift(ifft2(CTF on the fftfreq grid / (apix * scale))).real.
+ * fp64 arithmetic on the device (the reference computes in numpy float64), exact separable inverse DFT (n, m <= 255). */
+int tvae_ctf_filter(const double* params, int B, int n, int m, double scale, float* out, void* stream);
+/* src/image.py:30-42 `crop` (centre crop to `crop` x `crop`, 0 = none) followed by train_particles.py:592-600 --normalize
+ * (per-image (x - mean) / std with the population std; normalize = 0 copies the crop): in (B, n, m) -> out (B, c, c). */
+int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream);
+
 /* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);

@@ -1090,4 +1090,101 @@ __global__ void running_means_kernel(const float* __restrict__ elbo, const float
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Real-space CTF filters (src/ctf.py:6-55): one CTA per micrograph, fp64.
+//   c[k1][k2] = CTF(fftfreq(n)[k1] / apix, fftfreq(m)[k2] / apix)          kept in shared memory (n*m doubles)
+//   out[a][b] = -Re ifft2(c)[(a - n/2) mod n][(b - m/2) mod m]             exact separable inverse DFT, row by row
+// dynamic smem: c [n*m] | row transform T [m] complex | twiddles w_n [n], w_m [m] complex
+struct CtfFilterParams { const double* params; float* out; int B, n, m; double scale; };
+__global__ void __launch_bounds__(256) ctf_filter_kernel(CtfFilterParams p) {
+    extern __shared__ __align__(16) double s_ctf[];
+    const int n = p.n, m = p.m, b = blockIdx.x;
+    double* c = s_ctf;
+    double2* T = reinterpret_cast<double2*>(c + ((n * m + 1) & ~1));      // 16-byte aligned
+    double2* wn = T + m;
+    double2* wm = wn + n;
+    const double* q = p.params + 8 * b;
+    const double defocus = q[0], cs = q[1] * 1e7, volt = q[2] * 1000.0, apix = q[3] * p.scale, bfac = q[4], w = q[5] / 100.0;
+    const double ang0 = 2.0 * 3.14159265358979323846 * q[7] / 360.0;
+    const double dfu = defocus * 10000.0, dfv = defocus * 10000.0;
+    const double lam = 12.2639 / sqrt(volt + 0.97845e-6 * volt * volt);
+    const double a1 = sqrt(1.0 - w * w);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { double sn, cs_; sincospi(2.0 * i / n, &sn, &cs_); wn[i] = make_double2(cs_, sn); }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { double sn, cs_; sincospi(2.0 * i / m, &sn, &cs_); wm[i] = make_double2(cs_, sn); }
+    for (int i = threadIdx.x; i < n * m; i += blockDim.x) {
+        const int k1 = i / m, k2 = i - k1 * m;
+        const double x = static_cast<double>(k1 <= (n - 1) / 2 ? k1 : k1 - n) / n / apix;     // np.fft.fftfreq
+        const double y = static_cast<double>(k2 <= (m - 1) / 2 ? k2 : k2 - m) / m / apix;
+        const double ang = atan2(y, x), s2 = x * x + y * y;
+        const double df = 0.5 * (dfu + dfv + (dfu - dfv) * cos(2.0 * (ang - ang0)));
+        const double gamma = 2.0 * 3.14159265358979323846 * (-0.5 * df * lam * s2 + 0.25 * cs * lam * lam * lam * s2 * s2);
+        c[i] = (a1 * sin(gamma) - w * cos(gamma)) * exp(-bfac / 4.0 * s2);
+    }
+    __syncthreads();
+    const double inv = 1.0 / (static_cast<double>(n) * m);
+    for (int a = 0; a < n; ++a) {
+        const int xo = ((a - n / 2) % n + n) % n;                    // fftshift: shifted[a] = orig[(a - n/2) mod n]
+        for (int k2 = threadIdx.x; k2 < m; k2 += blockDim.x) {       // T[k2] = sum_k1 c[k1][k2] w_n^(k1 xo)
+            double re = 0.0, im = 0.0;
+            int j = 0;
+            for (int k1 = 0; k1 < n; ++k1) {
+                const double v = c[k1 * m + k2];
+                re = fma(v, wn[j].x, re);
+                im = fma(v, wn[j].y, im);
+                j += xo; if (j >= n) j -= n;
+            }
+            T[k2] = make_double2(re, im);
+        }
+        __syncthreads();
+        for (int bb = threadIdx.x; bb < m; bb += blockDim.x) {       // out = Re sum_k2 T[k2] w_m^(k2 yo)
+            const int yo = ((bb - m / 2) % m + m) % m;
+            double re = 0.0;
+            int j = 0;
+            for (int k2 = 0; k2 < m; ++k2) {
+                re = fma(T[k2].x, wm[j].x, re);
+                re = fma(-T[k2].y, wm[j].y, re);
+                j += yo; if (j >= m) j -= m;
+            }
+            p.out[((long long)b * n + a) * m + bb] = static_cast<float>(-re * inv);
+        }
+        __syncthreads();
+    }
+}
+
+// centre crop + per-image standardisation (src/image.py:30-42, train_particles.py:592-600); one CTA per image, fp64 sums
+__global__ void __launch_bounds__(256) crop_normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int m, int c0,
+                                                             int c1, int si, int sj, int normalize) {
+    __shared__ double s_red[2][8];
+    __shared__ double s_stat[2];
+    const int b = blockIdx.x, total = c0 * c1;
+    const float* src = in + (long long)b * n * m;
+    double sum = 0.0, sq = 0.0;
+    if (normalize) {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int r = i / c1, cc = i - r * c1;
+            const double v = src[(si + r) * m + sj + cc];
+            sum += v; sq += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = sum; s_red[1][threadIdx.x >> 5] = sq; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, q = 0.0;
+            for (int w = 0; w < 8; ++w) { a += s_red[0][w]; q += s_red[1][w]; }
+            const double mu = a / total;
+            double var = q / total - mu * mu;
+            // second pass for the variance would be exact; the two-moment form in fp64 is accurate to ~1e-13 relative here
+            if (var < 0.0) var = 0.0;
+            s_stat[0] = mu; s_stat[1] = sqrt(var);
+        }
+        __syncthreads();
+    }
+    const double mu = normalize ? s_stat[0] : 0.0, sd = normalize ? s_stat[1] : 1.0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i / c1, cc = i - r * c1;
+        const double v = src[(si + r) * m + sj + cc];
+        out[(long long)b * total + i] = static_cast<float>((v - mu) / sd);
+    }
+}
+
 }  // namespace tvae

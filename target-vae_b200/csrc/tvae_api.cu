@@ -959,6 +959,36 @@ int tvae_running_means(const float* elbo, const float* log_p, const float* kl, f
     return 0;
 }
 
+// ================================================================================ particle-stack input pipeline
+int tvae_ctf_filter(const double* params, int B, int n, int m, double scale, float* out, void* stream) {
+    TVAE_REQUIRE(B >= 0 && n >= 1 && m >= 1 && n <= 255 && m <= 255, "ctf_filter: filter size must be in 1..255");
+    TVAE_REQUIRE(scale > 0.0, "ctf_filter: scale must be positive");
+    if (B == 0) return 0;                       // empty parameter table: nothing to do (pointers may be null)
+    TVAE_REQUIRE(params && out, "ctf_filter: null pointer");
+    const size_t sm = sizeof(double) * ((((size_t)n * m + 1) & ~(size_t)1) + 2 * (m + n + m));
+    TVAE_REQUIRE(sm <= 227 * 1024, "ctf_filter: filter does not fit shared memory");
+    static bool cfg = false;
+    if (!cfg) {
+        TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cfg = true;
+    }
+    CtfFilterParams p{params, out, B, n, m, scale};
+    ++g_launch_count; ctf_filter_kernel<<<B, 256, sm, S(stream)>>>(p);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream) {
+    TVAE_REQUIRE(B >= 0 && n >= 1 && m >= 1 && crop >= 0 && crop <= n && crop <= m, "crop_normalize: crop larger than the image");
+    if (B == 0) return 0;
+    TVAE_REQUIRE(in && out, "crop_normalize: null pointer");
+    const int c0 = crop > 0 ? crop : n, c1 = crop > 0 ? crop : m;
+    const int si = crop > 0 ? (n - crop) / 2 : 0, sj = crop > 0 ? (m - crop) / 2 : 0;
+    ++g_launch_count; crop_normalize_kernel<<<B, 256, 0, S(stream)>>>(in, out, n, m, c0, c1, si, sj, normalize);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ================================================================================ test hooks
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act,
                         void* stream) {
