@@ -6,7 +6,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 
 namespace tvae {
 
@@ -177,6 +180,21 @@ inline int sm_count() {
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per (kernel, device): remembered per pair so that
+// a process driving several GPUs configures every one of them (the library keeps no other mutable global state).
+inline cudaError_t smem_optin(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert({kernel, dev});
+    return e;
 }
 
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }

@@ -23,11 +23,7 @@ inline int launch_gemm(typename P::Params& prm, int extra_bytes, cudaStream_t st
     if (prm.num_stages < 2) return fail(-1, "tile does not fit shared memory with >= 2 stages");
     if (prm.num_tiles <= 0) return 0;
     const SmemLayout L = make_smem_layout<P>(prm.num_stages, extra_bytes);
-    static int configured = 0;  // per policy instantiation
-    if (configured < static_cast<int>(L.total)) {
-        TVAE_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-        configured = kMaxSmemBytes;
-    }
+    TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&tc_gemm_kernel<P>), kMaxSmemBytes));
     const int threads = (kCtrlWarps + kEpiWarps * P::kEpiGroups + P::kProdWarps) * 32;
     const int grid = prm.num_tiles < sm_count() ? prm.num_tiles : sm_count();
     ++g_launch_count;
@@ -51,11 +47,7 @@ inline int launch_gemm2(typename P::Params& prm, int extra_bytes, cudaStream_t s
     if (prm.num_stages < 2) return fail(-1, "pair tile does not fit shared memory with >= 2 stages");
     if (prm.num_tiles <= 0) return 0;
     const Smem2Layout L = make_smem2_layout(prm.num_stages, extra_bytes);
-    static bool configured = false;  // per policy instantiation
-    if (!configured) {
-        TVAE_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-        configured = true;
-    }
+    TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&tc_gemm2_kernel<P>), kMaxSmemBytes));
     const int pairs_dev = sm_count() / 2;
     const int pairs = force_pairs > 0 ? force_pairs : (prm.num_tiles < pairs_dev ? prm.num_tiles : pairs_dev);
     ++g_launch_count;

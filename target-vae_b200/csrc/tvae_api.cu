@@ -67,11 +67,7 @@ int launch_thin_bwd_mma(ThinBwdParams& p, int G, cudaStream_t st) {
     const int n_red = (p.T + 1) * 128 + p.T;
     const size_t sm = sizeof(float) * ((n_red + 3) & ~3) + TT * 16 * 32 * 8 + kThinBufs * (((kThinRB * p.T + 3) & ~3) * 4 + kThinRB * kThinPitch * 2);
     if (sm > 48 * 1024) {
-        static bool cfg = false;
-        if (!cfg) {
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(thin_bwd_mma_kernel<PLANAR, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            cfg = true;
-        }
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&thin_bwd_mma_kernel<PLANAR, TT>), 100 * 1024));
     }
     TVAE_REQUIRE(sm <= 100 * 1024, "thin backward (mma): shared memory");
     ++g_launch_count;
@@ -436,12 +432,8 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         q.d_heads = a->d_heads; q.wh = a->wh; q.store_scale = a->scales + 0;
         q.dwh = a->dwh; q.dbh = a->dbh; q.db2 = a->db2;
         const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
-        static bool configured = false;
-        if (!configured) {
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_heads_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHbSmemBytes));
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_heads_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHbSmemBytes));
-            configured = true;
-        }
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&enc_heads_bwd_kernel<16>), kHbSmemBytes));
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&enc_heads_bwd_kernel<32>), kHbSmemBytes));
         ++g_launch_count;
         const int tslot = g_timer.begin("enc_heads_bwd", st);
         if (NH <= 16) enc_heads_bwd_kernel<16><<<grid, kHbThreads, kHbSmemBytes, st>>>(q);
@@ -474,11 +466,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         q.acc_scale = a->scales + 1; q.store_scale = a->scales + 2;
         q.colsum = bias_grad_slot(g, a->dbank); q.colsum_stride = g.kpad;
         q.dw2 = a->dw2;
-        static bool configured = false;
-        if (!configured) {
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(enc_dx1_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes));
-            configured = true;
-        }
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&enc_dx1_dw2_kernel), kFuSmemBytes));
         const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
         ++g_launch_count;
         const int tslot = g_timer.begin("enc_dx1_dw2", st);
@@ -887,12 +875,8 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
         mu_in = mu;
     } else if (ctf) {
         TVAE_REQUIRE(sm <= 227 * 1024, "gaussian: CTF window does not fit shared memory");
-        static bool cfg = false;
-        if (!cfg) {
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            cfg = true;
-        }
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&ctf_apply_kernel<false>), 227 * 1024));
+        TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&ctf_apply_kernel<true>), 227 * 1024));
         if (y_hat) { ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n); }
         mu_in = mu;
     }
@@ -967,11 +951,7 @@ int tvae_ctf_filter(const double* params, int B, int n, int m, double scale, flo
     TVAE_REQUIRE(params && out, "ctf_filter: null pointer");
     const size_t sm = sizeof(double) * ((((size_t)n * m + 1) & ~(size_t)1) + 2 * (m + n + m));
     TVAE_REQUIRE(sm <= 227 * 1024, "ctf_filter: filter does not fit shared memory");
-    static bool cfg = false;
-    if (!cfg) {
-        TVAE_CHECK_CUDA(cudaFuncSetAttribute(ctf_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        cfg = true;
-    }
+    TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&ctf_filter_kernel), 227 * 1024));
     CtfFilterParams p{params, out, B, n, m, scale};
     ++g_launch_count; ctf_filter_kernel<<<B, 256, sm, S(stream)>>>(p);
     TVAE_CHECK_CUDA(cudaGetLastError());
