@@ -129,7 +129,16 @@ def _reference_step_fn(cfg, B):
     saved = list(sys.path)
     sys.path[:] = [REF_DIR] + [p for p in sys.path if os.path.abspath(p or ".") != PKG]
     try:
+        # torchvision's import registers fake kernels through torch.library, which walks sys.modules with
+        # inspect.getmodule(); the reference's `src` has no __init__.py, i.e. it is a namespace package whose
+        # __file__ is None on Python 3.12, and inspect.getfile() raises on that.  Import torchvision first and give
+        # the namespace module a path so that later scans (any lazy torch.library registration) are safe too.
+        with contextlib.suppress(ImportError):
+            importlib.import_module("torchvision")
         ref_models = importlib.import_module("src.models")
+        ref_src = sys.modules["src"]
+        if getattr(ref_src, "__file__", None) is None:
+            ref_src.__file__ = os.path.join(REF_DIR, "src", "__init__.py")
         trainer = importlib.import_module(name)
     finally:
         sys.path[:] = saved
@@ -163,7 +172,7 @@ def _reference_step_fn(cfg, B):
     return step
 
 
-def cpu_reference_images_per_s(cfg, B, steps, warmup, budget_s=12.0):
+def cpu_reference_images_per_s(cfg, B, steps, warmup, budget_s=8.0):
     """The reference's CPU path on the host cores: the unmodified reference from baseline/_ref when installed
     (kind "reference"), else the oracle port of eval_minibatch + backward (kind "port").  All usable threads.
     The sample is bounded: a 2-image probe step estimates the per-image cost and the batch is cut so that one step
@@ -172,19 +181,36 @@ def cpu_reference_images_per_s(cfg, B, steps, warmup, budget_s=12.0):
     torch.set_num_threads(threads)
 
     def make(Bx):
-        step = _reference_step_fn(cfg, Bx)
+        try:
+            step = _reference_step_fn(cfg, Bx)
+        except Exception as e:   # a broken reference install must not take the bench line down: time the port instead
+            print(f"[bench] reference import failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+            step = None
         if step is not None:
             return step, "reference"
         from helpers import oracle_step
         return (lambda: oracle_step(cfg, Bx, dtype=torch.float32)), "port"
 
-    probe, kind = make(min(2, B))
+    # Size the sample on the machine it runs on.  The cost per image is not linear in the batch on every host (on a
+    # GPU box a 16-image step took 59 s where the 2-image probe had predicted under 12 s), so the probe only gives a first guess and the batch is
+    # cut again whenever a whole step of the chosen size overshoots the budget.
+    nprobe = min(2, B)
+    probe, kind = make(nprobe)
+    probe()                                    # one-time costs (primitive creation, page faults) stay out of the estimate
     t0 = time.perf_counter()
     probe()
-    per_image = (time.perf_counter() - t0) / min(2, B)
-    B = max(1, min(B, int(budget_s / max(per_image, 1e-6))))
-    step, kind = make(B)
-    for _ in range(warmup):
+    per_image = (time.perf_counter() - t0) / nprobe
+    while True:
+        B = max(1, min(B, int(budget_s / max(per_image, 1e-6))))
+        step, kind = make(B)
+        t0 = time.perf_counter()
+        step()                                 # warm-up at the final size, timed
+        t_warm = time.perf_counter() - t0
+        if t_warm <= 1.5 * budget_s or B == 1:
+            break
+        per_image = t_warm / B
+        B -= 1
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -462,10 +488,13 @@ def run_ours(args, cfg):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_batch or default_cpu_batch(cfg)
-        ips, _, kind, threads, Bc = cpu_reference_images_per_s(cfg, Bc, 2, 1)
-        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"2 steps of {Bc} images (after 1 warm-up), {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
-                         f"(os.cpu_count() = {os.cpu_count()})"}
+        try:
+            ips, _, kind, threads, Bc = cpu_reference_images_per_s(cfg, Bc, 2, 1)
+            cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"2 steps of {Bc} images (after 1 warm-up), {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
+                             f"(os.cpu_count() = {os.cpu_count()})"}
+        except Exception as e:   # the GPU measurement above stands on its own
+            cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

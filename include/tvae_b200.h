@@ -194,6 +194,13 @@ long long tvae_gaussian_workspace_bytes(int B, int n);
 int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
                   float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream);
 
+/* Gaussian with a learned per-pixel variance (--fit-noise: train_particles.py:289-296, 333-334, 663-666; generator
+ * n_out = 2, no CTF, no mask - with either the reference itself fails for B > 1).  y_hat2 is the generator output
+ * (B, N, 2) read the way the reference reads it: flattened to (B, 2N), first N values = mean, last N = log-variance.
+ * ll[b] = -0.5 sum_e ((mu_e - y_e)^2 / exp(lv_e) + lv_e); d_yhat2 (same layout, may be NULL) = g * d ll_b / d y_hat2. */
+int tvae_gaussian_fit_noise(const float* y_hat2, const float* y, float* ll, float* d_yhat2, const float* g, int B, int N,
+                            void* stream);
+
 /* ------------------------------------------------------------------ optimiser step and running statistics
  * torch.optim.Adam(params, lr).step() [+ zero_grad()] of train_mnist.py:323-324,579 for ALL generator and encoder
  * parameters in ONE launch (the reference's optimiser launches several kernels per parameter tensor).  Arithmetic of

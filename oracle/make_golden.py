@@ -66,6 +66,9 @@ CASES = {
                                                      likelihood="gaussian", ctf=True, mask_radius=5), 2),
     "g6_mnist_noref": ("mnist", HotPathConfig("cfg1_gn", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=32,
                                               rot_refinement=False), 2),
+    # --fit-noise (train_particles.py:663-666): generator n_out = 2, learned per-pixel log-variance, no CTF / mask
+    "g7_particles_fitnoise": ("particles", HotPathConfig("cfg4_gf", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
+                                                         likelihood="gaussian", n_out=2), 3),
 }
 
 
@@ -164,7 +167,7 @@ def run_case(name, ref_models, trainers, clustering):
 def main():
     ref_models, trainers, clustering = _import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):     # optional case names: regenerate only those fixtures
         out = run_case(name, ref_models, trainers, clustering)
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **out)

@@ -511,6 +511,36 @@ __global__ void __launch_bounds__(256) gaussian_kernel(const float* __restrict__
     if (threadIdx.x == 0) atomicAdd(ll + b, -0.5f * acc[0]);
 }
 
+// Gaussian likelihood with a learned per-pixel variance (--fit-noise, train_particles.py:289-296, 333-334; no CTF and no
+// mask: with either, the reference's own tensor shapes no longer line up for B > 1).  The generator emits (B, N, 2); the
+// reference flattens that to (B, 2N) and takes the FIRST N values as the mean and the LAST N as the log-variance, so
+//   mu_e = f[b][e], lv_e = f[b][N + e]   (not the per-pixel pairs) - reproduced as is:
+//   ll[b] = -0.5 sum_e ((mu_e - y_e)^2 exp(-lv_e) + lv_e)
+//   d f[b][e] = -g (mu_e - y_e) exp(-lv_e),  d f[b][N + e] = 0.5 g ((mu_e - y_e)^2 exp(-lv_e) - 1),  g = dLoss/d(ll_b)
+// One CTA per image: deterministic ll[b].
+__global__ void __launch_bounds__(256) gaussian_fit_noise_kernel(const float* __restrict__ f, const float* __restrict__ y, int N,
+                                                                 float* __restrict__ ll, float* __restrict__ d_f,
+                                                                 const float* __restrict__ g_ptr) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.x;
+    const float g = d_f ? __ldg(g_ptr) : 0.f;
+    const float* fb = f + (long long)b * 2 * N;
+    const float* yb = y + (long long)b * N;
+    float acc[1] = {0.f};
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        const float lv = fb[N + e];
+        const float diff = fb[e] - yb[e];
+        const float w = diff * expf(-lv);       // (mu - y) / var
+        acc[0] += fmaf(diff, w, lv);
+        if (d_f) {
+            d_f[(long long)b * 2 * N + e] = -g * w;
+            d_f[(long long)b * 2 * N + N + e] = 0.5f * g * (diff * w - 1.f);
+        }
+    }
+    block_reduce<1, false>(acc, scratch);
+    if (threadIdx.x == 0) ll[b] = -0.5f * acc[0];
+}
+
 // ------------------------------------------------------------------------------------------
 // Thin-layer backward.  A "thin" layer maps a wide activation a[m][W] to T outputs t[m][j] =
 // sum_c a[m][c] Wt[j][c] + bt[j]  (attention/theta/z heads: T = 3+2z; generator output layer: T = n_out).

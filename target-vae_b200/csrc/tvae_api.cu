@@ -899,6 +899,16 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
     return 0;
 }
 
+int tvae_gaussian_fit_noise(const float* y_hat2, const float* y, float* ll, float* d_yhat2, const float* g, int B, int N,
+                            void* stream) {
+    TVAE_REQUIRE(B >= 1 && N >= 1, "gaussian (fit-noise): empty batch");
+    TVAE_REQUIRE(y_hat2 && y && ll, "gaussian (fit-noise): null pointer");
+    TVAE_REQUIRE(!d_yhat2 || g, "gaussian (fit-noise): gradient requested without its scale");
+    ++g_launch_count; gaussian_fit_noise_kernel<<<B, 256, 0, S(stream)>>>(y_hat2, y, N, ll, d_yhat2, g);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ================================================================================ optimiser step
 int tvae_adam_step(const tvae_adam_tensor* tensors, int n, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int step, int zero_grad, void* stream) {

@@ -61,9 +61,18 @@ def eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, de
 
 def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, epoch, device,
                              theta_prior, groupconv, padding, mask_radius, noise=None, sync=None):
-    """train_particles signature; Gaussian likelihood, optional CTF and circular mask (no --fit-noise)."""
-    if generator_model.layers[-1].out_features != 1:
-        raise NotImplementedError("--fit-noise is not on the accelerated path (broken with CTF upstream, SURVEY §8 a-8)")
+    """train_particles signature; Gaussian likelihood with optional CTF and circular mask, or - generator n_out = 2,
+    the trainer's --fit-noise (train_particles.py:663-666) - with a learned per-pixel variance.  --fit-noise together
+    with a CTF or a mask is rejected: the reference's own shapes do not line up there for B > 1 (y_var becomes
+    (B*B, n*n) after the CTF convolution, :304-307; y_var[mask] flattens across the batch, :330-331)."""
+    n_out = generator_model.layers[-1].out_features
+    if n_out == 2:
+        if ctf is not None or int(mask_radius) > 0:
+            raise NotImplementedError("--fit-noise with --ctf-file or --mask-radius fails in the reference itself for "
+                                      "B > 1 (train_particles.py:304-307, 330-331); not reproduced")
+        return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "gaussian_fit_noise", 0, noise, sync)
+    if n_out != 1:
+        raise ValueError(f"eval_minibatch_particles: generator n_out must be 1 or 2 (--fit-noise), got {n_out}")
     if ctf is not None:
         ctf = ctf.to(device)
     return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync)

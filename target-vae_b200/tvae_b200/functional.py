@@ -186,7 +186,7 @@ def pixel_spacing(x_coord: torch.Tensor) -> float:
 class StepSpec:
     enc: EncoderSpec
     sigma: float
-    likelihood: str = "bernoulli"      # bernoulli | gaussian
+    likelihood: str = "bernoulli"      # bernoulli | gaussian | gaussian_fit_noise
     mask_radius: int = 0
     n_gen_hidden: int = 1
     # optional data-parallel gradient synchroniser (tvae_b200.dp.GradSync): bucket 0 (generator) is started as
@@ -227,6 +227,8 @@ class FusedStepFn(torch.autograd.Function):
         ctfc = None if ctf is None else ops.f32(ctf)
         if spec.likelihood == "bernoulli":
             ll, _ = ops.bernoulli(y_hat, yflat)
+        elif spec.likelihood == "gaussian_fit_noise":
+            ll, _ = ops.gaussian_fit_noise(y_hat, yflat)
         else:
             ll, _, mu = ops.gaussian(y_hat, yflat, n, ctfc, att["dx"], spacing, spec.mask_radius)
             ctx.mu = mu
@@ -255,6 +257,8 @@ class FusedStepFn(torch.autograd.Function):
         yflat = yc.reshape(B, -1)
         if spec.likelihood == "bernoulli":
             _, d_yhat = ops.bernoulli(y_hat, yflat, w_ll)
+        elif spec.likelihood == "gaussian_fit_noise":
+            _, d_yhat = ops.gaussian_fit_noise(y_hat, yflat, w_ll)
         else:
             _, d_yhat, _ = ops.gaussian(y_hat, yflat, s.n, ctfc if ctx.has_ctf else None, att["dx"], ctx.spacing,
                                         spec.mask_radius, w_ll, mu=ctx.mu)

@@ -87,8 +87,9 @@ def L():
         for name in ("tvae_filter_bank_fwd", "tvae_filter_bank_bwd", "tvae_encoder_fwd", "tvae_encoder_bwd",
                      "tvae_attn_log_prior", "tvae_attn_fwd", "tvae_attn_bwd", "tvae_attn_softmax_pair",
                      "tvae_get_latent", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
-                     "tvae_gaussian"):
+                     "tvae_gaussian", "tvae_gaussian_fit_noise"):
             getattr(lib, name).restype = c_int
+        lib.tvae_gaussian_fit_noise.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
         lib.tvae_gaussian.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
         lib.tvae_gaussian_workspace_bytes.restype = ctypes.c_longlong
@@ -372,6 +373,19 @@ def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None, u
                             _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
                             _p(g), B, n, _p(ws), stream_ptr().value), "tvae_gaussian")
     return ll, d, mu
+
+
+def gaussian_fit_noise(y_hat2, y, g=None):
+    """--fit-noise likelihood (train_particles.py:289-296, 333-334): y_hat2 (B*N, 2) generator output, y (B, N).
+    -> (ll (B), d_yhat2 or None).  The reference's flat-halves reading of the (B, N, 2) output is kept."""
+    B, N = y.shape[0], y.shape[1]
+    if y_hat2.numel() != 2 * B * N:
+        raise ValueError(f"gaussian_fit_noise: generator output has {y_hat2.numel()} values, expected {2 * B * N}")
+    ll = empty(B, device=y.device)
+    d = torch.empty_like(y_hat2) if g is not None else None
+    check(L().tvae_gaussian_fit_noise(_p(f32(y_hat2)), _p(f32(y)), _p(ll), _p(d), _p(g), B, N, stream_ptr().value),
+          "tvae_gaussian_fit_noise")
+    return ll, d
 
 
 # ----------------------------------------------------------------------------------------------- instrumentation

@@ -27,7 +27,8 @@ from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, HotPathConfig
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref"]
+GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
+          "g7_particles_fitnoise"]
 
 
 def build_models(cfg, seed=0, gain=1.0):

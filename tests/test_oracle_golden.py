@@ -10,7 +10,8 @@ import torch
 from helpers import load_golden, oracle_inputs, oracle_step, rel_err, step_config
 from oracle import target_vae_oracle as orc
 
-CASES = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref"]
+CASES = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
+          "g7_particles_fitnoise"]
 
 
 @pytest.mark.parametrize("name", CASES)
