@@ -66,6 +66,9 @@ CASES = {
                                                      likelihood="gaussian", ctf=True, mask_radius=5), 2),
     "g6_mnist_noref": ("mnist", HotPathConfig("cfg1_gn", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=32,
                                               rot_refinement=False), 2),
+    # --t-inf attention --r-inf unimodal --groupconv 0 (train_mnist.py:88-183, models.py:268-319): plain Conv2d encoder
+    "g8_mnist_attn_unimodal": ("mnist", HotPathConfig("cfg1_gu", C=1, n=16, k=16, p=8, G=1, z=2, O=32, hidden=64,
+                                                      rot_refinement=False, encoder="attn_unimodal"), 3),
     # --fit-noise (train_particles.py:663-666): generator n_out = 2, learned per-pixel log-variance, no CTF / mask
     "g7_particles_fitnoise": ("particles", HotPathConfig("cfg4_gf", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                          likelihood="gaussian", n_out=2), 3),
@@ -77,10 +80,15 @@ def build_reference_models(ref_models, cfg: HotPathConfig, seed=0):
         gen = ref_models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers,
                                           activation=nn.LeakyReLU, resid=False,
                                           fourier_expansion=cfg.fourier, sigma=cfg.sigma)
-        enc = ref_models.InferenceNetwork_AttentionTranslation_AttentionRotation(
-            cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
-            groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
-            normal_prior_over_r=cfg.normal_prior_over_r)
+        if cfg.encoder == "attn_unimodal":
+            assert cfg.k == cfg.n and cfg.p == cfg.n // 2 and cfg.G == 1
+            enc = ref_models.InferenceNetwork_AttentionTranslation_UnimodalRotation(
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, activation=nn.LeakyReLU, groupconv=0)
+        else:
+            enc = ref_models.InferenceNetwork_AttentionTranslation_AttentionRotation(
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+                groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
+                normal_prior_over_r=cfg.normal_prior_over_r)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()})
     enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg, seed).items()})
     return gen, enc
@@ -129,6 +137,9 @@ def run_case(name, ref_models, trainers, clustering):
     dev = torch.device("cpu")
     tm = trainers[trainer]
     r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+    unimodal = cfg.encoder == "attn_unimodal"
+    if unimodal:
+        r_inf = "unimodal"
     with SuppliedNoise(nz["gumbel"], nz["r_z"], nz["r_theta"]):
         if trainer == "particles":
             ctf = torch.from_numpy(data["ctf"]) if data["ctf"] is not None else None
@@ -149,13 +160,20 @@ def run_case(name, ref_models, trainers, clustering):
         out["grad.gen." + k] = p.grad.numpy().astype(np.float32)
     # encoder intermediates (module-interface contract, models.py:403) with the same Gumbel noise
     with torch.no_grad(), SuppliedNoise(nz["gumbel"], nz["r_z"], nz["r_theta"]):
-        attn, q, p_r, a_s, offs, theta, z = enc(y, dev)
-    out.update(attn=attn.numpy(), q_t_r=q.numpy(), p_r=p_r.numpy(), a_sampled=a_s.numpy(),
-               offsets=offs.numpy(), theta=theta.numpy(), z=z.numpy())
+        if unimodal:      # 4-tuple of models.py:319
+            attn, a_s, theta, z = enc(y, dev)
+            out.update(attn=attn.numpy(), a_sampled=a_s.numpy(), theta=theta.numpy(), z=z.numpy())
+        else:
+            attn, q, p_r, a_s, offs, theta, z = enc(y, dev)
+            out.update(attn=attn.numpy(), q_t_r=q.numpy(), p_r=p_r.numpy(), a_sampled=a_s.numpy(),
+                       offsets=offs.numpy(), theta=theta.numpy(), z=z.numpy())
     # rotated filter bank and group conv output (a-1, a-2)
     with torch.no_grad():
-        out["bank"] = enc.conv1.trans_filter(dev).numpy()
-        out["conv1_out"] = enc.conv1(y, dev).numpy()
+        if unimodal:
+            out["conv1_out"] = enc.conv1(y).numpy()
+        else:
+            out["bank"] = enc.conv1.trans_filter(dev).numpy()
+            out["conv1_out"] = enc.conv1(y, dev).numpy()
         zc, th, dx = clustering.get_latent(x, y, enc, "attention", r_inf, dev, cfg.n)
         out.update(latent_z=zc.numpy(), latent_theta=th.numpy(), latent_dx=dx.numpy())
         # generator alone on the untransformed grid (a-5, a-6)

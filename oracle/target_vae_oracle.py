@@ -204,6 +204,33 @@ def encoder_forward(y, p: EncoderParams, G: int, padding: int, rot_refinement: b
 
 
 # ----------------------------------------------------------------------------
+# f-4  InferenceNetwork_AttentionTranslation_UnimodalRotation, groupconv == 0 (models.py:281-287, 300-318):
+#      plain Conv2d(C, O, n, padding = n // 2) -> LeakyReLU -> 1x1 Conv2d -> LeakyReLU -> 1x1 heads.
+#      Weights keep the module's 4-D Conv2d shapes; the maps carry a rotation axis of size 1 so that the
+#      attention/attention code below (R = 1, no rotation prior, no offsets) restates
+#      train_mnist.py:88-183 as well.
+# ----------------------------------------------------------------------------
+def plainconv_head_maps(y, p: EncoderParams, padding: int):
+    x = F.leaky_relu(F.conv2d(y, p.conv1_w, p.conv1_b, padding=padding), LRELU_SLOPE).unsqueeze(2)
+    h = F.leaky_relu(_conv1x1(x, p.conv2_w, p.conv2_b), LRELU_SLOPE)
+    attn = _conv1x1(h, p.conv_a_w, p.conv_a_b).squeeze(1)     # (B,1,H',W')
+    theta = _conv1x1(h, p.conv_r_w, p.conv_r_b)               # (B,2,1,H',W')
+    z = _conv1x1(h, p.conv_z_w, p.conv_z_b)                   # (B,2z,1,H',W')
+    return attn, theta, z
+
+
+def plainconv_encoder_forward(y, p: EncoderParams, padding: int, gumbel: torch.Tensor):
+    """models.py:300-318 in the 7-tuple layout of encoder_forward: q_t = log_softmax(attn) is what
+    train_mnist.py:148 computes from the module's `attn`; p_r = 0 and offsets = 0 (one rotation, no prior)."""
+    dt = y.dtype
+    attn, theta, z = plainconv_head_maps(y, p, padding)
+    B = attn.shape[0]
+    q_t = F.log_softmax(attn.reshape(B, -1), dim=1).view_as(attn)
+    a_sampled = F.softmax(attn.reshape(B, -1) + gumbel.reshape(B, -1), dim=1).view_as(attn)
+    return attn, q_t, torch.zeros(1, 1, 1, dtype=dt), a_sampled, torch.zeros(1, dtype=dt), theta, z
+
+
+# ----------------------------------------------------------------------------
 # a-4  eval_minibatch, attention/attention(+offsets) branch
 #      (train_mnist.py:187-282, train_particles.py:186-280)
 # ----------------------------------------------------------------------------
@@ -424,14 +451,20 @@ class StepConfig:
     theta_prior: float = math.pi
     likelihood: str = "bernoulli"      # bernoulli | bernoulli_rgb | gaussian
     mask_radius: int = 0
+    encoder: str = "attn_attn"         # attn_attn (--r-inf attention[+offsets]) | attn_unimodal (--r-inf unimodal, --groupconv 0)
 
 
 def eval_minibatch(x_coord, y, enc: EncoderParams, gen: GeneratorParams, cfg: StepConfig,
                    gumbel, r_z, r_theta, ctf=None):
     """-> (elbo, log_p_x_g_z, kl_div) plus a dict of intermediates."""
-    enc_out = encoder_forward(y, enc, cfg.G, cfg.padding, cfg.rot_refinement,
-                              cfg.normal_prior_over_r, cfg.theta_prior, gumbel)
-    z_b, theta_b, dx, x_t, kl_div = attention_posterior(enc_out, x_coord, r_z, r_theta, cfg.G, cfg.G, cfg.theta_prior)
+    if cfg.encoder == "attn_unimodal":
+        # train_mnist.py:88-183: one rotation, N(0, theta_prior) prior on theta (:171)
+        enc_out = plainconv_encoder_forward(y, enc, cfg.padding, gumbel)
+        z_b, theta_b, dx, x_t, kl_div = attention_posterior(enc_out, x_coord, r_z, r_theta, 1, 0, cfg.theta_prior)
+    else:
+        enc_out = encoder_forward(y, enc, cfg.G, cfg.padding, cfg.rot_refinement,
+                                  cfg.normal_prior_over_r, cfg.theta_prior, gumbel)
+        z_b, theta_b, dx, x_t, kl_div = attention_posterior(enc_out, x_coord, r_z, r_theta, cfg.G, cfg.G, cfg.theta_prior)
     y_hat = generator_forward(x_t.contiguous(), z_b, gen)
     n = y.shape[-1]
     if cfg.likelihood == "bernoulli":
@@ -454,12 +487,15 @@ def eval_minibatch(x_coord, y, enc: EncoderParams, gen: GeneratorParams, cfg: St
 # a-10  get_latent, attention branch (clustering_mnist.py:122-161)
 # ----------------------------------------------------------------------------
 def get_latent(x_coord, y, enc: EncoderParams, G: int, padding: int, rot_refinement: bool,
-               normal_prior_over_r: bool, theta_prior: float):
+               normal_prior_over_r: bool, theta_prior: float, encoder: str = "attn_attn"):
     dt = y.dtype
-    attn_raw, theta, z = encoder_head_maps(y, enc, G, padding)
-    attn = attn_raw + rotation_log_prior(G, rot_refinement, normal_prior_over_r, theta_prior, dt)
-    if rot_refinement:
-        theta = torch.stack((theta[:, 0] + rotation_offsets(G, True, dt).view(1, G, 1, 1), theta[:, 1]), 1)
+    if encoder == "attn_unimodal":     # clustering_mnist.py:81-120 (t_inf attention, r_inf unimodal)
+        attn, theta, z = plainconv_head_maps(y, enc, padding)
+    else:
+        attn_raw, theta, z = encoder_head_maps(y, enc, G, padding)
+        attn = attn_raw + rotation_log_prior(G, rot_refinement, normal_prior_over_r, theta_prior, dt)
+        if rot_refinement:
+            theta = torch.stack((theta[:, 0] + rotation_offsets(G, True, dt).view(1, G, 1, 1), theta[:, 1]), 1)
     B, R, d, _ = attn.shape
     ind = attn.reshape(B, -1).argmax(1)
     ar = torch.arange(B)

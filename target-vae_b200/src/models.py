@@ -193,7 +193,10 @@ class InferenceNetwork_UnimodalTranslation_UnimodalRotation(nn.Module):
 
 
 class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
-    """models.py:268-319 (ablation encoder; parameters only)."""
+    """models.py:268-319: attention over translations only.  groupconv = 0 (plain Conv2d(C, O, n, padding n//2) ->
+    LeakyReLU -> 1x1 conv -> LeakyReLU -> heads) runs on the same tcgen05 kernels as the TARGET-VAE encoder with a
+    single, unrotated filter slot (G = 1); forward returns the reference's 4-tuple.  groupconv > 0 (group conv pooled
+    over rotations by `fc_r`) keeps its parameters / state_dict only."""
 
     def __init__(self, n, in_channels, latent_dim, kernels_num=128, activation=nn.LeakyReLU, groupconv=0):
         super(InferenceNetwork_AttentionTranslation_UnimodalRotation, self).__init__()
@@ -213,9 +216,40 @@ class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
         self.conv_a = nn.Conv2d(self.kernels_num, 1, 1)
         self.conv_r = nn.Conv2d(self.kernels_num, 2, 1)
         self.conv_z = nn.Conv2d(self.kernels_num, 2 * self.latent_dim, 1)
+        # geometry in the TARGET-VAE encoder's terms (used by tvae_b200.elbo)
+        self.kernels_size = self.input_size
+        self.padding = self.input_size // 2
+
+    # ---- helpers used by the fused step --------------------------------------------------------
+    def encoder_spec(self, theta_prior=np.pi):
+        """One rotation slot, no rotation prior, no offsets; the N(0, theta_prior) prior on theta is the trainer's
+        argument (train_mnist.py:171), not a module attribute."""
+        if not isinstance(self.activation, nn.LeakyReLU):
+            raise NotImplementedError("only LeakyReLU encoders are on the accelerated path (SURVEY.md §8f)")
+        if self.groupconv != 0:
+            raise NotImplementedError("attention/unimodal inference with groupconv > 0 (rotation pooling through fc_r) is "
+                                      "not on the accelerated path; groupconv = 0 is")
+        return TF.EncoderSpec(1, self.padding, self.latent_dim, False, False, float(theta_prior),
+                              theta_prior_std=float(theta_prior))
+
+    def hot_path_params(self):
+        return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv_a.weight, self.conv_a.bias,
+                self.conv_r.weight, self.conv_r.bias, self.conv_z.weight, self.conv_z.bias]
+
+    def head_maps(self, x):
+        """(B, 3+2z, 1, H', W') = [attn, theta_mu, theta_logstd, z...] with autograd."""
+        _require_cuda(x, "encoder forward")
+        return TF.EncoderHeadsFn.apply(self.encoder_spec(), x, *self.hot_path_params())
 
     def forward(self, x, device):
-        raise NotImplementedError("attention/unimodal inference is an ablation outside the accelerated hot path")
+        heads = self.head_maps(x).squeeze(2)
+        B = heads.shape[0]
+        attn = heads[:, 0:1]
+        theta = heads[:, 1:3]
+        z = heads[:, 3:]
+        # models.py:311-313: elementwise tail on the attention map; the fused step never materialises it
+        a_sampled = F.gumbel_softmax(attn.reshape(B, -1), dim=-1).view(B, heads.shape[2], heads.shape[3])
+        return attn, a_sampled, theta, z
 
 
 class InferenceNetwork_AttentionTranslation_AttentionRotation(nn.Module):

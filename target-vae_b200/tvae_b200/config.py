@@ -32,6 +32,10 @@ class HotPathConfig:
     ctf: bool = False
     mask_radius: int = 0
     batch: int = 100               # --minibatch-size
+    # attn_attn: InferenceNetwork_AttentionTranslation_AttentionRotation (--r-inf attention / attention+offsets);
+    # attn_unimodal: InferenceNetwork_AttentionTranslation_UnimodalRotation with --groupconv 0 (--r-inf unimodal):
+    # plain Conv2d(C, O, n, padding n//2), i.e. k = n, p = n // 2, G = 1 here
+    encoder: str = "attn_attn"
 
     @property
     def Hout(self) -> int:

@@ -28,17 +28,32 @@ def draw_noise(B, L, z, device, generator=None):
     return dict(gumbel=gumbel, r_z=r_z, r_theta=r_theta)
 
 
-def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, sync=None):
-    if not (t_inf == 'attention' and r_inf in ('attention', 'attention+offsets')):
-        raise NotImplementedError("only --t-inf attention with --r-inf attention / attention+offsets is on the "
-                                  "accelerated hot path (SURVEY.md §8)")
+def _encoder_spec(encoder_model, t_inf, r_inf, theta_prior):
+    """The inference branches of eval_minibatch that run on the kernels: attention/attention(+offsets)
+    (train_mnist.py:187-282) and attention/unimodal with a plain-conv encoder (train_mnist.py:88-183, --groupconv 0)."""
+    if t_inf == 'attention' and r_inf in ('attention', 'attention+offsets'):
+        es = encoder_model.encoder_spec()
+        if es.theta_prior_std is not None:
+            raise ValueError("r_inf attention needs InferenceNetwork_AttentionTranslation_AttentionRotation")
+        if (r_inf == 'attention+offsets') != es.rot_refinement:
+            raise ValueError("r_inf does not match the encoder's rot_refinement")
+        return es
+    if t_inf == 'attention' and r_inf == 'unimodal':
+        es = encoder_model.encoder_spec(theta_prior)
+        if es.theta_prior_std is None:
+            raise ValueError("r_inf unimodal needs InferenceNetwork_AttentionTranslation_UnimodalRotation")
+        return es
+    raise NotImplementedError("--t-inf unimodal (the MLP encoder of the spatial-VAE baseline) is not on the accelerated hot "
+                              "path (SURVEY.md §8)")
+
+
+def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, sync=None,
+          theta_prior=None):
+    es = _encoder_spec(encoder_model, t_inf, r_inf, theta_prior)
     y = y.to(device)
     x = x.to(device)
     if not y.is_cuda:
         raise RuntimeError("eval_minibatch: the hot path runs on sm_100a only (no CPU fallback)")
-    es = encoder_model.encoder_spec()
-    if (r_inf == 'attention+offsets') != es.rot_refinement:
-        raise ValueError("r_inf does not match the encoder's rot_refinement")
     B = y.shape[0]
     n = y.shape[-1]
     d = n + 2 * es.padding - encoder_model.kernels_size + 1
@@ -56,7 +71,7 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
 def eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
                    theta_prior, groupconv, image_dim, noise=None, sync=None):
     """train_mnist / train_dsprites / train_galaxy signature; Bernoulli likelihood (RGB handled by flat order)."""
-    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, sync)
+    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, sync, theta_prior)
 
 
 def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, epoch, device,
@@ -70,20 +85,22 @@ def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r
         if ctf is not None or int(mask_radius) > 0:
             raise NotImplementedError("--fit-noise with --ctf-file or --mask-radius fails in the reference itself for "
                                       "B > 1 (train_particles.py:304-307, 330-331); not reproduced")
-        return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "gaussian_fit_noise", 0, noise, sync)
+        return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "gaussian_fit_noise", 0, noise, sync,
+                     theta_prior)
     if n_out != 1:
         raise ValueError(f"eval_minibatch_particles: generator n_out must be 1 or 2 (--fit-noise), got {n_out}")
     if ctf is not None:
         ctf = ctf.to(device)
-    return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync)
+    return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync,
+                 theta_prior)
 
 
 def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
-    """clustering_*.get_latent, attention branch (clustering_mnist.py:122-161): one encoder pass + one reduction
-    kernel; returns (z_content (B,2z), theta_mu (B,1), dx (B,2))."""
+    """clustering_*.get_latent, attention branches (clustering_mnist.py:81-120 r_inf unimodal with a plain-conv encoder,
+    :122-161 r_inf attention[+offsets]): one encoder pass + one reduction kernel; returns (z_content (B,2z),
+    theta_mu (B,1), dx (B,2))."""
     from . import ops
-    if not (t_inf == 'attention' and r_inf in ('attention', 'attention+offsets')):
-        raise NotImplementedError("only the attention/attention branch is on the accelerated path")
+    _encoder_spec(encoder_model, t_inf, r_inf, None if r_inf != 'unimodal' else 1.0)   # validates the branch only
     with torch.no_grad():
         y = y.to(device)
         heads = encoder_model.head_maps(y)

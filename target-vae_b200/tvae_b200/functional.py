@@ -64,6 +64,9 @@ class EncoderSpec:
     rot_refinement: bool
     normal_prior_over_r: bool
     theta_prior: float
+    # std of the Normal prior on theta given (t, r): pi / G for the attention/attention branch (train_mnist.py:269-272);
+    # the attention/unimodal branch uses eval_minibatch's theta_prior argument instead (train_mnist.py:171)
+    theta_prior_std: Optional[float] = None
 
     def tables(self):
         p_r = ops.rotation_log_prior(self.G, self.rot_refinement, self.normal_prior_over_r, self.theta_prior)
@@ -77,6 +80,8 @@ ENC_PARAM_NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "
 
 def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz):
     B, n = y.shape[0], y.shape[-1]
+    if w1.dim() == 4:      # nn.Conv2d weight (O,C,k,k) of the groupconv = 0 encoder: one rotation, no rotation axis
+        w1 = w1.unsqueeze(2)
     O, C, _, k, _ = w1.shape
     s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z)
     p_r, offs = spec.tables()
@@ -88,15 +93,18 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
     return s, yc, w2m, wh, x1, h, heads
 
 
-def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads):
-    """-> grads in ENC_PARAM_NAMES order."""
+def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None):
+    """-> grads in ENC_PARAM_NAMES order (Conv3d shapes, or reshaped to `shapes` = the parameters' own shapes)."""
     dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
     dw1, db1 = ops.filter_bank_bwd(s, dbank)
     O, z = s.O, spec.z
     sh = (O, 1, 1, 1)
-    return [dw1, db1, dw2.view(O, O, 1, 1, 1), db2,
-            dwh[0:1].reshape(1, *sh), dbh[0:1], dwh[1:3].reshape(2, *sh), dbh[1:3],
-            dwh[3:].reshape(2 * z, *sh), dbh[3:]]
+    grads = [dw1, db1, dw2.view(O, O, 1, 1, 1), db2,
+             dwh[0:1].reshape(1, *sh), dbh[0:1], dwh[1:3].reshape(2, *sh), dbh[1:3],
+             dwh[3:].reshape(2 * z, *sh), dbh[3:]]
+    if shapes is not None:
+        grads = [g.reshape(sh_) for g, sh_ in zip(grads, shapes)]
+    return grads
 
 
 class EncoderHeadsFn(torch.autograd.Function):
@@ -106,6 +114,7 @@ class EncoderHeadsFn(torch.autograd.Function):
     def forward(ctx, spec, y, *params):
         s, yc, w2m, wh, x1, h, heads = _encoder_forward(spec, y, *params)
         ctx.spec, ctx.s = spec, s
+        ctx.shapes = [p.shape for p in params]
         ctx.save_for_backward(yc, w2m, wh, x1, h)
         d = s.n + 2 * s.p - s.k + 1
         return heads.view(s.B, 3 + 2 * spec.z, s.G, d, d)
@@ -113,7 +122,7 @@ class EncoderHeadsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         yc, w2m, wh, x1, h = ctx.saved_tensors
-        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous())
+        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous(), ctx.shapes)
         return (None, None, *grads)
 
 
@@ -211,7 +220,7 @@ class FusedStepFn(torch.autograd.Function):
         xc = ops.f32(x_coord)
         spacing = pixel_spacing(xc)
         p_r, offs = es.tables()
-        ashape = ops.attn_shape(B, s.G, d, es.z, spacing, offs)
+        ashape = ops.attn_shape(B, s.G, d, es.z, spacing, offs, es.theta_prior_std)
         log_prior = ops.attn_log_prior(ashape, p_r, y.device)
         gum, rz, rth = ops.f32(gumbel), ops.f32(r_z).reshape(B, es.z), ops.f32(r_theta).reshape(B)
         att = ops.attn_fwd(ashape, heads, gum, rz, rth, log_prior)
@@ -238,6 +247,7 @@ class FusedStepFn(torch.autograd.Function):
 
         ctx.spec, ctx.s, ctx.ashape, ctx.gs, ctx.gw, ctx.gsaved, ctx.att = spec, s, ashape, gs, gw, gsaved, att
         ctx.spacing = spacing
+        ctx.enc_shapes = [p.shape for p in enc_params]
         ctx.save_for_backward(yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc if ctfc is not None else yc)
         ctx.has_ctf = ctfc is not None
         return elbo, log_p, kl
@@ -268,7 +278,7 @@ class FusedStepFn(torch.autograd.Function):
         if spec.sync is not None:
             spec.sync.start(0, gen_grads)
         d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
-        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads)
+        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes)
         if spec.sync is not None:
             spec.sync.start(1, enc_grads)
             gen_grads, enc_grads = spec.sync.finish()

@@ -216,8 +216,10 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
 
 
 # ----------------------------------------------------------------------------------------------- attention
-def attn_shape(B, G, d, z, s, offsets) -> AttnShape:
-    a = AttnShape(B, G, d, z, float(s), float(torch.tensor(math.pi / G, dtype=torch.float32)))
+def attn_shape(B, G, d, z, s, offsets, theta_prior_std=None) -> AttnShape:
+    """theta_prior_std: None = pi / G (attention/attention branch, train_mnist.py:269-272)."""
+    std = math.pi / G if theta_prior_std is None else theta_prior_std
+    a = AttnShape(B, G, d, z, float(s), float(torch.tensor(std, dtype=torch.float32)))
     for i, o in enumerate(offsets):
         a.offsets[i] = o
     return a

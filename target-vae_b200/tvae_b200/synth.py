@@ -36,6 +36,8 @@ def encoder_state(cfg: HotPathConfig, seed: int = 0, gain: float = 1.0) -> dict:
         "conv_z.weight": _u(rng, (2 * z, O, 1, 1, 1), bo),
         "conv_z.bias": _u(rng, (2 * z,), bo),
     }
+    if cfg.encoder == "attn_unimodal":     # nn.Conv2d modules (models.py:281-287): the same draws without the rotation axis
+        sd = {k_: (v.reshape(v.shape[0], v.shape[1], *v.shape[3:]) if v.ndim == 5 else v) for k_, v in sd.items()}
     return sd
 
 

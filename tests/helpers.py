@@ -41,7 +41,7 @@ def oracle_inputs(cfg, B, seed=0, dtype=torch.float32, gain=1.0, requires_grad=T
 def step_config(cfg):
     return orc.StepConfig(G=cfg.G, padding=cfg.p, rot_refinement=cfg.rot_refinement,
                           normal_prior_over_r=cfg.normal_prior_over_r, theta_prior=cfg.theta_prior,
-                          likelihood=cfg.likelihood, mask_radius=cfg.mask_radius)
+                          likelihood=cfg.likelihood, mask_radius=cfg.mask_radius, encoder=cfg.encoder)
 
 
 def oracle_step(cfg, B, seed=0, dtype=torch.float32, gain=1.0, backward=True):

@@ -101,16 +101,16 @@ def test_argmax_parity(gain, label):
     assert agree >= agree_ref32 - 1e-3
 
 
-@pytest.mark.parametrize("name", ["g1_mnist", "g2_dsprites", "g4_particles_ctf", "g6_mnist_noref"])
+@pytest.mark.parametrize("name", ["g1_mnist", "g2_dsprites", "g4_particles_ctf", "g6_mnist_noref", "g8_mnist_attn_unimodal"])
 def test_get_latent_matches_reference_golden(name):
     """clustering_mnist.get_latent outputs of the unmodified reference (tests/golden) vs the CUDA path."""
-    from test_gpu_step import build_models
+    from test_gpu_step import build_models, r_inf_of
     from tvae_b200 import elbo as E
     g, cfg, B, _ = load_golden(name)
     _, enc = build_models(cfg)
     x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
     y = torch.from_numpy(synth.minibatch(cfg, B, 0)["y"]).to(DEV)
-    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+    r_inf = r_inf_of(cfg)
     zc, th, dx = E.get_latent(x, y, enc, "attention", r_inf, DEV, cfg.n)
     for mine, key in ((zc, "latent_z"), (th, "latent_theta"), (dx, "latent_dx")):
         ref = torch.from_numpy(g[key]).double()

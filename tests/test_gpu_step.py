@@ -28,7 +28,7 @@ from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, HotPathConfig
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
-          "g7_particles_fitnoise"]
+          "g7_particles_fitnoise", "g8_mnist_attn_unimodal"]
 
 
 def build_models(cfg, seed=0, gain=1.0):
@@ -36,13 +36,23 @@ def build_models(cfg, seed=0, gain=1.0):
     with contextlib.redirect_stdout(io.StringIO()):
         gen = models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=nn.LeakyReLU,
                                       resid=False, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
-        enc = models.InferenceNetwork_AttentionTranslation_AttentionRotation(
-            cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
-            groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
-            normal_prior_over_r=cfg.normal_prior_over_r)
+        if cfg.encoder == "attn_unimodal":
+            enc = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
+                                                                                activation=nn.LeakyReLU, groupconv=0)
+        else:
+            enc = models.InferenceNetwork_AttentionTranslation_AttentionRotation(
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+                groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
+                normal_prior_over_r=cfg.normal_prior_over_r)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()})
     enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg, seed, gain).items()})
     return gen.to(DEV), enc.to(DEV)
+
+
+def r_inf_of(cfg):
+    if cfg.encoder == "attn_unimodal":
+        return "unimodal"
+    return "attention+offsets" if cfg.rot_refinement else "attention"
 
 
 def run_step(cfg, B, seed=0, gain=1.0, backward=True):
@@ -52,7 +62,7 @@ def run_step(cfg, B, seed=0, gain=1.0, backward=True):
     nz = {k: torch.from_numpy(v).to(DEV) for k, v in synth.noise(cfg, B, seed).items()}
     x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
     y = torch.from_numpy(data["y"]).to(DEV)
-    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+    r_inf = r_inf_of(cfg)
     if cfg.likelihood == "gaussian":
         ctf = torch.from_numpy(data["ctf"]).to(DEV) if data["ctf"] is not None else None
         out = E.eval_minibatch_particles(x, y, ctf, gen, enc, "attention", r_inf, 0, DEV, cfg.theta_prior, cfg.G, cfg.p,
@@ -218,3 +228,41 @@ def test_empty_batch_fails_loudly():
     y = torch.zeros(0, 1, cfg.n, cfg.n, device=DEV)
     with pytest.raises((TvaeError, RuntimeError, ValueError)):
         E.eval_minibatch(x, y, gen, enc, "attention", "attention+offsets", 0, DEV, cfg.theta_prior, cfg.G, cfg.n)
+
+
+def test_attention_unimodal_matches_oracle_mnist_shaped():
+    """--t-inf attention --r-inf unimodal --groupconv 0 at MNIST's size (Conv2d(1, 128, 28, padding 14): 29 x 29 map),
+    theta prior std 0.5 (not pi, so the trainer's theta_prior argument is seen to reach the KL kernel)."""
+    cfg = HotPathConfig("cfg1_au", C=1, n=28, k=28, p=14, G=1, z=2, rot_refinement=False, encoder="attn_unimodal",
+                        theta_prior=0.5)
+    B = 6
+    elbo, logp, kl, grads = run_step(cfg, B)
+    o_elbo, o_logp, o_kl, _, o_grads = oracle_step(cfg, B, dtype=torch.float64)
+    print(f"cfg1_au B=6: elbo {elbo:.4f} / {float(o_elbo):.4f}, log_p {logp:.4f} / {float(o_logp):.4f}, kl {kl:.4f} / {float(o_kl):.4f}")
+    assert abs(elbo - float(o_elbo)) < 2e-3 * abs(float(o_elbo))
+    assert abs(logp - float(o_logp)) < 2e-3 * abs(float(o_logp))
+    assert abs(kl - float(o_kl)) < 2e-3 * abs(float(o_kl))
+    check_grads(grads, o_grads, 6e-2, "cfg1_au")
+
+
+def test_attention_unimodal_module_interface():
+    """InferenceNetwork_AttentionTranslation_UnimodalRotation.forward: the reference's 4-tuple (models.py:319) against
+    the golden outputs of the unmodified reference; groupconv > 0 is refused loudly."""
+    g, cfg, B, _ = load_golden("g8_mnist_attn_unimodal")
+    _, enc = build_models(cfg)
+    y = torch.from_numpy(synth.minibatch(cfg, B, 0)["y"]).to(DEV)
+    with torch.no_grad():
+        attn, a_s, theta, z = enc(y, DEV)
+    d = cfg.Hout
+    assert tuple(attn.shape) == (B, 1, d, d) and tuple(a_s.shape) == (B, d, d)
+    assert tuple(theta.shape) == (B, 2, d, d) and tuple(z.shape) == (B, 2 * cfg.z, d, d)
+    for key, t in (("attn", attn), ("theta", theta), ("z", z)):
+        ref = torch.from_numpy(g[key])
+        assert float((t.cpu() - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max())), key
+    assert abs(float(a_s.sum()) - B) < 1e-3
+    import src.models as models
+    with contextlib.redirect_stdout(io.StringIO()):
+        pooled = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
+                                                                               groupconv=4).to(DEV)
+    with pytest.raises(NotImplementedError):
+        pooled(y, DEV)

@@ -14,7 +14,11 @@ CASES = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particl
           "g7_particles_fitnoise"]
 
 
-@pytest.mark.parametrize("name", CASES)
+# --t-inf attention --r-inf unimodal --groupconv 0: plain Conv2d encoder, 4-tuple module interface
+AU_CASES = ["g8_mnist_attn_unimodal"]
+
+
+@pytest.mark.parametrize("name", CASES + AU_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_step_matches_reference(name, dtype):
     g, cfg, B, _ = load_golden(name)
@@ -86,3 +90,25 @@ def test_translation_grid_even_odd():
                 assert abs(float(gr[i, j, 0]) - (j - half) * 0.1) < 1e-6
                 yy = (half - i) if d % 2 else (half - 1 - i)
                 assert abs(float(gr[i, j, 1]) - yy * 0.1) < 1e-6
+
+
+@pytest.mark.parametrize("name", AU_CASES)
+def test_plainconv_encoder_and_get_latent_match_reference(name):
+    """InferenceNetwork_AttentionTranslation_UnimodalRotation(groupconv=0): module 4-tuple (models.py:319), conv1
+    output and clustering_mnist.get_latent's attention/unimodal branch (:81-120)."""
+    g, cfg, B, _ = load_golden(name)
+    enc, gen, x, y, ctf, nz = oracle_inputs(cfg, B, requires_grad=False)
+    assert enc.conv1_w.dim() == 4
+    attn, q_t, p_r, a_s, offs, theta, z = orc.plainconv_encoder_forward(y, enc, cfg.p, nz["gumbel"])
+    d = cfg.Hout
+    for key, t in (("attn", attn), ("a_sampled", a_s.reshape(B, d, d)), ("theta", theta.squeeze(2)), ("z", z.squeeze(2))):
+        ref = torch.from_numpy(g[key])
+        assert tuple(t.shape) == tuple(ref.shape), key
+        assert torch.allclose(t, ref, rtol=1e-4, atol=2e-5), (key, float((t - ref).abs().max()))
+    c1 = torch.nn.functional.conv2d(y, enc.conv1_w, enc.conv1_b, padding=cfg.p)
+    assert torch.allclose(c1, torch.from_numpy(g["conv1_out"]), rtol=1e-4, atol=1e-5)
+    zc, th, dx, ind = orc.get_latent(x, y, enc, 1, cfg.p, False, False, cfg.theta_prior, encoder="attn_unimodal")
+    assert torch.allclose(zc, torch.from_numpy(g["latent_z"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(th, torch.from_numpy(g["latent_theta"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(dx, torch.from_numpy(g["latent_dx"]), rtol=1e-4, atol=1e-5)
+    assert torch.equal(ind, torch.from_numpy(g["attn"]).reshape(B, -1).argmax(1))
