@@ -405,6 +405,20 @@ def run_ours(args, cfg):
     train_ms = max_over_ranks(e0.elapsed_time(e1))
     train_ips = world * B * K / (train_ms * 1e-3)
 
+    # ---- extra: clustering_*.get_latent over the same minibatches - encoder forward without the hidden
+    # map + one reduction kernel per minibatch (argmax (r,t), z / theta there, softmax-expected translation)
+    for i in range(2):
+        E.get_latent(x, y_dev[i % NB], enc, "attention", r_inf, dev, cfg.n)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        E.get_latent(x, y_dev[i % NB], enc, "attention", r_inf, dev, cfg.n)
+    e1.record()
+    barrier()
+    latent_ms = max_over_ranks(e0.elapsed_time(e1))
+    latent_ips = world * B * K / (latent_ms * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -505,6 +519,8 @@ def run_ours(args, cfg):
         "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12,
         "train_step": {"value": train_ips, "unit": UNIT, "ms_per_step": train_ms / K,
                        "what": "fwd + bwd + fused multi-tensor Adam (tvae_adam_step), inputs resident in HBM"},
+        "get_latent": {"value": latent_ips, "unit": UNIT, "ms_per_minibatch": latent_ms / K,
+                       "what": "clustering_*.get_latent (inference: encoder forward + argmax / expectation kernel), inputs resident in HBM"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -73,7 +73,8 @@ typedef struct {
     const float* bh;         /* [NH] */
     const float* head_add;   /* [NH][G]: p_r on channel 0, rotation offsets on channel 1, else 0 */
     void* x1;                /* out fp16 [B*G*P][O]  LeakyReLU(conv1) */
-    void* h;                 /* out fp16 [B*G*P][O]  LeakyReLU(conv2) */
+    void* h;                 /* out fp16 [B*G*P][O]  LeakyReLU(conv2); NULL = inference only (clustering_*.get_latent,
+                              * clustering_mnist.py:81-161): the hidden map feeds the heads on chip and is not written */
     float* heads;            /* out (B,NH,G,P) */
     void* w2_h;              /* scratch fp16 (O,O) */
 } tvae_enc_fwd_args;

@@ -90,7 +90,7 @@ struct Conv2Heads : PolicyBase {
             for (int j = 0; j < 32; ++j) v[j] = lrelu(__uint_as_float(rr[j]) + s_b2[o0 + j]);
             __half* dst = p.h + m * p.O + o0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; p.h != nullptr && j < 32; j += 8) {      // h == NULL: inference only, the hidden map is not kept
                 uint4 q;
                 __half2 hv;
                 hv = __floats2half2_rn(v[j], v[j + 1]);     q.x = *reinterpret_cast<uint32_t*>(&hv);
@@ -151,6 +151,7 @@ struct Conv2HeadsTCParams {
     int num_stages, num_tiles, k_chunks;
     long long R;
     int O, NH, NHpad, G, P;
+    int store_h;              // 0: tmH is not set up and h is not written (inference only)
     const float* b2;
     const float* wh;          // [NH][O] fp32 (split into fp16 hi / lo operand tiles in setup)
     const float* bh;
@@ -185,7 +186,7 @@ struct Conv2HeadsTC : PolicyBase {
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
-        tma_prefetch_desc(&p.tmH);
+        if (p.store_h) tma_prefetch_desc(&p.tmH);
     }
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         // Wh as K-major fp16 operand tiles: chunk kc = o / 64, rows [0, NHpad) = hi part, [NHpad, 2 NHpad) = lo part
@@ -281,9 +282,11 @@ struct Conv2HeadsTC : PolicyBase {
         named_bar_sync(bar_id, kEpiWarps * 32);
         const uint32_t d_tmem = st.tmem_free + st.grp * 64;                  // this group's heads accumulator (lane 0)
         if (row == 0) {
-            tma_store_2d(&p.tmH, smem_u32(buf), 0, ti.m0);
-            tma_store_2d(&p.tmH, smem_u32(buf + kBlockBytes), 64, ti.m0);
-            tma_store_commit();
+            if (p.store_h) {      // 0: inference only (get_latent) - h feeds the heads product from shared memory and is not kept
+                tma_store_2d(&p.tmH, smem_u32(buf), 0, ti.m0);
+                tma_store_2d(&p.tmH, smem_u32(buf + kBlockBytes), 64, ti.m0);
+                tma_store_commit();
+            }
             tc_fence_after();
             const uint32_t idesc2 = make_idesc_f16(kBM, 2 * p.NHpad, false, false, 0, 0);
             const uint32_t idesc1 = make_idesc_f16(kBM, p.NHpad, false, false, 0, 0);

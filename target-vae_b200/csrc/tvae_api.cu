@@ -377,7 +377,8 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
             Conv2HeadsTCParams q{};
             if ((rc = make_tmap_2d_h(&q.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
             if ((rc = make_tmap_2d_h(&q.tmB, a->w2_h, g.O, g.O, g.O, 128))) return rc;
-            if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, g.O, g.O, kBM))) return rc;
+            q.store_h = a->h != nullptr;
+            if (q.store_h && (rc = make_tmap_2d_h(&q.tmH, a->h, R, g.O, g.O, kBM))) return rc;
             q.R = R; q.O = g.O; q.NH = NH; q.NHpad = NH <= 16 ? 16 : 32; q.G = g.G; q.P = g.P;
             q.k_chunks = 2;
             q.num_tiles = cdiv(R, kBM);

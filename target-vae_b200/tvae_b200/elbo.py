@@ -103,9 +103,11 @@ def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
     _encoder_spec(encoder_model, t_inf, r_inf, None if r_inf != 'unimodal' else 1.0)   # validates the branch only
     with torch.no_grad():
         y = y.to(device)
-        heads = encoder_model.head_maps(y)
-        B, NH, G, d, _ = heads.shape
+        if not y.is_cuda:
+            raise RuntimeError("get_latent: the hot path runs on sm_100a only (no CPU fallback)")
         es = encoder_model.encoder_spec()
+        heads = TF.encoder_heads_inference(es, y, *encoder_model.hot_path_params())
+        B, NH, G, d, _ = heads.shape
         s = ops.attn_shape(B, G, d, es.z, TF.pixel_spacing(x.to(device)), es.tables()[1])
         zc, th, dx, _ = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
     return zc, th, dx

@@ -78,7 +78,7 @@ ENC_PARAM_NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "
                    "conv_r.weight", "conv_r.bias", "conv_z.weight", "conv_z.bias"]
 
 
-def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz):
+def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz, keep_h=True):
     B, n = y.shape[0], y.shape[-1]
     if w1.dim() == 4:      # nn.Conv2d weight (O,C,k,k) of the groupconv = 0 encoder: one rotation, no rotation axis
         w1 = w1.unsqueeze(2)
@@ -89,8 +89,16 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
     wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.G, p_r, offs, y.device)
     bank = ops.filter_bank_fwd(s, w1)
     w2m = ops.f32(w2).reshape(O, O)
-    x1, h, heads = ops.encoder_fwd(s, yc, bank, b1, w2m, b2, wh, bh, add)
+    x1, h, heads = ops.encoder_fwd(s, yc, bank, b1, w2m, b2, wh, bh, add, keep_h)
     return s, yc, w2m, wh, x1, h, heads
+
+
+def encoder_heads_inference(spec: EncoderSpec, y, *params):
+    """heads (B, 3+2z, G, H', W') without autograd and without keeping the hidden map (clustering_*.get_latent)."""
+    with torch.no_grad():
+        s, _, _, _, _, _, heads = _encoder_forward(spec, y, *params, keep_h=False)
+    d = s.n + 2 * s.p - s.k + 1
+    return heads.view(s.B, 3 + 2 * spec.z, s.G, d, d)
 
 
 def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None):

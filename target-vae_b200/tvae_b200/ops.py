@@ -178,7 +178,8 @@ def _head_add_table(NH, G, p_r, offsets, device):
     return add.to(device)
 
 
-def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add):
+def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add, keep_h=True):
+    """keep_h = False: inference only (get_latent) - the hidden map h is neither allocated nor written."""
     dev = y.device
     d = s.n + 2 * s.p - s.k + 1
     P = d * d
@@ -186,7 +187,7 @@ def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add):
     NH = 3 + 2 * s.z
     # activations are stored fp16 (the MMA operand format: 11-bit significand like TF32, half the HBM traffic)
     x1 = half(R, s.O, device=dev)
-    h = half(R, s.O, device=dev)
+    h = half(R, s.O, device=dev) if keep_h else None
     heads = empty(s.B, NH, s.G, P, device=dev)
     w2r = half(s.O, s.O, device=dev)
     a = _set(EncFwdArgs(), y=f32(y), bank=bank, conv1_bias=f32(b1), w2=f32(w2), b2=f32(b2), wh=wh, bh=bh,
