@@ -69,6 +69,9 @@ CASES = {
     # --t-inf attention --r-inf unimodal --groupconv 0 (train_mnist.py:88-183, models.py:268-319): plain Conv2d encoder
     "g8_mnist_attn_unimodal": ("mnist", HotPathConfig("cfg1_gu", C=1, n=16, k=16, p=8, G=1, z=2, O=32, hidden=64,
                                                       rot_refinement=False, encoder="attn_unimodal"), 3),
+    # --generator-resid-layers (train_mnist.py:422,508, models.py:22-30, 84-86): three ResidLinear hidden layers
+    "g9_mnist_resid": ("mnist", HotPathConfig("cfg1_gr", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=64, gen_layers=4,
+                                              gen_resid=True), 3),
     # --fit-noise (train_particles.py:663-666): generator n_out = 2, learned per-pixel log-variance, no CTF / mask
     "g7_particles_fitnoise": ("particles", HotPathConfig("cfg4_gf", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                          likelihood="gaussian", n_out=2), 3),
@@ -78,7 +81,7 @@ CASES = {
 def build_reference_models(ref_models, cfg: HotPathConfig, seed=0):
     with contextlib.redirect_stdout(io.StringIO()):
         gen = ref_models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers,
-                                          activation=nn.LeakyReLU, resid=False,
+                                          activation=nn.LeakyReLU, resid=cfg.gen_resid,
                                           fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
             assert cfg.k == cfg.n and cfg.p == cfg.n // 2 and cfg.G == 1

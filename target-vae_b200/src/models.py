@@ -33,7 +33,8 @@ def _require_cuda(t, what):
 
 
 class ResidLinear(nn.Module):
-    """models.py:22-30 (parameters only; residual generator layers are not on the accelerated path yet)."""
+    """models.py:22-30: act(linear(x) + x).  Inside SpatialGenerator it runs on the hidden-layer tensor-core kernels as a
+    plain layer with the effective weight W + I (tvae_b200.functional._gen_weights); it has no standalone forward."""
 
     def __init__(self, n_in, n_out, activation=nn.LeakyReLU):
         super(ResidLinear, self).__init__()
@@ -41,7 +42,7 @@ class ResidLinear(nn.Module):
         self.act = activation()
 
     def forward(self, x):
-        raise NotImplementedError("ResidLinear is outside the accelerated hot path (SURVEY.md §8f)")
+        raise NotImplementedError("ResidLinear runs only as a hidden layer of SpatialGenerator (fused kernels)")
 
 
 class RandomFourierEmbedding2d(nn.Module):
@@ -93,14 +94,14 @@ class SpatialGenerator(nn.Module):
 
     # ---- helpers used by the fused step --------------------------------------------------------
     def _check_supported(self):
-        if self._resid or not isinstance(self.layers[0], nn.LeakyReLU) or not hasattr(self, 'latent_linear'):
-            raise NotImplementedError("SpatialGenerator: only LeakyReLU, non-residual, latent-conditioned generators "
-                                      "are on the accelerated path (SURVEY.md §8f)")
+        if not isinstance(self.layers[0], nn.LeakyReLU) or not hasattr(self, 'latent_linear'):
+            raise NotImplementedError("SpatialGenerator: only LeakyReLU, latent-conditioned generators are on the "
+                                      "accelerated path (SURVEY.md §8f)")
 
     def hot_path_params(self):
         """coord_linear.{weight,bias}, latent_linear.weight, (hidden weight, bias)*, out weight, bias."""
         self._check_supported()
-        lin = [m for m in self.layers if isinstance(m, nn.Linear)]
+        lin = [m.linear if isinstance(m, ResidLinear) else m for m in self.layers if isinstance(m, (nn.Linear, ResidLinear))]
         ps = [self.coord_linear.weight, self.coord_linear.bias, self.latent_linear.weight]
         for m in lin:
             ps += [m.weight, m.bias]
@@ -118,7 +119,7 @@ class SpatialGenerator(nn.Module):
             z = z.unsqueeze(0)
         _require_cuda(x, "SpatialGenerator.forward")
         fw, fb = self.fourier_buffers()
-        return TF.GeneratorFn.apply(fw, fb, self._sigma, x, z, *self.hot_path_params())
+        return TF.GeneratorFn.apply(fw, fb, (self._sigma, self._resid), x, z, *self.hot_path_params())
 
 
 class GroupConv(nn.Module):

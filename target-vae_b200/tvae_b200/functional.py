@@ -138,13 +138,19 @@ class EncoderHeadsFn(torch.autograd.Function):
 GEN_FIXED = ["coord_linear.weight", "coord_linear.bias", "latent_linear.weight"]
 
 
-def _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout):
+def _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout, resid=False):
+    """resid: the hidden layers are ResidLinear modules, act(W x + b + x) = act((W + I) x + b) (models.py:29-30; the
+    activation comes after the residual add).  They run as plain layers with the effective weight W + I: the forward,
+    the input gradient dpre (W + I) and the fp16 gradient-scale bounds all see W + I, and the weight gradient
+    dpre^T x is the gradient w.r.t. W as it stands."""
     wf = None
     if fourier_w is not None:
         # F.linear(x, weight / sigma, bias) with sigma an fp32 tensor (models.py:40,57)
         wf = (ops.f32(fourier_w) / torch.tensor(sigma, dtype=torch.float32, device=fourier_w.device)).contiguous()
     hw = [hidden[i] for i in range(0, len(hidden), 2)]
     hb = [hidden[i] for i in range(1, len(hidden), 2)]
+    if resid:
+        hw = [ops.f32(w) + torch.eye(w.shape[0], dtype=torch.float32, device=w.device) for w in hw]
     return ops.GenWeights(wf, None if fourier_b is None else ops.f32(fourier_b), w1, b1, wz, hw, hb, wout, bout)
 
 
@@ -162,9 +168,12 @@ class GeneratorFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fourier_w, fourier_b, sigma, x, z, *params):
+        resid = False
+        if isinstance(sigma, tuple):       # (sigma, resid) from SpatialGenerator(resid=True)
+            sigma, resid = sigma
         w1, b1, wz = params[:3]
         hidden, (wout, bout) = params[3:-2], params[-2:]
-        gw = _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout)
+        gw = _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout, resid)
         B, N = x.shape[0], x.shape[1]
         s = ops.gen_shape(B, N, gw, z.shape[1])
         xc, zc = ops.f32(x).reshape(B * N, 2), ops.f32(z)
@@ -206,6 +215,7 @@ class StepSpec:
     likelihood: str = "bernoulli"      # bernoulli | gaussian | gaussian_fit_noise
     mask_radius: int = 0
     n_gen_hidden: int = 1
+    gen_resid: bool = False            # --generator-resid-layers: hidden layers are ResidLinear (models.py:22-30)
     # optional data-parallel gradient synchroniser (tvae_b200.dp.GradSync): bucket 0 (generator) is started as
     # soon as the generator backward has been issued, so its all-reduce overlaps the encoder backward.
     sync: Optional[object] = None
@@ -235,7 +245,7 @@ class FusedStepFn(torch.autograd.Function):
 
         w1, b1, wz = gen_params[:3]
         hidden, (wout, bout) = gen_params[3:-2], gen_params[-2:]
-        gw = _gen_weights(fourier_w, fourier_b, spec.sigma, w1, b1, wz, hidden, wout, bout)
+        gw = _gen_weights(fourier_w, fourier_b, spec.sigma, w1, b1, wz, hidden, wout, bout, spec.gen_resid)
         N = xc.shape[0]
         gs = ops.gen_shape(B, N, gw, es.z)
         y_hat, gsaved = ops.generator_fwd(gs, gw, xc, att["theta_b"], att["dx"], att["zb"])

@@ -54,9 +54,11 @@ def generator_state(cfg: HotPathConfig, seed: int = 0) -> dict:
     sd["latent_linear.weight"] = _u(rng, (H, cfg.z), 1 / math.sqrt(cfg.z))
     idx = 1
     for _ in range(1, cfg.gen_layers):
-        sd[f"layers.{idx}.weight"] = _u(rng, (H, H), 1 / math.sqrt(H))
-        sd[f"layers.{idx}.bias"] = _u(rng, (H,), 1 / math.sqrt(H))
-        idx += 2
+        # nn.Sequential indices: Linear, activation pairs - or one ResidLinear module per hidden layer (models.py:83-89)
+        pre = f"layers.{idx}.linear" if cfg.gen_resid else f"layers.{idx}"
+        sd[pre + ".weight"] = _u(rng, (H, H), 1 / math.sqrt(H))
+        sd[pre + ".bias"] = _u(rng, (H,), 1 / math.sqrt(H))
+        idx += 1 if cfg.gen_resid else 2
     sd[f"layers.{idx}.weight"] = _u(rng, (cfg.n_out, H), 1 / math.sqrt(H))
     sd[f"layers.{idx}.bias"] = _u(rng, (cfg.n_out,), 1 / math.sqrt(H))
     return sd

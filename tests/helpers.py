@@ -23,7 +23,7 @@ def oracle_inputs(cfg, B, seed=0, dtype=torch.float32, gain=1.0, requires_grad=T
     es = {k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg, seed, gain).items()}
     gs = {k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()}
     enc = orc.EncoderParams.from_state_dict(es, dtype)
-    gen = orc.GeneratorParams.from_state_dict(gs, cfg.sigma, dtype=dtype)
+    gen = orc.GeneratorParams.from_state_dict(gs, cfg.sigma, resid=cfg.gen_resid, dtype=dtype)
     if requires_grad:
         for t in enc.tensors():
             t.requires_grad_(True)
@@ -64,8 +64,9 @@ def gen_param_names(cfg):
     names = ["coord_linear.weight", "coord_linear.bias", "latent_linear.weight"]
     idx = 1
     for _ in range(1, cfg.gen_layers):
-        names += [f"layers.{idx}.weight", f"layers.{idx}.bias"]
-        idx += 2
+        pre = f"layers.{idx}.linear" if cfg.gen_resid else f"layers.{idx}"
+        names += [pre + ".weight", pre + ".bias"]
+        idx += 1 if cfg.gen_resid else 2
     names += [f"layers.{idx}.weight", f"layers.{idx}.bias"]
     return names
 

@@ -28,14 +28,14 @@ from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, HotPathConfig
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
-          "g7_particles_fitnoise", "g8_mnist_attn_unimodal"]
+          "g7_particles_fitnoise", "g8_mnist_attn_unimodal", "g9_mnist_resid"]
 
 
 def build_models(cfg, seed=0, gain=1.0):
     import src.models as models
     with contextlib.redirect_stdout(io.StringIO()):
         gen = models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=nn.LeakyReLU,
-                                      resid=False, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
+                                      resid=cfg.gen_resid, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
             enc = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
                                                                                 activation=nn.LeakyReLU, groupconv=0)
@@ -266,3 +266,26 @@ def test_attention_unimodal_module_interface():
                                                                                groupconv=4).to(DEV)
     with pytest.raises(NotImplementedError):
         pooled(y, DEV)
+
+
+def test_resid_generator_module_matches_oracle():
+    """SpatialGenerator(resid=True).forward / backward (--generator-resid-layers; ResidLinear = act(Wx + b + x),
+    models.py:22-30) through the module interface, against the fp64 oracle on explicit coordinates."""
+    from helpers import oracle_inputs, gen_param_names
+    from oracle import target_vae_oracle as orc
+    cfg = HotPathConfig("cfg1_resid", C=1, n=24, k=9, p=2, G=4, z=3, O=32, hidden=128, gen_layers=3, gen_resid=True)
+    B = 5
+    gen, _ = build_models(cfg)
+    _, ogen, x, _, _, nz = oracle_inputs(cfg, B, dtype=torch.float64)
+    xb = (x.expand(B, -1, -1) * torch.linspace(0.6, 1.1, B, dtype=torch.float64).view(B, 1, 1)).contiguous()
+    zb = nz["r_z"][:, :, 0]
+    ref = orc.generator_forward(xb, zb, ogen)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    (ref * w).sum().backward()
+    out = gen(xb.float().to(DEV), zb.float().to(DEV))
+    (out * w.float().to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu(), ref.detach()) < 2e-3
+    got = dict(gen.named_parameters())
+    for (_, t), name in zip(ogen.named_trainable(), gen_param_names(cfg)):
+        assert rel_err(got[name].grad.cpu(), t.grad) < 3e-2, name
