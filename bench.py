@@ -374,7 +374,7 @@ def run_ours(args, cfg):
     h2d = y_pin[0].numel() * 4 + (0 if ctf_pin[0] is None else ctf_pin[0].numel() * 4)
     for i in range(2):
         y_stage.copy_(y_pin[i % NB], non_blocking=True)
-        float(step(y_stage, ctf_stage if ctf_stage is None else ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)))
+        float(step(y_stage, ctf_stage if ctf_stage is None else ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)).detach())
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -78,7 +78,7 @@ def run_step(cfg, B, seed=0, gain=1.0, backward=True):
             grads["enc." + k] = p.grad.detach().cpu()
         for k, p in gen.named_parameters():
             grads["gen." + k] = p.grad.detach().cpu()
-    return float(elbo), float(logp), float(kl), grads
+    return float(elbo.detach()), float(logp.detach()), float(kl.detach()), grads
 
 
 def check_grads(grads, ref, tol, label):
