@@ -37,9 +37,14 @@ void tvae_profile_enable(int on);
 int tvae_profile_collect(const char** names, float* total_ms, int* launches, int cap);
 
 /* ------------------------------------------------------------------ encoder (models.py:132-225, 326-403) */
+/* --activation (train_mnist.py:423,516-519): the module-level activation of the encoder / generator */
+#define TVAE_ACT_LEAKYRELU 0     /* nn.LeakyReLU(), negative slope 0.01 */
+#define TVAE_ACT_TANH 1          /* nn.Tanh() */
+
 typedef struct {
     int B, C, n, k, p, G, O, z;
     int kpad;            /* row pitch of the filter bank: multiple of 32 and > C*k*k (tvae_bank_pitch) */
+    int act;             /* TVAE_ACT_* */
 } tvae_enc_shape;
 
 int tvae_bank_pitch(int C, int k);     /* row pitch (floats) of the fp32 bank GRADIENT dbank */
@@ -144,6 +149,7 @@ typedef struct {
     int H;                   /* hidden width */
     int L;                   /* number of hidden Linear(H,H) layers = num_layers - 1 */
     int n_out, zdim;
+    int act;                 /* TVAE_ACT_* */
 } tvae_gen_shape;
 
 typedef struct {

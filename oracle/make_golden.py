@@ -72,24 +72,33 @@ CASES = {
     # --generator-resid-layers (train_mnist.py:422,508, models.py:22-30, 84-86): three ResidLinear hidden layers
     "g9_mnist_resid": ("mnist", HotPathConfig("cfg1_gr", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=64, gen_layers=4,
                                               gen_resid=True), 3),
+    # --activation tanh (train_mnist.py:423,516-519), encoder and generator
+    "g10_mnist_tanh": ("mnist", HotPathConfig("cfg1_gt", C=1, n=14, k=7, p=2, G=4, z=2, O=32, hidden=64, gen_layers=3,
+                                              activation="tanh"), 3),
+    "g11_particles_tanh": ("particles", HotPathConfig("cfg4_gt", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
+                                                      likelihood="gaussian", ctf=True, activation="tanh"), 2),
     # --fit-noise (train_particles.py:663-666): generator n_out = 2, learned per-pixel log-variance, no CTF / mask
     "g7_particles_fitnoise": ("particles", HotPathConfig("cfg4_gf", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                          likelihood="gaussian", n_out=2), 3),
 }
 
 
+def act_cls(cfg):
+    return nn.Tanh if cfg.activation == "tanh" else nn.LeakyReLU
+
+
 def build_reference_models(ref_models, cfg: HotPathConfig, seed=0):
     with contextlib.redirect_stdout(io.StringIO()):
         gen = ref_models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers,
-                                          activation=nn.LeakyReLU, resid=cfg.gen_resid,
+                                          activation=act_cls(cfg), resid=cfg.gen_resid,
                                           fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
             assert cfg.k == cfg.n and cfg.p == cfg.n // 2 and cfg.G == 1
             enc = ref_models.InferenceNetwork_AttentionTranslation_UnimodalRotation(
-                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, activation=nn.LeakyReLU, groupconv=0)
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, activation=act_cls(cfg), groupconv=0)
         else:
             enc = ref_models.InferenceNetwork_AttentionTranslation_AttentionRotation(
-                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=act_cls(cfg),
                 groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
                 normal_prior_over_r=cfg.normal_prior_over_r)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()})

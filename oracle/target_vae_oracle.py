@@ -153,13 +153,14 @@ class EncoderParams:
     conv_r_b: torch.Tensor
     conv_z_w: torch.Tensor  # (2z,O,1,1,1)
     conv_z_b: torch.Tensor
+    activation: str = "leakyrelu"   # --activation (train_mnist.py:516-519): leakyrelu | tanh
 
     @staticmethod
-    def from_state_dict(sd, dtype=torch.float32):
+    def from_state_dict(sd, dtype=torch.float32, activation="leakyrelu"):
         g = lambda k: sd[k].detach().clone().to(dtype)
         return EncoderParams(g("conv1.weight"), g("conv1.bias"), g("conv2.weight"), g("conv2.bias"),
                              g("conv_a.weight"), g("conv_a.bias"), g("conv_r.weight"), g("conv_r.bias"),
-                             g("conv_z.weight"), g("conv_z.bias"))
+                             g("conv_z.weight"), g("conv_z.bias"), activation)
 
     def tensors(self):
         return [self.conv1_w, self.conv1_b, self.conv2_w, self.conv2_b, self.conv_a_w, self.conv_a_b,
@@ -177,8 +178,8 @@ def _conv1x1(x, w, b):
 def encoder_head_maps(y, p: EncoderParams, G: int, padding: int):
     """Returns raw head maps before priors/offsets: attn_raw (B,G,H',W'),
     theta_raw (B,2,G,H',W'), z (B,2z,G,H',W').  models.py:355-358,390-392."""
-    x = F.leaky_relu(groupconv_forward(y, p.conv1_w, p.conv1_b, G, padding), LRELU_SLOPE)
-    h = F.leaky_relu(_conv1x1(x, p.conv2_w, p.conv2_b), LRELU_SLOPE)
+    x = _act(groupconv_forward(y, p.conv1_w, p.conv1_b, G, padding), p.activation)
+    h = _act(_conv1x1(x, p.conv2_w, p.conv2_b), p.activation)
     attn = _conv1x1(h, p.conv_a_w, p.conv_a_b).squeeze(1)
     theta = _conv1x1(h, p.conv_r_w, p.conv_r_b)
     z = _conv1x1(h, p.conv_z_w, p.conv_z_b)
@@ -211,8 +212,8 @@ def encoder_forward(y, p: EncoderParams, G: int, padding: int, rot_refinement: b
 #      train_mnist.py:88-183 as well.
 # ----------------------------------------------------------------------------
 def plainconv_head_maps(y, p: EncoderParams, padding: int):
-    x = F.leaky_relu(F.conv2d(y, p.conv1_w, p.conv1_b, padding=padding), LRELU_SLOPE).unsqueeze(2)
-    h = F.leaky_relu(_conv1x1(x, p.conv2_w, p.conv2_b), LRELU_SLOPE)
+    x = _act(F.conv2d(y, p.conv1_w, p.conv1_b, padding=padding), p.activation).unsqueeze(2)
+    h = _act(_conv1x1(x, p.conv2_w, p.conv2_b), p.activation)
     attn = _conv1x1(h, p.conv_a_w, p.conv_a_b).squeeze(1)     # (B,1,H',W')
     theta = _conv1x1(h, p.conv_r_w, p.conv_r_b)               # (B,2,1,H',W')
     z = _conv1x1(h, p.conv_z_w, p.conv_z_b)                   # (B,2z,1,H',W')

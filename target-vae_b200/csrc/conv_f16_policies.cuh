@@ -113,7 +113,7 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
                     }
                     if (p.act) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = lrelu(v[q]);
+                        for (int q = 0; q < 8; ++q) v[q] = act_apply(v[q], p.act);
                     }
                     uint4 q4;
                     __half2 hv;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             v[j] = __uint_as_float(rr[j]) + s_bias[o0 + j];
-            if (p.act) v[j] = lrelu(v[j]);
+            if (p.act) v[j] = act_apply(v[j], p.act);
         }
         const long long off = (((long long)ti.a0 * g.G + r) * g.P + pos) * g.O + o0;
         if (p.x1h) {

@@ -41,6 +41,7 @@ struct Conv2HeadsParams {
     const float* head_add;    // [NH][G]
     __half* h;                // fp16 [R][O]
     float* heads;             // (B,NH,G,P)
+    int act;                  // kActTanh or LeakyReLU
 };
 
 template <int BN, int NHMAX>
@@ -87,7 +88,7 @@ struct Conv2Heads : PolicyBase {
             if (!ok || o0 >= p.O) continue;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = lrelu(__uint_as_float(rr[j]) + s_b2[o0 + j]);
+            for (int j = 0; j < 32; ++j) v[j] = act_apply(__uint_as_float(rr[j]) + s_b2[o0 + j], p.act);
             __half* dst = p.h + m * p.O + o0;
 #pragma unroll
             for (int j = 0; p.h != nullptr && j < 32; j += 8) {      // h == NULL: inference only, the hidden map is not kept
@@ -152,6 +153,7 @@ struct Conv2HeadsTCParams {
     long long R;
     int O, NH, NHpad, G, P;
     int store_h;              // 0: tmH is not set up and h is not written (inference only)
+    int act;                  // kActTanh or LeakyReLU
     const float* b2;
     const float* wh;          // [NH][O] fp32 (split into fp16 hi / lo operand tiles in setup)
     const float* bh;
@@ -254,10 +256,10 @@ struct Conv2HeadsTC : PolicyBase {
 #pragma unroll
                     for (int q = 0; q < 8; q += 4) {
                         const float4 bb = *reinterpret_cast<const float4*>(s_b2 + blk * 64 + hf * 32 + j + q);
-                        v[q] = lrelu(__uint_as_float(rr[hf][j + q]) + bb.x);
-                        v[q + 1] = lrelu(__uint_as_float(rr[hf][j + q + 1]) + bb.y);
-                        v[q + 2] = lrelu(__uint_as_float(rr[hf][j + q + 2]) + bb.z);
-                        v[q + 3] = lrelu(__uint_as_float(rr[hf][j + q + 3]) + bb.w);
+                        v[q] = act_apply(__uint_as_float(rr[hf][j + q]) + bb.x, p.act);
+                        v[q + 1] = act_apply(__uint_as_float(rr[hf][j + q + 1]) + bb.y, p.act);
+                        v[q + 2] = act_apply(__uint_as_float(rr[hf][j + q + 2]) + bb.z, p.act);
+                        v[q + 3] = act_apply(__uint_as_float(rr[hf][j + q + 3]) + bb.w, p.act);
                     }
                     uint32_t hi[4], lo[4];
 #pragma unroll

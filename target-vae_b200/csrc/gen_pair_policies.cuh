@@ -153,6 +153,7 @@ struct GenL1FwdPairParams {
     int E, H;
     const float* bias;        // (H)
     const float* zb;          // (B,H) latent_linear(z) or null
+    int act;                  // kActTanh or LeakyReLU
 };
 
 struct GenL1FwdPair : PolicyBase {
@@ -252,10 +253,10 @@ struct GenL1FwdPair : PolicyBase {
                         const int jj = j0 + hf * 32 + j + q;
                         const float4 bb = *reinterpret_cast<const float4*>(s_bias + jj);
                         const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[q] = lrelu(__uint_as_float(rr[hf][j + q]) + bb.x + bz.x);
-                        v[q + 1] = lrelu(__uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y);
-                        v[q + 2] = lrelu(__uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z);
-                        v[q + 3] = lrelu(__uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w);
+                        v[q] = act_apply(__uint_as_float(rr[hf][j + q]) + bb.x + bz.x, p.act);
+                        v[q + 1] = act_apply(__uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y, p.act);
+                        v[q + 2] = act_apply(__uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z, p.act);
+                        v[q + 3] = act_apply(__uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w, p.act);
                     }
                     *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) =
                         make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));

@@ -70,7 +70,7 @@ struct LinearNTArgs {
     int act = 0;
     const float* proj_w = nullptr; const float* proj_bias = nullptr; float* proj_out = nullptr; int n_proj = 0;
     void* C16 = nullptr; long long ldc16 = 0;
-    const void* aux16 = nullptr;
+    const void* aux16 = nullptr; int aux_act = 0;
     const float* acc_scale = nullptr; const float* store_scale = nullptr;
     float* colsum = nullptr; long long colsum_stride = 1;
 };
@@ -91,7 +91,7 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.num_tiles = cdiv(a.M, kBM) * p.tiles_n;
     p.C = a.C; p.ldc = a.ldc; p.bias = a.bias;
     p.row_bias = a.row_bias; p.rows_per_group = a.rows_per_group; p.ld_rb = a.ld_rb;
-    p.ld_aux = a.ld_aux; p.act = a.act;
+    p.ld_aux = a.ld_aux; p.act = a.act; p.aux_act = a.aux_act;
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
     p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;

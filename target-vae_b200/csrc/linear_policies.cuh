@@ -13,6 +13,13 @@ constexpr float kLreluSlope = 0.01f;
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kLreluSlope * x; }
 __device__ __forceinline__ float lrelu_grad_from_out(float a) { return a > 0.f ? 1.f : kLreluSlope; }
 
+// Activation selector carried by the shape structs and kernel parameters (--activation leakyrelu | tanh,
+// train_mnist.py:423,516-519): kActTanh selects tanh, every other value (zero-initialised parameter blocks) LeakyReLU(0.01).
+// Both derivatives are functions of the activation's OUTPUT, which is what the backward kernels have at hand.
+constexpr int kActTanh = 2;
+__device__ __forceinline__ float act_apply(float x, int act) { return act == kActTanh ? tanhf(x) : lrelu(x); }
+__device__ __forceinline__ float act_grad_from_out(float a, int act) { return act == kActTanh ? 1.f - a * a : lrelu_grad_from_out(a); }
+
 struct LinearNTParams {
     CUtensorMap tmA, tmB;
     int num_stages, num_tiles, tiles_n, k_chunks;
@@ -24,7 +31,8 @@ struct LinearNTParams {
     int rows_per_group;
     long long ld_rb;
     long long ld_aux;
-    int act;                  // 1 = LeakyReLU(0.01)
+    int act;                  // 0 = none, 1 = LeakyReLU(0.01), kActTanh = tanh
+    int aux_act;              // activation whose derivative aux16 yields (kActTanh or LeakyReLU)
     const float* proj_w;      // [n_proj][N] or null: fused  proj_out[m][o] += sum_n v[m][n] * proj_w[o][n]
     const float* proj_bias;   // [n_proj]
     float* proj_out;          // [M][n_proj], pre-zeroed
@@ -189,7 +197,7 @@ struct LinearNT : PolicyBase {
             }
             if (p.act) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.act);
             }
             if (ax_row) {
 #pragma unroll
@@ -201,8 +209,8 @@ struct LinearNT : PolicyBase {
                         for (int e = 0; e < 4; ++e) {
                             // lrelu'(a) from the sign bits of the packed halves (a > 0 <=> positive and non-zero)
                             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                            v[j + 2 * e] *= lrelu_grad_from_out(f.x);
-                            v[j + 2 * e + 1] *= lrelu_grad_from_out(f.y);
+                            v[j + 2 * e] *= act_grad_from_out(f.x, p.aux_act);
+                            v[j + 2 * e + 1] *= act_grad_from_out(f.y, p.aux_act);
                         }
                     }
                 }

@@ -41,7 +41,7 @@ __global__ void latent_bias_bwd_kernel(const float* __restrict__ dzb, const floa
 constexpr int kCoordRB = 64;
 template <int VEC>
 __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                              const float* __restrict__ zb, __half* __restrict__ a0, int H) {
+                                                              const float* __restrict__ zb, __half* __restrict__ a0, int H, int act) {
     __shared__ float2 s_x[kCoordRB];
     const int cgs = H / VEC, rpp = blockDim.x / cgs;
     const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
         for (int q = 0; q < VEC; q += 4) {
             float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0 + q));
-            o[q] = lrelu(fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x);
-            o[q + 1] = lrelu(fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y);
-            o[q + 2] = lrelu(fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z);
-            o[q + 3] = lrelu(fmaf(x.y, wy[q + 3], fmaf(x.x, wx[q + 3], bb[q + 3])) + z4.w);
+            o[q] = act_apply(fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x, act);
+            o[q + 1] = act_apply(fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y, act);
+            o[q + 2] = act_apply(fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z, act);
+            o[q + 3] = act_apply(fmaf(x.y, wy[q + 3], fmaf(x.x, wx[q + 3], bb[q + 3])) + z4.w, act);
         }
         if constexpr (VEC == 8)
             *reinterpret_cast<uint4*>(a0 + m * H + c0) = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "ptx.cuh"
+#include "linear_policies.cuh"   // act_apply / act_grad_from_out
 
 namespace tvae {
 
@@ -565,6 +566,7 @@ struct ThinBwdParams {
     int W, T, P;
     long long dt_outer, dt_chan;
     int rows_per_cta;
+    int act;             // activation that produced `a`: kActTanh or LeakyReLU (linear_policies.cuh)
 };
 constexpr int kThinRB = 64;
 
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(256) thin_bwd_kernel(ThinBwdParams p, int G) {
                         }
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
-                            g[v] *= (av[q][v] > 0.f ? 1.f : kSlope);
+                            g[v] *= act_grad_from_out(av[q][v], p.act);
                             dcol[v] += g[v];
                         }
                         if constexpr (H16) vec_store_h<VEC>(static_cast<__half*>(p.dpre) + (m0 + rr) * p.W + c0, g, store_scale);
@@ -890,8 +892,8 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
                 __half2* pa0 = reinterpret_cast<__half2*>(s_a + r0 * kThinPitch + col);
                 __half2* pa1 = reinterpret_cast<__half2*>(s_a + (r0 + 8) * kThinPitch + col);
                 const float2 a0 = __half22float2(*pa0), a1 = __half22float2(*pa1);
-                c[0] *= (a0.x > 0.f ? 1.f : kSlope); c[1] *= (a0.y > 0.f ? 1.f : kSlope);
-                c[2] *= (a1.x > 0.f ? 1.f : kSlope); c[3] *= (a1.y > 0.f ? 1.f : kSlope);
+                c[0] *= act_grad_from_out(a0.x, p.act); c[1] *= act_grad_from_out(a0.y, p.act);
+                c[2] *= act_grad_from_out(a1.x, p.act); c[3] *= act_grad_from_out(a1.y, p.act);
                 dcol[nt][0] += c[0] + c[2];
                 dcol[nt][1] += c[1] + c[3];
                 // in place: this element of the tile is read by no later ldmatrix of the warp (they move on to other columns)

@@ -368,7 +368,8 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
     const int NH = 3 + 2 * s->z;
     const long long R = (long long)g.B * g.G * g.P;
     cudaStream_t st = S(stream);
-    if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, nullptr, static_cast<__half*>(a->x1), 1, st))) return rc;
+    const int act = s->act == TVAE_ACT_TANH ? kActTanh : 1;
+    if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, nullptr, static_cast<__half*>(a->x1), act, st))) return rc;
     // ---- conv2 (1x1x1) + heads
     {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2_h), (long long)g.O * g.O);
@@ -383,6 +384,7 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
             q.k_chunks = 2;
             q.num_tiles = cdiv(R, kBM);
             q.b2 = a->b2; q.wh = a->wh; q.bh = a->bh; q.head_add = a->head_add; q.heads = a->heads;
+            q.act = act;
             return launch_gemm<Conv2HeadsTC>(q, Conv2HeadsTC::kExtraBytes, st);
         }
         Conv2HeadsParams p{};
@@ -394,6 +396,7 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
         p.k_chunks = cdiv(g.O, kBKh);
         p.num_tiles = cdiv(R, kBM);
         p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh; p.head_add = a->head_add; p.h = static_cast<__half*>(a->h); p.heads = a->heads;
+        p.act = act;
         const int extra = (NH * g.O + g.O) * static_cast<int>(sizeof(float));
         if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH>>(p, extra, st);
         else if (NH <= 8) rc = launch_gemm<Conv2Heads<128, 8>>(p, extra, st);
@@ -423,8 +426,11 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         ++g_launch_count; absmax_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->d_heads, n, a->scales + 7);
         ++g_launch_count; enc_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 7, a->wh, NH, a->w2, g.O, a->scales);
     }
-    // ---- heads backward: dhpre = (d_heads . Wh) * lrelu'(h), stored fp16 * s1; dWh, dbh, db2
-    if (g.O == 128 && NH <= 32) {
+    // ---- heads backward: dhpre = (d_heads . Wh) * act'(h), stored fp16 * s1; dWh, dbh, db2
+    // (the two fused kernels take the LeakyReLU derivative from sign bits of the staged tiles; tanh needs the values and
+    // runs on the general kernels)
+    const bool tanh_act = s->act == TVAE_ACT_TANH;
+    if (g.O == 128 && NH <= 32 && !tanh_act) {
         // tensor-core streaming kernel (enc_bwd_fused.cuh): one read of h and d_heads, one write of dhpre
         EncHeadsBwdParams q{};
         if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, 128, 128, kBM))) return rc;
@@ -445,6 +451,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         ThinBwdParams p{};
         p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
         p.store_scale = a->scales + 0;
+        p.act = tanh_act ? kActTanh : 0;
         p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
         // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]
         p.dt_outer = (long long)NH * g.G * g.P;   // stride of b
@@ -455,7 +462,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         if (rc) return rc;
     }
     ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
-    if (g.O == 128) {
+    if (g.O == 128 && !tanh_act) {
         // ---- one pass over dhpre and x1: dW2 = dhpre^T x1, dx1pre = (dhpre W2) * lrelu'(x1) (fp16 * s2) and its column
         // sums (the conv1 bias gradient)   (enc_bwd_fused.cuh)
         EncDx1Dw2Params q{};
@@ -483,6 +490,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_h; l.ldb = g.O;
         l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
         l.C = nullptr; l.C16 = a->dx1_16; l.ldc16 = g.O; l.aux16 = a->x1; l.ld_aux = g.O;
+        l.aux_act = tanh_act ? kActTanh : 0;
         l.acc_scale = a->scales + 1; l.store_scale = a->scales + 2;
         l.colsum = bias_grad_slot(g, a->dbank); l.colsum_stride = g.kpad;
         if ((rc = linear_nt(l, st))) return rc;
@@ -585,6 +593,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     const long long M = (long long)s->B * s->N;
     const int H = s->H, E = s->E;
     const CoordXform cx = make_xform(s, a);
+    const int gact = s->act == TVAE_ACT_TANH ? kActTanh : 1;
     ++g_launch_count; latent_bias_kernel<<<cdiv(s->B * H, 256), 256, 0, st>>>(a->z, a->wz, a->zb, s->B, H, s->zdim);
     __half* w1h = static_cast<__half*>(a->w_h);                                    // [H][E]
     __half* whh = static_cast<__half*>(a->w_h) + (long long)H * (E > 0 ? E : 2);   // [L][H][H]
@@ -599,7 +608,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
             if ((rc = make_tmap_2d_h(&q.tmB, w1h, H, E, E, 128))) return rc;
             if ((rc = make_tmap_2d_h(&q.tmC, a0, M, H, H, kBM))) return rc;
             q.cx = cx; q.wf_scaled = a->wf_scaled; q.bf = a->bf; q.E = E; q.H = H;
-            q.bias = a->b1; q.zb = a->zb;
+            q.bias = a->b1; q.zb = a->zb; q.act = gact;
             q.m_tiles = static_cast<int>(cdiv(M, kBM));
             q.k_chunks = cdiv(E, kBKh);
             q.num_tiles = cdiv(q.m_tiles, 2);
@@ -616,7 +625,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         const int BN = wide ? 256 : 128;
         if ((rc = make_tmap_2d_h(&p.tmB, w1h, H, E, E, BN))) return rc;
         p.cx = cx; p.wf_scaled = a->wf_scaled; p.bf = a->bf; p.E = E; p.H = H;
-        p.bias = a->b1; p.zb = a->zb; p.h1 = a0;
+        p.bias = a->b1; p.zb = a->zb; p.h1 = a0; p.act = gact;
         p.tiles_n = cdiv(H, BN);
         p.k_chunks = cdiv(E, kBKh);
         p.num_tiles = cdiv(M, kBM) * p.tiles_n;
@@ -628,10 +637,10 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         ++g_launch_count;
         if (H % 8 == 0 && H / 8 <= 256) {          // 16-byte stores
             const int cgs = H / 8, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
-            coord_layer_fwd_kernel<8><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+            coord_layer_fwd_kernel<8><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, gact);
         } else {
             const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
-            coord_layer_fwd_kernel<4><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+            coord_layer_fwd_kernel<4><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, gact);
         }
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
@@ -648,7 +657,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         l.M = static_cast<int>(M); l.N = H; l.K = H;
         l.C16 = acts + (long long)i * M * H; l.ldc16 = H;
         l.bias = a->bh + (long long)(i - 1) * H;
-        l.act = 1;
+        l.act = gact;
         if (i == s->L) { l.proj_w = a->wout; l.proj_bias = a->bout; l.proj_out = a->y_hat; l.n_proj = s->n_out; }
         if ((rc = linear_nt(l, st))) return rc;
     }
@@ -662,6 +671,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     const long long M = (long long)s->B * s->N;
     const int H = s->H, E = s->E, L = s->L;
     const CoordXform cx = make_xform(s, &a->f);
+    const int gact = s->act == TVAE_ACT_TANH ? kActTanh : 0;
     const __half* acts = static_cast<const __half*>(a->f.acts);
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwout, 0, sizeof(float) * s->n_out * H, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbout, 0, sizeof(float) * s->n_out, st));
@@ -690,6 +700,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         p.store_scale = a->scales + 2 * L;
         p.dWt = a->dwout; p.dbt = a->dbout; p.dcol = (L > 0) ? a->dbh + (long long)(L - 1) * H : nullptr;
         p.M = M; p.W = H; p.T = s->n_out; p.P = 1; p.dt_outer = s->n_out; p.dt_chan = 1;
+        p.act = gact;
         if ((rc = launch_thin_bwd<4, 4, false, true>(p, 1, st))) return rc;
     }
     // ---- hidden layers, last to first
@@ -702,7 +713,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         LinearNTArgs l{};
         l.A = dcur; l.lda = H; l.B = wt_h; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
-        l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H;
+        l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H; l.aux_act = gact;
         l.acc_scale = a->scales + 2 * i + 1; l.store_scale = a->scales + 2 * (i - 1);
         if (i - 1 >= 1) { l.colsum = a->dbh + (long long)(i - 2) * H; l.colsum_stride = 1; }   // bias gradient of hidden layer i-1
         if ((rc = linear_nt(l, st))) return rc;

@@ -94,9 +94,14 @@ class SpatialGenerator(nn.Module):
 
     # ---- helpers used by the fused step --------------------------------------------------------
     def _check_supported(self):
-        if not isinstance(self.layers[0], nn.LeakyReLU) or not hasattr(self, 'latent_linear'):
-            raise NotImplementedError("SpatialGenerator: only LeakyReLU, latent-conditioned generators are on the "
-                                      "accelerated path (SURVEY.md §8f)")
+        if not hasattr(self, 'latent_linear'):
+            raise NotImplementedError("SpatialGenerator: only latent-conditioned generators (latent_dim > 0) are on the "
+                                      "accelerated path")
+        return _ops.act_kind(self.layers[0])
+
+    def act_kind(self):
+        """ops.ACT_* of --activation (LeakyReLU or tanh, train_mnist.py:516-519)."""
+        return self._check_supported()
 
     def hot_path_params(self):
         """coord_linear.{weight,bias}, latent_linear.weight, (hidden weight, bias)*, out weight, bias."""
@@ -119,7 +124,7 @@ class SpatialGenerator(nn.Module):
             z = z.unsqueeze(0)
         _require_cuda(x, "SpatialGenerator.forward")
         fw, fb = self.fourier_buffers()
-        return TF.GeneratorFn.apply(fw, fb, (self._sigma, self._resid), x, z, *self.hot_path_params())
+        return TF.GeneratorFn.apply(fw, fb, (self._sigma, self._resid, self.act_kind()), x, z, *self.hot_path_params())
 
 
 class GroupConv(nn.Module):
@@ -225,13 +230,11 @@ class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
     def encoder_spec(self, theta_prior=np.pi):
         """One rotation slot, no rotation prior, no offsets; the N(0, theta_prior) prior on theta is the trainer's
         argument (train_mnist.py:171), not a module attribute."""
-        if not isinstance(self.activation, nn.LeakyReLU):
-            raise NotImplementedError("only LeakyReLU encoders are on the accelerated path (SURVEY.md §8f)")
         if self.groupconv != 0:
             raise NotImplementedError("attention/unimodal inference with groupconv > 0 (rotation pooling through fc_r) is "
                                       "not on the accelerated path; groupconv = 0 is")
         return TF.EncoderSpec(1, self.padding, self.latent_dim, False, False, float(theta_prior),
-                              theta_prior_std=float(theta_prior))
+                              theta_prior_std=float(theta_prior), act=_ops.act_kind(self.activation))
 
     def hot_path_params(self):
         return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv_a.weight, self.conv_a.bias,
@@ -279,12 +282,10 @@ class InferenceNetwork_AttentionTranslation_AttentionRotation(nn.Module):
 
     # ---- helpers used by the fused step --------------------------------------------------------
     def encoder_spec(self):
-        if not isinstance(self.activation, nn.LeakyReLU):
-            raise NotImplementedError("only LeakyReLU encoders are on the accelerated path (SURVEY.md §8f)")
         if self.groupconv < 1:
             raise NotImplementedError("the accelerated encoder needs groupconv in {4, 8, 16}")
         return TF.EncoderSpec(self.groupconv, self.padding, self.latent_dim, bool(self.rot_refinement),
-                              bool(self.normal_prior_over_r), float(self.theta_prior))
+                              bool(self.normal_prior_over_r), float(self.theta_prior), act=_ops.act_kind(self.activation))
 
     def hot_path_params(self):
         return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv_a.weight, self.conv_a.bias,

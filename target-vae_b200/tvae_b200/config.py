@@ -36,6 +36,7 @@ class HotPathConfig:
     # attn_unimodal: InferenceNetwork_AttentionTranslation_UnimodalRotation with --groupconv 0 (--r-inf unimodal):
     # plain Conv2d(C, O, n, padding n//2), i.e. k = n, p = n // 2, G = 1 here
     encoder: str = "attn_attn"
+    activation: str = "leakyrelu"  # --activation leakyrelu | tanh, encoder and generator alike (train_mnist.py:516-519)
     gen_resid: bool = False        # --generator-resid-layers: ResidLinear hidden layers (models.py:22-30, 84-86)
 
     @property

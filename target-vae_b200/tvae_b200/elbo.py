@@ -62,7 +62,8 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
     fw, fb = generator_model.fourier_buffers()
     gen_params = generator_model.hot_path_params()
     spec = TF.StepSpec(enc=es, sigma=generator_model._sigma, likelihood=likelihood, mask_radius=int(mask_radius),
-                       n_gen_hidden=(len(gen_params) - 5) // 2, gen_resid=bool(generator_model._resid))
+                       n_gen_hidden=(len(gen_params) - 5) // 2, gen_resid=bool(generator_model._resid),
+                       gen_act=generator_model.act_kind())
     spec.sync = sync
     return TF.FusedStepFn.apply(spec, x, y, ctf, noise["gumbel"], noise["r_z"], noise["r_theta"], fw, fb,
                                 *encoder_model.hot_path_params(), *gen_params)

@@ -67,6 +67,7 @@ class EncoderSpec:
     # std of the Normal prior on theta given (t, r): pi / G for the attention/attention branch (train_mnist.py:269-272);
     # the attention/unimodal branch uses eval_minibatch's theta_prior argument instead (train_mnist.py:171)
     theta_prior_std: Optional[float] = None
+    act: int = ops.ACT_LEAKYRELU       # --activation of the encoder (ops.ACT_*)
 
     def tables(self):
         p_r = ops.rotation_log_prior(self.G, self.rot_refinement, self.normal_prior_over_r, self.theta_prior)
@@ -83,7 +84,7 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
     if w1.dim() == 4:      # nn.Conv2d weight (O,C,k,k) of the groupconv = 0 encoder: one rotation, no rotation axis
         w1 = w1.unsqueeze(2)
     O, C, _, k, _ = w1.shape
-    s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z)
+    s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z, spec.act)
     p_r, offs = spec.tables()
     yc = ops.f32(y).reshape(B, C, n, n)
     wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.G, p_r, offs, y.device)
@@ -168,14 +169,14 @@ class GeneratorFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fourier_w, fourier_b, sigma, x, z, *params):
-        resid = False
-        if isinstance(sigma, tuple):       # (sigma, resid) from SpatialGenerator(resid=True)
-            sigma, resid = sigma
+        resid, act = False, ops.ACT_LEAKYRELU
+        if isinstance(sigma, tuple):       # (sigma, resid, act) from SpatialGenerator
+            sigma, resid, act = sigma
         w1, b1, wz = params[:3]
         hidden, (wout, bout) = params[3:-2], params[-2:]
         gw = _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout, resid)
         B, N = x.shape[0], x.shape[1]
-        s = ops.gen_shape(B, N, gw, z.shape[1])
+        s = ops.gen_shape(B, N, gw, z.shape[1], act)
         xc, zc = ops.f32(x).reshape(B * N, 2), ops.f32(z)
         y_hat, saved = ops.generator_fwd(s, gw, xc, None, None, zc)
         ctx.s, ctx.gw, ctx.saved = s, gw, saved
@@ -216,6 +217,7 @@ class StepSpec:
     mask_radius: int = 0
     n_gen_hidden: int = 1
     gen_resid: bool = False            # --generator-resid-layers: hidden layers are ResidLinear (models.py:22-30)
+    gen_act: int = ops.ACT_LEAKYRELU   # --activation of the generator (ops.ACT_*)
     # optional data-parallel gradient synchroniser (tvae_b200.dp.GradSync): bucket 0 (generator) is started as
     # soon as the generator backward has been issued, so its all-reduce overlaps the encoder backward.
     sync: Optional[object] = None
@@ -247,7 +249,7 @@ class FusedStepFn(torch.autograd.Function):
         hidden, (wout, bout) = gen_params[3:-2], gen_params[-2:]
         gw = _gen_weights(fourier_w, fourier_b, spec.sigma, w1, b1, wz, hidden, wout, bout, spec.gen_resid)
         N = xc.shape[0]
-        gs = ops.gen_shape(B, N, gw, es.z)
+        gs = ops.gen_shape(B, N, gw, es.z, spec.gen_act)
         y_hat, gsaved = ops.generator_fwd(gs, gw, xc, att["theta_b"], att["dx"], att["zb"])
 
         yflat = yc.reshape(B, -1)

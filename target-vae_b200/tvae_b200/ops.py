@@ -14,7 +14,7 @@ from ._lib import check, ptr, stream_ptr
 
 
 class EncShape(Structure):
-    _fields_ = [(n, c_int) for n in ("B", "C", "n", "k", "p", "G", "O", "z", "kpad")]
+    _fields_ = [(n, c_int) for n in ("B", "C", "n", "k", "p", "G", "O", "z", "kpad", "act")]
 
 
 class EncFwdArgs(Structure):
@@ -42,7 +42,7 @@ class AttnBwdArgs(Structure):
 
 
 class GenShape(Structure):
-    _fields_ = [(n, c_int) for n in ("B", "N", "E", "H", "L", "n_out", "zdim")]
+    _fields_ = [(n, c_int) for n in ("B", "N", "E", "H", "L", "n_out", "zdim", "act")]
 
 
 class GenFwdArgs(Structure):
@@ -115,8 +115,20 @@ def half(*shape, device):
 
 
 # ----------------------------------------------------------------------------------------------- encoder
-def enc_shape(B, C, n, k, p, G, O, z) -> EncShape:
-    return EncShape(B, C, n, k, p, G, O, z, L().tvae_bank_pitch(C, k))
+ACT_LEAKYRELU, ACT_TANH = 0, 1      # TVAE_ACT_* of include/tvae_b200.h
+
+
+def act_kind(module) -> int:
+    """nn.LeakyReLU() (default slope) / nn.Tanh() instance -> TVAE_ACT_*; anything else is not on the kernels."""
+    if isinstance(module, torch.nn.Tanh):
+        return ACT_TANH
+    if isinstance(module, torch.nn.LeakyReLU) and module.negative_slope == 0.01:
+        return ACT_LEAKYRELU
+    raise NotImplementedError(f"activation {module!r}: the trainers' --activation offers leakyrelu and tanh only")
+
+
+def enc_shape(B, C, n, k, p, G, O, z, act=ACT_LEAKYRELU) -> EncShape:
+    return EncShape(B, C, n, k, p, G, O, z, L().tvae_bank_pitch(C, k), act)
 
 
 def filter_bank_fwd(s: EncShape, weight: torch.Tensor) -> torch.Tensor:
@@ -304,8 +316,8 @@ class GenWeights:
         self.E = 0 if wf_scaled is None else wf_scaled.shape[0]
 
 
-def gen_shape(B, N, gw: GenWeights, zdim) -> GenShape:
-    return GenShape(B, N, gw.E, gw.H, gw.L, gw.wout.shape[0], zdim)
+def gen_shape(B, N, gw: GenWeights, zdim, act=ACT_LEAKYRELU) -> GenShape:
+    return GenShape(B, N, gw.E, gw.H, gw.L, gw.wout.shape[0], zdim, act)
 
 
 def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_h):

@@ -22,8 +22,8 @@ def load_golden(name):
 def oracle_inputs(cfg, B, seed=0, dtype=torch.float32, gain=1.0, requires_grad=True):
     es = {k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg, seed, gain).items()}
     gs = {k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()}
-    enc = orc.EncoderParams.from_state_dict(es, dtype)
-    gen = orc.GeneratorParams.from_state_dict(gs, cfg.sigma, resid=cfg.gen_resid, dtype=dtype)
+    enc = orc.EncoderParams.from_state_dict(es, dtype, activation=cfg.activation)
+    gen = orc.GeneratorParams.from_state_dict(gs, cfg.sigma, activation=cfg.activation, resid=cfg.gen_resid, dtype=dtype)
     if requires_grad:
         for t in enc.tensors():
             t.requires_grad_(True)

@@ -28,20 +28,25 @@ from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, HotPathConfig
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
-          "g7_particles_fitnoise", "g8_mnist_attn_unimodal", "g9_mnist_resid"]
+          "g7_particles_fitnoise", "g8_mnist_attn_unimodal", "g9_mnist_resid",
+          "g10_mnist_tanh", "g11_particles_tanh"]
+
+
+def act_cls(cfg):
+    return nn.Tanh if cfg.activation == "tanh" else nn.LeakyReLU
 
 
 def build_models(cfg, seed=0, gain=1.0):
     import src.models as models
     with contextlib.redirect_stdout(io.StringIO()):
-        gen = models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=nn.LeakyReLU,
+        gen = models.SpatialGenerator(cfg.z, cfg.hidden, n_out=cfg.n_out, num_layers=cfg.gen_layers, activation=act_cls(cfg),
                                       resid=cfg.gen_resid, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
             enc = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
-                                                                                activation=nn.LeakyReLU, groupconv=0)
+                                                                                activation=act_cls(cfg), groupconv=0)
         else:
             enc = models.InferenceNetwork_AttentionTranslation_AttentionRotation(
-                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=nn.LeakyReLU,
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=act_cls(cfg),
                 groupconv=cfg.G, rot_refinement=cfg.rot_refinement, theta_prior=cfg.theta_prior,
                 normal_prior_over_r=cfg.normal_prior_over_r)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg, seed).items()})

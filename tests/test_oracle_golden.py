@@ -11,7 +11,7 @@ from helpers import load_golden, oracle_inputs, oracle_step, rel_err, step_confi
 from oracle import target_vae_oracle as orc
 
 CASES = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
-          "g7_particles_fitnoise", "g9_mnist_resid"]
+          "g7_particles_fitnoise", "g9_mnist_resid", "g10_mnist_tanh", "g11_particles_tanh"]
 
 
 # --t-inf attention --r-inf unimodal --groupconv 0: plain Conv2d encoder, 4-tuple module interface
