@@ -73,7 +73,7 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
 constexpr int kStoreBlockBytes = kBM * 128;     // one staging buffer: 128 rows x 64 halves
 struct Conv1EpiState { int blocks; };           // 64-column blocks stored so far by this CTA (selects the staging buffer)
 
-template <class Prm>
+template <bool TANH, class Prm>
 __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, Conv1EpiState& st, int n0, uint32_t taddr, int row,
                                                    bool has_work, uint8_t* extra) {
     const ConvGeom& g = p.g;
@@ -111,10 +111,7 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
                         v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z;
                         v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w;
                     }
-                    if (p.act) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = act_apply(v[q], p.act);
-                    }
+                    if (p.act) act_vec<TANH>(v);
                     uint4 q4;
                     __half2 hv;
                     hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
@@ -145,10 +142,8 @@ __device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile&
         const int r = np / g.O, o0 = np - r * g.O;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(rr[j]) + s_bias[o0 + j];
-            if (p.act) v[j] = act_apply(v[j], p.act);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[o0 + j];
+        if (p.act) act_vec<TANH>(v);
         const long long off = (((long long)ti.a0 * g.G + r) * g.P + pos) * g.O + o0;
         if (p.x1h) {
             __half* dst = p.x1h + off;
@@ -193,7 +188,8 @@ struct Conv1FwdHParams {
                               // chunk walk reaches the next channel; the offset table is channel-relative
 };
 
-struct Conv1FwdH : PolicyBase {
+template <bool TANH>
+struct Conv1FwdHT : PolicyBase {
     static constexpr const char* kName = "conv1_fwd";
     using Params = Conv1FwdHParams;
     static constexpr bool kF16 = true;
@@ -369,9 +365,10 @@ struct Conv1FwdH : PolicyBase {
     }
     __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
                                     uint8_t* extra) {
-        conv1_fwd_epilogue(p, ti, st, n0, taddr, row, has_work, extra);
+        conv1_fwd_epilogue<TANH>(p, ti, st, n0, taddr, row, has_work, extra);
     }
 };
+using Conv1FwdH = Conv1FwdHT<false>;
 
 // ------------------------------------------------------------------------------------------------
 struct Conv1WgradHParams {

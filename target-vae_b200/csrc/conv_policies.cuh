@@ -44,7 +44,7 @@ struct Conv2HeadsParams {
     int act;                  // kActTanh or LeakyReLU
 };
 
-template <int BN, int NHMAX>
+template <int BN, int NHMAX, bool TANH = false>
 struct Conv2Heads : PolicyBase {
     static constexpr const char* kName = "conv2_heads";
     using Params = Conv2HeadsParams;
@@ -88,7 +88,8 @@ struct Conv2Heads : PolicyBase {
             if (!ok || o0 >= p.O) continue;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_apply(__uint_as_float(rr[j]) + s_b2[o0 + j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + s_b2[o0 + j];
+            act_vec<TANH>(v);
             __half* dst = p.h + m * p.O + o0;
 #pragma unroll
             for (int j = 0; p.h != nullptr && j < 32; j += 8) {      // h == NULL: inference only, the hidden map is not kept
@@ -161,7 +162,8 @@ struct Conv2HeadsTCParams {
     float* heads;
 };
 
-struct Conv2HeadsTC : PolicyBase {
+template <bool TANH>
+struct Conv2HeadsTCT : PolicyBase {
     static constexpr const char* kName = "conv2_heads";
     using Params = Conv2HeadsTCParams;
     static constexpr int kBN = 128;
@@ -256,11 +258,12 @@ struct Conv2HeadsTC : PolicyBase {
 #pragma unroll
                     for (int q = 0; q < 8; q += 4) {
                         const float4 bb = *reinterpret_cast<const float4*>(s_b2 + blk * 64 + hf * 32 + j + q);
-                        v[q] = act_apply(__uint_as_float(rr[hf][j + q]) + bb.x, p.act);
-                        v[q + 1] = act_apply(__uint_as_float(rr[hf][j + q + 1]) + bb.y, p.act);
-                        v[q + 2] = act_apply(__uint_as_float(rr[hf][j + q + 2]) + bb.z, p.act);
-                        v[q + 3] = act_apply(__uint_as_float(rr[hf][j + q + 3]) + bb.w, p.act);
+                        v[q] = __uint_as_float(rr[hf][j + q]) + bb.x;
+                        v[q + 1] = __uint_as_float(rr[hf][j + q + 1]) + bb.y;
+                        v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z;
+                        v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w;
                     }
+                    act_vec<TANH>(v);
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -342,5 +345,6 @@ struct Conv2HeadsTC : PolicyBase {
         ++st.tiles;
     }
 };
+using Conv2HeadsTC = Conv2HeadsTCT<false>;
 
 }  // namespace tvae

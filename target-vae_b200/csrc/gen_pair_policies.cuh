@@ -156,7 +156,8 @@ struct GenL1FwdPairParams {
     int act;                  // kActTanh or LeakyReLU
 };
 
-struct GenL1FwdPair : PolicyBase {
+template <bool TANH>
+struct GenL1FwdPairT : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
     using Params = GenL1FwdPairParams;
     static constexpr bool kF16 = true;
@@ -253,11 +254,12 @@ struct GenL1FwdPair : PolicyBase {
                         const int jj = j0 + hf * 32 + j + q;
                         const float4 bb = *reinterpret_cast<const float4*>(s_bias + jj);
                         const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[q] = act_apply(__uint_as_float(rr[hf][j + q]) + bb.x + bz.x, p.act);
-                        v[q + 1] = act_apply(__uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y, p.act);
-                        v[q + 2] = act_apply(__uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z, p.act);
-                        v[q + 3] = act_apply(__uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w, p.act);
+                        v[q] = __uint_as_float(rr[hf][j + q]) + bb.x + bz.x;
+                        v[q + 1] = __uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y;
+                        v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z;
+                        v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w;
                     }
+                    act_vec<TANH>(v);
                     *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) =
                         make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
                 }
@@ -272,5 +274,6 @@ struct GenL1FwdPair : PolicyBase {
         }
     }
 };
+using GenL1FwdPair = GenL1FwdPairT<false>;
 
 }  // namespace tvae

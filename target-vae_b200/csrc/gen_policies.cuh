@@ -74,7 +74,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int BN>
+template <int BN, bool TANH = false>
 struct GenL1Fwd : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
     using Params = GenL1FwdParams;
@@ -137,11 +137,12 @@ struct GenL1Fwd : PolicyBase {
                 for (int q = 0; q < 8; q += 4) {
                     const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + n0 + j + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + q));
-                    t[q] = act_apply(__uint_as_float(rr[j + q]) + bb.x + bz.x, p.act);
-                    t[q + 1] = act_apply(__uint_as_float(rr[j + q + 1]) + bb.y + bz.y, p.act);
-                    t[q + 2] = act_apply(__uint_as_float(rr[j + q + 2]) + bb.z + bz.z, p.act);
-                    t[q + 3] = act_apply(__uint_as_float(rr[j + q + 3]) + bb.w + bz.w, p.act);
+                    t[q] = __uint_as_float(rr[j + q]) + bb.x + bz.x;
+                    t[q + 1] = __uint_as_float(rr[j + q + 1]) + bb.y + bz.y;
+                    t[q + 2] = __uint_as_float(rr[j + q + 2]) + bb.z + bz.z;
+                    t[q + 3] = __uint_as_float(rr[j + q + 3]) + bb.w + bz.w;
                 }
+                act_vec<TANH>(t);
                 *reinterpret_cast<uint4*>(dst + j) =
                     make_uint4(pack_half2(t[0], t[1]), pack_half2(t[2], t[3]), pack_half2(t[4], t[5]), pack_half2(t[6], t[7]));
             }

@@ -106,6 +106,8 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
         if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;
         extra += LinearNT<128>::kEpiGroups * 2 * LinearNT<128>::kStageBytes;
     }
+    if (a.act == kActTanh || (a.aux16 && a.aux_act == kActTanh))
+        return wide ? launch_gemm<LinearNT<256, true>>(p, extra, stream) : launch_gemm<LinearNT<128, true>>(p, extra, stream);
     return wide ? launch_gemm<LinearNT<256>>(p, extra, stream) : launch_gemm<LinearNT<128>>(p, extra, stream);
 }
 

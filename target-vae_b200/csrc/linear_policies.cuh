@@ -17,8 +17,15 @@ __device__ __forceinline__ float lrelu_grad_from_out(float a) { return a > 0.f ?
 // train_mnist.py:423,516-519): kActTanh selects tanh, every other value (zero-initialised parameter blocks) LeakyReLU(0.01).
 // Both derivatives are functions of the activation's OUTPUT, which is what the backward kernels have at hand.
 constexpr int kActTanh = 2;
-__device__ __forceinline__ float act_apply(float x, int act) { return act == kActTanh ? tanhf(x) : lrelu(x); }
 __device__ __forceinline__ float act_grad_from_out(float a, int act) { return act == kActTanh ? 1.f - a * a : lrelu_grad_from_out(a); }
+// The run-time form is used by the CUDA-core backward kernels only (one FMA + select per element).
+// Compile-time variant for the tensor-core epilogues: their LeakyReLU instantiations must stay instruction-identical to
+// a build without tanh (a run-time selector, even hoisted, cost gen_l1_fwd +32 % and conv2_heads +11 %).
+template <bool TANH, int N>
+__device__ __forceinline__ void act_vec(float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = TANH ? tanhf(v[i]) : lrelu(v[i]);
+}
 
 struct LinearNTParams {
     CUtensorMap tmA, tmB;
@@ -31,8 +38,8 @@ struct LinearNTParams {
     int rows_per_group;
     long long ld_rb;
     long long ld_aux;
-    int act;                  // 0 = none, 1 = LeakyReLU(0.01), kActTanh = tanh
-    int aux_act;              // activation whose derivative aux16 yields (kActTanh or LeakyReLU)
+    int act;                  // 0 = none, else the activation of the instantiation (LinearNT<BN, TANH>)
+    int aux_act;              // informational: the host picks LinearNT<BN, true> when act or aux_act is kActTanh
     const float* proj_w;      // [n_proj][N] or null: fused  proj_out[m][o] += sum_n v[m][n] * proj_w[o][n]
     const float* proj_bias;   // [n_proj]
     float* proj_out;          // [M][n_proj], pre-zeroed
@@ -73,7 +80,7 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     return a[0];
 }
 
-template <int BN>
+template <int BN, bool TANH = false>
 struct LinearNT : PolicyBase {
     static constexpr const char* kName = "linear_nt";
     using Params = LinearNTParams;
@@ -195,10 +202,7 @@ struct LinearNT : PolicyBase {
                     }
                 }
             }
-            if (p.act) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.act);
-            }
+            if (p.act) act_vec<TANH>(v);
             if (ax_row) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
@@ -207,10 +211,10 @@ struct LinearNT : PolicyBase {
                         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            // lrelu'(a) from the sign bits of the packed halves (a > 0 <=> positive and non-zero)
+                            // lrelu'(a) from the sign of the packed halves; tanh'(a) = 1 - a^2
                             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                            v[j + 2 * e] *= act_grad_from_out(f.x, p.aux_act);
-                            v[j + 2 * e + 1] *= act_grad_from_out(f.y, p.aux_act);
+                            v[j + 2 * e] *= TANH ? 1.f - f.x * f.x : lrelu_grad_from_out(f.x);
+                            v[j + 2 * e + 1] *= TANH ? 1.f - f.y * f.y : lrelu_grad_from_out(f.y);
                         }
                     }
                 }

@@ -39,9 +39,9 @@ __global__ void latent_bias_bwd_kernel(const float* __restrict__ dzb, const floa
 // thread = VEC adjacent columns x one row slot streams 16-byte (VEC = 8) or 8-byte (VEC = 4) stores (HBM-bound: one
 // write of a0).
 constexpr int kCoordRB = 64;
-template <int VEC>
+template <int VEC, bool TANH>
 __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                              const float* __restrict__ zb, __half* __restrict__ a0, int H, int act) {
+                                                              const float* __restrict__ zb, __half* __restrict__ a0, int H) {
     __shared__ float2 s_x[kCoordRB];
     const int cgs = H / VEC, rpp = blockDim.x / cgs;
     const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
         for (int q = 0; q < VEC; q += 4) {
             float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0 + q));
-            o[q] = act_apply(fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x, act);
-            o[q + 1] = act_apply(fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y, act);
-            o[q + 2] = act_apply(fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z, act);
-            o[q + 3] = act_apply(fmaf(x.y, wy[q + 3], fmaf(x.x, wx[q + 3], bb[q + 3])) + z4.w, act);
+            o[q] = fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x;
+            o[q + 1] = fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y;
+            o[q + 2] = fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z;
+            o[q + 3] = fmaf(x.y, wy[q + 3], fmaf(x.x, wx[q + 3], bb[q + 3])) + z4.w;
         }
+        act_vec<TANH>(o);
         if constexpr (VEC == 8)
             *reinterpret_cast<uint4*>(a0 + m * H + c0) = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
         else

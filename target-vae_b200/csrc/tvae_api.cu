@@ -227,6 +227,7 @@ int conv1_forward(const ConvGeom& g, const float* y, const void* bank16, const f
         if ((rc = make_tmap_3d_store_h(&p.tmX, x1h, (uint64_t)g.B * g.G, g.P, g.O, kBM))) return rc;
         extra += 2 * kStoreBlockBytes;
     }
+    if (act == kActTanh) return launch_gemm2<Conv1FwdHT<true>>(p, extra, st, p.pairs);
     return launch_gemm2<Conv1FwdH>(p, extra, st, p.pairs);
 }
 // conv1 weight gradient w.r.t. the rotated bank (dbank pre-zeroed); dx1 is fp16 [(b,r,pos)][O] times 1 / *acc_scale
@@ -385,6 +386,7 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
             q.num_tiles = cdiv(R, kBM);
             q.b2 = a->b2; q.wh = a->wh; q.bh = a->bh; q.head_add = a->head_add; q.heads = a->heads;
             q.act = act;
+            if (act == kActTanh) return launch_gemm<Conv2HeadsTCT<true>>(q, Conv2HeadsTC::kExtraBytes, st);
             return launch_gemm<Conv2HeadsTC>(q, Conv2HeadsTC::kExtraBytes, st);
         }
         Conv2HeadsParams p{};
@@ -398,7 +400,13 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
         p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh; p.head_add = a->head_add; p.h = static_cast<__half*>(a->h); p.heads = a->heads;
         p.act = act;
         const int extra = (NH * g.O + g.O) * static_cast<int>(sizeof(float));
-        if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH>>(p, extra, st);
+        if (act == kActTanh) {
+            if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH, true>>(p, extra, st);
+            else if (NH <= 8) rc = launch_gemm<Conv2Heads<128, 8, true>>(p, extra, st);
+            else if (NH <= 20) rc = launch_gemm<Conv2Heads<128, 20, true>>(p, extra, st);
+            else rc = launch_gemm<Conv2Heads<128, kMaxNH, true>>(p, extra, st);
+        }
+        else if (wide) rc = launch_gemm<Conv2Heads<256, kMaxNH>>(p, extra, st);
         else if (NH <= 8) rc = launch_gemm<Conv2Heads<128, 8>>(p, extra, st);
         else if (NH <= 20) rc = launch_gemm<Conv2Heads<128, 20>>(p, extra, st);
         else rc = launch_gemm<Conv2Heads<128, kMaxNH>>(p, extra, st);
@@ -618,7 +626,8 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
             extra = (extra + 1023) / 1024 * 1024;
             q.stage_off = extra;
             extra += 2 * kStoreBlockBytes;
-            if ((rc = launch_gemm2<GenL1FwdPair>(q, extra, st))) return rc;
+            rc = gact == kActTanh ? launch_gemm2<GenL1FwdPairT<true>>(q, extra, st) : launch_gemm2<GenL1FwdPair>(q, extra, st);
+            if (rc) return rc;
         } else {
         GenL1FwdParams p{};
         const bool wide = H > 128;
@@ -630,17 +639,20 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         p.k_chunks = cdiv(E, kBKh);
         p.num_tiles = cdiv(M, kBM) * p.tiles_n;
         const int extra = E * 16;
-        rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
+        if (gact == kActTanh) rc = wide ? launch_gemm<GenL1Fwd<256, true>>(p, extra, st) : launch_gemm<GenL1Fwd<128, true>>(p, extra, st);
+        else rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
         if (rc) return rc;
         }
     } else {
         ++g_launch_count;
         if (H % 8 == 0 && H / 8 <= 256) {          // 16-byte stores
             const int cgs = H / 8, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
-            coord_layer_fwd_kernel<8><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, gact);
+            if (gact == kActTanh) coord_layer_fwd_kernel<8, true><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+            else coord_layer_fwd_kernel<8, false><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
         } else {
             const int cgs = H / 4, rpp = 256 / cgs > 0 ? 256 / cgs : 1;
-            coord_layer_fwd_kernel<4><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H, gact);
+            if (gact == kActTanh) coord_layer_fwd_kernel<4, true><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
+            else coord_layer_fwd_kernel<4, false><<<cdiv(M, kCoordRB), cgs * rpp, 0, st>>>(cx, a->w1, a->b1, a->zb, a0, H);
         }
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
