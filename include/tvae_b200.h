@@ -80,8 +80,14 @@ typedef struct {
     void* x1;                /* out fp16 [B*G*P][O]  LeakyReLU(conv1) */
     void* h;                 /* out fp16 [B*G*P][O]  LeakyReLU(conv2); NULL = inference only (clustering_*.get_latent,
                               * clustering_mnist.py:81-161): the hidden map feeds the heads on chip and is not written */
-    float* heads;            /* out (B,NH,G,P) */
+    float* heads;            /* out (B,NH,G,P); (B,NH,1,P) with rotation pooling */
     void* w2_h;              /* scratch fp16 (O,O) */
+    /* Rotation pooling of InferenceNetwork_AttentionTranslation_UnimodalRotation with groupconv > 0 (models.py:301-304):
+     * fc_w != NULL inserts xp = fc_r(x1 over the rotation axis) between conv1 and conv2; conv2, the heads and h then have
+     * B*P rows (one rotation slot) and head_add is [NH][1]. */
+    const float* fc_w;       /* fc_r.weight (G) or NULL */
+    const float* fc_b;       /* fc_r.bias (1) */
+    void* xp;                /* out fp16 [B*P][O] */
 } tvae_enc_fwd_args;
 /* GroupConv.forward + InferenceNetwork_AttentionTranslation_AttentionRotation.forward up to the head maps
  * (models.py:202-225, 355-358, 382, 390-399). */
@@ -103,6 +109,12 @@ typedef struct {
     float* db2;              /* out (O) */
     float* dwh;              /* out [NH][O] */
     float* dbh;              /* out [NH] */
+    /* rotation pooling (fc_w != NULL, see tvae_enc_fwd_args): h, d_heads, dhpre have B*P rows */
+    const float* fc_w;       /* fc_r.weight (G) or NULL */
+    const void* xp;          /* in: saved fp16 [B*P][O] */
+    void* dxp16;             /* scratch fp16 [B*P][O]: d(xp) * s2 */
+    float* dfc_w;            /* out (G) */
+    float* dfc_b;            /* out (1) */
 } tvae_enc_bwd_args;
 /* autograd of the above (convolution_backward x5, train_mnist.py:321). */
 int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* stream);

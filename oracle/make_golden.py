@@ -77,6 +77,9 @@ CASES = {
                                               activation="tanh"), 3),
     "g11_particles_tanh": ("particles", HotPathConfig("cfg4_gt", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                       likelihood="gaussian", ctf=True, activation="tanh"), 2),
+    # --t-inf attention --r-inf unimodal --groupconv 4: P4 group conv pooled over the rotations by fc_r (models.py:281-285, 301-304)
+    "g12_mnist_attn_unimodal_p4": ("mnist", HotPathConfig("cfg1_gup", C=1, n=16, k=16, p=8, G=4, z=2, O=32, hidden=64,
+                                                          rot_refinement=False, encoder="attn_unimodal"), 3),
     # --fit-noise (train_particles.py:663-666): generator n_out = 2, learned per-pixel log-variance, no CTF / mask
     "g7_particles_fitnoise": ("particles", HotPathConfig("cfg4_gf", C=1, n=16, k=9, p=2, G=8, z=2, O=32, hidden=32,
                                                          likelihood="gaussian", n_out=2), 3),
@@ -93,9 +96,9 @@ def build_reference_models(ref_models, cfg: HotPathConfig, seed=0):
                                           activation=act_cls(cfg), resid=cfg.gen_resid,
                                           fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
-            assert cfg.k == cfg.n and cfg.p == cfg.n // 2 and cfg.G == 1
+            assert cfg.k == cfg.n and cfg.p == cfg.n // 2
             enc = ref_models.InferenceNetwork_AttentionTranslation_UnimodalRotation(
-                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, activation=act_cls(cfg), groupconv=0)
+                cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, activation=act_cls(cfg), groupconv=cfg.G if cfg.G > 1 else 0)
         else:
             enc = ref_models.InferenceNetwork_AttentionTranslation_AttentionRotation(
                 cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=act_cls(cfg),
@@ -182,7 +185,7 @@ def run_case(name, ref_models, trainers, clustering):
     # rotated filter bank and group conv output (a-1, a-2)
     with torch.no_grad():
         if unimodal:
-            out["conv1_out"] = enc.conv1(y).numpy()
+            out["conv1_out"] = (enc.conv1(y, dev) if cfg.G > 1 else enc.conv1(y)).numpy()
         else:
             out["bank"] = enc.conv1.trans_filter(dev).numpy()
             out["conv1_out"] = enc.conv1(y, dev).numpy()

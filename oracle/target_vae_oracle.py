@@ -154,20 +154,26 @@ class EncoderParams:
     conv_z_w: torch.Tensor  # (2z,O,1,1,1)
     conv_z_b: torch.Tensor
     activation: str = "leakyrelu"   # --activation (train_mnist.py:516-519): leakyrelu | tanh
+    fc_r_w: Optional[torch.Tensor] = None   # (1,G)  rotation pooling of the attention/unimodal encoder, models.py:284
+    fc_r_b: Optional[torch.Tensor] = None   # (1,)
 
     @staticmethod
     def from_state_dict(sd, dtype=torch.float32, activation="leakyrelu"):
         g = lambda k: sd[k].detach().clone().to(dtype)
         return EncoderParams(g("conv1.weight"), g("conv1.bias"), g("conv2.weight"), g("conv2.bias"),
                              g("conv_a.weight"), g("conv_a.bias"), g("conv_r.weight"), g("conv_r.bias"),
-                             g("conv_z.weight"), g("conv_z.bias"), activation)
+                             g("conv_z.weight"), g("conv_z.bias"), activation,
+                             g("fc_r.weight") if "fc_r.weight" in sd else None,
+                             g("fc_r.bias") if "fc_r.bias" in sd else None)
 
     def tensors(self):
-        return [self.conv1_w, self.conv1_b, self.conv2_w, self.conv2_b, self.conv_a_w, self.conv_a_b,
-                self.conv_r_w, self.conv_r_b, self.conv_z_w, self.conv_z_b]
+        t = [self.conv1_w, self.conv1_b, self.conv2_w, self.conv2_b, self.conv_a_w, self.conv_a_b,
+             self.conv_r_w, self.conv_r_b, self.conv_z_w, self.conv_z_b]
+        return t + ([self.fc_r_w, self.fc_r_b] if self.fc_r_w is not None else [])
 
+    # state_dict names in tensors() order (fc_r.* only when present: zip() with tensors() stops at the shorter list)
     names = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv_a.weight", "conv_a.bias",
-             "conv_r.weight", "conv_r.bias", "conv_z.weight", "conv_z.bias"]
+             "conv_r.weight", "conv_r.bias", "conv_z.weight", "conv_z.bias", "fc_r.weight", "fc_r.bias"]
 
 
 def _conv1x1(x, w, b):
@@ -212,7 +218,14 @@ def encoder_forward(y, p: EncoderParams, G: int, padding: int, rot_refinement: b
 #      train_mnist.py:88-183 as well.
 # ----------------------------------------------------------------------------
 def plainconv_head_maps(y, p: EncoderParams, padding: int):
-    x = _act(F.conv2d(y, p.conv1_w, p.conv1_b, padding=padding), p.activation).unsqueeze(2)
+    if p.fc_r_w is not None:
+        # groupconv = G > 0 (models.py:281-285, 301-304): P_G group conv, activation, then nn.Linear(G, 1) over the
+        # rotation axis - (B,O,G,H',W') -> (B,O,H',W'); conv2 follows without an activation in between
+        G = p.fc_r_w.shape[1]
+        x = _act(groupconv_forward(y, p.conv1_w, p.conv1_b, G, padding), p.activation)
+        x = (F.linear(x.permute(0, 1, 3, 4, 2), p.fc_r_w, p.fc_r_b).squeeze(4)).unsqueeze(2)
+    else:
+        x = _act(F.conv2d(y, p.conv1_w, p.conv1_b, padding=padding), p.activation).unsqueeze(2)
     h = _act(_conv1x1(x, p.conv2_w, p.conv2_b), p.activation)
     attn = _conv1x1(h, p.conv_a_w, p.conv_a_b).squeeze(1)     # (B,1,H',W')
     theta = _conv1x1(h, p.conv_r_w, p.conv_r_b)               # (B,2,1,H',W')

@@ -996,6 +996,144 @@ __global__ void __launch_bounds__(256) enc_bwd_scales_kernel(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Rotation pooling of InferenceNetwork_AttentionTranslation_UnimodalRotation with groupconv = G > 0 (models.py:301-304):
+//   xp[(b,pos)][o] = sum_r fc_w[r] * x1[(b*G + r)*P + pos][o] + fc_b          (nn.Linear(G, 1) over the rotation axis;
+// x1 = act(conv1) is the group-conv activation, xp feeds conv2 un-activated).  HBM-bound: one read of x1, one write of xp.
+// Thread = (row of the pass, group of 8 channels); a CTA walks `rows_per_cta` consecutive (b,pos) rows.
+// ------------------------------------------------------------------------------------------
+struct RotPoolParams {
+    const __half* x1;        // [B*G*P][O]
+    const float* fc_w;       // [G]
+    const float* fc_b;       // [1]
+    __half* xp;              // fwd out [B*P][O]
+    // backward
+    const __half* dxp;       // [B*P][O] = d(xp) * s2
+    __half* dx1;             // out [B*G*P][O] = d(conv1 pre-activation) * s2 * c
+    const float* scales;     // [2] = s2, [3] = 1/s2, [4] = c (power of two, set by rot_pool_scales_kernel), [5] = 1/(s2 c)
+    float* dfc_w;            // out [G]  (pre-zeroed)
+    float* dfc_b;            // out [1]  (pre-zeroed)
+    float* db1;              // conv1 bias gradient slot, stride db1_stride, += sum over rows of d(conv1 pre-activation)
+    long long db1_stride;
+    int B, G, P, O, act;
+    int rows_per_cta;
+};
+
+__global__ void rot_pool_scales_kernel(const float* __restrict__ fc_w, int G, float* __restrict__ scales) {
+    float mw = 0.f;
+    for (int r = 0; r < G; ++r) mw = fmaxf(mw, fabsf(fc_w[r]));
+    float c = 1.f;
+    while (c * mw > 1.f && c > 1e-30f) c *= 0.5f;        // |w_r| c <= 1: the scaled fp16 gradient cannot grow past d(xp)'s bound
+    scales[4] = c;
+    scales[5] = scales[3] / c;
+}
+
+__device__ __forceinline__ void load8h(const __half* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8h(__half* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256) rot_pool_fwd_kernel(RotPoolParams p) {
+    const int cgs = p.O / 8, rpp = 256 / cgs;
+    const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
+    if (rs >= rpp) return;
+    const long long rows = (long long)p.B * p.P;
+    const long long row0 = (long long)blockIdx.x * p.rows_per_cta;
+    const long long row1 = min(rows, row0 + p.rows_per_cta);
+    const float fb = __ldg(p.fc_b);
+    for (long long m = row0 + rs; m < row1; m += rpp) {
+        const long long b = m / p.P;
+        const int pos = static_cast<int>(m - b * p.P);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fb;
+        for (int r = 0; r < p.G; ++r) {
+            float v[8];
+            load8h(p.x1 + (((b * p.G + r) * p.P + pos) * p.O + cg * 8), v);
+            const float w = __ldg(p.fc_w + r);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+        }
+        store8h(p.xp + m * p.O + cg * 8, acc);
+    }
+}
+
+// Adjoint: d(conv1 pre)[(b,r,pos)][o] = fc_w[r] * d(xp)[(b,pos)][o] * act'(x1[(b,r,pos)][o]),
+// dfc_w[r] = sum d(xp) * x1_r, dfc_b = sum d(xp), conv1 bias gradient = column sums of d(conv1 pre).
+__global__ void __launch_bounds__(256) rot_pool_bwd_kernel(RotPoolParams p) {
+    extern __shared__ float s_red[];                      // [O] bias-gradient partial sums, then [G + 1] fc gradients
+    float* s_db = s_red;
+    float* s_fc = s_red + p.O;
+    for (int i = threadIdx.x; i < p.O + p.G + 1; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+    const int cgs = p.O / 8, rpp = 256 / cgs;
+    const int cg = threadIdx.x % cgs, rs = threadIdx.x / cgs;
+    const long long rows = (long long)p.B * p.P;
+    const long long row0 = (long long)blockIdx.x * p.rows_per_cta;
+    const long long row1 = min(rows, row0 + p.rows_per_cta);
+    const float inv_s2 = p.scales[3], c = p.scales[4], inv_s3 = p.scales[5];
+    float db[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) db[e] = 0.f;
+    float dfb = 0.f;
+    // uniform trip counts for the whole CTA (the warp shuffles below need every lane): lanes without a row contribute zeros
+    for (long long mb = row0; mb < row1; mb += rpp) {
+        const long long m = mb + rs;
+        const bool valid = rs < rpp && m < row1;
+        const long long b = valid ? m / p.P : 0;
+        const int pos = valid ? static_cast<int>(m - b * p.P) : 0;
+        float d[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = 0.f;
+        if (valid) load8h(p.dxp + m * p.O + cg * 8, d);   // d(xp) * s2
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dfb += d[e];
+        for (int r = 0; r < p.G; ++r) {
+            float dw = 0.f;
+            if (valid) {
+                const long long off = ((b * p.G + r) * p.P + pos) * p.O + cg * 8;
+                float v[8], g[8];
+                load8h(p.x1 + off, v);
+                const float w = __ldg(p.fc_w + r) * c;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    dw = fmaf(d[e], v[e], dw);
+                    g[e] = d[e] * w * act_grad_from_out(v[e], p.act);      // * s2 * c
+                    db[e] += g[e];
+                }
+                store8h(p.dx1 + off, g);
+            }
+            // warp-level sum of this rotation's fc_w gradient, then one shared atomic per warp
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) dw += __shfl_xor_sync(0xffffffffu, dw, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(s_fc + r, dw);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(s_db + cg * 8 + e, db[e]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dfb += __shfl_xor_sync(0xffffffffu, dfb, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(s_fc + p.G, dfb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.O; i += blockDim.x) atomicAdd(p.db1 + (long long)i * p.db1_stride, s_db[i] * inv_s3);
+    for (int i = threadIdx.x; i < p.G; i += blockDim.x) atomicAdd(p.dfc_w + i, s_fc[i] * inv_s2);
+    if (threadIdx.x == 0) atomicAdd(p.dfc_b, s_fc[p.G] * inv_s2);
+}
+
 // Generator backward: dpre_L = (d_yhat . Wout) lrelu', dpre_{i-1} = (dpre_i . W_i) lrelu'; dpre_i is stored as
 // fp16(dpre_i * s_i) with s_i = scales[2i], 1/s_i = scales[2i + 1], i = 0..L.  Bounds: |dpre_L| <= amax max_c sum_o |Wout[o][c]|,
 // |dpre_{i-1}| <= bound_i max_c sum_j |W_i[j][c]|.

@@ -283,6 +283,24 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
     p.skip = 1;
     return b128 ? launch_gemm2<Conv1WgradH128>(p, extra, st) : launch_gemm2<Conv1WgradH>(p, extra, st);
 }
+// rotation pooling between conv1 and conv2 (simt_kernels.cuh: rot_pool_fwd_kernel / rot_pool_bwd_kernel)
+inline int rot_pool_rows_per_cta(long long rows, int O) {
+    const int rpp = 256 / (O / 8);
+    long long per = (rows + 4LL * sm_count() - 1) / (4LL * sm_count());
+    per = (per + rpp - 1) / rpp * rpp;
+    return static_cast<int>(per < rpp ? rpp : per);
+}
+inline int rot_pool_forward(const ConvGeom& g, const __half* x1, const float* fc_w, const float* fc_b, __half* xp, cudaStream_t st) {
+    TVAE_REQUIRE(g.O % 8 == 0 && g.O / 8 <= 256, "rotation pooling: kernel count must be a multiple of 8");
+    RotPoolParams p{};
+    p.x1 = x1; p.fc_w = fc_w; p.fc_b = fc_b; p.xp = xp;
+    p.B = g.B; p.G = g.G; p.P = g.P; p.O = g.O;
+    const long long rows = (long long)g.B * g.P;
+    p.rows_per_cta = rot_pool_rows_per_cta(rows, g.O);
+    ++g_launch_count; rot_pool_fwd_kernel<<<cdiv(rows, p.rows_per_cta), 256, 0, st>>>(p);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 // conv1 bias gradient slot: column K of dbank row (r = 0, o)  (summed over r by tvae_filter_bank_bwd)
 inline float* bias_grad_slot(const ConvGeom& g, float* dbank) { return dbank + g.K; }
 }  // namespace
@@ -365,19 +383,28 @@ int tvae_groupconv_wgrad(const tvae_enc_shape* s, const float* y, const float* d
 int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* stream) {
     int rc = check_enc_shape(s);
     if (rc) return rc;
-    const ConvGeom g = make_geom(s);
+    ConvGeom g = make_geom(s);
     const int NH = 3 + 2 * s->z;
-    const long long R = (long long)g.B * g.G * g.P;
+    long long R = (long long)g.B * g.G * g.P;
     cudaStream_t st = S(stream);
     const int act = s->act == TVAE_ACT_TANH ? kActTanh : 1;
     if ((rc = conv1_forward(g, a->y, a->bank, a->conv1_bias, nullptr, static_cast<__half*>(a->x1), act, st))) return rc;
+    const void* x_in = a->x1;
+    if (a->fc_w) {
+        // ---- rotation pooling (attention/unimodal encoder, groupconv > 0): conv2 and the heads see one rotation slot
+        TVAE_REQUIRE(a->fc_b && a->xp, "encoder: rotation pooling needs fc_b and xp");
+        if ((rc = rot_pool_forward(g, static_cast<const __half*>(a->x1), a->fc_w, a->fc_b, static_cast<__half*>(a->xp), st))) return rc;
+        x_in = a->xp;
+        R = (long long)g.B * g.P;
+        g.G = 1;
+    }
     // ---- conv2 (1x1x1) + heads
     {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2_h), (long long)g.O * g.O);
         if (g.O == 128 && NH <= 32) {
             // heads on the tensor core, h through staged TMA stores (Conv2HeadsTC)
             Conv2HeadsTCParams q{};
-            if ((rc = make_tmap_2d_h(&q.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
+            if ((rc = make_tmap_2d_h(&q.tmA, x_in, R, g.O, g.O, kBM))) return rc;
             if ((rc = make_tmap_2d_h(&q.tmB, a->w2_h, g.O, g.O, g.O, 128))) return rc;
             q.store_h = a->h != nullptr;
             if (q.store_h && (rc = make_tmap_2d_h(&q.tmH, a->h, R, g.O, g.O, kBM))) return rc;
@@ -392,7 +419,7 @@ int tvae_encoder_fwd(const tvae_enc_shape* s, const tvae_enc_fwd_args* a, void* 
         Conv2HeadsParams p{};
         const bool wide = g.O > 128;
         const int BN = wide ? 256 : 128;
-        if ((rc = make_tmap_2d_h(&p.tmA, a->x1, R, g.O, g.O, kBM))) return rc;
+        if ((rc = make_tmap_2d_h(&p.tmA, x_in, R, g.O, g.O, kBM))) return rc;
         if ((rc = make_tmap_2d_h(&p.tmB, a->w2_h, g.O, g.O, g.O, BN))) return rc;
         p.R = R; p.O = g.O; p.NH = NH; p.G = g.G; p.P = g.P;
         p.k_chunks = cdiv(g.O, kBKh);
@@ -420,7 +447,11 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
     if (rc) return rc;
     const ConvGeom g = make_geom(s);
     const int NH = 3 + 2 * s->z;
-    const long long R = (long long)g.B * g.G * g.P;
+    // rotation pooling (attention/unimodal encoder, groupconv > 0): everything after conv1 sees ONE rotation slot
+    const bool pooled = a->fc_w != nullptr;
+    TVAE_REQUIRE(!pooled || (a->xp && a->dxp16 && a->dfc_w && a->dfc_b), "encoder backward: rotation pooling needs xp, dxp16, dfc_w, dfc_b");
+    const int G2 = pooled ? 1 : g.G;
+    const long long R = (long long)g.B * G2 * g.P;          // rows of h / dhpre / the conv2 input
     cudaStream_t st = S(stream);
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dwh, 0, sizeof(float) * NH * g.O, st));
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->dbh, 0, sizeof(float) * NH, st));
@@ -430,7 +461,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
     // ---- power-of-two scales that keep the fp16 gradient operands in range (computed on the device, no sync)
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->scales, 0, sizeof(float) * 8, st));
     {
-        const long long n = (long long)g.B * NH * g.G * g.P;
+        const long long n = (long long)g.B * NH * G2 * g.P;
         ++g_launch_count; absmax_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->d_heads, n, a->scales + 7);
         ++g_launch_count; enc_bwd_scales_kernel<<<1, 256, 0, st>>>(a->scales + 7, a->wh, NH, a->w2, g.O, a->scales);
     }
@@ -443,7 +474,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         EncHeadsBwdParams q{};
         if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, 128, 128, kBM))) return rc;
         if ((rc = make_tmap_2d_h(&q.tmC, a->dhpre, R, 128, 128, kBM))) return rc;
-        q.R = R; q.num_tiles = static_cast<int>(cdiv(R, kBM)); q.NH = NH; q.G = g.G; q.P = g.P;
+        q.R = R; q.num_tiles = static_cast<int>(cdiv(R, kBM)); q.NH = NH; q.G = G2; q.P = g.P;
         q.d_heads = a->d_heads; q.wh = a->wh; q.store_scale = a->scales + 0;
         q.dwh = a->dwh; q.dbh = a->dbh; q.db2 = a->db2;
         const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
@@ -462,14 +493,39 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         p.act = tanh_act ? kActTanh : 0;
         p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
         // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]
-        p.dt_outer = (long long)NH * g.G * g.P;   // stride of b
-        p.dt_chan = (long long)g.G * g.P;         // stride of channel j
-        if (NH <= 8) rc = launch_thin_bwd<8, 4, true, true>(p, g.G, st);
-        else if (NH <= 20) rc = launch_thin_bwd<20, 2, true, true>(p, g.G, st);
-        else rc = launch_thin_bwd<kMaxHeads + 1, 1, true, true>(p, g.G, st);
+        p.dt_outer = (long long)NH * G2 * g.P;    // stride of b
+        p.dt_chan = (long long)G2 * g.P;          // stride of channel j
+        if (NH <= 8) rc = launch_thin_bwd<8, 4, true, true>(p, G2, st);
+        else if (NH <= 20) rc = launch_thin_bwd<20, 2, true, true>(p, G2, st);
+        else rc = launch_thin_bwd<kMaxHeads + 1, 1, true, true>(p, G2, st);
         if (rc) return rc;
     }
     ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)g.O * g.O, 256), 256, 0, st>>>(a->w2, static_cast<__half*>(a->w2t_h), g.O, g.O);
+    if (pooled) {
+        // ---- conv2 input is the pooled map xp (no activation in between): dW2 = dhpre^T xp, d(xp) = dhpre W2 (fp16 * s2),
+        // then the adjoint of the pooling spreads d(xp) over the rotations, applies act'(x1) and yields dfc_r
+        if ((rc = linear_tn(a->dhpre, g.O, a->xp, g.O, static_cast<int>(R), g.O, g.O, a->dw2, g.O, 0, st, a->scales + 1))) return rc;
+        LinearNTArgs l{};
+        l.A = a->dhpre; l.lda = g.O; l.B = a->w2t_h; l.ldb = g.O;
+        l.M = static_cast<int>(R); l.N = g.O; l.K = g.O;
+        l.C = nullptr; l.C16 = a->dxp16; l.ldc16 = g.O;
+        l.acc_scale = a->scales + 1; l.store_scale = a->scales + 2;
+        if ((rc = linear_nt(l, st))) return rc;
+        TVAE_CHECK_CUDA(cudaMemsetAsync(a->dfc_w, 0, sizeof(float) * g.G, st));
+        TVAE_CHECK_CUDA(cudaMemsetAsync(a->dfc_b, 0, sizeof(float), st));
+        ++g_launch_count; rot_pool_scales_kernel<<<1, 1, 0, st>>>(a->fc_w, g.G, a->scales);
+        RotPoolParams p{};
+        p.x1 = static_cast<const __half*>(a->x1); p.fc_w = a->fc_w; p.dxp = static_cast<const __half*>(a->dxp16);
+        p.dx1 = static_cast<__half*>(a->dx1_16); p.scales = a->scales; p.dfc_w = a->dfc_w; p.dfc_b = a->dfc_b;
+        p.db1 = bias_grad_slot(g, a->dbank); p.db1_stride = g.kpad;
+        p.B = g.B; p.G = g.G; p.P = g.P; p.O = g.O; p.act = tanh_act ? kActTanh : 0;
+        TVAE_REQUIRE(g.O % 8 == 0, "rotation pooling: kernel count must be a multiple of 8");
+        p.rows_per_cta = rot_pool_rows_per_cta(R, g.O);
+        ++g_launch_count;
+        rot_pool_bwd_kernel<<<cdiv(R, p.rows_per_cta), 256, sizeof(float) * (g.O + g.G + 1), st>>>(p);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+        return conv1_wgrad(g, a->y, a->dx1_16, a->scales + 5, a->dbank, st);
+    }
     if (g.O == 128 && !tanh_act) {
         // ---- one pass over dhpre and x1: dW2 = dhpre^T x1, dx1pre = (dhpre W2) * lrelu'(x1) (fp16 * s2) and its column
         // sums (the conv1 bias gradient)   (enc_bwd_fused.cuh)

@@ -201,8 +201,8 @@ class InferenceNetwork_UnimodalTranslation_UnimodalRotation(nn.Module):
 class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
     """models.py:268-319: attention over translations only.  groupconv = 0 (plain Conv2d(C, O, n, padding n//2) ->
     LeakyReLU -> 1x1 conv -> LeakyReLU -> heads) runs on the same tcgen05 kernels as the TARGET-VAE encoder with a
-    single, unrotated filter slot (G = 1); forward returns the reference's 4-tuple.  groupconv > 0 (group conv pooled
-    over rotations by `fc_r`) keeps its parameters / state_dict only."""
+    single, unrotated filter slot (G = 1); groupconv > 0 is the P_G group conv followed by the rotation pooling `fc_r`
+    (rot_pool_fwd / rot_pool_bwd kernels) and then one rotation slot.  forward returns the reference's 4-tuple."""
 
     def __init__(self, n, in_channels, latent_dim, kernels_num=128, activation=nn.LeakyReLU, groupconv=0):
         super(InferenceNetwork_AttentionTranslation_UnimodalRotation, self).__init__()
@@ -230,15 +230,16 @@ class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
     def encoder_spec(self, theta_prior=np.pi):
         """One rotation slot, no rotation prior, no offsets; the N(0, theta_prior) prior on theta is the trainer's
         argument (train_mnist.py:171), not a module attribute."""
-        if self.groupconv != 0:
-            raise NotImplementedError("attention/unimodal inference with groupconv > 0 (rotation pooling through fc_r) is "
-                                      "not on the accelerated path; groupconv = 0 is")
-        return TF.EncoderSpec(1, self.padding, self.latent_dim, False, False, float(theta_prior),
-                              theta_prior_std=float(theta_prior), act=_ops.act_kind(self.activation))
+        pool = self.groupconv > 0        # group conv over G rotations, pooled to one slot by fc_r (models.py:301-304)
+        return TF.EncoderSpec(self.groupconv if pool else 1, self.padding, self.latent_dim, False, False, float(theta_prior),
+                              theta_prior_std=float(theta_prior), act=_ops.act_kind(self.activation), pool=pool)
 
     def hot_path_params(self):
-        return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv_a.weight, self.conv_a.bias,
-                self.conv_r.weight, self.conv_r.bias, self.conv_z.weight, self.conv_z.bias]
+        ps = [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv_a.weight, self.conv_a.bias,
+              self.conv_r.weight, self.conv_r.bias, self.conv_z.weight, self.conv_z.bias]
+        if self.groupconv > 0:
+            ps += [self.fc_r.weight, self.fc_r.bias]
+        return ps
 
     def head_maps(self, x):
         """(B, 3+2z, 1, H', W') = [attn, theta_mu, theta_logstd, z...] with autograd."""

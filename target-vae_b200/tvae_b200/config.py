@@ -34,7 +34,8 @@ class HotPathConfig:
     batch: int = 100               # --minibatch-size
     # attn_attn: InferenceNetwork_AttentionTranslation_AttentionRotation (--r-inf attention / attention+offsets);
     # attn_unimodal: InferenceNetwork_AttentionTranslation_UnimodalRotation with --groupconv 0 (--r-inf unimodal):
-    # plain Conv2d(C, O, n, padding n//2), i.e. k = n, p = n // 2, G = 1 here
+    # k = n, p = n // 2; G = 1 = --groupconv 0 (plain Conv2d(C, O, n, padding n//2)), G > 1 = --groupconv G (P_G group
+    # conv pooled over the rotations by fc_r, models.py:281-285, 301-304)
     encoder: str = "attn_attn"
     activation: str = "leakyrelu"  # --activation leakyrelu | tanh, encoder and generator alike (train_mnist.py:516-519)
     gen_resid: bool = False        # --generator-resid-layers: ResidLinear hidden layers (models.py:22-30, 84-86)
@@ -50,7 +51,8 @@ class HotPathConfig:
 
     @property
     def L(self) -> int:
-        return self.G * self.Hout * self.Hout
+        """cells of the attention map: (r, t) for attention/attention, t only for attention/unimodal"""
+        return (1 if self.encoder == "attn_unimodal" else self.G) * self.Hout * self.Hout
 
     def with_(self, **kw) -> "HotPathConfig":
         return replace(self, **kw)

@@ -58,7 +58,7 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
     n = y.shape[-1]
     d = n + 2 * es.padding - encoder_model.kernels_size + 1
     if noise is None:
-        noise = draw_noise(B, es.G * d * d, es.z, y.device)
+        noise = draw_noise(B, es.attn_G * d * d, es.z, y.device)
     fw, fb = generator_model.fourier_buffers()
     gen_params = generator_model.hot_path_params()
     spec = TF.StepSpec(enc=es, sigma=generator_model._sigma, likelihood=likelihood, mask_radius=int(mask_radius),

@@ -68,10 +68,21 @@ class EncoderSpec:
     # the attention/unimodal branch uses eval_minibatch's theta_prior argument instead (train_mnist.py:171)
     theta_prior_std: Optional[float] = None
     act: int = ops.ACT_LEAKYRELU       # --activation of the encoder (ops.ACT_*)
+    # rotation pooling through fc_r between conv1 and conv2 (attention/unimodal encoder with groupconv > 0,
+    # models.py:301-304): the group conv keeps G rotations, everything after it has one rotation slot
+    pool: bool = False
+
+    @property
+    def attn_G(self) -> int:
+        return 1 if self.pool else self.G
+
+    @property
+    def n_params(self) -> int:
+        return 12 if self.pool else 10
 
     def tables(self):
-        p_r = ops.rotation_log_prior(self.G, self.rot_refinement, self.normal_prior_over_r, self.theta_prior)
-        offs = ops.rotation_offsets(self.G, self.rot_refinement)
+        p_r = ops.rotation_log_prior(self.attn_G, self.rot_refinement, self.normal_prior_over_r, self.theta_prior)
+        offs = ops.rotation_offsets(self.attn_G, self.rot_refinement)
         return p_r, offs
 
 
@@ -79,7 +90,7 @@ ENC_PARAM_NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "
                    "conv_r.weight", "conv_r.bias", "conv_z.weight", "conv_z.bias"]
 
 
-def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz, keep_h=True):
+def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, bz, fcw=None, fcb=None, keep_h=True):
     B, n = y.shape[0], y.shape[-1]
     if w1.dim() == 4:      # nn.Conv2d weight (O,C,k,k) of the groupconv = 0 encoder: one rotation, no rotation axis
         w1 = w1.unsqueeze(2)
@@ -87,30 +98,36 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
     s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z, spec.act)
     p_r, offs = spec.tables()
     yc = ops.f32(y).reshape(B, C, n, n)
-    wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.G, p_r, offs, y.device)
+    wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.attn_G, p_r, offs, y.device)
     bank = ops.filter_bank_fwd(s, w1)
     w2m = ops.f32(w2).reshape(O, O)
-    x1, h, heads = ops.encoder_fwd(s, yc, bank, b1, w2m, b2, wh, bh, add, keep_h)
-    return s, yc, w2m, wh, x1, h, heads
+    x1, h, heads, xp = ops.encoder_fwd(s, yc, bank, b1, w2m, b2, wh, bh, add, keep_h, (fcw, fcb) if spec.pool else None)
+    return s, yc, w2m, wh, x1, h, heads, xp
 
 
 def encoder_heads_inference(spec: EncoderSpec, y, *params):
     """heads (B, 3+2z, G, H', W') without autograd and without keeping the hidden map (clustering_*.get_latent)."""
     with torch.no_grad():
-        s, _, _, _, _, _, heads = _encoder_forward(spec, y, *params, keep_h=False)
+        s, _, _, _, _, _, heads, _ = _encoder_forward(spec, y, *params, keep_h=False)
     d = s.n + 2 * s.p - s.k + 1
-    return heads.view(s.B, 3 + 2 * spec.z, s.G, d, d)
+    return heads.view(s.B, 3 + 2 * spec.z, spec.attn_G, d, d)
 
 
-def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None):
-    """-> grads in ENC_PARAM_NAMES order (Conv3d shapes, or reshaped to `shapes` = the parameters' own shapes)."""
-    dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
+def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None, fcw=None, xp=None):
+    """-> grads in ENC_PARAM_NAMES order [+ fc_r.weight, fc_r.bias with rotation pooling] (Conv3d shapes, or reshaped to
+    `shapes` = the parameters' own shapes)."""
+    fc_grads = []
+    if spec.pool:
+        dbank, dw2, db2, dwh, dbh, dfc_w, dfc_b = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads, (fcw, xp))
+        fc_grads = [dfc_w.reshape(1, -1), dfc_b]
+    else:
+        dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
     dw1, db1 = ops.filter_bank_bwd(s, dbank)
     O, z = s.O, spec.z
     sh = (O, 1, 1, 1)
     grads = [dw1, db1, dw2.view(O, O, 1, 1, 1), db2,
              dwh[0:1].reshape(1, *sh), dbh[0:1], dwh[1:3].reshape(2, *sh), dbh[1:3],
-             dwh[3:].reshape(2 * z, *sh), dbh[3:]]
+             dwh[3:].reshape(2 * z, *sh), dbh[3:]] + fc_grads
     if shapes is not None:
         grads = [g.reshape(sh_) for g, sh_ in zip(grads, shapes)]
     return grads
@@ -121,17 +138,17 @@ class EncoderHeadsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, y, *params):
-        s, yc, w2m, wh, x1, h, heads = _encoder_forward(spec, y, *params)
+        s, yc, w2m, wh, x1, h, heads, xp = _encoder_forward(spec, y, *params)
         ctx.spec, ctx.s = spec, s
         ctx.shapes = [p.shape for p in params]
-        ctx.save_for_backward(yc, w2m, wh, x1, h)
+        ctx.save_for_backward(yc, w2m, wh, x1, h, *((params[10], xp) if spec.pool else ()))
         d = s.n + 2 * s.p - s.k + 1
-        return heads.view(s.B, 3 + 2 * spec.z, s.G, d, d)
+        return heads.view(s.B, 3 + 2 * spec.z, spec.attn_G, d, d)
 
     @staticmethod
     def backward(ctx, g):
-        yc, w2m, wh, x1, h = ctx.saved_tensors
-        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous(), ctx.shapes)
+        yc, w2m, wh, x1, h, *pool = ctx.saved_tensors
+        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous(), ctx.shapes, *pool)
         return (None, None, *grads)
 
 
@@ -227,20 +244,21 @@ class FusedStepFn(torch.autograd.Function):
     """(elbo, log_p_x_g_z, kl_div) of eval_minibatch's attention/attention(+offsets) branch.
 
     inputs: spec, x_coord (N,2), y (B,C,n,n), ctf or None, gumbel (B,L), r_z (B,z), r_theta (B),
-            fourier_w, fourier_b, then 10 encoder params (ENC_PARAM_NAMES) and the generator params.
+            fourier_w, fourier_b, then the encoder params (ENC_PARAM_NAMES; + fc_r.weight, fc_r.bias with rotation
+            pooling) and the generator params.
     """
 
     @staticmethod
     def forward(ctx, spec: StepSpec, x_coord, y, ctf, gumbel, r_z, r_theta, fourier_w, fourier_b, *params):
-        enc_params, gen_params = params[:10], params[10:]
         es = spec.enc
-        s, yc, w2m, wh, x1, h, heads = _encoder_forward(es, y, *enc_params)
+        enc_params, gen_params = params[:es.n_params], params[es.n_params:]
+        s, yc, w2m, wh, x1, h, heads, xp = _encoder_forward(es, y, *enc_params)
         B, n = s.B, s.n
         d = s.n + 2 * s.p - s.k + 1
         xc = ops.f32(x_coord)
         spacing = pixel_spacing(xc)
         p_r, offs = es.tables()
-        ashape = ops.attn_shape(B, s.G, d, es.z, spacing, offs, es.theta_prior_std)
+        ashape = ops.attn_shape(B, es.attn_G, d, es.z, spacing, offs, es.theta_prior_std)
         log_prior = ops.attn_log_prior(ashape, p_r, y.device)
         gum, rz, rth = ops.f32(gumbel), ops.f32(r_z).reshape(B, es.z), ops.f32(r_theta).reshape(B)
         att = ops.attn_fwd(ashape, heads, gum, rz, rth, log_prior)
@@ -268,13 +286,14 @@ class FusedStepFn(torch.autograd.Function):
         ctx.spec, ctx.s, ctx.ashape, ctx.gs, ctx.gw, ctx.gsaved, ctx.att = spec, s, ashape, gs, gw, gsaved, att
         ctx.spacing = spacing
         ctx.enc_shapes = [p.shape for p in enc_params]
-        ctx.save_for_backward(yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc if ctfc is not None else yc)
+        ctx.save_for_backward(yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc if ctfc is not None else yc,
+                              *((enc_params[10], xp) if es.pool else ()))
         ctx.has_ctf = ctfc is not None
         return elbo, log_p, kl
 
     @staticmethod
     def backward(ctx, g_elbo, g_logp, g_kl):
-        yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc = ctx.saved_tensors
+        yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc, *pool = ctx.saved_tensors
         spec, s, gs, att = ctx.spec, ctx.s, ctx.gs, ctx.att
         B = s.B
         zero = torch.zeros((), device=yc.device)
@@ -298,7 +317,7 @@ class FusedStepFn(torch.autograd.Function):
         if spec.sync is not None:
             spec.sync.start(0, gen_grads)
         d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
-        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes)
+        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes, *pool)
         if spec.sync is not None:
             spec.sync.start(1, enc_grads)
             gen_grads, enc_grads = spec.sync.finish()

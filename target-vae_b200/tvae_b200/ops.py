@@ -19,12 +19,12 @@ class EncShape(Structure):
 
 class EncFwdArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ("y", "bank", "conv1_bias", "w2", "b2", "wh", "bh", "head_add",
-                                         "x1", "h", "heads", "w2_h")]
+                                         "x1", "h", "heads", "w2_h", "fc_w", "fc_b", "xp")]
 
 
 class EncBwdArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ("y", "w2", "wh", "x1", "h", "d_heads", "dhpre", "dx1_16", "w2t_h", "scales", "dbank",
-                                         "dw2", "db2", "dwh", "dbh")]
+                                         "dw2", "db2", "dwh", "dbh", "fc_w", "xp", "dxp16", "dfc_w", "dfc_b")]
 
 
 class AttnShape(Structure):
@@ -190,8 +190,10 @@ def _head_add_table(NH, G, p_r, offsets, device):
     return add.to(device)
 
 
-def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add, keep_h=True):
-    """keep_h = False: inference only (get_latent) - the hidden map h is neither allocated nor written."""
+def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add, keep_h=True, pool=None):
+    """keep_h = False: inference only (get_latent) - the hidden map h is neither allocated nor written.
+    pool = (fc_r.weight, fc_r.bias): rotation pooling between conv1 and conv2 (attention/unimodal encoder with
+    groupconv > 0, models.py:301-304); h and the head maps then have one rotation slot.  -> x1, h, heads, xp."""
     dev = y.device
     d = s.n + 2 * s.p - s.k + 1
     P = d * d
@@ -199,20 +201,24 @@ def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add, keep_h=True)
     NH = 3 + 2 * s.z
     # activations are stored fp16 (the MMA operand format: 11-bit significand like TF32, half the HBM traffic)
     x1 = half(R, s.O, device=dev)
-    h = half(R, s.O, device=dev) if keep_h else None
-    heads = empty(s.B, NH, s.G, P, device=dev)
+    G2 = 1 if pool is not None else s.G
+    h = half(s.B * G2 * P, s.O, device=dev) if keep_h else None
+    heads = empty(s.B, NH, G2, P, device=dev)
     w2r = half(s.O, s.O, device=dev)
+    xp = half(s.B * P, s.O, device=dev) if pool is not None else None
     a = _set(EncFwdArgs(), y=f32(y), bank=bank, conv1_bias=f32(b1), w2=f32(w2), b2=f32(b2), wh=wh, bh=bh,
-             head_add=head_add, x1=x1, h=h, heads=heads, w2_h=w2r)
+             head_add=head_add, x1=x1, h=h, heads=heads, w2_h=w2r,
+             fc_w=None if pool is None else f32(pool[0]).reshape(-1), fc_b=None if pool is None else f32(pool[1]).reshape(-1), xp=xp)
     check(L().tvae_encoder_fwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_fwd")
-    return x1, h, heads
+    return x1, h, heads, xp
 
 
-def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
+def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads, pool=None):
+    """pool = (fc_r.weight, xp) with rotation pooling: additionally returns (dfc_w (G), dfc_b (1))."""
     dev = y.device
     NH = 3 + 2 * s.z
     R = x1.shape[0]
-    dhpre = half(R, s.O, device=dev)
+    dhpre = half(h.shape[0], s.O, device=dev)
     w2t = half(s.O, s.O, device=dev)
     scales = empty(8, device=dev)
     dbank = empty(s.G * s.O, s.kpad, device=dev)
@@ -224,7 +230,14 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads):
     a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, dx1_16=dx1_16, w2t_h=w2t,
              scales=scales,
              dbank=dbank, dw2=dw2, db2=db2, dwh=dwh, dbh=dbh)
+    dfc_w = dfc_b = None
+    if pool is not None:
+        fc_w, xp = pool
+        dfc_w, dfc_b = empty(s.G, device=dev), empty(1, device=dev)
+        _set(a, fc_w=f32(fc_w).reshape(-1), xp=xp, dxp16=half(xp.shape[0], s.O, device=dev), dfc_w=dfc_w, dfc_b=dfc_b)
     check(L().tvae_encoder_bwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_bwd")
+    if pool is not None:
+        return dbank, dw2, db2, dwh, dbh, dfc_w, dfc_b
     return dbank, dw2, db2, dwh, dbh
 
 

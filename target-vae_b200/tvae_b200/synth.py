@@ -37,7 +37,13 @@ def encoder_state(cfg: HotPathConfig, seed: int = 0, gain: float = 1.0) -> dict:
         "conv_z.bias": _u(rng, (2 * z,), bo),
     }
     if cfg.encoder == "attn_unimodal":     # nn.Conv2d modules (models.py:281-287): the same draws without the rotation axis
-        sd = {k_: (v.reshape(v.shape[0], v.shape[1], *v.shape[3:]) if v.ndim == 5 else v) for k_, v in sd.items()}
+        keep5 = ("conv1.weight",) if cfg.G > 1 else ()          # --groupconv G > 0: conv1 stays a GroupConv
+        sd = {k_: (v.reshape(v.shape[0], v.shape[1], *v.shape[3:]) if v.ndim == 5 and k_ not in keep5 else v)
+              for k_, v in sd.items()}
+        if cfg.G > 1:                      # fc_r = nn.Linear(G, 1), models.py:284
+            bg = 1.0 / math.sqrt(cfg.G)
+            sd["fc_r.weight"] = _u(rng, (1, cfg.G), bg)
+            sd["fc_r.bias"] = _u(rng, (1,), bg)
     return sd
 
 

@@ -101,7 +101,8 @@ def test_argmax_parity(gain, label):
     assert agree >= agree_ref32 - 1e-3
 
 
-@pytest.mark.parametrize("name", ["g1_mnist", "g2_dsprites", "g4_particles_ctf", "g6_mnist_noref", "g8_mnist_attn_unimodal"])
+@pytest.mark.parametrize("name", ["g1_mnist", "g2_dsprites", "g4_particles_ctf", "g6_mnist_noref", "g8_mnist_attn_unimodal",
+                                  "g12_mnist_attn_unimodal_p4"])
 def test_get_latent_matches_reference_golden(name):
     """clustering_mnist.get_latent outputs of the unmodified reference (tests/golden) vs the CUDA path."""
     from test_gpu_step import build_models, r_inf_of

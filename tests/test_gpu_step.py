@@ -29,7 +29,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particles_mask", "g6_mnist_noref",
           "g7_particles_fitnoise", "g8_mnist_attn_unimodal", "g9_mnist_resid",
-          "g10_mnist_tanh", "g11_particles_tanh"]
+          "g10_mnist_tanh", "g11_particles_tanh", "g12_mnist_attn_unimodal_p4"]
 
 
 def act_cls(cfg):
@@ -43,7 +43,8 @@ def build_models(cfg, seed=0, gain=1.0):
                                       resid=cfg.gen_resid, fourier_expansion=cfg.fourier, sigma=cfg.sigma)
         if cfg.encoder == "attn_unimodal":
             enc = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
-                                                                                activation=act_cls(cfg), groupconv=0)
+                                                                                activation=act_cls(cfg),
+                                                                                groupconv=cfg.G if cfg.G > 1 else 0)
         else:
             enc = models.InferenceNetwork_AttentionTranslation_AttentionRotation(
                 cfg.n, cfg.C, cfg.z, kernels_num=cfg.O, kernels_size=cfg.k, padding=cfg.p, activation=act_cls(cfg),
@@ -250,10 +251,11 @@ def test_attention_unimodal_matches_oracle_mnist_shaped():
     check_grads(grads, o_grads, 6e-2, "cfg1_au")
 
 
-def test_attention_unimodal_module_interface():
-    """InferenceNetwork_AttentionTranslation_UnimodalRotation.forward: the reference's 4-tuple (models.py:319) against
-    the golden outputs of the unmodified reference; groupconv > 0 is refused loudly."""
-    g, cfg, B, _ = load_golden("g8_mnist_attn_unimodal")
+@pytest.mark.parametrize("name", ["g8_mnist_attn_unimodal", "g12_mnist_attn_unimodal_p4"])
+def test_attention_unimodal_module_interface(name):
+    """InferenceNetwork_AttentionTranslation_UnimodalRotation.forward, groupconv = 0 and groupconv = 4 (rotation pooling):
+    the reference's 4-tuple (models.py:319) against the golden outputs of the unmodified reference."""
+    g, cfg, B, _ = load_golden(name)
     _, enc = build_models(cfg)
     y = torch.from_numpy(synth.minibatch(cfg, B, 0)["y"]).to(DEV)
     with torch.no_grad():
@@ -265,12 +267,40 @@ def test_attention_unimodal_module_interface():
         ref = torch.from_numpy(g[key])
         assert float((t.cpu() - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max())), key
     assert abs(float(a_s.sum()) - B) < 1e-3
-    import src.models as models
-    with contextlib.redirect_stdout(io.StringIO()):
-        pooled = models.InferenceNetwork_AttentionTranslation_UnimodalRotation(cfg.n, cfg.C, cfg.z, kernels_num=cfg.O,
-                                                                               groupconv=4).to(DEV)
-    with pytest.raises(NotImplementedError):
-        pooled(y, DEV)
+
+
+def test_attention_unimodal_pooled_matches_oracle():
+    """--r-inf unimodal --groupconv 8 at a larger size (O = 128: tensor-core heads kernels), tanh activation, against the
+    fp64 oracle: the rotation pooling kernels (rot_pool_fwd / rot_pool_bwd) with fc_r weights above 1 in magnitude (the
+    power-of-two down-scale of the fp16 gradient operand)."""
+    cfg = HotPathConfig("cfg1_aup", C=1, n=24, k=24, p=12, G=8, z=2, rot_refinement=False, encoder="attn_unimodal",
+                        hidden=128, theta_prior=0.7, activation="tanh")
+    B = 4
+    from tvae_b200 import elbo as E
+    gen, enc = build_models(cfg)
+    with torch.no_grad():
+        enc.fc_r.weight.mul_(4.0)                     # |w_r| up to ~1.4
+    data = synth.minibatch(cfg, B, 0)
+    nz = {k: torch.from_numpy(v).to(DEV) for k, v in synth.noise(cfg, B, 0).items()}
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    y = torch.from_numpy(data["y"]).to(DEV)
+    elbo, logp, kl = E.eval_minibatch(x, y, gen, enc, "attention", "unimodal", 0, DEV, cfg.theta_prior, cfg.G, cfg.n, noise=nz)
+    (-elbo).backward()
+    torch.cuda.synchronize()
+    from helpers import oracle_inputs, step_config, gen_param_names
+    from oracle import target_vae_oracle as orc
+    oenc, ogen, ox, oy, _, onz = oracle_inputs(cfg, B, dtype=torch.float64)
+    with torch.no_grad():
+        oenc.fc_r_w.mul_(4.0)
+    o_elbo, o_logp, o_kl, _ = orc.eval_minibatch(ox, oy, oenc, ogen, step_config(cfg), onz["gumbel"], onz["r_z"], onz["r_theta"])
+    (-o_elbo).backward()
+    assert abs(float(elbo) - float(o_elbo)) < 2e-3 * abs(float(o_elbo))
+    assert abs(float(kl) - float(o_kl)) < 2e-3 * abs(float(o_kl))
+    ref = {"enc." + n: t.grad for n, t in zip(orc.EncoderParams.names, oenc.tensors())}
+    ref.update({"gen." + n: t.grad for (_, t), n in zip(ogen.named_trainable(), gen_param_names(cfg))})
+    grads = {"enc." + k: p.grad.detach().cpu() for k, p in enc.named_parameters()}
+    grads.update({"gen." + k: p.grad.detach().cpu() for k, p in gen.named_parameters()})
+    check_grads(grads, ref, 6e-2, "cfg1_aup")
 
 
 def test_resid_generator_module_matches_oracle():

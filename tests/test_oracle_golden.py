@@ -15,7 +15,7 @@ CASES = ["g1_mnist", "g2_dsprites", "g3_galaxy", "g4_particles_ctf", "g5_particl
 
 
 # --t-inf attention --r-inf unimodal --groupconv 0: plain Conv2d encoder, 4-tuple module interface
-AU_CASES = ["g8_mnist_attn_unimodal"]
+AU_CASES = ["g8_mnist_attn_unimodal", "g12_mnist_attn_unimodal_p4"]
 
 
 @pytest.mark.parametrize("name", CASES + AU_CASES)
@@ -98,14 +98,17 @@ def test_plainconv_encoder_and_get_latent_match_reference(name):
     output and clustering_mnist.get_latent's attention/unimodal branch (:81-120)."""
     g, cfg, B, _ = load_golden(name)
     enc, gen, x, y, ctf, nz = oracle_inputs(cfg, B, requires_grad=False)
-    assert enc.conv1_w.dim() == 4
+    assert enc.conv1_w.dim() == (5 if cfg.G > 1 else 4)
     attn, q_t, p_r, a_s, offs, theta, z = orc.plainconv_encoder_forward(y, enc, cfg.p, nz["gumbel"])
     d = cfg.Hout
     for key, t in (("attn", attn), ("a_sampled", a_s.reshape(B, d, d)), ("theta", theta.squeeze(2)), ("z", z.squeeze(2))):
         ref = torch.from_numpy(g[key])
         assert tuple(t.shape) == tuple(ref.shape), key
         assert torch.allclose(t, ref, rtol=1e-4, atol=2e-5), (key, float((t - ref).abs().max()))
-    c1 = torch.nn.functional.conv2d(y, enc.conv1_w, enc.conv1_b, padding=cfg.p)
+    if cfg.G > 1:
+        c1 = orc.groupconv_forward(y, enc.conv1_w, enc.conv1_b, cfg.G, cfg.p)
+    else:
+        c1 = torch.nn.functional.conv2d(y, enc.conv1_w, enc.conv1_b, padding=cfg.p)
     assert torch.allclose(c1, torch.from_numpy(g["conv1_out"]), rtol=1e-4, atol=1e-5)
     zc, th, dx, ind = orc.get_latent(x, y, enc, 1, cfg.p, False, False, cfg.theta_prior, encoder="attn_unimodal")
     assert torch.allclose(zc, torch.from_numpy(g["latent_z"]), rtol=1e-4, atol=1e-5)
