@@ -90,7 +90,7 @@ def test_encoder_fwd_bwd(cfg):
     B = 3
     ops, enc, y, nz, s, wh, bh, add, t = _encoder_inputs(cfg, B)
     bank = ops.filter_bank_fwd(s, t(enc.conv1_w))
-    x1, h, heads = ops.encoder_fwd(s, t(y), bank, t(enc.conv1_b), t(enc.conv2_w).view(cfg.O, cfg.O), t(enc.conv2_b), wh, bh, add)
+    x1, h, heads, _ = ops.encoder_fwd(s, t(y), bank, t(enc.conv1_b), t(enc.conv2_w).view(cfg.O, cfg.O), t(enc.conv2_b), wh, bh, add)
     torch.cuda.synchronize()
     ref_heads = _oracle_heads(cfg, enc, y)
     # conv1 activation, internal layout [(b*G + r)*P + pos][O]
