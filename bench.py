@@ -246,7 +246,7 @@ def run_reference(args, cfg):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 def workload_config(cfg, B, n_gpus):
@@ -522,14 +522,34 @@ def run_ours(args, cfg):
         "get_latent": {"value": latent_ips, "unit": UNIT, "ms_per_minibatch": latent_ms / K,
                        "what": "clustering_*.get_latent (inference: encoder forward + argmax / expectation kernel), inputs resident in HBM"},
     }
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class StdoutForJsonOnly:
+    """stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL
+    prints "NCCL version ..." there even with NCCL_DEBUG_FILE set), so fd 1 is pointed at stderr for the whole run and
+    `emit` writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self._real, (line + "\n").encode())
+
+
+OUT = None
+
+
 def main():
+    global OUT
     args = parse()
     cfg = PRESETS[args.config]
+    OUT = StdoutForJsonOnly()
     if args.impl == "reference":
         run_reference(args, cfg)
     else:
