@@ -57,14 +57,29 @@ __global__ void __launch_bounds__(256) coord_layer_fwd_kernel(CoordXform cx, con
     for (int v = 0; v < VEC; ++v) { wx[v] = w1[2 * (c0 + v)]; wy[v] = w1[2 * (c0 + v) + 1]; bb[v] = b1[c0 + v]; }
     __syncthreads();
     const int rows = static_cast<int>(min((long long)kCoordRB, cx.M - m0));
+    // image of a row without a 64-bit division per row: one division per thread, then a running remainder.  A block that
+    // lies inside one image (always, when the pixels per image are a multiple of kCoordRB) folds the latent bias of that
+    // image into the bias registers and its row loop issues no loads at all.
+    const long long b_first = m0 / cx.N;
+    const long long rem0 = m0 - b_first * cx.N;
+    const bool one_image = rem0 + rows <= cx.N;
+    if (zb && one_image) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) bb[v] += __ldg(zb + b_first * H + c0 + v);
+    }
     for (int rr = rs; rr < rows; rr += rpp) {
         const long long m = m0 + rr;
         const float2 x = s_x[rr];
+        long long b = b_first;
+        if (zb && !one_image) {
+            long long rem = rem0 + rr;
+            while (rem >= cx.N) { rem -= cx.N; ++b; }
+        }
         float o[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; q += 4) {
             float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (zb) z4 = __ldg(reinterpret_cast<const float4*>(zb + (m / cx.N) * H + c0 + q));
+            if (zb && !one_image) z4 = __ldg(reinterpret_cast<const float4*>(zb + b * H + c0 + q));
             o[q] = fmaf(x.y, wy[q], fmaf(x.x, wx[q], bb[q])) + z4.x;
             o[q + 1] = fmaf(x.y, wy[q + 1], fmaf(x.x, wx[q + 1], bb[q + 1])) + z4.y;
             o[q + 2] = fmaf(x.y, wy[q + 2], fmaf(x.x, wx[q + 2], bb[q + 2])) + z4.z;
