@@ -324,3 +324,30 @@ def test_resid_generator_module_matches_oracle():
     got = dict(gen.named_parameters())
     for (_, t), name in zip(ogen.named_trainable(), gen_param_names(cfg)):
         assert rel_err(got[name].grad.cpu(), t.grad) < 3e-2, name
+
+
+@pytest.mark.parametrize("G", [1, 4])
+def test_attention_unimodal_module_backward(G):
+    """Autograd through InferenceNetwork_AttentionTranslation_UnimodalRotation.forward (EncoderHeadsFn), groupconv = 0
+    and groupconv = 4 (fc_r gradients): a fixed linear functional of (attn, theta, z) against the fp64 oracle.  tanh
+    activation: no derivative kinks, so the tolerance is the fp16-operand one."""
+    from helpers import oracle_inputs
+    from oracle import target_vae_oracle as orc
+    cfg = HotPathConfig("cfg1_aum", C=1, n=16, k=16, p=8, G=G, z=2, O=64, hidden=32, rot_refinement=False,
+                        encoder="attn_unimodal", activation="tanh")
+    B = 3
+    _, enc = build_models(cfg)
+    y = torch.from_numpy(synth.minibatch(cfg, B, 0)["y"]).to(DEV)
+    gen = torch.Generator().manual_seed(11)
+    d = cfg.Hout
+    wa, wt, wz = (torch.randn(B, c, d, d, generator=gen, dtype=torch.float64) for c in (1, 2, 2 * cfg.z))
+    attn, _, theta, z = enc(y, DEV)
+    ((attn * wa.float().to(DEV)).sum() + (theta * wt.float().to(DEV)).sum() + (z * wz.float().to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    oenc, _, _, oy, _, _ = oracle_inputs(cfg, B, dtype=torch.float64)
+    o_attn, o_theta, o_z = orc.plainconv_head_maps(oy, oenc, cfg.p)
+    ((o_attn * wa).sum() + (o_theta.squeeze(2) * wt).sum() + (o_z.squeeze(2) * wz).sum()).backward()
+    got = dict(enc.named_parameters())
+    for name, t in zip(orc.EncoderParams.names, oenc.tensors()):
+        assert tuple(got[name].grad.shape) == tuple(t.grad.shape), name
+        assert rel_err(got[name].grad.cpu(), t.grad) < 1e-2, (name, rel_err(got[name].grad.cpu(), t.grad))
