@@ -50,6 +50,7 @@ ConvGeom make_geom(const tvae_enc_shape* s) {
 int check_enc_shape(const tvae_enc_shape* s) {
     TVAE_REQUIRE(s->B > 0 && s->C > 0 && s->n > 0 && s->k > 0 && s->p >= 0, "encoder: non-positive dimension");
     TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG, "encoder: groupconv must be in 1..16");
+    TVAE_REQUIRE(s->act == TVAE_ACT_LEAKYRELU || s->act == TVAE_ACT_TANH, "encoder: act must be TVAE_ACT_LEAKYRELU or TVAE_ACT_TANH");
     TVAE_REQUIRE(s->O % 32 == 0 && s->O >= 32 && s->O <= 256, "encoder: kernel count must be a multiple of 32 in [32,256]");
     TVAE_REQUIRE(s->z >= 1 && 3 + 2 * s->z <= kMaxNH, "encoder: latent dim out of range");
     TVAE_REQUIRE(s->n + 2 * s->p - s->k + 1 >= 1, "encoder: kernel larger than padded image");
@@ -114,7 +115,7 @@ int launch_split_tn(typename P::Params& p, int out_tiles, int chunks_total, int 
 extern "C" {
 
 const char* tvae_last_error(void) { return g_last_error.c_str(); }
-int tvae_version(void) { return 100; }
+int tvae_version(void) { return 101; }   // 101: act in the shape structs, rotation-pooling fields in the encoder arguments
 long long tvae_launch_count(void) { return g_launch_count.load(); }
 
 // per-kernel timing of the tensor-core GEMM launches (CUDA events on the launching stream)
@@ -641,6 +642,7 @@ static int check_gen_shape(const tvae_gen_shape* s) {
     TVAE_REQUIRE(s->E == 0 || (s->E % 32 == 0 && s->E <= 4096), "generator: Fourier dim must be a multiple of 32");
     TVAE_REQUIRE(s->L >= 0 && s->L <= 8, "generator: 0..8 hidden layers");
     TVAE_REQUIRE(s->n_out >= 1 && s->n_out <= 4 && s->zdim >= 1, "generator: n_out in 1..4");
+    TVAE_REQUIRE(s->act == TVAE_ACT_LEAKYRELU || s->act == TVAE_ACT_TANH, "generator: act must be TVAE_ACT_LEAKYRELU or TVAE_ACT_TANH");
     return 0;
 }
 
