@@ -287,7 +287,7 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
 // rotation pooling between conv1 and conv2 (simt_kernels.cuh: rot_pool_fwd_kernel / rot_pool_bwd_kernel)
 inline int rot_pool_rows_per_cta(long long rows, int O) {
     const int rpp = 256 / (O / 8);
-    long long per = (rows + 4LL * sm_count() - 1) / (4LL * sm_count());
+    long long per = (rows + 8LL * sm_count() - 1) / (8LL * sm_count());   // 8 resident CTAs of 256 threads per SM = full occupancy
     per = (per + rpp - 1) / rpp * rpp;
     return static_cast<int>(per < rpp ? rpp : per);
 }
