@@ -8,8 +8,10 @@ GroupConv, the attention encoder and the spatial generator run hand-written CUDA
 operand generators, fused heads) through the C ABI in include/tvae_b200.h.  There is no CPU fallback: calling
 `forward` on CPU tensors or without the built library raises.
 
-Out of scope for this round ("next"): tanh activations, residual generator layers and the two
-unimodal ablation encoders - their classes are importable and hold the right parameters, `forward` raises.
+Covered variants: LeakyReLU and tanh activations, residual generator layers, the attention /
+unimodal-rotation encoder with a plain convolution (groupconv = 0) or a rotation-pooled group convolution
+(groupconv > 0).  The MLP encoder of the unimodal/unimodal spatial-VAE baseline (not in SURVEY.md §8) is importable,
+holds the right parameters and state_dict, and its `forward` raises.
 """
 from __future__ import print_function, division
 
@@ -177,7 +179,7 @@ class GroupConv(nn.Module):
 
 
 class InferenceNetwork_UnimodalTranslation_UnimodalRotation(nn.Module):
-    """models.py:229-260 (spatial-VAE style MLP baseline; ablation, not on the accelerated path)."""
+    """models.py:229-260 (spatial-VAE style MLP baseline, outside SURVEY.md §8: parameters / state_dict only)."""
 
     def __init__(self, n, latent_dim, hidden_dim, num_layers=1, activation=nn.LeakyReLU, resid=False):
         super(InferenceNetwork_UnimodalTranslation_UnimodalRotation, self).__init__()
@@ -195,7 +197,7 @@ class InferenceNetwork_UnimodalTranslation_UnimodalRotation(nn.Module):
         self.layers = nn.Sequential(*layers)
 
     def forward(self, x):
-        raise NotImplementedError("unimodal/unimodal inference is an ablation outside the accelerated hot path")
+        raise NotImplementedError("unimodal/unimodal inference (the spatial-VAE MLP baseline) is outside the accelerated hot path")
 
 
 class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):

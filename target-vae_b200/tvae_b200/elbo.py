@@ -1,6 +1,6 @@
-"""Fused `eval_minibatch` for the attention/attention(+offsets) branch - the reference's ELBO call site
-(train_mnist.py:26-294, train_dsprites.py:27-295, train_galaxy.py:27-295, train_particles.py:28-343) as one
-autograd node over the sm_100a kernels.
+"""Fused `eval_minibatch` for the attention branches (--t-inf attention with --r-inf attention, attention+offsets or
+unimodal) - the reference's ELBO call site (train_mnist.py:26-294, train_dsprites.py:27-295, train_galaxy.py:27-295,
+train_particles.py:28-343) as one autograd node over the sm_100a kernels.
 
     elbo, log_p_x_g_z, kl_div = eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
                                                theta_prior, groupconv, image_dim)
