@@ -31,18 +31,18 @@ def draw_noise(B, L, z, device, generator=None):
 def _encoder_spec(encoder_model, t_inf, r_inf, theta_prior):
     """The inference branches of eval_minibatch that run on the kernels: attention/attention(+offsets)
     (train_mnist.py:187-282) and attention/unimodal with a plain-conv encoder (train_mnist.py:88-183, --groupconv 0)."""
+    rotation_attention = hasattr(encoder_model, "rot_refinement")     # ..._AttentionRotation vs ..._UnimodalRotation
     if t_inf == 'attention' and r_inf in ('attention', 'attention+offsets'):
-        es = encoder_model.encoder_spec()
-        if es.theta_prior_std is not None:
+        if not rotation_attention:
             raise ValueError("r_inf attention needs InferenceNetwork_AttentionTranslation_AttentionRotation")
+        es = encoder_model.encoder_spec()
         if (r_inf == 'attention+offsets') != es.rot_refinement:
             raise ValueError("r_inf does not match the encoder's rot_refinement")
         return es
     if t_inf == 'attention' and r_inf == 'unimodal':
-        es = encoder_model.encoder_spec(theta_prior)
-        if es.theta_prior_std is None:
+        if rotation_attention:
             raise ValueError("r_inf unimodal needs InferenceNetwork_AttentionTranslation_UnimodalRotation")
-        return es
+        return encoder_model.encoder_spec(theta_prior)
     raise NotImplementedError("--t-inf unimodal (the MLP encoder of the spatial-VAE baseline) is not on the accelerated hot "
                               "path (SURVEY.md §8)")
 
