@@ -174,7 +174,8 @@ typedef struct {
     const float* w1;         /* coord_linear.weight (H, E or 2) */
     const float* b1;         /* (H) */
     const float* wz;         /* latent_linear.weight (H,zdim) */
-    const float* wh;         /* [L][H][H] hidden weights */
+    const float* wh;         /* [L][H][H] hidden weights; ResidLinear layers (--generator-resid-layers, models.py:22-30:
+                              * act(W x + b + x)) are passed as W + I - dwh is then the gradient w.r.t. W itself */
     const float* bh;         /* [L][H] */
     const float* wout;       /* (n_out,H) */
     const float* bout;       /* (n_out) */
