@@ -10,6 +10,7 @@ Backward runs on the autograd engine thread on the current stream, like the refe
 """
 from __future__ import annotations
 
+import functools
 import math
 from dataclasses import dataclass
 from typing import Callable, Optional
@@ -156,6 +157,11 @@ class EncoderHeadsFn(torch.autograd.Function):
 GEN_FIXED = ["coord_linear.weight", "coord_linear.bias", "latent_linear.weight"]
 
 
+@functools.lru_cache(maxsize=16)
+def _identity(n: int, device: str) -> torch.Tensor:
+    return torch.eye(n, dtype=torch.float32, device=device)
+
+
 def _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout, resid=False):
     """resid: the hidden layers are ResidLinear modules, act(W x + b + x) = act((W + I) x + b) (models.py:29-30; the
     activation comes after the residual add).  They run as plain layers with the effective weight W + I: the forward,
@@ -168,7 +174,7 @@ def _gen_weights(fourier_w, fourier_b, sigma, w1, b1, wz, hidden, wout, bout, re
     hw = [hidden[i] for i in range(0, len(hidden), 2)]
     hb = [hidden[i] for i in range(1, len(hidden), 2)]
     if resid:
-        hw = [ops.f32(w) + torch.eye(w.shape[0], dtype=torch.float32, device=w.device) for w in hw]
+        hw = [ops.f32(w) + _identity(w.shape[0], str(w.device)) for w in hw]
     return ops.GenWeights(wf, None if fourier_b is None else ops.f32(fourier_b), w1, b1, wz, hw, hb, wout, bout)
 
 
