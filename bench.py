@@ -116,8 +116,8 @@ def host_threads():
     return n
 
 
-def _reference_step_fn(cfg, B):
-    """eval_minibatch + backward of the UNMODIFIED reference (baseline/_ref), or None when it is not installed."""
+def _reference_step_fn(cfg, B, device="cpu"):
+    """eval_minibatch + backward of the UNMODIFIED reference (baseline/_ref) on `device`, or None when it is not installed."""
     name = TRAINER_OF.get(cfg.name.split("_")[0])
     if name is None or not os.path.exists(os.path.join(REF_DIR, name + ".py")):
         return None
@@ -152,12 +152,13 @@ def _reference_step_fn(cfg, B):
             normal_prior_over_r=cfg.normal_prior_over_r)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(cfg).items()})
     enc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.encoder_state(cfg).items()})
+    dev = torch.device(device)
+    gen, enc = gen.to(dev), enc.to(dev)
     params = list(gen.parameters()) + list(enc.parameters())
     data = synth.minibatch(cfg, B, seed=0)
-    x = torch.from_numpy(synth.image_coords(cfg.n))
-    y = torch.from_numpy(data["y"])
-    ctf = torch.from_numpy(data["ctf"]) if data["ctf"] is not None else None
-    dev = torch.device("cpu")
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(dev)
+    y = torch.from_numpy(data["y"]).to(dev)
+    ctf = torch.from_numpy(data["ctf"]).to(dev) if data["ctf"] is not None else None
     r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
 
     def step():
@@ -217,6 +218,29 @@ def cpu_reference_images_per_s(cfg, B, steps, warmup, budget_s=8.0):
             break
         Bx = min(B, 2 * Bx)
     return best[0], best[1], kind, threads, best[2]
+
+
+def gpu_reference_images_per_s(cfg, B, dev, steps=3):
+    """BASELINE.md §5 "the GPU baseline to beat": the unmodified reference's eval_minibatch + (-elbo).backward() run
+    eagerly on the same B200 (PyTorch defaults: cuDNN TF32 convolutions, fp32 linears), same synthetic shapes and weights,
+    device-resident inputs, CUDA events, 1 warm-up + `steps` timed steps.  None when baseline/_ref is not installed."""
+    step = _reference_step_fn(cfg, B, device=dev)
+    if step is None:
+        return None
+    step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": "reference-eager",
+            "sample": f"{steps} steps of {B} images (after 1 warm-up): unmodified reference train_*.eval_minibatch + "
+                      f"(-elbo).backward() from baseline/_ref on the same B200, torch {torch.__version__} defaults "
+                      f"(cudnn.allow_tf32 = {torch.backends.cudnn.allow_tf32}, matmul.allow_tf32 = "
+                      f"{torch.backends.cuda.matmul.allow_tf32}), inputs resident in HBM"}
 
 
 def default_cpu_batch(cfg):
@@ -499,6 +523,16 @@ def run_ours(args, cfg):
                                      "ms_per_launch": ms, "bytes_per_launch": nbytes}
         roofline["others"] = others
 
+    # ---- the GPU baseline BASELINE.md §5 names: the unmodified reference, eager, on this B200 (after our own legs: its
+    # allocations and cuDNN autotuning cannot disturb them); a failure is reported, it does not take the line down
+    gpu_ref = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            gpu_ref = gpu_reference_images_per_s(cfg, B, dev)
+        except Exception as e:
+            gpu_ref = {"value": None, "unit": UNIT, "kind": "reference-eager", "sample": f"failed: {type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_batch or default_cpu_batch(cfg)
@@ -515,7 +549,7 @@ def run_ours(args, cfg):
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": workload_config(cfg, B, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref,
         "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12,
         "train_step": {"value": train_ips, "unit": UNIT, "ms_per_step": train_ms / K,
                        "what": "fwd + bwd + fused multi-tensor Adam (tvae_adam_step), inputs resident in HBM"},
