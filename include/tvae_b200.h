@@ -207,11 +207,15 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
 int tvae_bernoulli(const float* y_hat, const float* y, float* ll, float* d_yhat, const float* g, int B, int E, void* stream);
 /* Gaussian with optional CTF and mask (train_particles.py:298-338): mu = ctf (*) y_hat (scratch (B,n,n)),
  * ll[b] = -0.5 sum mask (mu - y)^2, d_yhat = adjoint-ctf(g * mask * (mu - y)).  ctf may be NULL, radius 0 = no mask.
+ * ctf is (B, ctf_size, ctf_size), applied with zero padding ctf_size / 2 exactly like
+ * F.conv2d(..., padding=ctf.size(2)//2, groups=B) (train_particles.py:301): ctf_size = n - 1 (the trainer's default;
+ * 0 means n - 1) or any odd size (--crop keeps the filters of the uncropped micrograph size, train_particles.py:543-547).
  * With a ctf, y_hat may be NULL when `mu` still holds ctf (*) y_hat from the forward call (backward pass). */
 /* ws: scratch of tvae_gaussian_workspace_bytes(B, n) bytes for the tensor-core CTF path (banded-Toeplitz GEMM with
- * fp16 operands; even n <= 128).  ws == NULL, or a size query of 0, selects the CUDA-core correlation kernel. */
+ * fp16 operands; ctf_size = n - 1, even n <= 128).  ws == NULL, a size query of 0 or another filter size selects the
+ * CUDA-core correlation kernel (the centred part of the filter that can meet the image must fit shared memory). */
 long long tvae_gaussian_workspace_bytes(int B, int n);
-int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius,
+int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, int ctf_size, const float* dx, float s, int radius,
                   float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream);
 
 /* Gaussian with a learned per-pixel variance (--fit-noise: train_particles.py:289-296, 333-334, 663-666; generator

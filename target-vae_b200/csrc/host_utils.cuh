@@ -134,34 +134,41 @@ inline int make_tmap_3d_store_h(CUtensorMap* tm, void* ptr, uint64_t outer, uint
 
 // ---- optional per-kernel timing (bench.py): CUDA events recorded around every tc_gemm launch on its own stream
 struct KernelTimer {
-    static constexpr int kMaxNames = 32;
-    static constexpr int kMaxEvents = 8192;
-    bool enabled = false;
+    static constexpr int kMaxNames = 48;
+    static constexpr int kMaxEvents = 16384;
+    std::atomic<bool> enabled{false};
+    std::mutex mu;              // begin() / collect are called from the caller thread (forward) AND the autograd thread (backward)
     int n_names = 0;
     const char* names[kMaxNames];
     int n_events = 0;
     cudaEvent_t start[kMaxEvents], stop[kMaxEvents];
     int name_of[kMaxEvents];
     int n_created = 0;
-    int name_id(const char* nm) {
+    int name_id(const char* nm) {       // caller holds `mu`
         for (int i = 0; i < n_names; ++i)
             if (names[i] == nm) return i;
         if (n_names >= kMaxNames) return -1;
         names[n_names] = nm;
         return n_names++;
     }
-    // returns slot or -1
+    // returns slot or -1.  The slot (and with it the event pair) is reserved under the lock; recording the events needs
+    // no lock: each slot is used by exactly one launch.
     int begin(const char* nm, cudaStream_t st) {
-        if (!enabled || n_events >= kMaxEvents) return -1;
-        const int id = name_id(nm);
-        if (id < 0) return -1;
-        const int e = n_events++;
-        if (e >= n_created) {
-            cudaEventCreate(&start[e]);
-            cudaEventCreate(&stop[e]);
-            n_created = e + 1;
+        if (!enabled.load(std::memory_order_relaxed)) return -1;
+        int e;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (n_events >= kMaxEvents) return -1;
+            const int id = name_id(nm);
+            if (id < 0) return -1;
+            e = n_events++;
+            if (e >= n_created) {
+                cudaEventCreate(&start[e]);
+                cudaEventCreate(&stop[e]);
+                n_created = e + 1;
+            }
+            name_of[e] = id;
         }
-        name_of[e] = id;
         cudaEventRecord(start[e], st);
         return e;
     }
@@ -171,13 +178,17 @@ struct KernelTimer {
 };
 inline KernelTimer g_timer;
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }

@@ -446,9 +446,11 @@ __global__ void __launch_bounds__(256) bernoulli_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(256) ctf_apply_kernel(const float* __restrict__ in, const float* __restrict__ ctf,
-                                                        float* __restrict__ out, int n) {
+                                                        float* __restrict__ out, int n, int mf, int m) {
+    // mf: filter size as stored, pad = mf / 2 (train_particles.py:301 `padding=ctf.size(2)//2`); m <= mf: the centred
+    // m x m part of it that can meet the image (taps further than n - 1 from the centre only ever multiply padding)
     extern __shared__ float sm[];
-    const int m = n - 1, pad = m / 2;
+    const int pad = m / 2, off = (mf - m) / 2;
     const int b = blockIdx.z;
     const int ti = blockIdx.y * 16, tj = blockIdx.x * 16;
     const int ly = threadIdx.x / 16, lx = threadIdx.x % 16;
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(256) ctf_apply_kernel(const float* __restrict_
     float* win = sm;                       // W*W input window (zero padded)
     float* flt = sm + W * W;               // m*m filter
     const float* inb = in + (long long)b * n * n;
-    const float* fb = ctf + (long long)b * m * m;
+    const float* fb = ctf + (long long)b * mf * mf;
     // forward:  out[i,j] = sum in[i+v-pad, j+u-pad] f[v,u]       window origin (ti-pad, tj-pad)
     // adjoint:  out[i,j] = sum in[i-v+pad, j-u+pad] f[v,u]       window origin (ti+pad-(m-1), tj+pad-(m-1)), f flipped
     const int oy = TRANSPOSED ? ti + pad - (m - 1) : ti - pad;
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(256) ctf_apply_kernel(const float* __restrict_
     }
     for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
         const int v = idx / m, u = idx % m;
-        flt[idx] = TRANSPOSED ? fb[(m - 1 - v) * m + (m - 1 - u)] : fb[idx];
+        flt[idx] = TRANSPOSED ? fb[(off + m - 1 - v) * mf + (off + m - 1 - u)] : fb[(off + v) * mf + off + u];
     }
     __syncthreads();
     float acc = 0.f;

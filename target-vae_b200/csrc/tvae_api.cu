@@ -24,6 +24,14 @@ inline int blocks_for(long long n, int threads, int cap = 148 * 8) {
     return static_cast<int>(b);
 }
 
+// event-times the launches issued while it is alive (tvae_profile_enable; no-op otherwise)
+struct Timed {
+    int slot;
+    cudaStream_t st;
+    Timed(const char* name, cudaStream_t s) : slot(g_timer.begin(name, s)), st(s) {}
+    ~Timed() { g_timer.end(slot, st); }
+};
+
 RotTable make_rot_table(int G) {
     // theta accumulated in double exactly like models.py:181-195, cos/sin rounded to fp32 (models.py:186-190)
     RotTable t{};
@@ -120,12 +128,14 @@ long long tvae_launch_count(void) { return g_launch_count.load(); }
 
 // per-kernel timing of the tensor-core GEMM launches (CUDA events on the launching stream)
 void tvae_profile_enable(int on) {
-    g_timer.enabled = on != 0;
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    g_timer.enabled.store(on != 0);
     if (on) g_timer.n_events = 0;
 }
 // Synchronises, then fills up to `cap` entries: names[i] (static strings), total_ms[i], launches[i]. Returns count.
 int tvae_profile_collect(const char** names, float* total_ms, int* launches, int cap) {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_timer.mu);
     int n = g_timer.n_names < cap ? g_timer.n_names : cap;
     for (int i = 0; i < n; ++i) { names[i] = g_timer.names[i]; total_ms[i] = 0.f; launches[i] = 0; }
     for (int e = 0; e < g_timer.n_events; ++e) {
@@ -155,6 +165,7 @@ int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, void* ban
     if (rc) return rc;
     const int kpad16 = tvae_bank16_pitch(s->C, s->k);
     const long long total = (long long)s->G * s->O * kpad16;
+    Timed tm("filter_bank_fwd", S(stream));
     ++g_launch_count; filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -164,6 +175,7 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
     int rc = check_enc_shape(s);
     if (rc) return rc;
     const int K = s->C * s->k * s->k;
+    Timed tm("filter_bank_bwd", S(stream));
     TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
     const long long total = (long long)s->G * s->O * K;
     ++g_launch_count; filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
@@ -600,6 +612,7 @@ int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float
 int tvae_attn_fwd(const tvae_attn_shape* s, const tvae_attn_fwd_args* a, void* stream) {
     TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG && s->d >= 1 && s->B >= 1, "attention: bad shape");
     const AttnParams p = to_attn_params(s, a);
+    Timed tm("attn_fwd", S(stream));
     ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (attn_fwd_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(p)));
     TVAE_CHECK_CUDA(cudaGetLastError());
@@ -616,6 +629,7 @@ int tvae_attn_bwd(const tvae_attn_shape* s, const tvae_attn_bwd_args* a, void* s
     for (int i = 0; i < kMaxG; ++i) p.offsets[i] = s->offsets[i];
     const int L = s->G * s->d * s->d;
     dim3 grid(blocks_for(L, 256, 64), s->B);
+    Timed tm("attn_bwd", S(stream));
     ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ><<<grid, 256, 0, S(stream)>>>(p)));
     TVAE_CHECK_CUDA(cudaGetLastError());
@@ -936,14 +950,20 @@ long long tvae_gaussian_workspace_bytes(int B, int n) {
     return ctf_workspace(make_ctf_geom(B, n), nullptr).bytes;
 }
 
-int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const float* dx, float s, int radius, float* mu,
-                  float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream) {
+int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, int ctf_size, const float* dx, float s, int radius,
+                  float* mu, float* dmu, float* ll, float* d_yhat, const float* g, int B, int n, void* ws, void* stream) {
     cudaStream_t st = S(stream);
+    TVAE_REQUIRE(B >= 1 && n >= 1, "gaussian: empty batch");
     TVAE_CHECK_CUDA(cudaMemsetAsync(ll, 0, sizeof(float) * B, st));
-    const int m = n - 1, W = 16 + m - 1;
+    // filter size: the reference applies any (B,1,m,m) filter with padding m // 2 (train_particles.py:298-302); the
+    // output keeps the image size only for odd m (and for m = n - 1, the trainer's default, with even n)
+    const int mf = (ctf && ctf_size > 0) ? ctf_size : n - 1;
+    TVAE_REQUIRE(!ctf || mf == n - 1 || (mf % 2 == 1), "gaussian: CTF filter size must be odd (or n - 1)");
+    const int m = (mf != n - 1 && mf > 2 * n - 1) ? 2 * n - 1 : mf;     // taps beyond n - 1 from the centre never meet the image
+    const int W = 16 + m - 1;
     const size_t sm = sizeof(float) * (W * W + m * m);
     dim3 cgrid(cdiv(n, 16), cdiv(n, 16), B);
-    const bool gemm = ctf && ws && ctf_gemm_ok(n);
+    const bool gemm = ctf && ws && mf == n - 1 && ctf_gemm_ok(n);
     const CtfGeom cg = make_ctf_geom(B, n);
     const CtfWorkspace cw = ctf_workspace(cg, ws);
     int rc;
@@ -956,10 +976,10 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
         if (y_hat && (rc = ctf_apply_gemm(cg, cw, y_hat, cw.ctf16, nullptr, nullptr, mu, st))) return rc;
         mu_in = mu;
     } else if (ctf) {
-        TVAE_REQUIRE(sm <= 227 * 1024, "gaussian: CTF window does not fit shared memory");
+        TVAE_REQUIRE(sm <= 227 * 1024, "gaussian: CTF window does not fit shared memory (filter too large for this image size)");
         TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&ctf_apply_kernel<false>), 227 * 1024));
         TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&ctf_apply_kernel<true>), 227 * 1024));
-        if (y_hat) { ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n); }
+        if (y_hat) { ++g_launch_count; ctf_apply_kernel<false><<<cgrid, 256, sm, st>>>(y_hat, ctf, mu, n, mf, m); }
         mu_in = mu;
     }
     dim3 grid(1, B);   // one CTA per image: deterministic ll[b]
@@ -974,7 +994,7 @@ int tvae_gaussian(const float* y_hat, const float* y, const float* ctf, const fl
             ++g_launch_count; single_scale_kernel<<<1, 1, 0, st>>>(cw.scales + 7, cw.scales);
             if ((rc = ctf_apply_gemm(cg, cw, dmu, cw.flip16, cw.scales + 2, cw.scales + 3, d_yhat, st))) return rc;
         } else {
-            ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n);
+            ++g_launch_count; ctf_apply_kernel<true><<<cgrid, 256, sm, st>>>(dmu, ctf, d_yhat, n, mf, m);
         }
     }
     TVAE_CHECK_CUDA(cudaGetLastError());
@@ -1007,11 +1027,11 @@ int tvae_adam_step(const tvae_adam_tensor* tensors, int n, double lr, double bet
     h.one_minus_beta1 = static_cast<float>(1.0 - beta1);
     h.one_minus_beta2 = static_cast<float>(1.0 - beta2);
     h.zero_grad = zero_grad;
-    for (int first = 0; first < n; first += kAdamMaxTensors) {
+    for (int i = 0; i < n;) {          // `i` is the consumed index: empty tensors are skipped, never re-visited
         AdamTable tab{};
         int blocks = 0;
         tab.n = 0;
-        for (int i = first; i < n && tab.n < kAdamMaxTensors; ++i) {
+        for (; i < n && tab.n < kAdamMaxTensors; ++i) {
             const tvae_adam_tensor& t = tensors[i];
             if (t.numel <= 0) continue;
             TVAE_REQUIRE(t.param && t.grad && t.exp_avg && t.exp_avg_sq, "adam: null tensor pointer");

@@ -91,10 +91,20 @@ class SpatialGenerator(nn.Module):
                 layers.append(activation())
         layers.append(nn.Linear(hidden_dim, n_out))
         self.layers = nn.Sequential(*layers)
-        self._resid = resid
-        self._sigma = float(sigma)
 
     # ---- helpers used by the fused step --------------------------------------------------------
+    # Derived from state the reference's own modules carry, never from attributes only this __init__ would create: the
+    # reference checkpoints are whole-module pickles (src/utils.py:42-46) and unpickling does not run __init__.
+    @property
+    def _sigma(self) -> float:
+        """Fourier scale: RandomFourierEmbedding2d.sigma (models.py:40), a 0-d fp32 tensor attribute of the sub-module."""
+        return float(self.embed_latent.sigma) if self.fourier_expansion else 0.01
+
+    @property
+    def _resid(self) -> bool:
+        """--generator-resid-layers: the hidden layers are ResidLinear modules (models.py:84-86)."""
+        return any(isinstance(m, ResidLinear) for m in self.layers)
+
     def _check_supported(self):
         if not hasattr(self, 'latent_linear'):
             raise NotImplementedError("SpatialGenerator: only latent-conditioned generators (latent_dim > 0) are on the "
@@ -224,9 +234,16 @@ class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
         self.conv_a = nn.Conv2d(self.kernels_num, 1, 1)
         self.conv_r = nn.Conv2d(self.kernels_num, 2, 1)
         self.conv_z = nn.Conv2d(self.kernels_num, 2 * self.latent_dim, 1)
-        # geometry in the TARGET-VAE encoder's terms (used by tvae_b200.elbo)
-        self.kernels_size = self.input_size
-        self.padding = self.input_size // 2
+
+    # geometry in the TARGET-VAE encoder's terms (used by tvae_b200.elbo): properties of state the reference module
+    # also has, so that a reference checkpoint (a whole-module pickle, restored without __init__) works unchanged
+    @property
+    def kernels_size(self) -> int:
+        return self.input_size
+
+    @property
+    def padding(self) -> int:
+        return self.input_size // 2
 
     # ---- helpers used by the fused step --------------------------------------------------------
     def encoder_spec(self, theta_prior=np.pi):

@@ -50,6 +50,7 @@ def _encoder_spec(encoder_model, t_inf, r_inf, theta_prior):
 def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, sync=None,
           theta_prior=None):
     es = _encoder_spec(encoder_model, t_inf, r_inf, theta_prior)
+    spacing = TF.pixel_spacing(x)      # cached on the caller's grid tensor (not on the per-step device copy below)
     y = y.to(device)
     x = x.to(device)
     if not y.is_cuda:
@@ -65,6 +66,7 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
                        n_gen_hidden=(len(gen_params) - 5) // 2, gen_resid=bool(generator_model._resid),
                        gen_act=generator_model.act_kind())
     spec.sync = sync
+    spec.spacing = spacing
     return TF.FusedStepFn.apply(spec, x, y, ctf, noise["gumbel"], noise["r_z"], noise["r_theta"], fw, fb,
                                 *encoder_model.hot_path_params(), *gen_params)
 
@@ -91,6 +93,8 @@ def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r
     if n_out != 1:
         raise ValueError(f"eval_minibatch_particles: generator n_out must be 1 or 2 (--fit-noise), got {n_out}")
     if ctf is not None:
+        from . import ops
+        ops.ctf_filter_size(ctf, y.shape[0], y.shape[-1])     # one odd-sized square filter per image, or raise
         ctf = ctf.to(device)
     return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync,
                  theta_prior)
@@ -109,6 +113,7 @@ def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
         es = encoder_model.encoder_spec()
         heads = TF.encoder_heads_inference(es, y, *encoder_model.hot_path_params())
         B, NH, G, d, _ = heads.shape
-        s = ops.attn_shape(B, G, d, es.z, TF.pixel_spacing(x.to(device)), es.tables()[1])
-        zc, th, dx, _ = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
+        s = ops.attn_shape(B, G, d, es.z, TF.pixel_spacing(x), es.tables()[1])
+        with torch.cuda.device(heads.device):
+            zc, th, dx, _ = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
     return zc, th, dx

@@ -20,9 +20,26 @@ import torch
 from . import ops
 
 
+def on_tensor_device(fn):
+    """The library launches on the CURRENT CUDA device (stream, SM count, shared-memory opt-in): run `fn` with the
+    device of its first CUDA tensor argument current, so a model on cuda:1 works while cuda:0 is current.  (Backward
+    passes need nothing: the autograd engine already switches to the device of the incoming gradients.)"""
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapped
+
+
 # ------------------------------------------------------------------------------------------------ GroupConv
 class GroupConvFn(torch.autograd.Function):
     @staticmethod
+    @on_tensor_device
     def forward(ctx, y, weight, bias, G, padding):
         B, n = y.shape[0], y.shape[-1]
         O, C, _, k, _ = weight.shape
@@ -106,10 +123,15 @@ def _encoder_forward(spec: EncoderSpec, y, w1, b1, w2, b2, wa, ba, wr, br, wz, b
     return s, yc, w2m, wh, x1, h, heads, xp
 
 
+@on_tensor_device
+def _encoder_forward_inference(spec, y, *params):
+    return _encoder_forward(spec, y, *params, keep_h=False)
+
+
 def encoder_heads_inference(spec: EncoderSpec, y, *params):
     """heads (B, 3+2z, G, H', W') without autograd and without keeping the hidden map (clustering_*.get_latent)."""
     with torch.no_grad():
-        s, _, _, _, _, _, heads, _ = _encoder_forward(spec, y, *params, keep_h=False)
+        s, _, _, _, _, _, heads, _ = _encoder_forward_inference(spec, y, *params)
     d = s.n + 2 * s.p - s.k + 1
     return heads.view(s.B, 3 + 2 * spec.z, spec.attn_G, d, d)
 
@@ -138,6 +160,7 @@ class EncoderHeadsFn(torch.autograd.Function):
     """heads (B, 3+2z, G, H', W'): attn(+p_r), theta(+offsets), z stacked on dim 1."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, spec, y, *params):
         s, yc, w2m, wh, x1, h, heads, xp = _encoder_forward(spec, y, *params)
         ctx.spec, ctx.s = spec, s
@@ -191,6 +214,7 @@ class GeneratorFn(torch.autograd.Function):
     params = coord_linear.weight, coord_linear.bias, latent_linear.weight, (hidden w, b)*, out w, out b."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, fourier_w, fourier_b, sigma, x, z, *params):
         resid, act = False, ops.ACT_LEAKYRELU
         if isinstance(sigma, tuple):       # (sigma, resid, act) from SpatialGenerator
@@ -216,19 +240,25 @@ class GeneratorFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ fused step
-_spacing_cache: dict = {}
+_spacing_cache: dict = {}      # id(tensor) -> (weakref to the tensor, its _version, spacing)
 
 
 def pixel_spacing(x_coord: torch.Tensor) -> float:
-    """btw_pixels_space = x[1,0] - x[0,0] (train_mnist.py:30).  The reference syncs for it every step; the
-    coordinate grid is constant, so it is read once per grid and cached."""
-    key = (x_coord.data_ptr(), tuple(x_coord.shape), str(x_coord.device))
-    v = _spacing_cache.get(key)
-    if v is None:
-        v = float((x_coord[1, 0] - x_coord[0, 0]).float().cpu())
+    """btw_pixels_space = x[1,0] - x[0,0] (train_mnist.py:30).  The reference syncs for it every step; the coordinate
+    grid is constant, so it is read once per grid: cached on the IDENTITY and version counter of the caller's own tensor
+    (never on a data pointer - the caching allocator hands freed addresses to other grids), so a new or an in-place
+    rescaled grid is read again.  Call it on the tensor the trainer holds, not on a per-step `.to(device)` copy."""
+    import weakref
+    hit = _spacing_cache.get(id(x_coord))
+    if hit is not None and hit[0]() is x_coord and hit[1] == x_coord._version:
+        return hit[2]
+    v = float((x_coord[1, 0] - x_coord[0, 0]).float().cpu())
+    if len(_spacing_cache) > 64:
+        for k in [k for k, e in _spacing_cache.items() if e[0]() is None]:
+            del _spacing_cache[k]
         if len(_spacing_cache) > 64:
             _spacing_cache.clear()
-        _spacing_cache[key] = v
+    _spacing_cache[id(x_coord)] = (weakref.ref(x_coord), x_coord._version, v)
     return v
 
 
@@ -244,6 +274,7 @@ class StepSpec:
     # optional data-parallel gradient synchroniser (tvae_b200.dp.GradSync): bucket 0 (generator) is started as
     # soon as the generator backward has been issued, so its all-reduce overlaps the encoder backward.
     sync: Optional[object] = None
+    spacing: Optional[float] = None    # pixel_spacing(x_coord) of the caller's grid tensor (None: read from x_coord here)
 
 
 class FusedStepFn(torch.autograd.Function):
@@ -255,6 +286,7 @@ class FusedStepFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, spec: StepSpec, x_coord, y, ctf, gumbel, r_z, r_theta, fourier_w, fourier_b, *params):
         es = spec.enc
         enc_params, gen_params = params[:es.n_params], params[es.n_params:]
@@ -262,7 +294,7 @@ class FusedStepFn(torch.autograd.Function):
         B, n = s.B, s.n
         d = s.n + 2 * s.p - s.k + 1
         xc = ops.f32(x_coord)
-        spacing = pixel_spacing(xc)
+        spacing = spec.spacing if spec.spacing is not None else pixel_spacing(x_coord)
         p_r, offs = es.tables()
         ashape = ops.attn_shape(B, es.attn_G, d, es.z, spacing, offs, es.theta_prior_std)
         log_prior = ops.attn_log_prior(ashape, p_r, y.device)

@@ -90,7 +90,7 @@ def L():
                      "tvae_gaussian", "tvae_gaussian_fit_noise"):
             getattr(lib, name).restype = c_int
         lib.tvae_gaussian_fit_noise.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
-        lib.tvae_gaussian.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
+        lib.tvae_gaussian.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
         lib.tvae_gaussian_workspace_bytes.restype = ctypes.c_longlong
         lib.tvae_gaussian_workspace_bytes.argtypes = [c_int, c_int]
@@ -382,22 +382,38 @@ def bernoulli(y_hat, y, g=None):
     return ll, d
 
 
+def ctf_filter_size(ctf, B, n) -> int:
+    """Validates a CTF filter stack against the minibatch and returns its size m.  The reference applies
+    F.conv2d(y_mu.view(1,B,n,n), ctf, padding=ctf.size(2)//2, groups=B) (train_particles.py:298-302): one square filter
+    per image, any odd size (m = n - 1 by default; with --crop the filters keep the uncropped size)."""
+    if ctf.dim() == 4 and ctf.shape[1] == 1:
+        ctf = ctf[:, 0]
+    if ctf.dim() != 3 or ctf.shape[0] != B or ctf.shape[1] != ctf.shape[2]:
+        raise ValueError(f"ctf must be (B,1,m,m) or (B,m,m) with B = {B}, got {tuple(ctf.shape)}")
+    m = int(ctf.shape[-1])
+    if m != n - 1 and m % 2 == 0:
+        raise ValueError(f"ctf filter size {m} must be odd (or image_dim - 1 = {n - 1}): with an even size the reference's "
+                         "grouped convolution changes the image size")
+    return m
+
+
 def gaussian(y_hat, y, n, ctf=None, dx=None, s=1.0, radius=0, g=None, mu=None, use_ctf_gemm=True):
     """-> (ll, d_yhat, mu).  `mu` = ctf (*) y_hat of an earlier call lets the backward pass skip the forward CTF."""
     B = y.shape[0]
     dev = y.device
     ll = empty(B, device=dev)
+    m = 0 if ctf is None else ctf_filter_size(ctf, B, n)
     have_mu = mu is not None and ctf is not None
     if ctf is not None and mu is None:
         mu = empty(B, n * n, device=dev)
     dmu = empty(B, n * n, device=dev) if (ctf is not None and g is not None) else None
     d = torch.empty_like(y_hat) if g is not None else None
     ws = None
-    if ctf is not None and use_ctf_gemm:
+    if ctf is not None and use_ctf_gemm and m == n - 1:
         nbytes = int(L().tvae_gaussian_workspace_bytes(B, n))
         if nbytes > 0:
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    check(L().tvae_gaussian(_p(None if have_mu else f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)),
+    check(L().tvae_gaussian(_p(None if have_mu else f32(y_hat)), _p(f32(y)), _p(None if ctf is None else f32(ctf)), m,
                             _p(None if dx is None else f32(dx)), float(s), int(radius), _p(mu), _p(dmu), _p(ll), _p(d),
                             _p(g), B, n, _p(ws), stream_ptr().value), "tvae_gaussian")
     return ll, d, mu

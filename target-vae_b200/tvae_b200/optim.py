@@ -82,9 +82,13 @@ class Adam(torch.optim.Optimizer):
                 table = (AdamTensor * len(sel))()
                 for i, (_, p, g, m, v) in enumerate(sel):
                     table[i] = AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
-                check(lib.tvae_adam_step(ctypes.cast(table, ctypes.c_void_p), len(sel), float(group["lr"]), float(beta1),
-                                         float(beta2), float(group["eps"]), float(group["weight_decay"]), k,
-                                         1 if zero_grad else 0, stream_ptr()), "tvae_adam_step")
+                dev = sel[0][1].device
+                if any(t[1].device != dev for t in sel):
+                    raise RuntimeError("tvae_b200.optim.Adam: the parameters of one group must live on one CUDA device")
+                with torch.cuda.device(dev):      # the library launches on the current device
+                    check(lib.tvae_adam_step(ctypes.cast(table, ctypes.c_void_p), len(sel), float(group["lr"]), float(beta1),
+                                             float(beta2), float(group["eps"]), float(group["weight_decay"]), k,
+                                             1 if zero_grad else 0, stream_ptr()), "tvae_adam_step")
         return loss
 
 
@@ -97,8 +101,9 @@ class RunningMeans:
 
     def update(self, elbo, log_p, kl, b):
         e, l, k = (ops.f32(t).reshape(1) for t in (elbo, log_p, kl))
-        check(_lib().tvae_running_means(e.data_ptr(), l.data_ptr(), k.data_ptr(), float(b), self.state.data_ptr(),
-                                        stream_ptr()), "tvae_running_means")
+        with torch.cuda.device(self.state.device):
+            check(_lib().tvae_running_means(e.data_ptr(), l.data_ptr(), k.data_ptr(), float(b), self.state.data_ptr(),
+                                            stream_ptr()), "tvae_running_means")
 
     def read(self):
         c, elbo, err, kl = self.state.tolist()
