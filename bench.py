@@ -36,6 +36,7 @@ from tvae_b200.config import PRESETS  # noqa: E402
 
 METRIC = "train images/sec (fwd+bwd)"
 UNIT = "images/s"
+OTHER_CONFIGS = ("cfg1", "cfg3", "cfg4", "cfg5")     # BASELINE.json configs[0,2,3,4]; configs[1] = cfg2 is the headline workload
 
 
 def parse():
@@ -48,6 +49,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU minibatch (default: the trainer's 100; cfg5: 256)")
     ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg1/cfg3/cfg4/cfg5 measurements of the `configs` block")
     return ap.parse_args()
 
 
@@ -263,7 +265,9 @@ def run_reference(args, cfg):
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(cfg, args.batch or cfg.batch, args.gpus),
+        "data": "synthetic", "config": dict(workload_config(cfg, args.batch or cfg.batch, args.gpus), timed_batch=B,
+                                            note=f"CPU arm: a bounded sample - {steps} step(s) of {B} images (the reference's best "
+                                                 f"operating point on these host cores), not the GPU arm's per-GPU minibatch"),
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{steps} step(s) of {B} images, {_cpu_what(kind)}, torch CPU fp32, {threads} threads "
                                    f"(os.cpu_count() = {os.cpu_count()})"},
@@ -298,230 +302,311 @@ def build_models(cfg, dev):
     return gen.to(dev), enc.to(dev)
 
 
-def measure_tf32_peak(dev, dtype=torch.float32):
-    """cuBLAS TF32 (or fp16) GEMM 8192^3, best of 10 (same method MEASURED_PEAKS.json uses for bf16)."""
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written): the roofline denominators.  Event-timed single launches are compared with the
+    BURST bf16 figure (kind::f16 and bf16 issue at the same tensor-core rate); fallback = B200_PROFILING.md's numbers."""
     try:
-        n = 8192
-        a = torch.randn(n, n, device=dev, dtype=dtype); b = torch.randn(n, n, device=dev, dtype=dtype)
-        c = torch.empty(n, n, device=dev, dtype=dtype)
-        for _ in range(3):
-            torch.matmul(a, b, out=c)
-        best = 1e9
-        for _ in range(10):
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"tensor": float(pk["bf16_tflops"]), "tensor_sustained": float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])),
+                "hbm": float(pk["hbm_gbs"]), "source": "MEASURED_PEAKS.json (bf16_tflops burst / hbm_gbs)"}
+    except Exception:
+        return {"tensor": 1650.0, "tensor_sustained": 1390.0, "hbm": 6500.0, "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
-def run_ours(args, cfg):
-    import torch.distributed as dist
-    from tvae_b200 import dp, elbo as E, ops
+class Ctx:
+    """Process-wide measurement context: ranks, device, barrier / max-over-ranks helpers."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the single JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or cfg.batch
-    gen, enc = build_models(cfg, dev)
-    params = list(gen.parameters()) + list(enc.parameters())
-    sync = dp.GradSync() if world > 1 else None
-    x = torch.from_numpy(synth.image_coords(cfg.n)).to(dev)
-    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL writes its version / debug lines to stdout by default: keep stdout for the single JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    # distinct synthetic minibatches: pinned host copies (e2e leg) and device-resident copies (value leg)
-    NB = 4
-    host = [synth.minibatch(cfg, B, seed=100 * rank + i) for i in range(NB)]
-    y_pin = [torch.from_numpy(h["y"]).pin_memory() for h in host]
-    ctf_pin = [torch.from_numpy(h["ctf"]).pin_memory() if h["ctf"] is not None else None for h in host]
-    y_dev = [t.to(dev) for t in y_pin]
-    ctf_dev = [None if t is None else t.to(dev) for t in ctf_pin]
-    y_stage = torch.empty_like(y_dev[0])
-    ctf_stage = None if ctf_dev[0] is None else torch.empty_like(ctf_dev[0])
-
-    def step(y, ctf):
-        for p in params:
-            p.grad = None
-        if cfg.likelihood == "gaussian":
-            elbo, logp, kl = E.eval_minibatch_particles(x, y, ctf, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G,
-                                                        cfg.p, cfg.mask_radius, sync=sync)
-        else:
-            elbo, logp, kl = E.eval_minibatch(x, y, gen, enc, "attention", r_inf, 0, dev, cfg.theta_prior, cfg.G, cfg.n, sync=sync)
-        (-elbo).backward()
-        return elbo
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v):
-        if world == 1:
+    def max_over_ranks(self, v):
+        if self.world == 1:
             return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t)
 
-    W, K = max(args.warmup, 3), args.steps
-    for i in range(W):
-        step(y_dev[i % NB], ctf_dev[i % NB])
-    barrier()
-
-    # ---- value: inputs resident in HBM, device-timed, max over ranks
-    launches0 = ops.launch_count()
-    ops.profile_enable(True)
-    with ClockSampler(local) as clk:
-        barrier()
+    def timed(self, fn, K):
+        """K calls of fn(i) bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> ms total."""
+        self.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
-            step(y_dev[i % NB], ctf_dev[i % NB])
+            fn(i)
         e1.record()
-        barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+
+class Workload:
+    """Models, synthetic minibatches (pinned host + device copies) and the step function of one config."""
+    NB = 4
+
+    def __init__(self, ctx, cfg, B):
+        from tvae_b200 import dp, elbo as E
+        self.ctx, self.cfg, self.B, self.E = ctx, cfg, B, E
+        dev = ctx.dev
+        self.gen, self.enc = build_models(cfg, dev)
+        self.params = list(self.gen.parameters()) + list(self.enc.parameters())
+        self.sync = dp.GradSync() if ctx.world > 1 else None
+        self.x = torch.from_numpy(synth.image_coords(cfg.n)).to(dev)
+        self.r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+        host = [synth.minibatch(cfg, B, seed=100 * ctx.rank + i) for i in range(self.NB)]
+        self.y_pin = [torch.from_numpy(h["y"]).pin_memory() for h in host]
+        self.ctf_pin = [torch.from_numpy(h["ctf"]).pin_memory() if h["ctf"] is not None else None for h in host]
+        self.y_dev = [t.to(dev) for t in self.y_pin]
+        self.ctf_dev = [None if t is None else t.to(dev) for t in self.ctf_pin]
+        self.y_stage = torch.empty_like(self.y_dev[0])
+        self.ctf_stage = None if self.ctf_dev[0] is None else torch.empty_like(self.ctf_dev[0])
+
+    def step(self, y, ctf, noise=None, sync="default"):
+        cfg, E = self.cfg, self.E
+        sync = self.sync if sync == "default" else sync
+        for p in self.params:
+            p.grad = None
+        if cfg.likelihood == "gaussian":
+            elbo, logp, kl = E.eval_minibatch_particles(self.x, y, ctf, self.gen, self.enc, "attention", self.r_inf, 0, self.ctx.dev,
+                                                        cfg.theta_prior, cfg.G, cfg.p, cfg.mask_radius, noise=noise, sync=sync)
+        else:
+            elbo, logp, kl = E.eval_minibatch(self.x, y, self.gen, self.enc, "attention", self.r_inf, 0, self.ctx.dev, cfg.theta_prior,
+                                              cfg.G, cfg.n, noise=noise, sync=sync)
+        (-elbo).backward()
+        return elbo
+
+    def step_resident(self, i):
+        return self.step(self.y_dev[i % self.NB], self.ctf_dev[i % self.NB])
+
+    def step_e2e(self, i):
+        """the public call with HOST buffers: H2D of the step's inputs from pinned memory + D2H read of the ELBO"""
+        self.y_stage.copy_(self.y_pin[i % self.NB], non_blocking=True)
+        if self.ctf_stage is not None:
+            self.ctf_stage.copy_(self.ctf_pin[i % self.NB], non_blocking=True)
+        return float(self.step(self.y_stage, self.ctf_stage).detach())
+
+    @property
+    def h2d_bytes(self):
+        return self.y_pin[0].numel() * 4 + (0 if self.ctf_pin[0] is None else self.ctf_pin[0].numel() * 4)
+
+
+def kernel_rooflines(cfg, B, prof, K, ms_step, peaks, clk_summary, ops):
+    """Per-kernel rooflines from the CUDA-event timings taken INSIDE the timed region (tvae_profile_*).  Tensor-bound
+    kernels: algorithmic flop = SURVEY.md 8(d) dense MAC count x 2 (zero-padding taps included), with the executed-MAC
+    figure beside it for the conv kernels (they skip K chunks that only meet zero padding); HBM-bound kernels: algorithmic
+    bytes.  `achieved` of the dominant kernel is the EXECUTED rate (it cannot exceed the peak); `achieved_dense` is the
+    contract's dense-count figure."""
+    fl = cfg.flops_fwd()
+    M = B * cfg.n ** 2
+    pos = cfg.Hout ** 2
+    R = B * cfg.G * pos
+    NH = 3 + 2 * cfg.z
+    H, Lh = cfg.hidden, cfg.gen_layers - 1
+    # per STEP algorithmic work of every launch carrying that name
+    tensor = {"conv1_fwd": fl["conv1"] * B, "conv1_wgrad": fl["conv1"] * B}
+    if cfg.fourier:
+        first = 2.0 * cfg.fourier_dim * H * M
+        tensor.update({"gen_l1_fwd": first, "gen_l1_wgrad": first, "gen_l1_dgrad": first})
+    if Lh > 0:
+        tensor["linear_nt"] = 2.0 * Lh * 2.0 * H * H * M          # forward + input-gradient GEMM of every hidden layer
+        tensor["linear_tn"] = Lh * 2.0 * H * H * M                 # weight-gradient GEMM of every hidden layer
+    if cfg.ctf:
+        tensor["ctf_apply"] = 2.0 * 2.0 * cfg.n ** 2 * (cfg.n - 1) ** 2 * B
+    hbm = {
+        # read x1 (fp16), write h (fp16) and the (3+2z) fp32 head maps
+        "conv2_heads": R * cfg.O * 2 * 2 + R * NH * 4,
+        # read h, d_heads; write dhpre
+        "enc_heads_bwd": R * cfg.O * 2 * 2 + R * NH * 4,
+        # read dhpre, x1; write dx1
+        "enc_dx1_dw2": R * cfg.O * 2 * 3,
+        # SURVEY 8(d): fwd reads (3+2z) head maps + the Gumbel noise; bwd reads the same and writes the map gradients
+        "attn_fwd": B * cfg.L * (NH + 1) * 4,
+        "attn_bwd": B * cfg.L * (2 * NH + 1) * 4,
+    }
+    executed = {}
+    es = ops.enc_shape(B, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
+    executed["conv1_fwd"] = ops.conv1_executed_fraction(es, False)
+    executed["conv1_wgrad"] = ops.conv1_executed_fraction(es, True)
+    out = {}
+    for name, (ms_tot, n_launch) in prof.items():
+        if n_launch <= 0:
+            continue
+        ms = ms_tot / K                       # per step, all launches of that name
+        e = {"ms_per_step": ms, "launches_per_step": n_launch / K, "share_of_step": ms / ms_step}
+        if name in tensor:
+            dense = tensor[name] / (ms * 1e-3) / 1e12
+            ex = executed.get(name, 1.0)
+            e.update({"bound": "tensor", "achieved": dense * ex, "achieved_dense": dense, "executed_fraction": ex,
+                      "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": dense * ex / peaks["tensor"],
+                      "frac_dense": dense / peaks["tensor"]})
+        elif name in hbm:
+            gbs = hbm[name] / (ms * 1e-3) / 1e9
+            e.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                      "bytes_per_step": hbm[name]})
+        out[name] = e
+    cands = [k for k in out if out[k].get("bound") == "tensor"]
+    dom = max(cands, key=lambda k: out[k]["ms_per_step"], default=None)
+    if dom is None:
+        return None
+    d = out[dom]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(cfg.name.split("_")[0], {}).get(dom)
+    except Exception:
+        pass
+    roof = {"bound": "tensor", "kernel": dom, "achieved": d["achieved"], "peak": d["peak"], "unit": "TFLOP/s", "frac": d["frac"],
+            "traffic": traffic, "achieved_dense": d["achieved_dense"], "frac_dense": d["frac_dense"],
+            "executed_fraction": d["executed_fraction"],
+            "achieved_counts": "achieved = EXECUTED MAC x2 per launch / event-timed launch duration; achieved_dense = SURVEY 8(d) "
+                               "dense count (zero-padding taps included, what cuDNN executes) - the conv kernels skip all-padding K chunks",
+            "peak_source": peaks["source"], "ms_per_launch": d["ms_per_step"] / max(d["launches_per_step"], 1e-9),
+            "share_of_step": d["share_of_step"],
+            "precision": "every contraction is tcgen05.mma.kind::f16: FP16 operands (11-bit significand = TF32's, the reference's "
+                         "cuDNN default; NARROWER than the fp32 SGEMM the reference's generator nn.Linear layers use by default - "
+                         "per-parameter effect: profiles/r02_grad_parity_table.md) with FP32 accumulation; gradients carry exact "
+                         "power-of-two scales",
+            "others": {k: v for k, v in out.items() if k != dom}}
+    if clk_summary and clk_summary.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        hw_peak = sms * 8192 * clk_summary["sm_mhz"] * 1e6 / 1e12
+        roof["tensor_pipe_util_est"] = d["achieved"] / hw_peak
+        roof["tensor_pipe_util_how"] = (f"executed TFLOP/s / ({sms} SMs x 8192 flop/clk x {clk_summary['sm_mhz']:.0f} MHz sampled under "
+                                        f"load = {hw_peak:.0f} TFLOP/s)")
+    return roof
+
+
+def measure_config(ctx, cfg, B, K, W, legs=("e2e",)):
+    """value (inputs resident in HBM) [+ e2e / train-step / get_latent legs] of one config at ctx.world GPUs."""
+    from tvae_b200 import ops
+    wl = Workload(ctx, cfg, B)
+    for i in range(W):
+        wl.step_resident(i)
+    ctx.barrier()
+    launches0 = ops.launch_count()
+    ops.profile_enable(True)
+    with ClockSampler(ctx.local) as clk:
+        ms_total = ctx.timed(wl.step_resident, K)
     prof = ops.profile_collect()
     ops.profile_enable(False)
     launches = ops.launch_count() - launches0
-    value = world * B * K / (ms_total * 1e-3)
+    world = ctx.world
+    res = {"value": world * B * K / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total / K, "steps": K, "warmup": W,
+           "per_gpu_batch": B, "gpu_launches": launches, "clocks": clk.summary(),
+           "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12}
+    if "e2e" in legs:
+        for i in range(2):
+            wl.step_e2e(i)
+        e2e_ms = ctx.timed(wl.step_e2e, K)
+        res["e2e"] = {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4}
+    if "train" in legs:
+        # SURVEY 8f-1: the same step followed by the one-launch Adam update (reported next to the contract metric)
+        from tvae_b200.optim import Adam
+        opt = Adam(wl.params, lr=2e-4)
 
-    # ---- e2e: same call, host buffers: H2D of the step's inputs from pinned memory + D2H read of the result
-    h2d = y_pin[0].numel() * 4 + (0 if ctf_pin[0] is None else ctf_pin[0].numel() * 4)
-    for i in range(2):
-        y_stage.copy_(y_pin[i % NB], non_blocking=True)
-        float(step(y_stage, ctf_stage if ctf_stage is None else ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)).detach())
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        y_stage.copy_(y_pin[i % NB], non_blocking=True)
-        if ctf_stage is not None:
-            ctf_stage.copy_(ctf_pin[i % NB], non_blocking=True)
-        _ = float(step(y_stage, ctf_stage))        # D2H read of the ELBO every step
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    e2e = world * B * K / (e2e_ms * 1e-3)
+        def train_step(i):
+            wl.step_resident(i)
+            opt.step()
+        for i in range(2):
+            train_step(i)
+        ms = ctx.timed(train_step, K)
+        res["train_step"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+                             "what": "fwd + bwd + fused multi-tensor Adam (tvae_adam_step), inputs resident in HBM"}
+    if "latent" in legs:
+        # SURVEY 8f-2: clustering_*.get_latent over the same minibatches
+        def latent(i):
+            wl.E.get_latent(wl.x, wl.y_dev[i % wl.NB], wl.enc, "attention", wl.r_inf, ctx.dev, cfg.n)
+        for i in range(2):
+            latent(i)
+        ms = ctx.timed(latent, K)
+        res["get_latent"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT, "ms_per_minibatch": ms / K,
+                             "what": "clustering_*.get_latent (inference: encoder forward + argmax / expectation kernels), inputs resident in HBM"}
+    if "dp_parity" in legs and world > 1:
+        res["dp_parity"] = dp_parity_check(ctx, wl)
+    if ctx.rank == 0:
+        res["roofline"] = kernel_rooflines(cfg, B, prof, K, ms_total / K, measured_peaks(), res["clocks"], ops)
+    return res, wl
 
-    # ---- extra (SURVEY §8f-1): the same step followed by the one-launch Adam update (a true train step; reported next to
-    # the contract metric, never instead of it)
-    from tvae_b200.optim import Adam
-    opt = Adam(params, lr=2e-4)
-    for i in range(2):
-        step(y_dev[i % NB], ctf_dev[i % NB]); opt.step()
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        step(y_dev[i % NB], ctf_dev[i % NB])
-        opt.step()
-    e1.record()
-    barrier()
-    train_ms = max_over_ranks(e0.elapsed_time(e1))
-    train_ips = world * B * K / (train_ms * 1e-3)
 
-    # ---- extra (SURVEY §8f-2): clustering_*.get_latent over the same minibatches - encoder forward without the hidden
-    # map + one reduction kernel per minibatch (argmax (r,t), z / theta there, softmax-expected translation)
-    for i in range(2):
-        E.get_latent(x, y_dev[i % NB], enc, "attention", r_inf, dev, cfg.n)
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        E.get_latent(x, y_dev[i % NB], enc, "attention", r_inf, dev, cfg.n)
-    e1.record()
-    barrier()
-    latent_ms = max_over_ranks(e0.elapsed_time(e1))
-    latent_ips = world * B * K / (latent_ms * 1e-3)
+def dp_parity_check(ctx, wl):
+    """One-off self-check of the data-parallel path: the rank-averaged gradients of one sharded step equal the
+    gradients rank 0 computes alone on the WHOLE global minibatch (same images, same noise).  -> max over parameters of
+    the relative Frobenius error (atomics order and the batch-dependent power-of-two gradient scales make it ~1e-4)."""
+    cfg, B, world, dev = wl.cfg, wl.B, ctx.world, ctx.dev
+    ys = [synth.minibatch(cfg, B, seed=9000 + r) for r in range(world)]
+    nz = synth.noise(cfg, B * world, seed=77)
+    lo, hi = ctx.rank * B, (ctx.rank + 1) * B
+    my_noise = {k: torch.from_numpy(v[lo:hi].copy()).to(dev) for k, v in nz.items()}
+    my = ys[ctx.rank]
+    wl.step(torch.from_numpy(my["y"]).to(dev), None if my["ctf"] is None else torch.from_numpy(my["ctf"]).to(dev), noise=my_noise)
+    torch.cuda.synchronize()
+    sharded = [p.grad.detach().clone() for p in wl.params]
+    out = None
+    if ctx.rank == 0:
+        import numpy as np_
+        yg = torch.from_numpy(np_.concatenate([d["y"] for d in ys])).to(dev)
+        cg = None if ys[0]["ctf"] is None else torch.from_numpy(np_.concatenate([d["ctf"] for d in ys])).to(dev)
+        wl.step(yg, cg, noise={k: torch.from_numpy(v).to(dev) for k, v in nz.items()}, sync=None)
+        torch.cuda.synchronize()
+        names = [n for n, _ in wl.gen.named_parameters()] + [n for n, _ in wl.enc.named_parameters()]
+        errs = {n: float((a - p.grad).norm() / (p.grad.norm() + 1e-30)) for n, a, p in zip(names, sharded, wl.params)}
+        worst = max(errs, key=errs.get)
+        out = {"max_rel_err": errs[worst], "worst_param": worst, "global_batch": B * world,
+               "what": "||avg_ranks(grad) - grad(full global batch on rank 0)||_F / ||.||_F, max over parameters; identical images and noise"}
+    ctx.barrier()
+    return out
+
+
+def run_ours(args, cfg):
+    ctx = Ctx()
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    B = args.batch or cfg.batch
+    W, K = max(args.warmup, 3), args.steps
+    main, wl = measure_config(ctx, cfg, B, K, W, legs=("e2e", "train", "latent", "dp_parity"))
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs (north star: "throughput ... of each config's shape ... as a fraction of roofline"):
+    # a few steps each, same legs as the headline minus the extras; cfg5 is the weak-scaling config (B = 256 per GPU)
+    others = {}
+    if not args.no_other_configs:
+        for name in OTHER_CONFIGS:
+            if name == args.config:
+                continue
+            c = PRESETS[name]
+            k = max(3, min(K, 8 if name != "cfg5" else 4))
+            try:
+                r, w2 = measure_config(ctx, c, c.batch, k, 3, legs=("e2e",))
+                del w2
+                r["workload"] = workload_config(c, c.batch, world)["workload"]
+                if rank == 0 and r.get("roofline"):
+                    roof = r["roofline"]
+                    r["roofline"] = {kk: roof[kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "achieved_dense",
+                                                            "frac_dense", "executed_fraction", "share_of_step", "ms_per_launch")}
+                    r["kernels"] = {kn: {q: v[q] for q in ("ms_per_step", "bound", "achieved", "unit", "frac") if q in v}
+                                    for kn, v in {**roof["others"], roof["kernel"]: roof}.items() if isinstance(v, dict)}
+                others[name] = r
+            except Exception as e:           # a config that fails must not take the headline line down
+                others[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return
-
-    # ---- roofline of the dominant kernel (event-timed inside the timed region above)
-    flops = cfg.flops_fwd()
-    algo = {"conv1_fwd": flops["conv1"] * B, "conv1_wgrad": flops["conv1"] * B}
-    if cfg.fourier:
-        first = 2 * cfg.fourier_dim * cfg.hidden * cfg.n ** 2 * B
-        algo.update({"gen_l1_fwd": first, "gen_l1_wgrad": first, "gen_l1_dgrad": first})
-    dom = max((k for k in prof if k in algo), key=lambda k: prof[k][0], default=None)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    tf32_peak = measure_tf32_peak(dev)
-    f16_peak = measure_tf32_peak(dev, torch.float16)
-    roofline = None
-    if dom is not None and prof[dom][1] > 0:
-        ms_launch = prof[dom][0] / prof[dom][1]
-        achieved = algo[dom] / (ms_launch * 1e-3) / 1e12
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(cfg.name.split("_")[0], {}).get(dom)
-        except Exception:
-            pass
-        # the conv1 kernels skip K chunks that only meet zero padding: report the executed-MAC rate next to the
-        # dense-count (contract) figure - the dense-count figure can exceed the tensor peak, the executed one cannot
-        executed = 1.0
-        if dom.startswith("conv1"):
-            es = ops.enc_shape(B, cfg.C, cfg.n, cfg.k, cfg.p, cfg.G, cfg.O, cfg.z)
-            executed = ops.conv1_executed_fraction(es, dom == "conv1_wgrad")
-        op_peak, op_dtype = f16_peak, "fp16 operands / fp32 accumulate"
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": op_peak, "unit": "TFLOP/s",
-                    "frac": achieved / op_peak, "traffic": traffic,
-                    "achieved_counts": "dense MAC count x2 per launch (SURVEY 8d: zero-padding taps included, what cuDNN executes)",
-                    "executed_fraction": executed, "achieved_executed": achieved * executed,
-                    "frac_executed": achieved * executed / op_peak,
-                    "peak_source": f"cuBLAS {op_dtype} 8192^3 best-of-10 measured in this run, same method as "
-                                   "MEASURED_PEAKS.json; bf16_tflops_sustained there = %.1f -> frac_of_bf16" % bf16_peak,
-                    "f16_peak": f16_peak, "tf32_peak": tf32_peak,
-                    "precision": "every contraction is tcgen05.mma.kind::f16: FP16 operands (11-bit significand = TF32's, the "
-                                 "reference's cuDNN default) with FP32 accumulation; gradients carry exact power-of-two scales",
-                    "frac_of_bf16": achieved / bf16_peak, "ms_per_launch": ms_launch,
-                    "share_of_step": prof[dom][0] / ms_total,
-                    "kernels_ms_per_step": {k: v[0] / K for k, v in sorted(prof.items())}}
-
-    # count-based tensor-pipe utilisation of the dominant kernel: executed MMA flop / (SMs x 8192 flop/clk x sampled SM clock)
-    if roofline is not None:
-        cs = clk.summary()
-        if cs and cs.get("sm_mhz"):
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            hw_peak = sms * 8192 * cs["sm_mhz"] * 1e6 / 1e12
-            roofline["tensor_pipe_util_est"] = roofline["achieved_executed"] / hw_peak
-            roofline["tensor_pipe_util_how"] = (f"executed TFLOP/s / ({sms} SMs x 8192 flop/clk x {cs['sm_mhz']:.0f} MHz sampled under load "
-                                                f"= {hw_peak:.0f} TFLOP/s); ncu cycle-based figure in profiles/r01_ncu_step_cfg2_final.md")
-    # per-kernel rooflines of the other event-timed kernels (explanatory; the contract's `roofline` is the dominant one)
-    if roofline is not None:
-        hbm_peak = float(peaks.get("hbm_gbs", 6560.0))
-        pos = cfg.Hout ** 2
-        R = B * cfg.G * pos
-        others = {}
-        for k in algo:
-            if k != dom and k in prof and prof[k][1] > 0:
-                ms = prof[k][0] / prof[k][1]
-                tf = algo[k] / (ms * 1e-3) / 1e12
-                others[k] = {"bound": "tensor", "achieved": tf, "peak": f16_peak, "unit": "TFLOP/s", "frac": tf / f16_peak,
-                             "ms_per_launch": ms}
-        if "conv2_heads" in prof and prof["conv2_heads"][1] > 0:
-            # algorithmic bytes: read x1 (fp16), write h (fp16) and the (3+2z) fp32 head maps
-            nbytes = R * cfg.O * 2 * 2 + R * (3 + 2 * cfg.z) * 4
-            ms = prof["conv2_heads"][0] / prof["conv2_heads"][1]
-            gbs = nbytes / (ms * 1e-3) / 1e9
-            others["conv2_heads"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                     "ms_per_launch": ms, "bytes_per_launch": nbytes}
-        roofline["others"] = others
 
     # ---- the GPU baseline BASELINE.md §5 names: the unmodified reference, eager, on this B200 (after our own legs: its
     # allocations and cuDNN autotuning cannot disturb them); a failure is reported, it does not take the line down
@@ -545,20 +630,20 @@ def run_ours(args, cfg):
             cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": workload_config(cfg, B, world),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref,
-        "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12,
-        "train_step": {"value": train_ips, "unit": UNIT, "ms_per_step": train_ms / K,
-                       "what": "fwd + bwd + fused multi-tensor Adam (tvae_adam_step), inputs resident in HBM"},
-        "get_latent": {"value": latent_ips, "unit": UNIT, "ms_per_minibatch": latent_ms / K,
-                       "what": "clustering_*.get_latent (inference: encoder forward + argmax / expectation kernel), inputs resident in HBM"},
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "roofline": main["roofline"],
+        "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "tflops_step": main["tflops_step"],
+        "train_step": main.get("train_step"), "get_latent": main.get("get_latent"),
+        "configs": others,
     }
+    if "dp_parity" in main:
+        line["dp_parity_max_rel_err"] = None if main["dp_parity"] is None else main["dp_parity"]["max_rel_err"]
+        line["dp_parity"] = main["dp_parity"]
     OUT.emit(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 class StdoutForJsonOnly:

@@ -154,6 +154,39 @@ int tvae_attn_softmax_pair(const float* heads, const float* gumbel, float* q_t_r
 /* clustering_mnist.py:122-161: argmax (r,t), z/theta at the argmax, softmax-expected translation */
 int tvae_get_latent(const tvae_attn_shape* s, const float* heads, float* z_content, float* theta_mu, float* dx, int* argmax, void* stream);
 
+/* Argmax (rotation, translation) assignment at fp32 accuracy (clustering_mnist.py:127 `attn.view(B,-1).max(1)`, z / theta
+ * gathered there, :140-161).  The tensor-core encoder's FP16-operand logits are used as a FILTER: every cell of the fast
+ * attention map within rel_tol x (max - min) of its maximum is a candidate (at most TVAE_REFINE_MAX_CAND per image; the
+ * band is halved until they fit), and conv1 -> act -> [fc_r] -> conv2 -> act -> heads is re-evaluated at those cells from
+ * the fp32 image, the fp32 bilinear-rotated filters (models.py:174-197) and the fp32 weights, fp32 products summed in
+ * double and rounded to fp32 where the reference's fp32 layers round.  Outputs overwrite those of tvae_get_latent:
+ * argmax (B) cell index r*P + pos, z_content (B,2z) = [z_mu, exp(z_logstd)], theta_mu (B); the softmax-expected
+ * translation stays the one of tvae_get_latent.  `weight` is conv1.weight (O,C,1,k,k) itself, not the fp16 bank. */
+#define TVAE_REFINE_MAX_CAND 32
+typedef struct {
+    const float* y;          /* (B,C,n,n) */
+    const float* weight;     /* conv1.weight (O,C,1,k,k) */
+    const float* conv1_bias; /* (O) */
+    const float* w2;         /* conv2.weight (O,O) */
+    const float* b2;         /* (O) */
+    const float* wh;         /* [NH][O] stacked head weights */
+    const float* bh;         /* [NH] */
+    const float* head_add;   /* [NH][G] ([NH][1] with rotation pooling) */
+    const float* fc_w;       /* fc_r.weight (G) or NULL */
+    const float* fc_b;       /* fc_r.bias (1) */
+    const float* heads;      /* fast head maps (B,NH,G,P) from tvae_encoder_fwd */
+    float rel_tol;           /* candidate band as a fraction of the map's range; 2e-3 is 4x the largest flip observed */
+    float* bank32;           /* scratch fp32 [G*O][C*k*k] */
+    int* cand;               /* scratch/out (B, TVAE_REFINE_MAX_CAND) candidate cells */
+    int* n_cand;             /* scratch/out (B) */
+    float* cand_heads;       /* scratch/out (B, TVAE_REFINE_MAX_CAND, NH) refined head values at the candidates */
+    float* z_content;        /* out (B,2z) */
+    float* theta_mu;         /* out (B) */
+    int* argmax;             /* out (B) */
+    float* refined_logit;    /* out (B) or NULL: the refined maximal logit */
+} tvae_refine_args;
+int tvae_refine_argmax(const tvae_enc_shape* s, const tvae_refine_args* a, void* stream);
+
 /* ------------------------------------------------------------------ generator (models.py:53-58, 95-123) */
 typedef struct {
     int B, N;                /* images, pixels per image (M = B*N rows) */

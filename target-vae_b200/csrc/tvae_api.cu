@@ -11,6 +11,7 @@
 #include "simt_gen.cuh"
 #include "simt_kernels.cuh"
 #include "enc_bwd_fused.cuh"
+#include "refine.cuh"
 
 using namespace tvae;
 
@@ -645,6 +646,43 @@ int tvae_attn_softmax_pair(const float* heads, const float* gumbel, float* q_t_r
 int tvae_get_latent(const tvae_attn_shape* s, const float* heads, float* z_content, float* theta_mu, float* dx, int* argmax, void* stream) {
     ++g_launch_count;
     TVAE_DISPATCH_Z(s->z, (get_latent_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(heads, s->G, s->d, s->s, z_content, theta_mu, dx, argmax)));
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// exact re-evaluation of the attention logits at the near-maximal cells of the fast maps (refine.cuh)
+int tvae_refine_argmax(const tvae_enc_shape* s, const tvae_refine_args* a, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    TVAE_REQUIRE(a->y && a->weight && a->conv1_bias && a->w2 && a->b2 && a->wh && a->bh && a->head_add && a->heads,
+                 "refine_argmax: null input");
+    TVAE_REQUIRE(a->bank32 && a->cand && a->n_cand && a->cand_heads && a->z_content && a->theta_mu && a->argmax,
+                 "refine_argmax: null scratch / output");
+    TVAE_REQUIRE(a->rel_tol >= 0.f && a->rel_tol < 1.f, "refine_argmax: rel_tol must be in [0, 1)");
+    const ConvGeom g = make_geom(s);
+    const int NH = 3 + 2 * s->z;
+    const bool pooled = a->fc_w != nullptr;
+    TVAE_REQUIRE(!pooled || a->fc_b, "refine_argmax: rotation pooling needs fc_b");
+    const int G2 = pooled ? 1 : g.G;
+    const int L = G2 * g.P;
+    cudaStream_t st = S(stream);
+    Timed tm("refine_argmax", st);
+    ++g_launch_count;
+    filter_bank_f32_kernel<<<blocks_for((long long)g.G * g.O * g.K, 256), 256, 0, st>>>(a->weight, a->bank32, g.O, g.C, g.k, g.G, make_rot_table(g.G));
+    ++g_launch_count;
+    refine_select_kernel<<<g.B, 1024, 0, st>>>(a->heads, NH, L, a->rel_tol, a->cand, a->n_cand);
+    RefineEvalParams p{};
+    p.y = a->y; p.bank32 = a->bank32; p.conv1_bias = a->conv1_bias; p.w2 = a->w2; p.b2 = a->b2; p.wh = a->wh; p.bh = a->bh;
+    p.head_add = a->head_add; p.fc_w = a->fc_w; p.fc_b = a->fc_b; p.cand = a->cand; p.n_cand = a->n_cand; p.cand_heads = a->cand_heads;
+    p.C = g.C; p.n = g.n; p.k = g.k; p.p = g.p; p.G = g.G; p.O = g.O; p.d = g.d; p.NH = NH;
+    p.act = s->act == TVAE_ACT_TANH ? kActTanh : 0;
+    const size_t sm = sizeof(float) * (((g.K + 3) & ~3) + 3 * g.O);
+    TVAE_REQUIRE(sm <= 227 * 1024, "refine_argmax: filter window does not fit shared memory");
+    TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&refine_eval_kernel), 227 * 1024));
+    ++g_launch_count;
+    refine_eval_kernel<<<dim3(kRefineMaxCand, g.B), 256, sm, st>>>(p);
+    ++g_launch_count;
+    refine_pick_kernel<<<g.B, 32, 0, st>>>(a->cand, a->n_cand, a->cand_heads, NH, s->z, a->z_content, a->theta_mu, a->argmax, a->refined_logit);
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -100,10 +100,15 @@ def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r
                  theta_prior)
 
 
-def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
+def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim, refine=True, return_argmax=False):
     """clustering_*.get_latent, attention branches (clustering_mnist.py:81-120 r_inf unimodal with a plain-conv encoder,
     :122-161 r_inf attention[+offsets]): one encoder pass + one reduction kernel; returns (z_content (B,2z),
-    theta_mu (B,1), dx (B,2))."""
+    theta_mu (B,1), dx (B,2)) [+ the argmax cell index (B) with return_argmax].
+
+    refine (default): the argmax (r, t) - `attn.view(B,-1).max(1)`, clustering_mnist.py:127 - and the z / theta values
+    gathered there are those of an fp32 evaluation: the FP16-operand tensor-core maps only select the near-maximal
+    candidate cells, at which the logit chain is re-evaluated with fp32 operands (tvae_refine_argmax).  refine=False
+    keeps the fast maps' own argmax (can flip on images whose two best logits are within ~1e-4 of the map's range)."""
     from . import ops
     _encoder_spec(encoder_model, t_inf, r_inf, None if r_inf != 'unimodal' else 1.0)   # validates the branch only
     with torch.no_grad():
@@ -111,9 +116,15 @@ def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim):
         if not y.is_cuda:
             raise RuntimeError("get_latent: the hot path runs on sm_100a only (no CPU fallback)")
         es = encoder_model.encoder_spec()
-        heads = TF.encoder_heads_inference(es, y, *encoder_model.hot_path_params())
+        params = encoder_model.hot_path_params()
+        heads = TF.encoder_heads_inference(es, y, *params)
         B, NH, G, d, _ = heads.shape
         s = ops.attn_shape(B, G, d, es.z, TF.pixel_spacing(x), es.tables()[1])
         with torch.cuda.device(heads.device):
-            zc, th, dx, _ = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
+            zc, th, dx, am = ops.get_latent(s, heads.reshape(B, NH, G, d * d).contiguous())
+        if refine:
+            r = TF.refine_argmax(es, y, heads, *params)
+            zc, th, am = r["z_content"], r["theta_mu"], r["argmax"]
+    if return_argmax:
+        return zc, th, dx, am
     return zc, th, dx

@@ -136,6 +136,25 @@ def encoder_heads_inference(spec: EncoderSpec, y, *params):
     return heads.view(s.B, 3 + 2 * spec.z, spec.attn_G, d, d)
 
 
+@on_tensor_device
+def refine_argmax(spec: EncoderSpec, y, heads, *params, rel_tol=ops.REFINE_REL_TOL):
+    """fp32-accurate argmax (r, t) and the z / theta values there: the fast head maps select the candidate cells, the
+    logit chain is re-evaluated exactly at them (ops.refine_argmax).  heads: (B, NH, G2, H', W') from
+    encoder_heads_inference on the same images and parameters."""
+    w1, b1, w2, b2, wa, ba, wr, br, wz, bz = params[:10]
+    if w1.dim() == 4:
+        w1 = w1.unsqueeze(2)
+    O, C, _, k, _ = w1.shape
+    B, n = y.shape[0], y.shape[-1]
+    s = ops.enc_shape(B, C, n, k, spec.padding, spec.G, O, spec.z, spec.act)
+    p_r, offs = spec.tables()
+    wh, bh, add = ops.head_tables(wa, ba, wr, br, wz, bz, spec.attn_G, p_r, offs, y.device)
+    with torch.no_grad():
+        return ops.refine_argmax(s, ops.f32(y).reshape(B, C, n, n), w1, b1, ops.f32(w2).reshape(O, O), b2, wh, bh, add,
+                                 heads.reshape(B, heads.shape[1], spec.attn_G, -1).contiguous(),
+                                 pool=(params[10], params[11]) if spec.pool else None, rel_tol=rel_tol)
+
+
 def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None, fcw=None, xp=None):
     """-> grads in ENC_PARAM_NAMES order [+ fc_r.weight, fc_r.bias with rotation pooling] (Conv3d shapes, or reshaped to
     `shapes` = the parameters' own shapes)."""

@@ -27,6 +27,16 @@ class EncBwdArgs(Structure):
                                          "dw2", "db2", "dwh", "dbh", "fc_w", "xp", "dxp16", "dfc_w", "dfc_b")]
 
 
+class RefineArgs(Structure):
+    _fields_ = ([(n, c_void_p) for n in ("y", "weight", "conv1_bias", "w2", "b2", "wh", "bh", "head_add", "fc_w", "fc_b", "heads")]
+                + [("rel_tol", c_float)]
+                + [(n, c_void_p) for n in ("bank32", "cand", "n_cand", "cand_heads", "z_content", "theta_mu", "argmax", "refined_logit")])
+
+
+REFINE_MAX_CAND = 32          # TVAE_REFINE_MAX_CAND
+REFINE_REL_TOL = 2e-3         # candidate band, as a fraction of the attention map's range
+
+
 class AttnShape(Structure):
     _fields_ = [("B", c_int), ("G", c_int), ("d", c_int), ("z", c_int), ("s", c_float),
                 ("theta_prior_std", c_float), ("offsets", c_float * 16)]
@@ -86,7 +96,7 @@ def L():
         lib.tvae_conv1_executed_fraction.argtypes = [c_void_p, c_int]
         for name in ("tvae_filter_bank_fwd", "tvae_filter_bank_bwd", "tvae_encoder_fwd", "tvae_encoder_bwd",
                      "tvae_attn_log_prior", "tvae_attn_fwd", "tvae_attn_bwd", "tvae_attn_softmax_pair",
-                     "tvae_get_latent", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
+                     "tvae_get_latent", "tvae_refine_argmax", "tvae_generator_fwd", "tvae_generator_bwd", "tvae_bernoulli",
                      "tvae_gaussian", "tvae_gaussian_fit_noise"):
             getattr(lib, name).restype = c_int
         lib.tvae_gaussian_fit_noise.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
@@ -311,6 +321,27 @@ def get_latent(s: AttnShape, heads):
     am = torch.empty(s.B, device=dev, dtype=torch.int32)
     check(L().tvae_get_latent(byref(s), ptr(heads), ptr(zc), ptr(th), ptr(dx), ptr(am), stream_ptr()), "tvae_get_latent")
     return zc, th, dx, am
+
+
+def refine_argmax(s: EncShape, y, weight, b1, w2, b2, wh, bh, head_add, heads, pool=None, rel_tol=REFINE_REL_TOL):
+    """Exact re-evaluation of the logit chain at the near-maximal cells of the fast attention map (tvae_refine_argmax).
+    heads: fast maps (B, NH, G2, P).  -> dict(argmax (B) int32, z_content (B,2z), theta_mu (B,1), n_cand (B) int32,
+    cand (B,32) int32, cand_heads (B,32,NH), logit (B))."""
+    dev = heads.device
+    B, NH = heads.shape[0], heads.shape[1]
+    K = s.C * s.k * s.k
+    out = dict(argmax=torch.empty(B, device=dev, dtype=torch.int32), z_content=empty(B, 2 * s.z, device=dev),
+               theta_mu=empty(B, 1, device=dev), n_cand=torch.empty(B, device=dev, dtype=torch.int32),
+               cand=torch.zeros(B, REFINE_MAX_CAND, device=dev, dtype=torch.int32),
+               cand_heads=torch.zeros(B, REFINE_MAX_CAND, NH, device=dev, dtype=torch.float32), logit=empty(B, device=dev))
+    bank32 = empty(s.G * s.O, K, device=dev)
+    a = _set(RefineArgs(), y=f32(y), weight=f32(weight), conv1_bias=f32(b1), w2=f32(w2), b2=f32(b2), wh=wh, bh=bh, head_add=head_add,
+             fc_w=None if pool is None else f32(pool[0]).reshape(-1), fc_b=None if pool is None else f32(pool[1]).reshape(-1),
+             heads=heads, bank32=bank32, cand=out["cand"], n_cand=out["n_cand"], cand_heads=out["cand_heads"],
+             z_content=out["z_content"], theta_mu=out["theta_mu"], argmax=out["argmax"], refined_logit=out["logit"])
+    a.rel_tol = float(rel_tol)
+    check(L().tvae_refine_argmax(byref(s), byref(a), stream_ptr()), "tvae_refine_argmax")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- generator

@@ -1,0 +1,91 @@
+"""Full-size parity against the UNMODIFIED reference run on the same GPU (baseline/_ref; true fp32: cuDNN and matmul TF32
+off) - BASELINE.json's configs at their real image / filter sizes AND the trainer's real minibatch (B = 100), plus a
+B = 2 step of the cfg5 geometry (P16 group conv, z = 8, n = 128).  Identical weights, images and noise
+(ref_runner.SuppliedNoise patches the reference's two RNG draw sites).
+
+For every parameter the relative Frobenius error of the gradient is tabulated NEXT TO what the reference's own default
+GPU math mode (cuDNN TF32 convolutions, fp32 linears - SURVEY.md 2a) scores against the same fp32 run: the product's
+FP16-operand contractions are in TF32's precision class, and a LeakyReLU network's gradient is discontinuous in its
+pre-activations, so both move by the same mechanism (derivative flips of near-zero pre-activations).  The table is
+written to gpurun_out/r02_grad_parity_<cfg>.json (summarised in profiles/r02_grad_parity_table.md).
+
+Tolerances (stated here, derived from that table): ELBO / log p / KL 2e-3 relative; every gradient within GRAD_TOL
+relative Frobenius norm at B = 100, where the reference-TF32 column itself reaches REF_TF32_TYPICAL.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+import ref_runner
+from helpers import rel_err
+from tvae_b200 import synth
+from tvae_b200.config import CFG1, CFG2, CFG3, CFG4, CFG5
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GRAD_TOL = {100: 3e-2, 16: 6e-2, 2: 6e-2}     # per minibatch size: derivative flips average out with more images
+
+
+def _ours(cfg, B, data, noise):
+    from test_gpu_step import build_models
+    from tvae_b200 import elbo as E
+    gen, enc = build_models(cfg)
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    y = torch.from_numpy(data["y"]).to(DEV)
+    nz = {k: v.to(DEV) for k, v in noise.items()}
+    r_inf = "attention+offsets" if cfg.rot_refinement else "attention"
+    if cfg.likelihood == "gaussian":
+        ctf = torch.from_numpy(data["ctf"]).to(DEV) if data["ctf"] is not None else None
+        elbo, logp, kl = E.eval_minibatch_particles(x, y, ctf, gen, enc, "attention", r_inf, 0, DEV, cfg.theta_prior, cfg.G, cfg.p,
+                                                    cfg.mask_radius, noise=nz)
+    else:
+        elbo, logp, kl = E.eval_minibatch(x, y, gen, enc, "attention", r_inf, 0, DEV, cfg.theta_prior, cfg.G, cfg.n, noise=nz)
+    (-elbo).backward()
+    torch.cuda.synchronize()
+    grads = {"enc." + k: p.grad.detach() for k, p in enc.named_parameters()}
+    grads.update({"gen." + k: p.grad.detach() for k, p in gen.named_parameters()})
+    return (float(elbo.detach()), float(logp.detach()), float(kl.detach())), grads
+
+
+@pytest.mark.parametrize("cfg,B", [(CFG1, 100), (CFG2, 100), (CFG3, 16), (CFG4, 100), (CFG5, 2)], ids=lambda v: getattr(v, "name", str(v)))
+def test_step_matches_reference_on_gpu(cfg, B):
+    if not ref_runner.available():
+        pytest.skip("baseline/_ref not installed")
+    data = synth.minibatch(cfg, B, seed=3)
+    noise = {k: torch.from_numpy(v) for k, v in synth.noise(cfg, B, seed=3).items()}
+    (e32, l32, k32), g32 = ref_runner.reference_step(cfg, B, DEV, tf32=False, data=data, noise=noise)
+    g32 = {k: v.double().cpu() for k, v in g32.items()}
+    torch.cuda.empty_cache()
+    (etf, ltf, ktf), gtf = ref_runner.reference_step(cfg, B, DEV, tf32=True, data=data, noise=noise)
+    gtf = {k: v.double().cpu() for k, v in gtf.items()}
+    torch.cuda.empty_cache()
+    (e, l, k), g = _ours(cfg, B, data, noise)
+    table = {}
+    for name, r in g32.items():
+        if name == "enc.conv_a.bias":       # exactly zero in exact arithmetic (softmax shift invariance)
+            assert float(g[name].abs().max()) < 1e-3
+            continue
+        table[name] = {"ours": rel_err(g[name].cpu(), r), "reference_tf32": rel_err(gtf[name], r), "norm": float(r.norm())}
+    rec = {"config": cfg.name, "B": B,
+           "elbo": {"ours": e, "reference_fp32": e32, "reference_tf32": etf},
+           "log_p": {"ours": l, "reference_fp32": l32, "reference_tf32": ltf},
+           "kl": {"ours": k, "reference_fp32": k32, "reference_tf32": ktf},
+           "grad_rel_err": table,
+           "what": "relative Frobenius error of each parameter gradient against the unmodified reference in true fp32 on the same "
+                   "B200: `ours` = this implementation (FP16-operand tcgen05 contractions), `reference_tf32` = the reference in its "
+                   "own default GPU math mode (cuDNN TF32 convolutions, fp32 linears)"}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"r02_grad_parity_{cfg.name.split('_')[0]}_B{B}.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    worst = max(table, key=lambda n: table[n]["ours"])
+    worst_tf = max(table, key=lambda n: table[n]["reference_tf32"])
+    print(f"{cfg.name} B={B}: elbo {e:.4f} / ref fp32 {e32:.4f} / ref tf32 {etf:.4f}; worst gradient rel err ours "
+          f"{table[worst]['ours']:.2e} ({worst}), reference-TF32 {table[worst_tf]['reference_tf32']:.2e} ({worst_tf})")
+    for mine, ref in ((e, e32), (l, l32), (k, k32)):
+        assert abs(mine - ref) < 2e-3 * abs(ref)
+    tol = GRAD_TOL[B]
+    for name, row in table.items():
+        assert row["ours"] < tol, (cfg.name, name, row)

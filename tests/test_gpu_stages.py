@@ -293,3 +293,33 @@ def test_bernoulli_and_gaussian():
                 _, d2, _ = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV),
                                         dx.view(B, 2).float().to(DEV), float(s), radius, gsc, mu=mu_k, use_ctf_gemm=gemm)
                 assert rel_err(d2.cpu(), d.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("n,m", [(16, 9), (16, 31), (16, 41), (20, 39), (64, 127)])
+def test_gaussian_ctf_filter_of_any_odd_size(n, m):
+    """train_particles.py:298-302 applies whatever odd-sized (B,1,m,m) filter it is given with padding m // 2 (with
+    --crop the filters keep the uncropped micrograph's size, :543-547): smaller than, larger than, and (m > 2n - 1) far
+    larger than the image, against F.conv2d in fp64."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n * 1000 + m)
+    B = 3
+    ctf = torch.randn(B, 1, m, m, generator=g, dtype=torch.float64) / m
+    yh = torch.randn(B, n * n, generator=g, dtype=torch.float64).requires_grad_(True)
+    yy = torch.randn(B, n * n, generator=g, dtype=torch.float64)
+    gsc = torch.tensor([-1.0 / B], device=DEV)
+    mu = F.conv2d(yh.view(1, B, n, n), ctf, padding=m // 2, groups=B).view(B, -1)
+    ll_ref = -0.5 * ((mu - yy) ** 2).sum(1)
+    (ll_ref.sum() * (-1.0 / B)).backward()
+    ll, d, mu_k = ops.gaussian(yh.detach().float().to(DEV), yy.float().to(DEV), n, ctf.float().to(DEV), None, 1.0, 0, gsc)
+    torch.cuda.synchronize()
+    e = (rel_err(mu_k.cpu(), mu.detach()), rel_err(ll.cpu(), ll_ref.detach()), rel_err(d.cpu(), yh.grad))
+    assert max(e) < 1e-4, (n, m, e)
+
+
+def test_gaussian_ctf_rejects_bad_filters():
+    ops = _ops()
+    B, n = 2, 16
+    yh = torch.zeros(B, n * n, device=DEV)
+    for shape in ((B, 1, 10, 10), (B + 1, 1, 15, 15), (B, 1, 15, 13)):      # even size, wrong batch, not square
+        with pytest.raises(ValueError):
+            ops.gaussian(yh, yh, n, torch.zeros(*shape, device=DEV))
