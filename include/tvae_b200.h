@@ -286,11 +286,26 @@ int tvae_ctf_filter(const double* params, int B, int n, int m, double scale, flo
 /* src/image.py:30-42 `crop` (centre crop to `crop` x `crop`, 0 = none) followed by train_particles.py:592-600 --normalize
  * (per-image (x - mean) / std with the population std; normalize = 0 copies the crop): in (B, n, m) -> out (B, c, c). */
 int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream);
+/* The same on the image payload of an MRC / MRCS container as stored (src/mrc.py:108-140 `parse`: the array is
+ * np.frombuffer(content[1024 + next:], dtype by header.mode) reshaped (nz, ny, nx)): `in` = DEVICE copy of the payload
+ * bytes of B consecutive images - this rank's shard of the stack -, mode = 0 (int8), 1 (int16), 2 (float32), 6 (uint16);
+ * decoded, cropped and standardised in one pass (values widened to double like numpy does for an integer stack).
+ * The 1024-byte header is parsed on the host (tvae_b200/mrc.py). */
+int tvae_mrc_crop_normalize(const void* in, int mode, int B, int n, int m, int crop, int normalize, float* out, void* stream);
 
 /* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);
 int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream);
+/* A/B switch (process-wide, for measurements and tests): 0 sends the wide layers back to the tc_gemm LinearNT / LinearTN
+ * policies instead of the CTA-pair kernels (linear_nt_pair.cuh, linear_pair_policies.cuh).  Default: both 1. */
+void tvae_test_set_fast_paths(int pair_nt, int pair_tn);
+/* the hidden-layer GEMM with its whole epilogue: C16[M,N] fp16 = store_scale * mask(aux16) * act(acc_scale * A B^T + bias);
+ * colsum[N] += column sums, proj_out[M,n_proj] (pre-zeroed) += value . proj_w^T (+ proj_bias).  Any pointer may be NULL.
+ * use_pair = 1: the CTA-pair kernel takes N >= 256; 0: tc_gemm policies only. */
+int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, const float* bias, int act, void* C16,
+                             const void* aux16, int aux_act, const float* acc_scale, const float* store_scale, float* colsum,
+                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, int use_pair, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ def rotated_filter_bank(weight: torch.Tensor, G: int) -> torch.Tensor:
     assert D == 1 and k == k2
     dt = weight.dtype
     c0 = (k - 1) / 2.0
-    u = torch.arange(k, dtype=dt) - c0
+    u = torch.arange(k, dtype=dt, device=weight.device) - c0
     cy, cx = torch.meshgrid(u, u, indexing="ij")  # cy varies with v (rows)
     w2 = weight[:, :, 0]  # (O,C,k,k)
     banks = []
@@ -75,7 +75,7 @@ def rotated_filter_bank(weight: torch.Tensor, G: int) -> torch.Tensor:
         y0 = torch.floor(iy)
         fx = ix - x0
         fy = iy - y0
-        acc = torch.zeros(O, C, k, k, dtype=dt)
+        acc = torch.zeros(O, C, k, k, dtype=dt, device=weight.device)
         for dy, wy in ((0, 1 - fy), (1, fy)):
             for dx, wx in ((0, 1 - fx), (1, fx)):
                 xi = (x0 + dx).long()

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 #include <mutex>
 #include <set>
@@ -146,7 +147,7 @@ struct KernelTimer {
     int n_created = 0;
     int name_id(const char* nm) {       // caller holds `mu`
         for (int i = 0; i < n_names; ++i)
-            if (names[i] == nm) return i;
+            if (names[i] == nm || strcmp(names[i], nm) == 0) return i;
         if (n_names >= kMaxNames) return -1;
         names[n_names] = nm;
         return n_names++;

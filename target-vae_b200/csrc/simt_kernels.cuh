@@ -154,80 +154,6 @@ __device__ __forceinline__ void grid_xy(int t, int d, float s, float& gx, float&
     gy = (d - 1 - i - d / 2) * s;
 }
 
-template <int Z>
-__global__ void __launch_bounds__(1024) attn_fwd_kernel(AttnParams p) {
-    __shared__ float scratch[32 * (6 + 4 * Z)];
-    const int b = blockIdx.x;
-    const int P = p.d * p.d, L = p.G * P, NH = 3 + 2 * Z;
-    const float* hb = p.heads + (long long)b * NH * L;
-    const float* gb = p.gumbel + (long long)b * L;
-
-    // pass 1: maxima
-    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-        const float a = hb[l];
-        mx[0] = fmaxf(mx[0], a);
-        mx[1] = fmaxf(mx[1], a + gb[l]);
-    }
-    block_reduce<2, true>(mx, scratch);
-    float se[2] = {0.f, 0.f};
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-        const float a = hb[l];
-        se[0] += __expf(a - mx[0]);
-        se[1] += __expf(a + gb[l] - mx[1]);
-    }
-    block_reduce<2, false>(se, scratch);
-    const float lse_q = mx[0] + logf(se[0]);
-    const float lse_a = mx[1] + logf(se[1]);
-
-    // pass 2: expectations under a (Gumbel-softmax sample) and KL sums under pi = exp(q)
-    float acc[6 + 4 * Z];
-#pragma unroll
-    for (int i = 0; i < 6 + 4 * Z; ++i) acc[i] = 0.f;
-    const float inv2s2 = 1.f / (2.f * p.theta_prior_std * p.theta_prior_std);
-    const float log_sp = logf(p.theta_prior_std);
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-        const int r = l / P, t = l - r * P;
-        const float logit = hb[l];
-        const float q = logit - lse_q;
-        const float pi = expf(q);
-        const float a = expf(logit + gb[l] - lse_a);
-        float gx, gy;
-        grid_xy(t, p.d, p.s, gx, gy);
-        acc[0] += a * gx;
-        acc[1] += a * gy;
-        const bool dead = (pi == 0.f);  // train_mnist.py:246-254 guards
-        const float th_mu = hb[L + l], th_std = expf(hb[2 * L + l]) + kEpsStd;
-        acc[2] += a * th_mu;
-        acc[3] += a * th_std;
-        float f = q - p.log_prior[l];
-        if (!dead) {
-            const float dm = th_mu - p.offsets[r];
-            f += log_sp - logf(th_std) + (th_std * th_std + dm * dm) * inv2s2 - 0.5f;
-        }
-#pragma unroll
-        for (int k = 0; k < Z; ++k) {
-            const float zm = hb[(3 + k) * L + l], zs = expf(hb[(3 + Z + k) * L + l]) + kEpsStd;
-            acc[6 + k] += a * zm;
-            acc[6 + Z + k] += a * zs;
-            if (!dead) f += -logf(zs) + 0.5f * (zs * zs + zm * zm) - 0.5f;
-        }
-        acc[4] += pi * f;
-    }
-    block_reduce<6 + 4 * Z, false>(acc, scratch);
-    if (threadIdx.x == 0) {
-        p.stats[b * 4 + 0] = mx[0];
-        p.stats[b * 4 + 1] = lse_q;
-        p.stats[b * 4 + 2] = mx[1];
-        p.stats[b * 4 + 3] = lse_a;
-        p.dx[b * 2 + 0] = acc[0];
-        p.dx[b * 2 + 1] = acc[1];
-        p.theta_b[b] = acc[3] * p.r_theta[b] + acc[2];
-        p.kl[b] = acc[4];
-        for (int k = 0; k < Z; ++k) p.zb[b * Z + k] = acc[6 + Z + k] * p.r_z[b * Z + k] + acc[6 + k];
-    }
-}
-
 struct AttnBwdParams {
     const float* heads; const float* gumbel; const float* r_z; const float* r_theta; const float* log_prior;
     const float* stats; const float* zb; const float* theta_b; const float* dx; const float* kl;
@@ -240,67 +166,6 @@ struct AttnBwdParams {
     float s, theta_prior_std;
     float offsets[kMaxG];
 };
-
-// elementwise over (b, l): one read of the maps, one write of their gradients.
-template <int Z>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdParams p) {
-    const int P = p.d * p.d, L = p.G * P, NH = 3 + 2 * Z;
-    const int b = blockIdx.y;
-    const float* hb = p.heads + (long long)b * NH * L;
-    const float* gb = p.gumbel + (long long)b * L;
-    float* db = p.d_heads + (long long)b * NH * L;
-    const float lse_q = p.stats[b * 4 + 1], lse_a = p.stats[b * 4 + 3];
-    const float K = p.kl[b];
-    const float g_kl = __ldg(p.g_kl);
-    const float g_th = p.g_theta[b], r_th = p.r_theta[b];
-    const float gdx = p.g_dx[b * 2], gdy = p.g_dx[b * 2 + 1];
-    float gz[Z], rz[Z];
-    float s_ac = g_th * p.theta_b[b] + gdx * p.dx[b * 2] + gdy * p.dx[b * 2 + 1];
-#pragma unroll
-    for (int k = 0; k < Z; ++k) {
-        gz[k] = p.g_zb[b * Z + k];
-        rz[k] = p.r_z[b * Z + k];
-        s_ac += gz[k] * p.zb[b * Z + k];
-    }
-    const float inv_s2 = 1.f / (p.theta_prior_std * p.theta_prior_std);
-    const float log_sp = logf(p.theta_prior_std);
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
-        const int r = l / P, t = l - r * P;
-        const float logit = hb[l];
-        const float q = logit - lse_q;
-        const float pi = expf(q);
-        const float a = expf(logit + gb[l] - lse_a);
-        const bool dead = (pi == 0.f);
-        float gx, gy;
-        grid_xy(t, p.d, p.s, gx, gy);
-        const float th_mu = hb[L + l], e_th = expf(hb[2 * L + l]), th_std = e_th + kEpsStd;
-        float c = g_th * (th_std * r_th + th_mu) + gdx * gx + gdy * gy;
-        float f = q - p.log_prior[l];
-        float d_thmu = g_th * a, d_thls = g_th * r_th * a * e_th;
-        if (!dead) {
-            const float dm = th_mu - p.offsets[r];
-            f += log_sp - logf(th_std) + 0.5f * (th_std * th_std + dm * dm) * inv_s2 - 0.5f;
-            d_thmu += g_kl * pi * dm * inv_s2;
-            d_thls += g_kl * pi * (-1.f / th_std + th_std * inv_s2) * e_th;
-        }
-#pragma unroll
-        for (int k = 0; k < Z; ++k) {
-            const float zm = hb[(3 + k) * L + l], e_z = expf(hb[(3 + Z + k) * L + l]), zs = e_z + kEpsStd;
-            c += gz[k] * (zs * rz[k] + zm);
-            float d_zm = gz[k] * a, d_zl = gz[k] * rz[k] * a * e_z;
-            if (!dead) {
-                f += -logf(zs) + 0.5f * (zs * zs + zm * zm) - 0.5f;
-                d_zm += g_kl * pi * zm;
-                d_zl += g_kl * pi * (-1.f / zs + zs) * e_z;
-            }
-            db[(3 + k) * L + l] = d_zm;
-            db[(3 + Z + k) * L + l] = d_zl;
-        }
-        db[L + l] = d_thmu;
-        db[2 * L + l] = d_thls;
-        db[l] = a * (c - s_ac) + g_kl * pi * (f - K);
-    }
-}
 
 // log_prior[l] = log_softmax_{(r,t)}( sum_xy N(grid; 0, 0.1).log_prob + p_r[r] )   (one small CTA)
 __global__ void log_prior_kernel(float* __restrict__ out, int G, int d, float s, RotTable p_r_in_cs) {
@@ -1324,17 +1189,20 @@ __global__ void __launch_bounds__(256) ctf_filter_kernel(CtfFilterParams p) {
 }
 
 // centre crop + per-image standardisation (src/image.py:30-42, train_particles.py:592-600); one CTA per image, fp64 sums
-__global__ void __launch_bounds__(256) crop_normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int m, int c0,
+// T = element type of the stack as stored: float (arrays / MRC mode 2) or the integer types of MRC modes 0, 1, 6
+// (src/mrc.py:118-131); every value is widened to double first, like numpy's mean / std over an integer array.
+template <typename T>
+__global__ void __launch_bounds__(256) crop_normalize_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int m, int c0,
                                                              int c1, int si, int sj, int normalize) {
     __shared__ double s_red[2][8];
     __shared__ double s_stat[2];
     const int b = blockIdx.x, total = c0 * c1;
-    const float* src = in + (long long)b * n * m;
+    const T* src = in + (long long)b * n * m;
     double sum = 0.0, sq = 0.0;
     if (normalize) {
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int r = i / c1, cc = i - r * c1;
-            const double v = src[(si + r) * m + sj + cc];
+            const double v = static_cast<double>(src[(si + r) * m + sj + cc]);
             sum += v; sq += v * v;
         }
         for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
@@ -1354,7 +1222,7 @@ __global__ void __launch_bounds__(256) crop_normalize_kernel(const float* __rest
     const double mu = normalize ? s_stat[0] : 0.0, sd = normalize ? s_stat[1] : 1.0;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int r = i / c1, cc = i - r * c1;
-        const double v = src[(si + r) * m + sj + cc];
+        const double v = static_cast<double>(src[(si + r) * m + sj + cc]);
         out[(long long)b * total + i] = static_cast<float>((v - mu) / sd);
     }
 }

@@ -10,6 +10,7 @@
 #include "launch.cuh"
 #include "simt_gen.cuh"
 #include "simt_kernels.cuh"
+#include "attn_kernels.cuh"
 #include "enc_bwd_fused.cuh"
 #include "refine.cuh"
 
@@ -610,12 +611,49 @@ int tvae_attn_log_prior(const tvae_attn_shape* s, const float* p_r_host16, float
         default: return fail(-1, "latent dim not instantiated (supported: 1-6, 8, 10, 16)"); \
     }
 
+}  // extern "C"
+
+namespace {
+// cluster size of the attention forward: the smallest power of two (<= 8, the portable maximum) that gives every SM
+// about six CTAs of 256 threads (two resident rounds), never so large that a CTA's slice falls below two sweeps of its threads
+int attn_cluster_size(int B, int L) {
+    int cl = 1;
+    while (cl < 8 && B * cl < 6 * sm_count() && L / (2 * cl) >= kAttnThreads * 4) cl *= 2;
+    return cl;
+}
+template <int Z, int VEC>
+int launch_attn_fwd(const AttnParams& p, int B, int L, cudaStream_t st) {
+    const int cl = attn_cluster_size(B, L);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * cl, 1, 1);
+    cfg.blockDim = dim3(kAttnThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<Z, VEC>, p));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int tvae_attn_fwd(const tvae_attn_shape* s, const tvae_attn_fwd_args* a, void* stream) {
     TVAE_REQUIRE(s->G >= 1 && s->G <= kMaxG && s->d >= 1 && s->B >= 1, "attention: bad shape");
     const AttnParams p = to_attn_params(s, a);
+    const int L = s->G * s->d * s->d;
+    // 16-byte accesses need whole float4 planes (every plane starts at a multiple of L floats)
+    const bool vec = L % 4 == 0 && (reinterpret_cast<uintptr_t>(a->heads) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->gumbel) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->log_prior) & 15) == 0;
     Timed tm("attn_fwd", S(stream));
     ++g_launch_count;
-    TVAE_DISPATCH_Z(s->z, (attn_fwd_kernel<ZZ><<<s->B, 1024, 0, S(stream)>>>(p)));
+    int rc = 0;
+    if (vec) { TVAE_DISPATCH_Z(s->z, (rc = launch_attn_fwd<ZZ, 4>(p, s->B, L, S(stream)))); }
+    else { TVAE_DISPATCH_Z(s->z, (rc = launch_attn_fwd<ZZ, 1>(p, s->B, L, S(stream)))); }
+    if (rc) return rc;
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -629,10 +667,18 @@ int tvae_attn_bwd(const tvae_attn_shape* s, const tvae_attn_bwd_args* a, void* s
     p.B = s->B; p.G = s->G; p.d = s->d; p.z = s->z; p.s = s->s; p.theta_prior_std = s->theta_prior_std;
     for (int i = 0; i < kMaxG; ++i) p.offsets[i] = s->offsets[i];
     const int L = s->G * s->d * s->d;
-    dim3 grid(blocks_for(L, 256, 64), s->B);
+    const bool vec = L % 4 == 0 && (reinterpret_cast<uintptr_t>(a->f.heads) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->f.gumbel) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->f.log_prior) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->d_heads) & 15) == 0;
+    // enough CTAs of 256 threads to give every SM ~8 of them, one vector per thread and sweep
+    const int per_image = cdiv(L, 256 * (vec ? 4 : 1));
+    int gx = cdiv(8LL * sm_count(), s->B);
+    if (gx > per_image) gx = per_image;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, s->B);
     Timed tm("attn_bwd", S(stream));
     ++g_launch_count;
-    TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ><<<grid, 256, 0, S(stream)>>>(p)));
+    if (vec) { TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ, 4><<<grid, 256, 0, S(stream)>>>(p))); }
+    else { TVAE_DISPATCH_Z(s->z, (attn_bwd_kernel<ZZ, 1><<<grid, 256, 0, S(stream)>>>(p))); }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1108,15 +1154,27 @@ int tvae_ctf_filter(const double* params, int B, int n, int m, double scale, flo
     return 0;
 }
 
-int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream) {
+int tvae_mrc_crop_normalize(const void* in, int mode, int B, int n, int m, int crop, int normalize, float* out, void* stream) {
     TVAE_REQUIRE(B >= 0 && n >= 1 && m >= 1 && crop >= 0 && crop <= n && crop <= m, "crop_normalize: crop larger than the image");
+    TVAE_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 6, "crop_normalize: MRC mode must be 0 (int8), 1 (int16), 2 (float32) or 6 (uint16)");
     if (B == 0) return 0;
     TVAE_REQUIRE(in && out, "crop_normalize: null pointer");
     const int c0 = crop > 0 ? crop : n, c1 = crop > 0 ? crop : m;
     const int si = crop > 0 ? (n - crop) / 2 : 0, sj = crop > 0 ? (m - crop) / 2 : 0;
-    ++g_launch_count; crop_normalize_kernel<<<B, 256, 0, S(stream)>>>(in, out, n, m, c0, c1, si, sj, normalize);
+    cudaStream_t st = S(stream);
+    ++g_launch_count;
+    switch (mode) {
+        case 0: crop_normalize_kernel<signed char><<<B, 256, 0, st>>>(static_cast<const signed char*>(in), out, n, m, c0, c1, si, sj, normalize); break;
+        case 1: crop_normalize_kernel<short><<<B, 256, 0, st>>>(static_cast<const short*>(in), out, n, m, c0, c1, si, sj, normalize); break;
+        case 6: crop_normalize_kernel<unsigned short><<<B, 256, 0, st>>>(static_cast<const unsigned short*>(in), out, n, m, c0, c1, si, sj, normalize); break;
+        default: crop_normalize_kernel<float><<<B, 256, 0, st>>>(static_cast<const float*>(in), out, n, m, c0, c1, si, sj, normalize); break;
+    }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream) {
+    return tvae_mrc_crop_normalize(in, 2, B, n, m, crop, normalize, out, stream);
 }
 
 // ================================================================================ test hooks
@@ -1125,6 +1183,30 @@ int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, in
     LinearNTArgs a{};
     a.A = A; a.lda = K; a.B = B; a.ldb = K; a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = N; a.bias = bias; a.act = act;
     return linear_nt(a, S(stream));
+}
+
+// full epilogue of the hidden-layer GEMM: fp16 output (x *store_scale), bias, activation, derivative mask from aux16,
+// accumulator scale, column sums, fused projection.  use_pair = 0 forces the tc_gemm LinearNT policies, 1 lets the
+// CTA-pair kernel (linear_nt_pair.cuh) take the shapes it covers.
+int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, const float* bias, int act, void* C16,
+                             const void* aux16, int aux_act, const float* acc_scale, const float* store_scale, float* colsum,
+                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, int use_pair, void* stream) {
+    LinearNTArgs a{};
+    a.A = A; a.lda = K; a.B = B; a.ldb = K; a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act;
+    a.C16 = C16; a.ldc16 = N; a.aux16 = aux16; a.ld_aux = N; a.aux_act = aux_act;
+    a.acc_scale = acc_scale; a.store_scale = store_scale; a.colsum = colsum; a.colsum_stride = 1;
+    a.proj_w = proj_w; a.proj_bias = proj_bias; a.proj_out = proj_out; a.n_proj = n_proj;
+    const bool saved = g_linear_nt_pair_enabled;
+    g_linear_nt_pair_enabled = use_pair != 0;
+    const int rc = linear_nt(a, S(stream));
+    g_linear_nt_pair_enabled = saved;
+    return rc;
+}
+
+// A/B switch for the two wide-layer kernels (default: both on): the CTA-pair LinearNT and the CTA-pair LinearTN
+void tvae_test_set_fast_paths(int pair_nt, int pair_tn) {
+    g_linear_nt_pair_enabled = pair_nt != 0;
+    g_linear_pair_enabled = pair_tn != 0;
 }
 
 int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
