@@ -31,8 +31,10 @@ def shard(t: Optional[torch.Tensor], rank: int, world: int):
 
 
 class GradSync:
-    """Two-bucket gradient averaging.  start(i, grads) flattens bucket i and launches an async all-reduce;
-    finish() waits (stream-side on CUDA) and returns the averaged gradients with the original shapes."""
+    """Two-bucket gradient averaging, in place.  The backward kernels write each bucket's parameter gradients straight into
+    ONE flat fp32 buffer (ops.flat_views); start(i, flat) launches an async all-reduce on that buffer - no flatten copy -
+    and finish() makes the current stream wait for both (a stream-side wait, the host never blocks).  The per-parameter
+    gradients handed to autograd are views of the buckets, so they hold the averaged values afterwards."""
 
     def __init__(self, group=None):
         self.group = group
@@ -41,28 +43,20 @@ class GradSync:
         # NCCL averages inside the collective (no separate scaling kernel); gloo (CPU tests) only sums
         self._avg = dist.is_initialized() and self.world > 1 and dist.get_backend(group) == "nccl"
 
-    def start(self, bucket: int, grads: Sequence[torch.Tensor]):
-        flat = torch.cat([g.reshape(-1) for g in grads])
+    def start(self, bucket: int, flat: torch.Tensor):
         work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._pending[bucket] = (flat, work, [g.shape for g in grads])
+        self._pending[bucket] = (flat, work)
 
     def _resolve(self, bucket: int):
-        flat, work, shapes = self._pending[bucket]
+        flat, work = self._pending[bucket]
         if work is not None:
             work.wait()
             if not self._avg:
                 flat.mul_(1.0 / self.world)
-        out, off = [], 0
-        for sh in shapes:
-            n = 1
-            for d in sh:
-                n *= d
-            out.append(flat[off:off + n].view(sh))
-            off += n
         self._pending[bucket] = None
-        return out
+        return flat
 
     def finish(self):
         return self._resolve(0), self._resolve(1)

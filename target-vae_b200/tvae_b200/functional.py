@@ -20,6 +20,19 @@ import torch
 from . import ops
 
 
+class nvtx_range:
+    """NVTX range around one subsystem of the step (visible in nsys / ncu --nvtx; a no-op without a profiler attached)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+
+
 def on_tensor_device(fn):
     """The library launches on the CURRENT CUDA device (stream, SM count, shared-memory opt-in): run `fn` with the
     device of its first CUDA tensor argument current, so a model on cuda:1 works while cuda:0 is current.  (Backward
@@ -156,23 +169,23 @@ def refine_argmax(spec: EncoderSpec, y, heads, *params, rel_tol=ops.REFINE_REL_T
 
 
 def _encoder_backward(s, spec: EncoderSpec, yc, w2m, wh, x1, h, d_heads, shapes=None, fcw=None, xp=None):
-    """-> grads in ENC_PARAM_NAMES order [+ fc_r.weight, fc_r.bias with rotation pooling] (Conv3d shapes, or reshaped to
-    `shapes` = the parameters' own shapes)."""
-    fc_grads = []
-    if spec.pool:
-        dbank, dw2, db2, dwh, dbh, dfc_w, dfc_b = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads, (fcw, xp))
-        fc_grads = [dfc_w.reshape(1, -1), dfc_b]
-    else:
-        dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads)
-    dw1, db1 = ops.filter_bank_bwd(s, dbank)
-    O, z = s.O, spec.z
+    """-> (grads, flat): grads in ENC_PARAM_NAMES order [+ fc_r.weight, fc_r.bias with rotation pooling] (Conv3d shapes, or
+    reshaped to `shapes` = the parameters' own shapes), all of them views of ONE flat bucket `flat` the kernels wrote
+    into (the data-parallel all-reduce runs on it in place)."""
+    O, z, NH, dev = s.O, spec.z, 3 + 2 * spec.z, yc.device
+    bucket = [(O, s.C, 1, s.k, s.k), (O,), (O, O), (O,), (NH, O), (NH,)] + ([(s.G,), (1,)] if spec.pool else [])
+    flat, v = ops.flat_views(bucket, dev)
+    res = ops.encoder_bwd(s, yc, w2m, wh, x1, h, d_heads, (fcw, xp) if spec.pool else None, out=v[2:])
+    dbank = res[0]
+    ops.filter_bank_bwd(s, dbank, out=(v[0], v[1]))
+    dw1, db1, dw2, db2, dwh, dbh = v[:6]
     sh = (O, 1, 1, 1)
     grads = [dw1, db1, dw2.view(O, O, 1, 1, 1), db2,
              dwh[0:1].reshape(1, *sh), dbh[0:1], dwh[1:3].reshape(2, *sh), dbh[1:3],
-             dwh[3:].reshape(2 * z, *sh), dbh[3:]] + fc_grads
+             dwh[3:].reshape(2 * z, *sh), dbh[3:]] + ([v[6].reshape(1, -1), v[7]] if spec.pool else [])
     if shapes is not None:
         grads = [g.reshape(sh_) for g, sh_ in zip(grads, shapes)]
-    return grads
+    return grads, flat
 
 
 class EncoderHeadsFn(torch.autograd.Function):
@@ -191,7 +204,7 @@ class EncoderHeadsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         yc, w2m, wh, x1, h, *pool = ctx.saved_tensors
-        grads = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous(), ctx.shapes, *pool)
+        grads, _ = _encoder_backward(ctx.s, ctx.spec, yc, w2m, wh, x1, h, g.contiguous(), ctx.shapes, *pool)
         return (None, None, *grads)
 
 
@@ -309,7 +322,8 @@ class FusedStepFn(torch.autograd.Function):
     def forward(ctx, spec: StepSpec, x_coord, y, ctf, gumbel, r_z, r_theta, fourier_w, fourier_b, *params):
         es = spec.enc
         enc_params, gen_params = params[:es.n_params], params[es.n_params:]
-        s, yc, w2m, wh, x1, h, heads, xp = _encoder_forward(es, y, *enc_params)
+        with nvtx_range("tvae.encoder_fwd"):
+            s, yc, w2m, wh, x1, h, heads, xp = _encoder_forward(es, y, *enc_params)
         B, n = s.B, s.n
         d = s.n + 2 * s.p - s.k + 1
         xc = ops.f32(x_coord)
@@ -318,14 +332,16 @@ class FusedStepFn(torch.autograd.Function):
         ashape = ops.attn_shape(B, es.attn_G, d, es.z, spacing, offs, es.theta_prior_std)
         log_prior = ops.attn_log_prior(ashape, p_r, y.device)
         gum, rz, rth = ops.f32(gumbel), ops.f32(r_z).reshape(B, es.z), ops.f32(r_theta).reshape(B)
-        att = ops.attn_fwd(ashape, heads, gum, rz, rth, log_prior)
+        with nvtx_range("tvae.attention_fwd"):
+            att = ops.attn_fwd(ashape, heads, gum, rz, rth, log_prior)
 
         w1, b1, wz = gen_params[:3]
         hidden, (wout, bout) = gen_params[3:-2], gen_params[-2:]
         gw = _gen_weights(fourier_w, fourier_b, spec.sigma, w1, b1, wz, hidden, wout, bout, spec.gen_resid)
         N = xc.shape[0]
         gs = ops.gen_shape(B, N, gw, es.z, spec.gen_act)
-        y_hat, gsaved = ops.generator_fwd(gs, gw, xc, att["theta_b"], att["dx"], att["zb"])
+        with nvtx_range("tvae.generator_fwd"):
+            y_hat, gsaved = ops.generator_fwd(gs, gw, xc, att["theta_b"], att["dx"], att["zb"])
 
         yflat = yc.reshape(B, -1)
         ctfc = None if ctf is None else ops.f32(ctf)
@@ -369,15 +385,18 @@ class FusedStepFn(torch.autograd.Function):
             _, d_yhat, _ = ops.gaussian(y_hat, yflat, s.n, ctfc if ctx.has_ctf else None, att["dx"], ctx.spacing,
                                         spec.mask_radius, w_ll, mu=ctx.mu)
             ctx.mu = None
-        gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
+        with nvtx_range("tvae.generator_bwd"):
+            gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
         gen_grads = _gen_param_grads(gout, gs.L)
         if spec.sync is not None:
-            spec.sync.start(0, gen_grads)
-        d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
-        enc_grads = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes, *pool)
+            spec.sync.start(0, gout["flat"])
+        with nvtx_range("tvae.attention_bwd"):
+            d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
+        with nvtx_range("tvae.encoder_bwd"):
+            enc_grads, enc_flat = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes, *pool)
         if spec.sync is not None:
-            spec.sync.start(1, enc_grads)
-            gen_grads, enc_grads = spec.sync.finish()
+            spec.sync.start(1, enc_flat)
+            spec.sync.finish()            # gen_grads / enc_grads are views of the two buckets: averaged in place
         ctx.gsaved = None
         ctx.att = None
         return (None,) * 9 + tuple(enc_grads) + tuple(gen_grads)

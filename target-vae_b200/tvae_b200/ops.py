@@ -124,6 +124,19 @@ def half(*shape, device):
     return torch.empty(*shape, device=device, dtype=torch.float16)
 
 
+def flat_views(shapes, device):
+    """One flat fp32 buffer holding a tensor per shape (each starting on a 16-byte boundary) -> (flat, [views]).
+    The backward kernels write the parameter gradients straight into such a bucket through the C ABI's output pointers,
+    so that the data-parallel all-reduce (tvae_b200.dp.GradSync) runs on it in place - no flatten / concatenate copy."""
+    sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 3) // 4 * 4
+    flat = torch.empty(max(total, 4), device=device, dtype=torch.float32)
+    return flat, [flat[o:o + n].view(sh) for o, n, sh in zip(offs, sizes, shapes)]
+
+
 # ----------------------------------------------------------------------------------------------- encoder
 ACT_LEAKYRELU, ACT_TANH = 0, 1      # TVAE_ACT_* of include/tvae_b200.h
 
@@ -148,9 +161,9 @@ def filter_bank_fwd(s: EncShape, weight: torch.Tensor) -> torch.Tensor:
     return bank
 
 
-def filter_bank_bwd(s: EncShape, dbank: torch.Tensor):
-    dw = empty(s.O, s.C, 1, s.k, s.k, device=dbank.device)
-    db = empty(s.O, device=dbank.device)
+def filter_bank_bwd(s: EncShape, dbank: torch.Tensor, out=None):
+    """out = (dweight (O,C,1,k,k), dbias (O)) views to write into (a gradient bucket), or None to allocate."""
+    dw, db = out if out is not None else (empty(s.O, s.C, 1, s.k, s.k, device=dbank.device), empty(s.O, device=dbank.device))
     check(L().tvae_filter_bank_bwd(byref(s), ptr(dbank), ptr(dw), ptr(db), stream_ptr()), "tvae_filter_bank_bwd")
     return dw, db
 
@@ -223,8 +236,9 @@ def encoder_fwd(s: EncShape, y, bank, b1, w2, b2, wh, bh, head_add, keep_h=True,
     return x1, h, heads, xp
 
 
-def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads, pool=None):
-    """pool = (fc_r.weight, xp) with rotation pooling: additionally returns (dfc_w (G), dfc_b (1))."""
+def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads, pool=None, out=None):
+    """pool = (fc_r.weight, xp) with rotation pooling: additionally returns (dfc_w (G), dfc_b (1)).
+    out = (dw2 (O,O), db2 (O), dwh (NH,O), dbh (NH) [, dfc_w (G), dfc_b (1)]) views to write into, or None to allocate."""
     dev = y.device
     NH = 3 + 2 * s.z
     R = x1.shape[0]
@@ -232,10 +246,10 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads, pool=None):
     w2t = half(s.O, s.O, device=dev)
     scales = empty(8, device=dev)
     dbank = empty(s.G * s.O, s.kpad, device=dev)
-    dw2 = empty(s.O, s.O, device=dev)
-    db2 = empty(s.O, device=dev)
-    dwh = empty(NH, s.O, device=dev)
-    dbh = empty(NH, device=dev)
+    if out is not None:
+        dw2, db2, dwh, dbh = out[:4]
+    else:
+        dw2, db2, dwh, dbh = empty(s.O, s.O, device=dev), empty(s.O, device=dev), empty(NH, s.O, device=dev), empty(NH, device=dev)
     dx1_16 = half(R, s.O, device=dev)
     a = _set(EncBwdArgs(), y=f32(y), w2=f32(w2), wh=wh, x1=x1, h=h, d_heads=f32(d_heads), dhpre=dhpre, dx1_16=dx1_16, w2t_h=w2t,
              scales=scales,
@@ -243,7 +257,7 @@ def encoder_bwd(s: EncShape, y, w2, wh, x1, h, d_heads, pool=None):
     dfc_w = dfc_b = None
     if pool is not None:
         fc_w, xp = pool
-        dfc_w, dfc_b = empty(s.G, device=dev), empty(1, device=dev)
+        dfc_w, dfc_b = out[4:6] if out is not None else (empty(s.G, device=dev), empty(1, device=dev))
         _set(a, fc_w=f32(fc_w).reshape(-1), xp=xp, dxp16=half(xp.shape[0], s.O, device=dev), dfc_w=dfc_w, dfc_b=dfc_b)
     check(L().tvae_encoder_bwd(byref(s), byref(a), stream_ptr()), "tvae_encoder_bwd")
     if pool is not None:
@@ -386,15 +400,16 @@ def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_
     dev = z.device
     M = s.B * s.N
     H, E, Lh = s.H, s.E, s.L
-    out = dict(dw1=empty(H, max(E, 2), device=dev), db1=empty(H, device=dev), dwz=empty(H, s.zdim, device=dev),
-               dwh=empty(max(Lh, 1), H, H, device=dev), dbh=empty(max(Lh, 1), H, device=dev),
-               dwout=empty(s.n_out, H, device=dev), dbout=empty(s.n_out, device=dev),
-               d_theta=empty(s.B, device=dev), d_dx=empty(s.B, 2, device=dev), d_z=empty(s.B, s.zdim, device=dev))
+    # every parameter gradient lives in ONE flat bucket (out["flat"]): the data-parallel all-reduce runs on it in place
+    names = ("dw1", "db1", "dwz", "dwh", "dbh", "dwout", "dbout")
+    flat, views = flat_views([(H, max(E, 2)), (H,), (H, s.zdim), (max(Lh, 1), H, H), (max(Lh, 1), H), (s.n_out, H), (s.n_out,)], dev)
+    out = dict(zip(names, views))
+    out.update(flat=flat, d_theta=empty(s.B, device=dev), d_dx=empty(s.B, 2, device=dev), d_z=empty(s.B, s.zdim, device=dev))
     scratch = dict(dpre0=half(M, H, device=dev), dpre1=half(M, H, device=dev), wt_h=half(max(E * H, H * H), device=dev),
                    scales=empty(32, device=dev), dxp=empty(M, 2, device=dev), dzb=empty(s.B, H, device=dev))
     a = GenBwdArgs()
     a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_h"])
-    _set(a, d_yhat=f32(d_yhat), **scratch, **out)
+    _set(a, d_yhat=f32(d_yhat), **scratch, **{k: v for k, v in out.items() if k != "flat"})
     if theta is None:
         a.d_theta = None
         a.d_dx = None

@@ -38,11 +38,19 @@ def _worker(rank, world, port, q):
         assert xs.shape[0] == B // world
         loss = ((xs @ w_gen).tanh() @ w_enc).pow(2).mean()
         g_gen, g_enc = torch.autograd.grad(loss, [w_gen, w_enc])
+        # the backward kernels write each bucket's gradients into one flat buffer; the per-parameter gradients are views
+        from tvae_b200 import ops
+        flat0, (a_gen, a_gen0) = ops.flat_views([tuple(g_gen.shape), tuple(g_gen[0].shape)], "cpu")   # two shapes in one bucket
+        flat1, (a_enc,) = ops.flat_views([tuple(g_enc.shape)], "cpu")
+        flat0, flat1 = flat0.double(), flat1.double()
+        a_gen, a_gen0, a_enc = flat0[:g_gen.numel()].view_as(g_gen), flat0[16:16 + g_gen[0].numel()].view_as(g_gen[0]), flat1[:3]
+        a_gen.copy_(g_gen); a_gen0.copy_(g_gen[0]); a_enc.copy_(g_enc)
         sync = dp.GradSync()
-        sync.start(0, [g_gen, g_gen[0]])      # bucket with two tensors of different shapes
-        sync.start(1, [g_enc])
-        (a_gen, a_gen0), (a_enc,) = sync.finish()
-        ok = (torch.allclose(a_gen, g_full[0], atol=1e-12) and torch.allclose(a_enc, g_full[1], atol=1e-12)
+        sync.start(0, flat0)
+        sync.start(1, flat1)
+        r0, r1 = sync.finish()
+        ok = (r0 is flat0 and r1 is flat1                                     # averaged IN PLACE: the views see it
+              and torch.allclose(a_gen, g_full[0], atol=1e-12) and torch.allclose(a_enc, g_full[1], atol=1e-12)
               and torch.allclose(a_gen0, g_full[0][0], atol=1e-12) and a_gen.shape == g_gen.shape)
         sc = dp.all_reduce_scalars(torch.tensor([float(rank)], dtype=torch.float64))
         ok = ok and abs(float(sc) - (world - 1) / 2) < 1e-12
@@ -69,9 +77,12 @@ def test_shard_bounds():
     assert dp.shard_bounds(100, 3, 4) == (75, 100)
     with pytest.raises(ValueError):
         dp.shard_bounds(10, 0, 4)
-    sync = dp.GradSync()                       # single process: identity
-    g = [torch.arange(6.0).view(2, 3), torch.ones(4)]
-    sync.start(0, g)
-    sync.start(1, [torch.zeros(2)])
-    a, b = sync.finish()
-    assert torch.equal(a[0], g[0]) and torch.equal(a[1], g[1]) and b[0].shape == (2,)
+    sync = dp.GradSync()                       # single process: identity, in place
+    from tvae_b200 import ops
+    flat, (a, b) = ops.flat_views([(2, 3), (5,)], "cpu")
+    assert flat.numel() == 8 + 8 and a.data_ptr() == flat.data_ptr() and b.data_ptr() == flat.data_ptr() + 8 * 4   # 16-byte aligned views
+    a.copy_(torch.arange(6.0).view(2, 3)); b.fill_(1.0)
+    sync.start(0, flat)
+    sync.start(1, torch.zeros(4))
+    f0, f1 = sync.finish()
+    assert f0 is flat and torch.equal(a, torch.arange(6.0).view(2, 3)) and torch.equal(b, torch.ones(5)) and f1.shape == (4,)
