@@ -9,7 +9,8 @@
 //   sweep 1  online max / sum-exp of the two softmaxes (logits, logits + Gumbel)        -> per-CTA partials in shared memory
 //            cluster barrier; every CTA combines the partials of all ranks through distributed shared memory
 //   sweep 2  expectations under the Gumbel-softmax sample and the KL sums under q        -> per-CTA partials, cluster barrier,
-//            rank 0 combines them in rank order (bit-deterministic) and writes the per-image outputs
+//            rank 0 combines them in rank order (bit-deterministic) and writes the per-image outputs; a last cluster
+//            barrier keeps every CTA's shared memory alive until rank 0 has read it
 // The slice's logits / noise are read twice; the second read hits L1/L2 (a slice is a few tens of KB).
 // Backward: elementwise over (image, cell) with 16-byte loads and stores.
 // Per-cell exponentials / logarithms use the MUFU approximations (__expf / __logf, ~2 ulp): with 3 + 2z of each per cell the
@@ -52,7 +53,8 @@ template <int Z, int VEC>
 __global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(AttnParams p) {
     constexpr int NA = 6 + 4 * Z;
     __shared__ float scratch[32 * NA];
-    __shared__ float s_part[NA > 4 ? NA : 4];       // this CTA's partial results, read by its cluster peers
+    __shared__ float s_stat[4];                     // this CTA's softmax statistics, read by its cluster peers after sweep 1
+    __shared__ float s_part[NA];                    // this CTA's partial sums, read by rank 0 after sweep 2
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = static_cast<int>(cluster.num_blocks());
     const int rank = static_cast<int>(cluster.block_rank());
@@ -67,14 +69,28 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(AttnParams p)
 
     // ---- sweep 1: online (max, sum-exp) of logits and logits + Gumbel
     float mq = -CUDART_INF_F, sq = 0.f, ma = -CUDART_INF_F, sa = 0.f;
-    for (int l = l0 + threadIdx.x * VEC; l < l1; l += kAttnThreads * VEC) {
-        float a[VEC], g[VEC];
+    for (int l = l0 + threadIdx.x * VEC; l < l1; l += 2 * kAttnThreads * VEC) {
+        // two vectors per thread and round: twice the bytes in flight per memory-latency round
+        const int l2 = l + kAttnThreads * VEC;
+        const bool two = l2 < l1;
+        float a[VEC], g[VEC], a2[VEC], g2[VEC];
         AttnVec<VEC>::load(hb + l, a);
         AttnVec<VEC>::load(gb + l, g);
+        if (two) {
+            AttnVec<VEC>::load(hb + l2, a2);
+            AttnVec<VEC>::load(gb + l2, g2);
+        }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             online_add(mq, sq, a[e]);
             online_add(ma, sa, a[e] + g[e]);
+        }
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                online_add(mq, sq, a2[e]);
+                online_add(ma, sa, a2[e] + g2[e]);
+            }
         }
     }
 #pragma unroll
@@ -91,20 +107,19 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(AttnParams p)
             online_merge(m1, s1, scratch[w * 4 + 0], scratch[w * 4 + 1]);
             online_merge(m2, s2, scratch[w * 4 + 2], scratch[w * 4 + 3]);
         }
-        s_part[0] = m1; s_part[1] = s1; s_part[2] = m2; s_part[3] = s2;
+        s_stat[0] = m1; s_stat[1] = s1; s_stat[2] = m2; s_stat[3] = s2;
     }
     cluster.sync();
     {
         float m1 = -CUDART_INF_F, s1 = 0.f, m2 = -CUDART_INF_F, s2 = 0.f;
         for (int r = 0; r < CL; ++r) {                        // rank order: every CTA of the cluster gets the same bits
-            const float* rp = cluster.map_shared_rank(s_part, r);
+            const float* rp = cluster.map_shared_rank(s_stat, r);
             online_merge(m1, s1, rp[0], rp[1]);
             online_merge(m2, s2, rp[2], rp[3]);
         }
         mq = m1; sq = s1; ma = m2; sa = s2;
     }
     const float lse_q = mq + logf(sq), lse_a = ma + logf(sa);
-    cluster.sync();                                           // every rank has read the statistics before s_part is reused
 
     // ---- sweep 2: expectations under a (Gumbel-softmax sample) and KL sums under pi = exp(q)
     float acc[NA];

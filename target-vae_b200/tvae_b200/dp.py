@@ -31,30 +31,62 @@ def shard(t: Optional[torch.Tensor], rank: int, world: int):
 
 
 class GradSync:
-    """Two-bucket gradient averaging, in place.  The backward kernels write each bucket's parameter gradients straight into
-    ONE flat fp32 buffer (ops.flat_views); start(i, flat) launches an async all-reduce on that buffer - no flatten copy -
-    and finish() makes the current stream wait for both (a stream-side wait, the host never blocks).  The per-parameter
-    gradients handed to autograd are views of the buckets, so they hold the averaged values afterwards."""
+    """Two-bucket gradient averaging, in place, with an optional fused optimiser epilogue.
 
-    def __init__(self, group=None):
+    The backward kernels write each bucket's parameter gradients straight into ONE flat fp32 buffer (ops.flat_views);
+    start(i, flat) launches an async all-reduce on that buffer - no flatten copy - and finish() makes the current stream
+    wait for both (a stream-side wait, the host never blocks).  The per-parameter gradients handed to autograd are views
+    of the buckets, so they hold the averaged values afterwards.
+
+    optimizer = tvae_b200.optim.Adam: SURVEY.md 8f-1 "optimiser step fused with the all-reduce epilogue" - as soon as a
+    bucket's collective has finished (on a side stream: the backward pass keeps running), ONE multi-tensor Adam launch
+    updates that bucket's parameters from the averaged bucket (`optim.step()` must then not be called again for the step;
+    tvae_b200.train.train_epoch does this).  The generator's update runs underneath the encoder backward, the encoder's
+    right behind its all-reduce.  Works for a single process too (no collective, same epilogue)."""
+
+    def __init__(self, group=None, optimizer=None):
         self.group = group
+        self.optimizer = optimizer
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._pending: List = [None, None]
+        self._side = {}
         # NCCL averages inside the collective (no separate scaling kernel); gloo (CPU tests) only sums
         self._avg = dist.is_initialized() and self.world > 1 and dist.get_backend(group) == "nccl"
 
-    def start(self, bucket: int, flat: torch.Tensor):
+    def _side_stream(self, device):
+        s = self._side.get(device)
+        if s is None:
+            s = self._side[device] = torch.cuda.Stream(device=device)
+        return s
+
+    def start(self, bucket: int, flat: torch.Tensor, params: Optional[Sequence[torch.Tensor]] = None,
+              grads: Optional[Sequence[torch.Tensor]] = None):
+        """flat: the bucket; params / grads (views of `flat`, one per parameter): what the fused optimiser epilogue updates."""
         work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._pending[bucket] = (flat, work)
+        side = None
+        if self.optimizer is not None and params is not None and flat.is_cuda:
+            side = self._side_stream(flat.device)
+            side.wait_stream(torch.cuda.current_stream(flat.device))       # the kernels that filled the bucket
+            with torch.cuda.stream(side):
+                if work is not None:
+                    work.wait()                                            # the SIDE stream waits for the collective
+                    if not self._avg:
+                        flat.mul_(1.0 / self.world)
+                    work = None
+                self.optimizer.step_tensors(params, grads)
+                flat.record_stream(side)
+        self._pending[bucket] = (flat, work, side)
 
     def _resolve(self, bucket: int):
-        flat, work = self._pending[bucket]
+        flat, work, side = self._pending[bucket]
         if work is not None:
             work.wait()
             if not self._avg:
                 flat.mul_(1.0 / self.world)
+        if side is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(side)        # parameters are updated before anything that follows
         self._pending[bucket] = None
         return flat
 

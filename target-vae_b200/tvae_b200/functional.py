@@ -359,6 +359,7 @@ class FusedStepFn(torch.autograd.Function):
         ctx.spec, ctx.s, ctx.ashape, ctx.gs, ctx.gw, ctx.gsaved, ctx.att = spec, s, ashape, gs, gw, gsaved, att
         ctx.spacing = spacing
         ctx.enc_shapes = [p.shape for p in enc_params]
+        ctx.param_objs = (enc_params, gen_params) if spec.sync is not None else None   # for the fused optimiser epilogue
         ctx.save_for_backward(yc, w2m, wh, x1, h, heads, xc, gum, rz, rth, log_prior, y_hat, ctfc if ctfc is not None else yc,
                               *((enc_params[10], xp) if es.pool else ()))
         ctx.has_ctf = ctfc is not None
@@ -389,14 +390,15 @@ class FusedStepFn(torch.autograd.Function):
             gout = ops.generator_bwd(gs, ctx.gw, xc, att["theta_b"], att["dx"], att["zb"], ctx.gsaved, y_hat, d_yhat)
         gen_grads = _gen_param_grads(gout, gs.L)
         if spec.sync is not None:
-            spec.sync.start(0, gout["flat"])
+            spec.sync.start(0, gout["flat"], ctx.param_objs[1], gen_grads)
         with nvtx_range("tvae.attention_bwd"):
             d_heads = ops.attn_bwd(ctx.ashape, heads, gum, rz, rth, log_prior, att, gout["d_z"], gout["d_theta"], gout["d_dx"], w_kl)
         with nvtx_range("tvae.encoder_bwd"):
             enc_grads, enc_flat = _encoder_backward(s, spec.enc, yc, w2m, wh, x1, h, d_heads, ctx.enc_shapes, *pool)
         if spec.sync is not None:
-            spec.sync.start(1, enc_flat)
+            spec.sync.start(1, enc_flat, ctx.param_objs[0], enc_grads)
             spec.sync.finish()            # gen_grads / enc_grads are views of the two buckets: averaged in place
+            ctx.param_objs = None
         ctx.gsaved = None
         ctx.att = None
         return (None,) * 9 + tuple(enc_grads) + tuple(gen_grads)

@@ -40,7 +40,10 @@ def train_epoch(iterator, x_coord, generator_model, encoder_model, optim, t_inf,
                                                      theta_prior, groupconv, image_dim, particles, padding, mask_radius, sync)
         loss = -elbo
         loss.backward()
-        if fused:
+        if sync is not None and getattr(sync, "optimizer", None) is optim:
+            # the update already ran inside the backward pass, bucket by bucket, behind each gradient all-reduce
+            optim.zero_grad(set_to_none=True)
+        elif fused:
             optim.step()
             optim.zero_grad(set_to_none=True)
         else:

@@ -102,3 +102,35 @@ def test_train_epoch_and_eval_model():
     d = torch.cat([(a - b).abs().flatten() for a, b in zip(*finals)])
     assert float(d.max()) <= 2 * lr * steps * 1.01
     assert float(d.mean()) <= 0.02 * lr
+
+
+def test_optimizer_epilogue_behind_the_gradient_buckets():
+    """SURVEY 8f-1 as written: with dp.GradSync(optimizer=Adam) the update runs INSIDE the backward pass, one multi-tensor
+    launch per gradient bucket on a side stream (the generator's underneath the encoder backward), consuming the buckets
+    the backward kernels wrote in place.  Single process (no collective): the result must equal backward + optim.step()."""
+    from test_gpu_step import build_models
+    from tvae_b200 import dp, synth, train
+    from tvae_b200.optim import Adam
+    cfg = HotPathConfig("t_epi", C=1, n=24, k=9, p=3, G=8, z=2, O=32, hidden=128)
+    B = 6
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    batches = [(torch.from_numpy(synth.minibatch(cfg, B, seed=i)["y"]).to(DEV),) for i in range(3)]
+    finals, states = [], []
+    for epilogue in (True, False):
+        gen, enc = build_models(cfg)
+        params = list(gen.parameters()) + list(enc.parameters())
+        opt = Adam(params, lr=2e-4)
+        sync = dp.GradSync(optimizer=opt) if epilogue else None
+        torch.manual_seed(321)
+        out = train.train_epoch(batches, x, gen, enc, opt, "attention", "attention+offsets", 0, 1, 3 * B, DEV, params,
+                                cfg.theta_prior, cfg.G, cfg.n, sync=sync)
+        torch.cuda.synchronize()
+        assert all(np.isfinite(out))
+        assert all(int(opt.state[p]["step"]) == 3 for p in params)            # exactly one update per step, either way
+        finals.append([p.detach().clone() for p in params])
+        states.append([opt.state[p]["exp_avg"].clone() for p in params])
+    lr, steps = 2e-4, 3
+    d = torch.cat([(a - b).abs().flatten() for a, b in zip(*finals)])
+    assert float(d.max()) <= 2 * lr * steps * 1.01 and float(d.mean()) <= 0.02 * lr
+    for a, b in zip(*states):                                               # first moments: same gradients were consumed
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-3
