@@ -297,15 +297,14 @@ int tvae_mrc_crop_normalize(const void* in, int mode, int B, int n, int m, int c
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);
 int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream);
-/* A/B switch (process-wide, for measurements and tests): 0 sends the wide layers back to the tc_gemm LinearNT / LinearTN
- * policies instead of the CTA-pair kernels (linear_nt_pair.cuh, linear_pair_policies.cuh).  Default: both 1. */
-void tvae_test_set_fast_paths(int pair_nt, int pair_tn);
+/* A/B switch (process-wide, for measurements and tests): 0 sends wide weight gradients back to the tc_gemm LinearTN policy
+ * instead of the CTA-pair kernel (linear_pair_policies.cuh).  Default: 1. */
+void tvae_test_set_fast_paths(int pair_tn);
 /* the hidden-layer GEMM with its whole epilogue: C16[M,N] fp16 = store_scale * mask(aux16) * act(acc_scale * A B^T + bias);
- * colsum[N] += column sums, proj_out[M,n_proj] (pre-zeroed) += value . proj_w^T (+ proj_bias).  Any pointer may be NULL.
- * use_pair = 1: the CTA-pair kernel takes N >= 256; 0: tc_gemm policies only. */
+ * colsum[N] += column sums, proj_out[M,n_proj] (pre-zeroed) += value . proj_w^T (+ proj_bias).  Any pointer may be NULL. */
 int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, const float* bias, int act, void* C16,
                              const void* aux16, int aux_act, const float* acc_scale, const float* store_scale, float* colsum,
-                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, int use_pair, void* stream);
+                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,6 @@
 #include "host_utils.cuh"
 #include "linear_policies.cuh"
 #include "tc_gemm2.cuh"
-#include "linear_nt_pair.cuh"
 #include "linear_pair_policies.cuh"
 
 namespace tvae {
@@ -77,69 +76,8 @@ struct LinearNTArgs {
     float* colsum = nullptr; long long colsum_stride = 1;
 };
 
-// CTA-pair kernel (linear_nt_pair.cuh) for wide layers (N >= 256): returns 1 when the shape is not covered (the caller
-// falls back to the tc_gemm LinearNT policies), 0 on success, < 0 on error.
-inline bool g_linear_nt_pair_enabled = true;      // test hook (tvae_test_set_fast_paths): 0 = tc_gemm LinearNT policies only
-inline int linear_nt_pair(const LinearNTArgs& a, cudaStream_t stream) {
-    if (!g_linear_nt_pair_enabled) return 1;
-    if (a.N < 256 || a.N % 64 != 0 || a.N > 1024 || a.M < 256) return 1;
-    const bool tanh_inst = a.act == kActTanh || (a.aux16 && a.aux_act == kActTanh);
-    LinearNTPairParams q{};
-    LinearNTParams& p = q.nt;
-    int rc;
-    if ((rc = make_tmap_2d_h(&p.tmA, a.A, a.M, a.K, a.lda, kBM))) return rc;
-    if ((rc = make_tmap_2d_h(&p.tmB, a.B, a.N, a.K, a.ldb, 128))) return rc;
-    p.M = a.M; p.N = a.N;
-    p.k_chunks = cdiv(a.K, kBKh);
-    p.tiles_n = cdiv(a.N, 256);
-    p.C = a.C; p.ldc = a.ldc; p.bias = a.bias;
-    p.row_bias = a.row_bias; p.rows_per_group = a.rows_per_group; p.ld_rb = a.ld_rb;
-    p.ld_aux = a.ld_aux; p.act = a.act; p.aux_act = a.aux_act;
-    p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
-    p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
-    p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
-    p.npad = (a.N + 31) / 32 * 32;
-    p.cs_off = (1 + a.n_proj) * p.npad;
-    int extra = (LinearNT<256>::extra_floats(a.N, a.n_proj, a.colsum != nullptr) * 4 + 1023) / 1024 * 1024;
-    p.tma_store = (a.C16 != nullptr) ? 1 : 0;
-    p.stage_off = extra;
-    p.stage_bufs = 1;             // one staging buffer per epilogue group: the shared memory goes to the operand ring
-    if (p.tma_store) {
-        if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;
-        extra += kNpEpiGroups * LinearNT<256>::kStageBytes;
-    }
-    q.m_pairs = cdiv(a.M, 2 * kBM);
-    q.items = q.m_pairs * p.tiles_n;
-    p.num_tiles = q.items;
-    // the epilogue group's next item is two items further: the same column tile of the next row block (tiles_n = 2),
-    // or the row block after next (tiles_n = 1); in 128-row tiles of this CTA's rows:
-    p.pf_tile_stride = p.tiles_n == 1 ? 4 : (p.tiles_n == 2 ? 2 : 0);
-    int stages = (kMaxSmemBytes - np_smem_layout(0, extra).total) / kNpStageBytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return 1;
-    q.num_stages = stages;
-    const NpSmem L = np_smem_layout(stages, extra);
-    q.bar_off = L.bar_off; q.tmem_ptr_off = L.tmem_ptr_off; q.extra_off = L.extra_off;
-    const void* fn = tanh_inst ? reinterpret_cast<const void*>(&linear_nt_pair_kernel<true>)
-                               : reinterpret_cast<const void*>(&linear_nt_pair_kernel<false>);
-    TVAE_CHECK_CUDA(smem_optin(fn, kMaxSmemBytes));
-    const int pairs_dev = sm_count() / 2;
-    const int pairs = q.items < pairs_dev ? q.items : pairs_dev;
-    ++g_launch_count;
-    const int tslot = g_timer.begin("linear_nt", stream);
-    if (tanh_inst) linear_nt_pair_kernel<true><<<2 * pairs, kNpThreads, L.total, stream>>>(q);
-    else linear_nt_pair_kernel<false><<<2 * pairs, kNpThreads, L.total, stream>>>(q);
-    g_timer.end(tslot, stream);
-    TVAE_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
 inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     TVAE_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_nt: empty problem");
-    {
-        const int rc = linear_nt_pair(a, stream);
-        if (rc <= 0) return rc;
-    }
     TVAE_REQUIRE(a.N % 4 == 0 && a.N <= 1024, "linear_nt: N must be a multiple of 4, at most 1024");
     TVAE_REQUIRE(a.n_proj <= 4, "linear_nt: at most 4 fused projection outputs");
     LinearNTParams p{};
@@ -165,8 +103,6 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     int extra = (LinearNT<128>::extra_floats(a.N, a.n_proj, a.colsum != nullptr) * 4 + 1023) / 1024 * 1024;
     p.tma_store = (a.C16 != nullptr && a.N % 64 == 0) ? 1 : 0;
     p.stage_off = extra;
-    p.stage_bufs = 2;
-    p.pf_tile_stride = 0;
     if (p.tma_store) {
         if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;
         extra += LinearNT<128>::kEpiGroups * 2 * LinearNT<128>::kStageBytes;

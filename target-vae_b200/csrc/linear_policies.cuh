@@ -53,10 +53,7 @@ struct LinearNTParams {
     long long colsum_stride;
     CUtensorMap tmC;          // C16 as [M][N] fp16, boxes {64, 128 rows}, for the staged TMA stores (tma_store == 1)
     int tma_store;            // 1: C16 leaves the SM through a swizzled smem staging buffer + TMA store (N % 64 == 0)
-    int stage_off;            // byte offset of the staging buffers (stage_bufs 16 KB buffers per epilogue group) in the extra smem
-    int pf_tile_stride;       // 0: the epilogue group's next tile follows tc_gemm's contiguous (m, n) order; > 0: it is this many
-                              // 128-row tiles further down in the same columns (pair kernel) - L2 prefetch of the mask operand
-    int stage_bufs;           // 2 (tc_gemm LinearNT) or 1 (pair kernel: the shared memory goes to a deeper operand ring)
+    int stage_off;            // byte offset of the staging buffers (two 16 KB buffers per epilogue group) in the extra smem
     int npad;                 // N rounded up to 32: row pitch (floats) of the bias / projection / column-sum rows in the extra smem
     int cs_off;               // float offset of the column-sum rows
 };
@@ -98,7 +95,7 @@ struct LinearNT : PolicyBase {
         return (1 + n_proj + (colsum ? kEpiGroups * kEpiWarps : 0)) * npad;
     }
     static constexpr int kStageBytes = kBM * 128;      // [128 rows][64 halves], 128 B swizzle
-    struct EpiState { int cs, grp, blocks, col0; };    // col0: first column held by the bias / projection / column-sum rows in smem
+    struct EpiState { int cs, grp, blocks; };
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
         float* s = reinterpret_cast<float*>(extra);
         for (int i = tid; i < p.N; i += nthreads) s[i] = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -108,7 +105,6 @@ struct LinearNT : PolicyBase {
         st.cs = p.cs_off + (slot >> 5) * p.npad + (slot & 31);
         st.grp = slot >> 7;
         st.blocks = 0;
-        st.col0 = 0;
         if (!p.colsum) return;
         float* cs = reinterpret_cast<float*>(extra) + st.cs;
         for (int c = 0; c * 32 < p.N; ++c) cs[c * 32] = 0.f;
@@ -154,15 +150,8 @@ struct LinearNT : PolicyBase {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (ti.n0 + 8 * j < p.N) ax_next[j] = __ldg(reinterpret_cast<const uint4*>(ax_row) + j);
-            int mt, nt;
-            if (p.pf_tile_stride > 0) {
-                mt = ti.m0 / kBM + p.pf_tile_stride;
-                nt = ti.n0 / BN;
-            } else {
-                const int tile_next = (ti.m0 / kBM) * p.tiles_n + ti.n0 / BN + kEpiGroups;
-                mt = tile_next / p.tiles_n;
-                nt = tile_next - mt * p.tiles_n;
-            }
+            const int tile_next = (ti.m0 / kBM) * p.tiles_n + ti.n0 / BN + kEpiGroups;
+            const int mt = tile_next / p.tiles_n, nt = tile_next - mt * p.tiles_n;
             const long long mn = (long long)mt * kBM + row;
             if (mn < p.M) {
                 const char* pf = reinterpret_cast<const char*>(reinterpret_cast<const __half*>(p.aux16) + mn * p.ld_aux + nt * BN);
@@ -187,7 +176,6 @@ struct LinearNT : PolicyBase {
             }
             tmem_ld_wait();
             const int n_base = ti.n0 + c * 32;
-            const int ns = n_base - st.col0;      // column inside the smem rows (bias, projection weights, column sums)
             if (p.colsum || p.tma_store) {        // uniform path: every thread takes part in the shuffles / barriers
                 if (n_base >= p.N) continue;
             } else if (!m_ok || n_base >= p.N) {
@@ -200,7 +188,7 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (n_base + j < p.N) {
-                        const float4 t = *reinterpret_cast<const float4*>(s_bias + ns + j);
+                        const float4 t = *reinterpret_cast<const float4*>(s_bias + n_base + j);
                         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
@@ -236,7 +224,7 @@ struct LinearNT : PolicyBase {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
-                reinterpret_cast<float*>(extra)[st.cs + ns] += warp_colsum32(v, row & 31);
+                reinterpret_cast<float*>(extra)[st.cs + n_base] += warp_colsum32(v, row & 31);
                 if (!m_ok && !p.tma_store) continue;
             }
             if (p.tma_store) {
@@ -244,13 +232,9 @@ struct LinearNT : PolicyBase {
                 // read by the previous store), the odd one closes it and hands it to the TMA store unit; rows >= M
                 // are clipped by the tensor map
                 // two staging buffers per group, alternating: a block only waits for the store issued two blocks ago
-                const int nbuf = p.stage_bufs;     // staging buffers per epilogue group (2; 1 where shared memory is short)
-                uint8_t* buf = extra + p.stage_off + (st.grp * nbuf + (nbuf == 2 ? (st.blocks & 1) : 0)) * kStageBytes;
-                if ((c & 1) == 0 && st.blocks >= nbuf) {
-                    if (row == 0) {
-                        if (nbuf == 2) tma_store_wait_read<1>();
-                        else tma_store_wait_read<0>();
-                    }
+                uint8_t* buf = extra + p.stage_off + (st.grp * 2 + (st.blocks & 1)) * kStageBytes;
+                if ((c & 1) == 0 && st.blocks >= 2) {
+                    if (row == 0) tma_store_wait_read<1>();
                     named_bar_sync(2 + st.grp, kEpiWarps * 32);
                 }
 #pragma unroll
@@ -290,7 +274,7 @@ struct LinearNT : PolicyBase {
             }
             if (p.proj_w) {
                 for (int o = 0; o < p.n_proj; ++o) {
-                    const float* w = s_bias + (1 + o) * p.npad + ns;
+                    const float* w = s_bias + (1 + o) * p.npad + n_base;
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {

@@ -1186,28 +1186,20 @@ int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, in
 }
 
 // full epilogue of the hidden-layer GEMM: fp16 output (x *store_scale), bias, activation, derivative mask from aux16,
-// accumulator scale, column sums, fused projection.  use_pair = 0 forces the tc_gemm LinearNT policies, 1 lets the
-// CTA-pair kernel (linear_nt_pair.cuh) take the shapes it covers.
+// accumulator scale, column sums, fused projection
 int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, const float* bias, int act, void* C16,
                              const void* aux16, int aux_act, const float* acc_scale, const float* store_scale, float* colsum,
-                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, int use_pair, void* stream) {
+                             const float* proj_w, const float* proj_bias, float* proj_out, int n_proj, void* stream) {
     LinearNTArgs a{};
     a.A = A; a.lda = K; a.B = B; a.ldb = K; a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act;
     a.C16 = C16; a.ldc16 = N; a.aux16 = aux16; a.ld_aux = N; a.aux_act = aux_act;
     a.acc_scale = acc_scale; a.store_scale = store_scale; a.colsum = colsum; a.colsum_stride = 1;
     a.proj_w = proj_w; a.proj_bias = proj_bias; a.proj_out = proj_out; a.n_proj = n_proj;
-    const bool saved = g_linear_nt_pair_enabled;
-    g_linear_nt_pair_enabled = use_pair != 0;
-    const int rc = linear_nt(a, S(stream));
-    g_linear_nt_pair_enabled = saved;
-    return rc;
+    return linear_nt(a, S(stream));
 }
 
-// A/B switch for the two wide-layer kernels (default: both on): the CTA-pair LinearNT and the CTA-pair LinearTN
-void tvae_test_set_fast_paths(int pair_nt, int pair_tn) {
-    g_linear_nt_pair_enabled = pair_nt != 0;
-    g_linear_pair_enabled = pair_tn != 0;
-}
+// A/B switch for the wide weight-gradient kernel (default on): 0 sends it back to the tc_gemm LinearTN policy
+void tvae_test_set_fast_paths(int pair_tn) { g_linear_pair_enabled = pair_tn != 0; }
 
 int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
     return linear_tn(P, Ma, Q, Nb, R, Ma, Nb, C, transpose_out ? Ma : Nb, transpose_out, S(stream));

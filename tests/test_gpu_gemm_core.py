@@ -80,7 +80,7 @@ def test_linear_tn(R, Ma, Nb, transpose_out):
     assert e < 5e-5
 
 
-def _nt_full(A, B, use_pair, bias=None, act=0, aux=None, acc_scale=None, store_scale=None, colsum=False, proj=None):
+def _nt_full(A, B, bias=None, act=0, aux=None, acc_scale=None, store_scale=None, colsum=False, proj=None):
     """-> (C16 as float, colsum or None, proj_out or None) of the hidden-layer GEMM with its whole epilogue"""
     import ctypes
     from tvae_b200 import _lib
@@ -97,9 +97,9 @@ def _nt_full(A, B, use_pair, bias=None, act=0, aux=None, acc_scale=None, store_s
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     rc = fn(_lib.ptr(A), _lib.ptr(B), M, N, K, _lib.ptr(bias), act, _lib.ptr(C16), _lib.ptr(aux), 0, _lib.ptr(acc_scale),
-            _lib.ptr(store_scale), _lib.ptr(cs), _lib.ptr(pw), _lib.ptr(pb), _lib.ptr(po), n_proj, use_pair, _lib.stream_ptr())
+            _lib.ptr(store_scale), _lib.ptr(cs), _lib.ptr(pw), _lib.ptr(pb), _lib.ptr(po), n_proj, _lib.stream_ptr())
     _lib.check(rc, "tvae_test_linear_nt_full")
     torch.cuda.synchronize()
     return C16.float(), cs, po
@@ -107,10 +107,10 @@ def _nt_full(A, B, use_pair, bias=None, act=0, aux=None, acc_scale=None, store_s
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 256), (1000, 512, 512), (70001, 512, 512), (4097, 512, 128), (5, 256, 512)])
 @pytest.mark.parametrize("mode", ["forward", "dgrad"])
-def test_linear_nt_pair_kernel(M, N, K, mode):
-    """The CTA-pair LinearNT kernel (generator hidden layers: forward with bias + LeakyReLU + fused output
-    projection, input-gradient GEMM with the derivative mask, power-of-two scales and column sums) against fp64 on the
-    fp16-rounded operands, and against the tc_gemm LinearNT policies it replaces for these shapes."""
+def test_linear_nt_full_epilogue(M, N, K, mode):
+    """LinearNT with the whole epilogue of the generator's hidden layers - forward: bias + LeakyReLU + fp16 TMA stores + fused
+    output projection; input gradient: derivative mask, power-of-two scales, column sums - against fp64 on the fp16-rounded
+    operands."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
     B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
@@ -118,23 +118,20 @@ def test_linear_nt_pair_kernel(M, N, K, mode):
         bias = torch.randn(N, device="cuda", generator=g) * 0.1
         pw = torch.randn(3, N, device="cuda", generator=g) * 0.1
         pb = torch.randn(3, device="cuda", generator=g)
-        outs = [_nt_full(A, B, uc, bias=bias, act=1, proj=(pw, pb)) for uc in (1, 0)]
+        C, _, po = _nt_full(A, B, bias=bias, act=1, proj=(pw, pb))
         ref = torch.nn.functional.leaky_relu(A.double() @ B.double().t() + bias.double(), 0.01)
         ref_proj = ref @ pw.double().t() + pb.double()
-        for C, _, po in outs:
-            assert float((C.double() - ref).norm() / ref.norm()) < 6e-4          # fp16 rounding of the stored output
-            assert float((po.double() - ref_proj).norm() / ref_proj.norm()) < 2e-5
+        assert float((C.double() - ref).norm() / ref.norm()) < 6e-4          # fp16 rounding of the stored output
+        assert float((po.double() - ref_proj).norm() / ref_proj.norm()) < 2e-5
     else:
         aux = torch.randn(M, N, device="cuda", generator=g).half()
         acc_scale = torch.tensor([0.25], device="cuda")
         store_scale = torch.tensor([8.0], device="cuda")
-        outs = [_nt_full(A, B, uc, aux=aux, acc_scale=acc_scale, store_scale=store_scale, colsum=True) for uc in (1, 0)]
+        C, cs, _ = _nt_full(A, B, aux=aux, acc_scale=acc_scale, store_scale=store_scale, colsum=True)
         mask = torch.where(aux.double() > 0, 1.0, 0.01)
         val = 0.25 * (A.double() @ B.double().t()) * mask
-        for C, cs, _ in outs:
-            assert float((C.double() / 8.0 - val).norm() / val.norm()) < 6e-4
-            assert float((cs.double() - val.sum(0)).norm() / val.sum(0).norm()) < 1e-4
-    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-3 * float(outs[1][0].abs().max())
+        assert float((C.double() / 8.0 - val).norm() / val.norm()) < 6e-4
+        assert float((cs.double() - val.sum(0)).norm() / val.sum(0).norm()) < 1e-4
 
 
 @pytest.mark.parametrize("R,Ma,Nb", [(5000, 512, 512), (70001, 512, 512), (4096, 256, 512), (999, 512, 256), (3000, 200, 160)])
@@ -148,10 +145,10 @@ def test_linear_tn_pair_matches_tc_gemm(R, Ma, Nb):
     outs = []
     try:
         for pair in (1, 0):
-            _lib.lib().tvae_test_set_fast_paths(1, pair)
+            _lib.lib().tvae_test_set_fast_paths(pair)
             outs.append([_tn(P, Q, t) for t in (0, 1)])
     finally:
-        _lib.lib().tvae_test_set_fast_paths(1, 1)
+        _lib.lib().tvae_test_set_fast_paths(1)
     for o in outs:
         assert float((o[0].double() - ref).norm() / ref.norm()) < 5e-5
         assert float((o[1].double() - ref.t()).norm() / ref.norm()) < 5e-5
