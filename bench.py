@@ -490,6 +490,7 @@ def kernel_rooflines(cfg, B, prof, K, ms_step, peaks, clk_summary, ops):
             "achieved_counts": "achieved = EXECUTED MAC x2 per launch / event-timed launch duration; achieved_dense = SURVEY 8(d) "
                                "dense count (zero-padding taps included, what cuDNN executes) - the conv kernels skip all-padding K chunks",
             "peak_source": peaks["source"], "ms_per_launch": d["ms_per_step"] / max(d["launches_per_step"], 1e-9),
+            "ms_per_step": d["ms_per_step"],
             "share_of_step": d["share_of_step"],
             "precision": "every contraction is tcgen05.mma.kind::f16: FP16 operands (11-bit significand = TF32's, the reference's "
                          "cuDNN default; NARROWER than the fp32 SGEMM the reference's generator nn.Linear layers use by default - "

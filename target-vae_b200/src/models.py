@@ -140,8 +140,9 @@ class SpatialGenerator(nn.Module):
 
 
 class GroupConv(nn.Module):
-    """models.py:132-225: P_G lifting convolution; the rotated filter bank and the im2col operand are
-    generated on chip, the contraction runs on the tcgen05 tensor cores."""
+    """models.py:132-225: P_G lifting convolution.  The rotated filter bank is sampled once per call into an fp16 operand
+    that stays L2-resident (8-25 MB), the im2col operand is generated in shared memory, the contraction runs on the tcgen05
+    tensor cores."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1,
                  padding=0, bias=True, input_rot_dim=1, output_rot_dim=4):
