@@ -293,6 +293,24 @@ int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int norm
  * The 1024-byte header is parsed on the host (tvae_b200/mrc.py). */
 int tvae_mrc_crop_normalize(const void* in, int mode, int B, int n, int m, int crop, int normalize, float* out, void* stream);
 
+/* ------------------------------------------------------------------ standalone module interfaces of src/models.py
+ * (calls a user can make outside the fused step; not on the timed path)
+ * RandomFourierEmbedding2d.forward (models.py:53-58): out (M,E) = cos(x (M,2) . w_scaled^T + b), w_scaled = weight / sigma;
+ * backward: dx (M,2) from g (M,E). */
+int tvae_fourier_embed_fwd(const float* x, const float* w_scaled, const float* b, float* out, long long M, int E, void* stream);
+int tvae_fourier_embed_bwd(const float* x, const float* w_scaled, const float* b, const float* g, float* dx, long long M, int E, void* stream);
+/* ResidLinear.forward (models.py:29-30): y (M,N) = act(x (M,K) . W^T + bias [+ x]) on the LinearNT tensor-core kernel with fp16
+ * operands (resid = 1: W + I, N == K; resid = 0: a plain Linear + activation).  x16 (M*K halves) and w16 (N*K halves) are
+ * scratch; x16 is the saved operand of the backward call.  Backward: g (M,N) = dLoss/dy -> dx (M,K) (may be NULL), dw (N,K),
+ * db (N); dpre16 (M*N halves), wt16 (N*K halves) and scales8 (8 floats) are scratch. */
+int tvae_linear_act_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int resid, int act, float* y,
+                        void* x16, void* w16, void* stream);
+int tvae_linear_act_bwd(const void* x16, const float* w, const float* y, const float* g, int M, int N, int K, int resid, int act,
+                        void* dpre16, void* wt16, float* scales8, float* dx, float* dw, float* db, void* stream);
+/* backward of tvae_attn_softmax_pair (models.py:383-388 under autograd): d_attn (B,L) from d_q and / or d_a (either may be NULL) */
+int tvae_attn_softmax_pair_bwd(const float* q_t_r, const float* a_sampled, const float* d_q, const float* d_a, float* d_attn, int B, int L,
+                               void* stream);
+
 /* ------------------------------------------------------------------ test hooks for the GEMM core (fp16 operands, fp32 out)
  * nt: C[M,N] = act(A[M,K] B[N,K]^T + bias);  tn: C[Ma,Nb] (or its transpose) += sum_r P[r,Ma] Q[r,Nb], C zero-filled */
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act, void* stream);

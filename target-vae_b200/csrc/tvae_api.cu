@@ -13,6 +13,7 @@
 #include "attn_kernels.cuh"
 #include "enc_bwd_fused.cuh"
 #include "refine.cuh"
+#include "module_kernels.cuh"
 
 using namespace tvae;
 
@@ -1175,6 +1176,77 @@ int tvae_mrc_crop_normalize(const void* in, int mode, int B, int n, int m, int c
 
 int tvae_crop_normalize(const float* in, int B, int n, int m, int crop, int normalize, float* out, void* stream) {
     return tvae_mrc_crop_normalize(in, 2, B, n, m, crop, normalize, out, stream);
+}
+
+// ================================================================================ standalone module interfaces
+int tvae_fourier_embed_fwd(const float* x, const float* w_scaled, const float* b, float* out, long long M, int E, void* stream) {
+    TVAE_REQUIRE(M >= 0 && E >= 1, "fourier_embed: bad shape");
+    if (M == 0) return 0;
+    TVAE_REQUIRE(x && w_scaled && b && out, "fourier_embed: null pointer");
+    ++g_launch_count; fourier_embed_fwd_kernel<<<blocks_for(M * E, 256), 256, 0, S(stream)>>>(x, w_scaled, b, out, M, E);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int tvae_fourier_embed_bwd(const float* x, const float* w_scaled, const float* b, const float* g, float* dx, long long M, int E, void* stream) {
+    TVAE_REQUIRE(M >= 0 && E >= 1, "fourier_embed: bad shape");
+    if (M == 0) return 0;
+    TVAE_REQUIRE(x && w_scaled && b && g && dx, "fourier_embed: null pointer");
+    ++g_launch_count; fourier_embed_bwd_kernel<<<cdiv(M, 8), 256, 0, S(stream)>>>(x, w_scaled, b, g, dx, M, E);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tvae_linear_act_fwd(const float* x, const float* w, const float* bias, int M, int N, int K, int resid, int act, float* y,
+                        void* x16, void* w16, void* stream) {
+    TVAE_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 4 == 0 && N <= 1024, "linear_act: K must be a multiple of 8, N a multiple of 4 (<= 1024)");
+    TVAE_REQUIRE(!resid || N == K, "linear_act: a residual layer is square");
+    TVAE_REQUIRE(act == TVAE_ACT_LEAKYRELU || act == TVAE_ACT_TANH, "linear_act: act must be TVAE_ACT_LEAKYRELU or TVAE_ACT_TANH");
+    TVAE_REQUIRE(x && w && y && x16 && w16, "linear_act: null pointer");
+    cudaStream_t st = S(stream);
+    ++g_launch_count; to_half_kernel<<<blocks_for((long long)M * K, 256), 256, 0, st>>>(x, static_cast<__half*>(x16), (long long)M * K);
+    ++g_launch_count; weight_to_half_kernel<<<blocks_for((long long)N * K, 256), 256, 0, st>>>(w, static_cast<__half*>(w16), nullptr, N, K, resid);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    LinearNTArgs a{};
+    a.A = x16; a.lda = K; a.B = w16; a.ldb = K; a.M = M; a.N = N; a.K = K; a.C = y; a.ldc = N; a.bias = bias;
+    a.act = act == TVAE_ACT_TANH ? kActTanh : 1;
+    return linear_nt(a, st);
+}
+
+int tvae_linear_act_bwd(const void* x16, const float* w, const float* y, const float* g, int M, int N, int K, int resid, int act,
+                        void* dpre16, void* wt16, float* scales8, float* dx, float* dw, float* db, void* stream) {
+    TVAE_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0 && N <= 1024 && K <= 1024, "linear_act: bad shape");
+    TVAE_REQUIRE(x16 && w && y && g && dpre16 && wt16 && scales8 && dw && db, "linear_act: null pointer");
+    cudaStream_t st = S(stream);
+    const int kact = act == TVAE_ACT_TANH ? kActTanh : 0;
+    TVAE_CHECK_CUDA(cudaMemsetAsync(scales8, 0, sizeof(float) * 8, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
+    TVAE_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * N * K, st));
+    ++g_launch_count; actgrad_absmax_kernel<<<blocks_for((long long)M * N, 256), 256, 0, st>>>(g, y, (long long)M * N, kact, scales8 + 7);
+    ++g_launch_count; single_scale_kernel<<<1, 1, 0, st>>>(scales8 + 7, scales8);
+    const int rows_per_cta = static_cast<int>(((long long)M + 8LL * sm_count() - 1) / (8LL * sm_count()));
+    ++g_launch_count;
+    actgrad_to_half_colsum_kernel<<<cdiv(M, rows_per_cta), 256, N * sizeof(float), st>>>(g, y, static_cast<__half*>(dpre16), scales8, db, M, N, rows_per_cta, kact);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    int rc;
+    // dW[n][k] = sum_m dpre[m][n] x[m][k]
+    if ((rc = linear_tn(dpre16, N, x16, K, M, N, K, dw, K, 0, st, scales8 + 3))) return rc;
+    if (dx) {
+        // dx = dpre (W + I): B operand = (W + I)^T as [K][N]
+        ++g_launch_count; weight_to_half_kernel<<<blocks_for((long long)N * K, 256), 256, 0, st>>>(w, nullptr, static_cast<__half*>(wt16), N, K, resid);
+        TVAE_CHECK_CUDA(cudaGetLastError());
+        LinearNTArgs a{};
+        a.A = dpre16; a.lda = N; a.B = wt16; a.ldb = N; a.M = M; a.N = K; a.K = N; a.C = dx; a.ldc = K; a.acc_scale = scales8 + 3;
+        if ((rc = linear_nt(a, st))) return rc;
+    }
+    return 0;
+}
+
+int tvae_attn_softmax_pair_bwd(const float* q_t_r, const float* a_sampled, const float* d_q, const float* d_a, float* d_attn, int B, int L,
+                               void* stream) {
+    TVAE_REQUIRE(B >= 1 && L >= 1 && q_t_r && a_sampled && d_attn && (d_q || d_a), "softmax_pair_bwd: bad arguments");
+    ++g_launch_count; softmax_pair_bwd_kernel<<<B, 1024, 0, S(stream)>>>(q_t_r, a_sampled, d_q, d_a, d_attn, L);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // ================================================================================ test hooks

@@ -20,7 +20,6 @@ import math
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.nn import Parameter
 from torch.nn.modules.utils import _pair
 
@@ -36,7 +35,8 @@ def _require_cuda(t, what):
 
 class ResidLinear(nn.Module):
     """models.py:22-30: act(linear(x) + x).  Inside SpatialGenerator it runs on the hidden-layer tensor-core kernels as a
-    plain layer with the effective weight W + I (tvae_b200.functional._gen_weights); it has no standalone forward."""
+    plain layer with the effective weight W + I (tvae_b200.functional._gen_weights); called on its own it runs the same
+    way through tvae_linear_act_fwd / _bwd (FP16 operands, fp32 accumulation)."""
 
     def __init__(self, n_in, n_out, activation=nn.LeakyReLU):
         super(ResidLinear, self).__init__()
@@ -44,12 +44,14 @@ class ResidLinear(nn.Module):
         self.act = activation()
 
     def forward(self, x):
-        raise NotImplementedError("ResidLinear runs only as a hidden layer of SpatialGenerator (fused kernels)")
+        _require_cuda(x, "ResidLinear.forward")
+        return TF.LinearActFn.apply(x, self.linear.weight, self.linear.bias, True, _ops.act_kind(self.act))
 
 
 class RandomFourierEmbedding2d(nn.Module):
     """models.py:33-58: buffers `weight` ~ randn(E,2), `bias` ~ U(0, 2pi); cos(x W^T / sigma + b).
-    Inside SpatialGenerator the expansion is generated tile-by-tile in shared memory by the layer-1 GEMM."""
+    Inside SpatialGenerator the expansion is generated tile-by-tile in shared memory by the layer-1 GEMM and never
+    materialised; called on its own it is one elementwise kernel (tvae_fourier_embed_fwd / _bwd)."""
 
     def __init__(self, in_dim, embedding_dim, sigma=0.01):
         super(RandomFourierEmbedding2d, self).__init__()
@@ -63,7 +65,8 @@ class RandomFourierEmbedding2d(nn.Module):
     def forward(self, x):
         if x is None:
             return 0
-        raise NotImplementedError("RandomFourierEmbedding2d is evaluated inside SpatialGenerator's fused layer-1 kernel")
+        _require_cuda(x, "RandomFourierEmbedding2d.forward")
+        return TF.FourierEmbedFn.apply(x, self.weight, self.bias, float(self.sigma))
 
 
 class SpatialGenerator(nn.Module):
@@ -272,9 +275,10 @@ class InferenceNetwork_AttentionTranslation_UnimodalRotation(nn.Module):
         attn = heads[:, 0:1]
         theta = heads[:, 1:3]
         z = heads[:, 3:]
-        # models.py:311-313: elementwise tail on the attention map; the fused step never materialises it
-        a_sampled = F.gumbel_softmax(attn.reshape(B, -1), dim=-1).view(B, heads.shape[2], heads.shape[3])
-        return attn, a_sampled, theta, z
+        # models.py:311-313: Gumbel-softmax sample of the attention map (tvae_attn_softmax_pair; the fused step never
+        # materialises it)
+        _, a_sampled = TF.SoftmaxPairFn.apply(attn.reshape(B, -1), TF.gumbel_noise((B, heads.shape[2] * heads.shape[3]), heads.device))
+        return attn, a_sampled.view(B, heads.shape[2], heads.shape[3]), theta, z
 
 
 class InferenceNetwork_AttentionTranslation_AttentionRotation(nn.Module):
@@ -327,8 +331,8 @@ class InferenceNetwork_AttentionTranslation_AttentionRotation(nn.Module):
         p_r_list, offs_list = spec.tables()
         p_r = torch.tensor(p_r_list, dtype=torch.float32, device=heads.device).unsqueeze(1).unsqueeze(2)
         offsets = torch.tensor(offs_list, dtype=torch.float32, device=heads.device)
-        # module-interface tail (models.py:383-388): elementwise on the attention map; the fused training step
-        # (tvae_b200.elbo) never materialises these.
-        q_t_r = F.log_softmax(attn.reshape(B, -1), dim=1).view(attn.shape)
-        a_sampled = F.gumbel_softmax(attn.reshape(B, -1), dim=-1).view(attn.shape)
+        # module-interface tail (models.py:383-388): log_softmax and the Gumbel-softmax sample over all (r, t) cells in one
+        # kernel (tvae_attn_softmax_pair, backward tvae_attn_softmax_pair_bwd); the fused training step (tvae_b200.elbo)
+        # never materialises these.
+        q_t_r, a_sampled = TF.SoftmaxPairFn.apply(attn, TF.gumbel_noise((B, attn[0].numel()), heads.device))
         return attn, q_t_r, p_r, a_sampled, offsets, theta, z

@@ -271,6 +271,75 @@ class GeneratorFn(torch.autograd.Function):
         return (None, None, None, out["dxp"].view(s.B, s.N, 2), out["d_z"], *_gen_param_grads(out, s.L))
 
 
+# ------------------------------------------------------------------------------------------------ standalone module interfaces
+class FourierEmbedFn(torch.autograd.Function):
+    """RandomFourierEmbedding2d.forward (models.py:53-58): cos(x (W / sigma)^T + b) for x (..., 2)."""
+
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, x, weight, bias, sigma):
+        w = (ops.f32(weight) / torch.as_tensor(sigma, dtype=torch.float32, device=weight.device)).contiguous()
+        xc = ops.f32(x).reshape(-1, 2)
+        out = ops.fourier_embed_fwd(xc, w, ops.f32(bias))
+        ctx.save_for_backward(xc, w, ops.f32(bias))
+        ctx.xshape = x.shape
+        return out.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, w, b = ctx.saved_tensors
+        dx = ops.fourier_embed_bwd(xc, w, b, ops.f32(g).reshape(xc.shape[0], -1)) if ctx.needs_input_grad[0] else None
+        return (None if dx is None else dx.view(ctx.xshape)), None, None, None
+
+
+class LinearActFn(torch.autograd.Function):
+    """act(x W^T + b [+ x]) - ResidLinear.forward (models.py:29-30; the activation follows the residual add, so the layer is a
+    Linear with the effective weight W + I) on the tensor-core LinearNT / LinearTN kernels."""
+
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, x, weight, bias, resid, act):
+        xc = ops.f32(x).reshape(-1, x.shape[-1])
+        y, x16 = ops.linear_act_fwd(xc, ops.f32(weight), ops.f32(bias), resid, act)
+        ctx.save_for_backward(x16, ops.f32(weight), y)
+        ctx.resid, ctx.act, ctx.xshape = resid, act, x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x16, w, y = ctx.saved_tensors
+        dx, dw, db = ops.linear_act_bwd(x16, w, y, ops.f32(g).reshape(y.shape), ctx.resid, ctx.act, ctx.needs_input_grad[0])
+        return (None if dx is None else dx.view(ctx.xshape)), dw, db, None, None
+
+
+class SoftmaxPairFn(torch.autograd.Function):
+    """(q_t_r, a_sampled) = (log_softmax(attn), softmax(attn + gumbel)) over all (r, t) cells (models.py:383-388):
+    the module-interface tail of the encoders, one kernel forward, one backward."""
+
+    @staticmethod
+    @on_tensor_device
+    def forward(ctx, attn, gumbel):
+        B = attn.shape[0]
+        a2 = ops.f32(attn).reshape(B, 1, 1, -1)
+        q, a = ops.attn_softmax_pair(a2, ops.f32(gumbel).reshape(B, -1))
+        ctx.save_for_backward(q, a)
+        ctx.shape = attn.shape
+        return q.view(attn.shape), a.view(attn.shape)
+
+    @staticmethod
+    def backward(ctx, dq, da):
+        q, a = ctx.saved_tensors
+        B = q.shape[0]
+        d = ops.attn_softmax_pair_bwd(q, a, None if dq is None else ops.f32(dq).reshape(B, -1),
+                                      None if da is None else ops.f32(da).reshape(B, -1))
+        return d.view(ctx.shape), None
+
+
+def gumbel_noise(shape, device):
+    """the draw of F.gumbel_softmax (models.py:387): -log(Exp(1)) per cell, from torch's generator on the device"""
+    return -torch.empty(shape, device=device, dtype=torch.float32).exponential_().log()
+
+
 # ------------------------------------------------------------------------------------------------ fused step
 _spacing_cache: dict = {}      # id(tensor) -> (weakref to the tensor, its _version, spacing)
 

@@ -478,6 +478,70 @@ def gaussian_fit_noise(y_hat2, y, g=None):
     return ll, d
 
 
+# ----------------------------------------------------------------------------------------------- standalone module interfaces
+def _module_lib():
+    lib = L()
+    if not getattr(lib, "_tvae_module_configured", False):
+        ll, i, vp = ctypes.c_longlong, c_int, c_void_p
+        lib.tvae_fourier_embed_fwd.restype = c_int
+        lib.tvae_fourier_embed_fwd.argtypes = [vp, vp, vp, vp, ll, i, vp]
+        lib.tvae_fourier_embed_bwd.restype = c_int
+        lib.tvae_fourier_embed_bwd.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]
+        lib.tvae_linear_act_fwd.restype = c_int
+        lib.tvae_linear_act_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp]
+        lib.tvae_linear_act_bwd.restype = c_int
+        lib.tvae_linear_act_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+        lib.tvae_attn_softmax_pair_bwd.restype = c_int
+        lib.tvae_attn_softmax_pair_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
+        lib._tvae_module_configured = True
+    return lib
+
+
+def fourier_embed_fwd(x, w_scaled, b):
+    """RandomFourierEmbedding2d.forward: x (M,2) -> (M,E)."""
+    M, E = x.shape[0], w_scaled.shape[0]
+    out = empty(M, E, device=x.device)
+    check(_module_lib().tvae_fourier_embed_fwd(_p(x), _p(w_scaled), _p(b), _p(out), M, E, stream_ptr().value), "tvae_fourier_embed_fwd")
+    return out
+
+
+def fourier_embed_bwd(x, w_scaled, b, g):
+    M, E = x.shape[0], w_scaled.shape[0]
+    dx = empty(M, 2, device=x.device)
+    check(_module_lib().tvae_fourier_embed_bwd(_p(x), _p(w_scaled), _p(b), _p(g), _p(dx), M, E, stream_ptr().value), "tvae_fourier_embed_bwd")
+    return dx
+
+
+def linear_act_fwd(x, w, bias, resid, act):
+    """act(x W^T + b [+ x]) on the tensor-core LinearNT kernel -> (y (M,N) fp32, x16 saved for the backward)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = empty(M, N, device=x.device)
+    x16, w16 = half(M, K, device=x.device), half(N, K, device=x.device)
+    check(_module_lib().tvae_linear_act_fwd(_p(x), _p(w), _p(bias), M, N, K, int(resid), int(act), _p(y), _p(x16), _p(w16),
+                                            stream_ptr().value), "tvae_linear_act_fwd")
+    return y, x16
+
+
+def linear_act_bwd(x16, w, y, g, resid, act, need_dx=True):
+    M, K = x16.shape
+    N = w.shape[0]
+    dev = w.device
+    dx = empty(M, K, device=dev) if need_dx else None
+    dw, db = empty(N, K, device=dev), empty(N, device=dev)
+    dpre16, wt16, scales = half(M, N, device=dev), half(K, N, device=dev), empty(8, device=dev)
+    check(_module_lib().tvae_linear_act_bwd(_p(x16), _p(w), _p(y), _p(g), M, N, K, int(resid), int(act), _p(dpre16), _p(wt16), _p(scales),
+                                            _p(dx), _p(dw), _p(db), stream_ptr().value), "tvae_linear_act_bwd")
+    return dx, dw, db
+
+
+def attn_softmax_pair_bwd(q, a, dq, da):
+    B, Lr = q.shape
+    d = empty(B, Lr, device=q.device)
+    check(_module_lib().tvae_attn_softmax_pair_bwd(_p(q), _p(a), _p(dq), _p(da), _p(d), B, Lr, stream_ptr().value), "tvae_attn_softmax_pair_bwd")
+    return d
+
+
 # ----------------------------------------------------------------------------------------------- instrumentation
 def launch_count() -> int:
     return int(L().tvae_launch_count())
