@@ -24,19 +24,22 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    stamp = OUT + ".sha256"
+def build(force=False, verbose=False, probe=False):
+    """probe=True (or TVAE_PROBE=1 on the command line): the development build with the clock64 probes of tc_gemm2.cuh,
+    written next to the product library as libtvae_b200_probe.so (tools/probe_pair.py loads it through TVAE_LIB)."""
+    out = OUT.replace(".so", "_probe.so") if probe else OUT
+    stamp = out + ".sha256"
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return OUT
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(HERE, s) for s in SOURCES] + ["-o", OUT]
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + (["-DTVAE_PROBE"] if probe else [])
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(HERE, s) for s in SOURCES] + ["-o", out]
     subprocess.check_call(cmd, cwd=HERE)
     with open(stamp, "w") as f:
         f.write(dig)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probe=os.environ.get("TVAE_PROBE") == "1"))

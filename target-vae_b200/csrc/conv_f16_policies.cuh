@@ -35,6 +35,9 @@ struct Slab16Geom {
 };
 
 // slab[(c*rows_max + rr)*pitch + x] = fp16(image[c_lo + c][r_lo + rr - p][x - p]) (zero outside), written to both copies.
+// (A latency-oriented variant - 8-byte loads, eight in flight per warp, padding columns zeroed once - was measured and did not
+// shorten the kernels: the time the generator warps spend around a refill is the wait for the OTHER generator group at
+// the refill barrier, i.e. for the MMA issuer to free a stage, not the refill itself.)
 template <bool kBf16 = false>
 __device__ __forceinline__ void fill_slab16(uint32_t* slabw, const Slab16Geom& sg, const ConvGeom& g, const float* img, int c_lo,
                                             int nc, int r_lo, int rows, int tid, int nthreads) {
@@ -70,65 +73,146 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
 //     buffers, alternating) and one thread hands it to the TMA store unit - fully coalesced, asynchronous, and rows past
 //     the end of the image are clipped by the tensor map;
 //   * otherwise (fp32 output of GroupConv.forward alone, or O % 64 != 0) direct per-row stores.
-constexpr int kStoreBlockBytes = kBM * 128;     // one staging buffer: 128 rows x 64 halves
-struct Conv1EpiState { int blocks; };           // 64-column blocks stored so far by this CTA (selects the staging buffer)
+
+// NV (16 or 32) accumulator columns of one row: + add[0..NV) -> activation -> fp16 -> NV / 8 swizzled 16-byte chunks, starting at
+// chunk `chunk0` of the row's 128 bytes, of a staging buffer.  One warp per scheduler runs this, so it is written for
+// latency: the additive row of the NEXT 8 columns is loaded before the current 8 are stored (the compiler does not move a
+// shared-memory load above a shared-memory store), and LeakyReLU-or-identity is max(v, slope * v) without a branch.
+template <bool TANH, int NV>
+__device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const float* add, bool act, uint8_t* buf, int row, int chunk0) {
+    const float slope = act ? kLreluSlope : 1.f;
+    float4 b0 = *reinterpret_cast<const float4*>(add), b1 = *reinterpret_cast<const float4*>(add + 4);
+#pragma unroll
+    for (int j = 0; j < NV; j += 8) {
+        float4 n0 = b0, n1 = b1;
+        if (j + 8 < NV) {
+            n0 = *reinterpret_cast<const float4*>(add + j + 8);
+            n1 = *reinterpret_cast<const float4*>(add + j + 12);
+        }
+        float v[8];
+        v[0] = __uint_as_float(rr[j]) + b0.x;     v[1] = __uint_as_float(rr[j + 1]) + b0.y;
+        v[2] = __uint_as_float(rr[j + 2]) + b0.z; v[3] = __uint_as_float(rr[j + 3]) + b0.w;
+        v[4] = __uint_as_float(rr[j + 4]) + b1.x; v[5] = __uint_as_float(rr[j + 5]) + b1.y;
+        v[6] = __uint_as_float(rr[j + 6]) + b1.z; v[7] = __uint_as_float(rr[j + 7]) + b1.w;
+        if (TANH) {
+            if (act) act_vec<true>(v);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], slope * v[q]);
+        }
+        uint4 q4;
+        __half2 hv;
+        hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
+        hv = __floats2half2_rn(v[2], v[3]); q4.y = *reinterpret_cast<uint32_t*>(&hv);
+        hv = __floats2half2_rn(v[4], v[5]); q4.z = *reinterpret_cast<uint32_t*>(&hv);
+        hv = __floats2half2_rn(v[6], v[7]); q4.w = *reinterpret_cast<uint32_t*>(&hv);
+        *reinterpret_cast<uint4*>(buf + sw128_offset(row, chunk0 + (j >> 3))) = q4;
+        b0 = n0; b1 = n1;
+    }
+}
+
+// State of an epilogue that leaves through staged TMA stores (tc_gemm2's store issuer, warp 3)
+struct StagedEpiState {
+    uint32_t blocks;                    // 64-column blocks written so far by this CTA: buffer blocks % NBUF, use blocks / NBUF
+    uint32_t staged_bar, freed_bar;     // mbarrier arrays of the kernel
+    int sel;                            // policy scratch
+};
+
+// `nblk` 64-column blocks of one accumulator: value + add -> act -> fp16 -> swizzled staging buffer (ring of NBUF); the store
+// issuer warp hands each finished block to the TMA store unit.  The TMEM loads are software-pipelined in 32-column pieces
+// (the next piece is in flight while this one is converted).  Per block: wait until the store that last used the buffer
+// has read it (freed[b]), write, publish to the async proxy, one arrive per warp on staged[b].  No named barrier: a warp
+// never waits for the other epilogue warps, only for a free buffer.   add_ptr(blk) -> 64 floats (shared memory).
+template <bool TANH, int NBUF, int PROBE_SLOT, class AddPtr>
+__device__ __forceinline__ void staged_store_epilogue(uint32_t taddr, int nblk, StagedEpiState& st, uint8_t* stage0, int row, bool act,
+                                                      AddPtr add_ptr) {
+    if (nblk <= 0) return;
+    uint32_t ra[32], rb[32];
+#ifdef TVAE_PROBE
+    long long pr[6] = {0, 0, 0, 0, 0, 0}, pt = clock64(), pn;
+#define TVAE_EPI_LAP(i) pn = clock64(); pr[i] += pn - pt; pt = pn
+#else
+#define TVAE_EPI_LAP(i)
+#endif
+    tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+        const uint32_t b = st.blocks % NBUF, use = st.blocks / NBUF;
+        uint8_t* buf = stage0 + b * kStoreBlockBytes;
+        const float* add = add_ptr(blk);
+        tmem_ld_wait();
+        tmem_ld_32x32(taddr + blk * 64 + 32, rb);
+        TVAE_EPI_LAP(0);
+        if (use >= 1) mbar_wait(st.freed_bar + 8 * b, (use - 1) & 1);
+        TVAE_EPI_LAP(3);
+        epi_piece_store<TANH, 32>(ra, add, act, buf, row, 0);
+        TVAE_EPI_LAP(1);
+        tmem_ld_wait();
+        if (blk + 1 < nblk) tmem_ld_32x32(taddr + (blk + 1) * 64, ra);
+        TVAE_EPI_LAP(0);
+        epi_piece_store<TANH, 32>(rb, add + 32, act, buf, row, 4);
+        TVAE_EPI_LAP(1);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((row & 31) == 0) mbar_arrive(st.staged_bar + 8 * b);
+        TVAE_EPI_LAP(2);
+        ++st.blocks;
+    }
+#ifdef TVAE_PROBE
+    if (row == 0 && cluster_ctarank() == 0)
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_pair_probe[PROBE_SLOT][8 + i], (unsigned long long)pr[i]);
+#endif
+#undef TVAE_EPI_LAP
+}
+
+// Weight-gradient epilogue: `npieces` 32-column pieces of one accumulator, value * scale -> fp32 staging tile [32 columns][128
+// rows] (ring of NBUF 16 KB buffers) -> the store issuer adds the tile to global memory with ONE TMA reduce
+// (cp.reduce.async.bulk.tensor .add) instead of 4096 red.global.add.f32 issued by the SM: the atomics epilogue held the
+// accumulator 38 k clocks per tile at cfg2 (clock64 probe), 20 % of the conv1 weight-gradient kernel and 40 % at cfg1.
+// Rows / columns past the matrix are clipped by the tensor map.  Same buffer protocol as staged_store_epilogue.
+template <int NBUF>
+__device__ __forceinline__ void staged_reduce_epilogue(uint32_t taddr, int npieces, StagedEpiState& st, uint8_t* stage0, int row, float scale) {
+    if (npieces <= 0) return;
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(taddr, ra);
+    auto piece = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int c) {
+        const uint32_t b = st.blocks % NBUF, use = st.blocks / NBUF;
+        float* buf = reinterpret_cast<float*>(stage0 + b * kStoreBlockBytes);
+        tmem_ld_wait();
+        if (c + 1 < npieces) tmem_ld_32x32(taddr + (c + 1) * 32, nxt);
+        if (use >= 1) mbar_wait(st.freed_bar + 8 * b, (use - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) buf[j * kBM + row] = __uint_as_float(cur[j]) * scale;     // lanes = consecutive words: conflict-free
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((row & 31) == 0) mbar_arrive(st.staged_bar + 8 * b);
+        ++st.blocks;
+    };
+#pragma unroll 1
+    for (int c = 0; c < npieces; c += 2) {
+        piece(ra, rb, c);
+        if (c + 1 < npieces) piece(rb, ra, c + 1);
+    }
+}
+
+// 64-column blocks of the accumulator starting at column n0 that leave through staged TMA stores (uniform over the CTA)
+template <class Prm>
+__device__ __forceinline__ int conv1_store_blocks(const Prm& p, const PairTile& ti, int n0, bool has_work) {
+    if (!p.tma_store || !has_work || ti.m_tile < 0) return 0;
+    return min(kAccN / 64, (p.g.G * p.g.O - n0) / 64);
+}
 
 template <bool TANH, class Prm>
-__device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, Conv1EpiState& st, int n0, uint32_t taddr, int row,
+__device__ __forceinline__ void conv1_fwd_epilogue(const Prm& p, const PairTile& ti, StagedEpiState& st, int n0, uint32_t taddr, int row,
                                                    bool has_work, uint8_t* extra) {
     const ConvGeom& g = p.g;
     const int pos = ti.a1 + row;
     const int N = g.G * g.O;
     const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
     if (p.tma_store) {
-        const bool tile_ok = has_work && ti.m_tile >= 0;           // uniform over the CTA
-        uint8_t* stage0 = extra + p.stage_off;
-#pragma unroll 1
-        for (int blk = 0; blk < kAccN / 64; ++blk) {
-            const int np = n0 + blk * 64;
-            const bool blk_ok = tile_ok && np < N;                  // uniform
-            uint32_t rr[2][32];
-            tmem_ld_32x32(taddr + blk * 64, rr[0]);
-            tmem_ld_32x32(taddr + blk * 64 + 32, rr[1]);
-            tmem_ld_wait();
-            if (!blk_ok) continue;
-            uint8_t* buf = stage0 + (st.blocks & 1) * kStoreBlockBytes;
-            if (st.blocks >= 2) {                                   // the store that last used this buffer has read it
-                if (row == 0) tma_store_wait_read<1>();
-                named_bar_sync(2, kEpiWarps * 32);
-            }
-            const int r = np / g.O, o0 = np - r * g.O;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + o0 + hf * 32 + j + q);
-                        v[q] = __uint_as_float(rr[hf][j + q]) + bb.x;
-                        v[q + 1] = __uint_as_float(rr[hf][j + q + 1]) + bb.y;
-                        v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z;
-                        v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w;
-                    }
-                    if (p.act) act_vec<TANH>(v);
-                    uint4 q4;
-                    __half2 hv;
-                    hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
-                    hv = __floats2half2_rn(v[2], v[3]); q4.y = *reinterpret_cast<uint32_t*>(&hv);
-                    hv = __floats2half2_rn(v[4], v[5]); q4.z = *reinterpret_cast<uint32_t*>(&hv);
-                    hv = __floats2half2_rn(v[6], v[7]); q4.w = *reinterpret_cast<uint32_t*>(&hv);
-                    *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) = q4;
-                }
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(2, kEpiWarps * 32);
-            if (row == 0) {
-                tma_store_3d(&p.tmX, smem_u32(buf), o0, ti.a1, ti.a0 * g.G + r);
-                tma_store_commit();
-            }
-            ++st.blocks;
-        }
+        const int o_first = n0 % g.O;                               // O % 64 == 0: a block lies inside one rotation's O columns
+        staged_store_epilogue<TANH, 2, 1>(taddr, conv1_store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, p.act != 0,
+                                          [&](int blk) { int o = o_first + blk * 64; while (o >= g.O) o -= g.O; return s_bias + o; });
         return;
     }
     const bool ok = has_work && ti.m_tile >= 0 && pos < g.P;
@@ -191,6 +275,7 @@ struct Conv1FwdHParams {
 template <bool TANH>
 struct Conv1FwdHT : PolicyBase {
     static constexpr const char* kName = "conv1_fwd";
+    static constexpr int kProbeSlot = 1;
     using Params = Conv1FwdHParams;
     static constexpr bool kF16 = true;
     struct ChunkWalk {
@@ -208,10 +293,15 @@ struct Conv1FwdHT : PolicyBase {
         int base;                 // slab half-index of this thread's output cell
         ChunkWalk w;
     };
-    using EpiState = Conv1EpiState;
-    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; }
-    __device__ static void epi_finish(const Params& p, EpiState&, uint8_t*, int row) {
-        if (p.tma_store && row == 0) tma_store_wait<0>();      // staged stores have left shared memory before the CTA exits
+    using EpiState = StagedEpiState;
+    static constexpr int kStoreBufs = 2;      // staging buffers of the x1 stores (tc_gemm2's store issuer)
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; st.sel = 0; }
+    __device__ static int store_off(const Params& p) { return p.stage_off; }
+    __device__ static int store_blocks(const Params& p, const PairTile& ti, int n0, bool has_work) { return conv1_store_blocks(p, ti, n0, has_work); }
+    __device__ static void store_issue(const Params& p, const PairTile& ti, int n0, int blk, uint32_t src) {
+        const int np = n0 + blk * 64;
+        const int r = np / p.g.O;
+        tma_store_3d(&p.tmX, src, np - r * p.g.O, ti.a1, ti.a0 * p.g.G + r);
     }
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmB);
@@ -380,15 +470,19 @@ struct Conv1WgradHParams {
     const float* y;
     float* dbank;             // [G*O][kpad] fp32, zero-filled by the caller
     const float* acc_scale;   // device scalar: 1 / (scale dX1 was stored with)
+    CUtensorMap tmD;          // dbank as [G*O][K] fp32 (pitch kpad): target of the epilogue's TMA reduce-adds (tma_reduce == 1)
+    int tma_reduce, stage_off;   // stage_off: byte offset of the two fp32 staging tiles in the extra smem
     int quad;                 // 1: offset table per 4-tap quad, 0: per tap
     int skip;                 // 1: skip position chunks that only meet zero padding
 };
 
 // B128 = true (O % 64 == 0): dX1 is staged in 64-column blocks with the 128 B swizzle (tmQ from make_tmap_3d_mn128_h, p.nb
 // counts 64-column blocks per box); false: 32-column blocks / 64 B swizzle.
-template <bool B128>
+// NB = staging tiles of the TMA-reduce epilogue: 2, or 1 where the second would cost a pipeline stage (cfg4 / cfg5 slabs).
+template <bool B128, int NB = 2>
 struct Conv1WgradHT : PolicyBase {
     static constexpr const char* kName = "conv1_wgrad";
+    static constexpr int kProbeSlot = 2;
     static constexpr bool kBSw128MN = B128;
     static constexpr int kBlkCols = B128 ? 64 : 32;            // columns per staged block
     static constexpr int kBoxes = 128 / kBlkCols;              // blocks per 128-column accumulator half
@@ -596,11 +690,28 @@ struct Conv1WgradHT : PolicyBase {
             }
         }
     }
-    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState&, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
+    using EpiState = StagedEpiState;
+    static constexpr int kStoreBufs = NB;
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; st.sel = 0; }
+    __device__ static int store_off(const Params& p) { return p.stage_off; }
+    // 32-column pieces of the accumulator starting at column n0 that leave through TMA reduce-adds (uniform over the CTA)
+    __device__ static int store_blocks(const Params& p, const PairTile& ti, int n0, bool has_work) {
+        if (!p.tma_reduce || !has_work || ti.m_tile < 0) return 0;
+        return min(kAccN / 32, (p.g.G * p.g.O - n0 + 31) / 32);
+    }
+    __device__ static void store_issue(const Params& p, const PairTile& ti, int n0, int blk, uint32_t src) {
+        tma_reduce_add_2d(&p.tmD, src, ti.a0, n0 + blk * 32);
+    }
+    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
+                                    uint8_t* extra) {
+        if (p.tma_reduce) {
+            staged_reduce_epilogue<NB>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, __ldg(p.acc_scale));
+            return;
+        }
         const ConvGeom& g = p.g;
         const int kk = ti.a0 + row;
         const int N = g.G * g.O;
-        const bool ok = has_work && ti.m_tile >= 0 && kk < g.K;
+        const bool ok = has_work && ti.m_tile >= 0 && kk < g.K;      // per thread: the warp-collective TMEM loads stay unconditional
         const float acc_scale = __ldg(p.acc_scale);
 #pragma unroll 1
         for (int c = 0; c < kAccN / 32; ++c) {
@@ -620,5 +731,7 @@ struct Conv1WgradHT : PolicyBase {
 
 using Conv1WgradH = Conv1WgradHT<false>;
 using Conv1WgradH128 = Conv1WgradHT<true>;
+using Conv1WgradH_1 = Conv1WgradHT<false, 1>;
+using Conv1WgradH128_1 = Conv1WgradHT<true, 1>;
 
 }  // namespace tvae

@@ -28,10 +28,13 @@ struct GenL1WgradPairParams {
     int E, H;
     float* dW1;               // [H][E], zero-filled by the caller
     const float* acc_scale;   // device scalar: 1 / (scale dpre was stored with)
+    CUtensorMap tmD;          // dW1 as [H][E] fp32: target of the epilogue's TMA reduce-adds (tma_reduce == 1)
+    int tma_reduce, stage_off;   // stage_off: byte offset of the two fp32 staging tiles in the extra smem
 };
 
 struct GenL1WgradPair : PolicyBase {
     static constexpr const char* kName = "gen_l1_wgrad";
+    static constexpr int kProbeSlot = 4;
     using Params = GenL1WgradPairParams;
     static constexpr bool kF16 = true;
     static constexpr bool kAMajorMN = true;
@@ -41,6 +44,8 @@ struct GenL1WgradPair : PolicyBase {
         int q;                // current chunk
         int b;                // image whose rotation / shift are cached (-1: none)
         float cs, sn, dx0, dx1;
+        int pq, pb;           // prefetched coordinate: chunk it belongs to (-1: none), its image
+        float2 pv;
     };
     __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmQ); }
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
@@ -70,32 +75,53 @@ struct GenL1WgradPair : PolicyBase {
             if (a < ti.n_acc) tma_load_3d_pair(sb + a * kBHalfBytes, &p.tmQ, bar, 0, s.row0, s.jblk[a]);
         s.row0 += kBKh;
     }
-    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.q = 0; s.b = -1; s.cs = 1.f; s.sn = 0.f; s.dx0 = 0.f; s.dx1 = 0.f; }
-    __device__ static void gen_tile_begin(const Params&, const PairTile& ti, GenState& s, uint8_t*, int) { s.q = ti.kc_begin; }
+    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) {
+        s.q = 0; s.b = -1; s.cs = 1.f; s.sn = 0.f; s.dx0 = 0.f; s.dx1 = 0.f; s.pq = -1; s.pb = 0; s.pv = make_float2(0.f, 0.f);
+    }
+    __device__ static void gen_tile_begin(const Params&, const PairTile& ti, GenState& s, uint8_t*, int) { s.q = ti.kc_begin; s.pq = -1; }
     __device__ static void gen_prepare(const Params&, const PairTile&, GenState&, uint8_t*, int) {}
     __device__ static void gen_advance(const Params&, const PairTile&, GenState& s) { ++s.q; }
     // one group (128 threads) fills a stage: thread = (pixel row of the chunk, 64-feature block): 64 cosines, 8 swizzled
     // 16-byte stores.  The 8 lanes of a store phase write the same 16-byte column of 8 consecutive rows = 8 distinct
     // slots of the 128 B swizzle.
+    // raw coordinate of pixel row m and its image (32-bit division: M < 2^31 is checked by the host)
+    __device__ static void load_coord(const Params& p, long long m, float2& v, int& b) {
+        if (p.cx.theta == nullptr) {
+            v = __ldg(reinterpret_cast<const float2*>(p.cx.x) + m);
+            b = 0;
+        } else {
+            const unsigned mm = static_cast<unsigned>(m), N = static_cast<unsigned>(p.cx.N);
+            b = static_cast<int>(mm / N);
+            v = __ldg(reinterpret_cast<const float2*>(p.cx.x) + (mm - static_cast<unsigned>(b) * N));
+        }
+    }
     __device__ static void gen_chunk(const Params& p, const PairTile& ti, GenState& s, uint8_t* a_stage, uint8_t* extra, int gtid) {
         const float4* tab = reinterpret_cast<const float4*>(extra);
         const int prow = gtid & 63, blk = gtid >> 6;
         const long long m = (long long)s.q * kBKh + prow;
         const bool ok = ti.m_tile >= 0 && m < p.cx.M;
         float x0 = 0.f, x1 = 0.f;
+        // The pixel's coordinate was loaded while the group's PREVIOUS chunk was generated (a group owns every other chunk:
+        // + 2); the load for the next one is issued now and lands during this chunk's 64 cosines.  Without it every chunk began
+        // with an exposed global-load round trip on the warps that pace this kernel.
+        float2 v = s.pv;
+        int b = s.pb;
+        if (s.pq != s.q) { if (ok) load_coord(p, m, v, b); }
+        {
+            const long long mn = m + 2 * kBKh;
+            s.pq = s.q + 2;
+            if (ti.m_tile >= 0 && s.q + 2 < ti.kc_end && mn < p.cx.M) load_coord(p, mn, s.pv, s.pb);
+            else s.pq = -1;
+        }
         if (ok) {
             if (p.cx.theta == nullptr) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(p.cx.x) + m);
                 x0 = v.x; x1 = v.y;
             } else {
-                const int b = static_cast<int>(m / p.cx.N);
-                const int px = static_cast<int>(m - (long long)b * p.cx.N);
                 if (b != s.b) {                                   // rotation / shift of the image, cached across chunks
                     const float2 d = __ldg(reinterpret_cast<const float2*>(p.cx.dx) + b);
                     sincosf(__ldg(p.cx.theta + b), &s.sn, &s.cs);
                     s.dx0 = d.x; s.dx1 = d.y; s.b = b;
                 }
-                const float2 v = __ldg(reinterpret_cast<const float2*>(p.cx.x) + px);
                 const float t0 = v.x - s.dx0, t1 = v.y - s.dx1;
                 x0 = t0 * s.cs - t1 * s.sn;                        // x' = (x - dx) [[cos, sin], [-sin, cos]]  (train_mnist.py:234-239)
                 x1 = t0 * s.sn + t1 * s.cs;
@@ -103,6 +129,17 @@ struct GenL1WgradPair : PolicyBase {
         }
         const int f0 = ti.a0 + blk * 64;
         uint8_t* dst = a_stage + blk * (kBKh * 128);
+        if (ok && f0 + 64 <= p.E) {                                // whole block of live features: no per-feature predicates
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = __cosf(fourier_phase(tab[f0 + ch * 8 + q], x0, x1));
+                *reinterpret_cast<uint4*>(dst + sw128_offset(prow, ch)) =
+                    make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+            }
+            return;
+        }
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
             float e[8];
@@ -115,7 +152,23 @@ struct GenL1WgradPair : PolicyBase {
                 make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
         }
     }
-    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState&, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
+    using EpiState = StagedEpiState;
+    static constexpr int kStoreBufs = 2;
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; st.sel = 0; }
+    __device__ static int store_off(const Params& p) { return p.stage_off; }
+    __device__ static int store_blocks(const Params& p, const PairTile& ti, int n0, bool has_work) {
+        if (!p.tma_reduce || !has_work || ti.m_tile < 0) return 0;
+        return min(kAccN / 32, (p.H - n0 + 31) / 32);
+    }
+    __device__ static void store_issue(const Params& p, const PairTile& ti, int n0, int blk, uint32_t src) {
+        tma_reduce_add_2d(&p.tmD, src, ti.a0, n0 + blk * 32);
+    }
+    __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
+                                    uint8_t* extra) {
+        if (p.tma_reduce) {
+            staged_reduce_epilogue<2>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, __ldg(p.acc_scale));
+            return;
+        }
         const int f = ti.a0 + row;
         const bool ok = has_work && ti.m_tile >= 0 && f < p.E;
         const float acc_scale = __ldg(p.acc_scale);
@@ -147,7 +200,7 @@ struct GenL1FwdPairParams {
     CUtensorMap tmB;          // W1 fp16 [H][E], boxes {64 f, 128 rows}
     CUtensorMap tmC;          // h1 fp16 [M][H] store view, boxes {64, 128 rows}
     int num_stages, num_tiles, m_tiles, k_chunks;
-    int bias_off, stage_off;  // byte offsets in the extra smem: [H] b1 floats, 2 staging buffers of 16 KB
+    int bias_off, tab_off, stage_off;  // byte offsets in the extra smem: [H] b1 floats, [2][H] per-tile additive rows, 3 staging buffers of 16 KB
     CoordXform cx;
     const float* wf_scaled; const float* bf;
     int E, H;
@@ -159,11 +212,13 @@ struct GenL1FwdPairParams {
 template <bool TANH>
 struct GenL1FwdPairT : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
+    static constexpr int kProbeSlot = 3;
     using Params = GenL1FwdPairParams;
     static constexpr bool kF16 = true;
     struct TmaState { int kc, n_row0; };
     struct GenState { float x0, x1; int kc; };
-    struct EpiState { int blocks; };
+    using EpiState = StagedEpiState;
+    static constexpr int kStoreBufs = 3;      // staging buffers of the h1 stores (tc_gemm2's store issuer)
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmC);
@@ -173,9 +228,13 @@ struct GenL1FwdPairT : PolicyBase {
         float* s_bias = reinterpret_cast<float*>(extra + p.bias_off);
         for (int j = tid; j < p.H; j += nthreads) s_bias[j] = __ldg(p.bias + j);
     }
-    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; }
-    __device__ static void epi_finish(const Params&, EpiState&, uint8_t*, int row) {
-        if (row == 0) tma_store_wait<0>();
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; st.sel = 0; }
+    __device__ static int store_off(const Params& p) { return p.stage_off; }
+    __device__ static int store_blocks(const Params& p, const PairTile& ti, int n0, bool has_work) {
+        return (has_work && ti.m_tile >= 0) ? min(kAccN / 64, (p.H - n0) / 64) : 0;
+    }
+    __device__ static void store_issue(const Params& p, const PairTile& ti, int n0, int blk, uint32_t src) {
+        tma_store_2d(&p.tmC, src, n0 + blk * 64, ti.a0);
     }
     __device__ static void tile_info(const Params& p, int tile, uint32_t rank, PairTile& ti) {
         ti.n0 = 0;
@@ -209,6 +268,19 @@ struct GenL1FwdPairT : PolicyBase {
         const int row = gtid;
         const bool live = ti.m_tile >= 0;
         const int f0 = s.kc * kBKh;
+        if (live && f0 + kBKh <= p.E) {
+            // whole chunk of live features (E % 64 == 0 in every reference configuration): no per-feature predicates - they
+            // were 4 of the 10 instructions per feature on the warps that pace this kernel
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = __cosf(fourier_phase(tab[f0 + ch * 8 + q], s.x0, s.x1));
+                *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, ch)) =
+                    make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+            }
+            return;
+        }
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
             float e[8];
@@ -221,57 +293,33 @@ struct GenL1FwdPairT : PolicyBase {
                 make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
         }
     }
-    // 64-column blocks: bias + latent bias + LeakyReLU -> fp16 -> staging buffer (two, alternating) -> TMA store;
-    // rows past M are clipped by the tensor map.  Control flow is uniform over the 128 epilogue threads.
+    // Per tile, while its MMAs run: the additive row of the epilogue, b1 + latent bias of the image, once per image the
+    // tile's 128 rows can belong to (N >= 128 pixels per image: at most two).  The epilogue then reads shared memory only -
+    // the per-row global loads of the latent bias were the larger half of a latency-bound epilogue.
+    __device__ static void epi_tile_begin(const Params& p, const PairTile& ti, EpiState& st, uint8_t* extra, int row) {
+        st.sel = 0;
+        if (ti.m_tile < 0) return;                              // uniform over the CTA
+        float* tab = reinterpret_cast<float*>(extra + p.tab_off);
+        const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
+        const long long m_first = ti.a0, m_last = min((long long)ti.a0 + kBM - 1, p.cx.M - 1);
+        const int b_lo = static_cast<int>(m_first / p.cx.N), b_hi = static_cast<int>(m_last / p.cx.N);
+        const long long m = min((long long)ti.a0 + row, p.cx.M - 1);
+        st.sel = (m >= (long long)b_hi * p.cx.N && b_hi != b_lo) ? 1 : 0;
+        named_bar_sync(2, kEpiWarps * 32);                      // every warp's table reads of the previous tile are done
+        for (int j = row; j < 2 * p.H; j += kEpiWarps * 32) {
+            const int which = j >= p.H, jj = j - which * p.H;
+            const int b = which ? b_hi : b_lo;
+            tab[j] = s_bias[jj] + (p.zb ? __ldg(p.zb + (long long)b * p.H + jj) : 0.f);
+        }
+        named_bar_sync(2, kEpiWarps * 32);
+    }
+    // 64-column blocks: + (b1 + latent bias) + activation -> fp16 -> staging buffer (ring of three) -> TMA store by the store
+    // issuer warp (staged_store_epilogue); rows past M are clipped by the tensor map.
     __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
                                     uint8_t* extra) {
-        const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
-        const bool tile_ok = has_work && ti.m_tile >= 0;
-        const long long m = (long long)ti.a0 + row;
-        const float* zb = (p.zb && tile_ok && m < p.cx.M) ? p.zb + (m / p.cx.N) * p.H : nullptr;
-        uint8_t* stage0 = extra + p.stage_off;
-#pragma unroll 1
-        for (int blk = 0; blk < kAccN / 64; ++blk) {
-            const int j0 = n0 + blk * 64;
-            const bool blk_ok = tile_ok && j0 < p.H;                // uniform
-            uint32_t rr[2][32];
-            tmem_ld_32x32(taddr + blk * 64, rr[0]);
-            tmem_ld_32x32(taddr + blk * 64 + 32, rr[1]);
-            tmem_ld_wait();
-            if (!blk_ok) continue;
-            uint8_t* buf = stage0 + (st.blocks & 1) * kStoreBlockBytes;
-            if (st.blocks >= 2) {                                   // the store that last used this buffer has read it
-                if (row == 0) tma_store_wait_read<1>();
-                named_bar_sync(2, kEpiWarps * 32);
-            }
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q += 4) {
-                        const int jj = j0 + hf * 32 + j + q;
-                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + jj);
-                        const float4 bz = zb ? __ldg(reinterpret_cast<const float4*>(zb + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[q] = __uint_as_float(rr[hf][j + q]) + bb.x + bz.x;
-                        v[q + 1] = __uint_as_float(rr[hf][j + q + 1]) + bb.y + bz.y;
-                        v[q + 2] = __uint_as_float(rr[hf][j + q + 2]) + bb.z + bz.z;
-                        v[q + 3] = __uint_as_float(rr[hf][j + q + 3]) + bb.w + bz.w;
-                    }
-                    act_vec<TANH>(v);
-                    *reinterpret_cast<uint4*>(buf + sw128_offset(row, hf * 4 + (j >> 3))) =
-                        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-                }
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(2, kEpiWarps * 32);
-            if (row == 0) {
-                tma_store_2d(&p.tmC, smem_u32(buf), j0, ti.a0);
-                tma_store_commit();
-            }
-            ++st.blocks;
-        }
+        const float* tab = reinterpret_cast<const float*>(extra + p.tab_off) + st.sel * p.H;
+        staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
+                                          [&](int blk) { return tab + n0 + blk * 64; });
     }
 };
 using GenL1FwdPair = GenL1FwdPairT<false>;

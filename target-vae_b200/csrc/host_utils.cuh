@@ -133,6 +133,22 @@ inline int make_tmap_3d_store_h(CUtensorMap* tm, void* ptr, uint64_t outer, uint
     return 0;
 }
 
+// fp32 matrix [rows][cols] (row pitch ld elements) as the target of TMA reduce-adds: boxes {128 cols, 32 rows}, no swizzle;
+// the box is clipped at (cols, rows).  Returns 1 (not an error) when the matrix does not meet TMA's alignment rules.
+inline int make_tmap_2d_f32_reduce(CUtensorMap* tm, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15)) return 1;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {128, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (fp32 reduce target) failed with code " + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // ---- optional per-kernel timing (bench.py): CUDA events recorded around every tc_gemm launch on its own stream
 struct KernelTimer {
     static constexpr int kMaxNames = 48;

@@ -33,6 +33,7 @@ struct LinearTNPairParams {
 
 struct LinearTNPair : PolicyBase {
     static constexpr const char* kName = "linear_tn";
+    static constexpr int kProbeSlot = 5;
     using Params = LinearTNPairParams;
     static constexpr bool kF16 = true;
     static constexpr bool kAMajorMN = true;
@@ -93,6 +94,8 @@ struct LinearTNPair : PolicyBase {
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(dst + sw128_offset(prow, ch)) = v[ch];
     }
+    // fp32 atomics: the epilogue is 3-10 % of this kernel (the generator warps bound it); TMA reduce-adds (measured) made it
+    // 4-12 % slower - the reduces share the TMA unit with the operand loads the kernel is starved for
     __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState&, int n0, uint32_t taddr, int row, bool has_work, uint8_t*) {
         const int j = ti.a0 + row;
         const bool ok = has_work && ti.m_tile >= 0 && j < p.Ma;

@@ -250,11 +250,14 @@ struct PolicyBase {
     static constexpr bool kEpiSelfRelease = false;   // tc_gemm: the policy's epilogue arrives on EpiState::tempty itself
     static constexpr uint32_t kAFmt = 0;      // operand formats of kind::f16: 0 = FP16, 1 = BF16 (both operands must agree)
     static constexpr uint32_t kBFmt = 0;
+    static constexpr int kProbeSlot = 0;      // tc_gemm2, -DTVAE_PROBE builds: row of the probe counters this policy adds to
     struct EpiState {};
     struct GenState {};
     template <class Prm> __device__ static void setup(const Prm&, uint8_t*, int, int) {}
     template <class Prm, class St> __device__ static void epi_init(const Prm&, St&, uint8_t*, int) {}
     template <class Prm, class St> __device__ static void epi_finish(const Prm&, St&, uint8_t*, int) {}
+    template <class Prm, class Ti, class St> __device__ static void epi_tile_begin(const Prm&, const Ti&, St&, uint8_t*, int) {}   // tc_gemm2
+    static constexpr int kStoreBufs = 0;      // tc_gemm2: > 0 = the epilogue leaves through that many staging buffers and the store issuer warp
     template <class Prm, class St> __device__ static void gen_init(const Prm&, St&, uint8_t*, int) {}
     template <class Prm, class St> __device__ static void gen_tile_begin(const Prm&, const TileInfo&, St&, uint8_t*, int) {}
     template <class Prm, class St> __device__ static void gen_chunk(const Prm&, const TileInfo&, St&, int, uint8_t*, uint8_t*, int) {}

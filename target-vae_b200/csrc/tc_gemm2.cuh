@@ -12,6 +12,11 @@
 //   warp 0      TMA producer: this CTA's half of the B tile, complete_tx on the LEADER's full barrier
 //   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M = 256, N = 256
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, same warp in both CTAs)
+//   warp 3      store issuer (policies with kStoreBufs > 0): hands the epilogue's staged fp16 blocks to the TMA store unit.
+//               Issuing a bulk-tensor store costs the issuing thread 250-800 clocks (clock64 probe, tools/probe_pair.py);
+//               on an epilogue warp that sat on the critical path of every 64-column block (16 % of the epilogue, plus a
+//               named barrier per block).  The epilogue warps and this warp meet at mbarriers instead: staged[b] (one
+//               arrive per epilogue warp: block written) and freed[b] (the store that used buffer b has read it).
 //   warps 4-7   epilogue: tcgen05.ld of this CTA's 128 accumulator rows -> policy epilogue
 //   warps 8-15  operand generators: synthesise this CTA's 128 A rows straight into swizzled smem (two groups
 //               of 4 warps, alternate stages)
@@ -29,6 +34,8 @@ constexpr int kAcc = 2;                 // accumulators per CTA (N = 256 each)
 constexpr int kAccN = 256;
 constexpr int kBHalfBytes = 128 * 128;  // this CTA's half of one accumulator's B stage
 constexpr int kStage2Bytes = kAStageBytes + kAcc * kBHalfBytes;   // 48 KB
+constexpr int kMaxStoreBufs = 4;        // staging buffers of the epilogue's TMA stores (policy: kStoreBufs)
+constexpr int kStoreBlockBytes = kBM * 128;     // one staging buffer: 128 rows x 64 halves
 
 // ---------------------------------------------------------------- cluster / pair PTX
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -87,6 +94,19 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
                  : "memory");
 }
 
+// Development probe (-DTVAE_PROBE, csrc/build.py with TVAE_PROBE=1 -> libtvae_b200_probe.so; never part of the product
+// library): clock64() spent by the leader's MMA issuer waiting for a drained accumulator / for operand stages, by epilogue
+// thread 0 inside the policy epilogue, by generator thread 0 waiting for free stages / generating, summed over the pairs.
+// counters (8-13: segments of staged_store_epilogue, epilogue thread 0): 0 mma total, 1 mma wait tempty, 2 mma wait full, 3 epi wait tfull, 4 epi epilogue, 5 gen wait empty, 6 gen chunk, 7 #pairs
+#ifdef TVAE_PROBE
+__device__ unsigned long long g_pair_probe[8][16];      // [P::kProbeSlot][counter]
+#define TVAE_PROBE_T0() const long long probe_t0 = clock64()
+#define TVAE_PROBE_ADD(var) var += clock64() - probe_t0
+#else
+#define TVAE_PROBE_T0()
+#define TVAE_PROBE_ADD(var)
+#endif
+
 struct PairTile {
     int n0;              // first accumulator column of the pair-tile
     int n_acc;           // accumulators in use (1 or 2)
@@ -102,7 +122,7 @@ __host__ __device__ inline Smem2Layout make_smem2_layout(int stages, int extra_b
     Smem2Layout L;
     L.stage_off = 0;
     L.bar_off = stages * kStage2Bytes;
-    L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 2) * 8;
+    L.tmem_ptr_off = L.bar_off + (2 * kMaxStages + 2 + 2 * kMaxStoreBufs) * 8;
     L.extra_off = (L.tmem_ptr_off + 16 + 1023) & ~1023u;   // policies may keep 128 B-swizzled tiles in their extra region
     L.total = L.extra_off + extra_bytes;
     return L;
@@ -125,6 +145,8 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
     const uint32_t empty_bar = smem_u32(bars + kMaxStages);          // [stages]   (each CTA)
     const uint32_t tfull_bar = smem_u32(bars + 2 * kMaxStages);      // each CTA
     const uint32_t tempty_bar = smem_u32(bars + 2 * kMaxStages + 1); // leader
+    const uint32_t staged_bar = smem_u32(bars + 2 * kMaxStages + 2); // [kMaxStoreBufs] each CTA: epilogue warps -> store issuer
+    const uint32_t freed_bar = staged_bar + 8 * kMaxStoreBufs;       // [kMaxStoreBufs] each CTA: store issuer -> epilogue warps
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,6 +161,10 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         }
         mbar_init(tfull_bar, 1);
         mbar_init(tempty_bar, 2 * kEpiWarps);
+        for (int b = 0; b < kMaxStoreBufs; ++b) {
+            mbar_init(staged_bar + 8 * b, kEpiWarps);
+            mbar_init(freed_bar + 8 * b, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -186,13 +212,17 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         if (leader && lane == 0) {
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
+#ifdef TVAE_PROBE
+            long long pr_tempty = 0, pr_full = 0;
+            const long long pr_begin = clock64();
+#endif
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 PairTile ti;
                 P::tile_info(prm, tile, rank, ti);
-                mbar_wait(tempty_bar, tphase ^ 1);
+                { TVAE_PROBE_T0(); mbar_wait(tempty_bar, tphase ^ 1); TVAE_PROBE_ADD(pr_tempty); }
                 tc_fence_after();
                 for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
-                    mbar_wait(full_bar + 8 * stage, phase);
+                    { TVAE_PROBE_T0(); mbar_wait(full_bar + 8 * stage, phase); TVAE_PROBE_ADD(pr_full); }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + L.stage_off + stage * kStage2Bytes);
                     const uint32_t b_addr = a_addr + kAStageBytes;
@@ -217,6 +247,56 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                 umma_commit_pair(tfull_bar, 3);                   // accumulators complete -> both epilogues
                 tphase ^= 1;
             }
+#ifdef TVAE_PROBE
+            atomicAdd(&g_pair_probe[P::kProbeSlot][0], (unsigned long long)(clock64() - pr_begin));
+            atomicAdd(&g_pair_probe[P::kProbeSlot][1], (unsigned long long)pr_tempty);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][2], (unsigned long long)pr_full);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][7], 1ull);
+#endif
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ store issuer (both CTAs)
+        if constexpr (P::kStoreBufs > 0) {
+            if (lane == 0) {
+                constexpr int NB = P::kStoreBufs;
+                uint32_t cnt = 0;                                  // 64-column blocks stored so far: buffer cnt % NB, use cnt / NB
+#ifdef TVAE_PROBE
+                long long pr_st[3] = {0, 0, 0};
+#endif
+                for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+                    PairTile ti;
+                    P::tile_info(prm, tile, rank, ti);
+                    const bool has_work = ti.kc_end > ti.kc_begin;
+                    for (int a = 0; a < ti.n_acc; ++a) {
+                        const int n0 = ti.n0 + a * kAccN;
+                        const int nblk = P::store_blocks(prm, ti, n0, has_work);
+                        for (int blk = 0; blk < nblk; ++blk, ++cnt) {
+                            const uint32_t b = cnt % NB;
+                            // Free the NEXT block's buffer first: all but the NB - 2 youngest stores have read their
+                            // buffers, the oldest of them (NB - 1 back) used the buffer of block cnt + 1.  Doing this
+                            // before waiting for block cnt keeps the writers from running in lockstep with this thread.
+                            if constexpr (NB >= 2) {
+                                { TVAE_PROBE_T0(); tma_store_wait_read<(NB >= 2 ? NB - 2 : 0)>(); TVAE_PROBE_ADD(pr_st[2]); }
+                                if (cnt + 1 >= NB) mbar_arrive(freed_bar + 8 * ((cnt + 1) % NB));
+                            }
+                            { TVAE_PROBE_T0(); mbar_wait(staged_bar + 8 * b, (cnt / NB) & 1); TVAE_PROBE_ADD(pr_st[0]); }
+                            { TVAE_PROBE_T0();
+                            P::store_issue(prm, ti, n0, blk, smem_u32(extra + P::store_off(prm) + b * kStoreBlockBytes));
+                            tma_store_commit();
+                            TVAE_PROBE_ADD(pr_st[1]); }
+                            if constexpr (NB == 1) {                // a single buffer: the writers wait for this very store
+                                tma_store_wait_read<0>();
+                                mbar_arrive(freed_bar);
+                            }
+                        }
+                    }
+                }
+#ifdef TVAE_PROBE
+                if (leader) for (int i = 0; i < 3; ++i) atomicAdd(&g_pair_probe[P::kProbeSlot == 1 ? 6 : 7][i], (unsigned long long)pr_st[i]);
+                if (leader) atomicAdd(&g_pair_probe[P::kProbeSlot == 1 ? 6 : 7][3], (unsigned long long)cnt);
+#endif
+                tma_store_wait<0>();                               // staged stores have left shared memory before the CTA exits
+            }
         }
     } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
         // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
@@ -226,22 +306,35 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
         typename P::EpiState est;
         P::epi_init(prm, est, extra, row);
+        if constexpr (P::kStoreBufs > 0) { est.staged_bar = staged_bar; est.freed_bar = freed_bar; }
+#ifdef TVAE_PROBE
+        long long pr_tfull = 0, pr_epi = 0;
+#endif
         for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
             PairTile ti;
             P::tile_info(prm, tile, rank, ti);
-            mbar_wait(tfull_bar, tphase);
+            P::epi_tile_begin(prm, ti, est, extra, row);     // per-tile tables, built while the tile's MMAs run
+            { TVAE_PROBE_T0(); mbar_wait(tfull_bar, tphase); TVAE_PROBE_ADD(pr_tfull); }
             tc_fence_after();
             const bool has_work = ti.kc_end > ti.kc_begin;
+            TVAE_PROBE_T0();
             for (int a = 0; a < ti.n_acc; ++a) {
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + a * kAccN;
                 P::epilogue(prm, ti, est, ti.n0 + a * kAccN, taddr, row, has_work, extra);
             }
+            TVAE_PROBE_ADD(pr_epi);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader);
             tphase ^= 1;
         }
         P::epi_finish(prm, est, extra, row);
+#ifdef TVAE_PROBE
+        if (leader && row == 0) {
+            atomicAdd(&g_pair_probe[P::kProbeSlot][3], (unsigned long long)pr_tfull);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][4], (unsigned long long)pr_epi);
+        }
+#endif
     } else if (warp >= kFirstProdWarp) {
         // ------------------------------------------------------------ operand generators (both CTAs)
         // Two groups of 4 warps fill alternate stages: the fixed per-stage latencies (barrier wait, smem round trips,
@@ -254,23 +347,36 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
         const uint32_t full_leader = mapa_rank(full_bar, 0);
         typename P::GenState gst;
         P::gen_init(prm, gst, extra, ptid);
+#ifdef TVAE_PROBE
+        long long pr_empty = 0, pr_gen = 0, pr_gtb = 0, pr_gprep = 0;
+#endif
         for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
             PairTile ti;
             P::tile_info(prm, tile, rank, ti);
-            P::gen_tile_begin(prm, ti, gst, extra, ptid);
+            { TVAE_PROBE_T0(); P::gen_tile_begin(prm, ti, gst, extra, ptid); TVAE_PROBE_ADD(pr_gtb); }
             for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
-                P::gen_prepare(prm, ti, gst, extra, ptid);
+                { TVAE_PROBE_T0(); P::gen_prepare(prm, ti, gst, extra, ptid); TVAE_PROBE_ADD(pr_gprep); }
                 if (((q - ti.kc_begin) & 1) == grp) {
-                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    { TVAE_PROBE_T0(); mbar_wait(empty_bar + 8 * stage, phase ^ 1); TVAE_PROBE_ADD(pr_empty); }
+                    TVAE_PROBE_T0();
                     P::gen_chunk(prm, ti, gst, smem + L.stage_off + stage * kStage2Bytes, extra, gtid);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(full_leader + 8 * stage);
+                    TVAE_PROBE_ADD(pr_gen);
                 }
                 P::gen_advance(prm, ti, gst);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
+#ifdef TVAE_PROBE
+        if (leader && ptid == 0) {                             // generator thread 0 (group 0: every other chunk)
+            atomicAdd(&g_pair_probe[P::kProbeSlot][5], (unsigned long long)pr_empty);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][6], (unsigned long long)pr_gen);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][14], (unsigned long long)pr_gtb);
+            atomicAdd(&g_pair_probe[P::kProbeSlot][15], (unsigned long long)pr_gprep);
+        }
+#endif
     }
 
     tc_fence_before();

@@ -273,7 +273,22 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
     const bool straddles = g.C > 1 && (g.k * g.k) % kBM != 0;
     const int nc_max = straddles ? (g.C < kBM / (g.k * g.k) + 2 ? g.C : kBM / (g.k * g.k) + 2) : 1;
     p.sg = make_slab16(g, straddles ? g.n + 2 * g.p : g.d + (kBM - 1) / g.k + 1, nc_max);
-    const int extra = kBM * 4 + 2 * p.sg.copy_words * 4;
+    int extra = kBM * 4 + 2 * p.sg.copy_words * 4;
+    // epilogue: TMA reduce-adds of fp32 staging tiles into dbank [N][K] (pitch kpad); per-element atomics if dbank is not
+    // 16-byte aligned
+    rc = make_tmap_2d_f32_reduce(&p.tmD, dbank, N, g.K, g.kpad);
+    if (rc < 0) return rc;
+    p.tma_reduce = rc == 0;
+    int nbuf = 0;
+    if (p.tma_reduce) {
+        extra = (extra + 127) / 128 * 128;
+        p.stage_off = extra;
+        // two staging tiles unless the second costs a pipeline stage (then one; if even one does: atomics)
+        const int s0 = pick_stages2(extra);
+        nbuf = pick_stages2(extra + 2 * kStoreBlockBytes) == s0 ? 2 : (pick_stages2(extra + kStoreBlockBytes) == s0 ? 1 : 0);
+        extra += nbuf * kStoreBlockBytes;
+        p.tma_reduce = nbuf > 0;
+    }
     // Reduction splits.  Tiles are ordered split-major, so the CTA pairs of the device work on ~pairs/out_tiles
     // consecutive splits at any time, and every m-pair of a split re-reads the same dX1 rows: keep that footprint
     // inside L2, then minimise waves x (chunks per split + epilogue) over the candidates.
@@ -297,6 +312,7 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
     p.splits = cdiv(p.chunks_total, best_cps);
     p.num_tiles = out_tiles * p.splits;
     p.skip = 1;
+    if (nbuf == 1) return b128 ? launch_gemm2<Conv1WgradH128_1>(p, extra, st) : launch_gemm2<Conv1WgradH_1>(p, extra, st);
     return b128 ? launch_gemm2<Conv1WgradH128>(p, extra, st) : launch_gemm2<Conv1WgradH>(p, extra, st);
 }
 // rotation pooling between conv1 and conv2 (simt_kernels.cuh: rot_pool_fwd_kernel / rot_pool_bwd_kernel)
@@ -767,7 +783,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     __half* a0 = acts;
     if (E > 0) {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1h, (long long)H * E);
-        if (H % 64 == 0 && H <= 2 * kAccN && H > 128) {
+        if (H % 64 == 0 && H <= 2 * kAccN && H > 128 && s->N >= kBM) {
             // CTA-pair kernel: every generated feature chunk feeds all H hidden columns (gen_pair_policies.cuh)
             GenL1FwdPairParams q{};
             if ((rc = make_tmap_2d_h(&q.tmB, w1h, H, E, E, 128))) return rc;
@@ -780,9 +796,11 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
             int extra = E * 16;
             q.bias_off = extra;
             extra += H * 4;
+            q.tab_off = extra;
+            extra += 2 * H * 4;
             extra = (extra + 1023) / 1024 * 1024;
             q.stage_off = extra;
-            extra += 2 * kStoreBlockBytes;
+            extra += 3 * kStoreBlockBytes;
             rc = gact == kActTanh ? launch_gemm2<GenL1FwdPairT<true>>(q, extra, st) : launch_gemm2<GenL1FwdPair>(q, extra, st);
             if (rc) return rc;
         } else {
@@ -914,7 +932,12 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
             p.chunks_per_split = cdiv(p.chunks_total, splits);
             p.splits = cdiv(p.chunks_total, p.chunks_per_split);
             p.num_tiles = p.m_pairs * p.splits;
-            if ((rc = launch_gemm2<GenL1WgradPair>(p, E * 16, st))) return rc;
+            int extra = E * 16;
+            rc = make_tmap_2d_f32_reduce(&p.tmD, a->dw1, H, E, E);
+            if (rc < 0) return rc;
+            p.tma_reduce = rc == 0;
+            if (p.tma_reduce) { p.stage_off = extra; extra += 2 * kStoreBlockBytes; }
+            if ((rc = launch_gemm2<GenL1WgradPair>(p, extra, st))) return rc;
         } else {
             GenL1WgradParams p{};
             const bool wide = H > 128;
@@ -1250,6 +1273,16 @@ int tvae_attn_softmax_pair_bwd(const float* q_t_r, const float* a_sampled, const
 }
 
 // ================================================================================ test hooks
+#ifdef TVAE_PROBE
+// development probe of the CTA-pair kernel (tc_gemm2.cuh): read and clear the 8 x 16 counters (synchronises the device)
+extern "C" int tvae_probe_read(unsigned long long* out128) {
+    TVAE_CHECK_CUDA(cudaDeviceSynchronize());
+    TVAE_CHECK_CUDA(cudaMemcpyFromSymbol(out128, tvae::g_pair_probe, sizeof(unsigned long long) * 128));
+    unsigned long long zero[128] = {};
+    TVAE_CHECK_CUDA(cudaMemcpyToSymbol(tvae::g_pair_probe, zero, sizeof(zero)));
+    return 0;
+}
+#endif
 int tvae_test_linear_nt(const void* A, const void* B, float* C, int M, int N, int K, const float* bias, int act,
                         void* stream) {
     LinearNTArgs a{};

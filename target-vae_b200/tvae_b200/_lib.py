@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvae_b200.so")
+# TVAE_LIB: a development build of the SAME library (csrc/build.py with TVAE_PROBE=1), never a different implementation
+LIB_PATH = os.environ.get("TVAE_LIB") or os.path.join(_HERE, "libtvae_b200.so")
 
 _lib = None
 
