@@ -318,6 +318,7 @@ int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, i
 /* A/B switch (process-wide, for measurements and tests): 0 sends wide weight gradients back to the tc_gemm LinearTN policy
  * instead of the CTA-pair kernel (linear_pair_policies.cuh).  Default: 1. */
 void tvae_test_set_fast_paths(int pair_tn);
+void tvae_test_set_knob(int id, int value);   /* development knobs for A/B measurements; 0 = default heuristics */
 /* the hidden-layer GEMM with its whole epilogue: C16[M,N] fp16 = store_scale * mask(aux16) * act(acc_scale * A B^T + bias);
  * colsum[N] += column sums, proj_out[M,n_proj] (pre-zeroed) += value . proj_w^T (+ proj_bias).  Any pointer may be NULL. */
 int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, const float* bias, int act, void* C16,

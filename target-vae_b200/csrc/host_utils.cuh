@@ -15,6 +15,7 @@
 namespace tvae {
 
 inline thread_local std::string g_last_error;
+inline int g_dev_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // development knobs (tvae_test_set_knob): 0 = conv1_wgrad reduction splits
 inline std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py reports it)
 
 inline int fail(int code, const std::string& msg) {

@@ -289,25 +289,34 @@ int conv1_wgrad(const ConvGeom& g, const float* y, const void* dx1_16, const flo
         extra += nbuf * kStoreBlockBytes;
         p.tma_reduce = nbuf > 0;
     }
-    // Reduction splits.  Tiles are ordered split-major, so the CTA pairs of the device work on ~pairs/out_tiles
-    // consecutive splits at any time, and every m-pair of a split re-reads the same dX1 rows: keep that footprint
-    // inside L2, then minimise waves x (chunks per split + epilogue) over the candidates.
+    // Reduction splits: minimise waves x (chunks per split + epilogue).  The epilogue adds a 256 x 512 fp32 tile per pair into
+    // dbank; its cost grows with the number of pairs that add into the SAME output tile at the same time (L2 serialises
+    // reduces on one line): measured 16 k clocks per tile with 2.3 concurrent pairs per output tile (cfg2), 49 k with 9.3
+    // (cfg1).  Few, long splits win (clock64 probe, profiles/r02_pair_kernel_probe.md: 9 instead of 46 splits = -8 % at
+    // cfg2, -10 % at cfg4 / cfg5, -37 % at cfg1): the out-tiles of one split walk the same dX1 rows in near lockstep and
+    // share them through L2 even when a split's slice is far larger than L2, so round 1's L2-sized lower bound on the
+    // split count only bought more epilogues.
     const int out_tiles = p.m_pairs * p.n_passes;
     const int pairs_dev = sm_count() / 2;
-    const double bytes_img = 2.0 * g.G * g.P * g.O;
     const double inflight = out_tiles < pairs_dev ? static_cast<double>(pairs_dev) / out_tiles : 1.0;
-    int s_min = static_cast<int>(g.B * inflight * bytes_img / 48e6) + 1;
+    const double epi_clocks = 6000.0 + 5000.0 * inflight;
     const int s_cap = p.chunks_total / 32 > 1 ? p.chunks_total / 32 : 1;      // keep >= 32 chunks (2048 positions) per split
-    if (s_min > s_cap) s_min = s_cap;
+    // With the zero-padding skip a tile's chunk count depends on its kk rows (36 .. 65 live output rows of 65 at cfg2), and a
+    // pair's strided tile list only averages that out over enough tiles: 4 tiles per pair measured 6 % slower than 10
+    // although the mean per-pair time was lower.  Without the skip (cfg1) all tiles are equal and one wave is best.
+    const bool uneven = (g.k * g.k) % kBK16 == 0;
+    const int min_waves = uneven ? 8 : 1;
     double best = 1e30;
     int best_cps = p.chunks_total;
-    for (int s = s_min; s <= s_min + 96 && s <= p.chunks_total; ++s) {
+    for (int s = 1; s <= s_cap && s <= 4 * pairs_dev; ++s) {
         const int cps = cdiv(p.chunks_total, s);
         const int s_eff = cdiv(p.chunks_total, cps);
         const int waves = cdiv((long long)out_tiles * s_eff, pairs_dev);
-        const double cost = waves * (cps * 1024.0 + 15000.0);
+        if (waves < min_waves && s < s_cap) continue;
+        const double cost = waves * (cps * 1024.0 + epi_clocks);
         if (cost < best) { best = cost; best_cps = cps; }
     }
+    if (g_dev_knob[0] > 0) best_cps = cdiv(p.chunks_total, g_dev_knob[0]);
     p.chunks_per_split = best_cps;
     p.splits = cdiv(p.chunks_total, best_cps);
     p.num_tiles = out_tiles * p.splits;
@@ -1305,6 +1314,8 @@ int tvae_test_linear_nt_full(const void* A, const void* B, int M, int N, int K, 
 
 // A/B switch for the wide weight-gradient kernel (default on): 0 sends it back to the tc_gemm LinearTN policy
 void tvae_test_set_fast_paths(int pair_tn) { g_linear_pair_enabled = pair_tn != 0; }
+// development knobs for A/B measurements (0 = default heuristics): 0 = conv1 weight-gradient reduction splits
+void tvae_test_set_knob(int id, int value) { if (id >= 0 && id < 8) g_dev_knob[id] = value; }
 
 int tvae_test_linear_tn(const void* P, const void* Q, float* C, int R, int Ma, int Nb, int transpose_out, void* stream) {
     return linear_tn(P, Ma, Q, Nb, R, Ma, Nb, C, transpose_out ? Ma : Nb, transpose_out, S(stream));

@@ -31,6 +31,10 @@ def main():
     ctx = bench.Ctx()
     wl = bench.Workload(ctx, cfg, B)
     lib = _lib.lib()
+    for kv in sys.argv[3:]:                     # development knobs: id=value
+        k, v = kv.split("=")
+        lib.tvae_test_set_knob(int(k), int(v))
+        print("knob", k, "=", v)
     buf = (ctypes.c_ulonglong * 128)()
     for i in range(2):
         wl.step_resident(i)
