@@ -78,8 +78,10 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
 // chunk `chunk0` of the row's 128 bytes, of a staging buffer.  One warp per scheduler runs this, so it is written for
 // latency: the additive row of the NEXT 8 columns is loaded before the current 8 are stored (the compiler does not move a
 // shared-memory load above a shared-memory store), and LeakyReLU-or-identity is max(v, slope * v) without a branch.
-template <bool TANH, int NV>
-__device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const float* add, bool act, uint8_t* buf, int row, int chunk0) {
+struct NoPost { __device__ void operator()(int, const float (&)[8]) const {} };
+template <bool TANH, int NV, class Post = NoPost>
+__device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const float* add, bool act, uint8_t* buf, int row, int chunk0,
+                                                Post post = Post(), int col0 = 0) {
     const float slope = act ? kLreluSlope : 1.f;
     float4 b0 = *reinterpret_cast<const float4*>(add), b1 = *reinterpret_cast<const float4*>(add + 4);
 #pragma unroll
@@ -100,6 +102,7 @@ __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const 
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], slope * v[q]);
         }
+        post(col0 + j, v);
         uint4 q4;
         __half2 hv;
         hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
@@ -115,7 +118,8 @@ __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const 
 struct StagedEpiState {
     uint32_t blocks;                    // 64-column blocks written so far by this CTA: buffer blocks % NBUF, use blocks / NBUF
     uint32_t staged_bar, freed_bar;     // mbarrier arrays of the kernel
-    int sel;                            // policy scratch
+    int sel, b_lo, b_hi;                // policy scratch
+    float proj[4];                      // policy scratch (fused output projection of the row)
 };
 
 // `nblk` 64-column blocks of one accumulator: value + add -> act -> fp16 -> swizzled staging buffer (ring of NBUF); the store
@@ -123,9 +127,9 @@ struct StagedEpiState {
 // (the next piece is in flight while this one is converted).  Per block: wait until the store that last used the buffer
 // has read it (freed[b]), write, publish to the async proxy, one arrive per warp on staged[b].  No named barrier: a warp
 // never waits for the other epilogue warps, only for a free buffer.   add_ptr(blk) -> 64 floats (shared memory).
-template <bool TANH, int NBUF, int PROBE_SLOT, class AddPtr>
+template <bool TANH, int NBUF, int PROBE_SLOT, class AddPtr, class Post = NoPost>
 __device__ __forceinline__ void staged_store_epilogue(uint32_t taddr, int nblk, StagedEpiState& st, uint8_t* stage0, int row, bool act,
-                                                      AddPtr add_ptr) {
+                                                      AddPtr add_ptr, Post post = Post()) {
     if (nblk <= 0) return;
     uint32_t ra[32], rb[32];
 #ifdef TVAE_PROBE
@@ -145,12 +149,12 @@ __device__ __forceinline__ void staged_store_epilogue(uint32_t taddr, int nblk, 
         TVAE_EPI_LAP(0);
         if (use >= 1) mbar_wait(st.freed_bar + 8 * b, (use - 1) & 1);
         TVAE_EPI_LAP(3);
-        epi_piece_store<TANH, 32>(ra, add, act, buf, row, 0);
+        epi_piece_store<TANH, 32>(ra, add, act, buf, row, 0, post, blk * 64);
         TVAE_EPI_LAP(1);
         tmem_ld_wait();
         if (blk + 1 < nblk) tmem_ld_32x32(taddr + (blk + 1) * 64, ra);
         TVAE_EPI_LAP(0);
-        epi_piece_store<TANH, 32>(rb, add + 32, act, buf, row, 4);
+        epi_piece_store<TANH, 32>(rb, add + 32, act, buf, row, 4, post, blk * 64 + 32);
         TVAE_EPI_LAP(1);
         fence_proxy_async_smem();
         __syncwarp();

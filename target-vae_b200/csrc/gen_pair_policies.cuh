@@ -30,9 +30,15 @@ struct GenL1WgradPairParams {
     const float* acc_scale;   // device scalar: 1 / (scale dpre was stored with)
     CUtensorMap tmD;          // dW1 as [H][E] fp32: target of the epilogue's TMA reduce-adds (tma_reduce == 1)
     int tma_reduce, stage_off;   // stage_off: byte offset of the two fp32 staging tiles in the extra smem
+    const float* zbc;         // FEAT = 1: latent bias (B,E) of the coordinate layer whose activation is the generated operand
 };
 
-struct GenL1WgradPair : PolicyBase {
+// FEAT = 0: Fourier features cos(phase).  FEAT = 1 (generators WITHOUT Fourier features, cfg2): the generated operand is the
+// first-layer activation itself, a0[m][f] = LeakyReLU(W1[f] . x'_m + b1[f] + zb[image(m)][f]) - two FMAs per element -, so the
+// weight gradient of the first hidden layer, dWh[j][f] = sum_m dpre1[m][j] a0[m][f], needs no stored a0 (wf_scaled / bf then
+// hold W1 (E,2) / b1 (E), E = H features); see GenL1FwdPairT<., 1>.
+template <int FEAT = 0>
+struct GenL1WgradPairT : PolicyBase {
     static constexpr const char* kName = "gen_l1_wgrad";
     static constexpr int kProbeSlot = 4;
     using Params = GenL1WgradPairParams;
@@ -88,7 +94,7 @@ struct GenL1WgradPair : PolicyBase {
     __device__ static void load_coord(const Params& p, long long m, float2& v, int& b) {
         if (p.cx.theta == nullptr) {
             v = __ldg(reinterpret_cast<const float2*>(p.cx.x) + m);
-            b = 0;
+            b = FEAT == 1 ? static_cast<int>(static_cast<unsigned>(m) / static_cast<unsigned>(p.cx.N)) : 0;
         } else {
             const unsigned mm = static_cast<unsigned>(m), N = static_cast<unsigned>(p.cx.N);
             b = static_cast<int>(mm / N);
@@ -133,8 +139,21 @@ struct GenL1WgradPair : PolicyBase {
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
                 float e[8];
+                if constexpr (FEAT == 1) {
+                    const float* zrow = p.zbc + (long long)b * p.E + f0;
+                    // same arithmetic as the forward generator (GenL1FwdPairT<., 1>): bias = b1 + zb first, then the two FMAs
+                    const float4 z0 = __ldg(reinterpret_cast<const float4*>(zrow + ch * 8)), z1 = __ldg(reinterpret_cast<const float4*>(zrow + ch * 8 + 4));
+                    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) e[q] = __cosf(fourier_phase(tab[f0 + ch * 8 + q], x0, x1));
+                    for (int q = 0; q < 8; ++q) {
+                        float4 t = tab[f0 + ch * 8 + q];
+                        t.z += zz[q];
+                        e[q] = lrelu(fourier_phase(t, x0, x1));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) e[q] = __cosf(fourier_phase(tab[f0 + ch * 8 + q], x0, x1));
+                }
                 *reinterpret_cast<uint4*>(dst + sw128_offset(prow, ch)) =
                     make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
             }
@@ -146,7 +165,16 @@ struct GenL1WgradPair : PolicyBase {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int f = f0 + ch * 8 + q;
-                e[q] = (ok && f < p.E) ? __cosf(fourier_phase(tab[f], x0, x1)) : 0.f;
+                e[q] = 0.f;
+                if (ok && f < p.E) {
+                    if constexpr (FEAT == 1) {
+                        float4 t = tab[f];
+                        t.z += __ldg(p.zbc + (long long)b * p.E + f);
+                        e[q] = lrelu(fourier_phase(t, x0, x1));
+                    } else {
+                        e[q] = __cosf(fourier_phase(tab[f], x0, x1));
+                    }
+                }
             }
             *reinterpret_cast<uint4*>(dst + sw128_offset(prow, ch)) =
                 make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
@@ -186,6 +214,8 @@ struct GenL1WgradPair : PolicyBase {
     }
 };
 
+using GenL1WgradPair = GenL1WgradPairT<0>;
+
 // ------------------------------------------------------------------------------------------------
 // Generator layer 1 forward on the CTA-pair kernel:
 //
@@ -207,28 +237,52 @@ struct GenL1FwdPairParams {
     const float* bias;        // (H)
     const float* zb;          // (B,H) latent_linear(z) or null
     int act;                  // kActTanh or LeakyReLU
+    // FEAT = 1: the coordinate layer's activation is the generated operand (wf_scaled / bf = its weight (E,2) / bias (E))
+    const float* zbc;         // latent bias (B,E) of the coordinate layer
+    unsigned long long* mask_bits;   // out [E/64][M]: bit q of word (kc, m) = (pre-activation of feature 64 kc + q > 0), or null
+    const float* proj_w; const float* proj_bias; float* proj_out;   // fused output projection proj_out[m][o] = sum_j act[m][j] proj_w[o][j] + proj_bias[o]
+    int n_proj, proj_off;     // n_proj <= 4 (0: none); proj_off: byte offset of the [n_proj][H] weight rows in the extra smem
 };
 
-template <bool TANH>
+// FEAT = 1 - generators WITHOUT Fourier features (cfg2: dSprites): the coordinate layer
+//   a0[m][f] = LeakyReLU(W1[f] . x'_m + b1[f] + zb[image(m)][f])          (models.py:95-117, train_dsprites.py:222-239)
+// is two FMAs per element, so it is generated straight into the A operand of the FIRST HIDDEN layer's GEMM exactly like the
+// Fourier features (the table {w0, w1, b1 + zb} is rebuilt per tile for the at most two images it touches), and the kernel is
+//   acts1 = LeakyReLU(a0 Wh^T + bh),   y_hat = acts1 wout^T + bout  (fused projection when this is the last hidden layer)
+// - coordinate transform, first layer, hidden layer and output projection in ONE kernel; a0 (0.42 GB at cfg2) is never written
+// or read.  The backward pass regenerates a0 for the hidden weight gradient (GenL1WgradPairT<1>) and takes the LeakyReLU mask of
+// the input gradient from mask_bits (one bit per element, written here by the generator warps).
+template <bool TANH, int FEAT = 0>
 struct GenL1FwdPairT : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
     static constexpr int kProbeSlot = 3;
     using Params = GenL1FwdPairParams;
     static constexpr bool kF16 = true;
     struct TmaState { int kc, n_row0; };
-    struct GenState { float x0, x1; int kc; };
+    struct GenState { float x0, x1; int kc; int sel; long long m; int b_lo, b_hi; };
     using EpiState = StagedEpiState;
     static constexpr int kStoreBufs = 3;      // staging buffers of the h1 stores (tc_gemm2's store issuer)
+    // contiguous tile ranges per pair: consecutive tiles lie in the same image (N / 128 tiles per image), so the per-tile
+    // tables (generator: b1 + zb of the coordinate layer; epilogue: bias + latent bias) are rebuilt once per image only
+    static constexpr bool kContiguousTiles = true;
     __device__ static void prefetch_descs(const Params& p) {
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmC);
     }
     __device__ static void setup(const Params& p, uint8_t* extra, int tid, int nthreads) {
-        load_fourier_table(reinterpret_cast<float4*>(extra), p.wf_scaled, p.bf, p.E, tid, nthreads);
+        // FEAT = 1: the static part {w0, w1, b1} of the coordinate layer's table sits behind the two per-image tables
+        load_fourier_table(reinterpret_cast<float4*>(extra) + (FEAT == 1 ? 2 * p.E : 0), p.wf_scaled, p.bf, p.E, tid, nthreads);
         float* s_bias = reinterpret_cast<float*>(extra + p.bias_off);
         for (int j = tid; j < p.H; j += nthreads) s_bias[j] = __ldg(p.bias + j);
+        if (FEAT == 1) {
+            float* s_proj = reinterpret_cast<float*>(extra + p.proj_off);
+            for (int j = tid; j < p.n_proj * p.H; j += nthreads) s_proj[j] = __ldg(p.proj_w + j);
+        }
     }
-    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) { st.blocks = 0; st.sel = 0; }
+    __device__ static void epi_init(const Params&, EpiState& st, uint8_t*, int) {
+        st.blocks = 0; st.sel = 0; st.b_lo = -1; st.b_hi = -1;
+        st.proj[0] = st.proj[1] = st.proj[2] = st.proj[3] = 0.f;
+    }
     __device__ static int store_off(const Params& p) { return p.stage_off; }
     __device__ static int store_blocks(const Params& p, const PairTile& ti, int n0, bool has_work) {
         return (has_work && ti.m_tile >= 0) ? min(kAccN / 64, (p.H - n0) / 64) : 0;
@@ -254,10 +308,33 @@ struct GenL1FwdPairT : PolicyBase {
         for (int a = 0; a < ti.n_acc; ++a) tma_load_2d_pair(sb + a * kBHalfBytes, &p.tmB, bar, s.kc * kBKh, s.n_row0 + a * kAccN);
         ++s.kc;
     }
-    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.x0 = 0.f; s.x1 = 0.f; s.kc = 0; }
-    __device__ static void gen_tile_begin(const Params& p, const PairTile& ti, GenState& s, uint8_t*, int ptid) {
+    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.x0 = 0.f; s.x1 = 0.f; s.kc = 0; s.sel = 0; s.m = 0; s.b_lo = -1; s.b_hi = -1; }
+    __device__ static void gen_tile_begin(const Params& p, const PairTile& ti, GenState& s, uint8_t* extra, int ptid) {
         s.kc = 0;
+        s.sel = 0;
+        s.m = (long long)ti.a0 + (ptid & (kBM - 1));
         if (ti.m_tile < 0) { s.x0 = 0.f; s.x1 = 0.f; return; }
+        if (FEAT == 1) {
+            // feature table of the tile: {w0, w1, b1 + zb[image]} for the (at most two: N >= 128) images of its 128 rows;
+            // all 8 generator warps, uniform over the CTA
+            float4* tab = reinterpret_cast<float4*>(extra);
+            const long long m_last = min((long long)ti.a0 + kBM - 1, p.cx.M - 1);
+            const int b_lo = static_cast<int>(static_cast<unsigned>(ti.a0) / static_cast<unsigned>(p.cx.N));
+            const int b_hi = static_cast<int>(static_cast<unsigned>(m_last) / static_cast<unsigned>(p.cx.N));
+            if (b_lo != s.b_lo || b_hi != s.b_hi) {               // uniform over the CTA
+                named_bar_sync(1, kGenWarps * 32);                // the previous tile's table reads are done
+                const float4* stat = tab + 2 * p.E;               // {w0, w1, b1, 0} per feature (setup)
+                for (int j = ptid; j < 2 * p.E; j += kGenWarps * 32) {
+                    const int which = j >= p.E, f = j - which * p.E;
+                    float4 t = stat[f];
+                    t.z += __ldg(p.zbc + (long long)(which ? b_hi : b_lo) * p.E + f);
+                    tab[j] = t;
+                }
+                named_bar_sync(1, kGenWarps * 32);
+                s.b_lo = b_lo; s.b_hi = b_hi;
+            }
+            s.sel = (b_hi != b_lo && min(s.m, p.cx.M - 1) >= (long long)b_hi * p.cx.N) ? 1 : 0;
+        }
         transformed_coord(p.cx, (long long)ti.a0 + (ptid & (kBM - 1)), s.x0, s.x1);
     }
     __device__ static void gen_prepare(const Params&, const PairTile&, GenState&, uint8_t*, int) {}
@@ -268,6 +345,26 @@ struct GenL1FwdPairT : PolicyBase {
         const int row = gtid;
         const bool live = ti.m_tile >= 0;
         const int f0 = s.kc * kBKh;
+        if (FEAT == 1) {
+            // the coordinate layer's activation (E % 64 == 0: host); sign bits of the pre-activation for the backward mask
+            const float4* t2 = tab + s.sel * p.E + f0;
+            uint32_t bits[2] = {0u, 0u};
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float pre = live ? fourier_phase(t2[ch * 8 + q], s.x0, s.x1) : 0.f;
+                    if (pre > 0.f) bits[ch >> 2] |= 1u << ((ch & 3) * 8 + q);
+                    e[q] = TANH ? tanhf(pre) : lrelu(pre);
+                }
+                *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, ch)) =
+                    make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+            }
+            if (p.mask_bits && live && s.m < p.cx.M)
+                p.mask_bits[(long long)s.kc * p.cx.M + s.m] = bits[0] | (static_cast<unsigned long long>(bits[1]) << 32);
+            return;
+        }
         if (live && f0 + kBKh <= p.E) {
             // whole chunk of live features (E % 64 == 0 in every reference configuration): no per-feature predicates - they
             // were 4 of the 10 instructions per feature on the warps that pace this kernel
@@ -298,6 +395,7 @@ struct GenL1FwdPairT : PolicyBase {
     // the per-row global loads of the latent bias were the larger half of a latency-bound epilogue.
     __device__ static void epi_tile_begin(const Params& p, const PairTile& ti, EpiState& st, uint8_t* extra, int row) {
         st.sel = 0;
+        if (FEAT == 1) st.proj[0] = st.proj[1] = st.proj[2] = st.proj[3] = 0.f;
         if (ti.m_tile < 0) return;                              // uniform over the CTA
         float* tab = reinterpret_cast<float*>(extra + p.tab_off);
         const float* s_bias = reinterpret_cast<const float*>(extra + p.bias_off);
@@ -305,6 +403,8 @@ struct GenL1FwdPairT : PolicyBase {
         const int b_lo = static_cast<int>(m_first / p.cx.N), b_hi = static_cast<int>(m_last / p.cx.N);
         const long long m = min((long long)ti.a0 + row, p.cx.M - 1);
         st.sel = (m >= (long long)b_hi * p.cx.N && b_hi != b_lo) ? 1 : 0;
+        if (b_lo == st.b_lo && b_hi == st.b_hi) return;         // same images as the previous tile (uniform): table is current
+        st.b_lo = b_lo; st.b_hi = b_hi;
         named_bar_sync(2, kEpiWarps * 32);                      // every warp's table reads of the previous tile are done
         for (int j = row; j < 2 * p.H; j += kEpiWarps * 32) {
             const int which = j >= p.H, jj = j - which * p.H;
@@ -318,8 +418,37 @@ struct GenL1FwdPairT : PolicyBase {
     __device__ static void epilogue(const Params& p, const PairTile& ti, EpiState& st, int n0, uint32_t taddr, int row, bool has_work,
                                     uint8_t* extra) {
         const float* tab = reinterpret_cast<const float*>(extra + p.tab_off) + st.sel * p.H;
-        staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
-                                          [&](int blk) { return tab + n0 + blk * 64; });
+        if constexpr (FEAT == 1) {
+            const float* s_proj = reinterpret_cast<const float*>(extra + p.proj_off) + n0;
+            const int n_proj = p.n_proj, H = p.H;
+            staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
+                                              [&](int blk) { return tab + n0 + blk * 64; },
+                                              [&](int col, const float (&v)[8]) {          // fused output projection (fp32 activations)
+#pragma unroll
+                                                  for (int o = 0; o < 4; ++o) {            // static indices: proj[] stays in registers
+                                                      if (o < n_proj) {
+                                                          const float4 w0 = *reinterpret_cast<const float4*>(s_proj + o * H + col);
+                                                          const float4 w1 = *reinterpret_cast<const float4*>(s_proj + o * H + col + 4);
+                                                          // four independent chains (one warp per scheduler: dependent FMAs cost their latency)
+                                                          const float t0 = fmaf(v[1], w0.y, v[0] * w0.x), t1 = fmaf(v[3], w0.w, v[2] * w0.z);
+                                                          const float t2 = fmaf(v[5], w1.y, v[4] * w1.x), t3 = fmaf(v[7], w1.w, v[6] * w1.z);
+                                                          st.proj[o] += (t0 + t1) + (t2 + t3);
+                                                      }
+                                                  }
+                                              });
+        } else {
+            staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
+                                              [&](int blk) { return tab + n0 + blk * 64; });
+        }
+    }
+    // after both accumulators of the tile: the row's projected outputs
+    __device__ static void epi_tile_end(const Params& p, const PairTile& ti, EpiState& st, uint8_t*, int row, bool has_work) {
+        if (FEAT == 0 || p.n_proj == 0 || !has_work || ti.m_tile < 0) return;
+        const long long m = (long long)ti.a0 + row;
+        if (m >= p.cx.M) return;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (o < p.n_proj) p.proj_out[m * p.n_proj + o] = st.proj[o] + (p.proj_bias ? __ldg(p.proj_bias + o) : 0.f);
     }
 };
 using GenL1FwdPair = GenL1FwdPairT<false>;

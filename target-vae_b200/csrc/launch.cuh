@@ -72,6 +72,7 @@ struct LinearNTArgs {
     const float* proj_w = nullptr; const float* proj_bias = nullptr; float* proj_out = nullptr; int n_proj = 0;
     void* C16 = nullptr; long long ldc16 = 0;
     const void* aux16 = nullptr; int aux_act = 0;
+    const unsigned long long* aux_bits = nullptr;
     const float* acc_scale = nullptr; const float* store_scale = nullptr;
     float* colsum = nullptr; long long colsum_stride = 1;
 };
@@ -95,7 +96,8 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.ld_aux = a.ld_aux; p.act = a.act; p.aux_act = a.aux_act;
     p.proj_w = a.proj_w; p.proj_bias = a.proj_bias; p.proj_out = a.proj_out; p.n_proj = a.n_proj;
     p.C16 = a.C16; p.ldc16 = a.ldc16; p.colsum = a.colsum; p.colsum_stride = a.colsum_stride;
-    p.aux16 = a.aux16; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
+    p.aux16 = a.aux16; p.aux_bits = a.aux_bits; p.acc_scale = a.acc_scale; p.store_scale = a.store_scale;
+    TVAE_REQUIRE(!a.aux_bits || a.N % 64 == 0, "linear_nt: the one-bit mask needs N % 64 == 0");
     // extra smem: bias / projection / column-sum rows sized by the actual N, then (fp16 output with whole 64-column
     // blocks) the staging buffers of the TMA stores: two 16 KB buffers per epilogue group
     p.npad = (a.N + 31) / 32 * 32;

@@ -48,6 +48,8 @@ struct LinearNTParams {
     void* C16;                // [M][ldc16] fp16 output (value * *store_scale) or null
     long long ldc16;
     const void* aux16;        // [M][ld_aux] fp16 or null: multiply by lrelu'(aux16)
+    const unsigned long long* aux_bits;   // [N/64][M] or null: bit q of word (n/64, m) set = derivative 1, clear = LeakyReLU slope
+                                          // (the one-bit form of aux16, written by GenL1FwdPairT<., 1>; N % 64 == 0)
     const float* acc_scale;   // device scalar multiplied into the accumulator first (undoes the operand's scale) or null
     const float* store_scale; // device scalar applied to the fp16 store only (power of two) or null
     float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient) or null
@@ -161,6 +163,13 @@ struct LinearNT : PolicyBase {
                     if (nt * BN + 64 * j < p.N) prefetch_l2(pf + 128 * j);
             }
         }
+        // one-bit LeakyReLU mask: BN / 64 words per row, lanes = consecutive rows (coalesced)
+        unsigned long long mbits[BN / 64];
+        if (p.aux_bits) {
+#pragma unroll
+            for (int w = 0; w < BN / 64; ++w)
+                mbits[w] = (m_ok && ti.n0 + 64 * w < p.N) ? __ldg(p.aux_bits + (long long)(ti.n0 / 64 + w) * p.M + m) : 0ull;
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
@@ -219,6 +228,14 @@ struct LinearNT : PolicyBase {
                         }
                     }
                 }
+            }
+            if (p.aux_bits) {
+                unsigned long long wsel = mbits[0];
+#pragma unroll
+                for (int w = 1; w < BN / 64; ++w) wsel = (c >> 1) == w ? mbits[w] : wsel;
+                const uint32_t bits = static_cast<uint32_t>(wsel >> ((c & 1) * 32));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= ((bits >> j) & 1u) ? 1.f : kLreluSlope;
             }
             if (p.colsum) {
                 if (!m_ok) {

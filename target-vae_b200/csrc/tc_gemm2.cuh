@@ -182,7 +182,15 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
     const int pair = blockIdx.x >> 1;
     // strided schedule: tile costs vary smoothly with the tile index (zero-padding chunks are skipped), so
     // interleaving gives every pair the same mix
-    const int tile_begin = pair, tile_end = prm.num_tiles, tile_step = n_pairs;
+    // (policies with kContiguousTiles take contiguous ranges instead: equal-cost tiles whose per-tile tables only change
+    // from image to image)
+    int tile_begin = pair, tile_end = prm.num_tiles, tile_step = n_pairs;
+    if constexpr (P::kContiguousTiles) {
+        const int per = (prm.num_tiles + n_pairs - 1) / n_pairs;
+        tile_begin = pair * per;
+        tile_end = min(prm.num_tiles, tile_begin + per);
+        tile_step = 1;
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -322,6 +330,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + a * kAccN;
                 P::epilogue(prm, ti, est, ti.n0 + a * kAccN, taddr, row, has_work, extra);
             }
+            P::epi_tile_end(prm, ti, est, extra, row, has_work);
             TVAE_PROBE_ADD(pr_epi);
             tc_fence_before();
             __syncwarp();

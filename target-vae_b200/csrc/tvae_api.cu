@@ -770,6 +770,13 @@ static int check_gen_shape(const tvae_gen_shape* s) {
     return 0;
 }
 
+// Generators without Fourier features whose coordinate layer is fused into the first hidden layer's GEMM (forward) and
+// regenerated in its weight gradient (backward): LeakyReLU, 128 | H <= 512, whole 128-row tiles touch at most two images.
+static bool gen_coord_fused(const tvae_gen_shape* s) {
+    return g_dev_knob[1] == 0 && s->E == 0 && s->L >= 1 && s->act == TVAE_ACT_LEAKYRELU && s->H % 128 == 0 && s->H <= 2 * kAccN &&
+           s->N >= kBM && (long long)s->B * s->N < (1LL << 31);
+}
+
 static CoordXform make_xform(const tvae_gen_shape* s, const tvae_gen_fwd_args* a) {
     CoordXform c{};
     c.x = a->x; c.theta = a->theta; c.dx = a->dx; c.N = s->N; c.M = (long long)s->B * s->N;
@@ -790,6 +797,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     __half* acts = static_cast<__half*>(a->acts);
     if (s->L > 0) { ++g_launch_count; to_half_kernel<<<blocks_for((long long)s->L * H * H, 256), 256, 0, st>>>(a->wh, whh, (long long)s->L * H * H); }
     __half* a0 = acts;
+    int first_hidden = 1;
     if (E > 0) {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1h, (long long)H * E);
         if (H % 64 == 0 && H <= 2 * kAccN && H > 128 && s->N >= kBM) {
@@ -827,6 +835,33 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         else rc = wide ? launch_gemm<GenL1Fwd<256>>(p, extra, st) : launch_gemm<GenL1Fwd<128>>(p, extra, st);
         if (rc) return rc;
         }
+    } else if (gen_coord_fused(s)) {
+        // no Fourier features: coordinate layer generated as the A operand of the first hidden layer's GEMM, output
+        // projection fused when that is the last hidden layer (gen_pair_policies.cuh, GenL1FwdPairT<., 1>); acts[0] is never
+        // written - its buffer holds the one-bit LeakyReLU mask of the coordinate layer for the backward pass
+        GenL1FwdPairParams q{};
+        __half* a1 = acts + M * H;
+        if ((rc = make_tmap_2d_h(&q.tmB, whh, H, H, H, 128))) return rc;
+        if ((rc = make_tmap_2d_h(&q.tmC, a1, M, H, H, kBM))) return rc;
+        q.cx = cx; q.wf_scaled = a->w1; q.bf = a->b1; q.zbc = a->zb; q.E = H; q.H = H;
+        q.bias = a->bh; q.zb = nullptr; q.act = gact;
+        q.mask_bits = reinterpret_cast<unsigned long long*>(acts);
+        if (s->L == 1) { q.proj_w = a->wout; q.proj_bias = a->bout; q.proj_out = a->y_hat; q.n_proj = s->n_out; }
+        q.m_tiles = static_cast<int>(cdiv(M, kBM));
+        q.k_chunks = cdiv(H, kBKh);
+        q.num_tiles = cdiv(q.m_tiles, 2);
+        int extra = 3 * H * 16;                    // feature tables {w0, w1, b1 + zb} of two images + the static {w0, w1, b1}
+        q.bias_off = extra;
+        extra += H * 4;
+        q.tab_off = extra;
+        extra += 2 * H * 4;
+        q.proj_off = extra;
+        extra += q.n_proj * H * 4;
+        extra = (extra + 1023) / 1024 * 1024;
+        q.stage_off = extra;
+        extra += 3 * kStoreBlockBytes;
+        if ((rc = launch_gemm2<GenL1FwdPairT<false, 1>>(q, extra, st))) return rc;
+        first_hidden = 2;
     } else {
         ++g_launch_count;
         if (H % 8 == 0 && H / 8 <= 256) {          // 16-byte stores
@@ -845,8 +880,9 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         TVAE_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
+    if (first_hidden > s->L) return 0;             // the fused kernel was the last hidden layer and wrote y_hat itself
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->y_hat, 0, sizeof(float) * M * s->n_out, st));
-    for (int i = 1; i <= s->L; ++i) {
+    for (int i = first_hidden; i <= s->L; ++i) {
         LinearNTArgs l{};
         l.A = acts + (long long)(i - 1) * M * H; l.lda = H;
         l.B = whh + (long long)(i - 1) * H * H; l.ldb = H;
@@ -900,9 +936,33 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         if ((rc = launch_thin_bwd<4, 4, false, true>(p, 1, st))) return rc;
     }
     // ---- hidden layers, last to first
+    const bool coord_fused = gen_coord_fused(s);
     for (int i = L; i >= 1; --i) {
         const __half* a_prev = acts + (long long)(i - 1) * M * H;
         const float* w = a->f.wh + (long long)(i - 1) * H * H;
+        if (i == 1 && coord_fused) {
+            // dWh[0][j][f] = sum_m dpre1[m][j] a0[m][f] with a0 (the coordinate layer's activation) regenerated on chip
+            GenL1WgradPairParams p{};
+            if ((rc = make_tmap_3d_mn_h(&p.tmQ, dcur, M, H, H, kBKh, 4))) return rc;
+            p.cx = cx; p.wf_scaled = a->f.w1; p.bf = a->f.b1; p.zbc = a->f.zb; p.E = H; p.H = H; p.dW1 = a->dwh;
+            p.acc_scale = a->scales + 2 * i + 1;
+            p.m_tiles = cdiv(H, kBM);
+            p.m_pairs = cdiv(p.m_tiles, 2);
+            p.chunks_total = static_cast<int>(cdiv(M, kBKh));
+            const int pairs_dev = sm_count() / 2;
+            int splits = pairs_dev / p.m_pairs;
+            if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
+            if (splits < 1) splits = 1;
+            p.chunks_per_split = cdiv(p.chunks_total, splits);
+            p.splits = cdiv(p.chunks_total, p.chunks_per_split);
+            p.num_tiles = p.m_pairs * p.splits;
+            int extra = H * 16;
+            rc = make_tmap_2d_f32_reduce(&p.tmD, a->dwh, H, H, H);
+            if (rc < 0) return rc;
+            p.tma_reduce = rc == 0;
+            if (p.tma_reduce) { p.stage_off = extra; extra += 2 * kStoreBlockBytes; }
+            if ((rc = launch_gemm2<GenL1WgradPairT<1>>(p, extra, st))) return rc;
+        } else
         if ((rc = linear_tn(dcur, H, a_prev, H, static_cast<int>(M), H, H, a->dwh + (long long)(i - 1) * H * H, H, 0, st,
                             a->scales + 2 * i + 1))) return rc;
         ++g_launch_count; transpose_half_kernel<<<blocks_for((long long)H * H, 256), 256, 0, st>>>(w, wt_h, H, H);
@@ -910,6 +970,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         l.A = dcur; l.lda = H; l.B = wt_h; l.ldb = H;
         l.M = static_cast<int>(M); l.N = H; l.K = H;
         l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H; l.aux_act = gact;
+        if (i == 1 && coord_fused) { l.aux16 = nullptr; l.aux_bits = reinterpret_cast<const unsigned long long*>(acts); }   // one-bit mask written by the forward kernel
         l.acc_scale = a->scales + 2 * i + 1; l.store_scale = a->scales + 2 * (i - 1);
         if (i - 1 >= 1) { l.colsum = a->dbh + (long long)(i - 2) * H; l.colsum_stride = 1; }   // bias gradient of hidden layer i-1
         if ((rc = linear_nt(l, st))) return rc;
