@@ -307,6 +307,10 @@ int tvae_linear_act_fwd(const float* x, const float* w, const float* bias, int M
                         void* x16, void* w16, void* stream);
 int tvae_linear_act_bwd(const void* x16, const float* w, const float* y, const float* g, int M, int N, int K, int resid, int act,
                         void* dpre16, void* wt16, float* scales8, float* dx, float* dw, float* db, void* stream);
+/* GroupConv.forward's gradient w.r.t. its input image (models.py:202-225 under autograd; the training step never needs it -
+ * the image is data): dout fp32 [(b*G + r)*P + pos][O] (the layout tvae_groupconv_fwd writes) -> dy (B,C,n,n).  bank32 is
+ * scratch, G*O*C*k*k floats (the fp32 rotated bank).  CUDA-core kernel. */
+int tvae_groupconv_dgrad(const tvae_enc_shape* s, const float* weight, const float* dout, float* bank32, float* dy, void* stream);
 /* backward of tvae_attn_softmax_pair (models.py:383-388 under autograd): d_attn (B,L) from d_q and / or d_a (either may be NULL) */
 int tvae_attn_softmax_pair_bwd(const float* q_t_r, const float* a_sampled, const float* d_q, const float* d_a, float* d_attn, int B, int L,
                                void* stream);

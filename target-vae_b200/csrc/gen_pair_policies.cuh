@@ -259,7 +259,7 @@ struct GenL1FwdPairT : PolicyBase {
     using Params = GenL1FwdPairParams;
     static constexpr bool kF16 = true;
     struct TmaState { int kc, n_row0; };
-    struct GenState { float x0, x1; int kc; int sel; long long m; int b_lo, b_hi; };
+    struct GenState { float x0, x1; int kc; int sel; long long m; int b_lo, b_hi; unsigned long long pend_bits; long long pend_idx; };
     using EpiState = StagedEpiState;
     static constexpr int kStoreBufs = 3;      // staging buffers of the h1 stores (tc_gemm2's store issuer)
     // contiguous tile ranges per pair: consecutive tiles lie in the same image (N / 128 tiles per image), so the per-tile
@@ -300,15 +300,15 @@ struct GenL1FwdPairT : PolicyBase {
         ti.kc_end = p.k_chunks;
         ti.a1 = ti.a2 = ti.a3 = 0;
     }
-    __device__ static void tma_tile_begin(const Params&, const PairTile&, uint32_t rank, TmaState& s) {
+    __device__ static void tma_tile_begin(const Params&, const PairTile& ti, uint32_t rank, TmaState& s) {
         s.kc = 0;
-        s.n_row0 = static_cast<int>(rank) * 128;
+        s.n_row0 = ti.n0 + static_cast<int>(rank) * 128;
     }
     __device__ static void tma_chunk(const Params& p, const PairTile& ti, TmaState& s, uint32_t sb, uint32_t bar) {
         for (int a = 0; a < ti.n_acc; ++a) tma_load_2d_pair(sb + a * kBHalfBytes, &p.tmB, bar, s.kc * kBKh, s.n_row0 + a * kAccN);
         ++s.kc;
     }
-    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.x0 = 0.f; s.x1 = 0.f; s.kc = 0; s.sel = 0; s.m = 0; s.b_lo = -1; s.b_hi = -1; }
+    __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.x0 = 0.f; s.x1 = 0.f; s.kc = 0; s.sel = 0; s.m = 0; s.b_lo = -1; s.b_hi = -1; s.pend_idx = -1; s.pend_bits = 0; }
     __device__ static void gen_tile_begin(const Params& p, const PairTile& ti, GenState& s, uint8_t* extra, int ptid) {
         s.kc = 0;
         s.sel = 0;
@@ -339,6 +339,9 @@ struct GenL1FwdPairT : PolicyBase {
     }
     __device__ static void gen_prepare(const Params&, const PairTile&, GenState&, uint8_t*, int) {}
     __device__ static void gen_advance(const Params&, const PairTile&, GenState& s) { ++s.kc; }
+    __device__ static void gen_finish(const Params& p, GenState& s) {
+        if (FEAT == 1 && s.pend_idx >= 0) { p.mask_bits[s.pend_idx] = s.pend_bits; s.pend_idx = -1; }
+    }
     // one group (128 threads) fills a stage: thread = one pixel row, all 64 features of the chunk (8 swizzled 16-byte stores)
     __device__ static void gen_chunk(const Params& p, const PairTile& ti, GenState& s, uint8_t* a_stage, uint8_t* extra, int gtid) {
         const float4* tab = reinterpret_cast<const float4*>(extra);
@@ -346,23 +349,36 @@ struct GenL1FwdPairT : PolicyBase {
         const bool live = ti.m_tile >= 0;
         const int f0 = s.kc * kBKh;
         if (FEAT == 1) {
-            // the coordinate layer's activation (E % 64 == 0: host); sign bits of the pre-activation for the backward mask
+            // the coordinate layer's activation (E % 64 == 0: host); sign bits of the pre-activation for the backward mask.
+            // The mask word of the PREVIOUS chunk is stored now: the proxy fence that publishes a stage waits for the thread's
+            // outstanding global stores too, so a store right before it put a global round trip into every chunk (5.3 k clocks
+            // per chunk against 2 k for the cosine features).
+            if (s.pend_idx >= 0) { p.mask_bits[s.pend_idx] = s.pend_bits; s.pend_idx = -1; }
             const float4* t2 = tab + s.sel * p.E + f0;
             uint32_t bits[2] = {0u, 0u};
+            if (!live) {                                           // padding half of the last pair: zero operand rows
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, ch)) = make_uint4(0u, 0u, 0u, 0u);
+                return;
+            }
+            // branch-free: 64 independent {LDS.128, 2 FMA, compare, max} chains (a per-element branch serialised them: 5.3 k
+            // clocks per chunk against 2 k for the cosine features)
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
                 float e[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float pre = live ? fourier_phase(t2[ch * 8 + q], s.x0, s.x1) : 0.f;
-                    if (pre > 0.f) bits[ch >> 2] |= 1u << ((ch & 3) * 8 + q);
+                    const float pre = fourier_phase(t2[ch * 8 + q], s.x0, s.x1);
+                    bits[ch >> 2] |= static_cast<uint32_t>(pre > 0.f) << ((ch & 3) * 8 + q);
                     e[q] = TANH ? tanhf(pre) : lrelu(pre);
                 }
                 *reinterpret_cast<uint4*>(a_stage + sw128_offset(row, ch)) =
                     make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
             }
-            if (p.mask_bits && live && s.m < p.cx.M)
-                p.mask_bits[(long long)s.kc * p.cx.M + s.m] = bits[0] | (static_cast<unsigned long long>(bits[1]) << 32);
+            if (p.mask_bits && s.m < p.cx.M) {
+                s.pend_bits = bits[0] | (static_cast<unsigned long long>(bits[1]) << 32);
+                s.pend_idx = (long long)s.kc * p.cx.M + s.m;
+            }
             return;
         }
         if (live && f0 + kBKh <= p.E) {
@@ -447,8 +463,11 @@ struct GenL1FwdPairT : PolicyBase {
         const long long m = (long long)ti.a0 + row;
         if (m >= p.cx.M) return;
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-            if (o < p.n_proj) p.proj_out[m * p.n_proj + o] = st.proj[o] + (p.proj_bias ? __ldg(p.proj_bias + o) : 0.f);
+        for (int o = 0; o < 4; ++o) {
+            if (o < p.n_proj) {
+                p.proj_out[m * p.n_proj + o] = st.proj[o] + (p.proj_bias ? __ldg(p.proj_bias + o) : 0.f);
+            }
+        }
     }
 };
 using GenL1FwdPair = GenL1FwdPairT<false>;

@@ -101,4 +101,49 @@ __global__ void __launch_bounds__(1024) softmax_pair_bwd_kernel(const float* __r
     }
 }
 
+// Gradient of GroupConv.forward (models.py:202-225) w.r.t. its INPUT image - only needed when GroupConv is used on its own
+// with an input that requires a gradient (the training step never does: the image is data).  CUDA-core kernel, fp32:
+//   dy[b][c][iy][ix] = sum_{r,o} sum_{u,v} g[(b,r,u*d+v)][o] * bank[(r,o)][c][iy-u+p][ix-v+p]
+// one CTA per (image row iy, b*C + c); thread = (ix, half of the o range), four o per step (16-byte loads of g).
+__global__ void __launch_bounds__(256) groupconv_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ bank, float* __restrict__ dy,
+                                                              int C, int n, int k, int p, int G, int O, int d) {
+    __shared__ float part[256];
+    const int iy = blockIdx.x, bc = blockIdx.y, b = bc / C, c = bc - b * C;
+    const int K = C * k * k, P = d * d;
+    const int xl = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int o_begin = half * (O / 2), o_end = o_begin + O / 2;           // O % 8 == 0 (host)
+    const int u_lo = max(0, iy + p - k + 1), u_hi = min(d - 1, iy + p);
+    for (int ix0 = 0; ix0 < n; ix0 += 128) {
+        const int ix = ix0 + xl;
+        float acc = 0.f;
+        if (ix < n) {
+            const int v_lo = max(0, ix + p - k + 1), v_hi = min(d - 1, ix + p);
+            for (int r = 0; r < G; ++r) {
+                const float* gr = g + ((long long)(b * G + r) * P) * O;
+                const float* br = bank + (long long)r * O * K + (long long)c * k * k;
+                for (int u = u_lo; u <= u_hi; ++u) {
+                    const int ky = iy - u + p;
+                    for (int o = o_begin; o < o_end; o += 4) {
+                        const float* b0 = br + (long long)o * K + ky * k + ix + p;       // + (-v) below
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        for (int v = v_lo; v <= v_hi; ++v) {
+                            const float4 gq = __ldg(reinterpret_cast<const float4*>(gr + (long long)(u * d + v) * O + o));
+                            const float* bb = b0 - v;
+                            a0 = fmaf(gq.x, __ldg(bb), a0);
+                            a1 = fmaf(gq.y, __ldg(bb + K), a1);
+                            a2 = fmaf(gq.z, __ldg(bb + 2 * K), a2);
+                            a3 = fmaf(gq.w, __ldg(bb + 3 * K), a3);
+                        }
+                        acc += (a0 + a1) + (a2 + a3);
+                    }
+                }
+            }
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        if (half == 0 && ix < n) dy[((long long)bc * n + iy) * n + ix] = part[xl] + part[xl + 128];
+        __syncthreads();
+    }
+}
+
 }  // namespace tvae

@@ -378,6 +378,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
+        P::gen_finish(prm, gst);
 #ifdef TVAE_PROBE
         if (leader && ptid == 0) {                             // generator thread 0 (group 0: every other chunk)
             atomicAdd(&g_pair_probe[P::kProbeSlot][5], (unsigned long long)pr_empty);

@@ -1334,6 +1334,21 @@ int tvae_linear_act_bwd(const void* x16, const float* w, const float* y, const f
     return 0;
 }
 
+int tvae_groupconv_dgrad(const tvae_enc_shape* s, const float* weight, const float* dout, float* bank32, float* dy, void* stream) {
+    int rc = check_enc_shape(s);
+    if (rc) return rc;
+    TVAE_REQUIRE(weight && dout && bank32 && dy, "groupconv_dgrad: null pointer");
+    TVAE_REQUIRE(s->O % 8 == 0, "groupconv_dgrad: kernel count must be a multiple of 8");
+    const ConvGeom g = make_geom(s);
+    cudaStream_t st = S(stream);
+    ++g_launch_count;
+    filter_bank_f32_kernel<<<blocks_for((long long)g.G * g.O * g.K, 256), 256, 0, st>>>(weight, bank32, g.O, g.C, g.k, g.G, make_rot_table(g.G));
+    ++g_launch_count;
+    groupconv_dgrad_kernel<<<dim3(g.n, g.B * g.C), 256, 0, st>>>(dout, bank32, dy, g.C, g.n, g.k, g.p, g.G, g.O, g.d);
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int tvae_attn_softmax_pair_bwd(const float* q_t_r, const float* a_sampled, const float* d_q, const float* d_a, float* d_attn, int B, int L,
                                void* stream) {
     TVAE_REQUIRE(B >= 1 && L >= 1 && q_t_r && a_sampled && d_attn && (d_q || d_a), "softmax_pair_bwd: bad arguments");

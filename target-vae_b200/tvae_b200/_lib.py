@@ -28,6 +28,10 @@ def lib() -> ctypes.CDLL:
                 "(there is no CPU or PyTorch fallback for the TARGET-VAE hot path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.tvae_last_error.restype = ctypes.c_char_p
+        # development A/B knobs of the library (tvae_test_set_knob), e.g. TVAE_KNOBS="2=1,0=9"; unset = default heuristics
+        for kv in filter(None, os.environ.get("TVAE_KNOBS", "").split(",")):
+            k, v = kv.split("=")
+            _lib.tvae_test_set_knob(int(k), int(v))
     return _lib
 
 

@@ -65,6 +65,7 @@ class GroupConvFn(torch.autograd.Function):
                                              ops.ptr(None if bias is None else ops.f32(bias)), ops.ptr(out),
                                              ops.stream_ptr()), "tvae_groupconv_fwd")
         ctx.s, ctx.has_bias = s, bias is not None
+        ctx.weight, ctx.yshape = weight.detach(), y.shape
         ctx.save_for_backward(yc)
         # internal [(b,r,pos)][o] -> reference (B,O,G,H',W')
         return out.view(B, G, d, d, O).permute(0, 4, 1, 2, 3)
@@ -73,9 +74,15 @@ class GroupConvFn(torch.autograd.Function):
     def backward(ctx, g):
         (yc,) = ctx.saved_tensors
         s = ctx.s
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("GroupConv: gradient w.r.t. the input image is not part of the hot path")
         gi = g.permute(0, 2, 3, 4, 1).contiguous().view(-1, s.O).float()
+        dy = None
+        if ctx.needs_input_grad[0]:
+            # off the hot path (the training step's image is data): CUDA-core transposed convolution with the fp32 bank
+            dy = ops.empty(s.B, s.C, s.n, s.n, device=g.device)
+            bank32 = ops.empty(s.G * s.O, s.C * s.k * s.k, device=g.device)
+            ops.check(ops.L().tvae_groupconv_dgrad(ops.byref(s), ops.ptr(ops.f32(ctx.weight)), ops.ptr(gi), ops.ptr(bank32), ops.ptr(dy),
+                                                   ops.stream_ptr()), "tvae_groupconv_dgrad")
+            dy = dy.view(ctx.yshape)
         dbank = ops.empty(s.G * s.O, s.kpad, device=g.device)
         gi16 = ops.half(*gi.shape, device=g.device)
         scales = ops.empty(8, device=g.device)
@@ -83,7 +90,7 @@ class GroupConvFn(torch.autograd.Function):
                                                ops.stream_ptr()),
                   "tvae_groupconv_wgrad")
         dw, db = ops.filter_bank_bwd(s, dbank)
-        return None, dw, (db if ctx.has_bias else None), None, None
+        return dy, dw, (db if ctx.has_bias else None), None, None
 
 
 # ------------------------------------------------------------------------------------------------ encoder heads

@@ -62,6 +62,29 @@ def test_resid_linear_forward_backward(act, M, H):
     assert rel_err(layer.linear.bias.grad.cpu(), dpre.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("C,n,k,p,G,O", [(1, 14, 7, 3, 4, 32), (3, 10, 6, 2, 8, 32)])
+def test_groupconv_input_gradient(C, n, k, p, G, O):
+    """GroupConv used on its own with an input that requires a gradient (models.py:202-225 under autograd): the
+    CUDA-core input-gradient kernel against autograd through the fp64 oracle's group convolution.  The forward runs
+    FP16 operands (2e-3); the input gradient is an fp32 kernel over the fp32 rotated bank (1e-4)."""
+    import src.models as models
+    from oracle import target_vae_oracle as orc
+    torch.manual_seed(2)
+    conv = models.GroupConv(C, O, k, stride=1, padding=p, bias=True, input_rot_dim=1, output_rot_dim=G).to(DEV)
+    y = torch.randn(2, C, n, n, device=DEV, requires_grad=True)
+    out = conv(y, DEV)
+    yd = y.detach().double().cpu().requires_grad_(True)
+    wd = conv.weight.detach().double().cpu().requires_grad_(True)
+    ref = orc.groupconv_forward(yd, wd, conv.bias.detach().double().cpu(), G, p)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert rel_err(out.detach().cpu(), ref.detach()) < 2e-3
+    w = torch.randn(ref.shape)
+    (out * w.to(DEV)).sum().backward()
+    (ref * w.double()).sum().backward()
+    assert rel_err(y.grad.cpu(), yd.grad) < 1e-4
+    assert rel_err(conv.weight.grad.cpu(), wd.grad) < 5e-3
+
+
 def test_softmax_pair_autograd():
     from tvae_b200 import functional as TF
     g = torch.Generator().manual_seed(5)

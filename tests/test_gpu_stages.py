@@ -251,6 +251,53 @@ def test_generator_fwd_bwd(cfg, explicit_coords):
         assert v < 5e-3, (k, v)
 
 
+@pytest.mark.parametrize("layers,explicit_coords", [(2, False), (3, False), (2, True)])
+def test_generator_coord_fused_matches_unfused(layers, explicit_coords):
+    """Generators without Fourier features (cfg2): the coordinate layer fused into the first hidden layer's GEMM (a0 never
+    stored; hidden weight gradient regenerates it, input gradient masks with one bit per element) against the unfused
+    kernels of the same library (development knob 1 switches the fusion off) and against the fp64 oracle's forward.
+    n = 13 puts image boundaries inside 128-row tiles (169 pixels per image); layers = 3 leaves the projection to the
+    second hidden layer."""
+    ops = _ops()
+    cfg = HotPathConfig("t_fused", C=1, n=13, k=7, p=3, G=4, z=3, O=32, hidden=256, gen_layers=layers, fourier=False)
+    B = 5
+    enc, gen, x, y, ctf, nz = oracle_inputs(cfg, B, dtype=torch.float64)
+    g = torch.Generator().manual_seed(11)
+    theta = torch.randn(B, generator=g, dtype=torch.float64)
+    dx = torch.randn(B, 2, generator=g, dtype=torch.float64) * 0.1
+    zb = torch.randn(B, cfg.z, generator=g, dtype=torch.float64)
+    c, sn = torch.cos(theta), torch.sin(theta)
+    rot = torch.stack([torch.stack([c, sn], 1), torch.stack([-sn, c], 1)], 1)
+    xt = torch.bmm(x.expand(B, -1, 2) - dx.unsqueeze(1), rot)
+    y_ref = orc.generator_forward(xt, zb, gen)
+    t = lambda v: v.detach().float().to(DEV)
+    gw = ops.GenWeights(None, None, t(gen.coord_w), t(gen.coord_b), t(gen.latent_w), [t(w) for w in gen.hidden_w],
+                        [t(b) for b in gen.hidden_b], t(gen.out_w), t(gen.out_b))
+    N = cfg.n ** 2
+    s = ops.gen_shape(B, N, gw, cfg.z)
+    xin, th_in, dx_in = (t(xt).reshape(B * N, 2), None, None) if explicit_coords else (t(x), t(theta), t(dx))
+    D = torch.randn(B * N, cfg.n_out, generator=g).to(DEV)
+    res = {}
+    try:
+        for fused in (True, False):
+            ops.L().tvae_test_set_knob(1, 0 if fused else 1)
+            y_hat, saved = ops.generator_fwd(s, gw, xin, th_in, dx_in, t(zb))
+            out = ops.generator_bwd(s, gw, xin, th_in, dx_in, t(zb), saved, y_hat, D)
+            torch.cuda.synchronize()
+            res[fused] = (y_hat.clone(), {k: v.clone() for k, v in out.items() if k != "flat" and v is not None})
+    finally:
+        ops.L().tvae_test_set_knob(1, 0)
+    assert rel_err(res[True][0].cpu().view(B, N, -1), y_ref) < 5e-3
+    assert rel_err(res[True][0].cpu(), res[False][0].cpu()) < 2e-3
+    for k, v in res[True][1].items():
+        if explicit_coords and k in ("d_theta", "d_dx"):          # not computed with explicit coordinates (dxp is the gradient)
+            continue
+        e = rel_err(v.cpu(), res[False][1][k].cpu())
+        print(f"fused vs unfused {k}: {e:.1e}")
+        # a unit whose pre-activation rounds to the other side of zero in the two arithmetic orders flips its derivative
+        assert e < 2e-2, (k, e)
+
+
 def test_bernoulli_and_gaussian():
     ops = _ops()
     g = torch.Generator().manual_seed(6)
