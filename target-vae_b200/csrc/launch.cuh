@@ -136,6 +136,8 @@ inline int linear_tn_pair(const void* P, long long ldp, const void* Q, long long
     p.chunks_per_split = cdiv(p.chunks_total, splits);
     p.splits = cdiv(p.chunks_total, p.chunks_per_split);
     p.num_tiles = p.m_pairs * p.splits;
+    p.a_tma = (Ma % 64 == 0 && g_dev_knob[3] == 0) ? 1 : 0;
+    if (p.a_tma && (rc = make_tmap_3d_mn128_h(&p.tmP, P, R, Ma, ldp, kBKh, 2))) return rc;
     return launch_gemm2<LinearTNPair>(p, 0, stream);
 }
 

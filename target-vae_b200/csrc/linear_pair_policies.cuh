@@ -29,6 +29,8 @@ struct LinearTNPairParams {
     float* C;                 // stored TRANSPOSED: C[nb][ma] at C + nb * ldc + ma; zero-filled by the caller
     long long ldc;
     const float* acc_scale;   // device scalar multiplied into the accumulator (undoes the operands' power-of-two scale), or null
+    CUtensorMap tmP;          // a_tma == 1: P as {64 cols, rows, Ma / 64} (make_tmap_3d_mn128_h), boxes {64, 64 rows, 2}: one TMA fills the
+    int a_tma;                // CTA's whole A stage (two [64 rows][128 B] blocks, 128 B swizzle) - needs Ma % 64 == 0
 };
 
 struct LinearTNPair : PolicyBase {
@@ -40,7 +42,12 @@ struct LinearTNPair : PolicyBase {
     static constexpr bool kBMajorMN = true;
     struct TmaState { int row0; int jblk[kAcc]; };
     struct GenState { int q; };
-    __device__ static void prefetch_descs(const Params& p) { tma_prefetch_desc(&p.tmQ); }
+    // bytes the A-operand TMA loads of BOTH CTAs add to a stage's transaction count (tc_gemm2: the leader's expect_tx)
+    __device__ static uint32_t a_tx_bytes(const Params& p) { return p.a_tma ? 2u * kAStageBytes : 0u; }
+    __device__ static void prefetch_descs(const Params& p) {
+        tma_prefetch_desc(&p.tmQ);
+        if (p.a_tma) tma_prefetch_desc(&p.tmP);
+    }
     __device__ static void tile_info(const Params& p, int tile, uint32_t rank, PairTile& ti) {
         const int sp = tile / p.m_pairs;
         const int mp = tile - sp * p.m_pairs;
@@ -63,6 +70,9 @@ struct LinearTNPair : PolicyBase {
 #pragma unroll
         for (int a = 0; a < kAcc; ++a)
             if (a < ti.n_acc) tma_load_3d_pair(sb + a * kBHalfBytes, &p.tmQ, bar, 0, s.row0, s.jblk[a]);
+        // A operand (this CTA's 128 columns of P, 64 reduction rows) straight into the stage: the generator warps' copy through
+        // registers bound this kernel (84 % busy, the MMA issuer waiting for operands half of the time: clock64 probe)
+        if (p.a_tma) tma_load_3d_pair(sb - kAStageBytes, &p.tmP, bar, 0, s.row0, ti.a0 >> 6);
         s.row0 += kBKh;
     }
     __device__ static void gen_init(const Params&, GenState& s, uint8_t*, int) { s.q = 0; }
@@ -73,6 +83,7 @@ struct LinearTNPair : PolicyBase {
     // of a dpre row.  The 8 lanes of a store phase write the same 16-byte column of 8 consecutive rows = 8 distinct slots
     // of the 128 B swizzle.
     __device__ static void gen_chunk(const Params& p, const PairTile& ti, GenState& s, uint8_t* a_stage, uint8_t*, int gtid) {
+        if (p.a_tma) return;                   // the TMA producer loads A; the generator warps only keep the barrier protocol
         const int prow = gtid & 63, blk = gtid >> 6;
         const long long m = (long long)s.q * kBKh + prow;
         const int j0 = ti.a0 + blk * 64;

@@ -259,6 +259,7 @@ struct PolicyBase {
     template <class Prm, class Ti, class St> __device__ static void epi_tile_begin(const Prm&, const Ti&, St&, uint8_t*, int) {}   // tc_gemm2
     template <class Prm, class Ti, class St> __device__ static void epi_tile_end(const Prm&, const Ti&, St&, uint8_t*, int, bool) {}   // tc_gemm2
     template <class Prm, class St> __device__ static void gen_finish(const Prm&, St&) {}                        // tc_gemm2: after the last tile
+    template <class Prm> __device__ static uint32_t a_tx_bytes(const Prm&) { return 0u; }      // tc_gemm2: A operand loaded by TMA
     static constexpr bool kContiguousTiles = false;   // tc_gemm2: a pair takes a contiguous range of tiles instead of every n_pairs-th
     static constexpr int kStoreBufs = 0;      // tc_gemm2: > 0 = the epilogue leaves through that many staging buffers and the store issuer warp
     template <class Prm, class St> __device__ static void gen_init(const Prm&, St&, uint8_t*, int) {}

@@ -208,7 +208,7 @@ tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
                 for (int q = ti.kc_begin; q < ti.kc_end; ++q) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t fb = full_leader + 8 * stage;
-                    if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2u * ti.n_acc * kBHalfBytes);
+                    if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2u * ti.n_acc * kBHalfBytes + P::a_tx_bytes(prm));
                     const uint32_t sb = smem_u32(smem + L.stage_off + stage * kStage2Bytes + kAStageBytes);
                     P::tma_chunk(prm, ti, tst, sb, fb);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
