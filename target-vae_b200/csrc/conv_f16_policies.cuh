@@ -78,18 +78,28 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
 // chunk `chunk0` of the row's 128 bytes, of a staging buffer.  One warp per scheduler runs this, so it is written for
 // latency: the additive row of the NEXT 8 columns is loaded before the current 8 are stored (the compiler does not move a
 // shared-memory load above a shared-memory store), and LeakyReLU-or-identity is max(v, slope * v) without a branch.
-struct NoPost { __device__ void operator()(int, const float (&)[8]) const {} };
+// Post-processing hook of the staged epilogue: load(col) fetches what apply() needs for the 8 columns starting at col - it is
+// called one 8-column group AHEAD (before the previous group's shared-memory store, which the compiler will not move a
+// load across), apply(w, col, v) sees the group's fp32 values after the activation.
+struct NoPost {
+    struct W {};
+    __device__ W load(int) const { return W(); }
+    __device__ void apply(const W&, int, const float (&)[8]) const {}
+};
 template <bool TANH, int NV, class Post = NoPost>
 __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const float* add, bool act, uint8_t* buf, int row, int chunk0,
                                                 Post post = Post(), int col0 = 0) {
     const float slope = act ? kLreluSlope : 1.f;
     float4 b0 = *reinterpret_cast<const float4*>(add), b1 = *reinterpret_cast<const float4*>(add + 4);
+    typename Post::W pw = post.load(col0);
 #pragma unroll
     for (int j = 0; j < NV; j += 8) {
         float4 n0 = b0, n1 = b1;
+        typename Post::W pn = pw;
         if (j + 8 < NV) {
             n0 = *reinterpret_cast<const float4*>(add + j + 8);
             n1 = *reinterpret_cast<const float4*>(add + j + 12);
+            pn = post.load(col0 + j + 8);
         }
         float v[8];
         v[0] = __uint_as_float(rr[j]) + b0.x;     v[1] = __uint_as_float(rr[j + 1]) + b0.y;
@@ -102,7 +112,7 @@ __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const 
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], slope * v[q]);
         }
-        post(col0 + j, v);
+        post.apply(pw, col0 + j, v);
         uint4 q4;
         __half2 hv;
         hv = __floats2half2_rn(v[0], v[1]); q4.x = *reinterpret_cast<uint32_t*>(&hv);
@@ -111,6 +121,7 @@ __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const 
         hv = __floats2half2_rn(v[6], v[7]); q4.w = *reinterpret_cast<uint32_t*>(&hv);
         *reinterpret_cast<uint4*>(buf + sw128_offset(row, chunk0 + (j >> 3))) = q4;
         b0 = n0; b1 = n1;
+        pw = pn;
     }
 }
 

@@ -252,6 +252,33 @@ struct GenL1FwdPairParams {
 // - coordinate transform, first layer, hidden layer and output projection in ONE kernel; a0 (0.42 GB at cfg2) is never written
 // or read.  The backward pass regenerates a0 for the hidden weight gradient (GenL1WgradPairT<1>) and takes the LeakyReLU mask of
 // the input gradient from mask_bits (one bit per element, written here by the generator warps).
+// Fused output projection of the staged epilogue (fp32 activations): proj[o] += sum_j v[j] * w[o][col + j].  The first output's
+// weights are fetched one column group ahead (NoPost's contract); further outputs (n_proj <= 4) load theirs in place.
+struct ProjPost {
+    const float* s_proj;      // [n_proj][H] in shared memory, already offset to the accumulator's first column
+    int n_proj, H;
+    float* proj;              // the row's four accumulators (registers of the caller)
+    struct W { float4 a, b; };
+    __device__ W load(int col) const {
+        W w;
+        w.a = *reinterpret_cast<const float4*>(s_proj + col);
+        w.b = *reinterpret_cast<const float4*>(s_proj + col + 4);
+        return w;
+    }
+    __device__ static float dot8(const float4& a, const float4& b, const float (&v)[8]) {
+        // four independent chains (one warp per scheduler: dependent FMAs cost their latency)
+        const float t0 = fmaf(v[1], a.y, v[0] * a.x), t1 = fmaf(v[3], a.w, v[2] * a.z);
+        const float t2 = fmaf(v[5], b.y, v[4] * b.x), t3 = fmaf(v[7], b.w, v[6] * b.z);
+        return (t0 + t1) + (t2 + t3);
+    }
+    __device__ void apply(const W& w, int col, const float (&v)[8]) const {
+        if (n_proj > 0) proj[0] += dot8(w.a, w.b, v);
+#pragma unroll
+        for (int o = 1; o < 4; ++o)               // static indices: proj[] stays in registers
+            if (o < n_proj) proj[o] += dot8(*reinterpret_cast<const float4*>(s_proj + o * H + col), *reinterpret_cast<const float4*>(s_proj + o * H + col + 4), v);
+    }
+};
+
 template <bool TANH, int FEAT = 0>
 struct GenL1FwdPairT : PolicyBase {
     static constexpr const char* kName = "gen_l1_fwd";
@@ -435,23 +462,9 @@ struct GenL1FwdPairT : PolicyBase {
                                     uint8_t* extra) {
         const float* tab = reinterpret_cast<const float*>(extra + p.tab_off) + st.sel * p.H;
         if constexpr (FEAT == 1) {
-            const float* s_proj = reinterpret_cast<const float*>(extra + p.proj_off) + n0;
-            const int n_proj = p.n_proj, H = p.H;
+            ProjPost post{reinterpret_cast<const float*>(extra + p.proj_off) + n0, p.n_proj, p.H, st.proj};
             staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
-                                              [&](int blk) { return tab + n0 + blk * 64; },
-                                              [&](int col, const float (&v)[8]) {          // fused output projection (fp32 activations)
-#pragma unroll
-                                                  for (int o = 0; o < 4; ++o) {            // static indices: proj[] stays in registers
-                                                      if (o < n_proj) {
-                                                          const float4 w0 = *reinterpret_cast<const float4*>(s_proj + o * H + col);
-                                                          const float4 w1 = *reinterpret_cast<const float4*>(s_proj + o * H + col + 4);
-                                                          // four independent chains (one warp per scheduler: dependent FMAs cost their latency)
-                                                          const float t0 = fmaf(v[1], w0.y, v[0] * w0.x), t1 = fmaf(v[3], w0.w, v[2] * w0.z);
-                                                          const float t2 = fmaf(v[5], w1.y, v[4] * w1.x), t3 = fmaf(v[7], w1.w, v[6] * w1.z);
-                                                          st.proj[o] += (t0 + t1) + (t2 + t3);
-                                                      }
-                                                  }
-                                              });
+                                              [&](int blk) { return tab + n0 + blk * 64; }, post);
         } else {
             staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
                                               [&](int blk) { return tab + n0 + blk * 64; });
