@@ -440,6 +440,15 @@ def kernel_rooflines(cfg, B, prof, K, ms_step, peaks, clk_summary, ops):
     if Lh > 0:
         tensor["linear_nt"] = 2.0 * Lh * 2.0 * H * H * M          # forward + input-gradient GEMM of every hidden layer
         tensor["linear_tn"] = Lh * 2.0 * H * H * M                 # weight-gradient GEMM of every hidden layer
+        if not cfg.fourier and "gen_l1_fwd" in prof:
+            # generators without Fourier features (cfg2): the first hidden layer's forward GEMM runs inside gen_l1_fwd (the
+            # coordinate layer is its generated operand), its weight gradient inside gen_l1_wgrad (coordinate layer
+            # regenerated); linear_nt keeps that layer's input gradient and every GEMM of the further hidden layers
+            one = 2.0 * H * H * M
+            tensor["gen_l1_fwd"] = one
+            tensor["gen_l1_wgrad"] = one
+            tensor["linear_nt"] -= one
+            tensor["linear_tn"] -= one
     if cfg.ctf:
         tensor["ctf_apply"] = 2.0 * 2.0 * cfg.n ** 2 * (cfg.n - 1) ** 2 * B
     hbm = {
