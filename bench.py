@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU minibatch (default: the trainer's 100; cfg5: 256)")
     ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step's kernels eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg1/cfg3/cfg4/cfg5 measurements of the `configs` block")
     return ap.parse_args()
 
@@ -408,6 +409,17 @@ class Workload:
     def step_resident(self, i):
         return self.step(self.y_dev[i % self.NB], self.ctf_dev[i % self.NB])
 
+    def graphed(self):
+        """the same step (same public call, same models) captured once as a CUDA graph: tvae_b200.graph.GraphedStep"""
+        from tvae_b200.graph import GraphedStep
+        cfg = self.cfg
+        if cfg.likelihood == "gaussian":
+            return GraphedStep(self.x, self.y_dev[0].shape, self.gen, self.enc, "attention", self.r_inf, self.ctx.dev, cfg.theta_prior,
+                               cfg.G, ctf_shape=None if self.ctf_dev[0] is None else self.ctf_dev[0].shape, particles=True,
+                               padding=cfg.p, mask_radius=cfg.mask_radius, sync=self.sync)
+        return GraphedStep(self.x, self.y_dev[0].shape, self.gen, self.enc, "attention", self.r_inf, self.ctx.dev, cfg.theta_prior,
+                           cfg.G, cfg.n, sync=self.sync)
+
     def step_e2e(self, i):
         """the public call with HOST buffers: H2D of the step's inputs from pinned memory + D2H read of the ELBO"""
         self.y_stage.copy_(self.y_pin[i % self.NB], non_blocking=True)
@@ -501,6 +513,9 @@ def kernel_rooflines(cfg, B, prof, K, ms_step, peaks, clk_summary, ops):
             "peak_source": peaks["source"], "ms_per_launch": d["ms_per_step"] / max(d["launches_per_step"], 1e-9),
             "ms_per_step": d["ms_per_step"],
             "share_of_step": d["share_of_step"],
+            "timed_in": "launch durations from the library's CUDA events on the launching stream over K eagerly enqueued steps (the "
+                        "`ms_per_step_eager` pass, timed like the value pass right after it: events cannot be read back from the captured "
+                        "graph the value pass replays); share_of_step refers to that pass",
             "precision": "every contraction is tcgen05.mma.kind::f16: FP16 operands (11-bit significand = TF32's, the reference's "
                          "cuDNN default; NARROWER than the fp32 SGEMM the reference's generator nn.Linear layers use by default - "
                          "per-parameter effect: profiles/r02_grad_parity_table.md) with FP32 accumulation; gradients carry exact "
@@ -515,30 +530,57 @@ def kernel_rooflines(cfg, B, prof, K, ms_step, peaks, clk_summary, ops):
     return roof
 
 
-def measure_config(ctx, cfg, B, K, W, legs=("e2e",)):
+def measure_config(ctx, cfg, B, K, W, legs=("e2e",), graph=True):
     """value (inputs resident in HBM) [+ e2e / train-step / get_latent legs] of one config at ctx.world GPUs."""
     from tvae_b200 import ops
     wl = Workload(ctx, cfg, B)
+    world = ctx.world
+    # ---- value: K replays of the step captured once as a CUDA graph (tvae_b200.graph.GraphedStep - the same public call on the
+    # same models, NCCL bucket all-reduces included at N > 1), inputs resident in HBM: each step copies the next minibatch
+    # device -> device into the graph's staging buffer and replays.  --no-graph: the eager launch sequence instead.
+    gs = wl.graphed() if graph else None
+
+    def value_step(i):
+        if gs is None:
+            return wl.step_resident(i)
+        return gs(wl.y_dev[i % wl.NB], wl.ctf_dev[i % wl.NB])
+
+    def e2e_step(i):
+        if gs is None:
+            return wl.step_e2e(i)
+        # HOST buffers in (pinned: asynchronous H2D into the staging buffers), ELBO out (D2H, synchronises)
+        return float(gs(wl.y_pin[i % wl.NB], wl.ctf_pin[i % wl.NB])[0])
+
     with ClockSampler(ctx.local) as clk:
         for i in range(W):
-            wl.step_resident(i)
+            value_step(i)
         ctx.barrier()
-        launches0 = ops.launch_count()
-        ops.profile_enable(True)
         clk.mark(True)
-        ms_total = ctx.timed(wl.step_resident, K)
+        ms_total = ctx.timed(value_step, K)
         clk.mark(False)
+    # ---- per-kernel rooflines: the SAME K steps enqueued eagerly with the library's CUDA events around every launch (events
+    # cannot be read back from a captured stream), timed the same way; kernel shares refer to this pass
+    for i in range(2):
+        wl.step_resident(i)
+    ctx.barrier()
+    launches0 = ops.launch_count()
+    ops.profile_enable(True)
+    ms_eager = ctx.timed(wl.step_resident, K)
     prof = ops.profile_collect()
     ops.profile_enable(False)
     launches = ops.launch_count() - launches0
-    world = ctx.world
+    if gs is not None:
+        launches = gs.launches_per_replay * K
     res = {"value": world * B * K / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total / K, "steps": K, "warmup": W,
            "per_gpu_batch": B, "gpu_launches": launches, "clocks": clk.summary(),
+           "launch": ("one CUDA graph replay per step (GraphedStep: eval_minibatch + backward captured once; "
+                      f"{gs.launches_per_replay} library kernels per replay)") if gs is not None else "eager kernel launches",
+           "ms_per_step_eager": ms_eager / K,
            "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12}
     if "e2e" in legs:
         for i in range(2):
-            wl.step_e2e(i)
-        e2e_ms = ctx.timed(wl.step_e2e, K)
+            e2e_step(i)
+        e2e_ms = ctx.timed(e2e_step, K)
         res["e2e"] = {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4}
     if "train" in legs:
         # SURVEY 8f-1: a true train step - the same fwd + bwd with the optimiser fused behind the gradient buckets: one
@@ -569,7 +611,7 @@ def measure_config(ctx, cfg, B, K, W, legs=("e2e",)):
     if "dp_parity" in legs and world > 1:
         res["dp_parity"] = dp_parity_check(ctx, wl)
     if ctx.rank == 0:
-        res["roofline"] = kernel_rooflines(cfg, B, prof, K, ms_total / K, measured_peaks(), res["clocks"], ops)
+        res["roofline"] = kernel_rooflines(cfg, B, prof, K, ms_eager / K, measured_peaks(), res["clocks"], ops)
     return res, wl
 
 
@@ -611,7 +653,7 @@ def run_ours(args, cfg):
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     B = args.batch or cfg.batch
     W, K = max(args.warmup, 3), args.steps
-    main, wl = measure_config(ctx, cfg, B, K, W, legs=("e2e", "train", "latent", "dp_parity"))
+    main, wl = measure_config(ctx, cfg, B, K, W, legs=("e2e", "train", "latent", "dp_parity"), graph=not args.no_graph)
     del wl
     torch.cuda.empty_cache()
 
@@ -625,7 +667,7 @@ def run_ours(args, cfg):
             c = PRESETS[name]
             k = max(3, min(K, 8 if name != "cfg5" else 4))
             try:
-                r, w2 = measure_config(ctx, c, c.batch, k, 3, legs=("e2e",))
+                r, w2 = measure_config(ctx, c, c.batch, k, 3, legs=("e2e",), graph=not args.no_graph)
                 del w2
                 r["workload"] = workload_config(c, c.batch, world)["workload"]
                 if rank == 0 and r.get("roofline"):
@@ -667,7 +709,8 @@ def run_ours(args, cfg):
 
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "ms_per_step": main["ms_per_step"], "ms_per_step_eager": main["ms_per_step_eager"], "launch": main["launch"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "config": workload_config(cfg, B, world),
         "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "roofline": main["roofline"],
         "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "tflops_step": main["tflops_step"],

@@ -812,6 +812,40 @@ __global__ void __launch_bounds__(1024) group_colsum_kernel(const __half* __rest
     if (total) atomicAdd(total + c, acc);
 }
 
+// the same for W % 8 == 0, W <= 2048: thread = (8 adjacent columns, row slot), 16-byte loads, blockDim.x = (W / 8) * slots
+// with slots = 256 / (W / 8); the row slots are combined through shared memory before the atomics.
+__global__ void __launch_bounds__(256) group_colsum8_kernel(const __half* __restrict__ x, const float* __restrict__ inv_scale,
+                                                            float* __restrict__ out, float* __restrict__ total, int rows_per_group,
+                                                            int W, int rows_per_cta) {
+    extern __shared__ float s_part[];                    // [slots][W]
+    const int cgs = W / 8, slots = blockDim.x / cgs;
+    const int cg = threadIdx.x % cgs, slot = threadIdx.x / cgs, g = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows_per_group);
+    const __half* xg = x + ((long long)g * rows_per_group) * W + cg * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int r = r0 + slot; r < r1; r += slots) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(xg + (long long)r * W));
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+            acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_part[slot * W + cg * 8 + e] = acc[e];
+    __syncthreads();
+    const float inv = __ldg(inv_scale);
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        float v = 0.f;
+        for (int q = 0; q < slots; ++q) v += s_part[q * W + c];
+        v *= inv;
+        if (out) atomicAdd(out + (long long)g * W + c, v);
+        if (total) atomicAdd(total + c, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Power-of-two scales that keep the encoder's backward intermediates inside fp16's range.
 //   amax[0] = max |x| over a tensor (float bits compared as ints: all values are >= 0)
@@ -1004,30 +1038,29 @@ __global__ void __launch_bounds__(256) rot_pool_bwd_kernel(RotPoolParams p) {
 // Generator backward: dpre_L = (d_yhat . Wout) lrelu', dpre_{i-1} = (dpre_i . W_i) lrelu'; dpre_i is stored as
 // fp16(dpre_i * s_i) with s_i = scales[2i], 1/s_i = scales[2i + 1], i = 0..L.  Bounds: |dpre_L| <= amax max_c sum_o |Wout[o][c]|,
 // |dpre_{i-1}| <= bound_i max_c sum_j |W_i[j][c]|.
-// Step 1 (one CTA of 1024 threads per layer): colmax[layer] = max_c sum_j |W[j][c]|, thread = (column, quarter of the rows).
+// Step 1: colmax[layer] = max_c sum_j |W[j][c]|.  grid = (column slices of 32, L + 1 layers), block = 32 columns x 32 row
+// parts (one CTA per layer walked the whole 1 MB matrix alone: 23 us); colmax zero-filled by the caller.
 __global__ void __launch_bounds__(1024) gen_colmax_kernel(const float* __restrict__ wout, int n_out, const float* __restrict__ wh,
                                                           int L, int H, float* __restrict__ colmax) {
-    extern __shared__ float s_col[];                     // [H] column abs-sums
-    const int layer = blockIdx.x;                        // layer == L: Wout (n_out x H); else W_{layer+1} = wh[layer] (H x H)
+    __shared__ float s_part[32][33];
+    const int layer = blockIdx.y;                        // layer == L: Wout (n_out x H); else W_{layer+1} = wh[layer] (H x H)
     const float* w = layer == L ? wout : wh + (long long)layer * H * H;
     const int rows = layer == L ? n_out : H;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) s_col[c] = 0.f;
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float a = 0.f;
+    if (c < H)
+        for (int j = part; j < rows; j += 32) a += fabsf(__ldg(w + (long long)j * H + c));
+    s_part[part][lane] = a;
     __syncthreads();
-    // blockDim.x = parts * H: thread = (column c, row slice `part`)
-    const int parts = blockDim.x / H;
-    const int per = (rows + parts - 1) / parts;
-    {
-        const int c = threadIdx.x % H, part = threadIdx.x / H;
-        float a = 0.f;
-        for (int j = part * per; j < rows && j < (part + 1) * per; ++j) a += fabsf(w[(long long)j * H + c]);
-        atomicAdd(&s_col[c], a);
-    }
-    __syncthreads();
-    float m = 0.f;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) m = fmaxf(m, s_col[c]);
+    if (part == 0) {
+        float m = 0.f;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(colmax + layer), __float_as_int(m));
+        for (int q = 0; q < 32; ++q) m += s_part[q][lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(colmax + layer), __float_as_int(m));
+    }
 }
 // Step 2 (one thread): chain the bounds.  colmax must be zero-filled before step 1.
 __global__ void gen_bwd_scales_kernel(const float* __restrict__ amax, const float* __restrict__ colmax, int L, float* __restrict__ scales) {

@@ -918,8 +918,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     TVAE_CHECK_CUDA(cudaMemsetAsync(a->scales, 0, sizeof(float) * 32, st));
     ++g_launch_count; absmax_kernel<<<blocks_for(M * s->n_out, 256), 256, 0, st>>>(a->d_yhat, M * s->n_out, a->scales + 31);
     {   // scales[20 .. 20 + L]: per-layer max column abs-sum of the weights (L <= 8)
-        const int threads = H >= 1024 ? 1024 : (1024 / H) * H;
-        ++g_launch_count; gen_colmax_kernel<<<L + 1, threads, H * sizeof(float), st>>>(a->f.wout, s->n_out, a->f.wh, L, H, a->scales + 20);
+        ++g_launch_count; gen_colmax_kernel<<<dim3(cdiv(H, 32), L + 1), 1024, 0, st>>>(a->f.wout, s->n_out, a->f.wh, L, H, a->scales + 20);
         ++g_launch_count; gen_bwd_scales_kernel<<<1, 1, 0, st>>>(a->scales + 31, a->scales + 20, L, a->scales);
     }
     __half* dcur = static_cast<__half*>(a->dpre0);
@@ -983,7 +982,15 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         for (int r = kCoordRB; r <= s->N && r <= 512; r += kCoordRB)
             if (s->N % r == 0) coord_rows = r;
     }
-    if (!coord_rows) { ++g_launch_count; group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512); }
+    if (!coord_rows) {
+        ++g_launch_count;
+        if (H % 8 == 0 && H / 8 <= 256) {
+            const int cgs = H / 8, slots = 256 / cgs;
+            group_colsum8_kernel<<<dim3(cdiv(s->N, 512), s->B), cgs * slots, sizeof(float) * slots * H, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512);
+        } else {
+            group_colsum_kernel<<<dim3(cdiv(s->N, 512), s->B), H, 0, st>>>(dcur, a->scales + 1, a->dzb, a->db1, s->N, H, 512);
+        }
+    }
     // ---- layer 1 weight and coordinate gradients
     if (E > 0) {
         if (H % 128 == 0 && H <= 2 * kAccN) {
@@ -1057,7 +1064,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
                                                                       coord_rows ? a->dzb : nullptr, a->db1, H, static_cast<int>(rows));
         TVAE_CHECK_CUDA(cudaGetLastError());
     }
-    ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B > H ? s->B : H) * s->zdim, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
+    ++g_launch_count; latent_bias_bwd_kernel<<<cdiv((s->B + H) * s->zdim * 32, 128), 128, 0, st>>>(a->dzb, a->f.z, a->f.wz, a->dwz, a->d_z, s->B, H, s->zdim);
     TVAE_CHECK_CUDA(cudaGetLastError());
     if (a->f.theta && a->d_theta) {
         ++g_launch_count; coord_xform_bwd_kernel<<<s->B, 256, 0, st>>>(cx, a->dxp, a->d_theta, a->d_dx);

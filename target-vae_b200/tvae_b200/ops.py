@@ -556,8 +556,17 @@ def conv1_executed_fraction(s: EncShape, wgrad: bool) -> float:
     return float(L().tvae_conv1_executed_fraction(ctypes.cast(ctypes.pointer(s), c_void_p), 1 if wgrad else 0))
 
 
+_profiling = False
+
+
 def profile_enable(on: bool) -> None:
+    global _profiling
+    _profiling = bool(on)
     L().tvae_profile_enable(1 if on else 0)
+
+
+def profile_enabled() -> bool:
+    return _profiling
 
 
 def profile_collect():
