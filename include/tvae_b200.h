@@ -216,6 +216,10 @@ typedef struct {
     void* acts;              /* out fp16 [L+1][B*N][H] post-activation of every hidden layer */
     float* y_hat;            /* out (B*N, n_out) */
     void* w_h;               /* scratch fp16: H*max(E,2) + L*H*H halves (fp16 copies of the weights) */
+    void* mask_bits;         /* optional out, max(L,1) * (H/64) * B*N 64-bit words (LeakyReLU, H % 64 == 0): word (layer l, column
+                              * block c, row m) holds the derivative mask of acts[l][m][64c .. 64c+63] (bit set = 1, clear = the
+                              * LeakyReLU slope), written by the forward kernels; the backward pass then reads one bit per element
+                              * instead of the fp16 activation in the hidden layers' input gradients.  NULL: masks from acts. */
 } tvae_gen_fwd_args;
 int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void* stream);
 

@@ -81,10 +81,35 @@ __device__ __forceinline__ const uint32_t* slab16_words(const uint32_t* slabw, c
 // Post-processing hook of the staged epilogue: load(col) fetches what apply() needs for the 8 columns starting at col - it is
 // called one 8-column group AHEAD (before the previous group's shared-memory store, which the compiler will not move a
 // load across), apply(w, col, v) sees the group's fp32 values after the activation.
+// packed(col0, j, q) sees the same group as 8 packed halves (what is stored), j = its static offset inside the 32-column piece.
 struct NoPost {
     struct W {};
     __device__ W load(int) const { return W(); }
     __device__ void apply(const W&, int, const float (&)[8]) const {}
+    __device__ void packed(int, int, const uint4&) const {}
+};
+// One-bit LeakyReLU derivative mask of the stored activation (bit set = derivative 1, i.e. the stored half is not negative):
+// word (column / 64, row) of a [H / 64][M] array - the layout LinearNT's input-gradient epilogue reads (aux_bits).  `dst` points
+// at the row's word of the accumulator's first 64-column block (null: row past M or no mask wanted); lo / acc are two
+// registers of the caller.
+struct MaskBitsPost {
+    unsigned long long* dst;
+    long long M;
+    uint32_t* lo; uint32_t* acc;
+    struct W {};
+    __device__ W load(int) const { return W(); }
+    __device__ void apply(const W&, int, const float (&)[8]) const {}
+    __device__ void packed(int col0, int j, const uint4& q) const {
+        *acc |= half8_sign_bits(q) << j;
+        if (j == 24) {
+            if (col0 & 32) {
+                if (dst) dst[(long long)(col0 >> 6) * M] = ~((static_cast<unsigned long long>(*acc) << 32) | *lo);
+            } else {
+                *lo = *acc;
+            }
+            *acc = 0u;
+        }
+    }
 };
 template <bool TANH, int NV, class Post = NoPost>
 __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const float* add, bool act, uint8_t* buf, int row, int chunk0,
@@ -120,6 +145,7 @@ __device__ __forceinline__ void epi_piece_store(const uint32_t (&rr)[NV], const 
         hv = __floats2half2_rn(v[4], v[5]); q4.z = *reinterpret_cast<uint32_t*>(&hv);
         hv = __floats2half2_rn(v[6], v[7]); q4.w = *reinterpret_cast<uint32_t*>(&hv);
         *reinterpret_cast<uint4*>(buf + sw128_offset(row, chunk0 + (j >> 3))) = q4;
+        post.packed(col0, j, q4);
         b0 = n0; b1 = n1;
         pw = pn;
     }

@@ -240,6 +240,7 @@ struct GenL1FwdPairParams {
     // FEAT = 1: the coordinate layer's activation is the generated operand (wf_scaled / bf = its weight (E,2) / bias (E))
     const float* zbc;         // latent bias (B,E) of the coordinate layer
     unsigned long long* mask_bits;   // out [E/64][M]: bit q of word (kc, m) = (pre-activation of feature 64 kc + q > 0), or null
+                                     // FEAT = 0 (LeakyReLU): out [H/64][M], the same one-bit mask of the STORED activation h1, or null
     const float* proj_w; const float* proj_bias; float* proj_out;   // fused output projection proj_out[m][o] = sum_j act[m][j] proj_w[o][j] + proj_bias[o]
     int n_proj, proj_off;     // n_proj <= 4 (0: none); proj_off: byte offset of the [n_proj][H] weight rows in the extra smem
 };
@@ -271,6 +272,7 @@ struct ProjPost {
         const float t2 = fmaf(v[5], b.y, v[4] * b.x), t3 = fmaf(v[7], b.w, v[6] * b.z);
         return (t0 + t1) + (t2 + t3);
     }
+    __device__ void packed(int, int, const uint4&) const {}
     __device__ void apply(const W& w, int col, const float (&v)[8]) const {
         if (n_proj > 0) proj[0] += dot8(w.a, w.b, v);
 #pragma unroll
@@ -463,6 +465,15 @@ struct GenL1FwdPairT : PolicyBase {
         const float* tab = reinterpret_cast<const float*>(extra + p.tab_off) + st.sel * p.H;
         if constexpr (FEAT == 1) {
             ProjPost post{reinterpret_cast<const float*>(extra + p.proj_off) + n0, p.n_proj, p.H, st.proj};
+            staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
+                                              [&](int blk) { return tab + n0 + blk * 64; }, post);
+        } else if constexpr (!TANH) {
+            // + the one-bit derivative mask of h1 for the first hidden layer's input gradient (0.1 GB instead of a second
+            // 1.7 GB read of h1 at cfg4)
+            const long long m = (long long)ti.a0 + row;
+            uint32_t lo = 0u, acc = 0u;
+            MaskBitsPost post{(p.mask_bits && has_work && ti.m_tile >= 0 && m < p.cx.M) ? p.mask_bits + (long long)(n0 >> 6) * p.cx.M + m : nullptr,
+                              p.cx.M, &lo, &acc};
             staged_store_epilogue<TANH, 3, 3>(taddr, store_blocks(p, ti, n0, has_work), st, extra + p.stage_off, row, true,
                                               [&](int blk) { return tab + n0 + blk * 64; }, post);
         } else {

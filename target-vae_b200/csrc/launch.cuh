@@ -73,6 +73,7 @@ struct LinearNTArgs {
     void* C16 = nullptr; long long ldc16 = 0;
     const void* aux16 = nullptr; int aux_act = 0;
     const unsigned long long* aux_bits = nullptr;
+    unsigned long long* bits_out = nullptr;
     const float* acc_scale = nullptr; const float* store_scale = nullptr;
     float* colsum = nullptr; long long colsum_stride = 1;
 };
@@ -104,6 +105,8 @@ inline int linear_nt(const LinearNTArgs& a, cudaStream_t stream) {
     p.cs_off = (1 + a.n_proj) * p.npad;
     int extra = (LinearNT<128>::extra_floats(a.N, a.n_proj, a.colsum != nullptr) * 4 + 1023) / 1024 * 1024;
     p.tma_store = (a.C16 != nullptr && a.N % 64 == 0) ? 1 : 0;
+    TVAE_REQUIRE(!a.bits_out || p.tma_store, "linear_nt: the one-bit mask output needs an fp16 output with N % 64 == 0");
+    p.bits_out = a.bits_out;
     p.stage_off = extra;
     if (p.tma_store) {
         if ((rc = make_tmap_2d_h(&p.tmC, a.C16, a.M, a.N, a.ldc16, kBM))) return rc;

@@ -50,6 +50,8 @@ struct LinearNTParams {
     const void* aux16;        // [M][ld_aux] fp16 or null: multiply by lrelu'(aux16)
     const unsigned long long* aux_bits;   // [N/64][M] or null: bit q of word (n/64, m) set = derivative 1, clear = LeakyReLU slope
                                           // (the one-bit form of aux16, written by GenL1FwdPairT<., 1>; N % 64 == 0)
+    unsigned long long* bits_out;         // [N/64][M] or null: the same one-bit mask of the fp16 values stored here (forward: what the
+                                          // NEXT layer's input gradient needs of this layer's activation); needs tma_store
     const float* acc_scale;   // device scalar multiplied into the accumulator first (undoes the operand's scale) or null
     const float* store_scale; // device scalar applied to the fp16 store only (power of two) or null
     float* colsum;            // colsum[n * colsum_stride] += sum_m value[m][n] (bias gradient) or null
@@ -170,6 +172,7 @@ struct LinearNT : PolicyBase {
             for (int w = 0; w < BN / 64; ++w)
                 mbits[w] = (m_ok && ti.n0 + 64 * w < p.N) ? __ldg(p.aux_bits + (long long)(ti.n0 / 64 + w) * p.M + m) : 0ull;
         }
+        uint32_t neg_lo = 0u;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
@@ -255,6 +258,7 @@ struct LinearNT : PolicyBase {
                     if (row == 0) tma_store_wait_read<1>();
                     named_bar_sync(2 + st.grp, kEpiWarps * 32);
                 }
+                uint32_t neg = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     uint4 t;
@@ -264,6 +268,14 @@ struct LinearNT : PolicyBase {
                     h = __floats2half2_rn(v[j + 4] * store_scale, v[j + 5] * store_scale); t.z = *reinterpret_cast<uint32_t*>(&h);
                     h = __floats2half2_rn(v[j + 6] * store_scale, v[j + 7] * store_scale); t.w = *reinterpret_cast<uint32_t*>(&h);
                     *reinterpret_cast<uint4*>(buf + sw128_offset(row, (c & 1) * 4 + (j >> 3))) = t;
+                    if (p.bits_out) neg |= half8_sign_bits(t) << j;
+                }
+                if (p.bits_out) {
+                    if (c & 1) {
+                        if (m_ok) p.bits_out[(long long)((n_base - 32) >> 6) * p.M + m] = ~((static_cast<unsigned long long>(neg) << 32) | neg_lo);
+                    } else {
+                        neg_lo = neg;
+                    }
                 }
                 if (c & 1) {
                     fence_proxy_async_smem();

@@ -182,4 +182,15 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_ma
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
     return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }
+// bit i = sign bit of the i-th of 8 packed halves: two PRMTs replicate the four sign bits of a register pair over whole
+// bytes, a mask + multiply gathers them into a nibble
+__device__ __forceinline__ uint32_t half8_sign_bits(const uint4& q) {
+    uint32_t s01, s23;
+    asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(s01) : "r"(q.x), "r"(q.y));
+    asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(s23) : "r"(q.z), "r"(q.w));
+    const uint32_t n0 = ((s01 & 0x08040201u) * 0x01010101u) >> 24;
+    const uint32_t n1 = ((s23 & 0x08040201u) * 0x01010101u) >> 24;
+    return n0 | (n1 << 4);
+}
+
 }  // namespace tvae

@@ -126,7 +126,7 @@ int launch_split_tn(typename P::Params& p, int out_tiles, int chunks_total, int 
 extern "C" {
 
 const char* tvae_last_error(void) { return g_last_error.c_str(); }
-int tvae_version(void) { return 101; }   // 101: act in the shape structs, rotation-pooling fields in the encoder arguments
+int tvae_version(void) { return 102; }   // 102: tvae_gen_fwd_args.mask_bits; 101: act in the shape structs, rotation-pooling fields in the encoder arguments
 long long tvae_launch_count(void) { return g_launch_count.load(); }
 
 // per-kernel timing of the tensor-core GEMM launches (CUDA events on the launching stream)
@@ -777,6 +777,20 @@ static bool gen_coord_fused(const tvae_gen_shape* s) {
            s->N >= kBM && (long long)s->B * s->N < (1LL << 31);
 }
 
+// Fourier generators on the pair kernel (GenL1FwdPairT<., 0>)
+static bool gen_l1_pair(const tvae_gen_shape* s) {
+    return s->E > 0 && s->H % 64 == 0 && s->H <= 2 * kAccN && s->H > 128 && s->N >= kBM;
+}
+// One-bit LeakyReLU masks (tvae_gen_fwd_args.mask_bits): is the mask of acts[layer] written by the forward pass?  Layer 0 by the
+// pair kernel of the Fourier layer, layers 1 .. L-1 by the hidden layers' LinearNT epilogues (acts[L] feeds the output layer's
+// backward kernel, which reads the activation itself).  The coordinate-fused path keeps its own mask in the acts[0] buffer.
+static unsigned long long* gen_mask_words(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, int layer) {
+    if (!a->mask_bits || s->act != TVAE_ACT_LEAKYRELU || s->H % 64 != 0 || layer >= s->L) return nullptr;
+    if (layer == 0 && !gen_l1_pair(s)) return nullptr;
+    if (layer == 1 && gen_coord_fused(s)) return nullptr;            // acts[1] is written by the fused coordinate-layer kernel
+    return static_cast<unsigned long long*>(a->mask_bits) + (long long)layer * (s->H / 64) * s->B * s->N;
+}
+
 static CoordXform make_xform(const tvae_gen_shape* s, const tvae_gen_fwd_args* a) {
     CoordXform c{};
     c.x = a->x; c.theta = a->theta; c.dx = a->dx; c.N = s->N; c.M = (long long)s->B * s->N;
@@ -800,9 +814,10 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
     int first_hidden = 1;
     if (E > 0) {
         ++g_launch_count; to_half_kernel<<<blocks_for((long long)H * E, 256), 256, 0, st>>>(a->w1, w1h, (long long)H * E);
-        if (H % 64 == 0 && H <= 2 * kAccN && H > 128 && s->N >= kBM) {
+        if (gen_l1_pair(s)) {
             // CTA-pair kernel: every generated feature chunk feeds all H hidden columns (gen_pair_policies.cuh)
             GenL1FwdPairParams q{};
+            q.mask_bits = gen_mask_words(s, a, 0);
             if ((rc = make_tmap_2d_h(&q.tmB, w1h, H, E, E, 128))) return rc;
             if ((rc = make_tmap_2d_h(&q.tmC, a0, M, H, H, kBM))) return rc;
             q.cx = cx; q.wf_scaled = a->wf_scaled; q.bf = a->bf; q.E = E; q.H = H;
@@ -890,6 +905,7 @@ int tvae_generator_fwd(const tvae_gen_shape* s, const tvae_gen_fwd_args* a, void
         l.C16 = acts + (long long)i * M * H; l.ldc16 = H;
         l.bias = a->bh + (long long)(i - 1) * H;
         l.act = gact;
+        l.bits_out = gen_mask_words(s, a, i);
         if (i == s->L) { l.proj_w = a->wout; l.proj_bias = a->bout; l.proj_out = a->y_hat; l.n_proj = s->n_out; }
         if ((rc = linear_nt(l, st))) return rc;
     }
@@ -970,6 +986,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         l.M = static_cast<int>(M); l.N = H; l.K = H;
         l.C16 = dnext; l.ldc16 = H; l.aux16 = a_prev; l.ld_aux = H; l.aux_act = gact;
         if (i == 1 && coord_fused) { l.aux16 = nullptr; l.aux_bits = reinterpret_cast<const unsigned long long*>(acts); }   // one-bit mask written by the forward kernel
+        else if (const unsigned long long* mb = gen_mask_words(s, &a->f, i - 1)) { l.aux16 = nullptr; l.aux_bits = mb; }
         l.acc_scale = a->scales + 2 * i + 1; l.store_scale = a->scales + 2 * (i - 1);
         if (i - 1 >= 1) { l.colsum = a->dbh + (long long)(i - 2) * H; l.colsum_stride = 1; }   // bias gradient of hidden layer i-1
         if ((rc = linear_nt(l, st))) return rc;

@@ -57,7 +57,7 @@ class GenShape(Structure):
 
 class GenFwdArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ("x", "theta", "dx", "z", "wf_scaled", "bf", "w1", "b1", "wz", "wh", "bh",
-                                         "wout", "bout", "zb", "acts", "y_hat", "w_h")]
+                                         "wout", "bout", "zb", "acts", "y_hat", "w_h", "mask_bits")]
 
 
 class GenBwdArgs(Structure):
@@ -378,10 +378,10 @@ def gen_shape(B, N, gw: GenWeights, zdim, act=ACT_LEAKYRELU) -> GenShape:
     return GenShape(B, N, gw.E, gw.H, gw.L, gw.wout.shape[0], zdim, act)
 
 
-def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_h):
+def _gen_fwd_args(s: GenShape, gw: GenWeights, x, theta, dx, z, zb, acts, y_hat, w_h, mask_bits=None):
     return _set(GenFwdArgs(), x=f32(x), theta=None if theta is None else f32(theta), dx=None if dx is None else f32(dx),
                 z=f32(z), wf_scaled=gw.wf_scaled, bf=gw.bf, w1=gw.w1, b1=gw.b1, wz=gw.wz, wh=gw.wh, bh=gw.bh,
-                wout=gw.wout, bout=gw.bout, zb=zb, acts=acts, y_hat=y_hat, w_h=w_h)
+                wout=gw.wout, bout=gw.bout, zb=zb, acts=acts, y_hat=y_hat, w_h=w_h, mask_bits=mask_bits)
 
 
 def generator_fwd(s: GenShape, gw: GenWeights, x, theta, dx, z):
@@ -391,9 +391,13 @@ def generator_fwd(s: GenShape, gw: GenWeights, x, theta, dx, z):
     acts = half(s.L + 1, M, s.H, device=dev)        # fp16 activations: the MMA operand format, half the HBM traffic
     y_hat = empty(M, s.n_out, device=dev)
     w_h = half(s.H * max(s.E, 2) + s.L * s.H * s.H, device=dev)
-    a = _gen_fwd_args(s, gw, x, theta, dx, z, zb, acts, y_hat, w_h)
+    # one-bit LeakyReLU masks of acts[0 .. L-1] for the hidden layers' input gradients (1/16 of the activation's bytes)
+    mask_bits = None
+    if s.act == ACT_LEAKYRELU and s.H % 64 == 0 and s.L >= 1:
+        mask_bits = torch.empty(s.L * (s.H // 64) * M, device=dev, dtype=torch.int64)
+    a = _gen_fwd_args(s, gw, x, theta, dx, z, zb, acts, y_hat, w_h, mask_bits)
     check(L().tvae_generator_fwd(byref(s), byref(a), stream_ptr()), "tvae_generator_fwd")
-    return y_hat, dict(zb=zb, acts=acts, w_h=w_h)
+    return y_hat, dict(zb=zb, acts=acts, w_h=w_h, mask_bits=mask_bits)
 
 
 def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_yhat):
@@ -408,7 +412,7 @@ def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_
     scratch = dict(dpre0=half(M, H, device=dev), dpre1=half(M, H, device=dev), wt_h=half(max(E * H, H * H), device=dev),
                    scales=empty(32, device=dev), dxp=empty(M, 2, device=dev), dzb=empty(s.B, H, device=dev))
     a = GenBwdArgs()
-    a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_h"])
+    a.f = _gen_fwd_args(s, gw, x, theta, dx, z, saved["zb"], saved["acts"], y_hat, saved["w_h"], saved.get("mask_bits"))
     _set(a, d_yhat=f32(d_yhat), **scratch, **{k: v for k, v in out.items() if k != "flat"})
     if theta is None:
         a.d_theta = None
