@@ -796,6 +796,97 @@ __global__ void __launch_bounds__(256) thin_bwd_mma_kernel(ThinBwdParams p, int 
     if (p.dbt && blockIdx.y == 0 && tid < T) atomicAdd(p.dbt + tid, s_red[(T + 1) * 128 + tid]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming variant for the generator's OUTPUT layer (T = n_out <= 4 thin outputs, row-major dt[m][T], fp16 activation):
+// with one to four outputs the two thin contractions are 2 T FMAs per element, far below what the load / store stream costs,
+// so there is nothing to stage: thread = (8 adjacent columns, row slot), one 16-byte load and one 16-byte store per row, UNR
+// rows in flight per thread, Wt / dWt / column sums in registers.  (thin_bwd_mma pads T to 16 for mma.sync and passes every
+// tile through shared memory behind two CTA barriers per 64 rows: 0.66 of the HBM floor on this shape.)
+// blockDim.x = (W / 8) * slots; dynamic smem: [(T + 1) * W + T] CTA partial sums.
+// ------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(256) thin_bwd_stream_kernel(ThinBwdParams p) {
+    extern __shared__ float s_red[];
+    constexpr int UNR = 4;
+    const int cgs = p.W / 8, slots = blockDim.x / cgs;
+    const int cg = threadIdx.x % cgs, slot = threadIdx.x / cgs, c0 = cg * 8;
+    const int n_red = (T + 1) * p.W + T;
+    for (int i = threadIdx.x; i < n_red; i += blockDim.x) s_red[i] = 0.f;
+    const float store_scale = p.store_scale ? __ldg(p.store_scale) : 1.f;
+    const __half* a_g = static_cast<const __half*>(p.a);
+    __half* dpre_g = static_cast<__half*>(p.dpre);
+    float w[T][8], dw[T][8], dcol[8], dbt[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        dbt[t] = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) { w[t][v] = __ldg(p.Wt + (long long)t * p.W + c0 + v); dw[t][v] = 0.f; }
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) dcol[v] = 0.f;
+    const long long m_begin = (long long)blockIdx.x * p.rows_per_cta;
+    const long long m_end = min(m_begin + p.rows_per_cta, p.M);
+    const bool tanh_act = p.act == kActTanh;
+    for (long long m0 = m_begin + slot; m0 < m_end; m0 += (long long)slots * UNR) {
+        uint4 av[UNR];
+        float dv[UNR][T];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long m = m0 + (long long)u * slots;
+            if (m < m_end) {
+                av[u] = __ldg(reinterpret_cast<const uint4*>(a_g + m * p.W + c0));
+#pragma unroll
+                for (int t = 0; t < T; ++t) dv[u][t] = __ldg(p.dt + m * T + t);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const long long m = m0 + (long long)u * slots;
+            if (m >= m_end) break;
+            const uint32_t aw[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+            float a8[8], g[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+                a8[2 * e] = f.x; a8[2 * e + 1] = f.y;
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    acc = fmaf(dv[u][t], w[t][v], acc);
+                    dw[t][v] = fmaf(dv[u][t], a8[v], dw[t][v]);
+                }
+                acc *= tanh_act ? 1.f - a8[v] * a8[v] : lrelu_grad_from_out(a8[v]);
+                dcol[v] += acc;
+                g[v] = acc * store_scale;
+            }
+            if (cg == 0) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) dbt[t] += dv[u][t];
+            }
+            uint4 o;
+            o.x = pack_h2(g[0], g[1]); o.y = pack_h2(g[2], g[3]); o.z = pack_h2(g[4], g[5]); o.w = pack_h2(g[6], g[7]);
+            *reinterpret_cast<uint4*>(dpre_g + m * p.W + c0) = o;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) atomicAdd(s_red + t * p.W + c0 + v, dw[t][v]);
+        if (cg == 0) atomicAdd(s_red + (T + 1) * p.W + t, dbt[t]);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) atomicAdd(s_red + T * p.W + c0 + v, dcol[v]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * p.W; i += blockDim.x) atomicAdd(p.dWt + i, s_red[i]);
+    if (p.dcol)
+        for (int i = threadIdx.x; i < p.W; i += blockDim.x) atomicAdd(p.dcol + i, s_red[T * p.W + i]);
+    if (p.dbt && threadIdx.x < T) atomicAdd(p.dbt + threadIdx.x, s_red[(T + 1) * p.W + threadIdx.x]);
+}
+
 // column sums per group of rows: out[g][c] = sum_{m in group g} x[m][c]   (z-conditioned bias gradient),
 // and total[c] += sum over all rows.  grid = (chunks, groups), blockDim.x = W.
 // x is fp16 holding value * (1 / *inv_scale).

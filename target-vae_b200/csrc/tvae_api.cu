@@ -88,8 +88,30 @@ int launch_thin_bwd_mma(ThinBwdParams& p, int G, cudaStream_t st) {
     return 0;
 }
 
+// generator output layer: n_out <= 4 thin outputs, row-major dt, fp16 activation (thin_bwd_stream_kernel)
+inline int launch_thin_bwd_stream(ThinBwdParams& p, cudaStream_t st) {
+    const int cgs = p.W / 8, slots = 256 / cgs;
+    const int per_pass = slots * 4;
+    long long rows = (p.M + 148LL * 8 - 1) / (148LL * 8);
+    rows = (rows + per_pass - 1) / per_pass * per_pass;
+    p.rows_per_cta = static_cast<int>(rows);
+    const size_t sm = sizeof(float) * ((p.T + 1) * p.W + p.T);
+    TVAE_REQUIRE(sm <= 48 * 1024, "thin backward (stream): shared memory");
+    const dim3 grid(static_cast<unsigned>(cdiv(p.M, rows)));
+    ++g_launch_count;
+    switch (p.T) {
+        case 1: thin_bwd_stream_kernel<1><<<grid, cgs * slots, sm, st>>>(p); break;
+        case 2: thin_bwd_stream_kernel<2><<<grid, cgs * slots, sm, st>>>(p); break;
+        case 3: thin_bwd_stream_kernel<3><<<grid, cgs * slots, sm, st>>>(p); break;
+        default: thin_bwd_stream_kernel<4><<<grid, cgs * slots, sm, st>>>(p); break;
+    }
+    TVAE_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int TMAX, int VEC, bool PLANAR, bool H16 = false>
 int launch_thin_bwd(ThinBwdParams& p, int G, cudaStream_t st) {
+    if (H16 && !PLANAR && p.T >= 1 && p.T <= 4 && p.W % 8 == 0 && p.W / 8 <= 256 && g_dev_knob[4] == 0) return launch_thin_bwd_stream(p, st);
     if (H16 && p.T <= 16 && p.W % 128 == 0) return launch_thin_bwd_mma<PLANAR, 1>(p, G, st);
     if (H16 && p.T <= 24 && p.W % 128 == 0) return launch_thin_bwd_mma<PLANAR, 2>(p, G, st);
     TVAE_REQUIRE(p.W % VEC == 0 && p.W / VEC <= 256 && p.T <= TMAX, "thin backward: unsupported width");
