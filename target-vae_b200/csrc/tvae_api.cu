@@ -191,7 +191,12 @@ int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, void* ban
     const int kpad16 = tvae_bank16_pitch(s->C, s->k);
     const long long total = (long long)s->G * s->O * kpad16;
     Timed tm("filter_bank_fwd", S(stream));
-    ++g_launch_count; filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
+    ++g_launch_count;
+    const size_t plane = sizeof(float) * s->k * s->k;
+    if (plane <= 48 * 1024)
+        filter_bank_fwd_tile_kernel<<<s->O * s->C, 256, plane, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
+    else
+        filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -201,9 +206,15 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
     if (rc) return rc;
     const int K = s->C * s->k * s->k;
     Timed tm("filter_bank_bwd", S(stream));
-    TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
-    const long long total = (long long)s->G * s->O * K;
-    ++g_launch_count; filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    const size_t plane = sizeof(float) * s->k * s->k;
+    ++g_launch_count;
+    if (plane <= 48 * 1024) {
+        filter_bank_bwd_tile_kernel<<<s->O * s->C, 256, plane, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    } else {
+        TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
+        const long long total = (long long)s->G * s->O * K;
+        filter_bank_bwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    }
     if (dbias) { ++g_launch_count; bank_bias_grad_kernel<<<cdiv(s->O, 128), 128, 0, S(stream)>>>(dbank, dbias, s->O, s->G, s->kpad, K); }
     TVAE_CHECK_CUDA(cudaGetLastError());
     return 0;
