@@ -92,61 +92,67 @@ __global__ void filter_bank_bwd_kernel(const float* __restrict__ dbank, long lon
     }
 }
 
-// Tile variants of the two kernels above: one CTA per filter plane (o, c).  Forward: the k x k plane is read once into shared
-// memory and sampled G times from there (the grid-stride form paid 64-bit index arithmetic and four scattered global loads
-// per output: 42 us for the 8 MB bank of cfg2).  Backward: the G rotated gradients of the plane are scattered into a
-// shared-memory tile and written ONCE (the global form issued 16.8 M atomics: 73 us at cfg2); dweight needs no zero-fill.
+// Plane variants of the two kernels above (k * k floats fit shared memory).
+// Forward, grid (O * C planes, G rotations): the k x k plane is read once into shared memory and sampled from there (the
+// grid-stride form paid 64-bit index arithmetic and four scattered global loads per output).
 // dynamic smem: k * k floats.
-__global__ void __launch_bounds__(256) filter_bank_fwd_tile_kernel(const float* __restrict__ w, __half* __restrict__ bank, int O, int C,
-                                                                   int k, int G, int kpad, RotTable rot) {
+__global__ void __launch_bounds__(256) filter_bank_fwd_plane_kernel(const float* __restrict__ w, __half* __restrict__ bank, int O, int C,
+                                                                    int k, int kpad, RotTable rot) {
     extern __shared__ float s_plane[];
-    const int oc = blockIdx.x, o = oc / C, c = oc - o * C, kk2 = k * k;
+    const int oc = blockIdx.x, o = oc / C, c = oc - o * C, kk2 = k * k, r = blockIdx.y;
     const float* wp = w + (long long)oc * kk2;
     for (int i = threadIdx.x; i < kk2; i += blockDim.x) s_plane[i] = __ldg(wp + i);
     __syncthreads();
-    for (int r = 0; r < G; ++r) {
-        __half* out = bank + (long long)(r * O + o) * kpad + c * kk2;
-        const float cs = rot.cs[r], sn = rot.sn[r];
-        for (int kk = threadIdx.x; kk < kk2; kk += blockDim.x) {
-            const int v = kk / k, u = kk - v * k;
-            const BilinearTap t = rot_tap(u, v, k, cs, sn);
-            const bool x0ok = t.x0 >= 0 && t.x0 < k, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < k;
-            const bool y0ok = t.y0 >= 0 && t.y0 < k, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < k;
-            float val = 0.f;
-            if (y0ok && x0ok) val += s_plane[t.y0 * k + t.x0] * (t.wy0 * t.wx0);
-            if (y0ok && x1ok) val += s_plane[t.y0 * k + t.x0 + 1] * (t.wy0 * t.wx1);
-            if (y1ok && x0ok) val += s_plane[(t.y0 + 1) * k + t.x0] * (t.wy1 * t.wx0);
-            if (y1ok && x1ok) val += s_plane[(t.y0 + 1) * k + t.x0 + 1] * (t.wy1 * t.wx1);
-            out[kk] = __float2half_rn(val);
-        }
-        if (c == C - 1)                                    // the row's padding columns [C k^2, kpad)
-            for (int kk = C * kk2 + threadIdx.x; kk < kpad; kk += blockDim.x) bank[(long long)(r * O + o) * kpad + kk] = __float2half_rn(0.f);
+    __half* out = bank + (long long)(r * O + o) * kpad + c * kk2;
+    const float cs = rot.cs[r], sn = rot.sn[r];
+    for (int kk = threadIdx.x; kk < kk2; kk += blockDim.x) {
+        const int v = kk / k, u = kk - v * k;
+        const BilinearTap t = rot_tap(u, v, k, cs, sn);
+        const bool x0ok = t.x0 >= 0 && t.x0 < k, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < k;
+        const bool y0ok = t.y0 >= 0 && t.y0 < k, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < k;
+        float val = 0.f;
+        if (y0ok && x0ok) val += s_plane[t.y0 * k + t.x0] * (t.wy0 * t.wx0);
+        if (y0ok && x1ok) val += s_plane[t.y0 * k + t.x0 + 1] * (t.wy0 * t.wx1);
+        if (y1ok && x0ok) val += s_plane[(t.y0 + 1) * k + t.x0] * (t.wy1 * t.wx0);
+        if (y1ok && x1ok) val += s_plane[(t.y0 + 1) * k + t.x0 + 1] * (t.wy1 * t.wx1);
+        out[kk] = __float2half_rn(val);
     }
+    if (c == C - 1)                                        // the row's padding columns [C k^2, kpad)
+        for (int kk = C * kk2 + threadIdx.x; kk < kpad; kk += blockDim.x) bank[(long long)(r * O + o) * kpad + kk] = __float2half_rn(0.f);
 }
-__global__ void __launch_bounds__(256) filter_bank_bwd_tile_kernel(const float* __restrict__ dbank, long long ld, float* __restrict__ dw,
-                                                                   int O, int C, int k, int G, RotTable rot) {
-    extern __shared__ float s_plane[];
+// Backward as a GATHER, thread = one weight pixel (x, y) of plane (o, c): for every rotation the output taps (u, v) whose
+// bilinear footprint covers (x, y) lie within sqrt(2) of the inversely rotated pixel - at most 4 x 4 candidates, each
+// contributing dbank * max(0, 1 - |ix - x|) * max(0, 1 - |iy - y|), which is exactly the forward's corner weight.  No atomics
+// (the scatter form issued 16.8 M of them at cfg2: 73 us), no zero-fill of dweight, bit-deterministic.
+// grid (O * C, ceil(k * k / 256)).
+__global__ void __launch_bounds__(256) filter_bank_bwd_gather_kernel(const float* __restrict__ dbank, long long ld, float* __restrict__ dw,
+                                                                     int O, int C, int k, int G, RotTable rot) {
     const int oc = blockIdx.x, o = oc / C, c = oc - o * C, kk2 = k * k;
-    for (int i = threadIdx.x; i < kk2; i += blockDim.x) s_plane[i] = 0.f;
-    __syncthreads();
+    const int px = blockIdx.y * blockDim.x + threadIdx.x;
+    if (px >= kk2) return;
+    const int y = px / k, x = px - y * k;
+    const float c0 = 0.5f * (k - 1);
+    const float fx = x - c0, fy = y - c0;
+    float acc = 0.f;
     for (int r = 0; r < G; ++r) {
-        const float* gp = dbank + (long long)(r * O + o) * ld + c * kk2;
         const float cs = rot.cs[r], sn = rot.sn[r];
-        for (int kk = threadIdx.x; kk < kk2; kk += blockDim.x) {
-            const int v = kk / k, u = kk - v * k;
-            const float g = __ldg(gp + kk);
-            const BilinearTap t = rot_tap(u, v, k, cs, sn);
-            const bool x0ok = t.x0 >= 0 && t.x0 < k, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 < k;
-            const bool y0ok = t.y0 >= 0 && t.y0 < k, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 < k;
-            if (y0ok && x0ok) atomicAdd(s_plane + t.y0 * k + t.x0, g * (t.wy0 * t.wx0));
-            if (y0ok && x1ok) atomicAdd(s_plane + t.y0 * k + t.x0 + 1, g * (t.wy0 * t.wx1));
-            if (y1ok && x0ok) atomicAdd(s_plane + (t.y0 + 1) * k + t.x0, g * (t.wy1 * t.wx0));
-            if (y1ok && x1ok) atomicAdd(s_plane + (t.y0 + 1) * k + t.x0 + 1, g * (t.wy1 * t.wx1));
+        const float* gp = dbank + (long long)(r * O + o) * ld + c * kk2;
+        // inverse of (ix, iy) = (cs cx + sn cy, -sn cx + cs cy) + c0
+        const float cu = cs * fx - sn * fy + c0, cv = sn * fx + cs * fy + c0;
+        const int u_lo = max(0, static_cast<int>(ceilf(cu - 1.5f))), u_hi = min(k - 1, static_cast<int>(floorf(cu + 1.5f)));
+        const int v_lo = max(0, static_cast<int>(ceilf(cv - 1.5f))), v_hi = min(k - 1, static_cast<int>(floorf(cv + 1.5f)));
+        for (int v = v_lo; v <= v_hi; ++v) {
+            const float cy = v - c0;
+            for (int u = u_lo; u <= u_hi; ++u) {
+                const float cx = u - c0;
+                const float ix = cs * cx + sn * cy + c0;            // the forward's expressions (rot_tap), term by term
+                const float iy = -sn * cx + cs * cy + c0;
+                const float wx = 1.f - fabsf(ix - x), wy = 1.f - fabsf(iy - y);
+                if (wx > 0.f && wy > 0.f) acc = fmaf(__ldg(gp + v * k + u), wx * wy, acc);
+            }
         }
     }
-    __syncthreads();
-    float* wp = dw + (long long)oc * kk2;
-    for (int i = threadIdx.x; i < kk2; i += blockDim.x) wp[i] = s_plane[i];
+    dw[(long long)oc * kk2 + px] = acc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -194,7 +194,7 @@ int tvae_filter_bank_fwd(const tvae_enc_shape* s, const float* weight, void* ban
     ++g_launch_count;
     const size_t plane = sizeof(float) * s->k * s->k;
     if (plane <= 48 * 1024)
-        filter_bank_fwd_tile_kernel<<<s->O * s->C, 256, plane, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
+        filter_bank_fwd_plane_kernel<<<dim3(s->O * s->C, s->G), 256, plane, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, kpad16, make_rot_table(s->G));
     else
         filter_bank_fwd_kernel<<<blocks_for(total, 256), 256, 0, S(stream)>>>(weight, static_cast<__half*>(bank), s->O, s->C, s->k, s->G, kpad16, make_rot_table(s->G));
     TVAE_CHECK_CUDA(cudaGetLastError());
@@ -206,10 +206,9 @@ int tvae_filter_bank_bwd(const tvae_enc_shape* s, const float* dbank, float* dwe
     if (rc) return rc;
     const int K = s->C * s->k * s->k;
     Timed tm("filter_bank_bwd", S(stream));
-    const size_t plane = sizeof(float) * s->k * s->k;
     ++g_launch_count;
-    if (plane <= 48 * 1024) {
-        filter_bank_bwd_tile_kernel<<<s->O * s->C, 256, plane, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
+    if (g_dev_knob[5] == 0) {
+        filter_bank_bwd_gather_kernel<<<dim3(s->O * s->C, cdiv(s->k * s->k, 256)), 256, 0, S(stream)>>>(dbank, s->kpad, dweight, s->O, s->C, s->k, s->G, make_rot_table(s->G));
     } else {
         TVAE_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * s->O * K, S(stream)));
         const long long total = (long long)s->G * s->O * K;

@@ -44,7 +44,7 @@ def eager(cfg, gen, enc, x, y, ctf):
     (-out[0]).backward()
     names = [f"gen.{n}" for n, _ in gen.named_parameters()] + [f"enc.{n}" for n, _ in enc.named_parameters()]
     grads = {n: p.grad.detach().clone() for n, p in zip(names, list(gen.parameters()) + list(enc.parameters()))}
-    return [float(t) for t in out], grads
+    return [float(t.detach()) for t in out], grads
 
 
 @pytest.mark.parametrize("cfg", CASES, ids=lambda c: c.name)
@@ -97,3 +97,35 @@ def test_guards():
         gs(y[0], torch.zeros(B, 1, cfg.n - 1, cfg.n - 1, device=DEV))
     with pytest.raises(RuntimeError):
         GraphedStep(x, y[0].shape, gen, enc, "attention", r_inf_of(cfg), "cpu", cfg.theta_prior, cfg.G, cfg.n)
+
+
+def test_train_epoch_with_graph_matches_eager():
+    """train_epoch(graph=True): three full minibatches replayed, the last shorter one eager; same seeds -> the parameters end
+    where the eager epoch puts them (Adam moves a weight by ~lr per step: same bound as tests/test_gpu_optim.py)."""
+    from tvae_b200 import train
+    from tvae_b200.optim import Adam
+    cfg, B = CASES[0], 6
+    x = torch.from_numpy(synth.image_coords(cfg.n)).to(DEV)
+    batches = [(torch.from_numpy(synth.minibatch(cfg, B if i < 3 else 4, seed=i)["y"]).to(DEV),) for i in range(4)]
+    finals, outs = [], []
+    for graph in (False, True):
+        gen, enc = build_models(cfg, seed=3)
+        params = list(gen.parameters()) + list(enc.parameters())
+        opt = Adam(params, lr=2e-4)
+        cache = {} if graph else False
+        if graph:      # capture (with its warm-up passes, which draw noise) before seeding, so both epochs see the same stream
+            train.train_epoch(batches[:1], x, gen, enc, Adam(params, lr=0.0), "attention", r_inf_of(cfg), 0, 1, B, DEV, params,
+                              cfg.theta_prior, cfg.G, cfg.n, graph=cache)
+            assert len(cache) == 1
+        torch.manual_seed(99)
+        out = train.train_epoch(batches, x, gen, enc, opt, "attention", r_inf_of(cfg), 0, 1, 3 * B + 4, DEV, params,
+                                cfg.theta_prior, cfg.G, cfg.n, graph=cache)
+        torch.cuda.synchronize()
+        assert all(np.isfinite(out))
+        assert all(int(opt.state[p]["step"]) == 4 for p in params)
+        finals.append([p.detach().clone() for p in params])
+        outs.append(out)
+    np.testing.assert_allclose(outs[1], outs[0], rtol=1e-3)
+    lr, steps = 2e-4, 4
+    d = torch.cat([(a - b).abs().flatten() for a, b in zip(*finals)])
+    assert float(d.max()) <= 2 * lr * steps * 1.01 and float(d.mean()) <= 0.02 * lr
