@@ -538,7 +538,19 @@ def measure_config(ctx, cfg, B, K, W, legs=("e2e",), graph=True):
     # ---- value: K replays of the step captured once as a CUDA graph (tvae_b200.graph.GraphedStep - the same public call on the
     # same models, NCCL bucket all-reduces included at N > 1), inputs resident in HBM: each step copies the next minibatch
     # device -> device into the graph's staging buffer and replays.  --no-graph: the eager launch sequence instead.
-    gs = wl.graphed() if graph else None
+    gs, graph_note = None, None
+    if graph:
+        try:
+            gs = wl.graphed()
+        except Exception as e:                  # reported in `launch`; the eager launch sequence is the same kernels
+            graph_note = f"{type(e).__name__}: {e}"[:200]
+            torch.cuda.synchronize()
+        if world > 1:
+            # every rank must take the same path (the captured step contains the NCCL bucket all-reduces)
+            ok = torch.tensor([1.0 if gs is not None else 0.0], device=ctx.dev)
+            ctx.dist.all_reduce(ok, op=ctx.dist.ReduceOp.MIN)
+            if float(ok) == 0.0 and gs is not None:
+                gs, graph_note = None, "graph capture failed on another rank"
 
     def value_step(i):
         if gs is None:
@@ -574,7 +586,8 @@ def measure_config(ctx, cfg, B, K, W, legs=("e2e",), graph=True):
     res = {"value": world * B * K / (ms_total * 1e-3), "unit": UNIT, "ms_per_step": ms_total / K, "steps": K, "warmup": W,
            "per_gpu_batch": B, "gpu_launches": launches, "clocks": clk.summary(),
            "launch": ("one CUDA graph replay per step (GraphedStep: eval_minibatch + backward captured once; "
-                      f"{gs.launches_per_replay} library kernels per replay)") if gs is not None else "eager kernel launches",
+                      f"{gs.launches_per_replay} library kernels per replay)") if gs is not None else
+                     ("eager kernel launches" + (f" (graph capture failed: {graph_note})" if graph_note else "")),
            "ms_per_step_eager": ms_eager / K,
            "tflops_step": world * B * cfg.flops_fwd_bwd() * K / (ms_total * 1e-3) / 1e12}
     if "e2e" in legs:

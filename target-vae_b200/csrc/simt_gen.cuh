@@ -195,19 +195,20 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_kernel(CoordXform cx, con
 }
 
 // Row-streaming variant of the above for H % 8 == 0, H <= 512 (cfg2: H = 512): a warp owns a 256-column slice of whole
-// rows (lane l holds columns 256 g + 8 l + [0,8), g = warp % ceil(H / 256)), four rows = four 16-byte loads in flight
+// rows (lane l holds columns 256 g + 8 l + [0,8), g = warp % ceil(H / 256)), kCoordU rows = kCoordU 16-byte loads in flight
 // per lane at 3 CTAs per SM, the transformed coordinates of the CTA's rows computed once into shared memory, one warp
 // reduction per row slice for dxp and per-lane register accumulators for dW1 / db1 / dzb.
 // HBM-bound: one read of dpre (2 H bytes per row).
-constexpr int kCoordMaxRows = 512;
+constexpr int kCoordMaxRows = 2048;
+constexpr int kCoordU = 4;            // rows in flight per lane of coord_layer_bwd_rows_kernel
 __global__ void __launch_bounds__(256) coord_layer_bwd_rows_kernel(CoordXform cx, const float* __restrict__ w1, const __half* __restrict__ dpre,
                                                                    const float* __restrict__ inv_scale, float* __restrict__ dw1,
                                                                    float* __restrict__ dxp, float* __restrict__ dzb, float* __restrict__ db1,
                                                                    int H, int rows_per_cta) {
     extern __shared__ float s_cl[];
-    float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [kCoordMaxRows] transformed coordinates
-    float* s_dx = s_cl + 2 * kCoordMaxRows;                         // [kCoordMaxRows][2] dxp of the CTA's rows
-    float* s_dw = s_dx + 2 * kCoordMaxRows;                         // [H][2]
+    float2* s_x = reinterpret_cast<float2*>(s_cl);                 // [rows_per_cta] transformed coordinates
+    float* s_dx = s_cl + 2 * rows_per_cta;                          // [rows_per_cta][2] dxp of the CTA's rows
+    float* s_dw = s_dx + 2 * rows_per_cta;                          // [H][2]
     float* s_sum = s_dw + 2 * H;                                    // [H]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncg = (H + 255) / 256;                                // column groups (1 or 2)
@@ -234,15 +235,15 @@ __global__ void __launch_bounds__(256) coord_layer_bwd_rows_kernel(CoordXform cx
     }
     __syncthreads();
     const __half* base = dpre + m_begin * H + c0;
-    for (int r0 = rw; r0 < rows; r0 += 4 * nrw) {                   // rows r0 + nrw * {0,1,2,3} of this warp
-        uint4 t[4];
+    for (int r0 = rw; r0 < rows; r0 += kCoordU * nrw) {                  // rows r0 + nrw * {0 .. kCoordU-1} of this warp: kCoordU 16-byte loads in flight per lane
+        uint4 t[kCoordU];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kCoordU; ++q) {
             const int r = r0 + nrw * q;
             t[q] = (r < rows && col_ok) ? __ldg(reinterpret_cast<const uint4*>(base + (long long)r * H)) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kCoordU; ++q) {
             const int r = r0 + nrw * q;
             if (r >= rows) break;                                    // uniform per warp
             const float2 x = s_x[r];

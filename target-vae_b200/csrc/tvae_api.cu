@@ -1028,7 +1028,8 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
     // whole 64-row blocks per image they come out of the coordinate-layer backward pass below instead.
     int coord_rows = 0;
     if (E == 0 && s->N % kCoordRB == 0) {
-        for (int r = kCoordRB; r <= s->N && r <= 512; r += kCoordRB)
+        const int cap = g_dev_knob[6] > 0 ? g_dev_knob[6] : 1024;   // measured at cfg2: 1024 rows per CTA 166 us, 512 176 us, 256 194 us, 2048 278 us (8 rows in flight per lane: 210 us - the kernel is issue-bound, not latency-bound)
+        for (int r = kCoordRB; r <= s->N && r <= cap && r <= kCoordMaxRows; r += kCoordRB)
             if (s->N % r == 0) coord_rows = r;
     }
     if (!coord_rows) {
@@ -1105,7 +1106,7 @@ int tvae_generator_bwd(const tvae_gen_shape* s, const tvae_gen_bwd_args* a, void
         ++g_launch_count;
         if (H % 8 == 0 && H <= 512 && rows <= kCoordMaxRows) {
             // row-streaming kernel: warps own whole rows, 16-byte loads, register accumulators
-            const size_t smr = sizeof(float) * (4 * kCoordMaxRows + 3 * H);
+            const size_t smr = sizeof(float) * (4 * rows + 3 * H);
             coord_layer_bwd_rows_kernel<<<cdiv(M, rows), 256, smr, st>>>(cx, a->f.w1, dcur, a->scales + 1, a->dw1, a->dxp,
                                                                           coord_rows ? a->dzb : nullptr, a->db1, H, static_cast<int>(rows));
         } else

@@ -24,6 +24,15 @@ for name in (sys.argv[1:] or ["cfg1", "cfg2"]):
     for i in range(3):
         gs(wl.y_dev[i % wl.NB], wl.ctf_dev[i % wl.NB])
     ms_graph = ctx.timed(lambda i: gs(wl.y_dev[i % wl.NB], wl.ctf_dev[i % wl.NB]), K) / K
+    ms_eager2 = ctx.timed(wl.step_resident, K) / K
+    ms_graph2 = ctx.timed(lambda i: gs(wl.y_dev[i % wl.NB], wl.ctf_dev[i % wl.NB]), K) / K
+
+    def synced(i):
+        gs(wl.y_dev[i % wl.NB], wl.ctf_dev[i % wl.NB])
+        torch.cuda.synchronize()
+    ms_graph_sync = ctx.timed(synced, K) / K
+    if ctx.rank == 0:
+        print(f"{cfg.name}: second pass eager {ms_eager2:.3f}, graph {ms_graph2:.3f}, graph with a host sync per step {ms_graph_sync:.3f} ms/step", flush=True)
     # agreement on identical seeds
     torch.manual_seed(1234)
     e0 = wl.step_resident(1).detach().clone()
@@ -32,7 +41,8 @@ for name in (sys.argv[1:] or ["cfg1", "cfg2"]):
     e1 = gs(wl.y_dev[1], wl.ctf_dev[1])[0].clone()
     torch.cuda.synchronize()
     err = max(float((a - p.grad).norm() / (a.norm() + 1e-30)) for a, p in zip(g0, gs.params) if float(a.norm()) > 1e-12)
-    print(f"{cfg.name} B={B}: eager {ms_eager:.3f} ms/step, graph {ms_graph:.3f} ms/step ({gs.launches_per_replay} library launches per replay); "
+    if ctx.rank == 0:
+      print(f"{cfg.name} B={B}: eager {ms_eager:.3f} ms/step, graph {ms_graph:.3f} ms/step ({gs.launches_per_replay} library launches per replay); "
           f"elbo eager {float(e0):.6f} graph {float(e1):.6f}, worst relative gradient difference {err:.2e}", flush=True)
     del wl, gs
     torch.cuda.empty_cache()
