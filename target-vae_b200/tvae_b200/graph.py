@@ -1,8 +1,8 @@
 """One training minibatch (eval_minibatch forward + (-elbo).backward()) of a fixed shape as ONE CUDA graph.
 
 The fused step enqueues 35-60 kernels (ours + torch's noise draws and scalar arithmetic) and never synchronises with the
-host, so the whole pass is capturable; at the small configs (cfg1: 2.3 ms of kernels per step) the host cannot enqueue
-them as fast as the GPU retires them, and a replay removes the launch gaps.  Same call convention as the trainers'
+host, so the whole pass is capturable; a replay removes the gaps between them (measured: cfg1 2.74 -> 2.55 ms/step, cfg2
+6.48 -> 6.46, the large configs unchanged - the eager step is already 99 % kernel time).  Same call convention as the trainers'
 `eval_minibatch` (train_mnist.py:26, train_particles.py:28) - built once per (shape, models), then called per minibatch:
 
     step = GraphedStep(x_coord, y_shape, generator_model, encoder_model, t_inf, r_inf, device, theta_prior, groupconv,
