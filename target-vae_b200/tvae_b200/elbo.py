@@ -48,7 +48,7 @@ def _encoder_spec(encoder_model, t_inf, r_inf, theta_prior):
 
 
 def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likelihood, mask_radius, noise, sync=None,
-          theta_prior=None):
+          theta_prior=None, alias=None):
     es = _encoder_spec(encoder_model, t_inf, r_inf, theta_prior)
     spacing = TF.pixel_spacing(x)      # cached on the caller's grid tensor (not on the per-step device copy below)
     y = y.to(device)
@@ -62,23 +62,27 @@ def _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, likel
         noise = draw_noise(B, es.attn_G * d * d, es.z, y.device)
     fw, fb = generator_model.fourier_buffers()
     gen_params = generator_model.hot_path_params()
+    enc_params = encoder_model.hot_path_params()
+    if alias is not None:      # tvae_b200.graph: fresh leaves sharing the parameters' storage (see GraphedStep._eager)
+        gen_params = [alias(t) for t in gen_params]
+        enc_params = [alias(t) for t in enc_params]
     spec = TF.StepSpec(enc=es, sigma=generator_model._sigma, likelihood=likelihood, mask_radius=int(mask_radius),
                        n_gen_hidden=(len(gen_params) - 5) // 2, gen_resid=bool(generator_model._resid),
                        gen_act=generator_model.act_kind())
     spec.sync = sync
     spec.spacing = spacing
     return TF.FusedStepFn.apply(spec, x, y, ctf, noise["gumbel"], noise["r_z"], noise["r_theta"], fw, fb,
-                                *encoder_model.hot_path_params(), *gen_params)
+                                *enc_params, *gen_params)
 
 
 def eval_minibatch(x, y, generator_model, encoder_model, t_inf, r_inf, epoch, device,
-                   theta_prior, groupconv, image_dim, noise=None, sync=None):
+                   theta_prior, groupconv, image_dim, noise=None, sync=None, _alias=None):
     """train_mnist / train_dsprites / train_galaxy signature; Bernoulli likelihood (RGB handled by flat order)."""
-    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, sync, theta_prior)
+    return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "bernoulli", 0, noise, sync, theta_prior, _alias)
 
 
 def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, epoch, device,
-                             theta_prior, groupconv, padding, mask_radius, noise=None, sync=None):
+                             theta_prior, groupconv, padding, mask_radius, noise=None, sync=None, _alias=None):
     """train_particles signature; Gaussian likelihood with optional CTF and circular mask, or - generator n_out = 2,
     the trainer's --fit-noise (train_particles.py:663-666) - with a learned per-pixel variance.  --fit-noise together
     with a CTF or a mask is rejected: the reference's own shapes do not line up there for B > 1 (y_var becomes
@@ -89,7 +93,7 @@ def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r
             raise NotImplementedError("--fit-noise with --ctf-file or --mask-radius fails in the reference itself for "
                                       "B > 1 (train_particles.py:304-307, 330-331); not reproduced")
         return _step(x, y, None, generator_model, encoder_model, t_inf, r_inf, device, "gaussian_fit_noise", 0, noise, sync,
-                     theta_prior)
+                     theta_prior, _alias)
     if n_out != 1:
         raise ValueError(f"eval_minibatch_particles: generator n_out must be 1 or 2 (--fit-noise), got {n_out}")
     if ctf is not None:
@@ -97,7 +101,7 @@ def eval_minibatch_particles(x, y, ctf, generator_model, encoder_model, t_inf, r
         ops.ctf_filter_size(ctf, y.shape[0], y.shape[-1])     # one odd-sized square filter per image, or raise
         ctf = ctf.to(device)
     return _step(x, y, ctf, generator_model, encoder_model, t_inf, r_inf, device, "gaussian", mask_radius, noise, sync,
-                 theta_prior)
+                 theta_prior, _alias)
 
 
 def get_latent(x, y, encoder_model, t_inf, r_inf, device, image_dim, refine=True, return_argmax=False):

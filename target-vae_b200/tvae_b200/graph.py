@@ -20,7 +20,8 @@ offset per replay, so every replay draws fresh noise exactly like the eager call
 The optimiser step stays outside the graph (its bias-correction step count is a host scalar of `tvae_adam_step`).
 Data-parallel runs pass `sync=dp.GradSync()` (without a fused optimiser): the two bucket all-reduces are NCCL launches on
 NCCL's stream, forked from and joined back into the capturing stream, so they become nodes of the same graph and still
-overlap the encoder backward.
+overlap the encoder backward.  Drop the GraphedStep before `destroy_process_group()`: a live graph that holds captured NCCL
+launches stalls the communicator's teardown (measured: two minutes).
 """
 from __future__ import annotations
 
@@ -72,24 +73,45 @@ class GraphedStep:
             self.graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             try:
-                with torch.cuda.graph(self.graph):
-                    elbo, logp, kl = self._eager()
+                # thread_local: only THIS thread's calls are checked against the capture.  Under the default ("global") a CUDA
+                # call of any other thread - ProcessGroupNCCL's watchdog polling the events of earlier collectives - invalidates
+                # it (seen with two ranks: cudaErrorStreamCaptureInvalidated); the step itself makes no unsafe call on any thread
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    elbo, logp, kl, grads = self._eager()
             finally:
                 ops.profile_enable(was_profiling)
             self.launches_per_replay = ops.launch_count() - n0      # library launches inside one replay
             self.elbo, self.log_p_x_g_z, self.kl_div = elbo.detach(), logp.detach(), kl.detach()
-            self.grads = [p.grad for p in self.params]
+            self.grads = [None if g is None else g.detach() for g in grads]
+            for p, g in zip(self.params, self.grads):
+                p.grad = g
 
     def _eager(self):
+        """One pass.  The step runs on fresh leaf ALIASES of the parameters (same storage) and takes its gradients with
+        torch.autograd.grad: no AccumulateGrad node of the real parameters takes part.  Those nodes are cached on the parameter
+        while any earlier graph of the caller is alive (a kept `elbo`), and they are bound to the stream they were created on -
+        usually the legacy default stream, which a capturing stream must never be joined into
+        (cudaErrorStreamCaptureImplicit).  The gradients are what the fused node returns: views of its flat buckets."""
         t_inf, r_inf, theta_prior, groupconv, image_dim, padding, mask_radius = self._args
+        aliases = {}
+
+        def alias(t):
+            if not t.requires_grad:
+                return t
+            a = aliases.get(id(t))
+            if a is None:
+                a = aliases[id(t)] = t.detach().requires_grad_(True)
+            return a
         if self.particles:
             elbo, logp, kl = E.eval_minibatch_particles(self.x, self.y, self.ctf, self.gen, self.enc, t_inf, r_inf, 0, self.device,
-                                                        theta_prior, groupconv, padding, mask_radius, sync=self.sync)
+                                                        theta_prior, groupconv, padding, mask_radius, sync=self.sync, _alias=alias)
         else:
             elbo, logp, kl = E.eval_minibatch(self.x, self.y, self.gen, self.enc, t_inf, r_inf, 0, self.device, theta_prior,
-                                              groupconv, image_dim, sync=self.sync)
-        (-elbo).backward()
-        return elbo, logp, kl
+                                              groupconv, image_dim, sync=self.sync, _alias=alias)
+        used = [p for p in self.params if id(p) in aliases]
+        got = torch.autograd.grad(-elbo, [aliases[id(p)] for p in used], allow_unused=True)
+        by_id = {id(p): g for p, g in zip(used, got)}
+        return elbo, logp, kl, [by_id.get(id(p)) for p in self.params]
 
     def __call__(self, y, ctf=None):
         """Copies the minibatch into the staging buffers (any device; pinned host memory copies asynchronously), replays
@@ -106,6 +128,6 @@ class GraphedStep:
             self.ctf.copy_(ctf.reshape(self.ctf.shape), non_blocking=True)
         for p, g in zip(self.params, self.grads):
             if p.grad is not g:
-                p.grad = g                      # re-attach after an optimiser's zero_grad(set_to_none=True)
+                p.grad = g                      # re-attach after an optimiser's zero_grad(set_to_none=True) / an eager backward
         self.graph.replay()
         return self.elbo, self.log_p_x_g_z, self.kl_div

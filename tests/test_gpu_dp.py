@@ -61,7 +61,28 @@ def _worker(rank, world, port, q):
             err = float((p.grad - g_full[k]).norm() / (g_full[k].norm() + 1e-30))
             worst = max(worst, err)
         ok = worst < 2e-3 and abs(float(e_mean) - float(e_full)) < 1e-5 * abs(float(e_full))
-        q.put((rank, bool(ok), worst, float(e_mean), float(e_full)))
+        # the same sharded step as ONE CUDA graph (the two NCCL bucket all-reduces are nodes of it): replay == eager call on the
+        # same generator seed (noise drawn inside, different per rank)
+        from tvae_b200.graph import GraphedStep
+        gs = GraphedStep(x, ys.shape, gen, enc, "attention", "attention+offsets", dev, cfg.theta_prior, cfg.G, cfg.n, sync=dp.GradSync())
+        for _, p in params:
+            p.grad = None
+        torch.manual_seed(500 + rank)
+        e2, _, _ = E.eval_minibatch(x, ys, gen, enc, "attention", "attention+offsets", 0, dev, cfg.theta_prior, cfg.G, cfg.n, sync=sync)
+        (-e2).backward()
+        torch.cuda.synchronize()
+        g_eager = {k: p.grad.clone() for k, p in params}
+        torch.manual_seed(500 + rank)
+        e3 = float(gs(ys)[0])
+        worst_g = max(float((p.grad - g_eager[k]).norm() / (g_eager[k].norm() + 1e-30)) for k, p in params if k != "conv_a.bias")
+        ok = ok and worst_g < 5e-4 and abs(e3 - float(e2)) < 1e-5 * abs(float(e2))
+        del gs                               # a live graph holding captured NCCL launches stalls destroy_process_group
+        torch.cuda.synchronize()
+        q.put((rank, bool(ok), worst, float(e_mean), float(e_full), worst_g))
+    except Exception as exc:                 # report instead of leaving the parent to time out on the queue
+        import traceback
+        q.put((rank, False, f"{type(exc).__name__}: {exc}", traceback.format_exc()[-1500:]))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -75,7 +96,7 @@ def test_two_rank_step_matches_full_batch():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     print(res)
