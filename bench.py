@@ -632,7 +632,10 @@ def dp_parity_check(ctx, wl):
     """One-off self-check of the data-parallel path: the rank-averaged gradients of one sharded step equal the
     gradients rank 0 computes alone on the WHOLE global minibatch (same images, same noise).  -> max over parameters of
     the relative Frobenius error (atomics order and the batch-dependent power-of-two gradient scales make it ~1e-4)."""
-    cfg, B, world, dev = wl.cfg, wl.B, ctx.world, ctx.dev
+    cfg, world, dev = wl.cfg, ctx.world, ctx.dev
+    # rank 0 also runs the WHOLE global minibatch of the check: keep it at one ordinary per-GPU minibatch (cfg5 at B = 256 per
+    # rank and 8 ranks would be 2 048 images = 73 GB of activations on one GPU)
+    B = max(1, min(wl.B, wl.B // world if wl.B >= world else 1))
     ys = [synth.minibatch(cfg, B, seed=9000 + r) for r in range(world)]
     nz = synth.noise(cfg, B * world, seed=77)
     lo, hi = ctx.rank * B, (ctx.rank + 1) * B
