@@ -264,6 +264,7 @@ struct EncHeadsBwdParams {
     const float* d_heads;     // (B, NH, G, P) fp32
     const float* wh;          // [NH][128] fp32
     const float* store_scale; // device scalar s1
+    const float* in_scale;    // device scalar s0 (power of two): S = fp16(d_heads * s0), divided out of dhpre / dWh again
     float* dwh;               // [NH][128], zero-filled by the caller
     float* dbh;               // [NH]
     float* db2;               // [128]
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(kHbThreads, 1) enc_heads_bwd_kernel(const __gr
         // ------------------------------------------------------------ generators: S = fp16(d_heads) tiles, dbh
         const int row = threadIdx.x - 12 * 32;
         const long long chan = (long long)p.G * p.P;
+        const float s0 = __ldg(p.in_scale);
         float dbh[NHP];
 #pragma unroll
         for (int t = 0; t < NHP; ++t) dbh[t] = 0.f;
@@ -402,10 +404,10 @@ __global__ void __launch_bounds__(kHbThreads, 1) enc_heads_bwd_kernel(const __gr
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
                 if (u < NHP / 8) {
                     __half2 hh;
-                    hh = __floats2half2_rn(v[8 * u], v[8 * u + 1]);     q.x = *reinterpret_cast<uint32_t*>(&hh);
-                    hh = __floats2half2_rn(v[8 * u + 2], v[8 * u + 3]); q.y = *reinterpret_cast<uint32_t*>(&hh);
-                    hh = __floats2half2_rn(v[8 * u + 4], v[8 * u + 5]); q.z = *reinterpret_cast<uint32_t*>(&hh);
-                    hh = __floats2half2_rn(v[8 * u + 6], v[8 * u + 7]); q.w = *reinterpret_cast<uint32_t*>(&hh);
+                    hh = __floats2half2_rn(v[8 * u] * s0, v[8 * u + 1] * s0);     q.x = *reinterpret_cast<uint32_t*>(&hh);
+                    hh = __floats2half2_rn(v[8 * u + 2] * s0, v[8 * u + 3] * s0); q.y = *reinterpret_cast<uint32_t*>(&hh);
+                    hh = __floats2half2_rn(v[8 * u + 4] * s0, v[8 * u + 5] * s0); q.z = *reinterpret_cast<uint32_t*>(&hh);
+                    hh = __floats2half2_rn(v[8 * u + 6] * s0, v[8 * u + 7] * s0); q.w = *reinterpret_cast<uint32_t*>(&hh);
                 }
                 *reinterpret_cast<uint4*>(st + sw128_offset(row, u)) = q;
             }
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(kHbThreads, 1) enc_heads_bwd_kernel(const __gr
         const int ewarp = (warp - kFirstEpiWarp) & 3, grp = (warp - kFirstEpiWarp) >> 2;
         const int row = ewarp * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(ewarp * 32) << 16;
-        const float store_scale = __ldg(p.store_scale);
+        const float store_scale = __ldg(p.store_scale), inv_s0 = 1.f / __ldg(p.in_scale);
         const int bar_id = 2 + grp;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
         int blocks = 0;
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(kHbThreads, 1) enc_heads_bwd_kernel(const __gr
                 float v[32];
                 const uint32_t mb = c == 0 ? mbits[0] : (c == 1 ? mbits[1] : (c == 2 ? mbits[2] : mbits[3]));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * (((mb >> j) & 1u) ? 1.f : kLreluSlope);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * (((mb >> j) & 1u) ? inv_s0 : kLreluSlope * inv_s0);
                 {
                     const float colsum = warp_colsum32(v, lane);
                     if (c == 0) cs[0] += colsum; else if (c == 1) cs[1] += colsum; else if (c == 2) cs[2] += colsum; else cs[3] += colsum;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(kHbThreads, 1) enc_heads_bwd_kernel(const __gr
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c * 16 + j < p.NH) atomicAdd(p.dwh + (c * 16 + j) * 128 + row, __uint_as_float(r[j]));
+                    if (c * 16 + j < p.NH) atomicAdd(p.dwh + (c * 16 + j) * 128 + row, __uint_as_float(r[j]) * inv_s0);
             }
         }
     }

@@ -548,7 +548,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         if ((rc = make_tmap_2d_h(&q.tmH, a->h, R, 128, 128, kBM))) return rc;
         if ((rc = make_tmap_2d_h(&q.tmC, a->dhpre, R, 128, 128, kBM))) return rc;
         q.R = R; q.num_tiles = static_cast<int>(cdiv(R, kBM)); q.NH = NH; q.G = G2; q.P = g.P;
-        q.d_heads = a->d_heads; q.wh = a->wh; q.store_scale = a->scales + 0;
+        q.d_heads = a->d_heads; q.wh = a->wh; q.store_scale = a->scales + 0; q.in_scale = a->scales + 6;
         q.dwh = a->dwh; q.dbh = a->dbh; q.db2 = a->db2;
         const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
         TVAE_CHECK_CUDA(smem_optin(reinterpret_cast<const void*>(&enc_heads_bwd_kernel<16>), kHbSmemBytes));
@@ -563,6 +563,7 @@ int tvae_encoder_bwd(const tvae_enc_shape* s, const tvae_enc_bwd_args* a, void* 
         ThinBwdParams p{};
         p.a = a->h; p.dt = a->d_heads; p.Wt = a->wh; p.dpre = a->dhpre; p.dWt = a->dwh; p.dbt = a->dbh; p.dcol = a->db2;
         p.store_scale = a->scales + 0;
+        p.dt_scale = a->scales + 6;       // used by the mma.sync kernel (fp16 operand); the CUDA-core kernel reads d_heads in fp32
         p.act = tanh_act ? kActTanh : 0;
         p.M = R; p.W = g.O; p.T = NH; p.P = g.P;
         // row m = (b*G + r)*P + pos  ->  d_heads[((b*NH + j)*G + r)*P + pos]
