@@ -419,6 +419,7 @@ def generator_bwd(s: GenShape, gw: GenWeights, x, theta, dx, z, saved, y_hat, d_
         a.d_dx = None
     check(L().tvae_generator_bwd(byref(s), byref(a), stream_ptr()), "tvae_generator_bwd")
     out["dxp"] = scratch["dxp"]
+    out["scales"] = scratch["scales"]      # the per-layer power-of-two scales chosen on the device (diagnostics)
     return out
 
 

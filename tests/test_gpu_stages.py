@@ -125,6 +125,38 @@ def test_encoder_fwd_bwd(cfg):
         assert v < 5e-3, (k, v)
 
 
+@pytest.mark.parametrize("cfg", small_cfgs()[:3], ids=lambda c: c.name)
+def test_encoder_bwd_wide_dynamic_range(cfg):
+    """Head-map gradients span far more than fp16's exponent range in a real step: the attention-logit channel is O(1 / B),
+    the theta / z channels are q(t, r) / B times an O(1) factor - 2.6e-8 at cfg5 (150 k cells, B = 256).  They are an fp16 MMA
+    operand of the heads backward, so they are scaled by a power of two chosen on the device before the rounding
+    (scales[6], enc_bwd_scales_kernel); unscaled, the theta / z rows of dWh flushed to zero.  Cotangent here: channel 0 at
+    O(1), every other channel at 1e-8: each row block of dWh must keep its relative accuracy."""
+    B = 3
+    ops, enc, y, nz, s, wh, bh, add, t = _encoder_inputs(cfg, B)
+    bank = ops.filter_bank_fwd(s, t(enc.conv1_w))
+    x1, h, heads, _ = ops.encoder_fwd(s, t(y), bank, t(enc.conv1_b), t(enc.conv2_w).view(cfg.O, cfg.O), t(enc.conv2_b), wh, bh, add)
+    torch.cuda.synchronize()
+    ref_heads = _oracle_heads(cfg, enc, y)
+    g = torch.Generator().manual_seed(4)
+    D = torch.randn(ref_heads.shape, generator=g, dtype=torch.float64)
+    D[:, 1:] *= 1e-8
+    d = cfg.Hout
+    to_ref = lambda a: a.cpu().double().view(B, cfg.G, d, d, cfg.O).permute(0, 4, 1, 2, 3)
+    with ForcedActivations([to_ref(x1), to_ref(h)]):
+        forced_heads = _oracle_heads(cfg, enc, y)
+    (forced_heads * D).sum().backward()
+    dbank, dw2, db2, dwh, dbh = ops.encoder_bwd(s, t(y), t(enc.conv2_w).view(cfg.O, cfg.O), wh, x1, h, D.float().to(DEV))
+    torch.cuda.synchronize()
+    errs = {"conv_a.weight": rel_err(dwh[0].cpu(), enc.conv_a_w.grad.view(-1)),
+            "conv_r.weight": rel_err(dwh[1:3].cpu(), enc.conv_r_w.grad.view(2, -1)),
+            "conv_z.weight": rel_err(dwh[3:].cpu(), enc.conv_z_w.grad.view(-1, cfg.O)),
+            "conv_z.bias": rel_err(dbh[3:].cpu(), enc.conv_z_b.grad.view(-1))}
+    print(f"{cfg.name}: wide-range head gradients, rel errs {errs}")
+    for k, v in errs.items():
+        assert v < 5e-3, (k, v)
+
+
 def _enc_out_from_heads(heads, cfg, gumbel, dt):
     B = heads.shape[0]
     d = cfg.Hout

@@ -14,6 +14,9 @@ from tvae_b200.config import PRESETS
 
 cfg = PRESETS[sys.argv[1]]
 B, S = int(sys.argv[2]), int(sys.argv[3])
+for kv in sys.argv[4:]:                      # overrides, e.g. ctf=0 z=2
+    k, v = kv.split("=")
+    cfg = cfg.with_(**{k: type(getattr(cfg, k))(int(v))})
 ctx = bench.Ctx()
 wl = bench.Workload(ctx, cfg, 4)
 dev = ctx.dev
