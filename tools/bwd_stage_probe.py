@@ -44,11 +44,11 @@ _ga = ops.gaussian
 
 def gaussian(y_hat, *a, **k):
     out = _ga(y_hat, *a, **k)
+    per_image = cfg.n * cfg.n * cfg.n_out
     if out[1] is not None:                       # the backward call: d_yhat
-        rec.setdefault("d_yhat", []).append(out[1].detach().reshape(-1, y_hat.numel() // (y_hat.numel() // (cfg.n * cfg.n * cfg.n_out))).clone()
-                                              if False else out[1].detach().reshape(-1, cfg.n * cfg.n * cfg.n_out).clone())
+        rec.setdefault("d_yhat", []).append(out[1].detach().reshape(-1, per_image).clone())
     else:
-        rec.setdefault("y_hat", []).append(y_hat.detach().reshape(-1, cfg.n * cfg.n * cfg.n_out).clone())
+        rec.setdefault("y_hat", []).append(y_hat.detach().reshape(-1, per_image).clone())
     return out
 
 
