@@ -98,3 +98,27 @@ def test_fit_noise_combinations_the_reference_cannot_run_are_refused():
         E.eval_minibatch_particles(x, y, ctf, gen, enc, "attention", "attention+offsets", 0, "cpu", cfg.theta_prior, cfg.G, cfg.p, 0)
     with pytest.raises(NotImplementedError, match="fit-noise"):
         E.eval_minibatch_particles(x, y, None, gen, enc, "attention", "attention+offsets", 0, "cpu", cfg.theta_prior, cfg.G, cfg.p, 4)
+
+
+def test_graphed_step_host_contract():
+    """tvae_b200.graph.GraphedStep (one CUDA graph per minibatch): no CPU fallback, a GradSync with a fused optimiser is refused
+    (its Adam step count is a host scalar), train_epoch exposes graph=; the header declares the one-bit mask buffer."""
+    import inspect
+    import os
+    from tvae_b200 import train
+    from tvae_b200.graph import GraphedStep
+    _, cfg, _, _ = load_golden("g1_mnist")
+    gen, enc = build(cfg)
+    x = torch.from_numpy(synth.image_coords(cfg.n))
+    with pytest.raises(RuntimeError):
+        GraphedStep(x, (2, cfg.C, cfg.n, cfg.n), gen, enc, "attention", "attention+offsets", "cpu", cfg.theta_prior, cfg.G, cfg.n)
+
+    class FusedSync:
+        optimizer = object()
+    with pytest.raises((ValueError, RuntimeError, AssertionError)):
+        GraphedStep(x, (2, cfg.C, cfg.n, cfg.n), gen, enc, "attention", "attention+offsets", "cuda", cfg.theta_prior, cfg.G, cfg.n,
+                    sync=FusedSync())
+    assert "graph" in inspect.signature(train.train_epoch).parameters
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "tvae_b200.h")).read()
+    assert "mask_bits" in header
+    assert [n for n, _ in ops.GenFwdArgs._fields_][-1] == "mask_bits"
